@@ -1,0 +1,258 @@
+#!/usr/bin/env python
+"""bench.py -- RK4 cell-steps/s of the fused tendency+RK4 path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME] [--dtype f64|f32]
+
+A "step" is one RungeKutta4 step (four fused stage kernels) over the whole mesh.  Workloads
+(BASELINE.json configs): igw2048 = configs[2] (single-B200 roofline run, the N=1 default),
+igw4096 = configs[3] (N>1 default), igw512 = configs[1], igw64 = configs[0].
+Inputs (2.5 GB of mesh + state at 2048x2048) are far larger than the 126 MB L2, so no flush is needed.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "mpas-ocean.jl_b200"))
+
+WORKLOADS = {"igw64": 64, "igw512": 512, "igw1024": 1024, "igw2048": 2048, "igw4096": 4096}
+# algorithmic bytes per cell per RK4 step on a planar hex mesh (SURVEY.md 8d / BASELINE.md section 3)
+ALGO_BYTES_PER_CELL_STEP = {"f64": 2400.0, "f32": 1536.0}
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": reasons}
+
+
+def build_case(nx: int, dtype: str):
+    import moka_b200 as mb
+    t0 = time.time()
+    m = mb.periodic_hex(nx, nx, 1.0e7 / nx, with_dual=False)
+    ssh, u, h = mb.inertialGravityWave(m).initial_state()
+    return m, (ssh, u, h), mb.cfl_dt(m["dc"]), time.time() - t0
+
+
+def run_b200(args):
+    import moka_b200 as mb
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        from moka_b200 import multi_gpu
+        return multi_gpu.bench_main(args, rank, world, local)
+
+    nx = WORKLOADS[args.workload]
+    npdt = np.float64 if args.dtype == "f64" else np.float32
+    m, (ssh, u, h), dt, t_gen = build_case(nx, args.dtype)
+    nC, nE = m["nCells"], m["nEdges"]
+    backend = mb.B200(local)
+    t0 = time.time()
+    mesh = mb.Mesh(m, backend)
+    t_mesh = time.time() - t0
+    prog = mb.PrognosticVars(ssh.astype(npdt), u.astype(npdt), h.astype(npdt), 2, mesh)
+    diag, tend = mb.DiagnosticVars(prog), mb.TendencyVars(prog)
+    K, W = args.steps, max(args.warmup, 3)
+
+    # ---- device-resident throughput (inputs already in HBM) -----------------------------------------
+    mb.ocn_run_loop(dt, prog, diag, tend, None, mb.RungeKutta4, W)
+    backend.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    l0 = backend.launch_count()
+    backend.timer_start()
+    mb.ocn_timestep(dt, prog, diag, tend, None, mb.RungeKutta4, nsteps=K)
+    ms = backend.timer_stop()
+    launches_total = backend.launch_count() - l0
+    stage_launches = 4 * K                                  # + 2 ssh refresh kernels at the end of the call
+    # keep the GPU under the same load while nvidia-smi gets its samples (not part of the number)
+    t_end = time.time() + (0.0 if args.quick else 1.0)
+    while time.time() < t_end:
+        mb.ocn_timestep(dt, prog, diag, tend, None, mb.RungeKutta4, nsteps=10)
+        backend.synchronize()
+    clocks = sampler.stop()
+    value = nC * K / (ms * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers ----------------------------------------------
+    hu, hh = backend.pinned(nE, npdt), backend.pinned(nC, npdt)
+    hout = backend.pinned(nC, npdt)
+    hu[:], hh[:] = u.astype(npdt), h.astype(npdt)
+    from moka_b200 import _lib as L
+    def e2e_step():
+        prog.dev.set(L.NORMAL_VELOCITY, hu)
+        prog.dev.set(L.LAYER_THICKNESS, hh)
+        mb.ocn_timestep(dt, prog, diag, tend, None, mb.RungeKutta4, nsteps=1)
+        prog.dev.get(L.SSH, hout)
+    for _ in range(0 if args.quick else 2):
+        e2e_step()
+    backend.synchronize()
+    Ke = 1 if args.quick else max(3, min(K, 20))
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        e2e_step()
+    backend.synchronize()
+    e2e_s = (time.perf_counter() - t0) / Ke
+    item = np.dtype(npdt).itemsize
+
+    # ---- roofline of the dominant kernel (k_rk_stage) -----------------------------------------------------------
+    peak, peak_src = measured_peak_gbs()
+    algo_bytes_per_launch = ALGO_BYTES_PER_CELL_STEP[args.dtype] / 4.0 * nC
+    avg_launch_s = (ms * 1e-3) / stage_launches
+    achieved = algo_bytes_per_launch / avg_launch_s / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(f"{args.workload}_{args.dtype}")
+    except Exception:
+        pass
+
+    out = {
+        "metric": "RK4 cell-steps/sec", "value": value, "unit": "cell-steps/s", "n_gpus": 1, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": f"inertial gravity wave, {nx}x{nx} periodic planar hex mesh ({nC} cells, {nE} edges), "
+                               f"{'Float64' if args.dtype == 'f64' else 'Float32'} RK4, dt={dt:.4g}s",
+                   "name": args.workload, "l2": "inputs larger than L2 (no flush)" if nx >= 1024 else "fits in L2",
+                   "mesh_gen_s": round(t_gen, 2), "mesh_upload_s": round(t_mesh, 2)},
+        "clocks": clocks,
+        "e2e": {"value": nC / e2e_s, "unit": "cell-steps/s", "h2d_bytes_per_step": int((nE + nC) * item),
+                "d2h_bytes_per_step": int(nC * item), "ms_per_step": e2e_s * 1e3},
+        "gpu_launches": int(launches_total),
+        "roofline": {"bound": "hbm", "kernel": "k_rk_stage", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": algo_bytes_per_launch, "avg_launch_ms": avg_launch_s * 1e3},
+    }
+    if not args.no_cpu:
+        out["cpu_baseline"] = cpu_baseline(m, (ssh, u, h), dt, budget_s=args.cpu_budget)
+    print(json.dumps(out))
+
+
+def cpu_baseline(m, state, dt, budget_s=15.0):
+    """The C/OpenMP restatement of the reference path (oracle/), timed on this box's host cores on a
+    bounded sample: RK4 steps on the same mesh until ~budget_s of CPU work."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import moka_oracle_c as OC
+    ssh, u, h = state
+    om = OC.OracleModel(m, ssh, u, h)
+    om.run_loop(dt, 1, "RungeKutta4")                       # warm-up (thread pool, page faults)
+    t0 = time.perf_counter()
+    om.run_loop(dt, 1, "RungeKutta4")
+    t1 = time.perf_counter() - t0
+    n = int(max(1, min(50, budget_s / max(t1, 1e-6))))
+    t0 = time.perf_counter()
+    om.run_loop(dt, n, "RungeKutta4")
+    tt = time.perf_counter() - t0
+    return {"value": m["nCells"] * n / tt, "unit": "cell-steps/s", "cores": om.num_threads(), "kind": "port",
+            "sample": f"{n} RK4 steps of the same {m['nCells']}-cell mesh, C/OpenMP restatement of the reference's unfused "
+                      f"per-stage kernel sequence (no Julia in this image), {tt:.1f} s"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference is Julia and
+    Julia is not installed, so this is the oracle port (kind "port") with all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    nx = WORKLOADS[args.workload]
+    m, (ssh, u, h), dt, _ = build_case(nx, "f64")
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import moka_oracle_c as OC
+    # each "step" is a bounded sample: one RK4 step on the workload mesh (capped so the run ends in minutes)
+    om = OC.OracleModel(m, ssh, u, h)
+    K, W = args.steps, args.warmup
+    om.run_loop(dt, 1, "RungeKutta4")
+    t0 = time.perf_counter()
+    om.run_loop(dt, 1, "RungeKutta4")
+    t1 = time.perf_counter() - t0
+    K = int(max(1, min(K, 120.0 / max(t1, 1e-6))))
+    W = int(max(0, min(W, 20.0 / max(t1, 1e-6))))
+    if W:
+        om.run_loop(dt, W, "RungeKutta4")
+    t0 = time.perf_counter()
+    om.run_loop(dt, K, "RungeKutta4")
+    tt = time.perf_counter() - t0
+    v = m["nCells"] * K / tt
+    print(json.dumps({
+        "impl": "reference", "metric": "RK4 cell-steps/sec", "value": v, "unit": "cell-steps/s", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": tt / K * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"inertial gravity wave, {nx}x{nx} periodic planar hex mesh ({m['nCells']} cells), Float64 RK4",
+                   "name": args.workload},
+        "cpu_baseline": {"value": v, "unit": "cell-steps/s", "cores": om.num_threads(), "kind": "port",
+                         "sample": f"{K} RK4 steps on the full {m['nCells']}-cell mesh, C/OpenMP restatement of the "
+                                   "reference's per-stage kernel sequence (Julia absent)"},
+        "e2e": {"value": v, "unit": "cell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--quick", action="store_true", help="profiling runs: no clock-sampling load loop, one e2e step")
+    args = ap.parse_args()
+    if args.workload is None:
+        args.workload = "igw2048" if args.gpus == 1 else "igw4096"
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,177 @@
+/* moka_b200.h -- C ABI of libmoka_b200.so: the B200 (sm_100a) implementation of MPAS-Ocean.jl's
+ * ("MOKA") forward-model hot path: tendency evaluation + ForwardEuler / RungeKutta4 stepping on the
+ * MPAS Voronoi C-grid.
+ *
+ * The reference has no FFI: its seam is Julia multiple dispatch on a `backend` value threaded through
+ * the constructors and entry points listed below.  Each function here names the
+ * reference interface it stands behind (paths relative to the reference repository).  A Julia `B200`
+ * architecture type forwards those entry points here with `ccall`; in this repository
+ * the same ABI is driven from Python ctypes (mpas-ocean.jl_b200/moka_b200/).
+ *
+ * Conventions
+ *  - plain C: opaque handles, plain pointers and sizes, no C++/torch types.
+ *  - every function returns 0 on success, non-zero on error; mokab_last_error() gives the message
+ *    (the reference raises `error(msg)`: src/Architectures.jl:23,31,39).  No exceptions cross the ABI.
+ *  - host arrays are in the REFERENCE layout and numbering: column-major (slot, entity), Int32 1-based
+ *    connectivity with 0 = absent, exactly what ReadHorzMesh returns (src/infra/MPASMesh/HorzMesh.jl:
+ *    166-290).  The library renumbers cells/edges/vertices for locality internally; mokab_state_set/get
+ *    always speak the caller's numbering.
+ *  - the caller owns host memory (copied during the call, never retained); the library owns device
+ *    memory behind handles.  A context is bound to one device; calls on one context must be serialised
+ *    by the caller (the reference drives from a single task: src/forward/run_loop.jl:8-22).
+ *  - there is no CPU fallback: every entry point needs a CUDA device and fails loudly without one.
+ */
+#ifndef MOKA_B200_H
+#define MOKA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOKAB_VERSION 100
+
+typedef struct mokab_ctx   mokab_ctx;
+typedef struct mokab_mesh  mokab_mesh;
+typedef struct mokab_state mokab_state;
+
+/* element type of a state (reference: Float64 hard-coded, src/ocn/PrognosticVars.jl:91-93) */
+enum { MOKAB_F64 = 0, MOKAB_F32 = 1 };
+
+/* fields addressable with mokab_state_set / mokab_state_get */
+enum {
+    MOKAB_SSH = 0,                 /* Prog.ssh[end]            (nCells)    PrognosticVars.jl:6-18 */
+    MOKAB_NORMAL_VELOCITY = 1,     /* Prog.normalVelocity[end] (nEdges)                            */
+    MOKAB_LAYER_THICKNESS = 2,     /* Prog.layerThickness[end] (nCells)                            */
+    MOKAB_SSH_PREV = 3,            /* Prog.ssh[1]              time level "previous"               */
+    MOKAB_NORMAL_VELOCITY_PREV = 4,
+    MOKAB_LAYER_THICKNESS_PREV = 5,
+    MOKAB_LAYER_THICKNESS_EDGE = 6, /* Diag.layerThicknessEdge (nEdges)    DiagnosticVars.jl:6-73  */
+    MOKAB_THICKNESS_FLUX = 7,       /* Diag.thicknessFlux      (nEdges)                            */
+    MOKAB_VELOCITY_DIV_CELL = 8,    /* Diag.velocityDivCell    (nCells)                            */
+    MOKAB_RELATIVE_VORTICITY = 9,   /* Diag.relativeVorticity  (nVertices)                         */
+    MOKAB_TEND_NORMAL_VELOCITY = 10,/* Tend.tendNormalVelocity (nEdges)    TendencyVars.jl:7-49    */
+    MOKAB_TEND_LAYER_THICKNESS = 11 /* Tend.tendLayerThickness (nCells)                            */
+};
+
+/* reductions (replaces the serial sumArray kernel, src/forward/run_loop.jl:47-51) */
+enum {
+    MOKAB_SUM_SSH2 = 0,   /* sum_c ssh[c]^2                          (what sumArray computes)        */
+    MOKAB_SUM_MASS = 1,   /* sum_c areaCell[c] * layerThickness[c]                                   */
+    MOKAB_SUM_ENERGY = 2  /* sum_c area*(g*ssh^2/2) + sum_e (dc*dv/2)*hEdge*u^2/2  (kinetic+potential) */
+};
+
+/* entity kinds for mokab_mesh_get_perm */
+enum { MOKAB_CELLS = 0, MOKAB_EDGES = 1, MOKAB_VERTICES = 2 };
+
+/* RungeKutta4 implementations */
+enum {
+    MOKAB_RK4_FUSED = 0,    /* one fused tendency+update kernel per stage, CUDA-graph resident loop      */
+    MOKAB_RK4_UNFUSED = 1   /* the reference's per-stage kernel sequence, reference operation order      */
+};
+
+/* mesh_create flags */
+enum {
+    MOKAB_MESH_RENUMBER = 1u  /* locality renumbering (space-filling curve); 0 keeps the caller's order */
+};
+
+/* Host view of the reference mesh structs.  Pointers marked (opt) may be NULL.
+ *   Edges          src/infra/MPASMesh/HorzMesh.jl:64-95
+ *   PrimaryCells   src/infra/MPASMesh/HorzMesh.jl:102-132
+ *   DualCells      src/infra/MPASMesh/HorzMesh.jl:135-162
+ *   VerticalMesh   src/infra/MPASMesh/VertMesh.jl:3-17 (single stacked layer: nVertLevels == 1)      */
+typedef struct mokab_mesh_desc {
+    int64_t nCells, nEdges, nVertices;          /* nVertices may be 0: no curl diagnostic           */
+    int64_t maxEdges, maxEdges2, vertexDegree;
+    /* Edges */
+    const int32_t *cellsOnEdge;      /* (2, nEdges)                                                  */
+    const int32_t *verticesOnEdge;   /* (2, nEdges)            (opt; needed to derive edgeSignOnVertex) */
+    const int32_t *edgesOnEdge;      /* (maxEdges2, nEdges)                                          */
+    const int32_t *nEdgesOnEdge;     /* (nEdges)                                                     */
+    const double  *weightsOnEdge;    /* (maxEdges2, nEdges)                                          */
+    const double  *dcEdge, *dvEdge;  /* (nEdges)                                                     */
+    const double  *fEdge;            /* (nEdges)               (opt: zeros, HorzMesh.jl:257-262)     */
+    const double  *xEdge, *yEdge, *zEdge; /* (opt; unused by the kernels)                            */
+    /* PrimaryCells */
+    const int32_t *edgesOnCell;      /* (maxEdges, nCells)                                           */
+    const int32_t *nEdgesOnCell;     /* (nCells)                                                     */
+    const int32_t *edgeSignOnCell;   /* (maxEdges, nCells)     (opt: derived as HorzMesh.jl:292-311) */
+    const double  *areaCell;         /* (nCells)                                                     */
+    const double  *xCell, *yCell, *zCell; /* (opt; drive the locality renumbering)                   */
+    /* DualCells */
+    const int32_t *edgesOnVertex;    /* (vertexDegree, nVertices) (opt if nVertices == 0)            */
+    const int32_t *edgeSignOnVertex; /* (maxEdges, nVertices)  (opt: derived as HorzMesh.jl:313-332) */
+    const double  *areaTriangle;     /* (nVertices)                                                  */
+    /* VerticalMesh */
+    const double  *restingThicknessSum; /* (nCells)            VertMesh.jl:73                        */
+    /* masks (legacy glossary src/infra/Mesh.jl:110-114; project-defined for non-periodic meshes)    */
+    const int32_t *boundaryEdge;     /* (nEdges) (opt) 1 = solid-wall edge: u = tendU = 0            */
+} mokab_mesh_desc;
+
+/* ---- context: Architectures.jl backend object ------------------------------------------------ */
+/* `B200()` architecture instance on CUDA device `device` (src/Architectures.jl:12; the reference
+ * picks its backend at src/driver/mpas_ocean.jl:28). */
+int  mokab_init(int device, mokab_ctx **out);
+int  mokab_finalize(mokab_ctx *ctx);
+/* KA.synchronize(backend) (e.g. src/ocn/Tendencies/normalVelocity/pressure_gradient.jl:39) */
+int  mokab_synchronize(mokab_ctx *ctx);
+/* Use a caller-owned cudaStream_t for all work of this context (NULL restores the library's own). */
+int  mokab_set_stream(mokab_ctx *ctx, void *cuda_stream);
+/* CUDA-event stopwatch on the context's stream (milliseconds between start and stop). */
+int  mokab_timer_start(mokab_ctx *ctx);
+int  mokab_timer_stop(mokab_ctx *ctx, double *elapsed_ms);
+/* number of kernels this context has launched (graph replays count their kernel nodes) */
+int  mokab_launch_count(mokab_ctx *ctx, int64_t *out);
+/* page-locked host memory for state_set/get staging (Adapt.adapt source/target buffers) */
+int  mokab_host_alloc(void **out, int64_t bytes);
+int  mokab_host_free(void *p);
+const char *mokab_last_error(void);
+int  mokab_version(void);
+
+/* ---- mesh: ReadHorzMesh + VerticalMesh + Adapt.adapt_structure(backend, mesh) ---------------- */
+/* Upload a mesh (HorzMesh.jl:334-355 does the sign fields + H2D copy; VertMesh.jl:46-82). */
+int  mokab_mesh_create(mokab_ctx *ctx, const mokab_mesh_desc *desc, uint32_t flags, mokab_mesh **out);
+int  mokab_mesh_destroy(mokab_mesh *mesh);
+/* perm[new] = old (0-based) for MOKAB_CELLS / MOKAB_EDGES / MOKAB_VERTICES */
+int  mokab_mesh_get_perm(const mokab_mesh *mesh, int kind, int32_t *perm_out);
+int  mokab_mesh_device_bytes(const mokab_mesh *mesh, int64_t *out);
+
+/* ---- state: PrognosticVars + DiagnosticVars + TendencyVars on the backend ------------------- */
+/* Zero-initialised (DiagnosticVars.jl:90-93, TendencyVars.jl:61-62); two time levels. */
+int  mokab_state_create(mokab_ctx *ctx, const mokab_mesh *mesh, int dtype, mokab_state **out);
+int  mokab_state_destroy(mokab_state *state);
+/* Host arrays hold the state's dtype, caller numbering.  Setting MOKAB_LAYER_THICKNESS does NOT touch
+ * ssh (the reference reads both from file, PrognosticVars.jl:85-99).  `set` of a time-level-`end`
+ * prognostic field also fills the "previous" level, like the deepcopy at PrognosticVars.jl:49-53. */
+int  mokab_state_set(mokab_state *state, int field, const void *host);
+int  mokab_state_get(mokab_state *state, int field, void *host);
+
+/* ---- src/ocn entry points (operator level; reference operation order, Float64 bit-faithful) --- */
+/* diagnostic_compute!(Mesh, Diag, Prog)                      src/ocn/DiagnosticVars.jl:108-117     */
+int  mokab_diagnostic_compute(mokab_state *state);
+/* computeNormalVelocityTendency!(Tend, Prog, Diag, Mesh, Config)   .../normalVelocity.jl:21-53     */
+int  mokab_compute_normal_velocity_tendency(mokab_state *state);
+/* computeLayerThicknessTendency!(Tend, Prog, Diag, Mesh, Config)   .../layerThickness.jl:14-28     */
+int  mokab_compute_layer_thickness_tendency(mokab_state *state);
+/* Stand-alone operators on host Float64 arrays (src/ocn/Operators.jl:46-74, 102-120, 151-177, 179-199) */
+int  mokab_gradient_on_edge(mokab_ctx *ctx, const mokab_mesh *mesh, const double *scalar_cell, double *grad_edge);
+int  mokab_divergence_on_cell(mokab_ctx *ctx, const mokab_mesh *mesh, const double *vec_edge, double *div_cell);
+int  mokab_curl_on_vertex(mokab_ctx *ctx, const mokab_mesh *mesh, const double *vec_edge, double *curl_vertex_inout);
+int  mokab_interpolate_cell2edge(mokab_ctx *ctx, const mokab_mesh *mesh, const double *cell_value, double *edge_value);
+
+/* ---- src/forward entry points ------------------------------------------------------------------ */
+/* ocn_run_loop + ocn_timestep(::ForwardEuler): `nsteps` steps of src/forward/time_integration.jl:
+ * 150-193 in the reference's order (lagged hEdge, scratch aliasing, accumulating vorticity). */
+int  mokab_timestep_forward_euler(mokab_state *state, double dt, int64_t nsteps);
+/* ocn_run_loop + ocn_timestep(::RungeKutta4) as intended by time_integration.jl:61-148; `impl` is
+ * MOKAB_RK4_FUSED or MOKAB_RK4_UNFUSED.  On return Prog.*[end] is the new state, Prog.*[1] the state
+ * one step earlier, ssh = layerThickness - restingThicknessSum. */
+int  mokab_timestep_rk4(mokab_state *state, double dt, int64_t nsteps, int impl);
+/* sumArray replacement (deterministic two-level reduction); result always Float64. */
+int  mokab_reduce(mokab_state *state, int which, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOKA_B200_H */

@@ -1,0 +1,145 @@
+// common.cuh -- context, error plumbing, device buffers and small load/store helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/moka_b200.h"
+
+namespace mokab {
+
+extern thread_local std::string g_last_error;
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+#define MOKAB_CUDA(expr)                                                                     \
+    do {                                                                                     \
+        cudaError_t e__ = (expr);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            throw ::mokab::Error(std::string(#expr) + " failed: " + cudaGetErrorString(e__) + \
+                                 " (" __FILE__ ":" + std::to_string(__LINE__) + ")");        \
+    } while (0)
+
+#define MOKAB_REQUIRE(cond, msg)                       \
+    do {                                               \
+        if (!(cond)) throw ::mokab::Error(std::string(msg)); \
+    } while (0)
+
+// Run `body`, translate exceptions to the C convention (non-zero + thread-local message).
+template <class F>
+static inline int guarded(F &&body) noexcept
+{
+    try {
+        body();
+        return 0;
+    } catch (const std::exception &ex) {
+        g_last_error = ex.what();
+        return 1;
+    } catch (...) {
+        g_last_error = "unknown error";
+        return 2;
+    }
+}
+
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    void alloc(size_t count)
+    {
+        release();
+        n = count;
+        if (count) MOKAB_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    }
+    void upload(const std::vector<T> &h, cudaStream_t s)
+    {
+        alloc(h.size());
+        if (n) MOKAB_CUDA(cudaMemcpyAsync(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    void zero(cudaStream_t s)
+    {
+        if (n) MOKAB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+    }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+}  // namespace mokab
+
+struct mokab_ctx {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;  // the stream in use (own or caller's)
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int64_t launches = 0;
+    void bind() const { MOKAB_CUDA(cudaSetDevice(device)); }
+};
+
+namespace mokab {
+
+// ---- device helpers -----------------------------------------------------------------------------
+// Streaming (read-once) loads: keep them out of L1 so the gathered state stays resident there.
+template <class T>
+__device__ __forceinline__ T ld_stream(const T *p);
+template <>
+__device__ __forceinline__ int ld_stream<int>(const int *p)
+{
+    int v;
+    asm("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+template <>
+__device__ __forceinline__ unsigned short ld_stream<unsigned short>(const unsigned short *p)
+{
+    unsigned short v;
+    asm("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p));
+    return v;
+}
+template <>
+__device__ __forceinline__ unsigned char ld_stream<unsigned char>(const unsigned char *p)
+{
+    unsigned int v;
+    asm("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return (unsigned char)v;
+}
+template <>
+__device__ __forceinline__ int2 ld_stream<int2>(const int2 *p)
+{
+    int2 v;
+    asm("ld.global.nc.L1::no_allocate.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+template <>
+__device__ __forceinline__ double ld_stream<double>(const double *p)
+{
+    double v;
+    asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+template <>
+__device__ __forceinline__ float ld_stream<float>(const float *p)
+{
+    float v;
+    asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+}  // namespace mokab

@@ -1,0 +1,240 @@
+// kernels_fused.cuh -- the fused RungeKutta4 stage: tendencies + provisional state + accumulator in
+// one pass over the mesh (the reference's intent at src/forward/time_integration.jl:112-137, which as
+// written would be ~12 launches and 5 extra array round trips per stage).
+//
+// Per stage s, for every edge e and cell c (provisional state "old" = output of stage s-1):
+//   kU[e] = -(g/dc[e]) * ((hOld[c2]-H[c2]) - (hOld[c1]-H[c1])) + sum_i wf[i,e] * uOld[eoe[i,e]]
+//           (pressure_gradient.jl:63 and horizontal_advection_and_coriolis.jl:70-72, with
+//            wf = weightsOnEdge * fEdge[eoe] folded at upload)
+//   kH[c] = invArea[c] * sum_i sign[i,c] * dv[e_i] * uOld[e_i] * (hOld[c1(e_i)] + hOld[c2(e_i)])/2
+//           (horizontal_advection.jl:64-65 with flux = u*hEdge, DiagnosticVars.jl:158-173, and
+//            hEdge = interpolateCell2Edge of the SAME provisional state, Operators.jl:201-222)
+//   stage 1:   out = cur + a*k ; acc  = cur + b*k        (acc never read)
+//   stage 2,3: out = cur + a*k ; acc += b*k
+//   stage 4:                      acc += b*k             (acc is the other time level: no copy-back)
+// Neither tend*, thicknessFlux, layerThicknessEdge nor ssh ever touch HBM.
+//
+// v1 data path: static connectivity / weights are slot-major and streamed with L1::no_allocate loads
+// (read once per stage), the provisional state is gathered through L1/L2 -- after the Hilbert
+// renumbering the 10+2 gathers of an edge and the 6x3 gathers of a cell land in lines its
+// neighbours in the warp also touch.  A block owns TC consecutive cells and the edges they own,
+// so the two halves of the block share their working set in L1.
+#pragma once
+#include "common.cuh"
+
+namespace mokab {
+namespace fused {
+
+constexpr int kTC = 256;       // cells per block
+constexpr int kThreads = 256;
+
+template <class R>
+struct StageArgs {
+    int nE, nC;
+    // static (see mesh.cuh)
+    const int2 *ce;
+    const int32_t *eoe;      // (S2, nE) absent -> self
+    const int32_t *eoc;      // (S, nC)  (edge << 1) | (sign > 0)
+    const uint8_t *nEoE, *nEoC;
+    const int32_t *blkEdgeStart;
+    const R *gdc, *wf, *dv, *invArea, *H;
+    // dynamic
+    const R *uOld, *hOld;    // provisional state the tendencies are evaluated at
+    const R *uCur, *hCur;    // state at the start of the step
+    R *uAcc, *hAcc;          // accumulator == the other time level
+    R *uOut, *hOut;          // next provisional state (stages 1-3)
+    R a, b;
+};
+
+// STAGE: 1 = first, 2 = middle (2 and 3), 4 = last.  S2/S: compile-time maxEdges2/maxEdges (0 = runtime).
+template <class R, int STAGE, int S2T, int ST>
+__global__ void __launch_bounds__(kThreads)
+k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
+{
+    const int S2 = S2T ? S2T : S2rt;
+    const int S = ST ? ST : Srt;
+    const int nE = A.nE, nC = A.nC;
+    const int b = blockIdx.x;
+
+    // ---- edges owned by this block's cells ----------------------------------------------------------
+    const int e0 = A.blkEdgeStart[b], e1 = A.blkEdgeStart[b + 1];
+    for (int e = e0 + threadIdx.x; e < e1; e += kThreads) {
+        const int2 c = ld_stream(A.ce + e);
+        const int n = ld_stream(A.nEoE + e);
+        int idx[S2T ? S2T : 1];
+        R w[S2T ? S2T : 1];
+        R k;
+        if constexpr (S2T != 0) {
+#pragma unroll
+            for (int i = 0; i < S2T; ++i) {
+                idx[i] = i < n ? ld_stream(A.eoe + (size_t)i * nE + e) : e;
+                w[i] = i < n ? ld_stream(A.wf + (size_t)i * nE + e) : R(0);
+            }
+        }
+        const R h1 = __ldg(A.hOld + c.x), h2 = __ldg(A.hOld + c.y);
+        const R H1 = __ldg(A.H + c.x), H2 = __ldg(A.H + c.y);
+        R cor = R(0);
+        if constexpr (S2T != 0) {
+            R uu[S2T ? S2T : 1];
+#pragma unroll
+            for (int i = 0; i < S2T; ++i) uu[i] = __ldg(A.uOld + idx[i]);
+#pragma unroll
+            for (int i = 0; i < S2T; ++i) cor += w[i] * uu[i];
+        } else {
+            for (int i = 0; i < n; ++i)
+                cor += ld_stream(A.wf + (size_t)i * nE + e) * __ldg(A.uOld + ld_stream(A.eoe + (size_t)i * nE + e));
+        }
+        k = cor - ld_stream(A.gdc + e) * ((h2 - H2) - (h1 - H1));
+        const R cur = (STAGE == 4) ? R(0) : A.uCur[e];
+        if (STAGE != 4) A.uOut[e] = cur + A.a * k;
+        if (STAGE == 1) A.uAcc[e] = cur + A.b * k;
+        else            A.uAcc[e] = A.uAcc[e] + A.b * k;
+    }
+
+    // ---- cells of this block ----------------------------------------------------------------------------
+    const int cc = b * kTC + threadIdx.x;
+    if (cc < nC) {
+        const int n = ld_stream(A.nEoC + cc);
+        const R hc = __ldg(A.hOld + cc);
+        R acc = R(0);
+        if constexpr (ST != 0) {
+            int ee[ST ? ST : 1];
+#pragma unroll
+            for (int i = 0; i < ST; ++i) ee[i] = i < n ? ld_stream(A.eoc + (size_t)i * nC + cc) : -1;
+            int2 cs[ST ? ST : 1];
+            R uu[ST ? ST : 1], dd[ST ? ST : 1];
+#pragma unroll
+            for (int i = 0; i < ST; ++i) {
+                const int e = ee[i] >= 0 ? (ee[i] >> 1) : 0;
+                cs[i] = __ldg(A.ce + e);
+                uu[i] = __ldg(A.uOld + e);
+                dd[i] = __ldg(A.dv + e);
+            }
+#pragma unroll
+            for (int i = 0; i < ST; ++i) {
+                const int other = cs[i].x == cc ? cs[i].y : cs[i].x;
+                const R ho = __ldg(A.hOld + other);
+                const R f = dd[i] * uu[i] * (R(0.5) * (hc + ho));
+                if (ee[i] >= 0) acc += (ee[i] & 1) ? f : -f;
+            }
+        } else {
+            for (int i = 0; i < n; ++i) {
+                const int ex = ld_stream(A.eoc + (size_t)i * nC + cc);
+                const int e = ex >> 1;
+                const int2 cs = __ldg(A.ce + e);
+                const int other = cs.x == cc ? cs.y : cs.x;
+                const R f = __ldg(A.dv + e) * __ldg(A.uOld + e) * (R(0.5) * (hc + __ldg(A.hOld + other)));
+                acc += (ex & 1) ? f : -f;
+            }
+        }
+        const R k = acc * ld_stream(A.invArea + cc);
+        const R cur = (STAGE == 4) ? R(0) : A.hCur[cc];
+        if (STAGE != 4) A.hOut[cc] = cur + A.a * k;
+        if (STAGE == 1) A.hAcc[cc] = cur + A.b * k;
+        else            A.hAcc[cc] = A.hAcc[cc] + A.b * k;
+    }
+}
+
+// ---- construction of the fused-form arrays from the reference-form device arrays ---------------------
+template <class R>
+__global__ void __launch_bounds__(256)
+k_build_fused_edges(int nE, int S2, const double *__restrict__ dc, const double *__restrict__ dv,
+                    const double *__restrict__ fE, const int32_t *__restrict__ eoe, const double *__restrict__ woe,
+                    const uint8_t *__restrict__ nEoE, R *__restrict__ gdc, R *__restrict__ dvR, R *__restrict__ wf,
+                    int32_t *__restrict__ eoeF)
+{
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e >= nE) return;
+    gdc[e] = (R)__dmul_rn(9.80616, 1.0 / dc[e]);
+    dvR[e] = (R)dv[e];
+    const int n = nEoE[e];
+    for (int i = 0; i < S2; ++i) {
+        const size_t k = (size_t)i * nE + e;
+        const int x = i < n ? eoe[k] : -1;
+        wf[k] = x >= 0 ? (R)__dmul_rn(woe[k], fE[x]) : R(0);
+        if (eoeF) eoeF[k] = x >= 0 ? x : e;
+    }
+}
+
+template <class R>
+__global__ void __launch_bounds__(256)
+k_build_fused_cells(int nC, int S, const double *__restrict__ area, const double *__restrict__ H,
+                    const int32_t *__restrict__ eoc, const int32_t *__restrict__ sgn, const uint8_t *__restrict__ nEoC,
+                    R *__restrict__ invArea, R *__restrict__ HR, int32_t *__restrict__ eocF)
+{
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= nC) return;
+    invArea[c] = (R)(1.0 / area[c]);
+    HR[c] = (R)H[c];
+    if (!eocF) return;
+    const int n = nEoC[c];
+    for (int i = 0; i < S; ++i) {
+        const size_t k = (size_t)i * nC + c;
+        eocF[k] = i < n ? ((eoc[k] << 1) | (sgn[k] > 0 ? 1 : 0)) : -1;
+    }
+}
+
+}  // namespace fused
+
+// ---- deterministic reductions (replace sumArray, reference run_loop.jl:47-51) --------------------------
+namespace reduce {
+constexpr int kBlocks = 1024, kThreads = 256;
+
+__device__ __forceinline__ double block_sum(double v)
+{
+    __shared__ double sm[kThreads / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    v = threadIdx.x < kThreads / 32 ? sm[threadIdx.x] : 0.0;
+    if (threadIdx.x < 32) {
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    }
+    return v;  // valid in thread 0
+}
+
+// which: 0 sum ssh^2 ; 1 sum area*h ; 2 potential energy sum area*g/2*ssh^2
+template <class R>
+__global__ void __launch_bounds__(kThreads)
+k_cells(int which, int64_t nC, const R *__restrict__ h, const R *__restrict__ H, const double *__restrict__ area,
+        double *__restrict__ partial)
+{
+    double s = 0.0;
+    for (int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x; c < nC; c += (int64_t)kBlocks * kThreads) {
+        const double ssh = (double)(h[c] - H[c]);
+        if (which == 0) s += ssh * ssh;
+        else if (which == 1) s += area[c] * (double)h[c];
+        else s += area[c] * (0.5 * 9.80616) * ssh * ssh;
+    }
+    s = block_sum(s);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+// kinetic energy sum_e (dc*dv/2) * hEdge * u^2
+template <class R>
+__global__ void __launch_bounds__(kThreads)
+k_edges_ke(int64_t nE, const int2 *__restrict__ ce, const double *__restrict__ dc, const double *__restrict__ dv,
+           const R *__restrict__ u, const R *__restrict__ h, double *__restrict__ partial)
+{
+    double s = 0.0;
+    for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < nE; e += (int64_t)kBlocks * kThreads) {
+        const int2 c = ce[e];
+        const double he = 0.5 * ((double)h[c.x] + (double)h[c.y]), ue = (double)u[e];
+        s += 0.5 * dc[e] * dv[e] * he * ue * ue;
+    }
+    s = block_sum(s);
+    if (threadIdx.x == 0) partial[blockIdx.x] += s;
+}
+
+__global__ void __launch_bounds__(kThreads) k_final(const double *__restrict__ partial, double *__restrict__ out)
+{
+    double s = 0.0;
+    for (int i = threadIdx.x; i < kBlocks; i += kThreads) s += partial[i];
+    s = block_sum(s);
+    if (threadIdx.x == 0) out[0] = s;
+}
+}  // namespace reduce
+
+}  // namespace mokab

@@ -1,0 +1,265 @@
+// mesh.cuh -- host-side mesh preparation (validation, sign fields, locality renumbering, SoA
+// transposition) and the device-resident mesh.
+//
+// Stands behind ReadHorzMesh / signIndexField! / Adapt.adapt_structure(backend, mesh)
+// (reference src/infra/MPASMesh/HorzMesh.jl:292-355) and VerticalMesh (VertMesh.jl:46-82).
+//
+// Device layout (all 0-based, renumbered):
+//   * connectivity is Int32 and slot-major ("SoA-transposed"): row i of edgesOnEdge is a contiguous
+//     array over edges, so a warp reading slot i of 32 consecutive edges reads 128 contiguous bytes.
+//   * cells follow a Hilbert curve over (xCell, yCell) (Morton over x,y,z when z varies); edges are
+//     ordered by their owner cell cellsOnEdge[1] (stable), vertices by cellsOnVertex-free rule:
+//     the smallest new edge id touching them.  Index ranges are therefore compact in space and the
+//     indirect gathers of neighbouring threads fall into the same few cache lines.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+#include "common.cuh"
+
+namespace mokab {
+
+// Hilbert index of (x, y) on a 2^order grid.
+static inline uint64_t hilbert_xy(uint32_t x, uint32_t y, int order)
+{
+    uint64_t d = 0;
+    for (uint32_t s = 1u << (order - 1); s > 0; s >>= 1) {
+        uint32_t rx = (x & s) ? 1 : 0, ry = (y & s) ? 1 : 0;
+        d += (uint64_t)s * s * ((3 * rx) ^ ry);
+        if (ry == 0) {
+            if (rx == 1) {
+                x = s - 1 - x;
+                y = s - 1 - y;
+            }
+            std::swap(x, y);
+        }
+    }
+    return d;
+}
+
+static inline uint64_t spread3(uint64_t v)  // 21 bits -> every third bit
+{
+    v &= 0x1fffff;
+    v = (v | v << 32) & 0x1f00000000ffffULL;
+    v = (v | v << 16) & 0x1f0000ff0000ffULL;
+    v = (v | v << 8) & 0x100f00f00f00f00fULL;
+    v = (v | v << 4) & 0x10c30c30c30c30c3ULL;
+    v = (v | v << 2) & 0x1249249249249249ULL;
+    return v;
+}
+
+// Everything the kernels need, on the host, renumbered and 0-based (-1 = absent).
+struct HostMesh {
+    int64_t nC = 0, nE = 0, nV = 0;
+    int S = 0, S2 = 0, D = 0;  // maxEdges, maxEdges2, vertexDegree
+    std::vector<int32_t> permC, permE, permV;  // perm[new] = old
+    std::vector<int32_t> ce;                   // (nE, 2) c1, c2 (c2 = c1 on masked edges)
+    std::vector<int32_t> eoe;                  // slot-major (S2, nE)
+    std::vector<double> woe;                   // slot-major (S2, nE); 0 beyond nEoE / on masked edges
+    std::vector<uint8_t> nEoE;
+    std::vector<double> dc, dv, fE;
+    std::vector<int32_t> eoc, sgnC;            // slot-major (S, nC)
+    std::vector<uint8_t> nEoC;
+    std::vector<double> area, H;
+    std::vector<int32_t> eov, sgnV;            // slot-major (D, nV)
+    std::vector<double> areaTri;
+    bool any_boundary = false;
+};
+
+static void build_host_mesh(const mokab_mesh_desc &d, uint32_t flags, HostMesh &m)
+{
+    MOKAB_REQUIRE(d.nCells > 0 && d.nEdges > 0, "mesh_create: nCells and nEdges must be positive");
+    MOKAB_REQUIRE(d.nEdges < (int64_t)1 << 30 && d.nCells < (int64_t)1 << 30, "mesh_create: mesh too large for Int32 ids");
+    MOKAB_REQUIRE(d.maxEdges > 0 && d.maxEdges <= 16 && d.maxEdges2 > 0 && d.maxEdges2 <= 32,
+                  "mesh_create: maxEdges must be in 1..16 and maxEdges2 in 1..32");
+    MOKAB_REQUIRE(d.cellsOnEdge && d.edgesOnEdge && d.nEdgesOnEdge && d.weightsOnEdge && d.dcEdge && d.dvEdge,
+                  "mesh_create: missing Edges arrays");
+    MOKAB_REQUIRE(d.edgesOnCell && d.nEdgesOnCell && d.areaCell, "mesh_create: missing PrimaryCells arrays");
+    MOKAB_REQUIRE(d.restingThicknessSum, "mesh_create: missing restingThicknessSum");
+    if (d.nVertices > 0)
+        MOKAB_REQUIRE(d.edgesOnVertex && d.areaTriangle && d.vertexDegree > 0 && d.vertexDegree <= 8 &&
+                          (d.edgeSignOnVertex || d.verticesOnEdge),
+                      "mesh_create: nVertices > 0 needs edgesOnVertex, areaTriangle and edgeSignOnVertex or verticesOnEdge");
+
+    const int64_t nC = d.nCells, nE = d.nEdges, nV = d.nVertices;
+    const int S = (int)d.maxEdges, S2 = (int)d.maxEdges2, D = nV ? (int)d.vertexDegree : 0;
+    m.nC = nC; m.nE = nE; m.nV = nV; m.S = S; m.S2 = S2; m.D = D;
+
+    // ---- validate index ranges (the reference does none; a bad index here would fault the GPU) ----
+    for (int64_t e = 0; e < nE; ++e) {
+        int32_t c1 = d.cellsOnEdge[2 * e], c2 = d.cellsOnEdge[2 * e + 1];
+        bool bnd = d.boundaryEdge && d.boundaryEdge[e];
+        MOKAB_REQUIRE(c1 >= 1 && c1 <= nC, "mesh_create: cellsOnEdge[1, e] out of range");
+        MOKAB_REQUIRE((c2 >= 1 && c2 <= nC) || (bnd && c2 == 0),
+                      "mesh_create: cellsOnEdge[2, e] out of range (0 is allowed only on boundaryEdge edges)");
+        int32_t n = d.nEdgesOnEdge[e];
+        MOKAB_REQUIRE(n >= 0 && n <= S2, "mesh_create: nEdgesOnEdge out of range");
+        for (int i = 0; i < n; ++i) {
+            int32_t x = d.edgesOnEdge[(int64_t)S2 * e + i];
+            MOKAB_REQUIRE(x >= 0 && x <= nE, "mesh_create: edgesOnEdge out of range");
+        }
+        if (bnd) m.any_boundary = true;
+    }
+    for (int64_t c = 0; c < nC; ++c) {
+        int32_t n = d.nEdgesOnCell[c];
+        MOKAB_REQUIRE(n >= 1 && n <= S, "mesh_create: nEdgesOnCell out of range");
+        for (int i = 0; i < n; ++i) {
+            int32_t x = d.edgesOnCell[(int64_t)S * c + i];
+            MOKAB_REQUIRE(x >= 1 && x <= nE, "mesh_create: edgesOnCell out of range");
+        }
+    }
+    for (int64_t v = 0; v < nV; ++v)
+        for (int j = 0; j < D; ++j) {
+            int32_t x = d.edgesOnVertex[(int64_t)D * v + j];
+            MOKAB_REQUIRE(x >= 1 && x <= nE, "mesh_create: edgesOnVertex out of range");
+        }
+
+    // ---- cell permutation: space-filling curve over the cell centres ---------------------------
+    m.permC.resize(nC);
+    std::iota(m.permC.begin(), m.permC.end(), 0);
+    if ((flags & MOKAB_MESH_RENUMBER) && d.xCell && d.yCell) {
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        const double *xyz[3] = {d.xCell, d.yCell, d.zCell};
+        for (int a = 0; a < 3; ++a) {
+            if (!xyz[a]) { lo[a] = hi[a] = 0; continue; }
+            for (int64_t c = 0; c < nC; ++c) { lo[a] = std::min(lo[a], xyz[a][c]); hi[a] = std::max(hi[a], xyz[a][c]); }
+        }
+        const bool planar = !(hi[2] > lo[2]);
+        std::vector<uint64_t> key(nC);
+        if (planar) {
+            const int order = 16;
+            const double ext = std::max(hi[0] - lo[0], hi[1] - lo[1]);
+            const double sc = ext > 0 ? (double)((1u << order) - 1) / ext : 0.0;
+#pragma omp parallel for schedule(static)
+            for (int64_t c = 0; c < nC; ++c) {
+                uint32_t qx = (uint32_t)((d.xCell[c] - lo[0]) * sc), qy = (uint32_t)((d.yCell[c] - lo[1]) * sc);
+                key[c] = hilbert_xy(qx, qy, order);
+            }
+        } else {
+            double sc[3];
+            for (int a = 0; a < 3; ++a) sc[a] = hi[a] > lo[a] ? 2097151.0 / (hi[a] - lo[a]) : 0.0;
+#pragma omp parallel for schedule(static)
+            for (int64_t c = 0; c < nC; ++c)
+                key[c] = spread3((uint64_t)((d.xCell[c] - lo[0]) * sc[0])) | spread3((uint64_t)((d.yCell[c] - lo[1]) * sc[1])) << 1 |
+                         spread3((uint64_t)((d.zCell[c] - lo[2]) * sc[2])) << 2;
+        }
+        std::stable_sort(m.permC.begin(), m.permC.end(), [&](int32_t a, int32_t b) { return key[a] < key[b]; });
+    }
+    std::vector<int32_t> invC(nC);
+    for (int64_t i = 0; i < nC; ++i) invC[m.permC[i]] = (int32_t)i;
+
+    // ---- edge permutation: counting sort by new id of the owner cell cellsOnEdge[1] (stable) --------
+    m.permE.resize(nE);
+    std::vector<int32_t> invE(nE);
+    {
+        std::vector<int64_t> start(nC + 1, 0);
+        for (int64_t e = 0; e < nE; ++e) start[invC[d.cellsOnEdge[2 * e] - 1] + 1]++;
+        for (int64_t c = 0; c < nC; ++c) start[c + 1] += start[c];
+        for (int64_t e = 0; e < nE; ++e) {
+            int64_t pos = start[invC[d.cellsOnEdge[2 * e] - 1]]++;
+            m.permE[pos] = (int32_t)e;
+        }
+        for (int64_t i = 0; i < nE; ++i) invE[m.permE[i]] = (int32_t)i;
+    }
+    // ---- vertex permutation: by the smallest new edge id on the vertex ------------------------------
+    std::vector<int32_t> invV(nV);
+    m.permV.resize(nV);
+    if (nV) {
+        std::vector<int64_t> key(nV);
+        for (int64_t v = 0; v < nV; ++v) {
+            int64_t k = INT64_MAX;
+            for (int j = 0; j < D; ++j) k = std::min<int64_t>(k, invE[d.edgesOnVertex[(int64_t)D * v + j] - 1]);
+            key[v] = k;
+        }
+        std::iota(m.permV.begin(), m.permV.end(), 0);
+        std::stable_sort(m.permV.begin(), m.permV.end(), [&](int32_t a, int32_t b) { return key[a] < key[b]; });
+        for (int64_t i = 0; i < nV; ++i) invV[m.permV[i]] = (int32_t)i;
+    }
+
+    // ---- edges -----------------------------------------------------------------------------------
+    m.ce.resize(2 * nE); m.eoe.assign((size_t)S2 * nE, -1); m.woe.assign((size_t)S2 * nE, 0.0);
+    m.nEoE.resize(nE); m.dc.resize(nE); m.dv.resize(nE); m.fE.resize(nE);
+#pragma omp parallel for schedule(static)
+    for (int64_t en = 0; en < nE; ++en) {
+        const int64_t eo = m.permE[en];
+        const bool bnd = d.boundaryEdge && d.boundaryEdge[eo];
+        int32_t c1 = d.cellsOnEdge[2 * eo], c2 = d.cellsOnEdge[2 * eo + 1];
+        m.ce[2 * en] = invC[c1 - 1];
+        m.ce[2 * en + 1] = (c2 >= 1 && !bnd) ? invC[c2 - 1] : invC[c1 - 1];  // masked: zero gradient
+        m.dc[en] = d.dcEdge[eo]; m.dv[en] = d.dvEdge[eo];
+        m.fE[en] = d.fEdge ? d.fEdge[eo] : 0.0;  // HorzMesh.jl:257-262
+        const int n = d.nEdgesOnEdge[eo];
+        m.nEoE[en] = (uint8_t)n;
+        for (int i = 0; i < n; ++i) {
+            int32_t x = d.edgesOnEdge[(int64_t)S2 * eo + i];
+            m.eoe[(size_t)i * nE + en] = x ? invE[x - 1] : -1;  // 0 entries are skipped (coriolis kernel :67)
+            m.woe[(size_t)i * nE + en] = bnd ? 0.0 : d.weightsOnEdge[(int64_t)S2 * eo + i];
+        }
+    }
+    // ---- cells (edgeSignOnCell derived as HorzMesh.jl:292-311 when not supplied) ---------------------
+    m.eoc.assign((size_t)S * nC, -1); m.sgnC.assign((size_t)S * nC, 0);
+    m.nEoC.resize(nC); m.area.resize(nC); m.H.resize(nC);
+#pragma omp parallel for schedule(static)
+    for (int64_t cn = 0; cn < nC; ++cn) {
+        const int64_t co = m.permC[cn];
+        const int n = d.nEdgesOnCell[co];
+        m.nEoC[cn] = (uint8_t)n; m.area[cn] = d.areaCell[co]; m.H[cn] = d.restingThicknessSum[co];
+        for (int i = 0; i < n; ++i) {
+            int32_t e = d.edgesOnCell[(int64_t)S * co + i];
+            m.eoc[(size_t)i * nC + cn] = invE[e - 1];
+            m.sgnC[(size_t)i * nC + cn] = d.edgeSignOnCell ? d.edgeSignOnCell[(int64_t)S * co + i]
+                                                           : ((int32_t)(co + 1) == d.cellsOnEdge[2 * (int64_t)(e - 1)] ? -1 : 1);
+        }
+    }
+    // ---- vertices (edgeSignOnVertex derived as HorzMesh.jl:313-332 when not supplied) ----------------
+    m.eov.assign((size_t)D * nV, -1); m.sgnV.assign((size_t)D * nV, 0); m.areaTri.resize(nV);
+#pragma omp parallel for schedule(static)
+    for (int64_t vn = 0; vn < nV; ++vn) {
+        const int64_t vo = m.permV[vn];
+        m.areaTri[vn] = d.areaTriangle[vo];
+        for (int j = 0; j < D; ++j) {
+            int32_t e = d.edgesOnVertex[(int64_t)D * vo + j];
+            m.eov[(size_t)j * nV + vn] = invE[e - 1];
+            m.sgnV[(size_t)j * nV + vn] = d.edgeSignOnVertex ? d.edgeSignOnVertex[(int64_t)d.maxEdges * vo + j]
+                                                             : ((int32_t)(vo + 1) == d.verticesOnEdge[2 * (int64_t)(e - 1)] ? -1 : 1);
+        }
+    }
+}
+
+// Arrays of the fused RK4 path in precision R: f folded into the weights, g/dc and 1/area
+// precomputed, the cell-side sign carried in bit 0 of the edge id.
+template <class R>
+struct FusedMesh {
+    DevBuf<R> gdc, wf, dv, invArea, H;
+    bool ready = false;
+};
+
+}  // namespace mokab
+
+struct mokab_mesh {
+    mokab_ctx *ctx = nullptr;
+    int64_t nC = 0, nE = 0, nV = 0;
+    int S = 0, S2 = 0, D = 0;
+    std::vector<int32_t> permC, permE, permV;
+    // reference-form arrays (Float64, unfolded) for the operator-level kernels
+    mokab::DevBuf<int2> ce;
+    mokab::DevBuf<int32_t> eoe, eoc, sgnC, eov, sgnV, dPermC, dPermE, dPermV;
+    mokab::DevBuf<uint8_t> nEoE, nEoC;
+    mokab::DevBuf<double> woe, dc, dv, fE, area, H, areaTri;
+    // fused-path arrays
+    mokab::DevBuf<int32_t> eoeF, eocF;   // absent -> self / sign in bit 0
+    mokab::DevBuf<int32_t> blkEdgeStart; // per block of FUSED_TC cells: first owned edge
+    int fusedBlocks = 0;
+    mokab::FusedMesh<double> f64;
+    mokab::FusedMesh<float> f32;
+    mokab::HostMesh host;  // kept for lazily building the other precision
+    int64_t device_bytes() const
+    {
+        return (int64_t)(ce.bytes() + eoe.bytes() + eoc.bytes() + sgnC.bytes() + eov.bytes() + sgnV.bytes() + dPermC.bytes() +
+                         dPermE.bytes() + dPermV.bytes() + nEoE.bytes() + nEoC.bytes() + woe.bytes() + dc.bytes() + dv.bytes() +
+                         fE.bytes() + area.bytes() + H.bytes() + areaTri.bytes() + eoeF.bytes() + eocF.bytes() +
+                         blkEdgeStart.bytes() + f64.gdc.bytes() + f64.wf.bytes() + f64.dv.bytes() + f64.invArea.bytes() +
+                         f64.H.bytes() + f32.gdc.bytes() + f32.wf.bytes() + f32.dv.bytes() + f32.invArea.bytes() + f32.H.bytes());
+    }
+};

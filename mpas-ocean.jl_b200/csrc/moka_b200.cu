@@ -1,0 +1,765 @@
+// moka_b200.cu -- libmoka_b200.so: C ABI (include/moka_b200.h) over the sm_100a kernels.
+#include "common.cuh"
+#include "kernels_fused.cuh"
+#include "kernels_ref.cuh"
+#include "mesh.cuh"
+
+namespace mokab {
+thread_local std::string g_last_error;
+
+#define LAUNCH(ctx, kernel, grid, block, ...)                          \
+    do {                                                               \
+        kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);    \
+        MOKAB_CUDA(cudaGetLastError());                                \
+        (ctx)->launches++;                                             \
+    } while (0)
+
+static inline int nblk(int64_t n, int t = 256) { return (int)((n + t - 1) / t); }
+
+// ---- typed state ----------------------------------------------------------------------------------------
+template <class R>
+struct StateT {
+    DevBuf<R> u[2], h[2], ssh[2];          // two time levels; `cur` holds Prog.*[end]
+    DevBuf<R> uP[2], hP[2];                // RK provisional ping-pong
+    DevBuf<R> hEdge, flux, divC, relVort, tendU, tendH, sshProv;
+    DevBuf<R> staging;
+    DevBuf<double> partial, result;
+    // fused RK4 graphs: [parity] one step starting with cur == parity; pair = two steps
+    cudaGraphExec_t gStep[2] = {nullptr, nullptr};
+    cudaGraphExec_t gPair[2] = {nullptr, nullptr};
+    double graph_dt = 0.0;
+    bool graphs_ready = false;
+    void drop_graphs()
+    {
+        for (int p = 0; p < 2; ++p) {
+            if (gStep[p]) cudaGraphExecDestroy(gStep[p]);
+            if (gPair[p]) cudaGraphExecDestroy(gPair[p]);
+            gStep[p] = gPair[p] = nullptr;
+        }
+        graphs_ready = false;
+    }
+    ~StateT() { drop_graphs(); }
+};
+}  // namespace mokab
+
+struct mokab_state {
+    mokab_ctx *ctx = nullptr;
+    const mokab_mesh *mesh = nullptr;
+    int dtype = MOKAB_F64;
+    int cur = 1;  // index of the time level holding Prog.*[end]
+    mokab::StateT<double> *d = nullptr;
+    mokab::StateT<float> *f = nullptr;
+    ~mokab_state()
+    {
+        delete d;
+        delete f;
+    }
+};
+
+namespace mokab {
+
+template <class R> static StateT<R> *typed(mokab_state *s);
+template <> StateT<double> *typed<double>(mokab_state *s) { return s->d; }
+template <> StateT<float> *typed<float>(mokab_state *s) { return s->f; }
+template <class R> static FusedMesh<R> &fused_of(mokab_mesh *m);
+template <> FusedMesh<double> &fused_of<double>(mokab_mesh *m) { return m->f64; }
+template <> FusedMesh<float> &fused_of<float>(mokab_mesh *m) { return m->f32; }
+
+// ---- mesh upload ----------------------------------------------------------------------------------------
+static void upload_mesh(mokab_ctx *ctx, HostMesh &hm, mokab_mesh *m)
+{
+    cudaStream_t s = ctx->stream;
+    m->ctx = ctx;
+    m->nC = hm.nC; m->nE = hm.nE; m->nV = hm.nV; m->S = hm.S; m->S2 = hm.S2; m->D = hm.D;
+    std::vector<int2> ce2(hm.nE);
+    for (int64_t e = 0; e < hm.nE; ++e) ce2[e] = make_int2(hm.ce[2 * e], hm.ce[2 * e + 1]);
+    m->ce.upload(ce2, s);
+    m->eoe.upload(hm.eoe, s); m->woe.upload(hm.woe, s); m->nEoE.upload(hm.nEoE, s);
+    m->dc.upload(hm.dc, s); m->dv.upload(hm.dv, s); m->fE.upload(hm.fE, s);
+    m->eoc.upload(hm.eoc, s); m->sgnC.upload(hm.sgnC, s); m->nEoC.upload(hm.nEoC, s);
+    m->area.upload(hm.area, s); m->H.upload(hm.H, s);
+    m->eov.upload(hm.eov, s); m->sgnV.upload(hm.sgnV, s); m->areaTri.upload(hm.areaTri, s);
+    m->dPermC.upload(hm.permC, s); m->dPermE.upload(hm.permE, s); m->dPermV.upload(hm.permV, s);
+    // per-block edge ranges of the fused kernel: edges are sorted by owner cell, block b owns cells
+    // [b*kTC, (b+1)*kTC) and the edges whose owner lies in that range.
+    const int nb = (int)((hm.nC + fused::kTC - 1) / fused::kTC);
+    std::vector<int32_t> start(nb + 1, 0);
+    {
+        int64_t e = 0;
+        for (int b = 0; b <= nb; ++b) {
+            const int64_t cfirst = (int64_t)b * fused::kTC;
+            while (e < hm.nE && hm.ce[2 * e] < cfirst) ++e;
+            start[b] = (int32_t)e;
+        }
+        start[nb] = (int32_t)hm.nE;
+    }
+    m->blkEdgeStart.upload(start, s);
+    m->fusedBlocks = nb;
+    m->permC.swap(hm.permC); m->permE.swap(hm.permE); m->permV.swap(hm.permV);
+    MOKAB_CUDA(cudaStreamSynchronize(s));
+}
+
+template <class R>
+static void ensure_fused(mokab_mesh *m)
+{
+    FusedMesh<R> &f = fused_of<R>(m);
+    if (f.ready) return;
+    mokab_ctx *ctx = m->ctx;
+    const bool need_idx = m->eoeF.n == 0;
+    if (need_idx) {
+        m->eoeF.alloc((size_t)m->S2 * m->nE);
+        m->eocF.alloc((size_t)m->S * m->nC);
+    }
+    f.gdc.alloc(m->nE); f.dv.alloc(m->nE); f.wf.alloc((size_t)m->S2 * m->nE);
+    f.invArea.alloc(m->nC); f.H.alloc(m->nC);
+    LAUNCH(ctx, fused::k_build_fused_edges<R>, nblk(m->nE), 256, (int)m->nE, m->S2, m->dc.p, m->dv.p, m->fE.p, m->eoe.p,
+           m->woe.p, m->nEoE.p, f.gdc.p, f.dv.p, f.wf.p, need_idx ? m->eoeF.p : nullptr);
+    LAUNCH(ctx, fused::k_build_fused_cells<R>, nblk(m->nC), 256, (int)m->nC, m->S, m->area.p, m->H.p, m->eoc.p, m->sgnC.p,
+           m->nEoC.p, f.invArea.p, f.H.p, need_idx ? m->eocF.p : nullptr);
+    f.ready = true;
+}
+
+// ---- state helpers ------------------------------------------------------------------------------------------
+template <class R>
+static void alloc_state(mokab_state *st)
+{
+    const mokab_mesh *m = st->mesh;
+    cudaStream_t s = st->ctx->stream;
+    auto *t = new StateT<R>();
+    if (sizeof(R) == 8) st->d = (StateT<double> *)(void *)t; else st->f = (StateT<float> *)(void *)t;
+    for (int l = 0; l < 2; ++l) {
+        t->u[l].alloc(m->nE); t->u[l].zero(s);
+        t->h[l].alloc(m->nC); t->h[l].zero(s);
+        t->ssh[l].alloc(m->nC); t->ssh[l].zero(s);
+        t->uP[l].alloc(m->nE); t->uP[l].zero(s);
+        t->hP[l].alloc(m->nC); t->hP[l].zero(s);
+    }
+    t->hEdge.alloc(m->nE); t->hEdge.zero(s);      // DiagnosticVars.jl:90-93
+    t->flux.alloc(m->nE); t->flux.zero(s);
+    t->divC.alloc(m->nC); t->divC.zero(s);
+    t->relVort.alloc(std::max<int64_t>(m->nV, 1)); t->relVort.zero(s);
+    t->tendU.alloc(m->nE); t->tendU.zero(s);      // TendencyVars.jl:61-62
+    t->tendH.alloc(m->nC); t->tendH.zero(s);
+    t->sshProv.alloc(m->nC); t->sshProv.zero(s);
+    t->staging.alloc(std::max(std::max(m->nE, m->nC), std::max<int64_t>(m->nV, 1)));
+    t->partial.alloc(reduce::kBlocks); t->result.alloc(1);
+    MOKAB_CUDA(cudaStreamSynchronize(s));
+}
+
+struct FieldRef { void *p; int64_t n; const int32_t *perm; bool prognostic_end; int prev_of; };
+
+template <class R>
+static FieldRef field_ref(mokab_state *st, int field)
+{
+    StateT<R> *t = typed<R>(st);
+    const mokab_mesh *m = st->mesh;
+    const int c = st->cur, o = 1 - st->cur;
+    switch (field) {
+    case MOKAB_SSH: return {t->ssh[c].p, m->nC, m->dPermC.p, true, field};
+    case MOKAB_NORMAL_VELOCITY: return {t->u[c].p, m->nE, m->dPermE.p, true, field};
+    case MOKAB_LAYER_THICKNESS: return {t->h[c].p, m->nC, m->dPermC.p, true, field};
+    case MOKAB_SSH_PREV: return {t->ssh[o].p, m->nC, m->dPermC.p, false, 0};
+    case MOKAB_NORMAL_VELOCITY_PREV: return {t->u[o].p, m->nE, m->dPermE.p, false, 0};
+    case MOKAB_LAYER_THICKNESS_PREV: return {t->h[o].p, m->nC, m->dPermC.p, false, 0};
+    case MOKAB_LAYER_THICKNESS_EDGE: return {t->hEdge.p, m->nE, m->dPermE.p, false, 0};
+    case MOKAB_THICKNESS_FLUX: return {t->flux.p, m->nE, m->dPermE.p, false, 0};
+    case MOKAB_VELOCITY_DIV_CELL: return {t->divC.p, m->nC, m->dPermC.p, false, 0};
+    case MOKAB_RELATIVE_VORTICITY: return {t->relVort.p, m->nV, m->dPermV.p, false, 0};
+    case MOKAB_TEND_NORMAL_VELOCITY: return {t->tendU.p, m->nE, m->dPermE.p, false, 0};
+    case MOKAB_TEND_LAYER_THICKNESS: return {t->tendH.p, m->nC, m->dPermC.p, false, 0};
+    default: throw Error("unknown field id " + std::to_string(field));
+    }
+}
+
+template <class R>
+static void state_set(mokab_state *st, int field, const void *host)
+{
+    mokab_ctx *ctx = st->ctx;
+    StateT<R> *t = typed<R>(st);
+    FieldRef f = field_ref<R>(st, field);
+    if (f.n == 0) return;
+    MOKAB_CUDA(cudaMemcpyAsync(t->staging.p, host, f.n * sizeof(R), cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, k_permute_in<R>, nblk(f.n), 256, f.n, f.perm, (const R *)t->staging.p, (R *)f.p);
+    if (f.prognostic_end) {  // deepcopy into every time level, PrognosticVars.jl:49-53
+        FieldRef prev = field_ref<R>(st, field + 3);
+        MOKAB_CUDA(cudaMemcpyAsync(prev.p, f.p, f.n * sizeof(R), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    MOKAB_CUDA(cudaStreamSynchronize(ctx->stream));  // the caller may reuse `host` immediately
+}
+
+template <class R>
+static void state_get(mokab_state *st, int field, void *host)
+{
+    mokab_ctx *ctx = st->ctx;
+    StateT<R> *t = typed<R>(st);
+    FieldRef f = field_ref<R>(st, field);
+    if (f.n == 0) return;
+    LAUNCH(ctx, k_permute_out<R>, nblk(f.n), 256, f.n, f.perm, (const R *)f.p, (R *)t->staging.p);
+    MOKAB_CUDA(cudaMemcpyAsync(host, t->staging.p, f.n * sizeof(R), cudaMemcpyDeviceToHost, ctx->stream));
+    MOKAB_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+// ---- reference-order operator sequences (Float64) -----------------------------------------------------------
+static void require_f64(mokab_state *st, const char *what)
+{
+    MOKAB_REQUIRE(st->dtype == MOKAB_F64,
+                  std::string(what) + ": the reference-order path is Float64 only (PrognosticVars.jl:91-93); "
+                                      "Float32 states support mokab_timestep_rk4(MOKAB_RK4_FUSED), set/get and reduce");
+}
+
+static void diag_compute(mokab_state *st, const double *u, const double *h)
+{
+    mokab_ctx *ctx = st->ctx; const mokab_mesh *m = st->mesh; StateT<double> *t = st->d;
+    LAUNCH(ctx, ref::k_diag_edges, nblk(m->nE), 256, (int)m->nE, m->ce.p, u, h, t->hEdge.p, t->flux.p);
+    LAUNCH(ctx, ref::k_divergence_on_cell, nblk(m->nC), 256, (int)m->nC, m->eoc.p, m->sgnC.p, m->nEoC.p, m->area.p, m->dv.p, u,
+           t->divC.p);
+    if (m->nV)
+        LAUNCH(ctx, ref::k_curl_on_vertex, nblk(m->nV), 256, (int)m->nV, m->D, m->eov.p, m->sgnV.p, m->areaTri.p, m->dc.p, u,
+               t->relVort.p);
+}
+
+static void tend_u(mokab_state *st, const double *ssh, const double *u)
+{
+    mokab_ctx *ctx = st->ctx; const mokab_mesh *m = st->mesh;
+    LAUNCH(ctx, ref::k_tend_normal_velocity, nblk(m->nE), 256, (int)m->nE, m->S2, m->ce.p, m->dc.p, m->eoe.p, m->woe.p, m->nEoE.p,
+           m->fE.p, ssh, u, st->d->tendU.p);
+}
+
+static void tend_h(mokab_state *st, const double *flux)
+{
+    mokab_ctx *ctx = st->ctx; const mokab_mesh *m = st->mesh;
+    LAUNCH(ctx, ref::k_tend_layer_thickness, nblk(m->nC), 256, (int)m->nC, m->eoc.p, m->sgnC.p, m->nEoC.p, m->area.p, m->dv.p, flux,
+           st->d->tendH.p);
+}
+
+// advanceTimeLevels! (time_integration.jl:10-40): previous <- new
+static void advance_time_levels(mokab_state *st)
+{
+    mokab_ctx *ctx = st->ctx; const mokab_mesh *m = st->mesh; StateT<double> *t = st->d;
+    const int c = st->cur, o = 1 - c;
+    MOKAB_CUDA(cudaMemcpyAsync(t->ssh[o].p, t->ssh[c].p, m->nC * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    MOKAB_CUDA(cudaMemcpyAsync(t->u[o].p, t->u[c].p, m->nE * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    MOKAB_CUDA(cudaMemcpyAsync(t->h[o].p, t->h[c].p, m->nC * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+}
+
+// ocn_timestep(::ForwardEuler), time_integration.jl:150-193
+static void step_forward_euler(mokab_state *st, double dt)
+{
+    mokab_ctx *ctx = st->ctx; const mokab_mesh *m = st->mesh; StateT<double> *t = st->d;
+    advance_time_levels(st);
+    const int c = st->cur;
+    diag_compute(st, t->u[c].p, t->h[c].p);
+    tend_u(st, t->ssh[c].p, t->u[c].p);
+    tend_h(st, t->flux.p);
+    LAUNCH(ctx, ref::k_axpy, nblk(m->nE), 256, m->nE, (const double *)t->u[c].p, dt, (const double *)t->tendU.p, t->u[c].p);
+    LAUNCH(ctx, ref::k_axpy, nblk(m->nC), 256, m->nC, (const double *)t->h[c].p, dt, (const double *)t->tendH.p, t->h[c].p);
+    LAUNCH(ctx, k_update_ssh<double>, nblk(m->nC), 256, m->nC, (const double *)t->h[c].p, (const double *)m->H.p, t->ssh[c].p);
+}
+
+// ocn_timestep(::RungeKutta4) with the reference's per-stage kernel sequence (time_integration.jl:112-137)
+static void step_rk4_unfused(mokab_state *st, double dt)
+{
+    mokab_ctx *ctx = st->ctx; const mokab_mesh *m = st->mesh; StateT<double> *t = st->d;
+    const double a[3] = {dt / 2.0, dt / 2.0, dt};
+    const double b[4] = {dt / 6.0, dt / 3.0, dt / 3.0, dt / 6.0};
+    advance_time_levels(st);
+    const int c = st->cur, o = 1 - c;
+    const double *uCur = t->u[o].p, *hCur = t->h[o].p;
+    double *uPro = t->uP[0].p, *hPro = t->hP[0].p, *uNew = t->uP[1].p, *hNew = t->hP[1].p;
+    cudaStream_t s = ctx->stream;
+    MOKAB_CUDA(cudaMemcpyAsync(uPro, uCur, m->nE * 8, cudaMemcpyDeviceToDevice, s));
+    MOKAB_CUDA(cudaMemcpyAsync(hPro, hCur, m->nC * 8, cudaMemcpyDeviceToDevice, s));
+    MOKAB_CUDA(cudaMemcpyAsync(uNew, uCur, m->nE * 8, cudaMemcpyDeviceToDevice, s));
+    MOKAB_CUDA(cudaMemcpyAsync(hNew, hCur, m->nC * 8, cudaMemcpyDeviceToDevice, s));
+    for (int sg = 0; sg < 4; ++sg) {
+        LAUNCH(ctx, k_update_ssh<double>, nblk(m->nC), 256, m->nC, (const double *)hPro, (const double *)m->H.p, t->sshProv.p);
+        LAUNCH(ctx, ref::k_interpolate_cell2edge, nblk(m->nE), 256, (int)m->nE, m->ce.p, (const double *)hPro, t->hEdge.p);
+        LAUNCH(ctx, ref::k_mul, nblk(m->nE), 256, m->nE, (const double *)uPro, (const double *)t->hEdge.p, t->flux.p);
+        tend_u(st, t->sshProv.p, uPro);
+        tend_h(st, t->flux.p);
+        if (sg < 3) {
+            LAUNCH(ctx, ref::k_axpy, nblk(m->nE), 256, m->nE, uCur, a[sg], (const double *)t->tendU.p, uPro);
+            LAUNCH(ctx, ref::k_axpy, nblk(m->nC), 256, m->nC, hCur, a[sg], (const double *)t->tendH.p, hPro);
+        }
+        LAUNCH(ctx, ref::k_axpy, nblk(m->nE), 256, m->nE, (const double *)uNew, b[sg], (const double *)t->tendU.p, uNew);
+        LAUNCH(ctx, ref::k_axpy, nblk(m->nC), 256, m->nC, (const double *)hNew, b[sg], (const double *)t->tendH.p, hNew);
+    }
+    MOKAB_CUDA(cudaMemcpyAsync(t->u[c].p, uNew, m->nE * 8, cudaMemcpyDeviceToDevice, s));
+    MOKAB_CUDA(cudaMemcpyAsync(t->h[c].p, hNew, m->nC * 8, cudaMemcpyDeviceToDevice, s));
+    LAUNCH(ctx, k_update_ssh<double>, nblk(m->nC), 256, m->nC, (const double *)hNew, (const double *)m->H.p, t->ssh[c].p);
+}
+
+// ---- fused RK4 ------------------------------------------------------------------------------------------------
+template <class R, int STAGE>
+static void launch_stage(mokab_ctx *ctx, const mokab_mesh *m, const fused::StageArgs<R> &A)
+{
+    const int grid = m->fusedBlocks;
+    if (m->S2 == 10 && m->S == 6)
+        LAUNCH(ctx, (fused::k_rk_stage<R, STAGE, 10, 6>), grid, fused::kThreads, A, m->S2, m->S);
+    else
+        LAUNCH(ctx, (fused::k_rk_stage<R, STAGE, 0, 0>), grid, fused::kThreads, A, m->S2, m->S);
+}
+
+// one RK4 step reading time level `p`, writing level 1-p (four launches)
+template <class R>
+static void enqueue_rk4_step(mokab_state *st, double dt, int p)
+{
+    mokab_ctx *ctx = st->ctx; mokab_mesh *m = const_cast<mokab_mesh *>(st->mesh);
+    StateT<R> *t = typed<R>(st);
+    FusedMesh<R> &fm = fused_of<R>(m);
+    fused::StageArgs<R> A;
+    A.nE = (int)m->nE; A.nC = (int)m->nC;
+    A.ce = m->ce.p; A.eoe = m->eoeF.p; A.eoc = m->eocF.p; A.nEoE = m->nEoE.p; A.nEoC = m->nEoC.p;
+    A.blkEdgeStart = m->blkEdgeStart.p;
+    A.gdc = fm.gdc.p; A.wf = fm.wf.p; A.dv = fm.dv.p; A.invArea = fm.invArea.p; A.H = fm.H.p;
+    A.uCur = t->u[p].p; A.hCur = t->h[p].p; A.uAcc = t->u[1 - p].p; A.hAcc = t->h[1 - p].p;
+    const double a[3] = {dt / 2.0, dt / 2.0, dt};                       // time_integration.jl:77
+    const double b[4] = {dt / 6.0, dt / 3.0, dt / 3.0, dt / 6.0};       // time_integration.jl:78
+    // stage 1: provisional == current
+    A.uOld = t->u[p].p; A.hOld = t->h[p].p; A.uOut = t->uP[0].p; A.hOut = t->hP[0].p; A.a = (R)a[0]; A.b = (R)b[0];
+    launch_stage<R, 1>(ctx, m, A);
+    A.uOld = t->uP[0].p; A.hOld = t->hP[0].p; A.uOut = t->uP[1].p; A.hOut = t->hP[1].p; A.a = (R)a[1]; A.b = (R)b[1];
+    launch_stage<R, 2>(ctx, m, A);
+    A.uOld = t->uP[1].p; A.hOld = t->hP[1].p; A.uOut = t->uP[0].p; A.hOut = t->hP[0].p; A.a = (R)a[2]; A.b = (R)b[2];
+    launch_stage<R, 2>(ctx, m, A);
+    A.uOld = t->uP[0].p; A.hOld = t->hP[0].p; A.uOut = nullptr; A.hOut = nullptr; A.a = R(0); A.b = (R)b[3];
+    launch_stage<R, 4>(ctx, m, A);
+}
+
+template <class R>
+static void build_graphs(mokab_state *st, double dt)
+{
+    mokab_ctx *ctx = st->ctx;
+    StateT<R> *t = typed<R>(st);
+    t->drop_graphs();
+    const int64_t saved = ctx->launches;
+    for (int p = 0; p < 2; ++p)
+        for (int pair = 0; pair < 2; ++pair) {
+            cudaGraph_t g = nullptr;
+            MOKAB_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+            try {
+                enqueue_rk4_step<R>(st, dt, p);
+                if (pair) enqueue_rk4_step<R>(st, dt, 1 - p);
+            } catch (...) {
+                cudaStreamEndCapture(ctx->stream, &g);
+                if (g) cudaGraphDestroy(g);
+                throw;
+            }
+            MOKAB_CUDA(cudaStreamEndCapture(ctx->stream, &g));
+            cudaGraphExec_t ge = nullptr;
+            cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
+            cudaGraphDestroy(g);
+            MOKAB_CUDA(e);
+            (pair ? t->gPair : t->gStep)[p] = ge;
+        }
+    ctx->launches = saved;  // capture enqueues are not executions
+    t->graph_dt = dt;
+    t->graphs_ready = true;
+}
+
+template <class R>
+static void refresh_ssh(mokab_state *st)
+{
+    mokab_ctx *ctx = st->ctx; mokab_mesh *m = const_cast<mokab_mesh *>(st->mesh);
+    StateT<R> *t = typed<R>(st);
+    FusedMesh<R> &fm = fused_of<R>(m);
+    for (int l = 0; l < 2; ++l)
+        LAUNCH(ctx, k_update_ssh<R>, nblk(m->nC), 256, m->nC, (const R *)t->h[l].p, (const R *)fm.H.p, t->ssh[l].p);
+}
+
+template <class R>
+static void run_rk4_fused(mokab_state *st, double dt, int64_t nsteps)
+{
+    mokab_ctx *ctx = st->ctx;
+    StateT<R> *t = typed<R>(st);
+    ensure_fused<R>(const_cast<mokab_mesh *>(st->mesh));
+    if (!t->graphs_ready || t->graph_dt != dt) build_graphs<R>(st, dt);
+    int64_t left = nsteps;
+    while (left >= 2) {
+        MOKAB_CUDA(cudaGraphLaunch(t->gPair[st->cur], ctx->stream));
+        ctx->launches += 8;
+        left -= 2;
+    }
+    if (left) {
+        MOKAB_CUDA(cudaGraphLaunch(t->gStep[st->cur], ctx->stream));
+        ctx->launches += 4;
+        st->cur = 1 - st->cur;
+    }
+    if (nsteps > 0) refresh_ssh<R>(st);
+}
+
+template <class R>
+static void do_reduce(mokab_state *st, int which, double *out)
+{
+    mokab_ctx *ctx = st->ctx; mokab_mesh *m = const_cast<mokab_mesh *>(st->mesh);
+    StateT<R> *t = typed<R>(st);
+    ensure_fused<R>(m);
+    FusedMesh<R> &fm = fused_of<R>(m);
+    const int c = st->cur;
+    MOKAB_REQUIRE(which >= 0 && which <= 2, "reduce: unknown reduction id");
+    LAUNCH(ctx, reduce::k_cells<R>, reduce::kBlocks, reduce::kThreads, which, m->nC, (const R *)t->h[c].p, (const R *)fm.H.p,
+           (const double *)m->area.p, t->partial.p);
+    if (which == MOKAB_SUM_ENERGY)
+        LAUNCH(ctx, reduce::k_edges_ke<R>, reduce::kBlocks, reduce::kThreads, m->nE, (const int2 *)m->ce.p, (const double *)m->dc.p,
+               (const double *)m->dv.p, (const R *)t->u[c].p, (const R *)t->h[c].p, t->partial.p);
+    LAUNCH(ctx, reduce::k_final, 1, reduce::kThreads, (const double *)t->partial.p, t->result.p);
+    MOKAB_CUDA(cudaMemcpyAsync(out, t->result.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    MOKAB_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+// stand-alone operators on host arrays -------------------------------------------------------------------
+struct OpBufs {
+    DevBuf<double> in, in_p, out, out_p;
+};
+
+}  // namespace mokab
+
+using namespace mokab;
+
+// =================================================================================================================
+extern "C" {
+
+const char *mokab_last_error(void) { return g_last_error.c_str(); }
+int mokab_version(void) { return MOKAB_VERSION; }
+
+int mokab_init(int device, mokab_ctx **out)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(out, "mokab_init: out is NULL");
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0)
+            throw Error(std::string("mokab_init: no CUDA device available (") + cudaGetErrorString(e) +
+                        "); libmoka_b200 has no CPU fallback");
+        MOKAB_REQUIRE(device >= 0 && device < n, "mokab_init: device index out of range");
+        MOKAB_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        MOKAB_CUDA(cudaGetDeviceProperties(&prop, device));
+        MOKAB_REQUIRE(prop.major >= 10, std::string("mokab_init: device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                                            std::to_string(prop.minor) + "; this library is built for sm_100a only");
+        auto *c = new mokab_ctx();
+        c->device = device;
+        c->num_sms = prop.multiProcessorCount;
+        MOKAB_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+        c->stream = c->own_stream;
+        MOKAB_CUDA(cudaEventCreate(&c->ev0));
+        MOKAB_CUDA(cudaEventCreate(&c->ev1));
+        *out = c;
+    });
+}
+
+int mokab_finalize(mokab_ctx *ctx)
+{
+    return guarded([&] {
+        if (!ctx) return;
+        ctx->bind();
+        cudaStreamSynchronize(ctx->stream);
+        cudaEventDestroy(ctx->ev0);
+        cudaEventDestroy(ctx->ev1);
+        cudaStreamDestroy(ctx->own_stream);
+        delete ctx;
+    });
+}
+
+int mokab_synchronize(mokab_ctx *ctx)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(ctx, "synchronize: ctx is NULL");
+        ctx->bind();
+        MOKAB_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+int mokab_set_stream(mokab_ctx *ctx, void *cuda_stream)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(ctx, "set_stream: ctx is NULL");
+        ctx->bind();
+        MOKAB_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    });
+}
+
+int mokab_timer_start(mokab_ctx *ctx)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(ctx, "timer_start: ctx is NULL");
+        ctx->bind();
+        MOKAB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    });
+}
+
+int mokab_timer_stop(mokab_ctx *ctx, double *elapsed_ms)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(ctx && elapsed_ms, "timer_stop: NULL argument");
+        ctx->bind();
+        MOKAB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+        MOKAB_CUDA(cudaEventSynchronize(ctx->ev1));
+        float ms = 0.f;
+        MOKAB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        *elapsed_ms = (double)ms;
+    });
+}
+
+int mokab_launch_count(mokab_ctx *ctx, int64_t *out)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(ctx && out, "launch_count: NULL argument");
+        *out = ctx->launches;
+    });
+}
+
+int mokab_host_alloc(void **out, int64_t bytes)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(out && bytes >= 0, "host_alloc: bad argument");
+        MOKAB_CUDA(cudaHostAlloc(out, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocDefault));
+    });
+}
+
+int mokab_host_free(void *p)
+{
+    return guarded([&] {
+        if (p) MOKAB_CUDA(cudaFreeHost(p));
+    });
+}
+
+// ---- mesh ------------------------------------------------------------------------------------------------------
+int mokab_mesh_create(mokab_ctx *ctx, const mokab_mesh_desc *desc, uint32_t flags, mokab_mesh **out)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(ctx && desc && out, "mesh_create: NULL argument");
+        ctx->bind();
+        HostMesh hm;
+        build_host_mesh(*desc, flags, hm);
+        auto *m = new mokab_mesh();
+        try {
+            upload_mesh(ctx, hm, m);
+        } catch (...) {
+            delete m;
+            throw;
+        }
+        *out = m;
+    });
+}
+
+int mokab_mesh_destroy(mokab_mesh *mesh)
+{
+    return guarded([&] {
+        if (!mesh) return;
+        mesh->ctx->bind();
+        cudaStreamSynchronize(mesh->ctx->stream);
+        delete mesh;
+    });
+}
+
+int mokab_mesh_get_perm(const mokab_mesh *mesh, int kind, int32_t *perm_out)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(mesh && perm_out, "mesh_get_perm: NULL argument");
+        const std::vector<int32_t> *p = kind == MOKAB_CELLS ? &mesh->permC : kind == MOKAB_EDGES ? &mesh->permE
+                                        : kind == MOKAB_VERTICES ? &mesh->permV : nullptr;
+        MOKAB_REQUIRE(p, "mesh_get_perm: unknown entity kind");
+        if (!p->empty()) memcpy(perm_out, p->data(), p->size() * sizeof(int32_t));
+    });
+}
+
+int mokab_mesh_device_bytes(const mokab_mesh *mesh, int64_t *out)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(mesh && out, "mesh_device_bytes: NULL argument");
+        *out = mesh->device_bytes();
+    });
+}
+
+// ---- state -----------------------------------------------------------------------------------------------------
+int mokab_state_create(mokab_ctx *ctx, const mokab_mesh *mesh, int dtype, mokab_state **out)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(ctx && mesh && out, "state_create: NULL argument");
+        MOKAB_REQUIRE(mesh->ctx == ctx, "state_create: mesh belongs to a different context (src/Architectures.jl:27-33)");
+        MOKAB_REQUIRE(dtype == MOKAB_F64 || dtype == MOKAB_F32, "state_create: dtype must be MOKAB_F64 or MOKAB_F32");
+        ctx->bind();
+        auto *st = new mokab_state();
+        st->ctx = ctx; st->mesh = mesh; st->dtype = dtype;
+        try {
+            if (dtype == MOKAB_F64) alloc_state<double>(st); else alloc_state<float>(st);
+        } catch (...) {
+            delete st;
+            throw;
+        }
+        *out = st;
+    });
+}
+
+int mokab_state_destroy(mokab_state *state)
+{
+    return guarded([&] {
+        if (!state) return;
+        state->ctx->bind();
+        cudaStreamSynchronize(state->ctx->stream);
+        delete state;
+    });
+}
+
+int mokab_state_set(mokab_state *state, int field, const void *host)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(state && host, "state_set: NULL argument");
+        MOKAB_REQUIRE(field >= MOKAB_SSH && field <= MOKAB_TEND_LAYER_THICKNESS, "state_set: unknown field id");
+        state->ctx->bind();
+        if (state->dtype == MOKAB_F64) state_set<double>(state, field, host); else state_set<float>(state, field, host);
+    });
+}
+
+int mokab_state_get(mokab_state *state, int field, void *host)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(state && host, "state_get: NULL argument");
+        MOKAB_REQUIRE(field >= MOKAB_SSH && field <= MOKAB_TEND_LAYER_THICKNESS, "state_get: unknown field id");
+        state->ctx->bind();
+        if (state->dtype == MOKAB_F64) state_get<double>(state, field, host); else state_get<float>(state, field, host);
+    });
+}
+
+// ---- src/ocn entry points -----------------------------------------------------------------------------------------
+int mokab_diagnostic_compute(mokab_state *state)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(state, "diagnostic_compute: state is NULL");
+        require_f64(state, "diagnostic_compute");
+        state->ctx->bind();
+        diag_compute(state, state->d->u[state->cur].p, state->d->h[state->cur].p);
+    });
+}
+
+int mokab_compute_normal_velocity_tendency(mokab_state *state)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(state, "compute_normal_velocity_tendency: state is NULL");
+        require_f64(state, "compute_normal_velocity_tendency");
+        state->ctx->bind();
+        tend_u(state, state->d->ssh[state->cur].p, state->d->u[state->cur].p);
+    });
+}
+
+int mokab_compute_layer_thickness_tendency(mokab_state *state)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(state, "compute_layer_thickness_tendency: state is NULL");
+        require_f64(state, "compute_layer_thickness_tendency");
+        state->ctx->bind();
+        tend_h(state, state->d->flux.p);
+    });
+}
+
+static void op_common(mokab_ctx *ctx, const mokab_mesh *mesh, const double *in, int64_t nin, const int32_t *perm_in,
+                      double *out, int64_t nout, const int32_t *perm_out, bool out_is_inout, OpBufs &B)
+{
+    B.in.alloc(nin); B.in_p.alloc(nin); B.out.alloc(nout); B.out_p.alloc(nout);
+    MOKAB_CUDA(cudaMemcpyAsync(B.in.p, in, nin * 8, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, k_permute_in<double>, nblk(nin), 256, nin, perm_in, (const double *)B.in.p, B.in_p.p);
+    if (out_is_inout) {
+        MOKAB_CUDA(cudaMemcpyAsync(B.out.p, out, nout * 8, cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCH(ctx, k_permute_in<double>, nblk(nout), 256, nout, perm_out, (const double *)B.out.p, B.out_p.p);
+    }
+}
+static void op_finish(mokab_ctx *ctx, double *out, int64_t nout, const int32_t *perm_out, OpBufs &B)
+{
+    LAUNCH(ctx, k_permute_out<double>, nblk(nout), 256, nout, perm_out, (const double *)B.out_p.p, B.out.p);
+    MOKAB_CUDA(cudaMemcpyAsync(out, B.out.p, nout * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    MOKAB_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+int mokab_gradient_on_edge(mokab_ctx *ctx, const mokab_mesh *m, const double *scalar_cell, double *grad_edge)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(ctx && m && scalar_cell && grad_edge, "gradient_on_edge: NULL argument");
+        ctx->bind();
+        OpBufs B;
+        op_common(ctx, m, scalar_cell, m->nC, m->dPermC.p, grad_edge, m->nE, m->dPermE.p, false, B);
+        LAUNCH(ctx, ref::k_gradient_on_edge, nblk(m->nE), 256, (int)m->nE, m->ce.p, m->dc.p, (const double *)B.in_p.p, B.out_p.p);
+        op_finish(ctx, grad_edge, m->nE, m->dPermE.p, B);
+    });
+}
+
+int mokab_divergence_on_cell(mokab_ctx *ctx, const mokab_mesh *m, const double *vec_edge, double *div_cell)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(ctx && m && vec_edge && div_cell, "divergence_on_cell: NULL argument");
+        ctx->bind();
+        OpBufs B;
+        op_common(ctx, m, vec_edge, m->nE, m->dPermE.p, div_cell, m->nC, m->dPermC.p, false, B);
+        LAUNCH(ctx, ref::k_divergence_on_cell, nblk(m->nC), 256, (int)m->nC, m->eoc.p, m->sgnC.p, m->nEoC.p, m->area.p, m->dv.p,
+               (const double *)B.in_p.p, B.out_p.p);
+        op_finish(ctx, div_cell, m->nC, m->dPermC.p, B);
+    });
+}
+
+int mokab_curl_on_vertex(mokab_ctx *ctx, const mokab_mesh *m, const double *vec_edge, double *curl_vertex_inout)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(ctx && m && vec_edge && curl_vertex_inout, "curl_on_vertex: NULL argument");
+        MOKAB_REQUIRE(m->nV > 0, "curl_on_vertex: the mesh was created without vertex arrays");
+        ctx->bind();
+        OpBufs B;
+        op_common(ctx, m, vec_edge, m->nE, m->dPermE.p, curl_vertex_inout, m->nV, m->dPermV.p, true, B);
+        LAUNCH(ctx, ref::k_curl_on_vertex, nblk(m->nV), 256, (int)m->nV, m->D, m->eov.p, m->sgnV.p, m->areaTri.p, m->dc.p,
+               (const double *)B.in_p.p, B.out_p.p);
+        op_finish(ctx, curl_vertex_inout, m->nV, m->dPermV.p, B);
+    });
+}
+
+int mokab_interpolate_cell2edge(mokab_ctx *ctx, const mokab_mesh *m, const double *cell_value, double *edge_value)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(ctx && m && cell_value && edge_value, "interpolate_cell2edge: NULL argument");
+        ctx->bind();
+        OpBufs B;
+        op_common(ctx, m, cell_value, m->nC, m->dPermC.p, edge_value, m->nE, m->dPermE.p, false, B);
+        LAUNCH(ctx, ref::k_interpolate_cell2edge, nblk(m->nE), 256, (int)m->nE, m->ce.p, (const double *)B.in_p.p, B.out_p.p);
+        op_finish(ctx, edge_value, m->nE, m->dPermE.p, B);
+    });
+}
+
+// ---- src/forward entry points ----------------------------------------------------------------------------------------
+int mokab_timestep_forward_euler(mokab_state *state, double dt, int64_t nsteps)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(state, "timestep_forward_euler: state is NULL");
+        MOKAB_REQUIRE(nsteps >= 0, "timestep_forward_euler: nsteps must be >= 0");
+        require_f64(state, "timestep_forward_euler");
+        state->ctx->bind();
+        for (int64_t i = 0; i < nsteps; ++i) step_forward_euler(state, dt);
+    });
+}
+
+int mokab_timestep_rk4(mokab_state *state, double dt, int64_t nsteps, int impl)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(state, "timestep_rk4: state is NULL");
+        MOKAB_REQUIRE(nsteps >= 0, "timestep_rk4: nsteps must be >= 0");
+        MOKAB_REQUIRE(impl == MOKAB_RK4_FUSED || impl == MOKAB_RK4_UNFUSED, "timestep_rk4: unknown impl");
+        state->ctx->bind();
+        if (impl == MOKAB_RK4_UNFUSED) {
+            require_f64(state, "timestep_rk4(MOKAB_RK4_UNFUSED)");
+            for (int64_t i = 0; i < nsteps; ++i) step_rk4_unfused(state, dt);
+        } else if (state->dtype == MOKAB_F64) {
+            run_rk4_fused<double>(state, dt, nsteps);
+        } else {
+            run_rk4_fused<float>(state, dt, nsteps);
+        }
+    });
+}
+
+int mokab_reduce(mokab_state *state, int which, double *out)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(state && out, "reduce: NULL argument");
+        state->ctx->bind();
+        if (state->dtype == MOKAB_F64) do_reduce<double>(state, which, out); else do_reduce<float>(state, which, out);
+    });
+}
+
+}  // extern "C"

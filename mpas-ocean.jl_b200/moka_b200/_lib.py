@@ -1,0 +1,96 @@
+"""ctypes binding of libmoka_b200.so (include/moka_b200.h).  No CPU fallback: a missing library
+or a missing CUDA device raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libmoka_b200.so")
+
+F64, F32 = 0, 1
+(SSH, NORMAL_VELOCITY, LAYER_THICKNESS, SSH_PREV, NORMAL_VELOCITY_PREV, LAYER_THICKNESS_PREV,
+ LAYER_THICKNESS_EDGE, THICKNESS_FLUX, VELOCITY_DIV_CELL, RELATIVE_VORTICITY,
+ TEND_NORMAL_VELOCITY, TEND_LAYER_THICKNESS) = range(12)
+SUM_SSH2, SUM_MASS, SUM_ENERGY = range(3)
+CELLS, EDGES, VERTICES = range(3)
+RK4_FUSED, RK4_UNFUSED = 0, 1
+MESH_RENUMBER = 1
+
+_I32P, _F64P = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+
+# name -> pointer type, in the order of struct mokab_mesh_desc
+_DESC_PTRS = [
+    ("cellsOnEdge", _I32P), ("verticesOnEdge", _I32P), ("edgesOnEdge", _I32P), ("nEdgesOnEdge", _I32P),
+    ("weightsOnEdge", _F64P), ("dcEdge", _F64P), ("dvEdge", _F64P), ("fEdge", _F64P),
+    ("xEdge", _F64P), ("yEdge", _F64P), ("zEdge", _F64P),
+    ("edgesOnCell", _I32P), ("nEdgesOnCell", _I32P), ("edgeSignOnCell", _I32P), ("areaCell", _F64P),
+    ("xCell", _F64P), ("yCell", _F64P), ("zCell", _F64P),
+    ("edgesOnVertex", _I32P), ("edgeSignOnVertex", _I32P), ("areaTriangle", _F64P),
+    ("restingThicknessSum", _F64P), ("boundaryEdge", _I32P),
+]
+
+
+class MeshDesc(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("nCells", "nEdges", "nVertices", "maxEdges", "maxEdges2", "vertexDegree")] + _DESC_PTRS
+
+
+class MokaError(RuntimeError):
+    """What the Julia shim raises with `error(msg)` (reference convention src/Architectures.jl:23)."""
+
+
+_lib = None
+
+# every symbol include/moka_b200.h declares
+SYMBOLS = [
+    "mokab_init", "mokab_finalize", "mokab_synchronize", "mokab_set_stream", "mokab_timer_start", "mokab_timer_stop",
+    "mokab_launch_count", "mokab_host_alloc", "mokab_host_free", "mokab_last_error", "mokab_version",
+    "mokab_mesh_create", "mokab_mesh_destroy", "mokab_mesh_get_perm", "mokab_mesh_device_bytes",
+    "mokab_state_create", "mokab_state_destroy", "mokab_state_set", "mokab_state_get",
+    "mokab_diagnostic_compute", "mokab_compute_normal_velocity_tendency", "mokab_compute_layer_thickness_tendency",
+    "mokab_gradient_on_edge", "mokab_divergence_on_cell", "mokab_curl_on_vertex", "mokab_interpolate_cell2edge",
+    "mokab_timestep_forward_euler", "mokab_timestep_rk4", "mokab_reduce",
+]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MokaError(f"{LIB_PATH} is missing: build it with `make -C {os.path.dirname(LIB_PATH)}` "
+                            "(python __graft_entry__.py build); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        L.mokab_last_error.restype = C.c_char_p
+        vp, i64, dbl = C.c_void_p, C.c_int64, C.c_double
+        sig = {
+            "mokab_init": [C.c_int, C.POINTER(vp)], "mokab_finalize": [vp], "mokab_synchronize": [vp],
+            "mokab_set_stream": [vp, vp], "mokab_timer_start": [vp], "mokab_timer_stop": [vp, C.POINTER(dbl)],
+            "mokab_launch_count": [vp, C.POINTER(i64)], "mokab_host_alloc": [C.POINTER(vp), i64], "mokab_host_free": [vp],
+            "mokab_mesh_create": [vp, C.POINTER(MeshDesc), C.c_uint32, C.POINTER(vp)], "mokab_mesh_destroy": [vp],
+            "mokab_mesh_get_perm": [vp, C.c_int, _I32P], "mokab_mesh_device_bytes": [vp, C.POINTER(i64)],
+            "mokab_state_create": [vp, vp, C.c_int, C.POINTER(vp)], "mokab_state_destroy": [vp],
+            "mokab_state_set": [vp, C.c_int, vp], "mokab_state_get": [vp, C.c_int, vp],
+            "mokab_diagnostic_compute": [vp], "mokab_compute_normal_velocity_tendency": [vp],
+            "mokab_compute_layer_thickness_tendency": [vp],
+            "mokab_gradient_on_edge": [vp, vp, _F64P, _F64P], "mokab_divergence_on_cell": [vp, vp, _F64P, _F64P],
+            "mokab_curl_on_vertex": [vp, vp, _F64P, _F64P], "mokab_interpolate_cell2edge": [vp, vp, _F64P, _F64P],
+            "mokab_timestep_forward_euler": [vp, dbl, i64], "mokab_timestep_rk4": [vp, dbl, i64, C.c_int],
+            "mokab_reduce": [vp, C.c_int, C.POINTER(dbl)],
+        }
+        for name, args in sig.items():
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise MokaError(lib().mokab_last_error().decode("utf-8", "replace"))
+
+
+def fptr(a: np.ndarray):
+    return a.ctypes.data_as(_F64P)

@@ -55,7 +55,7 @@ def periodic_hex(nx: int, ny: int, dc: float, f0: float = 1.0e-4,
     c = np.arange(nC, dtype=np.int64)
     i, j = nb["i"], nb["j"]
 
-    m: dict = {"nCells": nC, "nEdges": 3 * nC, "nVertices": 2 * nC, "maxEdges": 6,
+    m: dict = {"nCells": nC, "nEdges": 3 * nC, "nVertices": 2 * nC if with_dual else 0, "maxEdges": 6,
                "maxEdges2": 10, "vertexDegree": 3, "nVertLevels": 1, "is_periodic": "YES",
                "x_period": nx * dc, "y_period": ny * dc * SQRT3 / 2.0, "dc": float(dc),
                "nx": nx, "ny": ny}

@@ -65,7 +65,7 @@ def sign_index_fields(m: dict) -> None:
     act = np.arange(m["maxEdges"])[None, :] < m["nEdgesOnCell"][:, None]
     c1 = m["cellsOnEdge"][np.where(act, eoc, 0), 0]
     m["edgeSignOnCell"] = np.where(act, np.where(c1 == (np.arange(nC) + 1)[:, None], -1, 1), 0).astype(np.int32)
-    if m.get("nVertices", 0):
+    if m.get("nVertices", 0) and "edgesOnVertex" in m:
         nV = m["nVertices"]
         eov = m["edgesOnVertex"].astype(np.int64) - 1
         v1 = m["verticesOnEdge"][eov, 0]
