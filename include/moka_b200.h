@@ -107,6 +107,10 @@ typedef struct mokab_mesh_desc {
     const double  *restingThicknessSum; /* (nCells)            VertMesh.jl:73                        */
     /* masks (legacy glossary src/infra/Mesh.jl:110-114; project-defined for non-periodic meshes)    */
     const int32_t *boundaryEdge;     /* (nEdges) (opt) 1 = solid-wall edge: u = tendU = 0            */
+    /* domain decomposition (no reference counterpart): the first nCellsOwned cells
+     * and nEdgesOwned edges are computed by this rank, the rest are halo copies filled by
+     * mokab_halo_unpack.  0 = everything is owned.  Connectivity rows of halo entities are not read.  */
+    int64_t nCellsOwned, nEdgesOwned;
 } mokab_mesh_desc;
 
 /* ---- context: Architectures.jl backend object ------------------------------------------------ */
@@ -168,8 +172,31 @@ int  mokab_timestep_forward_euler(mokab_state *state, double dt, int64_t nsteps)
  * MOKAB_RK4_FUSED or MOKAB_RK4_UNFUSED.  On return Prog.*[end] is the new state, Prog.*[1] the state
  * one step earlier, ssh = layerThickness - restingThicknessSum. */
 int  mokab_timestep_rk4(mokab_state *state, double dt, int64_t nsteps, int impl);
-/* sumArray replacement (deterministic two-level reduction); result always Float64. */
+/* sumArray replacement (deterministic two-level reduction) over the OWNED entities; result always Float64. */
 int  mokab_reduce(mokab_state *state, int which, double *out);
+
+/* ---- staged RungeKutta4 for domain-decomposed runs (one process per GPU) --------------------------
+ * The same fused stage kernel, launched per stage and per part so the host can overlap the halo
+ * exchange of stage s with the interior of stage s.  `cuda_stream` NULL = the
+ * context's stream.  Entities are addressed in the combined local index space [cells | edges]
+ * (edge k -> nCells + k), caller numbering, 0-based. */
+enum { MOKAB_PART_ALL = 0, MOKAB_PART_INTERIOR = 1, MOKAB_PART_BOUNDARY = 2 };
+/* send_idx: owned entities whose values neighbours need; recv_idx: halo entities, in message order.
+ * Blocks that hold a send entity join the BOUNDARY part, so a message can be packed as soon as the
+ * boundary launch of a stage has finished.  Call before creating states on the mesh. */
+int  mokab_halo_setup(mokab_mesh *mesh, int64_t n_send, const int32_t *send_idx, int64_t n_recv, const int32_t *recv_idx);
+/* stage 0 = the current state Prog.*[end]; stage s = 1..4 = the output of RK stage s of the step in flight.
+ * pack: device message buffer (state dtype, n_send elements) <- values; unpack: halo slots <- message. */
+int  mokab_halo_pack(mokab_state *state, int stage, void *send_buf_device, void *cuda_stream);
+int  mokab_halo_unpack(mokab_state *state, int stage, const void *recv_buf_device, void *cuda_stream);
+/* one fused RK stage (1..4) over MOKAB_PART_ALL / _INTERIOR / _BOUNDARY blocks */
+int  mokab_rk4_stage(mokab_state *state, double dt, int stage, int part, void *cuda_stream);
+/* after stage 4 (and its exchange): the other time level becomes Prog.*[end] */
+int  mokab_rk4_finish_step(mokab_state *state);
+/* ssh = layerThickness - restingThicknessSum on both time levels (Update_ssh!, time_integration.jl:205-212) */
+int  mokab_refresh_ssh(mokab_state *state, void *cuda_stream);
+/* number of interior / boundary blocks of the fused kernel (diagnostic) */
+int  mokab_mesh_block_counts(const mokab_mesh *mesh, int64_t *interior, int64_t *boundary);
 
 #ifdef __cplusplus
 }

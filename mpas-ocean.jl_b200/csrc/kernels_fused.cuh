@@ -30,7 +30,9 @@ constexpr int kThreads = 256;
 
 template <class R>
 struct StageArgs {
-    int nE, nC;
+    int nE, nC;              // local entity counts (= strides of the slot-major arrays)
+    int nCown;               // cells computed by this rank (the rest are halo copies)
+    const int32_t *blockList;  // block ids to run (interior / boundary part) or nullptr = all
     // static (see mesh.cuh)
     const int2 *ce;
     const int32_t *eoe;      // (S2, nE) absent -> self
@@ -54,7 +56,7 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
     const int S2 = S2T ? S2T : S2rt;
     const int S = ST ? ST : Srt;
     const int nE = A.nE, nC = A.nC;
-    const int b = blockIdx.x;
+    const int b = A.blockList ? A.blockList[blockIdx.x] : blockIdx.x;
 
     // ---- edges owned by this block's cells ----------------------------------------------------------
     const int e0 = A.blkEdgeStart[b], e1 = A.blkEdgeStart[b + 1];
@@ -93,7 +95,7 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
 
     // ---- cells of this block ----------------------------------------------------------------------------
     const int cc = b * kTC + threadIdx.x;
-    if (cc < nC) {
+    if (cc < A.nCown) {
         const int n = ld_stream(A.nEoC + cc);
         const R hc = __ldg(A.hOld + cc);
         R acc = R(0);
@@ -175,6 +177,27 @@ k_build_fused_cells(int nC, int S, const double *__restrict__ area, const double
 }
 
 }  // namespace fused
+
+// ---- halo messages: combined index space [cells | edges] (device numbering) ---------------------------------
+template <class R>
+__global__ void __launch_bounds__(256)
+k_halo_pack(int n, int nC, const int32_t *__restrict__ idx, const R *__restrict__ h, const R *__restrict__ u, R *__restrict__ buf)
+{
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= n) return;
+    const int i = idx[k];
+    buf[k] = i < nC ? h[i] : u[i - nC];
+}
+template <class R>
+__global__ void __launch_bounds__(256)
+k_halo_unpack(int n, int nC, const int32_t *__restrict__ idx, const R *__restrict__ buf, R *__restrict__ h, R *__restrict__ u)
+{
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= n) return;
+    const int i = idx[k];
+    if (i < nC) h[i] = buf[k];
+    else u[i - nC] = buf[k];
+}
 
 // ---- deterministic reductions (replace sumArray, reference run_loop.jl:47-51) --------------------------
 namespace reduce {

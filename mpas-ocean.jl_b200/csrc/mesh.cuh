@@ -52,6 +52,8 @@ static inline uint64_t spread3(uint64_t v)  // 21 bits -> every third bit
 // Everything the kernels need, on the host, renumbered and 0-based (-1 = absent).
 struct HostMesh {
     int64_t nC = 0, nE = 0, nV = 0;
+    int64_t nCo = 0, nEo = 0;                  // owned (computed) cells / edges; the rest are halo copies
+    std::vector<int32_t> blkEdgeStart, blkInterior, blkBoundary;  // fused-kernel blocks (kBlockCells cells each)
     int S = 0, S2 = 0, D = 0;  // maxEdges, maxEdges2, vertexDegree
     std::vector<int32_t> permC, permE, permV;  // perm[new] = old
     std::vector<int32_t> ce;                   // (nE, 2) c1, c2 (c2 = c1 on masked edges)
@@ -66,6 +68,8 @@ struct HostMesh {
     std::vector<double> areaTri;
     bool any_boundary = false;
 };
+
+constexpr int kBlockCells = 256;  // cells per block of the fused kernel (fused::kTC)
 
 static void build_host_mesh(const mokab_mesh_desc &d, uint32_t flags, HostMesh &m)
 {
@@ -84,13 +88,21 @@ static void build_host_mesh(const mokab_mesh_desc &d, uint32_t flags, HostMesh &
 
     const int64_t nC = d.nCells, nE = d.nEdges, nV = d.nVertices;
     const int S = (int)d.maxEdges, S2 = (int)d.maxEdges2, D = nV ? (int)d.vertexDegree : 0;
-    m.nC = nC; m.nE = nE; m.nV = nV; m.S = S; m.S2 = S2; m.D = D;
+    const int64_t nCo = d.nCellsOwned > 0 ? d.nCellsOwned : nC, nEo = d.nEdgesOwned > 0 ? d.nEdgesOwned : nE;
+    MOKAB_REQUIRE(nCo <= nC && nEo <= nE, "mesh_create: nCellsOwned/nEdgesOwned exceed nCells/nEdges");
+    MOKAB_REQUIRE((nCo == nC && nEo == nE) || nV == 0, "mesh_create: decomposed meshes carry no vertex arrays");
+    m.nC = nC; m.nE = nE; m.nV = nV; m.S = S; m.S2 = S2; m.D = D; m.nCo = nCo; m.nEo = nEo;
 
     // ---- validate index ranges (the reference does none; a bad index here would fault the GPU) ----
-    for (int64_t e = 0; e < nE; ++e) {
+    for (int64_t e = nEo; e < nE; ++e) {  // halo edges: at least one local cell, first cell not owned
+        int32_t c1 = d.cellsOnEdge[2 * e], c2 = d.cellsOnEdge[2 * e + 1];
+        MOKAB_REQUIRE(c1 >= 0 && c1 <= nC && c2 >= 0 && c2 <= nC && (c1 > 0 || c2 > 0), "mesh_create: halo edge without a local cell");
+        MOKAB_REQUIRE(c1 == 0 || c1 > nCo, "mesh_create: an edge whose first cell is owned must be among the first nEdgesOwned edges");
+    }
+    for (int64_t e = 0; e < nEo; ++e) {
         int32_t c1 = d.cellsOnEdge[2 * e], c2 = d.cellsOnEdge[2 * e + 1];
         bool bnd = d.boundaryEdge && d.boundaryEdge[e];
-        MOKAB_REQUIRE(c1 >= 1 && c1 <= nC, "mesh_create: cellsOnEdge[1, e] out of range");
+        MOKAB_REQUIRE(c1 >= 1 && c1 <= nCo, "mesh_create: cellsOnEdge[1, e] out of range (must be an owned cell)");
         MOKAB_REQUIRE((c2 >= 1 && c2 <= nC) || (bnd && c2 == 0),
                       "mesh_create: cellsOnEdge[2, e] out of range (0 is allowed only on boundaryEdge edges)");
         int32_t n = d.nEdgesOnEdge[e];
@@ -101,7 +113,7 @@ static void build_host_mesh(const mokab_mesh_desc &d, uint32_t flags, HostMesh &
         }
         if (bnd) m.any_boundary = true;
     }
-    for (int64_t c = 0; c < nC; ++c) {
+    for (int64_t c = 0; c < nCo; ++c) {
         int32_t n = d.nEdgesOnCell[c];
         MOKAB_REQUIRE(n >= 1 && n <= S, "mesh_create: nEdgesOnCell out of range");
         for (int i = 0; i < n; ++i) {
@@ -144,7 +156,9 @@ static void build_host_mesh(const mokab_mesh_desc &d, uint32_t flags, HostMesh &
                 key[c] = spread3((uint64_t)((d.xCell[c] - lo[0]) * sc[0])) | spread3((uint64_t)((d.yCell[c] - lo[1]) * sc[1])) << 1 |
                          spread3((uint64_t)((d.zCell[c] - lo[2]) * sc[2])) << 2;
         }
-        std::stable_sort(m.permC.begin(), m.permC.end(), [&](int32_t a, int32_t b) { return key[a] < key[b]; });
+        auto by_key = [&](int32_t a, int32_t b) { return key[a] < key[b]; };
+        std::stable_sort(m.permC.begin(), m.permC.begin() + nCo, by_key);  // owned first ...
+        std::stable_sort(m.permC.begin() + nCo, m.permC.end(), by_key);    // ... halo copies after
     }
     std::vector<int32_t> invC(nC);
     for (int64_t i = 0; i < nC; ++i) invC[m.permC[i]] = (int32_t)i;
@@ -153,11 +167,13 @@ static void build_host_mesh(const mokab_mesh_desc &d, uint32_t flags, HostMesh &
     m.permE.resize(nE);
     std::vector<int32_t> invE(nE);
     {
-        std::vector<int64_t> start(nC + 1, 0);
-        for (int64_t e = 0; e < nE; ++e) start[invC[d.cellsOnEdge[2 * e] - 1] + 1]++;
-        for (int64_t c = 0; c < nC; ++c) start[c + 1] += start[c];
+        // bucket = new id of the first cell; halo edges without a local first cell go last (bucket nC)
+        auto bucket = [&](int64_t e) -> int64_t { int32_t c1 = d.cellsOnEdge[2 * e]; return c1 > 0 ? invC[c1 - 1] : nC; };
+        std::vector<int64_t> start(nC + 2, 0);
+        for (int64_t e = 0; e < nE; ++e) start[bucket(e) + 1]++;
+        for (int64_t c = 0; c <= nC; ++c) start[c + 1] += start[c];
         for (int64_t e = 0; e < nE; ++e) {
-            int64_t pos = start[invC[d.cellsOnEdge[2 * e] - 1]]++;
+            int64_t pos = start[bucket(e)]++;
             m.permE[pos] = (int32_t)e;
         }
         for (int64_t i = 0; i < nE; ++i) invE[m.permE[i]] = (int32_t)i;
@@ -185,11 +201,12 @@ static void build_host_mesh(const mokab_mesh_desc &d, uint32_t flags, HostMesh &
         const int64_t eo = m.permE[en];
         const bool bnd = d.boundaryEdge && d.boundaryEdge[eo];
         int32_t c1 = d.cellsOnEdge[2 * eo], c2 = d.cellsOnEdge[2 * eo + 1];
+        if (c1 < 1) c1 = c2;                                                   // halo edge, first cell not local
         m.ce[2 * en] = invC[c1 - 1];
         m.ce[2 * en + 1] = (c2 >= 1 && !bnd) ? invC[c2 - 1] : invC[c1 - 1];  // masked: zero gradient
         m.dc[en] = d.dcEdge[eo]; m.dv[en] = d.dvEdge[eo];
         m.fE[en] = d.fEdge ? d.fEdge[eo] : 0.0;  // HorzMesh.jl:257-262
-        const int n = d.nEdgesOnEdge[eo];
+        const int n = eo < nEo ? d.nEdgesOnEdge[eo] : 0;                       // halo rows are never read
         m.nEoE[en] = (uint8_t)n;
         for (int i = 0; i < n; ++i) {
             int32_t x = d.edgesOnEdge[(int64_t)S2 * eo + i];
@@ -203,7 +220,7 @@ static void build_host_mesh(const mokab_mesh_desc &d, uint32_t flags, HostMesh &
 #pragma omp parallel for schedule(static)
     for (int64_t cn = 0; cn < nC; ++cn) {
         const int64_t co = m.permC[cn];
-        const int n = d.nEdgesOnCell[co];
+        const int n = co < nCo ? d.nEdgesOnCell[co] : 0;                       // halo rows are never read
         m.nEoC[cn] = (uint8_t)n; m.area[cn] = d.areaCell[co]; m.H[cn] = d.restingThicknessSum[co];
         for (int i = 0; i < n; ++i) {
             int32_t e = d.edgesOnCell[(int64_t)S * co + i];
@@ -224,6 +241,33 @@ static void build_host_mesh(const mokab_mesh_desc &d, uint32_t flags, HostMesh &
             m.sgnV[(size_t)j * nV + vn] = d.edgeSignOnVertex ? d.edgeSignOnVertex[(int64_t)d.maxEdges * vo + j]
                                                              : ((int32_t)(vo + 1) == d.verticesOnEdge[2 * (int64_t)(e - 1)] ? -1 : 1);
         }
+    }
+    // ---- blocks of the fused kernel: block b = owned cells [b*kBlockCells, ...) + the owned edges whose first
+    //      cell lies in that range (edges are sorted by it).  A block is "boundary" when any of its stencils reads
+    //      a halo cell or halo edge; interior blocks can run while the halo exchange is in flight. ---------------
+    const int nb = (int)((nCo + kBlockCells - 1) / kBlockCells);
+    m.blkEdgeStart.assign(nb + 1, 0);
+    {
+        int64_t e = 0;
+        for (int b = 0; b <= nb; ++b) {
+            const int64_t cfirst = (int64_t)b * kBlockCells;
+            while (e < nEo && m.ce[2 * e] < cfirst) ++e;
+            m.blkEdgeStart[b] = (int32_t)e;
+        }
+        m.blkEdgeStart[nb] = (int32_t)nEo;
+    }
+    for (int b = 0; b < nb; ++b) {
+        bool halo = false;
+        for (int64_t e = m.blkEdgeStart[b]; e < m.blkEdgeStart[b + 1] && !halo; ++e) {
+            if (m.ce[2 * e + 1] >= nCo) halo = true;
+            for (int i = 0; i < m.nEoE[e] && !halo; ++i) halo = m.eoe[(size_t)i * nE + e] >= nEo;
+        }
+        for (int64_t c = (int64_t)b * kBlockCells; c < std::min<int64_t>(nCo, (int64_t)(b + 1) * kBlockCells) && !halo; ++c)
+            for (int i = 0; i < m.nEoC[c] && !halo; ++i) {
+                const int64_t e = m.eoc[(size_t)i * nC + c];
+                halo = e >= nEo || m.ce[2 * e] >= nCo || m.ce[2 * e + 1] >= nCo;
+            }
+        (halo ? m.blkBoundary : m.blkInterior).push_back(b);
     }
 }
 
@@ -249,11 +293,15 @@ struct mokab_mesh {
     mokab::DevBuf<double> woe, dc, dv, fE, area, H, areaTri;
     // fused-path arrays
     mokab::DevBuf<int32_t> eoeF, eocF;   // absent -> self / sign in bit 0
-    mokab::DevBuf<int32_t> blkEdgeStart; // per block of FUSED_TC cells: first owned edge
-    int fusedBlocks = 0;
+    mokab::DevBuf<int32_t> blkEdgeStart; // per block of kBlockCells cells: first owned edge
+    mokab::DevBuf<int32_t> blkInterior, blkBoundary;  // block ids by part
+    int64_t nCo = 0, nEo = 0;            // owned cells / edges (== nC / nE without decomposition)
+    int fusedBlocks = 0, nInterior = 0, nBoundary = 0;
+    std::vector<int32_t> hBlkEdgeStart, hBlkInterior, hBlkBoundary;  // host copies (halo_setup re-classifies)
+    mokab::DevBuf<int32_t> haloSend, haloRecv;  // combined [cells | edges] indices, device numbering
+    bool halo_ready = false;
     mokab::FusedMesh<double> f64;
     mokab::FusedMesh<float> f32;
-    mokab::HostMesh host;  // kept for lazily building the other precision
     int64_t device_bytes() const
     {
         return (int64_t)(ce.bytes() + eoe.bytes() + eoc.bytes() + sgnC.bytes() + eov.bytes() + sgnV.bytes() + dPermC.bytes() +

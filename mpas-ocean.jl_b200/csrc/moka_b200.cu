@@ -80,21 +80,14 @@ static void upload_mesh(mokab_ctx *ctx, HostMesh &hm, mokab_mesh *m)
     m->area.upload(hm.area, s); m->H.upload(hm.H, s);
     m->eov.upload(hm.eov, s); m->sgnV.upload(hm.sgnV, s); m->areaTri.upload(hm.areaTri, s);
     m->dPermC.upload(hm.permC, s); m->dPermE.upload(hm.permE, s); m->dPermV.upload(hm.permV, s);
-    // per-block edge ranges of the fused kernel: edges are sorted by owner cell, block b owns cells
-    // [b*kTC, (b+1)*kTC) and the edges whose owner lies in that range.
-    const int nb = (int)((hm.nC + fused::kTC - 1) / fused::kTC);
-    std::vector<int32_t> start(nb + 1, 0);
-    {
-        int64_t e = 0;
-        for (int b = 0; b <= nb; ++b) {
-            const int64_t cfirst = (int64_t)b * fused::kTC;
-            while (e < hm.nE && hm.ce[2 * e] < cfirst) ++e;
-            start[b] = (int32_t)e;
-        }
-        start[nb] = (int32_t)hm.nE;
-    }
-    m->blkEdgeStart.upload(start, s);
-    m->fusedBlocks = nb;
+    m->nCo = hm.nCo; m->nEo = hm.nEo;
+    m->blkEdgeStart.upload(hm.blkEdgeStart, s);
+    m->blkInterior.upload(hm.blkInterior, s);
+    m->blkBoundary.upload(hm.blkBoundary, s);
+    m->fusedBlocks = (int)hm.blkEdgeStart.size() - 1;
+    m->nInterior = (int)hm.blkInterior.size();
+    m->nBoundary = (int)hm.blkBoundary.size();
+    m->hBlkEdgeStart.swap(hm.blkEdgeStart); m->hBlkInterior.swap(hm.blkInterior); m->hBlkBoundary.swap(hm.blkBoundary);
     m->permC.swap(hm.permC); m->permE.swap(hm.permE); m->permV.swap(hm.permV);
     MOKAB_CUDA(cudaStreamSynchronize(s));
 }
@@ -291,39 +284,101 @@ static void step_rk4_unfused(mokab_state *st, double dt)
 
 // ---- fused RK4 ------------------------------------------------------------------------------------------------
 template <class R, int STAGE>
-static void launch_stage(mokab_ctx *ctx, const mokab_mesh *m, const fused::StageArgs<R> &A)
+static void launch_stage(mokab_ctx *ctx, const mokab_mesh *m, fused::StageArgs<R> A, int part = MOKAB_PART_ALL,
+                         cudaStream_t stream = nullptr)
 {
-    const int grid = m->fusedBlocks;
+    int grid = m->fusedBlocks;
+    A.blockList = nullptr;
+    if (part == MOKAB_PART_INTERIOR) { grid = m->nInterior; A.blockList = m->blkInterior.p; }
+    if (part == MOKAB_PART_BOUNDARY) { grid = m->nBoundary; A.blockList = m->blkBoundary.p; }
+    if (grid == 0) return;
+    cudaStream_t s = stream ? stream : ctx->stream;
     if (m->S2 == 10 && m->S == 6)
-        LAUNCH(ctx, (fused::k_rk_stage<R, STAGE, 10, 6>), grid, fused::kThreads, A, m->S2, m->S);
+        fused::k_rk_stage<R, STAGE, 10, 6><<<grid, fused::kThreads, 0, s>>>(A, m->S2, m->S);
     else
-        LAUNCH(ctx, (fused::k_rk_stage<R, STAGE, 0, 0>), grid, fused::kThreads, A, m->S2, m->S);
+        fused::k_rk_stage<R, STAGE, 0, 0><<<grid, fused::kThreads, 0, s>>>(A, m->S2, m->S);
+    MOKAB_CUDA(cudaGetLastError());
+    ctx->launches++;
+}
+
+template <class R>
+static fused::StageArgs<R> stage_args(mokab_state *st, double dt, int p, int stage)
+{
+    mokab_mesh *m = const_cast<mokab_mesh *>(st->mesh);
+    StateT<R> *t = typed<R>(st);
+    FusedMesh<R> &fm = fused_of<R>(m);
+    fused::StageArgs<R> A;
+    A.nE = (int)m->nE; A.nC = (int)m->nC; A.nCown = (int)m->nCo; A.blockList = nullptr;
+    A.ce = m->ce.p; A.eoe = m->eoeF.p; A.eoc = m->eocF.p; A.nEoE = m->nEoE.p; A.nEoC = m->nEoC.p;
+    A.blkEdgeStart = m->blkEdgeStart.p;
+    A.gdc = fm.gdc.p; A.wf = fm.wf.p; A.dv = fm.dv.p; A.invArea = fm.invArea.p; A.H = fm.H.p;
+    A.uCur = t->u[p].p; A.hCur = t->h[p].p; A.uAcc = t->u[1 - p].p; A.hAcc = t->h[1 - p].p;
+    const double a[4] = {dt / 2.0, dt / 2.0, dt, 0.0};                  // time_integration.jl:77
+    const double b[4] = {dt / 6.0, dt / 3.0, dt / 3.0, dt / 6.0};       // time_integration.jl:78
+    A.a = (R)a[stage - 1]; A.b = (R)b[stage - 1];
+    switch (stage) {
+    case 1: A.uOld = t->u[p].p;  A.hOld = t->h[p].p;  A.uOut = t->uP[0].p; A.hOut = t->hP[0].p; break;  // provisional == current
+    case 2: A.uOld = t->uP[0].p; A.hOld = t->hP[0].p; A.uOut = t->uP[1].p; A.hOut = t->hP[1].p; break;
+    case 3: A.uOld = t->uP[1].p; A.hOld = t->hP[1].p; A.uOut = t->uP[0].p; A.hOut = t->hP[0].p; break;
+    default: A.uOld = t->uP[0].p; A.hOld = t->hP[0].p; A.uOut = nullptr; A.hOut = nullptr; break;
+    }
+    return A;
+}
+
+// the (u, h) buffers holding the output of RK stage `stage` (0 = the current state) for step parity p
+template <class R>
+static void stage_output(mokab_state *st, int stage, R **u, R **h)
+{
+    StateT<R> *t = typed<R>(st);
+    const int p = st->cur;
+    switch (stage) {
+    case 0: *u = t->u[p].p; *h = t->h[p].p; break;
+    case 1: case 3: *u = t->uP[0].p; *h = t->hP[0].p; break;
+    case 2: *u = t->uP[1].p; *h = t->hP[1].p; break;
+    default: *u = t->u[1 - p].p; *h = t->h[1 - p].p; break;
+    }
+}
+
+template <class R>
+static void run_stage(mokab_state *st, double dt, int stage, int part, cudaStream_t stream)
+{
+    mokab_ctx *ctx = st->ctx; const mokab_mesh *m = st->mesh;
+    ensure_fused<R>(const_cast<mokab_mesh *>(m));
+    fused::StageArgs<R> A = stage_args<R>(st, dt, st->cur, stage);
+    switch (stage) {
+    case 1: launch_stage<R, 1>(ctx, m, A, part, stream); break;
+    case 2: case 3: launch_stage<R, 2>(ctx, m, A, part, stream); break;
+    default: launch_stage<R, 4>(ctx, m, A, part, stream); break;
+    }
+}
+
+template <class R>
+static void halo_pack(mokab_state *st, int stage, void *buf, cudaStream_t stream, bool unpack)
+{
+    mokab_ctx *ctx = st->ctx; const mokab_mesh *m = st->mesh;
+    R *u, *h;
+    stage_output<R>(st, stage, &u, &h);
+    cudaStream_t s = stream ? stream : ctx->stream;
+    if (!unpack) {
+        const int n = (int)m->haloSend.n;
+        if (n) k_halo_pack<R><<<nblk(n), 256, 0, s>>>(n, (int)m->nC, m->haloSend.p, (const R *)h, (const R *)u, (R *)buf);
+    } else {
+        const int n = (int)m->haloRecv.n;
+        if (n) k_halo_unpack<R><<<nblk(n), 256, 0, s>>>(n, (int)m->nC, m->haloRecv.p, (const R *)buf, h, u);
+    }
+    MOKAB_CUDA(cudaGetLastError());
+    ctx->launches++;
 }
 
 // one RK4 step reading time level `p`, writing level 1-p (four launches)
 template <class R>
 static void enqueue_rk4_step(mokab_state *st, double dt, int p)
 {
-    mokab_ctx *ctx = st->ctx; mokab_mesh *m = const_cast<mokab_mesh *>(st->mesh);
-    StateT<R> *t = typed<R>(st);
-    FusedMesh<R> &fm = fused_of<R>(m);
-    fused::StageArgs<R> A;
-    A.nE = (int)m->nE; A.nC = (int)m->nC;
-    A.ce = m->ce.p; A.eoe = m->eoeF.p; A.eoc = m->eocF.p; A.nEoE = m->nEoE.p; A.nEoC = m->nEoC.p;
-    A.blkEdgeStart = m->blkEdgeStart.p;
-    A.gdc = fm.gdc.p; A.wf = fm.wf.p; A.dv = fm.dv.p; A.invArea = fm.invArea.p; A.H = fm.H.p;
-    A.uCur = t->u[p].p; A.hCur = t->h[p].p; A.uAcc = t->u[1 - p].p; A.hAcc = t->h[1 - p].p;
-    const double a[3] = {dt / 2.0, dt / 2.0, dt};                       // time_integration.jl:77
-    const double b[4] = {dt / 6.0, dt / 3.0, dt / 3.0, dt / 6.0};       // time_integration.jl:78
-    // stage 1: provisional == current
-    A.uOld = t->u[p].p; A.hOld = t->h[p].p; A.uOut = t->uP[0].p; A.hOut = t->hP[0].p; A.a = (R)a[0]; A.b = (R)b[0];
-    launch_stage<R, 1>(ctx, m, A);
-    A.uOld = t->uP[0].p; A.hOld = t->hP[0].p; A.uOut = t->uP[1].p; A.hOut = t->hP[1].p; A.a = (R)a[1]; A.b = (R)b[1];
-    launch_stage<R, 2>(ctx, m, A);
-    A.uOld = t->uP[1].p; A.hOld = t->hP[1].p; A.uOut = t->uP[0].p; A.hOut = t->hP[0].p; A.a = (R)a[2]; A.b = (R)b[2];
-    launch_stage<R, 2>(ctx, m, A);
-    A.uOld = t->uP[0].p; A.hOld = t->hP[0].p; A.uOut = nullptr; A.hOut = nullptr; A.a = R(0); A.b = (R)b[3];
-    launch_stage<R, 4>(ctx, m, A);
+    mokab_ctx *ctx = st->ctx; const mokab_mesh *m = st->mesh;
+    launch_stage<R, 1>(ctx, m, stage_args<R>(st, dt, p, 1));
+    launch_stage<R, 2>(ctx, m, stage_args<R>(st, dt, p, 2));
+    launch_stage<R, 2>(ctx, m, stage_args<R>(st, dt, p, 3));
+    launch_stage<R, 4>(ctx, m, stage_args<R>(st, dt, p, 4));
 }
 
 template <class R>
@@ -358,13 +413,18 @@ static void build_graphs(mokab_state *st, double dt)
 }
 
 template <class R>
-static void refresh_ssh(mokab_state *st)
+static void refresh_ssh(mokab_state *st, cudaStream_t stream = nullptr)
 {
     mokab_ctx *ctx = st->ctx; mokab_mesh *m = const_cast<mokab_mesh *>(st->mesh);
     StateT<R> *t = typed<R>(st);
+    ensure_fused<R>(m);
     FusedMesh<R> &fm = fused_of<R>(m);
-    for (int l = 0; l < 2; ++l)
-        LAUNCH(ctx, k_update_ssh<R>, nblk(m->nC), 256, m->nC, (const R *)t->h[l].p, (const R *)fm.H.p, t->ssh[l].p);
+    cudaStream_t s = stream ? stream : ctx->stream;
+    for (int l = 0; l < 2; ++l) {
+        k_update_ssh<R><<<nblk(m->nC), 256, 0, s>>>(m->nC, (const R *)t->h[l].p, (const R *)fm.H.p, t->ssh[l].p);
+        MOKAB_CUDA(cudaGetLastError());
+        ctx->launches++;
+    }
 }
 
 template <class R>
@@ -372,6 +432,8 @@ static void run_rk4_fused(mokab_state *st, double dt, int64_t nsteps)
 {
     mokab_ctx *ctx = st->ctx;
     StateT<R> *t = typed<R>(st);
+    MOKAB_REQUIRE(st->mesh->nCo == st->mesh->nC && st->mesh->nEo == st->mesh->nE,
+                  "timestep_rk4: this mesh has halo entities; drive it with mokab_rk4_stage + mokab_halo_pack/unpack");
     ensure_fused<R>(const_cast<mokab_mesh *>(st->mesh));
     if (!t->graphs_ready || t->graph_dt != dt) build_graphs<R>(st, dt);
     int64_t left = nsteps;
@@ -397,10 +459,10 @@ static void do_reduce(mokab_state *st, int which, double *out)
     FusedMesh<R> &fm = fused_of<R>(m);
     const int c = st->cur;
     MOKAB_REQUIRE(which >= 0 && which <= 2, "reduce: unknown reduction id");
-    LAUNCH(ctx, reduce::k_cells<R>, reduce::kBlocks, reduce::kThreads, which, m->nC, (const R *)t->h[c].p, (const R *)fm.H.p,
+    LAUNCH(ctx, reduce::k_cells<R>, reduce::kBlocks, reduce::kThreads, which, m->nCo, (const R *)t->h[c].p, (const R *)fm.H.p,
            (const double *)m->area.p, t->partial.p);
     if (which == MOKAB_SUM_ENERGY)
-        LAUNCH(ctx, reduce::k_edges_ke<R>, reduce::kBlocks, reduce::kThreads, m->nE, (const int2 *)m->ce.p, (const double *)m->dc.p,
+        LAUNCH(ctx, reduce::k_edges_ke<R>, reduce::kBlocks, reduce::kThreads, m->nEo, (const int2 *)m->ce.p, (const double *)m->dc.p,
                (const double *)m->dv.p, (const R *)t->u[c].p, (const R *)t->h[c].p, t->partial.p);
     LAUNCH(ctx, reduce::k_final, 1, reduce::kThreads, (const double *)t->partial.p, t->result.p);
     MOKAB_CUDA(cudaMemcpyAsync(out, t->result.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -759,6 +821,115 @@ int mokab_reduce(mokab_state *state, int which, double *out)
         MOKAB_REQUIRE(state && out, "reduce: NULL argument");
         state->ctx->bind();
         if (state->dtype == MOKAB_F64) do_reduce<double>(state, which, out); else do_reduce<float>(state, which, out);
+    });
+}
+
+// ---- staged RK4 + halo messages (domain-decomposed runs) ----------------------------------------------------------
+int mokab_halo_setup(mokab_mesh *m, int64_t n_send, const int32_t *send_idx, int64_t n_recv, const int32_t *recv_idx)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(m && (n_send == 0 || send_idx) && (n_recv == 0 || recv_idx) && n_send >= 0 && n_recv >= 0,
+                      "halo_setup: bad argument");
+        m->ctx->bind();
+        std::vector<int32_t> invC(m->nC), invE(m->nE);
+        for (int64_t i = 0; i < m->nC; ++i) invC[m->permC[i]] = (int32_t)i;
+        for (int64_t i = 0; i < m->nE; ++i) invE[m->permE[i]] = (int32_t)i;
+        auto conv = [&](int64_t n, const int32_t *idx, bool send, std::vector<int32_t> &out) {
+            out.resize(n);
+            for (int64_t k = 0; k < n; ++k) {
+                const int64_t i = idx[k];
+                MOKAB_REQUIRE(i >= 0 && i < m->nC + m->nE, "halo_setup: index out of range");
+                const bool cell = i < m->nC;
+                const int32_t dev = cell ? invC[i] : invE[i - m->nC];
+                const bool owned = cell ? dev < m->nCo : dev < m->nEo;
+                MOKAB_REQUIRE(owned == send, send ? "halo_setup: send list names a halo entity" : "halo_setup: recv list names an owned entity");
+                out[k] = cell ? dev : (int32_t)(m->nC + dev);
+            }
+        };
+        std::vector<int32_t> s, r;
+        conv(n_send, send_idx, true, s);
+        conv(n_recv, recv_idx, false, r);
+        // blocks holding a send entity must run in the boundary part
+        std::vector<char> isB(m->fusedBlocks, 0);
+        for (int32_t b : m->hBlkBoundary) isB[b] = 1;
+        for (int32_t i : s) {
+            int b;
+            if (i < m->nC) b = i / kBlockCells;
+            else b = (int)(std::upper_bound(m->hBlkEdgeStart.begin(), m->hBlkEdgeStart.end(), (int32_t)(i - m->nC)) - m->hBlkEdgeStart.begin()) - 1;
+            if (b >= 0 && b < m->fusedBlocks) isB[b] = 1;
+        }
+        m->hBlkInterior.clear(); m->hBlkBoundary.clear();
+        for (int b = 0; b < m->fusedBlocks; ++b) (isB[b] ? m->hBlkBoundary : m->hBlkInterior).push_back(b);
+        cudaStream_t st = m->ctx->stream;
+        m->blkInterior.upload(m->hBlkInterior, st); m->blkBoundary.upload(m->hBlkBoundary, st);
+        m->nInterior = (int)m->hBlkInterior.size(); m->nBoundary = (int)m->hBlkBoundary.size();
+        m->haloSend.upload(s, st);
+        m->haloRecv.upload(r, st);
+        MOKAB_CUDA(cudaStreamSynchronize(st));
+        m->halo_ready = true;
+    });
+}
+
+int mokab_halo_pack(mokab_state *state, int stage, void *send_buf_device, void *cuda_stream)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(state && state->mesh->halo_ready, "halo_pack: call mokab_halo_setup first");
+        MOKAB_REQUIRE(stage >= 0 && stage <= 4, "halo_pack: stage must be 0..4");
+        MOKAB_REQUIRE(send_buf_device || state->mesh->haloSend.n == 0, "halo_pack: NULL buffer");
+        state->ctx->bind();
+        if (state->dtype == MOKAB_F64) halo_pack<double>(state, stage, send_buf_device, (cudaStream_t)cuda_stream, false);
+        else halo_pack<float>(state, stage, send_buf_device, (cudaStream_t)cuda_stream, false);
+    });
+}
+
+int mokab_halo_unpack(mokab_state *state, int stage, const void *recv_buf_device, void *cuda_stream)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(state && state->mesh->halo_ready, "halo_unpack: call mokab_halo_setup first");
+        MOKAB_REQUIRE(stage >= 0 && stage <= 4, "halo_unpack: stage must be 0..4");
+        MOKAB_REQUIRE(recv_buf_device || state->mesh->haloRecv.n == 0, "halo_unpack: NULL buffer");
+        state->ctx->bind();
+        if (state->dtype == MOKAB_F64) halo_pack<double>(state, stage, const_cast<void *>(recv_buf_device), (cudaStream_t)cuda_stream, true);
+        else halo_pack<float>(state, stage, const_cast<void *>(recv_buf_device), (cudaStream_t)cuda_stream, true);
+    });
+}
+
+int mokab_rk4_stage(mokab_state *state, double dt, int stage, int part, void *cuda_stream)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(state, "rk4_stage: state is NULL");
+        MOKAB_REQUIRE(stage >= 1 && stage <= 4, "rk4_stage: stage must be 1..4");
+        MOKAB_REQUIRE(part >= MOKAB_PART_ALL && part <= MOKAB_PART_BOUNDARY, "rk4_stage: unknown part");
+        state->ctx->bind();
+        if (state->dtype == MOKAB_F64) run_stage<double>(state, dt, stage, part, (cudaStream_t)cuda_stream);
+        else run_stage<float>(state, dt, stage, part, (cudaStream_t)cuda_stream);
+    });
+}
+
+int mokab_rk4_finish_step(mokab_state *state)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(state, "rk4_finish_step: state is NULL");
+        state->cur = 1 - state->cur;
+    });
+}
+
+int mokab_refresh_ssh(mokab_state *state, void *cuda_stream)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(state, "refresh_ssh: state is NULL");
+        state->ctx->bind();
+        if (state->dtype == MOKAB_F64) refresh_ssh<double>(state, (cudaStream_t)cuda_stream);
+        else refresh_ssh<float>(state, (cudaStream_t)cuda_stream);
+    });
+}
+
+int mokab_mesh_block_counts(const mokab_mesh *mesh, int64_t *interior, int64_t *boundary)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(mesh && interior && boundary, "mesh_block_counts: NULL argument");
+        *interior = mesh->nInterior;
+        *boundary = mesh->nBoundary;
     });
 }
 

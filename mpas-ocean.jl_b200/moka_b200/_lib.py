@@ -17,6 +17,7 @@ F64, F32 = 0, 1
 SUM_SSH2, SUM_MASS, SUM_ENERGY = range(3)
 CELLS, EDGES, VERTICES = range(3)
 RK4_FUSED, RK4_UNFUSED = 0, 1
+PART_ALL, PART_INTERIOR, PART_BOUNDARY = 0, 1, 2
 MESH_RENUMBER = 1
 
 _I32P, _F64P = C.POINTER(C.c_int32), C.POINTER(C.c_double)
@@ -34,7 +35,8 @@ _DESC_PTRS = [
 
 
 class MeshDesc(C.Structure):
-    _fields_ = [(n, C.c_int64) for n in ("nCells", "nEdges", "nVertices", "maxEdges", "maxEdges2", "vertexDegree")] + _DESC_PTRS
+    _fields_ = ([(n, C.c_int64) for n in ("nCells", "nEdges", "nVertices", "maxEdges", "maxEdges2", "vertexDegree")] + _DESC_PTRS
+                + [("nCellsOwned", C.c_int64), ("nEdgesOwned", C.c_int64)])
 
 
 class MokaError(RuntimeError):
@@ -52,6 +54,8 @@ SYMBOLS = [
     "mokab_diagnostic_compute", "mokab_compute_normal_velocity_tendency", "mokab_compute_layer_thickness_tendency",
     "mokab_gradient_on_edge", "mokab_divergence_on_cell", "mokab_curl_on_vertex", "mokab_interpolate_cell2edge",
     "mokab_timestep_forward_euler", "mokab_timestep_rk4", "mokab_reduce",
+    "mokab_halo_setup", "mokab_halo_pack", "mokab_halo_unpack", "mokab_rk4_stage", "mokab_rk4_finish_step",
+    "mokab_refresh_ssh", "mokab_mesh_block_counts",
 ]
 
 
@@ -78,6 +82,10 @@ def lib():
             "mokab_curl_on_vertex": [vp, vp, _F64P, _F64P], "mokab_interpolate_cell2edge": [vp, vp, _F64P, _F64P],
             "mokab_timestep_forward_euler": [vp, dbl, i64], "mokab_timestep_rk4": [vp, dbl, i64, C.c_int],
             "mokab_reduce": [vp, C.c_int, C.POINTER(dbl)],
+            "mokab_halo_setup": [vp, i64, _I32P, i64, _I32P], "mokab_halo_pack": [vp, C.c_int, vp, vp],
+            "mokab_halo_unpack": [vp, C.c_int, vp, vp], "mokab_rk4_stage": [vp, dbl, C.c_int, C.c_int, vp],
+            "mokab_rk4_finish_step": [vp], "mokab_refresh_ssh": [vp, vp],
+            "mokab_mesh_block_counts": [vp, C.POINTER(i64), C.POINTER(i64)],
         }
         for name, args in sig.items():
             fn = getattr(L, name)

@@ -105,6 +105,9 @@ class Mesh:
         d = L.MeshDesc()
         d.nCells, d.nEdges, d.nVertices = self.nCells, self.nEdges, self.nVertices
         d.maxEdges, d.maxEdges2, d.vertexDegree = self.maxEdges, self.maxEdges2, self.vertexDegree
+        self.nCellsOwned = int(fields.get("nCellsOwned", 0)) or self.nCells
+        self.nEdgesOwned = int(fields.get("nEdgesOwned", 0)) or self.nEdges
+        d.nCellsOwned, d.nEdgesOwned = self.nCellsOwned, self.nEdgesOwned
         keep = []
         rts = fields.get("restingThicknessSum")
         if rts is None:                                               # VertMesh.jl:73
@@ -134,6 +137,17 @@ class Mesh:
         out = np.empty(n, np.int32)
         L.check(L.lib().mokab_mesh_get_perm(self.handle, k, out.ctypes.data_as(L._I32P)))
         return out
+
+    def halo_setup(self, send_idx, recv_idx) -> None:
+        """Register the halo message layout (combined [cells | edges] local indices, 0-based)."""
+        s = np.ascontiguousarray(send_idx, dtype=np.int32)
+        r = np.ascontiguousarray(recv_idx, dtype=np.int32)
+        L.check(L.lib().mokab_halo_setup(self.handle, s.size, s.ctypes.data_as(L._I32P), r.size, r.ctypes.data_as(L._I32P)))
+
+    def block_counts(self):
+        a, b = C.c_int64(), C.c_int64()
+        L.check(L.lib().mokab_mesh_block_counts(self.handle, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def device_bytes(self) -> int:
         n = C.c_int64()

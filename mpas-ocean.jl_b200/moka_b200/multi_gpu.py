@@ -1,0 +1,278 @@
+"""One process per GPU: domain-decomposed RK4 with the halo exchange overlapped with interior compute.
+
+The reference has no multi-device path; this follows BASELINE.json's north_star:
+owned/halo cell and edge layers (partition.py), one packed message per neighbour and RK stage
+exchanged with NCCL over NVLink (`torch.distributed` is the plumbing), overlapped with the interior
+blocks of the same stage:
+
+    per stage s:   compute stream:  wait X[s-1] -> BOUNDARY blocks(s) -> record B[s] -> INTERIOR blocks(s)
+                   comm stream:     wait B[s] -> pack(s) -> all_to_all -> unpack(s) -> record X[s]
+
+BOUNDARY blocks are those whose stencils read a halo entity or that hold an entity a neighbour needs
+(mokab_halo_setup), so the message of stage s leaves while the bulk of stage s is still computing and
+is in place before stage s+1 touches the halo.  Reductions are per-rank partial sums over owned
+entities + all_reduce.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import time
+
+import numpy as np
+
+from . import _lib as L
+from . import api, partition
+
+
+class HaloExchanger:
+    """Packed all-to-all of halo messages (works for NCCL/CUDA and gloo/CPU tensors)."""
+
+    def __init__(self, send_counts, recv_counts, dtype, device, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group = torch, dist, group
+        self.send_counts, self.recv_counts = list(send_counts), list(recv_counts)
+        self.send = torch.zeros(max(1, sum(send_counts)), dtype=dtype, device=device)
+        self.recv = torch.zeros(max(1, sum(recv_counts)), dtype=dtype, device=device)
+        self.rank = dist.get_rank(group)
+        self.use_a2a = device != "cpu" and str(device) != "cpu"
+
+    def exchange(self) -> None:
+        ns, nr = sum(self.send_counts), sum(self.recv_counts)
+        if self.use_a2a:
+            self.dist.all_to_all_single(self.recv[:nr], self.send[:ns], self.recv_counts, self.send_counts, group=self.group)
+            return
+        ops, so, ro = [], 0, 0
+        for q, (cs, cr) in enumerate(zip(self.send_counts, self.recv_counts)):
+            if cr:
+                ops.append(self.dist.P2POp(self.dist.irecv, self.recv[ro:ro + cr], q, group=self.group))
+            if cs:
+                ops.append(self.dist.P2POp(self.dist.isend, self.send[so:so + cs], q, group=self.group))
+            so, ro = so + cs, ro + cr
+        if ops:
+            for w in self.dist.batch_isend_irecv(ops):
+                w.wait()
+
+
+class DecomposedModel:
+    """This rank's share of the mesh on its GPU + the stage/exchange schedule."""
+
+    def __init__(self, loc: dict, state, backend: api.B200, device_index: int, dtype=np.float64, group=None, overlap=True):
+        import torch
+        self.torch = torch
+        self.loc, self.backend, self.overlap = loc, backend, overlap
+        self.nparts = loc["nparts"]
+        self.mesh = api.Mesh(loc, backend)
+        sidx, scnt, ridx, rcnt = partition.flat_halo(loc, self.nparts)
+        self.mesh.halo_setup(sidx, ridx)
+        ssh, u, h = state
+        self.prog = api.PrognosticVars(np.asarray(ssh, dtype), np.asarray(u, dtype), np.asarray(h, dtype), 2, self.mesh)
+        tdt = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
+        self.dev = torch.device("cuda", device_index)
+        self.ex = HaloExchanger(scnt, rcnt, tdt, self.dev, group)
+        self.compute = torch.cuda.Stream(self.dev)
+        self.comm = torch.cuda.Stream(self.dev)
+        self.ev_b = [torch.cuda.Event() for _ in range(4)]
+        self.ev_x = torch.cuda.Event()
+        self.ev_x.record(self.compute)
+        self.handle = self.prog.dev.handle
+
+    def _stage(self, dt, s, part, stream):
+        L.check(L.lib().mokab_rk4_stage(self.handle, float(dt), s, part, C.c_void_p(stream.cuda_stream)))
+
+    def _exchange(self, s, stream):
+        lib = L.lib()
+        with self.torch.cuda.stream(stream):
+            L.check(lib.mokab_halo_pack(self.handle, s, C.c_void_p(self.ex.send.data_ptr()), C.c_void_p(stream.cuda_stream)))
+            self.ex.exchange()
+            L.check(lib.mokab_halo_unpack(self.handle, s, C.c_void_p(self.ex.recv.data_ptr()), C.c_void_p(stream.cuda_stream)))
+
+    def step(self, dt: float, nsteps: int = 1) -> None:
+        for _ in range(nsteps):
+            for s in (1, 2, 3, 4):
+                if self.overlap:
+                    self.compute.wait_event(self.ev_x)
+                    self._stage(dt, s, L.PART_BOUNDARY, self.compute)
+                    self.ev_b[s - 1].record(self.compute)
+                    self._stage(dt, s, L.PART_INTERIOR, self.compute)
+                    self.comm.wait_event(self.ev_b[s - 1])
+                    self._exchange(s, self.comm)
+                    self.ev_x.record(self.comm)
+                else:
+                    self._stage(dt, s, L.PART_ALL, self.compute)
+                    self._exchange(s, self.compute)
+            L.check(L.lib().mokab_rk4_finish_step(self.handle))
+        self.compute.wait_event(self.ev_x)
+
+    def finish(self) -> None:
+        L.check(L.lib().mokab_refresh_ssh(self.handle, C.c_void_p(self.compute.cuda_stream)))
+        self.compute.synchronize()
+        self.comm.synchronize()
+
+    def owned(self, field: str) -> np.ndarray:
+        a = getattr(self.prog, field)
+        n = self.loc["nCellsOwned"] if field in ("ssh", "layerThickness") else self.loc["nEdgesOwned"]
+        return a[:n]
+
+    def reduce(self, which: str) -> float:
+        import torch.distributed as dist
+        v = self.torch.tensor([api.reduce_sum(self.prog, which)], dtype=self.torch.float64, device=self.dev)
+        dist.all_reduce(v)
+        return float(v.item())
+
+
+def local_state(loc: dict, ssh, u, h):
+    return ssh[loc["cellsGlobal"]], u[loc["edgesGlobal"]], h[loc["cellsGlobal"]]
+
+
+def gather_owned(model: DecomposedModel, nC: int, nE: int):
+    """Assemble the global (ssh, u, h) on every rank from the owned parts (test/diagnostic helper)."""
+    import torch
+    import torch.distributed as dist
+    loc = model.loc
+    out = []
+    for field, n, ids, no in (("ssh", nC, loc["cellsGlobal"], loc["nCellsOwned"]),
+                              ("normalVelocity", nE, loc["edgesGlobal"], loc["nEdgesOwned"]),
+                              ("layerThickness", nC, loc["cellsGlobal"], loc["nCellsOwned"])):
+        g = torch.zeros(n, dtype=torch.float64, device=model.dev)
+        g[torch.as_tensor(ids[:no], device=model.dev)] = torch.as_tensor(np.asarray(model.owned(field), np.float64), device=model.dev)
+        dist.all_reduce(g)
+        out.append(g.cpu().numpy())
+    return out
+
+
+# ---- bench leg for torchrun (N > 1) -------------------------------------------------------------------------
+def _share_locals(args, rank, world, nx, dtype):
+    """Rank 0 builds the global mesh, decomposes it and hands every rank its local mesh through /dev/shm."""
+    import torch.distributed as dist
+    tag = f"/dev/shm/mokab_{os.environ.get('MASTER_PORT', '0')}_{nx}_{world}"
+    t0 = time.time()
+    if rank == 0:
+        from . import planar_hex
+        m = planar_hex.periodic_hex(nx, nx, 1.0e7 / nx, with_dual=False)
+        ssh, u, h = api.inertialGravityWave(m).initial_state()
+        locs = partition.decompose(m, world)
+        for r, loc in enumerate(locs):
+            ls = local_state(loc, ssh, u, h)
+            flat = {k: v for k, v in loc.items() if isinstance(v, np.ndarray)}
+            meta = {k: v for k, v in loc.items() if not isinstance(v, (np.ndarray, dict))}
+            halo = loc["halo"]
+            for q in halo["peers"]:
+                flat[f"halo_send_{q}"], flat[f"halo_recv_{q}"] = halo["send"][q], halo["recv"][q]
+            meta["peers"] = halo["peers"]
+            flat["state_ssh"], flat["state_u"], flat["state_h"] = ls
+            np.savez(f"{tag}_{r}.npz", meta=json.dumps(meta), **flat)
+        del m, locs
+    dist.barrier()
+    z = np.load(f"{tag}_{rank}.npz")
+    meta = json.loads(str(z["meta"]))
+    loc = {k: z[k] for k in z.files if k != "meta" and not k.startswith(("halo_", "state_"))}
+    loc.update({k: v for k, v in meta.items() if k != "peers"})
+    loc["halo"] = {"peers": meta["peers"], "send": {q: z[f"halo_send_{q}"] for q in meta["peers"]},
+                   "recv": {q: z[f"halo_recv_{q}"] for q in meta["peers"]}}
+    state = (z["state_ssh"], z["state_u"], z["state_h"])
+    dist.barrier()
+    if rank == 0:
+        for r in range(world):
+            try:
+                os.remove(f"{tag}_{r}.npz")
+            except OSError:
+                pass
+    return loc, state, time.time() - t0
+
+
+def bench_main(args, rank, world, local):
+    import torch
+    import torch.distributed as dist
+    from bench import ALGO_BYTES_PER_CELL_STEP, WORKLOADS, ClockSampler, measured_peak_gbs
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    nx = WORKLOADS[args.workload]
+    npdt = np.float64 if args.dtype == "f64" else np.float32
+    loc, state, t_setup = _share_locals(args, rank, world, nx, npdt)
+    nC_glob = nx * nx
+    dt = api.cfl_dt(1.0e7 / nx)
+    backend = api.B200(local)
+    model = DecomposedModel(loc, state, backend, local, dtype=npdt, overlap=not getattr(args, "no_overlap", False))
+    K, W = args.steps, max(args.warmup, 3)
+    model.step(dt, W)
+    model.finish()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    dist.barrier()
+    torch.cuda.synchronize()
+    l0 = backend.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(model.compute)
+    model.step(dt, K)
+    e1.record(model.compute)
+    model.compute.synchronize()
+    model.comm.synchronize()
+    ms_local = e0.elapsed_time(e1)
+    launches = backend.launch_count() - l0
+    t = torch.tensor([ms_local], dtype=torch.float64, device=model.dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    model.finish()
+
+    # end to end with HOST buffers: every step uploads this rank's (u, h) and reads back ssh
+    nCl, nEl = loc["nCells"], loc["nEdges"]
+    hu, hh, hout = backend.pinned(nEl, npdt), backend.pinned(nCl, npdt), backend.pinned(nCl, npdt)
+    hu[:], hh[:] = np.asarray(state[1], npdt), np.asarray(state[2], npdt)
+    Ke = max(3, min(K, 10))
+
+    def e2e_step():
+        model.prog.dev.set(L.NORMAL_VELOCITY, hu)
+        model.prog.dev.set(L.LAYER_THICKNESS, hh)
+        model.step(dt, 1)
+        model.finish()
+        model.prog.dev.get(L.SSH, hout)
+    e2e_step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        e2e_step()
+    torch.cuda.synchronize()
+    te = torch.tensor([(time.perf_counter() - t0) / Ke], dtype=torch.float64, device=model.dev)
+    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    cnt = torch.tensor([nCl + nEl, nCl, loc["nCellsOwned"], launches], dtype=torch.float64, device=model.dev)
+    dist.all_reduce(cnt)
+    blocks = model.mesh.block_counts()
+    halo_bytes = (sum(model.ex.send_counts) + sum(model.ex.recv_counts)) * np.dtype(npdt).itemsize
+    if rank == 0:
+        item = np.dtype(npdt).itemsize
+        peak, peak_src = measured_peak_gbs()
+        value = nC_glob * K / (ms * 1e-3)
+        algo_per_launch = ALGO_BYTES_PER_CELL_STEP[args.dtype] / 4.0 * loc["nCellsOwned"]
+        achieved = algo_per_launch / ((ms * 1e-3) / (4 * K)) / 1e9
+        print(json.dumps({
+            "metric": "RK4 cell-steps/sec", "value": value, "unit": "cell-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype,
+            "data": "synthetic",
+            "config": {"workload": f"inertial gravity wave, {nx}x{nx} periodic planar hex mesh ({nC_glob} cells), "
+                                   f"{'Float64' if args.dtype == 'f64' else 'Float32'} RK4, dt={dt:.4g}s, recursive-coordinate-bisection "
+                                   f"into {world} parts, 1 halo layer, NCCL all-to-all per stage "
+                                   f"{'overlapped with interior blocks' if model.overlap else '(no overlap)'}",
+                       "name": args.workload, "l2": "inputs larger than L2 (no flush)", "setup_s": round(t_setup, 1),
+                       "rank0_blocks_interior_boundary": list(blocks), "rank0_halo_bytes_per_stage": int(halo_bytes)},
+            "clocks": clocks,
+            "e2e": {"value": nC_glob / e2e_s, "unit": "cell-steps/s", "h2d_bytes_per_step": int(cnt[0].item() * item),
+                    "d2h_bytes_per_step": int(cnt[1].item() * item), "ms_per_step": e2e_s * 1e3},
+            "gpu_launches": int(cnt[3].item()),
+            "roofline": {"bound": "hbm", "kernel": "k_rk_stage", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "note": "per GPU: algorithmic bytes of rank 0's owned cells per stage / (max-over-ranks step time / 4)"},
+        }))
+    dist.barrier()
+    dist.destroy_process_group()

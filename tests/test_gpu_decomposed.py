@@ -1,0 +1,134 @@
+"""GPU: the domain-decomposed path.  (1) P ranks emulated in ONE process on one GPU (messages moved
+with device copies instead of NCCL) -- checks owned/halo renumbering, interior/boundary block parts,
+halo pack/unpack and the staged RK4 entry points against the single-domain oracle; (2) the real
+one-process-per-GPU NCCL path under torchrun when the box has >= 2 GPUs."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import moka_b200 as mb
+import moka_oracle_c as OC
+from conftest import hex_mesh, rel_l2
+from moka_b200 import _lib as L
+from moka_b200 import multi_gpu, partition
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class _Rank:
+    def __init__(self, backend, loc, state, nparts, dtype=np.float64):
+        import torch
+        self.loc = loc
+        self.mesh = mb.Mesh(loc, backend)
+        self.sidx, self.scnt, self.ridx, self.rcnt = partition.flat_halo(loc, nparts)
+        self.mesh.halo_setup(self.sidx, self.ridx)
+        ssh, u, h = multi_gpu.local_state(loc, *state)
+        self.prog = mb.PrognosticVars(ssh.astype(dtype), u.astype(dtype), h.astype(dtype), 2, self.mesh)
+        tdt = torch.float64 if dtype == np.float64 else torch.float32
+        self.send = torch.zeros(max(1, len(self.sidx)), dtype=tdt, device="cuda")
+        self.recv = torch.zeros(max(1, len(self.ridx)), dtype=tdt, device="cuda")
+        self.h = self.prog.dev.handle
+
+
+def _run_emulated(backend, m, state, nparts, dt, nsteps, split_parts=True, dtype=np.float64):
+    import torch
+    locs = partition.decompose(m, nparts)
+    ranks = [_Rank(backend, loc, state, nparts, dtype) for loc in locs]
+    lib = L.lib()
+    for _ in range(nsteps):
+        for s in (1, 2, 3, 4):
+            for r in ranks:
+                if split_parts:
+                    L.check(lib.mokab_rk4_stage(r.h, dt, s, L.PART_BOUNDARY, None))
+                    L.check(lib.mokab_halo_pack(r.h, s, C.c_void_p(r.send.data_ptr()), None))
+                    L.check(lib.mokab_rk4_stage(r.h, dt, s, L.PART_INTERIOR, None))
+                else:
+                    L.check(lib.mokab_rk4_stage(r.h, dt, s, L.PART_ALL, None))
+                    L.check(lib.mokab_halo_pack(r.h, s, C.c_void_p(r.send.data_ptr()), None))
+            backend.synchronize()
+            for r in ranks:                      # the "all-to-all": recv segment from q <- q's send segment to r
+                ro = 0
+                for q, cr in enumerate(r.rcnt):
+                    if cr:
+                        so = sum(ranks[q].scnt[:r.loc["rank"]])
+                        r.recv[ro:ro + cr] = ranks[q].send[so:so + cr]
+                    ro += cr
+            torch.cuda.synchronize()
+            for r in ranks:
+                L.check(lib.mokab_halo_unpack(r.h, s, C.c_void_p(r.recv.data_ptr()), None))
+        for r in ranks:
+            L.check(lib.mokab_rk4_finish_step(r.h))
+    gu, gh, gs = np.full(m["nEdges"], np.nan), np.full(m["nCells"], np.nan), np.full(m["nCells"], np.nan)
+    for r in ranks:
+        L.check(lib.mokab_refresh_ssh(r.h, None))
+        no, ne = r.loc["nCellsOwned"], r.loc["nEdgesOwned"]
+        gu[r.loc["edgesGlobal"][:ne]] = r.prog.normalVelocity[:ne]
+        gh[r.loc["cellsGlobal"][:no]] = r.prog.layerThickness[:no]
+        gs[r.loc["cellsGlobal"][:no]] = r.prog.ssh[:no]
+    return gu, gh, gs, ranks
+
+
+@pytest.mark.parametrize("nx,nparts,split", [(32, 2, True), (48, 4, True), (64, 8, True), (64, 3, False)])
+def test_emulated_ranks_match_oracle(backend, nx, nparts, split):
+    m = hex_mesh(nx)
+    state = mb.inertialGravityWave(m).initial_state()
+    dt = mb.cfl_dt(m["dc"])
+    gu, gh, gs, ranks = _run_emulated(backend, m, state, nparts, dt, 12, split_parts=split)
+    om = OC.OracleModel(m, *state)
+    om.run_loop(dt, 12, "RungeKutta4")
+    assert rel_l2(gu, om.normalVelocity[1]) <= 1e-12
+    assert rel_l2(gh, om.layerThickness[1]) <= 1e-12
+    assert rel_l2(gs, om.ssh[1]) <= 1e-12
+    # and identical to the single-domain GPU run (same kernel, same per-entity arithmetic)
+    mesh = mb.Mesh(m, backend)
+    prog = mb.PrognosticVars(*state, 2, mesh)
+    mb.ocn_run_loop(dt, prog, None, None, None, mb.RungeKutta4, 12)
+    assert np.array_equal(gu, prog.normalVelocity) and np.array_equal(gh, prog.layerThickness)
+    for r in ranks:
+        ni, nb = r.mesh.block_counts()
+        assert ni + nb == -(-r.loc["nCellsOwned"] // 256) and nb >= 1
+
+
+def test_block_parts_at_scale(backend):
+    """512x512 over 4 ranks: most blocks are interior; decomposed == single-domain result."""
+    m = hex_mesh(512, with_dual=False)
+    state = mb.inertialGravityWave(m).initial_state()
+    dt = mb.cfl_dt(m["dc"])
+    gu, gh, gs, ranks = _run_emulated(backend, m, state, 4, dt, 4)
+    mesh = mb.Mesh(m, backend)
+    prog = mb.PrognosticVars(*state, 2, mesh)
+    mb.ocn_run_loop(dt, prog, None, None, None, mb.RungeKutta4, 4)
+    assert np.array_equal(gu, prog.normalVelocity) and np.array_equal(gh, prog.layerThickness)
+    for r in ranks:
+        ni, nb = r.mesh.block_counts()
+        assert ni > 3 * nb, (ni, nb)
+    mass = sum(mb.reduce_sum(r.prog, "mass") for r in ranks)
+    assert abs(mass - mb.reduce_sum(prog, "mass")) <= 1e-13 * mass
+
+
+def test_decomposed_state_refuses_single_domain_stepper(backend):
+    m = hex_mesh(16)
+    loc = partition.decompose(m, 2)[0]
+    mesh = mb.Mesh(loc, backend)
+    ssh, u, h = multi_gpu.local_state(loc, *mb.inertialGravityWave(m).initial_state())
+    prog = mb.PrognosticVars(ssh, u, h, 2, mesh)
+    with pytest.raises(mb.MokaError, match="halo"):
+        mb.ocn_timestep(1.0, prog, None, None, None, mb.RungeKutta4)
+    with pytest.raises(mb.MokaError, match="halo_setup"):
+        L.check(L.lib().mokab_halo_pack(prog.dev.handle, 1, None, None))
+
+
+def test_nccl_two_ranks_torchrun():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29611",
+                          os.path.join(ROOT, "tests", "multi_gpu_check.py")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "MULTI_GPU_CHECK_OK" in out.stdout

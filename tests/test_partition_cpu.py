@@ -1,0 +1,121 @@
+"""CPU: domain decomposition (host logic) pinned bit-exactly by the loop oracle, and the N>1 path
+exercised with world_size-2 gloo processes (the per-rank compute is the numpy oracle here -- the
+product's compute needs a GPU and is covered by the -m gpu tests)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import moka_oracle as O
+import partition_oracle as PO
+from conftest import hex_mesh
+from moka_b200 import partition
+
+
+@pytest.mark.parametrize("nx,ny,nparts", [(16, 16, 2), (16, 12, 3), (24, 16, 4), (16, 16, 8)])
+def test_partition_and_halo_lists_bit_exact_vs_loop_oracle(nx, ny, nparts):
+    m = hex_mesh(nx, ny, 1000.0)
+    part = partition.rcb_partition(m["xCell"], m["yCell"], nparts)
+    part_o = PO.rcb_partition(m["xCell"].tolist(), m["yCell"].tolist(), nparts)
+    assert part.dtype == np.int32 and part.tolist() == part_o
+    sizes = np.bincount(part, minlength=nparts)
+    assert sizes.max() - sizes.min() <= nparts                    # balanced
+    locs = partition.decompose(m, nparts, part)
+    mo = {k: (v.tolist() if isinstance(v, np.ndarray) else v) for k, v in m.items()
+          if k in ("nCells", "cellsOnEdge", "edgesOnCell", "nEdgesOnCell")}
+    sets, halos = PO.halo_lists(mo, part_o, nparts)
+    owned_cells = np.zeros(m["nCells"], int)
+    owned_edges = np.zeros(m["nEdges"], int)
+    for r, loc in enumerate(locs):
+        cells, nco, edges, neo = sets[r]
+        assert loc["cellsGlobal"].tolist() == cells and loc["nCellsOwned"] == nco
+        assert loc["edgesGlobal"].tolist() == edges and loc["nEdgesOwned"] == neo
+        owned_cells[loc["cellsGlobal"][:nco]] += 1
+        owned_edges[loc["edgesGlobal"][:neo]] += 1
+        assert sorted(loc["halo"]["recv"]) == sorted(q for q in halos[r]["recv"])
+        for q in loc["halo"]["peers"]:
+            assert loc["halo"]["recv"][q].tolist() == halos[r]["recv"].get(q, [])
+            assert loc["halo"]["send"][q].tolist() == halos[r]["send"].get(q, [])
+        # every stencil of an owned entity stays inside the local mesh
+        no, ne = loc["nCellsOwned"], loc["nEdgesOwned"]
+        assert np.all(loc["cellsOnEdge"][:ne] > 0)
+        assert np.all(loc["edgesOnEdge"][:ne] > 0)
+        assert np.all(loc["edgesOnCell"][:no] > 0)
+        nb = loc["cellsOnEdge"][loc["edgesOnCell"][:no].astype(np.int64) - 1]
+        assert np.all(nb > 0)
+    assert np.all(owned_cells == 1) and np.all(owned_edges == 1)   # a partition: every entity owned exactly once
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, nx, nsteps, out_dir):
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path[:0] = [here, os.path.join(os.path.dirname(here), "mpas-ocean.jl_b200"), os.path.join(os.path.dirname(here), "oracle")]
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import moka_b200.planar_hex as ph
+    import moka_oracle_c as OC
+    from moka_b200 import multi_gpu
+    m = ph.periodic_hex(nx, nx, 1.0e7 / nx, with_dual=False)
+    OC.sign_index_fields(m)
+    ssh, u, h = O.InertialGravityWave(m).initial_state()
+    loc = partition.decompose(m, world)[rank]
+    OC.sign_index_fields(loc)
+    sidx, scnt, ridx, rcnt = partition.flat_halo(loc, world)
+    ex = multi_gpu.HaloExchanger(scnt, rcnt, torch.float64, "cpu")
+    nCl = loc["nCells"]
+    ls, lu, lh = multi_gpu.local_state(loc, ssh, u, h)
+    dt = 0.5 * (1.0e7 / nx) / np.sqrt(O.GRAVITY * 1000.0)
+    a, b = [dt / 2, dt / 2, dt], [dt / 6, dt / 3, dt / 3, dt / 6]
+
+    def exchange(uu, hh):
+        comb = np.concatenate([hh, uu])
+        ex.send[:len(sidx)] = torch.from_numpy(comb[sidx])
+        ex.exchange()
+        comb[ridx] = ex.recv[:len(ridx)].numpy()
+        return comb[nCl:], comb[:nCl]
+
+    u_cur, h_cur = lu.copy(), lh.copy()
+    for _ in range(nsteps):
+        u_pro, h_pro, u_new, h_new = u_cur.copy(), h_cur.copy(), u_cur.copy(), h_cur.copy()
+        for s in range(4):
+            tu, th = O.tendencies_consistent(loc, u_pro, h_pro)
+            if s < 3:
+                u_pro, h_pro = exchange(u_cur + a[s] * tu, h_cur + a[s] * th)
+            u_new, h_new = u_new + b[s] * tu, h_new + b[s] * th
+        u_cur, h_cur = exchange(u_new, h_new)
+    no, ne = loc["nCellsOwned"], loc["nEdgesOwned"]
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), u=u_cur[:ne], h=h_cur[:no], ce=loc["cellsGlobal"][:no], ee=loc["edgesGlobal"][:ne],
+             halo_u=u_cur[ne:], halo_e=loc["edgesGlobal"][ne:])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_two_rank_gloo_halo_exchange_matches_single_domain(tmp_path, world):
+    import torch.multiprocessing as mp
+    nx, nsteps = 16, 5
+    mp.spawn(_worker, args=(world, _free_port(), nx, nsteps, str(tmp_path)), nprocs=world, join=True)
+    m = hex_mesh(nx, with_dual=False) if False else hex_mesh(nx)
+    ssh, u, h = O.InertialGravityWave(m).initial_state()
+    prog = O.new_state(m, ssh, u, h)
+    dt = 0.5 * (1.0e7 / nx) / np.sqrt(O.GRAVITY * 1000.0)
+    for _ in range(nsteps):
+        O.timestep_rk4(m, prog, dt)
+    gu, gh = np.full(m["nEdges"], np.nan), np.full(m["nCells"], np.nan)
+    for r in range(world):
+        z = np.load(tmp_path / f"r{r}.npz")
+        gu[z["ee"]], gh[z["ce"]] = z["u"], z["h"]
+        assert np.array_equal(z["halo_u"], prog["normalVelocity"][-1][z["halo_e"]])     # halos hold the owners' values
+    assert np.array_equal(gu, prog["normalVelocity"][-1])         # bit-exact: same arithmetic per entity
+    assert np.array_equal(gh, prog["layerThickness"][-1])
