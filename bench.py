@@ -150,7 +150,7 @@ def run_b200(args):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(f"{args.workload}_{args.dtype}")
+            traffic = (json.load(f).get(f"{args.workload}_{args.dtype}") or {}).get("bytes_per_launch")
     except Exception:
         pass
 
