@@ -23,7 +23,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "mpas-ocean.jl_b200"))
 
-WORKLOADS = {"igw64": 64, "igw512": 512, "igw1024": 1024, "igw2048": 2048, "igw4096": 4096}
+WORKLOADS = {"igw64": 64, "igw512": 512, "igw1024": 1024, "igw2048": 2048, "igw4096": 4096, "kelvin1024": 1024}
 # algorithmic bytes per cell per RK4 step on a planar hex mesh (SURVEY.md 8d / BASELINE.md section 3)
 ALGO_BYTES_PER_CELL_STEP = {"f64": 2400.0, "f32": 1536.0}
 
@@ -75,8 +75,12 @@ class ClockSampler:
 def build_case(nx: int, dtype: str):
     import moka_b200 as mb
     t0 = time.time()
-    m = mb.periodic_hex(nx, nx, 1.0e7 / nx, with_dual=False)
-    ssh, u, h = mb.inertialGravityWave(m).initial_state()
+    if dtype == "kelvin":
+        m = mb.channel_hex(nx, nx, 1.0e7 / nx)
+        ssh, u, h = mb.kelvinWave(m).initial_state()
+    else:
+        m = mb.periodic_hex(nx, nx, 1.0e7 / nx, with_dual=False)
+        ssh, u, h = mb.inertialGravityWave(m).initial_state()
     return m, (ssh, u, h), mb.cfl_dt(m["dc"]), time.time() - t0
 
 
@@ -91,7 +95,8 @@ def run_b200(args):
 
     nx = WORKLOADS[args.workload]
     npdt = np.float64 if args.dtype == "f64" else np.float32
-    m, (ssh, u, h), dt, t_gen = build_case(nx, args.dtype)
+    kelvin = args.workload.startswith("kelvin")
+    m, (ssh, u, h), dt, t_gen = build_case(nx, "kelvin" if kelvin else args.dtype)
     nC, nE = m["nCells"], m["nEdges"]
     backend = mb.B200(local)
     t0 = time.time()
@@ -158,7 +163,8 @@ def run_b200(args):
         "metric": "RK4 cell-steps/sec", "value": value, "unit": "cell-steps/s", "n_gpus": 1, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": f"inertial gravity wave, {nx}x{nx} periodic planar hex mesh ({nC} cells, {nE} edges), "
+        "config": {"workload": (f"coastal Kelvin wave, {nx}x{nx} channel hex mesh with boundary-edge masks" if kelvin else
+                                f"inertial gravity wave, {nx}x{nx} periodic planar hex mesh") + f" ({nC} cells, {nE} edges), "
                                f"{'Float64' if args.dtype == 'f64' else 'Float32'} RK4, dt={dt:.4g}s",
                    "name": args.workload, "l2": "inputs larger than L2 (no flush)" if nx >= 1024 else "fits in L2",
                    "mesh_gen_s": round(t_gen, 2), "mesh_upload_s": round(t_mesh, 2)},
@@ -171,16 +177,18 @@ def run_b200(args):
                      "algorithmic_bytes_per_launch": algo_bytes_per_launch, "avg_launch_ms": avg_launch_s * 1e3},
     }
     if not args.no_cpu:
-        out["cpu_baseline"] = cpu_baseline(m, (ssh, u, h), dt, budget_s=args.cpu_budget)
+        out["cpu_baseline"] = cpu_baseline(m, (ssh, u, h), dt, budget_s=args.cpu_budget, kelvin=kelvin)
     print(json.dumps(out))
 
 
-def cpu_baseline(m, state, dt, budget_s=15.0):
+def cpu_baseline(m, state, dt, budget_s=15.0, kelvin=False):
     """The C/OpenMP restatement of the reference path (oracle/), timed on this box's host cores on a
     bounded sample: RK4 steps on the same mesh until ~budget_s of CPU work."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import moka_oracle_c as OC
     ssh, u, h = state
+    if kelvin:
+        m = OC.apply_boundary_mask(m)
     om = OC.OracleModel(m, ssh, u, h)
     om.run_loop(dt, 1, "RungeKutta4")                       # warm-up (thread pool, page faults)
     t0 = time.perf_counter()
@@ -203,9 +211,12 @@ def run_reference(args):
         return
     world = int(os.environ.get("WORLD_SIZE", "1"))
     nx = WORKLOADS[args.workload]
-    m, (ssh, u, h), dt, _ = build_case(nx, "f64")
+    kelvin = args.workload.startswith("kelvin")
+    m, (ssh, u, h), dt, _ = build_case(nx, "kelvin" if kelvin else "f64")
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import moka_oracle_c as OC
+    if kelvin:
+        m = OC.apply_boundary_mask(m)
     # each "step" is a bounded sample: one RK4 step on the workload mesh (capped so the run ends in minutes)
     om = OC.OracleModel(m, ssh, u, h)
     K, W = args.steps, args.warmup

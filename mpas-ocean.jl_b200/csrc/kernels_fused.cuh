@@ -49,8 +49,11 @@ struct StageArgs {
 };
 
 // STAGE: 1 = first, 2 = middle (2 and 3), 4 = last.  S2/S: compile-time maxEdges2/maxEdges (0 = runtime).
+#ifndef MOKAB_MINBLOCKS
+#define MOKAB_MINBLOCKS 6   // <= 40 registers: 6 blocks (48 warps) per SM measured best (profiles/README.md)
+#endif
 template <class R, int STAGE, int S2T, int ST>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, MOKAB_MINBLOCKS)
 k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
 {
     const int S2 = S2T ? S2T : S2rt;
@@ -63,6 +66,10 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
     for (int e = e0 + threadIdx.x; e < e1; e += kThreads) {
         const int2 c = ld_stream(A.ce + e);
         const int n = ld_stream(A.nEoE + e);
+        // the RK operands are independent of the tendency: issue their loads now (they may alias the
+        // stores below, so the compiler cannot hoist them itself)
+        const R cur = (STAGE == 4) ? R(0) : A.uCur[e];
+        const R accIn = (STAGE == 1) ? R(0) : A.uAcc[e];
         int idx[S2T ? S2T : 1];
         R w[S2T ? S2T : 1];
         R k;
@@ -87,10 +94,9 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
                 cor += ld_stream(A.wf + (size_t)i * nE + e) * __ldg(A.uOld + ld_stream(A.eoe + (size_t)i * nE + e));
         }
         k = cor - ld_stream(A.gdc + e) * ((h2 - H2) - (h1 - H1));
-        const R cur = (STAGE == 4) ? R(0) : A.uCur[e];
         if (STAGE != 4) A.uOut[e] = cur + A.a * k;
         if (STAGE == 1) A.uAcc[e] = cur + A.b * k;
-        else            A.uAcc[e] = A.uAcc[e] + A.b * k;
+        else            A.uAcc[e] = accIn + A.b * k;
     }
 
     // ---- cells of this block ----------------------------------------------------------------------------
@@ -98,6 +104,8 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
     if (cc < A.nCown) {
         const int n = ld_stream(A.nEoC + cc);
         const R hc = __ldg(A.hOld + cc);
+        const R cur = (STAGE == 4) ? R(0) : A.hCur[cc];
+        const R accIn = (STAGE == 1) ? R(0) : A.hAcc[cc];
         R acc = R(0);
         if constexpr (ST != 0) {
             int ee[ST ? ST : 1];
@@ -130,10 +138,9 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
             }
         }
         const R k = acc * ld_stream(A.invArea + cc);
-        const R cur = (STAGE == 4) ? R(0) : A.hCur[cc];
         if (STAGE != 4) A.hOut[cc] = cur + A.a * k;
         if (STAGE == 1) A.hAcc[cc] = cur + A.b * k;
-        else            A.hAcc[cc] = A.hAcc[cc] + A.b * k;
+        else            A.hAcc[cc] = accIn + A.b * k;
     }
 }
 

@@ -3,5 +3,5 @@ from ._lib import LIB_PATH, MokaError, SYMBOLS  # noqa: F401
 from .api import (B200, CurlOnVertex, DiagnosticVars, DivergenceOnCell, ForwardEuler, GradientOnEdge, Mesh,  # noqa: F401
                   PrognosticVars, RungeKutta4, TendencyVars, cfl_dt, check_eltype_args, check_typeof_args,
                   computeLayerThicknessTendency, computeNormalVelocityTendency, diagnostic_compute,
-                  inertialGravityWave, interpolateCell2Edge, ocn_run_loop, ocn_timestep, reduce_sum, reference_dt)
+                  inertialGravityWave, interpolateCell2Edge, kelvinWave, ocn_run_loop, ocn_timestep, reduce_sum, reference_dt)
 from .planar_hex import channel_hex, periodic_hex  # noqa: F401

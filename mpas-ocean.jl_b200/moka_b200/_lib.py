@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libmoka_b200.so")
+LIB_PATH = os.path.join(os.path.dirname(_HERE), os.environ.get("MOKAB_LIB", "libmoka_b200.so"))
 
 F64, F32 = 0, 1
 (SSH, NORMAL_VELOCITY, LAYER_THICKNESS, SSH_PREV, NORMAL_VELOCITY_PREV, LAYER_THICKNESS_PREV,

@@ -359,3 +359,32 @@ class inertialGravityWave:
     def initial_state(self):
         ssh = self.exact_ssh(0.0)
         return ssh, self.exact_norm_vel(0.0), self.bottom_depth + ssh
+
+
+class kelvinWave:
+    """Coastal Kelvin wave on a `channel_hex` mesh (project-defined; the reference
+    rejects non-periodic meshes, VertMesh.jl:50-52): coast at x = 0, c = sqrt(g H), R = c / f0,
+    eta = eta0 * exp(-x / R) * cos(ky * (y + c t)), u = 0, v = -(g / c) * eta; normal velocity is zero
+    on solid-wall edges (`boundaryEdge`)."""
+
+    def __init__(self, fields: dict, mode: int = 2):
+        self.g, self.f0, self.eta0, self.bottom_depth = GRAVITY, 1e-4, 1.0, 1000.0
+        self.c = np.sqrt(self.g * self.bottom_depth)
+        self.R = self.c / self.f0
+        self.ky = mode * 2.0 * np.pi / fields["y_period"]
+        self.f = fields
+
+    def exact_ssh(self, t: float, x=None, y=None):
+        x = self.f["xCell"] if x is None else x
+        y = self.f["yCell"] if y is None else y
+        return self.eta0 * np.exp(-x / self.R) * np.cos(self.ky * (y + self.c * t))
+
+    def exact_norm_vel(self, t: float):
+        f = self.f
+        v = -(self.g / self.c) * self.exact_ssh(t, f["xEdge"], f["yEdge"])
+        un = v * np.sin(f["angleEdge"])
+        return np.where(f["boundaryEdge"] != 0, 0.0, un)
+
+    def initial_state(self):
+        ssh = self.exact_ssh(0.0)
+        return ssh, self.exact_norm_vel(0.0), self.bottom_depth + ssh

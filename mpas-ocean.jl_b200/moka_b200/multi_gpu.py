@@ -151,8 +151,12 @@ def _share_locals(args, rank, world, nx, dtype):
     t0 = time.time()
     if rank == 0:
         from . import planar_hex
-        m = planar_hex.periodic_hex(nx, nx, 1.0e7 / nx, with_dual=False)
-        ssh, u, h = api.inertialGravityWave(m).initial_state()
+        if args.workload.startswith("kelvin"):
+            m = planar_hex.channel_hex(nx, nx, 1.0e7 / nx)
+            ssh, u, h = api.kelvinWave(m).initial_state()
+        else:
+            m = planar_hex.periodic_hex(nx, nx, 1.0e7 / nx, with_dual=False)
+            ssh, u, h = api.inertialGravityWave(m).initial_state()
         locs = partition.decompose(m, world)
         for r, loc in enumerate(locs):
             ls = local_state(loc, ssh, u, h)
@@ -260,7 +264,8 @@ def bench_main(args, rank, world, local):
             "metric": "RK4 cell-steps/sec", "value": value, "unit": "cell-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype,
             "data": "synthetic",
-            "config": {"workload": f"inertial gravity wave, {nx}x{nx} periodic planar hex mesh ({nC_glob} cells), "
+            "config": {"workload": ("coastal Kelvin wave, %dx%d channel hex mesh with boundary-edge masks" % (nx, nx) if args.workload.startswith("kelvin")
+                                    else f"inertial gravity wave, {nx}x{nx} periodic planar hex mesh") + f" ({nC_glob} cells), "
                                    f"{'Float64' if args.dtype == 'f64' else 'Float32'} RK4, dt={dt:.4g}s, recursive-coordinate-bisection "
                                    f"into {world} parts, 1 halo layer, NCCL all-to-all per stage "
                                    f"{'overlapped with interior blocks' if model.overlap else '(no overlap)'}",

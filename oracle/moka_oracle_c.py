@@ -74,6 +74,21 @@ def sign_index_fields(m: dict) -> None:
         m["edgeSignOnVertex"] = s
 
 
+def apply_boundary_mask(m: dict) -> dict:
+    """Project-defined solid-wall treatment, as mesh preprocessing so the plain
+    reference kernels need no branch: a `boundaryEdge` gets cellsOnEdge[2] := cellsOnEdge[1] (zero
+    SSH gradient, hEdge = h of the one cell) and a zero `weightsOnEdge` row (no Coriolis), so its
+    tendency is exactly 0 and u stays 0.  Returns a shallow copy with the two arrays replaced."""
+    out = dict(m)
+    b = m["boundaryEdge"] != 0
+    coe = m["cellsOnEdge"].copy()
+    coe[b, 1] = coe[b, 0]
+    w = m["weightsOnEdge"].copy()
+    w[b, :] = 0.0
+    out["cellsOnEdge"], out["weightsOnEdge"] = coe, w
+    return out
+
+
 class OracleModel:
     """Mesh + state living in numpy arrays, stepped by the C restatement."""
 

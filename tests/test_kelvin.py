@@ -1,0 +1,86 @@
+"""configs[4]: coastal Kelvin wave on a non-periodic (channel) hex mesh with boundary-edge masks.
+The reference rejects non-periodic meshes (VertMesh.jl:50-52); the masked treatment is project-defined
+ and identical in the oracle (mesh preprocessing) and the library (at upload)."""
+import numpy as np
+import pytest
+
+import moka_b200 as mb
+import moka_oracle as O
+import moka_oracle_c as OC
+from conftest import rel_l2
+
+
+def _case(nx):
+    m = mb.channel_hex(nx, nx, 1.0e7 / nx)
+    mm = OC.apply_boundary_mask(m)
+    OC.sign_index_fields(mm)
+    return m, mm, mb.kelvinWave(m)
+
+
+def test_channel_mesh_structure():
+    m, mm, kw = _case(16)
+    nC, nE = m["nCells"], m["nEdges"]
+    assert nE == 3 * nC + int(m["boundaryEdge"].sum()) // 2
+    coe, eoc = m["cellsOnEdge"], m["edgesOnCell"]
+    assert np.all((coe[:, 1] == 0) == (m["boundaryEdge"] != 0))
+    for c in range(nC):                                   # every edge of a cell lists that cell
+        for i in range(6):
+            assert c + 1 in coe[eoc[c, i] - 1]
+    assert set(np.unique(m["nEdgesOnEdge"])) == {5, 10}
+    # TRiSK: uniform flow along the wall is reconstructed exactly on interior edges away from the wall
+    eoe, w = m["edgesOnEdge"].astype(np.int64) - 1, m["weightsOnEdge"]
+    un = np.sin(m["angleEdge"])
+    un[m["boundaryEdge"] != 0] = 0.0
+    rec = np.sum(np.where(eoe >= 0, w * un[np.maximum(eoe, 0)], 0.0), axis=1)
+    interior = (m["nEdgesOnEdge"] == 10) & np.all(m["boundaryEdge"][np.maximum(eoe, 0)] == 0, axis=1)
+    assert np.max(np.abs(rec[interior] - np.cos(m["angleEdge"][interior]))) < 1e-14
+
+
+def test_kelvin_oracle_converges_and_conserves():
+    errs = []
+    for nx in (32, 64):
+        m, mm, kw = _case(nx)
+        ssh, u, h = kw.initial_state()
+        om = OC.OracleModel(mm, ssh, u, h)
+        T = 10000.0
+        n = int(np.ceil(T / mb.cfl_dt(m["dc"])))
+        om.run_loop(T / n, n, "RungeKutta4")
+        errs.append(O.rel_l2(om.ssh[1], kw.exact_ssh(T)))
+        assert abs(np.sum(om.layerThickness[1] - h)) < 1e-9
+        assert np.all(om.normalVelocity[1][m["boundaryEdge"] != 0] == 0.0)      # walls stay closed
+    assert errs[0] < 0.15 and errs[1] < 0.6 * errs[0]                          # first order (staircase coast)
+
+
+@pytest.mark.gpu
+def test_kelvin_gpu_parity(backend):
+    m, mm, kw = _case(64)
+    ssh, u, h = kw.initial_state()
+    dt = mb.cfl_dt(m["dc"])
+    mesh = mb.Mesh(m, backend)
+    # live reference path (ForwardEuler order) bit-exact
+    prog = mb.PrognosticVars(ssh, u, h, 2, mesh)
+    mb.ocn_run_loop(dt, prog, None, None, None, mb.ForwardEuler, 30)
+    om = OC.OracleModel(mm, ssh, u, h)
+    om.run_loop(dt, 30, "ForwardEuler")
+    assert np.array_equal(prog.normalVelocity, om.normalVelocity[1]) and np.array_equal(prog.layerThickness, om.layerThickness[1])
+    # fused RK4
+    prog = mb.PrognosticVars(ssh, u, h, 2, mesh)
+    mb.ocn_run_loop(dt, prog, None, None, None, mb.RungeKutta4, 60)
+    om = OC.OracleModel(mm, ssh, u, h)
+    om.run_loop(dt, 60, "RungeKutta4")
+    assert rel_l2(prog.ssh, om.ssh[1]) <= 1e-12
+    assert rel_l2(prog.normalVelocity, om.normalVelocity[1]) <= 1e-12
+    assert np.all(prog.normalVelocity[m["boundaryEdge"] != 0] == 0.0)
+    assert abs(mb.reduce_sum(prog, "mass") - float(np.sum(m["areaCell"] * h))) <= 1e-13 * float(np.sum(m["areaCell"] * h))
+
+
+@pytest.mark.gpu
+def test_kelvin_decomposed_emulated(backend):
+    from test_gpu_decomposed import _run_emulated
+    m, mm, kw = _case(48)
+    state = kw.initial_state()
+    dt = mb.cfl_dt(m["dc"])
+    gu, gh, gs, _ = _run_emulated(backend, m, state, 4, dt, 10)
+    om = OC.OracleModel(mm, *state)
+    om.run_loop(dt, 10, "RungeKutta4")
+    assert rel_l2(gu, om.normalVelocity[1]) <= 1e-12 and rel_l2(gh, om.layerThickness[1]) <= 1e-12
