@@ -28,6 +28,13 @@ namespace fused {
 constexpr int kTC = 256;       // cells per block
 constexpr int kThreads = 256;
 
+// Round-to-nearest multiply/add that the compiler may not contract into FMA: the fused kernel keeps the
+// reference's operation order so that Float64 results are bit-identical to the oracle.
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+
 template <class R>
 struct StageArgs {
     int nE, nC;              // local entity counts (= strides of the slot-major arrays)
@@ -46,13 +53,18 @@ struct StageArgs {
     R *uAcc, *hAcc;          // accumulator == the other time level
     R *uOut, *hOut;          // next provisional state (stages 1-3)
     R a, b;
+    R f0;                    // uniform fEdge (FOLD = false): weights stay unfolded, (w*u)*f0 formed as the reference does;
+                             // FOLD = true: wf already holds weightsOnEdge*fEdge[eoe] (variable f; differs by round-off)
 };
 
 // STAGE: 1 = first, 2 = middle (2 and 3), 4 = last.  S2/S: compile-time maxEdges2/maxEdges (0 = runtime).
-#ifndef MOKAB_MINBLOCKS
-#define MOKAB_MINBLOCKS 6   // <= 40 registers: 6 blocks (48 warps) per SM measured best (profiles/README.md)
+#ifndef MOKAB_W_LATE
+#define MOKAB_W_UPFRONT 1   // issue the weight loads together with the index loads (measured +5 % over loading at use)
 #endif
-template <class R, int STAGE, int S2T, int ST>
+#ifndef MOKAB_MINBLOCKS
+#define MOKAB_MINBLOCKS 5   // <= 48 registers, 5 blocks (40 warps) per SM: measured best of 4/5/6 (profiles/README.md)
+#endif
+template <class R, int STAGE, int S2T, int ST, bool FOLD>
 __global__ void __launch_bounds__(kThreads, MOKAB_MINBLOCKS)
 k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
 {
@@ -70,33 +82,42 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
         // stores below, so the compiler cannot hoist them itself)
         const R cur = (STAGE == 4) ? R(0) : A.uCur[e];
         const R accIn = (STAGE == 1) ? R(0) : A.uAcc[e];
-        int idx[S2T ? S2T : 1];
-        R w[S2T ? S2T : 1];
         R k;
-        if constexpr (S2T != 0) {
-#pragma unroll
-            for (int i = 0; i < S2T; ++i) {
-                idx[i] = i < n ? ld_stream(A.eoe + (size_t)i * nE + e) : e;
-                w[i] = i < n ? ld_stream(A.wf + (size_t)i * nE + e) : R(0);
-            }
-        }
         const R h1 = __ldg(A.hOld + c.x), h2 = __ldg(A.hOld + c.y);
         const R H1 = __ldg(A.H + c.x), H2 = __ldg(A.H + c.y);
-        R cor = R(0);
         if constexpr (S2T != 0) {
+            int idx[S2T ? S2T : 1];
+#pragma unroll
+            for (int i = 0; i < S2T; ++i) idx[i] = i < n ? ld_stream(A.eoe + (size_t)i * nE + e) : e;
+#ifdef MOKAB_W_UPFRONT
+            R w[S2T ? S2T : 1];
+#pragma unroll
+            for (int i = 0; i < S2T; ++i) w[i] = i < n ? ld_stream(A.wf + (size_t)i * nE + e) : R(0);
+#endif
             R uu[S2T ? S2T : 1];
 #pragma unroll
             for (int i = 0; i < S2T; ++i) uu[i] = __ldg(A.uOld + idx[i]);
+            // tend = 0 - (g/dc)*(ssh2 - ssh1), then += (w*u)*f slot by slot (pressure_gradient.jl:63, coriolis :70-72)
+            k = -mul_rn(ld_stream(A.gdc + e), add_rn(add_rn(h2, -H2), -add_rn(h1, -H1)));
 #pragma unroll
-            for (int i = 0; i < S2T; ++i) cor += w[i] * uu[i];
+            for (int i = 0; i < S2T; ++i) {
+#ifdef MOKAB_W_UPFRONT
+                const R wi = w[i];
+#else
+                const R wi = i < n ? ld_stream(A.wf + (size_t)i * nE + e) : R(0);
+#endif
+                k = add_rn(k, FOLD ? mul_rn(wi, uu[i]) : mul_rn(mul_rn(wi, uu[i]), A.f0));
+            }
         } else {
-            for (int i = 0; i < n; ++i)
-                cor += ld_stream(A.wf + (size_t)i * nE + e) * __ldg(A.uOld + ld_stream(A.eoe + (size_t)i * nE + e));
+            k = -mul_rn(ld_stream(A.gdc + e), add_rn(add_rn(h2, -H2), -add_rn(h1, -H1)));
+            for (int i = 0; i < n; ++i) {
+                const R wu = mul_rn(ld_stream(A.wf + (size_t)i * nE + e), __ldg(A.uOld + ld_stream(A.eoe + (size_t)i * nE + e)));
+                k = add_rn(k, FOLD ? wu : mul_rn(wu, A.f0));
+            }
         }
-        k = cor - ld_stream(A.gdc + e) * ((h2 - H2) - (h1 - H1));
-        if (STAGE != 4) A.uOut[e] = cur + A.a * k;
-        if (STAGE == 1) A.uAcc[e] = cur + A.b * k;
-        else            A.uAcc[e] = accIn + A.b * k;
+        if (STAGE != 4) A.uOut[e] = add_rn(cur, mul_rn(A.a, k));       // Provis = Curr + a*tend (time_integration.jl:124)
+        if (STAGE == 1) A.uAcc[e] = add_rn(cur, mul_rn(A.b, k));       // New = Curr + b1*tend    (:108-110, :134)
+        else            A.uAcc[e] = add_rn(accIn, mul_rn(A.b, k));     // New += b*tend           (:134)
     }
 
     // ---- cells of this block ----------------------------------------------------------------------------
@@ -120,27 +141,31 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
                 uu[i] = __ldg(A.uOld + e);
                 dd[i] = __ldg(A.dv + e);
             }
+            const R invA = ld_stream(A.invArea + cc);
 #pragma unroll
             for (int i = 0; i < ST; ++i) {
                 const int other = cs[i].x == cc ? cs[i].y : cs[i].x;
                 const R ho = __ldg(A.hOld + other);
-                const R f = dd[i] * uu[i] * (R(0.5) * (hc + ho));
-                if (ee[i] >= 0) acc += (ee[i] & 1) ? f : -f;
+                // flux = u*hEdge (DiagnosticVars.jl:158-173), hEdge = 0.5*(h1+h2) (Operators.jl:201-222),
+                // tend += flux*dv*sign*invArea (horizontal_advection.jl:64-65)
+                const R f = mul_rn(mul_rn(mul_rn(uu[i], mul_rn(R(0.5), add_rn(hc, ho))), dd[i]), invA);
+                if (ee[i] >= 0) acc = add_rn(acc, (ee[i] & 1) ? f : -f);
             }
         } else {
+            const R invA = ld_stream(A.invArea + cc);
             for (int i = 0; i < n; ++i) {
                 const int ex = ld_stream(A.eoc + (size_t)i * nC + cc);
                 const int e = ex >> 1;
                 const int2 cs = __ldg(A.ce + e);
                 const int other = cs.x == cc ? cs.y : cs.x;
-                const R f = __ldg(A.dv + e) * __ldg(A.uOld + e) * (R(0.5) * (hc + __ldg(A.hOld + other)));
-                acc += (ex & 1) ? f : -f;
+                const R f = mul_rn(mul_rn(mul_rn(__ldg(A.uOld + e), mul_rn(R(0.5), add_rn(hc, __ldg(A.hOld + other)))), __ldg(A.dv + e)), invA);
+                acc = add_rn(acc, (ex & 1) ? f : -f);
             }
         }
-        const R k = acc * ld_stream(A.invArea + cc);
-        if (STAGE != 4) A.hOut[cc] = cur + A.a * k;
-        if (STAGE == 1) A.hAcc[cc] = cur + A.b * k;
-        else            A.hAcc[cc] = accIn + A.b * k;
+        const R k = acc;
+        if (STAGE != 4) A.hOut[cc] = add_rn(cur, mul_rn(A.a, k));
+        if (STAGE == 1) A.hAcc[cc] = add_rn(cur, mul_rn(A.b, k));
+        else            A.hAcc[cc] = add_rn(accIn, mul_rn(A.b, k));
     }
 }
 
@@ -150,7 +175,7 @@ __global__ void __launch_bounds__(256)
 k_build_fused_edges(int nE, int S2, const double *__restrict__ dc, const double *__restrict__ dv,
                     const double *__restrict__ fE, const int32_t *__restrict__ eoe, const double *__restrict__ woe,
                     const uint8_t *__restrict__ nEoE, R *__restrict__ gdc, R *__restrict__ dvR, R *__restrict__ wf,
-                    int32_t *__restrict__ eoeF)
+                    int32_t *__restrict__ eoeF, int foldF)
 {
     const int e = blockIdx.x * 256 + threadIdx.x;
     if (e >= nE) return;
@@ -160,7 +185,7 @@ k_build_fused_edges(int nE, int S2, const double *__restrict__ dc, const double 
     for (int i = 0; i < S2; ++i) {
         const size_t k = (size_t)i * nE + e;
         const int x = i < n ? eoe[k] : -1;
-        wf[k] = x >= 0 ? (R)__dmul_rn(woe[k], fE[x]) : R(0);
+        wf[k] = x >= 0 ? (foldF ? (R)__dmul_rn(woe[k], fE[x]) : (R)woe[k]) : R(0);
         if (eoeF) eoeF[k] = x >= 0 ? x : e;
     }
 }

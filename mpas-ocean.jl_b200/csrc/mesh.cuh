@@ -67,6 +67,8 @@ struct HostMesh {
     std::vector<int32_t> eov, sgnV;            // slot-major (D, nV)
     std::vector<double> areaTri;
     bool any_boundary = false;
+    bool uniformF = true;     // fEdge identical on every edge (f-plane): Coriolis weights stay unfolded
+    double f0 = 0.0;
 };
 
 constexpr int kBlockCells = 256;  // cells per block of the fused kernel (fused::kTC)
@@ -214,6 +216,9 @@ static void build_host_mesh(const mokab_mesh_desc &d, uint32_t flags, HostMesh &
             m.woe[(size_t)i * nE + en] = bnd ? 0.0 : d.weightsOnEdge[(int64_t)S2 * eo + i];
         }
     }
+    m.f0 = m.fE[0];
+    for (int64_t e = 0; e < nE; ++e)
+        if (m.fE[e] != m.f0) { m.uniformF = false; break; }
     // ---- cells (edgeSignOnCell derived as HorzMesh.jl:292-311 when not supplied) ---------------------
     m.eoc.assign((size_t)S * nC, -1); m.sgnC.assign((size_t)S * nC, 0);
     m.nEoC.resize(nC); m.area.resize(nC); m.H.resize(nC);
@@ -297,6 +302,7 @@ struct mokab_mesh {
     mokab::DevBuf<int32_t> blkInterior, blkBoundary;  // block ids by part
     int64_t nCo = 0, nEo = 0;            // owned cells / edges (== nC / nE without decomposition)
     int fusedBlocks = 0, nInterior = 0, nBoundary = 0;
+    bool uniformF = true; double f0 = 0.0;
     std::vector<int32_t> hBlkEdgeStart, hBlkInterior, hBlkBoundary;  // host copies (halo_setup re-classifies)
     mokab::DevBuf<int32_t> haloSend, haloRecv;  // combined [cells | edges] indices, device numbering
     bool halo_ready = false;

@@ -80,7 +80,7 @@ static void upload_mesh(mokab_ctx *ctx, HostMesh &hm, mokab_mesh *m)
     m->area.upload(hm.area, s); m->H.upload(hm.H, s);
     m->eov.upload(hm.eov, s); m->sgnV.upload(hm.sgnV, s); m->areaTri.upload(hm.areaTri, s);
     m->dPermC.upload(hm.permC, s); m->dPermE.upload(hm.permE, s); m->dPermV.upload(hm.permV, s);
-    m->nCo = hm.nCo; m->nEo = hm.nEo;
+    m->nCo = hm.nCo; m->nEo = hm.nEo; m->uniformF = hm.uniformF; m->f0 = hm.f0;
     m->blkEdgeStart.upload(hm.blkEdgeStart, s);
     m->blkInterior.upload(hm.blkInterior, s);
     m->blkBoundary.upload(hm.blkBoundary, s);
@@ -106,7 +106,7 @@ static void ensure_fused(mokab_mesh *m)
     f.gdc.alloc(m->nE); f.dv.alloc(m->nE); f.wf.alloc((size_t)m->S2 * m->nE);
     f.invArea.alloc(m->nC); f.H.alloc(m->nC);
     LAUNCH(ctx, fused::k_build_fused_edges<R>, nblk(m->nE), 256, (int)m->nE, m->S2, m->dc.p, m->dv.p, m->fE.p, m->eoe.p,
-           m->woe.p, m->nEoE.p, f.gdc.p, f.dv.p, f.wf.p, need_idx ? m->eoeF.p : nullptr);
+           m->woe.p, m->nEoE.p, f.gdc.p, f.dv.p, f.wf.p, need_idx ? m->eoeF.p : nullptr, m->uniformF ? 0 : 1);
     LAUNCH(ctx, fused::k_build_fused_cells<R>, nblk(m->nC), 256, (int)m->nC, m->S, m->area.p, m->H.p, m->eoc.p, m->sgnC.p,
            m->nEoC.p, f.invArea.p, f.H.p, need_idx ? m->eocF.p : nullptr);
     f.ready = true;
@@ -293,10 +293,11 @@ static void launch_stage(mokab_ctx *ctx, const mokab_mesh *m, fused::StageArgs<R
     if (part == MOKAB_PART_BOUNDARY) { grid = m->nBoundary; A.blockList = m->blkBoundary.p; }
     if (grid == 0) return;
     cudaStream_t s = stream ? stream : ctx->stream;
-    if (m->S2 == 10 && m->S == 6)
-        fused::k_rk_stage<R, STAGE, 10, 6><<<grid, fused::kThreads, 0, s>>>(A, m->S2, m->S);
-    else
-        fused::k_rk_stage<R, STAGE, 0, 0><<<grid, fused::kThreads, 0, s>>>(A, m->S2, m->S);
+    const bool hex = m->S2 == 10 && m->S == 6;
+    if (hex && m->uniformF)        fused::k_rk_stage<R, STAGE, 10, 6, false><<<grid, fused::kThreads, 0, s>>>(A, m->S2, m->S);
+    else if (hex)                  fused::k_rk_stage<R, STAGE, 10, 6, true><<<grid, fused::kThreads, 0, s>>>(A, m->S2, m->S);
+    else if (m->uniformF)          fused::k_rk_stage<R, STAGE, 0, 0, false><<<grid, fused::kThreads, 0, s>>>(A, m->S2, m->S);
+    else                           fused::k_rk_stage<R, STAGE, 0, 0, true><<<grid, fused::kThreads, 0, s>>>(A, m->S2, m->S);
     MOKAB_CUDA(cudaGetLastError());
     ctx->launches++;
 }
@@ -316,6 +317,7 @@ static fused::StageArgs<R> stage_args(mokab_state *st, double dt, int p, int sta
     const double a[4] = {dt / 2.0, dt / 2.0, dt, 0.0};                  // time_integration.jl:77
     const double b[4] = {dt / 6.0, dt / 3.0, dt / 3.0, dt / 6.0};       // time_integration.jl:78
     A.a = (R)a[stage - 1]; A.b = (R)b[stage - 1];
+    A.f0 = (R)m->f0;
     switch (stage) {
     case 1: A.uOld = t->u[p].p;  A.hOld = t->h[p].p;  A.uOut = t->uP[0].p; A.hOut = t->hP[0].p; break;  // provisional == current
     case 2: A.uOld = t->uP[0].p; A.hOld = t->hP[0].p; A.uOut = t->uP[1].p; A.hOut = t->hP[1].p; break;

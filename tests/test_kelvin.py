@@ -68,8 +68,10 @@ def test_kelvin_gpu_parity(backend):
     mb.ocn_run_loop(dt, prog, None, None, None, mb.RungeKutta4, 60)
     om = OC.OracleModel(mm, ssh, u, h)
     om.run_loop(dt, 60, "RungeKutta4")
-    assert rel_l2(prog.ssh, om.ssh[1]) <= 1e-12
-    assert rel_l2(prog.normalVelocity, om.normalVelocity[1]) <= 1e-12
+    assert rel_l2(prog.normalVelocity, om.normalVelocity[1]) <= 1e-12 and rel_l2(prog.layerThickness, om.layerThickness[1]) <= 1e-12
+    # f-plane mesh: the fused kernel is bit-identical to the oracle (ssh = h - 1000 is too ill-conditioned here,
+    # RMS ssh 0.16 m against ulp(1000 m) = 1.1e-13, for two different operation orders to agree to 1e-12)
+    assert np.array_equal(prog.ssh, om.ssh[1]) and np.array_equal(prog.normalVelocity, om.normalVelocity[1])
     assert np.all(prog.normalVelocity[m["boundaryEdge"] != 0] == 0.0)
     assert abs(mb.reduce_sum(prog, "mass") - float(np.sum(m["areaCell"] * h))) <= 1e-13 * float(np.sum(m["areaCell"] * h))
 
