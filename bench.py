@@ -255,6 +255,8 @@ def main():
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--no-overlap", dest="no_overlap", action="store_true", help="multi-GPU: exchange after each full stage")
+    ap.add_argument("--no-graph", dest="no_graph", action="store_true", help="multi-GPU: do not capture steps into a CUDA graph")
     ap.add_argument("--quick", action="store_true", help="profiling runs: no clock-sampling load loop, one e2e step")
     args = ap.parse_args()
     if args.workload is None:

@@ -57,12 +57,21 @@ class HaloExchanger:
 
 
 class DecomposedModel:
-    """This rank's share of the mesh on its GPU + the stage/exchange schedule."""
+    """This rank's share of the mesh on its GPU + the stage/exchange schedule.
 
-    def __init__(self, loc: dict, state, backend: api.B200, device_index: int, dtype=np.float64, group=None, overlap=True):
+    Two streams per rank: `compute` runs the INTERIOR blocks, the high-priority `halo` stream runs the
+    BOUNDARY blocks, then pack -> all-to-all -> unpack.  Stage s on either stream needs stage s-1 of BOTH
+    (events `ev_i`, `ev_b`); the unpack of stage s-1 precedes the boundary launch of stage s on the same
+    stream.  Both parts of a stage therefore start together, the boundary blocks win the SMs first, and
+    the message travels while the interior blocks run.  With `graph=True` two consecutive steps (one per
+    time-level parity) are captured -- NCCL calls included -- into one CUDA graph and replayed.
+    """
+
+    def __init__(self, loc: dict, state, backend: api.B200, device_index: int, dtype=np.float64, group=None, overlap=True,
+                 graph=False):
         import torch
         self.torch = torch
-        self.loc, self.backend, self.overlap = loc, backend, overlap
+        self.loc, self.backend, self.overlap, self.use_graph = loc, backend, overlap, graph
         self.nparts = loc["nparts"]
         self.mesh = api.Mesh(loc, backend)
         sidx, scnt, ridx, rcnt = partition.flat_halo(loc, self.nparts)
@@ -73,11 +82,10 @@ class DecomposedModel:
         self.dev = torch.device("cuda", device_index)
         self.ex = HaloExchanger(scnt, rcnt, tdt, self.dev, group)
         self.compute = torch.cuda.Stream(self.dev)
-        self.comm = torch.cuda.Stream(self.dev)
-        self.ev_b = [torch.cuda.Event() for _ in range(4)]
-        self.ev_x = torch.cuda.Event()
-        self.ev_x.record(self.compute)
+        self.halo = torch.cuda.Stream(self.dev, priority=-1)
+        self.comm = self.halo
         self.handle = self.prog.dev.handle
+        self._graph, self._graph_dt = None, None
 
     def _stage(self, dt, s, part, stream):
         L.check(L.lib().mokab_rk4_stage(self.handle, float(dt), s, part, C.c_void_p(stream.cuda_stream)))
@@ -89,27 +97,65 @@ class DecomposedModel:
             self.ex.exchange()
             L.check(lib.mokab_halo_unpack(self.handle, s, C.c_void_p(self.ex.recv.data_ptr()), C.c_void_p(stream.cuda_stream)))
 
-    def step(self, dt: float, nsteps: int = 1) -> None:
-        for _ in range(nsteps):
-            for s in (1, 2, 3, 4):
-                if self.overlap:
-                    self.compute.wait_event(self.ev_x)
-                    self._stage(dt, s, L.PART_BOUNDARY, self.compute)
-                    self.ev_b[s - 1].record(self.compute)
-                    self._stage(dt, s, L.PART_INTERIOR, self.compute)
-                    self.comm.wait_event(self.ev_b[s - 1])
-                    self._exchange(s, self.comm)
-                    self.ev_x.record(self.comm)
-                else:
+    def _enqueue_steps(self, dt: float, nsteps: int) -> None:
+        """Enqueue `nsteps` RK4 steps; on entry and exit both streams are joined on `compute`."""
+        torch = self.torch
+        if not self.overlap:
+            for _ in range(nsteps):
+                for s in (1, 2, 3, 4):
                     self._stage(dt, s, L.PART_ALL, self.compute)
                     self._exchange(s, self.compute)
+                L.check(L.lib().mokab_rk4_finish_step(self.handle))
+            return
+        self.halo.wait_stream(self.compute)                      # fork
+        for _ in range(nsteps):
+            for s in (1, 2, 3, 4):
+                ev_i, ev_b = torch.cuda.Event(), torch.cuda.Event()
+                self._stage(dt, s, L.PART_BOUNDARY, self.halo)
+                ev_b.record(self.halo)
+                self._stage(dt, s, L.PART_INTERIOR, self.compute)
+                ev_i.record(self.compute)
+                self._exchange(s, self.halo)
+                self.compute.wait_event(ev_b)                    # stage s+1 interior reads stage s boundary output
+                self.halo.wait_event(ev_i)                       # stage s+1 boundary reads stage s interior output
             L.check(L.lib().mokab_rk4_finish_step(self.handle))
-        self.compute.wait_event(self.ev_x)
+        self.compute.wait_stream(self.halo)                      # join
+
+    def step(self, dt: float, nsteps: int = 1) -> None:
+        torch = self.torch
+        if self.use_graph and nsteps >= 2:
+            if self._graph is None or self._graph_dt != dt:
+                self.compute.synchronize()
+                self.halo.synchronize()
+                self._enqueue_steps(dt, 2)                       # warm up NCCL + lazy library state outside capture
+                self.compute.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self.compute):
+                    self._enqueue_steps(dt, 2)
+                self._graph, self._graph_dt = g, dt
+                self._warm = 2
+                nsteps -= 2
+            with torch.cuda.stream(self.compute):
+                for _ in range(nsteps // 2):
+                    self._graph.replay()
+            nsteps = nsteps % 2
+        if nsteps:
+            self._enqueue_steps(dt, nsteps)
 
     def finish(self) -> None:
         L.check(L.lib().mokab_refresh_ssh(self.handle, C.c_void_p(self.compute.cuda_stream)))
         self.compute.synchronize()
-        self.comm.synchronize()
+        self.halo.synchronize()
+
+    def close(self) -> None:
+        """Drop the captured graph (it pins NCCL resources: the process group cannot be destroyed while
+        it is alive) and drain both streams."""
+        self.compute.synchronize()
+        self.halo.synchronize()
+        self._graph = None
+        import gc
+        gc.collect()
+        self.torch.cuda.synchronize()
 
     def owned(self, field: str) -> np.ndarray:
         a = getattr(self.prog, field)
@@ -199,7 +245,8 @@ def bench_main(args, rank, world, local):
     nC_glob = nx * nx
     dt = api.cfl_dt(1.0e7 / nx)
     backend = api.B200(local)
-    model = DecomposedModel(loc, state, backend, local, dtype=npdt, overlap=not getattr(args, "no_overlap", False))
+    model = DecomposedModel(loc, state, backend, local, dtype=npdt, overlap=not getattr(args, "no_overlap", False),
+                            graph=not getattr(args, "no_graph", False))
     K, W = args.steps, max(args.warmup, 3)
     model.step(dt, W)
     model.finish()
@@ -211,15 +258,16 @@ def bench_main(args, rank, world, local):
         time.sleep(0.3)
     dist.barrier()
     torch.cuda.synchronize()
-    l0 = backend.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(model.compute)
     model.step(dt, K)
     e1.record(model.compute)
     model.compute.synchronize()
-    model.comm.synchronize()
+    model.halo.synchronize()
     ms_local = e0.elapsed_time(e1)
-    launches = backend.launch_count() - l0
+    # this library's kernels per step: 4 stages x (boundary + interior + pack + unpack), or 4 x (all + pack + unpack);
+    # graph replays do not pass through the host-side counter, so the count is by construction
+    launches = K * (16 if model.overlap else 12)
     t = torch.tensor([ms_local], dtype=torch.float64, device=model.dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
@@ -268,7 +316,8 @@ def bench_main(args, rank, world, local):
                                     else f"inertial gravity wave, {nx}x{nx} periodic planar hex mesh") + f" ({nC_glob} cells), "
                                    f"{'Float64' if args.dtype == 'f64' else 'Float32'} RK4, dt={dt:.4g}s, recursive-coordinate-bisection "
                                    f"into {world} parts, 1 halo layer, NCCL all-to-all per stage "
-                                   f"{'overlapped with interior blocks' if model.overlap else '(no overlap)'}",
+                                   f"{'overlapped with interior blocks' if model.overlap else '(no overlap)'}"
+                                   f"{', 2-step CUDA graph incl. NCCL' if model.use_graph else ''}",
                        "name": args.workload, "l2": "inputs larger than L2 (no flush)", "setup_s": round(t_setup, 1),
                        "rank0_blocks_interior_boundary": list(blocks), "rank0_halo_bytes_per_stage": int(halo_bytes)},
             "clocks": clocks,
@@ -279,5 +328,7 @@ def bench_main(args, rank, world, local):
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "note": "per GPU: algorithmic bytes of rank 0's owned cells per stage / (max-over-ranks step time / 4)"},
         }))
+    model.close()
     dist.barrier()
+    torch.cuda.synchronize()
     dist.destroy_process_group()

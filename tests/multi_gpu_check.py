@@ -27,12 +27,14 @@ def main():
     loc = partition.decompose(m, world)[rank]
     backend = mb.B200(local)
     errs = []
-    for overlap in (True, False):
-        model = multi_gpu.DecomposedModel(loc, multi_gpu.local_state(loc, *state), backend, local, overlap=overlap)
+    for overlap, graph in ((True, False), (False, False), (True, True)):
+        model = multi_gpu.DecomposedModel(loc, multi_gpu.local_state(loc, *state), backend, local, overlap=overlap, graph=graph)
         model.step(dt, nsteps)
         model.finish()
         gs, gu, gh = multi_gpu.gather_owned(model, m["nCells"], m["nEdges"])
         mass = model.reduce("mass")
+        model.close()
+        del model
         if rank == 0:
             OC.sign_index_fields(m)
             om = OC.OracleModel(m, *state)
@@ -40,12 +42,14 @@ def main():
             rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))
             e = (rel(gs, om.ssh[1]), rel(gu, om.normalVelocity[1]), rel(gh, om.layerThickness[1]))
             m0 = float(np.sum(m["areaCell"] * om.layerThickness[1]))
-            errs.append((overlap, e, abs(mass - m0) / m0))
+            errs.append(((overlap, graph), e, abs(mass - m0) / m0))
     if rank == 0:
         print(errs)
         ok = all(max(e) <= 1e-12 and dm <= 1e-13 for _, e, dm in errs)
         print("MULTI_GPU_CHECK_OK" if ok else "MULTI_GPU_CHECK_FAILED")
+    sys.stdout.flush()
     dist.barrier()
+    torch.cuda.synchronize()
     dist.destroy_process_group()
 
 
