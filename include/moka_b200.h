@@ -150,6 +150,15 @@ int  mokab_state_destroy(mokab_state *state);
  * prognostic field also fills the "previous" level, like the deepcopy at PrognosticVars.jl:49-53. */
 int  mokab_state_set(mokab_state *state, int field, const void *host);
 int  mokab_state_get(mokab_state *state, int field, void *host);
+/* Pipelined variants for callers that stream states through the device (ensembles, per-step output,
+ * the reference's write_netcdf adapt-to-CPU at src/infra/OutPut.jl:122-124 without stalling the loop):
+ * the PCIe copy runs on a copy stream of the state, only the (un)permute kernel is ordered with the
+ * context's stream, so the upload of the next inputs and the download of the last result overlap the
+ * step kernels.  `host_pinned` must be page-locked (mokab_host_alloc) and stay valid -- and, for get,
+ * unread -- until mokab_state_synchronize.  set_async does not touch the "previous" time level. */
+int  mokab_state_set_async(mokab_state *state, int field, const void *host_pinned);
+int  mokab_state_get_async(mokab_state *state, int field, void *host_pinned);
+int  mokab_state_synchronize(mokab_state *state);
 
 /* ---- src/ocn entry points (operator level; reference operation order, Float64 bit-faithful) --- */
 /* diagnostic_compute!(Mesh, Diag, Prog)                      src/ocn/DiagnosticVars.jl:108-117     */

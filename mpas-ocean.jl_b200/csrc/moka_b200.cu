@@ -29,6 +29,25 @@ struct StateT {
     cudaGraphExec_t gPair[2] = {nullptr, nullptr};
     double graph_dt = 0.0;
     bool graphs_ready = false;
+    // asynchronous host transfers (mokab_state_set_async / _get_async): rings of staging slots, one copy
+    // stream per direction, events ordering copy <-> permute kernels
+    static constexpr int kInSlots = 4, kOutSlots = 2;
+    DevBuf<R> stIn[kInSlots], stOut[kOutSlots];
+    cudaEvent_t evInCopied[kInSlots] = {}, evInFree[kInSlots] = {}, evOutReady[kOutSlots] = {}, evOutCopied[kOutSlots] = {};
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    int inSlot = 0, outSlot = 0;
+    bool async_ready = false;
+    void drop_async()
+    {
+        if (!async_ready) return;
+        cudaStreamSynchronize(h2d);
+        cudaStreamSynchronize(d2h);
+        for (int i = 0; i < kInSlots; ++i) { cudaEventDestroy(evInCopied[i]); cudaEventDestroy(evInFree[i]); }
+        for (int i = 0; i < kOutSlots; ++i) { cudaEventDestroy(evOutReady[i]); cudaEventDestroy(evOutCopied[i]); }
+        cudaStreamDestroy(h2d);
+        cudaStreamDestroy(d2h);
+        async_ready = false;
+    }
     void drop_graphs()
     {
         for (int p = 0; p < 2; ++p) {
@@ -38,7 +57,11 @@ struct StateT {
         }
         graphs_ready = false;
     }
-    ~StateT() { drop_graphs(); }
+    ~StateT()
+    {
+        drop_graphs();
+        drop_async();
+    }
 };
 }  // namespace mokab
 
@@ -190,6 +213,78 @@ static void state_get(mokab_state *st, int field, void *host)
     LAUNCH(ctx, k_permute_out<R>, nblk(f.n), 256, f.n, f.perm, (const R *)f.p, (R *)t->staging.p);
     MOKAB_CUDA(cudaMemcpyAsync(host, t->staging.p, f.n * sizeof(R), cudaMemcpyDeviceToHost, ctx->stream));
     MOKAB_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+// ---- pipelined host transfers -----------------------------------------------------------------------------------
+// The H2D copy of a field runs on its own stream into a staging slot and only the permute kernel joins the
+// context's stream, so the upload for step n+1 overlaps the kernels of step n; likewise the D2H copy of a
+// result overlaps the kernels that follow it.  `host` must be page-locked and stay valid until
+// mokab_state_synchronize.
+template <class R>
+static void ensure_async(mokab_state *st)
+{
+    StateT<R> *t = typed<R>(st);
+    if (t->async_ready) return;
+    const mokab_mesh *m = st->mesh;
+    const size_t nmax = (size_t)std::max(std::max(m->nE, m->nC), std::max<int64_t>(m->nV, 1));
+    MOKAB_CUDA(cudaStreamCreateWithFlags(&t->h2d, cudaStreamNonBlocking));
+    MOKAB_CUDA(cudaStreamCreateWithFlags(&t->d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < StateT<R>::kInSlots; ++i) {
+        t->stIn[i].alloc(nmax);
+        MOKAB_CUDA(cudaEventCreateWithFlags(&t->evInCopied[i], cudaEventDisableTiming));
+        MOKAB_CUDA(cudaEventCreateWithFlags(&t->evInFree[i], cudaEventDisableTiming));
+    }
+    for (int i = 0; i < StateT<R>::kOutSlots; ++i) {
+        t->stOut[i].alloc(nmax);
+        MOKAB_CUDA(cudaEventCreateWithFlags(&t->evOutReady[i], cudaEventDisableTiming));
+        MOKAB_CUDA(cudaEventCreateWithFlags(&t->evOutCopied[i], cudaEventDisableTiming));
+    }
+    t->async_ready = true;
+}
+
+template <class R>
+static void state_set_async(mokab_state *st, int field, const void *host)
+{
+    mokab_ctx *ctx = st->ctx;
+    StateT<R> *t = typed<R>(st);
+    ensure_async<R>(st);
+    FieldRef f = field_ref<R>(st, field);
+    if (f.n == 0) return;
+    const int slot = t->inSlot;
+    t->inSlot = (slot + 1) % StateT<R>::kInSlots;
+    MOKAB_CUDA(cudaStreamWaitEvent(t->h2d, t->evInFree[slot], 0));      // the slot's previous permute has run
+    MOKAB_CUDA(cudaMemcpyAsync(t->stIn[slot].p, host, f.n * sizeof(R), cudaMemcpyHostToDevice, t->h2d));
+    MOKAB_CUDA(cudaEventRecord(t->evInCopied[slot], t->h2d));
+    MOKAB_CUDA(cudaStreamWaitEvent(ctx->stream, t->evInCopied[slot], 0));
+    LAUNCH(ctx, k_permute_in<R>, nblk(f.n), 256, f.n, f.perm, (const R *)t->stIn[slot].p, (R *)f.p);
+    MOKAB_CUDA(cudaEventRecord(t->evInFree[slot], ctx->stream));
+}
+
+template <class R>
+static void state_get_async(mokab_state *st, int field, void *host)
+{
+    mokab_ctx *ctx = st->ctx;
+    StateT<R> *t = typed<R>(st);
+    ensure_async<R>(st);
+    FieldRef f = field_ref<R>(st, field);
+    if (f.n == 0) return;
+    const int slot = t->outSlot;
+    t->outSlot = (slot + 1) % StateT<R>::kOutSlots;
+    MOKAB_CUDA(cudaStreamWaitEvent(ctx->stream, t->evOutCopied[slot], 0));  // the slot's previous D2H has left
+    LAUNCH(ctx, k_permute_out<R>, nblk(f.n), 256, f.n, f.perm, (const R *)f.p, (R *)t->stOut[slot].p);
+    MOKAB_CUDA(cudaEventRecord(t->evOutReady[slot], ctx->stream));
+    MOKAB_CUDA(cudaStreamWaitEvent(t->d2h, t->evOutReady[slot], 0));
+    MOKAB_CUDA(cudaMemcpyAsync(host, t->stOut[slot].p, f.n * sizeof(R), cudaMemcpyDeviceToHost, t->d2h));
+    MOKAB_CUDA(cudaEventRecord(t->evOutCopied[slot], t->d2h));
+}
+
+template <class R>
+static void state_synchronize(mokab_state *st)
+{
+    StateT<R> *t = typed<R>(st);
+    if (t->async_ready) MOKAB_CUDA(cudaStreamSynchronize(t->h2d));
+    MOKAB_CUDA(cudaStreamSynchronize(st->ctx->stream));
+    if (t->async_ready) MOKAB_CUDA(cudaStreamSynchronize(t->d2h));
 }
 
 // ---- reference-order operator sequences (Float64) -----------------------------------------------------------
@@ -684,6 +779,37 @@ int mokab_state_get(mokab_state *state, int field, void *host)
         MOKAB_REQUIRE(field >= MOKAB_SSH && field <= MOKAB_TEND_LAYER_THICKNESS, "state_get: unknown field id");
         state->ctx->bind();
         if (state->dtype == MOKAB_F64) state_get<double>(state, field, host); else state_get<float>(state, field, host);
+    });
+}
+
+int mokab_state_set_async(mokab_state *state, int field, const void *host_pinned)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(state && host_pinned, "state_set_async: NULL argument");
+        MOKAB_REQUIRE(field >= MOKAB_SSH && field <= MOKAB_TEND_LAYER_THICKNESS, "state_set_async: unknown field id");
+        state->ctx->bind();
+        if (state->dtype == MOKAB_F64) state_set_async<double>(state, field, host_pinned);
+        else state_set_async<float>(state, field, host_pinned);
+    });
+}
+
+int mokab_state_get_async(mokab_state *state, int field, void *host_pinned)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(state && host_pinned, "state_get_async: NULL argument");
+        MOKAB_REQUIRE(field >= MOKAB_SSH && field <= MOKAB_TEND_LAYER_THICKNESS, "state_get_async: unknown field id");
+        state->ctx->bind();
+        if (state->dtype == MOKAB_F64) state_get_async<double>(state, field, host_pinned);
+        else state_get_async<float>(state, field, host_pinned);
+    });
+}
+
+int mokab_state_synchronize(mokab_state *state)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(state, "state_synchronize: state is NULL");
+        state->ctx->bind();
+        if (state->dtype == MOKAB_F64) state_synchronize<double>(state); else state_synchronize<float>(state);
     });
 }
 

@@ -51,6 +51,7 @@ SYMBOLS = [
     "mokab_launch_count", "mokab_host_alloc", "mokab_host_free", "mokab_last_error", "mokab_version",
     "mokab_mesh_create", "mokab_mesh_destroy", "mokab_mesh_get_perm", "mokab_mesh_device_bytes",
     "mokab_state_create", "mokab_state_destroy", "mokab_state_set", "mokab_state_get",
+    "mokab_state_set_async", "mokab_state_get_async", "mokab_state_synchronize",
     "mokab_diagnostic_compute", "mokab_compute_normal_velocity_tendency", "mokab_compute_layer_thickness_tendency",
     "mokab_gradient_on_edge", "mokab_divergence_on_cell", "mokab_curl_on_vertex", "mokab_interpolate_cell2edge",
     "mokab_timestep_forward_euler", "mokab_timestep_rk4", "mokab_reduce",
@@ -76,6 +77,8 @@ def lib():
             "mokab_mesh_get_perm": [vp, C.c_int, _I32P], "mokab_mesh_device_bytes": [vp, C.POINTER(i64)],
             "mokab_state_create": [vp, vp, C.c_int, C.POINTER(vp)], "mokab_state_destroy": [vp],
             "mokab_state_set": [vp, C.c_int, vp], "mokab_state_get": [vp, C.c_int, vp],
+            "mokab_state_set_async": [vp, C.c_int, vp], "mokab_state_get_async": [vp, C.c_int, vp],
+            "mokab_state_synchronize": [vp],
             "mokab_diagnostic_compute": [vp], "mokab_compute_normal_velocity_tendency": [vp],
             "mokab_compute_layer_thickness_tendency": [vp],
             "mokab_gradient_on_edge": [vp, vp, _F64P, _F64P], "mokab_divergence_on_cell": [vp, vp, _F64P, _F64P],

@@ -182,6 +182,21 @@ class _DeviceState:
         L.check(L.lib().mokab_state_get(self.handle, field, out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def set_async(self, field: int, host_pinned: np.ndarray) -> None:
+        """Enqueue the upload of a page-locked host array (B200.pinned); returns before the copy has run."""
+        if host_pinned.dtype != self.np_dtype or host_pinned.size != self._len(field) or not host_pinned.flags.c_contiguous:
+            raise MokaError(f"set_async: field {field} needs a contiguous {self.np_dtype} array of {self._len(field)} elements")
+        L.check(L.lib().mokab_state_set_async(self.handle, field, host_pinned.ctypes.data_as(C.c_void_p)))
+
+    def get_async(self, field: int, out_pinned: np.ndarray) -> None:
+        """Enqueue the download into a page-locked host array; valid after `synchronize()`."""
+        if out_pinned.dtype != self.np_dtype or out_pinned.size != self._len(field) or not out_pinned.flags.c_contiguous:
+            raise MokaError(f"get_async: field {field} needs a contiguous {self.np_dtype} array of {self._len(field)} elements")
+        L.check(L.lib().mokab_state_get_async(self.handle, field, out_pinned.ctypes.data_as(C.c_void_p)))
+
+    def synchronize(self) -> None:
+        L.check(L.lib().mokab_state_synchronize(self.handle))
+
     def _len(self, field: int) -> int:
         m = self.mesh
         if field in (L.SSH, L.LAYER_THICKNESS, L.SSH_PREV, L.LAYER_THICKNESS_PREV, L.VELOCITY_DIV_CELL, L.TEND_LAYER_THICKNESS):
@@ -209,6 +224,21 @@ class PrognosticVars:
         self.dev.set(L.SSH, ssh)
         self.dev.set(L.NORMAL_VELOCITY, normalVelocity)
         self.dev.set(L.LAYER_THICKNESS, layerThickness)
+
+    def upload_async(self, normalVelocity=None, layerThickness=None, ssh=None) -> None:
+        """Adapt.adapt(backend, host arrays) without stalling the device: pipelined H2D from page-locked arrays."""
+        for field, a in ((L.NORMAL_VELOCITY, normalVelocity), (L.LAYER_THICKNESS, layerThickness), (L.SSH, ssh)):
+            if a is not None:
+                self.dev.set_async(field, a)
+
+    def download_async(self, ssh=None, normalVelocity=None, layerThickness=None) -> None:
+        """Adapt.adapt(CPU(), Prog) (what write_netcdf does, OutPut.jl:122-124) into page-locked arrays, pipelined."""
+        for field, a in ((L.SSH, ssh), (L.NORMAL_VELOCITY, normalVelocity), (L.LAYER_THICKNESS, layerThickness)):
+            if a is not None:
+                self.dev.get_async(field, a)
+
+    def synchronize(self) -> None:
+        self.dev.synchronize()
 
     ssh = property(lambda s: s.dev.get(L.SSH))
     normalVelocity = property(lambda s: s.dev.get(L.NORMAL_VELOCITY))

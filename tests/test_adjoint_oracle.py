@@ -1,0 +1,62 @@
+"""CPU: the adjoint oracle against the reference's own acceptance test for gradients (central finite
+differences of J = sum ssh^2, test/enzyme/test_Enzyme_end2end.jl:112-180) and the dot-product identity."""
+import numpy as np
+
+import adjoint_oracle as A
+import moka_b200 as mb
+import moka_oracle as O
+import moka_oracle_c as OC
+from conftest import hex_mesh
+
+
+def _case(nx=16, kelvin=False):
+    if kelvin:
+        m = OC.apply_boundary_mask(mb.channel_hex(nx, nx, 1.0e7 / nx))
+        OC.sign_index_fields(m)
+        ssh, u, h = mb.kelvinWave(m).initial_state()
+    else:
+        m = hex_mesh(nx)
+        ssh, u, h = mb.inertialGravityWave(m).initial_state()
+    return m, u, h, mb.cfl_dt(m["dc"])
+
+
+def test_vjp_is_the_transpose_of_jvp():
+    for kelvin in (False, True):
+        m, u, h, dt = _case(12, kelvin)
+        rng = np.random.default_rng(0)
+        du, dh = rng.standard_normal(m["nEdges"]), rng.standard_normal(m["nCells"])
+        wu, wh = rng.standard_normal(m["nEdges"]), rng.standard_normal(m["nCells"])
+        tu, th = A.tendencies_jvp(m, u, h, du, dh)
+        ub, hb = A.tendencies_vjp(m, u, h, wu, wh)
+        lhs, rhs = tu @ wu + th @ wh, du @ ub + dh @ hb
+        assert abs(lhs - rhs) <= 1e-12 * max(abs(lhs), abs(rhs))
+        # jvp itself: F is quadratic, so a central difference is exact up to round-off
+        e = 1e-3
+        fp, fm = O.tendencies_consistent(m, u + e * du, h + e * dh), O.tendencies_consistent(m, u - e * du, h - e * dh)
+        assert O.rel_l2((fp[0] - fm[0]) / (2 * e), tu) < 1e-9 and O.rel_l2((fp[1] - fm[1]) / (2 * e), th) < 1e-9
+
+
+def test_gradient_matches_finite_differences_like_the_reference_test():
+    m, u, h, dt = _case(16)
+    J, gu, gh = A.gradient_sum_ssh2(m, u, h, dt, 5)
+    assert J > 0
+    for k in (4, 77, 200):                                               # the reference checks index 5 (1-based)
+        fd_h = A.finite_difference(m, u, h, dt, 5, "h", k, eps=1e-7)
+        fd_u = A.finite_difference(m, u, h, dt, 5, "u", k, eps=1e-4)
+        assert abs(gh[k] - fd_h) < 1e-4                                  # atol of test_Enzyme_end2end.jl:176
+        assert abs(gu[k] - fd_u) < 1e-2                                  # atol of :177
+        assert abs(gh[k] - fd_h) < 1e-5 * abs(gh[k]) + 1e-7 and abs(gu[k] - fd_u) < 1e-5 * abs(gu[k]) + 1e-5
+
+
+def test_step_vjp_dot_product_identity():
+    m, u, h, dt = _case(12, kelvin=True)
+    rng = np.random.default_rng(1)
+    du, dh = 1e-3 * rng.standard_normal(m["nEdges"]), rng.standard_normal(m["nCells"])
+    lu, lh = rng.standard_normal(m["nEdges"]), rng.standard_normal(m["nCells"])
+    e = 1e-4
+    up, hp = A.rk4_step(m, u + e * du, h + e * dh, dt)
+    um, hm = A.rk4_step(m, u - e * du, h - e * dh, dt)
+    lhs = ((up - um) / (2 * e)) @ lu + ((hp - hm) / (2 * e)) @ lh
+    bu, bh = A.rk4_step_vjp(m, u, h, dt, lu, lh)
+    rhs = du @ bu + dh @ bh
+    assert abs(lhs - rhs) <= 1e-7 * max(abs(lhs), abs(rhs))

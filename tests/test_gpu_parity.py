@@ -237,3 +237,35 @@ def test_error_paths(backend):
         mb.Mesh(bad, backend)
     with pytest.raises(mb.MokaError, match="nTimeLevels"):
         mb.PrognosticVars(np.zeros(m["nCells"]), np.zeros(m["nEdges"]), np.zeros(m["nCells"]), 3, mesh)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_pipelined_upload_download_matches_blocking_path(backend, dtype):
+    """mokab_state_set_async / get_async (the e2e leg of bench.py): a stream of distinct host states pushed
+    through upload -> RK4 step -> download without host synchronisation gives, for every state, exactly what
+    the blocking set / step / get sequence gives (and therefore the oracle's result for Float64)."""
+    m = hex_mesh(48)
+    mesh, prog, diag, tend, (ssh, u, h) = _setup(backend, m, dtype)
+    dt = mb.cfl_dt(m["dc"])
+    n = 7                                                       # more states in flight than staging slots
+    rng = np.random.default_rng(3)
+    ins = [(backend.pinned(m["nEdges"], dtype), backend.pinned(m["nCells"], dtype)) for _ in range(n)]
+    outs = [(backend.pinned(m["nCells"], dtype), backend.pinned(m["nEdges"], dtype)) for _ in range(n)]
+    for hu, hh in ins:
+        hu[:] = (u * rng.uniform(0.5, 1.5)).astype(dtype)
+        hh[:] = (1000.0 + ssh * rng.uniform(0.5, 1.5)).astype(dtype)
+    for (hu, hh), (os_, ou) in zip(ins, outs):
+        prog.upload_async(normalVelocity=hu, layerThickness=hh)
+        mb.ocn_timestep(dt, prog, diag, tend, None, mb.RungeKutta4, nsteps=1)
+        prog.download_async(ssh=os_, normalVelocity=ou)
+    prog.synchronize()
+    for (hu, hh), (os_, ou) in zip(ins, outs):
+        p2 = mb.PrognosticVars((hh - 1000.0).astype(dtype), hu.copy(), hh.copy(), 2, mesh)
+        mb.ocn_timestep(dt, p2, diag, tend, None, mb.RungeKutta4, nsteps=1)
+        assert np.array_equal(p2.ssh, os_) and np.array_equal(p2.normalVelocity, ou)
+    if dtype == np.float64:
+        om = OC.OracleModel(m, ins[-1][1] - 1000.0, ins[-1][0], ins[-1][1])
+        om.run_loop(dt, 1, "RungeKutta4")
+        assert rel_l2(outs[-1][0], om.ssh[1]) <= TOL64 and rel_l2(outs[-1][1], om.normalVelocity[1]) <= TOL64
+    with pytest.raises(mb.MokaError):
+        prog.dev.set_async(mb._lib.SSH, np.zeros(3, dtype))
