@@ -52,7 +52,12 @@ enum {
     MOKAB_VELOCITY_DIV_CELL = 8,    /* Diag.velocityDivCell    (nCells)                            */
     MOKAB_RELATIVE_VORTICITY = 9,   /* Diag.relativeVorticity  (nVertices)                         */
     MOKAB_TEND_NORMAL_VELOCITY = 10,/* Tend.tendNormalVelocity (nEdges)    TendencyVars.jl:7-49    */
-    MOKAB_TEND_LAYER_THICKNESS = 11 /* Tend.tendLayerThickness (nCells)                            */
+    MOKAB_TEND_LAYER_THICKNESS = 11,/* Tend.tendLayerThickness (nCells)                            */
+    /* shadow state d_Prog of the reverse mode (ocn_init_shadows, src/forward/init.jl:32-40; the
+     * `Duplicated(Prog, d_Prog)` argument at test/enzyme/test_Enzyme_end2end.jl:78-96)             */
+    MOKAB_D_SSH = 12,               /* d_Prog.ssh[end]            (nCells)                           */
+    MOKAB_D_NORMAL_VELOCITY = 13,   /* d_Prog.normalVelocity[end] (nEdges)                           */
+    MOKAB_D_LAYER_THICKNESS = 14    /* d_Prog.layerThickness[end] (nCells)                           */
 };
 
 /* reductions (replaces the serial sumArray kernel, src/forward/run_loop.jl:47-51) */
@@ -183,6 +188,23 @@ int  mokab_timestep_forward_euler(mokab_state *state, double dt, int64_t nsteps)
 int  mokab_timestep_rk4(mokab_state *state, double dt, int64_t nsteps, int impl);
 /* sumArray replacement (deterministic two-level reduction) over the OWNED entities; result always Float64. */
 int  mokab_reduce(mokab_state *state, int which, double *out);
+
+/* ---- reverse mode: what the reference gets from Enzyme ----------------------------------------------
+ * `autodiff(Reverse, ocn_run_loop, Duplicated(Prog, d_Prog), ...)` (test/enzyme/test_Enzyme_end2end.jl:30-110,
+ * ext/MPASEnzymeExt.jl) -- NaN on CUDA in the reference (test_Enzyme_end2end.jl:182-186).  Here: a hand-written
+ * discrete adjoint of the fused RungeKutta4 path (csrc/kernels_adjoint.cuh).  Usage:
+ *   mokab_tape_begin(state, nsteps);  mokab_timestep_rk4(state, dt, nsteps, MOKAB_RK4_FUSED);
+ *   mokab_adjoint_seed(state, MOKAB_SUM_SSH2)      (or mokab_state_set of the MOKAB_D_* fields);
+ *   mokab_adjoint_rk4(state);  mokab_state_get(state, MOKAB_D_NORMAL_VELOCITY / MOKAB_D_LAYER_THICKNESS, ...)
+ * leaves dJ/d(initial normalVelocity, layerThickness) in the shadow fields. */
+/* Start recording: every following RK4_FUSED step stores its input state (max_steps * (nEdges + nCells) elements). */
+int  mokab_tape_begin(mokab_state *state, int64_t max_steps);
+int  mokab_tape_length(mokab_state *state, int64_t *out);
+/* d_ssh = dJ/dssh of the current state for J = `which` (MOKAB_SUM_SSH2: sumArray, run_loop.jl:47-51); d_u = d_h = 0 */
+int  mokab_adjoint_seed(mokab_state *state, int which);
+/* Reverse sweep over the recorded steps (newest first); stops recording and empties the tape.  d_ssh is folded
+ * into d_layerThickness first (ssh = layerThickness - restingThicknessSum, time_integration.jl:205-212). */
+int  mokab_adjoint_rk4(mokab_state *state);
 
 /* ---- staged RungeKutta4 for domain-decomposed runs (one process per GPU) --------------------------
  * The same fused stage kernel, launched per stage and per part so the host can overlap the halo

@@ -58,7 +58,7 @@ k_rk_stage_adj(const AdjArgs<R> A)
     for (int e = e0 + threadIdx.x; e < e1; e += kThreads) {
         const int2 c = ld_stream(A.ce + e);
         const int n = ld_stream(A.nEoET + e);
-        const R lam = A.lamU[e];
+        const R lam = MODE == 2 ? R(0) : A.lamU[e];
         const R accIn = MODE == 0 ? lam : A.accU[e];
         const R q1 = kq(c.x), h1 = __ldg(A.hY + c.x);
         const bool masked = c.x == c.y;
@@ -76,7 +76,7 @@ k_rk_stage_adj(const AdjArgs<R> A)
     const int cc = b * kThreads + threadIdx.x;
     if (cc < A.nCown) {
         const int n = ld_stream(A.nEoC + cc);
-        const R lam = A.lamH[cc];
+        const R lam = MODE == 2 ? R(0) : A.lamH[cc];
         const R accIn = MODE == 0 ? lam : A.accH[cc];
         const R qc = kq(cc);
         R yb = R(0);

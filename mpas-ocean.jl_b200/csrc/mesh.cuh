@@ -281,6 +281,7 @@ static void build_host_mesh(const mokab_mesh_desc &d, uint32_t flags, HostMesh &
 template <class R>
 struct FusedMesh {
     DevBuf<R> gdc, wf, dv, invArea, H;
+    DevBuf<R> wfT;             // adjoint: transposed Coriolis weights (see moka_b200.cu: ensure_adjoint_mesh)
     bool ready = false;
 };
 
@@ -306,6 +307,12 @@ struct mokab_mesh {
     std::vector<int32_t> hBlkEdgeStart, hBlkInterior, hBlkBoundary;  // host copies (halo_setup re-classifies)
     mokab::DevBuf<int32_t> haloSend, haloRecv;  // combined [cells | edges] indices, device numbering
     bool halo_ready = false;
+    // adjoint: transpose of the Coriolis stencil (built on first use)
+    mokab::DevBuf<int32_t> eoeT;
+    mokab::DevBuf<double> woeT;
+    mokab::DevBuf<uint8_t> nEoET;
+    int S2T = 0;
+    bool adj_ready = false;
     mokab::FusedMesh<double> f64;
     mokab::FusedMesh<float> f32;
     int64_t device_bytes() const

@@ -1,6 +1,7 @@
 // moka_b200.cu -- libmoka_b200.so: C ABI (include/moka_b200.h) over the sm_100a kernels.
 #include "common.cuh"
 #include "kernels_fused.cuh"
+#include "kernels_adjoint.cuh"
 #include "kernels_ref.cuh"
 #include "mesh.cuh"
 
@@ -37,6 +38,16 @@ struct StateT {
     cudaStream_t h2d = nullptr, d2h = nullptr;
     int inSlot = 0, outSlot = 0;
     bool async_ready = false;
+    // reverse mode (mokab_tape_* / mokab_adjoint_*): trajectory tape, stage states, adjoint ping-pong buffers
+    DevBuf<R> tapeU, tapeH;                 // (tapeCap, nE), (tapeCap, nC): the state before each recorded step
+    std::vector<double> tapeDt;             // dt of every recorded step
+    int64_t tapeCap = 0;
+    bool taping = false;
+    DevBuf<R> yU[3], yH[3];                 // y_2, y_3, y_4 of the step being reversed
+    DevBuf<R> kbU[2], kbH[2];               // kbar ping-pong (kbH carries invArea * kbar_h)
+    DevBuf<R> lamU[2], lamH[2], dSsh;       // lam' / lam, swapped every reversed step; seed on ssh
+    int lamCur = 0;
+    bool adj_ready = false;
     void drop_async()
     {
         if (!async_ready) return;
@@ -164,6 +175,24 @@ static void alloc_state(mokab_state *st)
 
 struct FieldRef { void *p; int64_t n; const int32_t *perm; bool prognostic_end; int prev_of; };
 
+// shadow state d_Prog (ocn_init_shadows, reference src/forward/init.jl:32-40): zeros
+template <class R>
+static void ensure_adj_state(mokab_state *st)
+{
+    StateT<R> *t = typed<R>(st);
+    if (t->adj_ready) return;
+    const mokab_mesh *m = st->mesh;
+    cudaStream_t s = st->ctx->stream;
+    for (int i = 0; i < 3; ++i) { t->yU[i].alloc(m->nE); t->yH[i].alloc(m->nC); }
+    for (int i = 0; i < 2; ++i) {
+        t->kbU[i].alloc(m->nE); t->kbH[i].alloc(m->nC);
+        t->lamU[i].alloc(m->nE); t->lamU[i].zero(s);
+        t->lamH[i].alloc(m->nC); t->lamH[i].zero(s);
+    }
+    t->dSsh.alloc(m->nC); t->dSsh.zero(s);
+    t->adj_ready = true;
+}
+
 template <class R>
 static FieldRef field_ref(mokab_state *st, int field)
 {
@@ -183,6 +212,9 @@ static FieldRef field_ref(mokab_state *st, int field)
     case MOKAB_RELATIVE_VORTICITY: return {t->relVort.p, m->nV, m->dPermV.p, false, 0};
     case MOKAB_TEND_NORMAL_VELOCITY: return {t->tendU.p, m->nE, m->dPermE.p, false, 0};
     case MOKAB_TEND_LAYER_THICKNESS: return {t->tendH.p, m->nC, m->dPermC.p, false, 0};
+    case MOKAB_D_SSH: ensure_adj_state<R>(st); return {t->dSsh.p, m->nC, m->dPermC.p, false, 0};
+    case MOKAB_D_NORMAL_VELOCITY: ensure_adj_state<R>(st); return {t->lamU[t->lamCur].p, m->nE, m->dPermE.p, false, 0};
+    case MOKAB_D_LAYER_THICKNESS: ensure_adj_state<R>(st); return {t->lamH[t->lamCur].p, m->nC, m->dPermC.p, false, 0};
     default: throw Error("unknown field id " + std::to_string(field));
     }
 }
@@ -532,6 +564,20 @@ static void run_rk4_fused(mokab_state *st, double dt, int64_t nsteps)
     MOKAB_REQUIRE(st->mesh->nCo == st->mesh->nC && st->mesh->nEo == st->mesh->nE,
                   "timestep_rk4: this mesh has halo entities; drive it with mokab_rk4_stage + mokab_halo_pack/unpack");
     ensure_fused<R>(const_cast<mokab_mesh *>(st->mesh));
+    if (t->taping) {  // record the state before every step (plain launches: the tape slot changes per step)
+        const mokab_mesh *m = st->mesh;
+        MOKAB_REQUIRE((int64_t)t->tapeDt.size() + nsteps <= t->tapeCap, "timestep_rk4: the tape is full (mokab_tape_begin max_steps)");
+        for (int64_t i = 0; i < nsteps; ++i) {
+            const size_t k = t->tapeDt.size();
+            MOKAB_CUDA(cudaMemcpyAsync(t->tapeU.p + k * m->nE, t->u[st->cur].p, m->nE * sizeof(R), cudaMemcpyDeviceToDevice, ctx->stream));
+            MOKAB_CUDA(cudaMemcpyAsync(t->tapeH.p + k * m->nC, t->h[st->cur].p, m->nC * sizeof(R), cudaMemcpyDeviceToDevice, ctx->stream));
+            t->tapeDt.push_back(dt);
+            enqueue_rk4_step<R>(st, dt, st->cur);
+            st->cur = 1 - st->cur;
+        }
+        if (nsteps > 0) refresh_ssh<R>(st);
+        return;
+    }
     if (!t->graphs_ready || t->graph_dt != dt) build_graphs<R>(st, dt);
     int64_t left = nsteps;
     while (left >= 2) {
@@ -564,6 +610,170 @@ static void do_reduce(mokab_state *st, int which, double *out)
     LAUNCH(ctx, reduce::k_final, 1, reduce::kThreads, (const double *)t->partial.p, t->result.p);
     MOKAB_CUDA(cudaMemcpyAsync(out, t->result.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     MOKAB_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+// ---- reverse mode -------------------------------------------------------------------------------------------
+// Transpose of the Coriolis stencil: row x lists the edges e whose sum reads u[x], with w[i,e] * f[x]
+// (horizontal_advection_and_coriolis.jl:70-72).  Built on the host from the device arrays, once per mesh; also
+// checks the two structural facts the gather-form adjoint relies on.
+static void ensure_adjoint_mesh(mokab_mesh *m)
+{
+    if (m->adj_ready) return;
+    MOKAB_REQUIRE(m->nCo == m->nC && m->nEo == m->nE, "adjoint: domain-decomposed meshes are not supported");
+    mokab_ctx *ctx = m->ctx;
+    const int64_t nE = m->nE, nC = m->nC;
+    const int S2 = m->S2, S = m->S;
+    std::vector<int32_t> eoe((size_t)S2 * nE), eoc((size_t)S * nC), sgn((size_t)S * nC);
+    std::vector<double> woe((size_t)S2 * nE), fE(nE);
+    std::vector<uint8_t> nEoE(nE), nEoC(nC);
+    std::vector<int2> ce(nE);
+    MOKAB_CUDA(cudaStreamSynchronize(ctx->stream));
+    MOKAB_CUDA(cudaMemcpy(eoe.data(), m->eoe.p, eoe.size() * 4, cudaMemcpyDeviceToHost));
+    MOKAB_CUDA(cudaMemcpy(woe.data(), m->woe.p, woe.size() * 8, cudaMemcpyDeviceToHost));
+    MOKAB_CUDA(cudaMemcpy(fE.data(), m->fE.p, fE.size() * 8, cudaMemcpyDeviceToHost));
+    MOKAB_CUDA(cudaMemcpy(nEoE.data(), m->nEoE.p, nEoE.size(), cudaMemcpyDeviceToHost));
+    MOKAB_CUDA(cudaMemcpy(eoc.data(), m->eoc.p, eoc.size() * 4, cudaMemcpyDeviceToHost));
+    MOKAB_CUDA(cudaMemcpy(sgn.data(), m->sgnC.p, sgn.size() * 4, cudaMemcpyDeviceToHost));
+    MOKAB_CUDA(cudaMemcpy(nEoC.data(), m->nEoC.p, nEoC.size(), cudaMemcpyDeviceToHost));
+    MOKAB_CUDA(cudaMemcpy(ce.data(), m->ce.p, ce.size() * sizeof(int2), cudaMemcpyDeviceToHost));
+    // (1) edgeSignOnCell follows HorzMesh.jl:292-311 (-1 on the cellsOnEdge[1] side); (2) every edge is listed by
+    // both of its cells (once by its only cell when masked)
+    std::vector<uint8_t> seen(nE, 0);
+    for (int64_t c = 0; c < nC; ++c)
+        for (int i = 0; i < nEoC[c]; ++i) {
+            const int32_t e = eoc[(size_t)i * nC + c];
+            const bool first = ce[e].x == c;
+            MOKAB_REQUIRE(first || ce[e].y == c, "adjoint: edgesOnCell lists an edge that does not border the cell");
+            MOKAB_REQUIRE((sgn[(size_t)i * nC + c] > 0) == !first,
+                          "adjoint: edgeSignOnCell does not follow the reference's orientation rule (HorzMesh.jl:292-311)");
+            seen[e]++;
+        }
+    for (int64_t e = 0; e < nE; ++e)
+        MOKAB_REQUIRE(seen[e] == (ce[e].x == ce[e].y ? 1 : 2), "adjoint: an edge is not listed by both of its cells");
+    std::vector<int32_t> cnt(nE, 0);
+    for (int64_t e = 0; e < nE; ++e)
+        for (int i = 0; i < nEoE[e]; ++i) {
+            const int32_t x = eoe[(size_t)i * nE + e];
+            if (x >= 0) cnt[x]++;
+        }
+    int S2T = 1;
+    for (int64_t e = 0; e < nE; ++e) S2T = std::max(S2T, (int)cnt[e]);
+    MOKAB_REQUIRE(S2T <= 255, "adjoint: transposed Coriolis stencil too wide");
+    std::vector<int32_t> eoeT((size_t)S2T * nE, 0);
+    std::vector<double> wT((size_t)S2T * nE, 0.0);
+    std::vector<uint8_t> nT(nE, 0);
+    for (int64_t e = 0; e < nE; ++e)
+        for (int i = 0; i < nEoE[e]; ++i) {
+            const int32_t x = eoe[(size_t)i * nE + e];
+            if (x < 0) continue;
+            const int j = nT[x]++;
+            eoeT[(size_t)j * nE + x] = (int32_t)e;
+            wT[(size_t)j * nE + x] = woe[(size_t)i * nE + e] * fE[x];
+        }
+    m->S2T = S2T;
+    m->eoeT.upload(eoeT, ctx->stream);
+    m->woeT.upload(wT, ctx->stream);
+    m->nEoET.upload(nT, ctx->stream);
+    MOKAB_CUDA(cudaStreamSynchronize(ctx->stream));
+    m->adj_ready = true;
+}
+
+template <class R>
+static void ensure_adjoint(mokab_state *st)
+{
+    mokab_mesh *m = const_cast<mokab_mesh *>(st->mesh);
+    mokab_ctx *ctx = st->ctx;
+    ensure_fused<R>(m);
+    ensure_adjoint_mesh(m);
+    ensure_adj_state<R>(st);
+    FusedMesh<R> &f = fused_of<R>(m);
+    if (f.wfT.n == 0) {
+        f.wfT.alloc(m->woeT.n);
+        LAUNCH(ctx, (k_convert<double, R>), nblk(m->woeT.n), 256, (int64_t)m->woeT.n, (const double *)m->woeT.p, f.wfT.p);
+    }
+}
+
+// Reverse one recorded step: recompute y_2..y_4 from the taped state (three forward stage launches), then the
+// four adjoint stages 4, 3, 2, 1.
+template <class R>
+static void adjoint_step(mokab_state *st, int64_t k)
+{
+    mokab_ctx *ctx = st->ctx; mokab_mesh *m = const_cast<mokab_mesh *>(st->mesh);
+    StateT<R> *t = typed<R>(st);
+    FusedMesh<R> &fm = fused_of<R>(m);
+    const double dt = t->tapeDt[k];
+    const double a[4] = {dt / 2.0, dt / 2.0, dt, 0.0};
+    const double b[4] = {dt / 6.0, dt / 3.0, dt / 3.0, dt / 6.0};
+    const R *u0 = t->tapeU.p + (size_t)k * m->nE, *h0 = t->tapeH.p + (size_t)k * m->nC;
+    // forward recompute; the accumulator output of the forward kernel goes to a kbar buffer that is still free
+    for (int s = 1; s <= 3; ++s) {
+        fused::StageArgs<R> A = stage_args<R>(st, dt, st->cur, s);
+        A.uCur = u0; A.hCur = h0; A.uAcc = t->kbU[1].p; A.hAcc = t->kbH[1].p;
+        A.uOld = s == 1 ? u0 : t->yU[s - 2].p; A.hOld = s == 1 ? h0 : t->yH[s - 2].p;
+        A.uOut = t->yU[s - 1].p; A.hOut = t->yH[s - 1].p;
+        if (s == 1) launch_stage<R, 1>(ctx, m, A); else launch_stage<R, 2>(ctx, m, A);
+    }
+    adjoint::AdjArgs<R> B;
+    B.nE = (int)m->nE; B.nC = (int)m->nC; B.nCown = (int)m->nCo; B.S2T = m->S2T; B.S = m->S;
+    B.ce = m->ce.p; B.eoeT = m->eoeT.p; B.eoc = m->eocF.p; B.nEoET = m->nEoET.p; B.nEoC = m->nEoC.p;
+    B.blkEdgeStart = m->blkEdgeStart.p;
+    B.gdc = fm.gdc.p; B.wfT = fm.wfT.p; B.dv = fm.dv.p; B.invArea = fm.invArea.p;
+    const int p = t->lamCur;
+    B.lamU = t->lamU[p].p; B.lamH = t->lamH[p].p; B.accU = t->lamU[1 - p].p; B.accH = t->lamH[1 - p].p;
+    B.bThis = (R)b[3];
+    const int grid = m->fusedBlocks;
+    for (int s = 4; s >= 1; --s) {
+        B.uY = s == 1 ? u0 : t->yU[s - 2].p; B.hY = s == 1 ? h0 : t->yH[s - 2].p;
+        // kbar buffers alternate: stage 4 writes [1], 3 reads [1] writes [0], 2 reads [0] writes [1], 1 reads [1]
+        B.kuIn = t->kbU[s & 1].p; B.kqIn = t->kbH[s & 1].p;
+        B.kuOut = t->kbU[(s - 1) & 1].p; B.kqOut = t->kbH[(s - 1) & 1].p;
+        B.aPrev = s > 1 ? (R)a[s - 2] : R(0); B.bPrev = s > 1 ? (R)b[s - 2] : R(0);
+        if (s == 4) adjoint::k_rk_stage_adj<R, 0><<<grid, adjoint::kThreads, 0, ctx->stream>>>(B);
+        else if (s > 1) adjoint::k_rk_stage_adj<R, 1><<<grid, adjoint::kThreads, 0, ctx->stream>>>(B);
+        else adjoint::k_rk_stage_adj<R, 2><<<grid, adjoint::kThreads, 0, ctx->stream>>>(B);
+        MOKAB_CUDA(cudaGetLastError());
+        ctx->launches++;
+    }
+    t->lamCur = 1 - p;
+}
+
+template <class R>
+static void tape_begin(mokab_state *st, int64_t max_steps)
+{
+    StateT<R> *t = typed<R>(st);
+    const mokab_mesh *m = st->mesh;
+    if (t->tapeCap < max_steps) {
+        t->tapeU.alloc((size_t)max_steps * m->nE);
+        t->tapeH.alloc((size_t)max_steps * m->nC);
+        t->tapeCap = max_steps;
+    }
+    t->tapeDt.clear();
+    t->taping = true;
+}
+
+template <class R>
+static void adjoint_seed(mokab_state *st, int which)
+{
+    mokab_ctx *ctx = st->ctx; mokab_mesh *m = const_cast<mokab_mesh *>(st->mesh);
+    StateT<R> *t = typed<R>(st);
+    MOKAB_REQUIRE(which == MOKAB_SUM_SSH2, "adjoint_seed: only MOKAB_SUM_SSH2 has a built-in seed; set the MOKAB_D_* fields for others");
+    ensure_adjoint<R>(st);
+    FusedMesh<R> &fm = fused_of<R>(m);
+    t->lamU[t->lamCur].zero(ctx->stream);
+    t->lamH[t->lamCur].zero(ctx->stream);
+    LAUNCH(ctx, adjoint::k_seed_ssh2<R>, nblk(m->nC), 256, m->nC, (const R *)t->h[st->cur].p, (const R *)fm.H.p, t->dSsh.p);
+}
+
+template <class R>
+static void adjoint_run(mokab_state *st)
+{
+    mokab_ctx *ctx = st->ctx; const mokab_mesh *m = st->mesh;
+    StateT<R> *t = typed<R>(st);
+    ensure_adjoint<R>(st);
+    t->taping = false;
+    LAUNCH(ctx, adjoint::k_fold_dssh<R>, nblk(m->nC), 256, m->nC, t->dSsh.p, t->lamH[t->lamCur].p);
+    for (int64_t k = (int64_t)t->tapeDt.size() - 1; k >= 0; --k) adjoint_step<R>(st, k);
+    t->tapeDt.clear();
 }
 
 // stand-alone operators on host arrays -------------------------------------------------------------------
@@ -766,7 +976,7 @@ int mokab_state_set(mokab_state *state, int field, const void *host)
 {
     return guarded([&] {
         MOKAB_REQUIRE(state && host, "state_set: NULL argument");
-        MOKAB_REQUIRE(field >= MOKAB_SSH && field <= MOKAB_TEND_LAYER_THICKNESS, "state_set: unknown field id");
+        MOKAB_REQUIRE(field >= MOKAB_SSH && field <= MOKAB_D_LAYER_THICKNESS, "state_set: unknown field id");
         state->ctx->bind();
         if (state->dtype == MOKAB_F64) state_set<double>(state, field, host); else state_set<float>(state, field, host);
     });
@@ -776,7 +986,7 @@ int mokab_state_get(mokab_state *state, int field, void *host)
 {
     return guarded([&] {
         MOKAB_REQUIRE(state && host, "state_get: NULL argument");
-        MOKAB_REQUIRE(field >= MOKAB_SSH && field <= MOKAB_TEND_LAYER_THICKNESS, "state_get: unknown field id");
+        MOKAB_REQUIRE(field >= MOKAB_SSH && field <= MOKAB_D_LAYER_THICKNESS, "state_get: unknown field id");
         state->ctx->bind();
         if (state->dtype == MOKAB_F64) state_get<double>(state, field, host); else state_get<float>(state, field, host);
     });
@@ -786,7 +996,7 @@ int mokab_state_set_async(mokab_state *state, int field, const void *host_pinned
 {
     return guarded([&] {
         MOKAB_REQUIRE(state && host_pinned, "state_set_async: NULL argument");
-        MOKAB_REQUIRE(field >= MOKAB_SSH && field <= MOKAB_TEND_LAYER_THICKNESS, "state_set_async: unknown field id");
+        MOKAB_REQUIRE(field >= MOKAB_SSH && field <= MOKAB_D_LAYER_THICKNESS, "state_set_async: unknown field id");
         state->ctx->bind();
         if (state->dtype == MOKAB_F64) state_set_async<double>(state, field, host_pinned);
         else state_set_async<float>(state, field, host_pinned);
@@ -797,7 +1007,7 @@ int mokab_state_get_async(mokab_state *state, int field, void *host_pinned)
 {
     return guarded([&] {
         MOKAB_REQUIRE(state && host_pinned, "state_get_async: NULL argument");
-        MOKAB_REQUIRE(field >= MOKAB_SSH && field <= MOKAB_TEND_LAYER_THICKNESS, "state_get_async: unknown field id");
+        MOKAB_REQUIRE(field >= MOKAB_SSH && field <= MOKAB_D_LAYER_THICKNESS, "state_get_async: unknown field id");
         state->ctx->bind();
         if (state->dtype == MOKAB_F64) state_get_async<double>(state, field, host_pinned);
         else state_get_async<float>(state, field, host_pinned);
@@ -949,6 +1159,42 @@ int mokab_reduce(mokab_state *state, int which, double *out)
         MOKAB_REQUIRE(state && out, "reduce: NULL argument");
         state->ctx->bind();
         if (state->dtype == MOKAB_F64) do_reduce<double>(state, which, out); else do_reduce<float>(state, which, out);
+    });
+}
+
+// ---- reverse mode ------------------------------------------------------------------------------------------------
+int mokab_tape_begin(mokab_state *state, int64_t max_steps)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(state && max_steps > 0, "tape_begin: bad argument");
+        state->ctx->bind();
+        if (state->dtype == MOKAB_F64) tape_begin<double>(state, max_steps); else tape_begin<float>(state, max_steps);
+    });
+}
+
+int mokab_tape_length(mokab_state *state, int64_t *out)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(state && out, "tape_length: NULL argument");
+        *out = state->dtype == MOKAB_F64 ? (int64_t)state->d->tapeDt.size() : (int64_t)state->f->tapeDt.size();
+    });
+}
+
+int mokab_adjoint_seed(mokab_state *state, int which)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(state, "adjoint_seed: state is NULL");
+        state->ctx->bind();
+        if (state->dtype == MOKAB_F64) adjoint_seed<double>(state, which); else adjoint_seed<float>(state, which);
+    });
+}
+
+int mokab_adjoint_rk4(mokab_state *state)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(state, "adjoint_rk4: state is NULL");
+        state->ctx->bind();
+        if (state->dtype == MOKAB_F64) adjoint_run<double>(state); else adjoint_run<float>(state);
     });
 }
 

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), os.environ.get("MOKAB_LIB", "lib
 F64, F32 = 0, 1
 (SSH, NORMAL_VELOCITY, LAYER_THICKNESS, SSH_PREV, NORMAL_VELOCITY_PREV, LAYER_THICKNESS_PREV,
  LAYER_THICKNESS_EDGE, THICKNESS_FLUX, VELOCITY_DIV_CELL, RELATIVE_VORTICITY,
- TEND_NORMAL_VELOCITY, TEND_LAYER_THICKNESS) = range(12)
+ TEND_NORMAL_VELOCITY, TEND_LAYER_THICKNESS, D_SSH, D_NORMAL_VELOCITY, D_LAYER_THICKNESS) = range(15)
 SUM_SSH2, SUM_MASS, SUM_ENERGY = range(3)
 CELLS, EDGES, VERTICES = range(3)
 RK4_FUSED, RK4_UNFUSED = 0, 1
@@ -55,6 +55,7 @@ SYMBOLS = [
     "mokab_diagnostic_compute", "mokab_compute_normal_velocity_tendency", "mokab_compute_layer_thickness_tendency",
     "mokab_gradient_on_edge", "mokab_divergence_on_cell", "mokab_curl_on_vertex", "mokab_interpolate_cell2edge",
     "mokab_timestep_forward_euler", "mokab_timestep_rk4", "mokab_reduce",
+    "mokab_tape_begin", "mokab_tape_length", "mokab_adjoint_seed", "mokab_adjoint_rk4",
     "mokab_halo_setup", "mokab_halo_pack", "mokab_halo_unpack", "mokab_rk4_stage", "mokab_rk4_finish_step",
     "mokab_refresh_ssh", "mokab_mesh_block_counts",
 ]
@@ -85,6 +86,8 @@ def lib():
             "mokab_curl_on_vertex": [vp, vp, _F64P, _F64P], "mokab_interpolate_cell2edge": [vp, vp, _F64P, _F64P],
             "mokab_timestep_forward_euler": [vp, dbl, i64], "mokab_timestep_rk4": [vp, dbl, i64, C.c_int],
             "mokab_reduce": [vp, C.c_int, C.POINTER(dbl)],
+            "mokab_tape_begin": [vp, i64], "mokab_tape_length": [vp, C.POINTER(i64)],
+            "mokab_adjoint_seed": [vp, C.c_int], "mokab_adjoint_rk4": [vp],
             "mokab_halo_setup": [vp, i64, _I32P, i64, _I32P], "mokab_halo_pack": [vp, C.c_int, vp, vp],
             "mokab_halo_unpack": [vp, C.c_int, vp, vp], "mokab_rk4_stage": [vp, dbl, C.c_int, C.c_int, vp],
             "mokab_rk4_finish_step": [vp], "mokab_refresh_ssh": [vp, vp],

@@ -199,7 +199,8 @@ class _DeviceState:
 
     def _len(self, field: int) -> int:
         m = self.mesh
-        if field in (L.SSH, L.LAYER_THICKNESS, L.SSH_PREV, L.LAYER_THICKNESS_PREV, L.VELOCITY_DIV_CELL, L.TEND_LAYER_THICKNESS):
+        if field in (L.SSH, L.LAYER_THICKNESS, L.SSH_PREV, L.LAYER_THICKNESS_PREV, L.VELOCITY_DIV_CELL, L.TEND_LAYER_THICKNESS,
+                     L.D_SSH, L.D_LAYER_THICKNESS):
             return m.nCells
         if field == L.RELATIVE_VORTICITY:
             return m.nVertices
@@ -348,6 +349,49 @@ def reduce_sum(Prog, which: str) -> float:
     out = C.c_double()
     L.check(L.lib().mokab_reduce(Prog.dev.handle, {"ssh2": L.SUM_SSH2, "mass": L.SUM_MASS, "energy": L.SUM_ENERGY}[which], C.byref(out)))
     return out.value
+
+
+# ---- reverse mode (ext/MPASEnzymeExt.jl, test/enzyme/test_Enzyme_end2end.jl) -------------------------------------
+class ShadowPrognosticVars:
+    """d_Prog: the shadow of a PrognosticVars that `Duplicated(Prog, d_Prog)` carries through Enzyme's
+    `autodiff(Reverse, ocn_run_loop, ...)` (test_Enzyme_end2end.jl:52-96); created zeroed like
+    `ocn_init_shadows` (init.jl:32-40).  Lives on the device next to `Prog`."""
+
+    def __init__(self, prog: PrognosticVars):
+        self.dev = prog.dev
+        for f, n in ((L.D_SSH, prog.mesh.nCells), (L.D_NORMAL_VELOCITY, prog.mesh.nEdges), (L.D_LAYER_THICKNESS, prog.mesh.nCells)):
+            self.dev.set(f, np.zeros(n, self.dev.np_dtype))
+
+    ssh = property(lambda s: s.dev.get(L.D_SSH), lambda s, v: s.dev.set(L.D_SSH, v))
+    normalVelocity = property(lambda s: s.dev.get(L.D_NORMAL_VELOCITY), lambda s, v: s.dev.set(L.D_NORMAL_VELOCITY, v))
+    layerThickness = property(lambda s: s.dev.get(L.D_LAYER_THICKNESS), lambda s, v: s.dev.set(L.D_LAYER_THICKNESS, v))
+
+
+def ocn_init_shadows(Prog: PrognosticVars, Diag=None, Tend=None) -> ShadowPrognosticVars:
+    """ocn_init_shadows(Prog, Diag, Tend; backend) (init.jl:32-40)."""
+    return ShadowPrognosticVars(Prog)
+
+
+def autodiff_reverse_run_loop(timestep: float, Prog: PrognosticVars, d_Prog: ShadowPrognosticVars, Diag, Tend, Setup,
+                              stepper, nsteps: int, seed: str | None = "ssh2") -> float:
+    """`autodiff(Enzyme.Reverse, ocn_run_loop, Duplicated(sumCPU, ..), .., Duplicated(Prog, d_Prog), ..)`
+    (test_Enzyme_end2end.jl:78-96): runs `nsteps` RungeKutta4 steps recording the trajectory, then the reverse
+    sweep.  With `seed="ssh2"` the objective is the run loop's sum of squared SSH (run_loop.jl:24-44) and its
+    value is returned; with `seed=None` whatever the caller stored in `d_Prog` is the adjoint of the final state.
+    On return d_Prog holds dJ/d(initial normalVelocity, layerThickness)."""
+    if stepper is not RungeKutta4:
+        raise MokaError("autodiff_reverse_run_loop: the hand-written adjoint covers the fused RungeKutta4 stepper")
+    h = Prog.dev.handle
+    L.check(L.lib().mokab_tape_begin(h, int(nsteps)))
+    L.check(L.lib().mokab_timestep_rk4(h, float(timestep), int(nsteps), L.RK4_FUSED))
+    J = float("nan")
+    if seed is not None:
+        if seed != "ssh2":
+            raise MokaError("autodiff_reverse_run_loop: unknown seed")
+        J = reduce_sum(Prog, "ssh2")
+        L.check(L.lib().mokab_adjoint_seed(h, L.SUM_SSH2))
+    L.check(L.lib().mokab_adjoint_rk4(h))
+    return J
 
 
 def reference_dt(mesh: Mesh) -> float:

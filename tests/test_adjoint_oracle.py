@@ -60,3 +60,59 @@ def test_step_vjp_dot_product_identity():
     bu, bh = A.rk4_step_vjp(m, u, h, dt, lu, lh)
     rhs = du @ bu + dh @ bh
     assert abs(lhs - rhs) <= 1e-7 * max(abs(lhs), abs(rhs))
+
+
+def _gather_form_step_vjp(m, u, h, dt, lam_u, lam_h):
+    """numpy emulation of csrc/kernels_adjoint.cuh + adjoint_step (moka_b200.cu): the GATHER formulation with the
+    transposed Coriolis stencil, q = invArea * kbar_h, and the fused RK bookkeeping, statement for statement."""
+    nC, nE = m["nCells"], m["nEdges"]
+    c1, c2 = m["cellsOnEdge"][:, 0] - 1, m["cellsOnEdge"][:, 1] - 1
+    masked = c1 == c2
+    gdc, dv, inv_area = O.GRAVITY * (1.0 / m["dcEdge"]), m["dvEdge"], 1.0 / m["areaCell"]
+    eoe, w, ne, f = m["edgesOnEdge"], m["weightsOnEdge"], m["nEdgesOnEdge"], m["fEdge"]
+    rows = [[] for _ in range(nE)]                                    # ensure_adjoint_mesh: row x <- (e, w[i,e]*f[x])
+    for e in range(nE):
+        for i in range(ne[e]):
+            x = eoe[e, i] - 1
+            if x >= 0:
+                rows[x].append((e, w[e, i] * f[x]))
+    eoc, n_eoc = m["edgesOnCell"], m["nEdgesOnCell"]
+    a = [dt / 2.0, dt / 2.0, dt]
+    b = [dt / 6.0, dt / 3.0, dt / 3.0, dt / 6.0]
+    ys = A.rk4_stage_states(m, u, h, dt)
+    acc_u = acc_h = ku = kq = None
+    for s in (4, 3, 2, 1):
+        uY, hY = ys[s - 1]
+        if s == 4:
+            ku, kq = b[3] * lam_u, b[3] * inv_area * lam_h
+        G_e = dv * (np.where(masked, 0.0, kq[c2]) - kq[c1])
+        yb_u = 0.5 * (hY[c1] + np.where(masked, hY[c1], hY[c2])) * G_e
+        for x in range(nE):
+            for e, wt in rows[x]:
+                yb_u[x] += wt * ku[e]
+        yb_h = np.zeros(nC)
+        for c in range(nC):
+            for i in range(n_eoc[c]):
+                e = eoc[c, i] - 1
+                sgn = -1.0 if c1[e] == c else 1.0
+                other = c2[e] if c1[e] == c else c1[e]
+                G = dv[e] * sgn * (kq[c] if masked[e] else kq[c] - kq[other])
+                yb_h[c] += (1.0 if masked[e] else 0.5) * uY[e] * G
+                if not masked[e]:
+                    yb_h[c] -= sgn * gdc[e] * ku[e]
+        acc_u = (lam_u if s == 4 else acc_u) + yb_u
+        acc_h = (lam_h if s == 4 else acc_h) + yb_h
+        if s > 1:
+            ku = b[s - 2] * lam_u + a[s - 2] * yb_u
+            kq = inv_area * (b[s - 2] * lam_h + a[s - 2] * yb_h)
+    return acc_u, acc_h
+
+
+def test_gather_form_of_the_cuda_adjoint_equals_the_scatter_oracle():
+    for kelvin in (False, True):
+        m, u, h, dt = _case(8, kelvin)
+        rng = np.random.default_rng(2)
+        lu, lh = rng.standard_normal(m["nEdges"]), rng.standard_normal(m["nCells"])
+        gu, gh = _gather_form_step_vjp(m, u, h, dt, lu, lh)
+        su, sh = A.rk4_step_vjp(m, u, h, dt, lu, lh)
+        assert O.rel_l2(gu, su) < 1e-13 and O.rel_l2(gh, sh) < 1e-13

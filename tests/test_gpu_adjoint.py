@@ -1,0 +1,105 @@
+"""GPU: the hand-written reverse mode of the fused RK4 path (csrc/kernels_adjoint.cuh) against the adjoint
+oracle (scatter form, oracle/adjoint_oracle.py) and against the reference's own acceptance criterion for
+gradients -- central finite differences of J = sum ssh^2 (test/enzyme/test_Enzyme_end2end.jl:112-180)."""
+import numpy as np
+import pytest
+
+import adjoint_oracle as A
+import moka_b200 as mb
+import moka_oracle_c as OC
+from conftest import hex_mesh, rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL64, TOL32 = 1e-12, 1e-3
+
+
+def _case(nx, kelvin):
+    if kelvin:
+        m = mb.channel_hex(nx, nx, 1.0e7 / nx)
+        ssh, u, h = mb.kelvinWave(m).initial_state()
+        mo = OC.apply_boundary_mask(m)
+        OC.sign_index_fields(mo)
+    else:
+        m = mo = hex_mesh(nx)
+        ssh, u, h = mb.inertialGravityWave(m).initial_state()
+    return m, mo, ssh, u, h, mb.cfl_dt(m["dc"])
+
+
+@pytest.mark.parametrize("kelvin", [False, True])
+@pytest.mark.parametrize("renumber", [True, False])
+def test_gradient_of_sum_ssh2_matches_adjoint_oracle(backend, kelvin, renumber):
+    m, mo, ssh, u, h, dt = _case(24, kelvin)
+    nsteps = 6
+    mesh = mb.Mesh(m, backend, renumber=renumber)
+    prog = mb.PrognosticVars(ssh, u, h, 2, mesh)
+    d_prog = mb.ocn_init_shadows(prog)
+    J = mb.autodiff_reverse_run_loop(dt, prog, d_prog, None, None, None, mb.RungeKutta4, nsteps)
+    Jo, gu, gh = A.gradient_sum_ssh2(mo, u, h, dt, nsteps)
+    assert abs(J - Jo) <= 1e-12 * Jo
+    du, dh = d_prog.normalVelocity, d_prog.layerThickness
+    assert rel_l2(du, gu) <= TOL64 and rel_l2(dh, gh) <= TOL64
+    assert np.all(d_prog.ssh == 0)                # folded into d_layerThickness
+    # the forward state is untouched by the reverse sweep
+    prog2 = mb.PrognosticVars(ssh, u, h, 2, mesh)
+    mb.ocn_timestep(dt, prog2, None, None, None, mb.RungeKutta4, nsteps=nsteps)
+    assert np.array_equal(prog.layerThickness, prog2.layerThickness) and np.array_equal(prog.normalVelocity, prog2.normalVelocity)
+
+
+def test_gradient_matches_central_finite_differences_on_the_gpu(backend):
+    """The reference's check (test_Enzyme_end2end.jl:112-180): perturb one layerThickness / normalVelocity entry by a
+    relative eps, difference J of two forward runs -- both runs on the GPU here."""
+    m, mo, ssh, u, h, dt = _case(16, False)
+    nsteps = 5
+    mesh = mb.Mesh(m, backend)
+    prog = mb.PrognosticVars(ssh, u, h, 2, mesh)
+    d_prog = mb.ocn_init_shadows(prog)
+    mb.autodiff_reverse_run_loop(dt, prog, d_prog, None, None, None, mb.RungeKutta4, nsteps)
+    du, dh = d_prog.normalVelocity, d_prog.layerThickness
+
+    def J_of(u_, h_):
+        p = mb.PrognosticVars(h_ - 1000.0, u_, h_, 2, mesh)
+        return mb.ocn_run_loop(dt, p, None, None, None, mb.RungeKutta4, nsteps, sum_ssh2=True)
+
+    for k in (4, 100):                                                   # the reference checks index 5 (1-based)
+        hp, hm = h.copy(), h.copy()
+        hp[k] += abs(h[k]) * 1e-7
+        hm[k] -= abs(h[k]) * 1e-7
+        fd = (J_of(u, hp) - J_of(u, hm)) / (hp[k] - hm[k])
+        assert abs(dh[k] - fd) < 1e-4                                    # atol of test_Enzyme_end2end.jl:176
+        up, um = u.copy(), u.copy()
+        up[k] += abs(u[k]) * 1e-4
+        um[k] -= abs(u[k]) * 1e-4
+        fd = (J_of(up, h) - J_of(um, h)) / (up[k] - um[k])
+        assert abs(du[k] - fd) < 1e-2                                    # atol of :177
+        assert abs(du[k] - fd) < 1e-5 * abs(du[k]) + 1e-4
+
+
+def test_user_seed_and_float32(backend):
+    """A caller-provided adjoint of the final state (seed=None) and the Float32 path."""
+    m, mo, ssh, u, h, dt = _case(16, False)
+    rng = np.random.default_rng(5)
+    lu, lh = rng.standard_normal(m["nEdges"]), rng.standard_normal(m["nCells"])
+    want_u, want_h = lu.copy(), lh.copy()
+    traj = A.run_forward(mo, u, h, dt, 3)
+    for n in (2, 1, 0):
+        want_u, want_h = A.rk4_step_vjp(mo, traj[n][0], traj[n][1], dt, want_u, want_h)
+    for dtype, tol in ((np.float64, TOL64), (np.float32, TOL32)):
+        mesh = mb.Mesh(m, backend)
+        prog = mb.PrognosticVars(ssh.astype(dtype), u.astype(dtype), h.astype(dtype), 2, mesh)
+        d_prog = mb.ocn_init_shadows(prog)
+        d_prog.normalVelocity, d_prog.layerThickness = lu.astype(dtype), lh.astype(dtype)
+        mb.autodiff_reverse_run_loop(dt, prog, d_prog, None, None, None, mb.RungeKutta4, 3, seed=None)
+        assert rel_l2(d_prog.normalVelocity, want_u) <= tol and rel_l2(d_prog.layerThickness, want_h) <= tol
+
+
+def test_tape_overflow_and_stepper_errors(backend):
+    m, mo, ssh, u, h, dt = _case(8, False)
+    mesh = mb.Mesh(m, backend)
+    prog = mb.PrognosticVars(ssh, u, h, 2, mesh)
+    d_prog = mb.ocn_init_shadows(prog)
+    with pytest.raises(mb.MokaError):
+        mb.autodiff_reverse_run_loop(dt, prog, d_prog, None, None, None, mb.ForwardEuler, 2)
+    from moka_b200 import _lib as L
+    L.check(L.lib().mokab_tape_begin(prog.dev.handle, 2))
+    with pytest.raises(mb.MokaError, match="tape is full"):
+        mb.ocn_timestep(dt, prog, None, None, None, mb.RungeKutta4, nsteps=3)
