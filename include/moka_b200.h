@@ -177,6 +177,11 @@ int  mokab_gradient_on_edge(mokab_ctx *ctx, const mokab_mesh *mesh, const double
 int  mokab_divergence_on_cell(mokab_ctx *ctx, const mokab_mesh *mesh, const double *vec_edge, double *div_cell);
 int  mokab_curl_on_vertex(mokab_ctx *ctx, const mokab_mesh *mesh, const double *vec_edge, double *curl_vertex_inout);
 int  mokab_interpolate_cell2edge(mokab_ctx *ctx, const mokab_mesh *mesh, const double *cell_value, double *edge_value);
+/* Reverse mode of the two operators the reference differentiates with Enzyme (test/enzyme/
+ * test_Enzyme_Operators.jl:40-125 GradientOnEdge!, :127-227 DivergenceOnCell!): given the adjoint of the output,
+ * return the adjoint of the input (the `Duplicated(Scalar, d_Scalar)` / `Duplicated(VecEdge, d_VecEdge)` shadows). */
+int  mokab_gradient_on_edge_vjp(mokab_ctx *ctx, const mokab_mesh *mesh, const double *d_grad_edge, double *d_scalar_cell);
+int  mokab_divergence_on_cell_vjp(mokab_ctx *ctx, const mokab_mesh *mesh, const double *d_div_cell, double *d_vec_edge);
 
 /* ---- src/forward entry points ------------------------------------------------------------------ */
 /* ocn_run_loop + ocn_timestep(::ForwardEuler): `nsteps` steps of src/forward/time_integration.jl:

@@ -45,8 +45,15 @@ struct AdjArgs {
 };
 
 // MODE: 0 = FIRST (RK stage 4: kbar = b_4 lam', acc = lam' + ybar), 1 = MIDDLE (stages 3, 2), 2 = LAST (stage 1)
-template <class R, int MODE>
-__global__ void __launch_bounds__(kThreads, 4)
+// S2TT / ST: compile-time row widths of the transposed Coriolis stencil / edgesOnCell (0 = runtime loops).  With
+// compile-time widths all index and weight loads of a row are issued first, then all gathers, so ~20 (edge) /
+// ~30 (cell) independent loads are in flight per thread -- the kernel is latency-bound otherwise (ncu: 0.24
+// eligible warps per cycle with rolled loops).
+#ifndef MOKAB_ADJ_MINBLOCKS
+#define MOKAB_ADJ_MINBLOCKS 4
+#endif
+template <class R, int MODE, int S2TT, int ST>
+__global__ void __launch_bounds__(kThreads, MOKAB_ADJ_MINBLOCKS)
 k_rk_stage_adj(const AdjArgs<R> A)
 {
     const int nE = A.nE, nC = A.nC;
@@ -60,14 +67,30 @@ k_rk_stage_adj(const AdjArgs<R> A)
         const int n = ld_stream(A.nEoET + e);
         const R lam = MODE == 2 ? R(0) : A.lamU[e];
         const R accIn = MODE == 0 ? lam : A.accU[e];
-        const R q1 = kq(c.x), h1 = __ldg(A.hY + c.x);
         const bool masked = c.x == c.y;
-        const R q2 = masked ? R(0) : kq(c.y), h2 = masked ? h1 : __ldg(A.hY + c.y);
-        const R G = ld_stream(A.dv + e) * (q2 - q1);
-        R yb = R(0.5) * (h1 + h2) * G;
-        for (int j = 0; j < n; ++j) {
-            const int x = ld_stream(A.eoeT + (size_t)j * nE + e);
-            yb += ld_stream(A.wfT + (size_t)j * nE + e) * ku(x);
+        R yb;
+        if constexpr (S2TT != 0) {
+            int idx[S2TT ? S2TT : 1];
+            R w[S2TT ? S2TT : 1], kk[S2TT ? S2TT : 1];
+#pragma unroll
+            for (int j = 0; j < S2TT; ++j) idx[j] = j < n ? ld_stream(A.eoeT + (size_t)j * nE + e) : e;
+#pragma unroll
+            for (int j = 0; j < S2TT; ++j) w[j] = j < n ? ld_stream(A.wfT + (size_t)j * nE + e) : R(0);
+#pragma unroll
+            for (int j = 0; j < S2TT; ++j) kk[j] = ku(idx[j]);
+            const R q1 = kq(c.x), h1 = __ldg(A.hY + c.x);
+            const R q2 = masked ? R(0) : kq(c.y), h2 = masked ? h1 : __ldg(A.hY + c.y);
+            yb = R(0.5) * (h1 + h2) * (ld_stream(A.dv + e) * (q2 - q1));
+#pragma unroll
+            for (int j = 0; j < S2TT; ++j) yb += w[j] * kk[j];
+        } else {
+            const R q1 = kq(c.x), h1 = __ldg(A.hY + c.x);
+            const R q2 = masked ? R(0) : kq(c.y), h2 = masked ? h1 : __ldg(A.hY + c.y);
+            yb = R(0.5) * (h1 + h2) * (ld_stream(A.dv + e) * (q2 - q1));
+            for (int j = 0; j < n; ++j) {
+                const int x = ld_stream(A.eoeT + (size_t)j * nE + e);
+                yb += ld_stream(A.wfT + (size_t)j * nE + e) * ku(x);
+            }
         }
         A.accU[e] = accIn + yb;
         if (MODE != 2) A.kuOut[e] = A.bPrev * lam + A.aPrev * yb;
@@ -80,17 +103,50 @@ k_rk_stage_adj(const AdjArgs<R> A)
         const R accIn = MODE == 0 ? lam : A.accH[cc];
         const R qc = kq(cc);
         R yb = R(0);
-        for (int i = 0; i < n; ++i) {
-            const int ex = ld_stream(A.eoc + (size_t)i * nC + cc);
-            const int e = ex >> 1;
-            const R sgn = (ex & 1) ? R(1) : R(-1);
-            const int2 cs = __ldg(A.ce + e);
-            const bool masked = cs.x == cs.y;
-            const int other = cs.x == cc ? cs.y : cs.x;
-            const R kue = ku(e);
-            const R G = __ldg(A.dv + e) * sgn * (masked ? qc : qc - kq(other));
-            yb += (masked ? R(1) : R(0.5)) * __ldg(A.uY + e) * G;
-            if (!masked) yb -= sgn * __ldg(A.gdc + e) * kue;
+        if constexpr (ST != 0) {
+            int ee[ST ? ST : 1];
+#pragma unroll
+            for (int i = 0; i < ST; ++i) ee[i] = i < n ? ld_stream(A.eoc + (size_t)i * nC + cc) : -1;
+            // two half-rows at a time: 5 gathers per slot would not fit the register budget for a whole row
+            constexpr int CH = (ST % 3 == 0) ? 3 : (ST % 2 == 0 ? 2 : 1);
+#pragma unroll
+            for (int i0 = 0; i0 < ST; i0 += CH) {
+                int2 cs[CH];
+                R kue[CH], dd[CH], uu[CH], gg[CH], qo[CH];
+#pragma unroll
+                for (int i = 0; i < CH; ++i) {
+                    const int e = ee[i0 + i] >= 0 ? (ee[i0 + i] >> 1) : 0;
+                    cs[i] = __ldg(A.ce + e);
+                    kue[i] = ku(e);
+                    dd[i] = __ldg(A.dv + e);
+                    uu[i] = __ldg(A.uY + e);
+                    gg[i] = __ldg(A.gdc + e);
+                }
+#pragma unroll
+                for (int i = 0; i < CH; ++i) qo[i] = kq(cs[i].x == cc ? cs[i].y : cs[i].x);
+#pragma unroll
+                for (int i = 0; i < CH; ++i) {
+                    if (ee[i0 + i] < 0) continue;
+                    const R sgn = (ee[i0 + i] & 1) ? R(1) : R(-1);
+                    const bool masked = cs[i].x == cs[i].y;
+                    const R G = dd[i] * sgn * (masked ? qc : qc - qo[i]);
+                    yb += (masked ? R(1) : R(0.5)) * uu[i] * G;
+                    if (!masked) yb -= sgn * gg[i] * kue[i];
+                }
+            }
+        } else {
+            for (int i = 0; i < n; ++i) {
+                const int ex = ld_stream(A.eoc + (size_t)i * nC + cc);
+                const int e = ex >> 1;
+                const R sgn = (ex & 1) ? R(1) : R(-1);
+                const int2 cs = __ldg(A.ce + e);
+                const bool masked = cs.x == cs.y;
+                const int other = cs.x == cc ? cs.y : cs.x;
+                const R kue = ku(e);
+                const R G = __ldg(A.dv + e) * sgn * (masked ? qc : qc - kq(other));
+                yb += (masked ? R(1) : R(0.5)) * __ldg(A.uY + e) * G;
+                if (!masked) yb -= sgn * __ldg(A.gdc + e) * kue;
+            }
         }
         A.accH[cc] = accIn + yb;
         if (MODE != 2) A.kqOut[cc] = ld_stream(A.invArea + cc) * (A.bPrev * lam + A.aPrev * yb);
@@ -115,6 +171,41 @@ k_seed_ssh2(int64_t n, const R *__restrict__ h, const R *__restrict__ H, R *__re
 {
     const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (c < n) dssh[c] = R(2) * (h[c] - H[c]);
+}
+
+// ---- operator-level transposes (test/enzyme/test_Enzyme_Operators.jl differentiates exactly these two) -------
+// GradientOnEdge (Operators.jl:84-100): grad[e] = (s[c2] - s[c1]) / dc[e]
+//   => sbar[c] = sum_{e of c} sign(c,e) * gbar[e] / dc[e]      (sign = edgeSignOnCell: -1 on the c1 side)
+__global__ void __launch_bounds__(256)
+k_gradient_on_edge_vjp(int nC, const int32_t *__restrict__ eoc, const int32_t *__restrict__ sgn, const uint8_t *__restrict__ nEoC,
+                       const int2 *__restrict__ ce, const double *__restrict__ dc, const double *__restrict__ gbar,
+                       double *__restrict__ sbar)
+{
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= nC) return;
+    double acc = 0.0;
+    const int n = nEoC[c];
+    for (int i = 0; i < n; ++i) {
+        const int e = eoc[(size_t)i * nC + c];
+        const int2 cs = ce[e];
+        if (cs.x == cs.y) continue;                       // masked edge: zero gradient
+        acc += (double)sgn[(size_t)i * nC + c] * gbar[e] / dc[e];
+    }
+    sbar[c] = acc;
+}
+
+// DivergenceOnCell (Operators.jl:12-44): div[c] = -(1/area[c]) * sum_i sign[i,c] * dv[e_i] * F[e_i]
+//   => Fbar[e] = dv[e] * (dbar[c1]/area[c1] - dbar[c2]/area[c2])
+__global__ void __launch_bounds__(256)
+k_divergence_on_cell_vjp(int nE, const int2 *__restrict__ ce, const double *__restrict__ dv, const double *__restrict__ area,
+                         const double *__restrict__ dbar, double *__restrict__ fbar)
+{
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e >= nE) return;
+    const int2 c = ce[e];
+    const double t1 = dbar[c.x] / area[c.x];
+    const double t2 = c.x == c.y ? 0.0 : dbar[c.y] / area[c.y];
+    fbar[e] = dv[e] * (t1 - t2);
 }
 
 }  // namespace adjoint

@@ -728,9 +728,17 @@ static void adjoint_step(mokab_state *st, int64_t k)
         B.kuIn = t->kbU[s & 1].p; B.kqIn = t->kbH[s & 1].p;
         B.kuOut = t->kbU[(s - 1) & 1].p; B.kqOut = t->kbH[(s - 1) & 1].p;
         B.aPrev = s > 1 ? (R)a[s - 2] : R(0); B.bPrev = s > 1 ? (R)b[s - 2] : R(0);
-        if (s == 4) adjoint::k_rk_stage_adj<R, 0><<<grid, adjoint::kThreads, 0, ctx->stream>>>(B);
-        else if (s > 1) adjoint::k_rk_stage_adj<R, 1><<<grid, adjoint::kThreads, 0, ctx->stream>>>(B);
-        else adjoint::k_rk_stage_adj<R, 2><<<grid, adjoint::kThreads, 0, ctx->stream>>>(B);
+        const bool hex = m->S2T == 10 && m->S == 6;
+        const int mode = s == 4 ? 0 : s > 1 ? 1 : 2;
+#define MOKAB_ADJ_LAUNCH(MODE)                                                                                         \
+    do {                                                                                                               \
+        if (hex) adjoint::k_rk_stage_adj<R, MODE, 10, 6><<<grid, adjoint::kThreads, 0, ctx->stream>>>(B);              \
+        else adjoint::k_rk_stage_adj<R, MODE, 0, 0><<<grid, adjoint::kThreads, 0, ctx->stream>>>(B);                   \
+    } while (0)
+        if (mode == 0) MOKAB_ADJ_LAUNCH(0);
+        else if (mode == 1) MOKAB_ADJ_LAUNCH(1);
+        else MOKAB_ADJ_LAUNCH(2);
+#undef MOKAB_ADJ_LAUNCH
         MOKAB_CUDA(cudaGetLastError());
         ctx->launches++;
     }
@@ -1120,6 +1128,33 @@ int mokab_interpolate_cell2edge(mokab_ctx *ctx, const mokab_mesh *m, const doubl
         op_common(ctx, m, cell_value, m->nC, m->dPermC.p, edge_value, m->nE, m->dPermE.p, false, B);
         LAUNCH(ctx, ref::k_interpolate_cell2edge, nblk(m->nE), 256, (int)m->nE, m->ce.p, (const double *)B.in_p.p, B.out_p.p);
         op_finish(ctx, edge_value, m->nE, m->dPermE.p, B);
+    });
+}
+
+// reverse mode of the two operators test/enzyme/test_Enzyme_Operators.jl differentiates
+int mokab_gradient_on_edge_vjp(mokab_ctx *ctx, const mokab_mesh *m, const double *d_grad_edge, double *d_scalar_cell)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(ctx && m && d_grad_edge && d_scalar_cell, "gradient_on_edge_vjp: NULL argument");
+        ctx->bind();
+        OpBufs B;
+        op_common(ctx, m, d_grad_edge, m->nE, m->dPermE.p, d_scalar_cell, m->nC, m->dPermC.p, false, B);
+        LAUNCH(ctx, adjoint::k_gradient_on_edge_vjp, nblk(m->nC), 256, (int)m->nC, m->eoc.p, m->sgnC.p, m->nEoC.p, m->ce.p, m->dc.p,
+               (const double *)B.in_p.p, B.out_p.p);
+        op_finish(ctx, d_scalar_cell, m->nC, m->dPermC.p, B);
+    });
+}
+
+int mokab_divergence_on_cell_vjp(mokab_ctx *ctx, const mokab_mesh *m, const double *d_div_cell, double *d_vec_edge)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(ctx && m && d_div_cell && d_vec_edge, "divergence_on_cell_vjp: NULL argument");
+        ctx->bind();
+        OpBufs B;
+        op_common(ctx, m, d_div_cell, m->nC, m->dPermC.p, d_vec_edge, m->nE, m->dPermE.p, false, B);
+        LAUNCH(ctx, adjoint::k_divergence_on_cell_vjp, nblk(m->nE), 256, (int)m->nE, m->ce.p, m->dv.p, m->area.p,
+               (const double *)B.in_p.p, B.out_p.p);
+        op_finish(ctx, d_vec_edge, m->nE, m->dPermE.p, B);
     });
 }
 

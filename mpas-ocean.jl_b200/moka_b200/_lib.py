@@ -54,6 +54,7 @@ SYMBOLS = [
     "mokab_state_set_async", "mokab_state_get_async", "mokab_state_synchronize",
     "mokab_diagnostic_compute", "mokab_compute_normal_velocity_tendency", "mokab_compute_layer_thickness_tendency",
     "mokab_gradient_on_edge", "mokab_divergence_on_cell", "mokab_curl_on_vertex", "mokab_interpolate_cell2edge",
+    "mokab_gradient_on_edge_vjp", "mokab_divergence_on_cell_vjp",
     "mokab_timestep_forward_euler", "mokab_timestep_rk4", "mokab_reduce",
     "mokab_tape_begin", "mokab_tape_length", "mokab_adjoint_seed", "mokab_adjoint_rk4",
     "mokab_halo_setup", "mokab_halo_pack", "mokab_halo_unpack", "mokab_rk4_stage", "mokab_rk4_finish_step",
@@ -83,6 +84,7 @@ def lib():
             "mokab_diagnostic_compute": [vp], "mokab_compute_normal_velocity_tendency": [vp],
             "mokab_compute_layer_thickness_tendency": [vp],
             "mokab_gradient_on_edge": [vp, vp, _F64P, _F64P], "mokab_divergence_on_cell": [vp, vp, _F64P, _F64P],
+            "mokab_gradient_on_edge_vjp": [vp, vp, _F64P, _F64P], "mokab_divergence_on_cell_vjp": [vp, vp, _F64P, _F64P],
             "mokab_curl_on_vertex": [vp, vp, _F64P, _F64P], "mokab_interpolate_cell2edge": [vp, vp, _F64P, _F64P],
             "mokab_timestep_forward_euler": [vp, dbl, i64], "mokab_timestep_rk4": [vp, dbl, i64, C.c_int],
             "mokab_reduce": [vp, C.c_int, C.POINTER(dbl)],

@@ -315,6 +315,17 @@ def interpolateCell2Edge(edge_value, cell_value, mesh: Mesh):
     return _op(L.lib().mokab_interpolate_cell2edge, mesh, cell_value, mesh.nEdges, edge_value)
 
 
+def GradientOnEdge_vjp(d_grad, mesh: Mesh):
+    """Adjoint of GradientOnEdge!: d_Scalar for a given d_gradNum (autodiff(Reverse, gradient_test, ...),
+    test/enzyme/test_Enzyme_Operators.jl:47-64)."""
+    return _op(L.lib().mokab_gradient_on_edge_vjp, mesh, d_grad, mesh.nCells)
+
+
+def DivergenceOnCell_vjp(d_div, mesh: Mesh):
+    """Adjoint of DivergenceOnCell!: d_VecEdge for a given d_divNum (test_Enzyme_Operators.jl:130-152)."""
+    return _op(L.lib().mokab_divergence_on_cell_vjp, mesh, d_div, mesh.nEdges)
+
+
 # ---- src/forward ------------------------------------------------------------------------------------------
 class ForwardEuler:       # time_integration.jl:4
     pass

@@ -103,3 +103,37 @@ def test_tape_overflow_and_stepper_errors(backend):
     L.check(L.lib().mokab_tape_begin(prog.dev.handle, 2))
     with pytest.raises(mb.MokaError, match="tape is full"):
         mb.ocn_timestep(dt, prog, None, None, None, mb.RungeKutta4, nsteps=3)
+
+
+def test_operator_adjoints_like_test_Enzyme_Operators(backend):
+    """test/enzyme/test_Enzyme_Operators.jl: reverse mode of GradientOnEdge! (seed d_gradNum[1] = 1, read d_Scalar[1],
+    :47-64) and of DivergenceOnCell! (seed d_divNum[1] = 1, read d_VecEdge[2], :130-152) against central finite
+    differences with a relative step of 1e-8 (atol 1e-6, :121 and :221), on the 48x48 planar test mesh and fields."""
+    import moka_oracle as O
+    m = hex_mesh(48, 48, 1000.0)
+    mesh = mb.Mesh(m, backend)
+    f = O.planar_test_fields(m)
+    eps = 1e-8
+    # gradient: input index kBegin = 1, output index kEnd = 1 (1-based in the reference)
+    seed = np.zeros(m["nEdges"]); seed[0] = 1.0
+    rev = mb.GradientOnEdge_vjp(seed, mesh)[0]
+    sp, sm = f["h"].copy(), f["h"].copy()
+    sp[0] += abs(sp[0]) * eps
+    sm[0] -= abs(sm[0]) * eps
+    fd = (mb.GradientOnEdge(None, sp, mesh)[0] - mb.GradientOnEdge(None, sm, mesh)[0]) / (sp[0] - sm[0])
+    assert abs(rev - fd) < 1e-6
+    # divergence: input index kBegin = 2, output index kEnd = 1
+    seed = np.zeros(m["nCells"]); seed[0] = 1.0
+    rev = mb.DivergenceOnCell_vjp(seed, mesh)[1]
+    vp, vm = f["F_edge"].copy(), f["F_edge"].copy()
+    vp[1] += abs(vp[1]) * eps
+    vm[1] -= abs(vm[1]) * eps
+    fd = (mb.DivergenceOnCell(None, vp, None, mesh)[0] - mb.DivergenceOnCell(None, vm, None, mesh)[0]) / (vp[1] - vm[1])
+    assert abs(rev - fd) < 1e-6
+    # and the full transposes: <A x, y> == <x, A^T y> for random x, y
+    rng = np.random.default_rng(7)
+    x, y = rng.standard_normal(m["nCells"]), rng.standard_normal(m["nEdges"])
+    lhs, rhs = mb.GradientOnEdge(None, x, mesh) @ y, x @ mb.GradientOnEdge_vjp(y, mesh)
+    assert abs(lhs - rhs) <= 1e-12 * abs(lhs)
+    lhs, rhs = mb.DivergenceOnCell(None, y, None, mesh) @ x, y @ mb.DivergenceOnCell_vjp(x, mesh)
+    assert abs(lhs - rhs) <= 1e-12 * abs(lhs)
