@@ -26,8 +26,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "mpas-ocean.jl_b200"))
 
 WORKLOADS = {"igw64": 64, "igw512": 512, "igw1024": 1024, "igw2048": 2048, "igw4096": 4096, "kelvin1024": 1024}
-# algorithmic bytes per cell per RK4 step on a planar hex mesh (SURVEY.md 8d / BASELINE.md section 3)
+# algorithmic bytes per cell per RK4 step on a planar hex mesh (SURVEY.md 8d / BASELINE.md section 3): every distinct
+# array element moved once per stage, edgesOnEdge included
 ALGO_BYTES_PER_CELL_STEP = {"f64": 2400.0, "f32": 1536.0}
+# the same tally for the kernel that rebuilds edgesOnEdge from edgesOnCell: per stage and cell
+# 3 edges x (40 B of indices -> 1 position byte) less
+ALGO_BYTES_PER_CELL_STEP_DERIVED = {"f64": 2400.0 - 4 * 3 * 39, "f32": 1536.0 - 4 * 3 * 39}
+
+
+def algo_bytes_per_cell_step(dtype: str, derived_fraction: float) -> float:
+    return derived_fraction * ALGO_BYTES_PER_CELL_STEP_DERIVED[dtype] + (1.0 - derived_fraction) * ALGO_BYTES_PER_CELL_STEP[dtype]
 
 
 def measured_peak_gbs():
@@ -102,8 +110,9 @@ def run_b200(args):
     nC, nE = m["nCells"], m["nEdges"]
     backend = mb.B200(local)
     t0 = time.time()
-    mesh = mb.Mesh(m, backend)
+    mesh = mb.Mesh(m, backend, explicit_eoe=args.explicit_eoe)
     t_mesh = time.time() - t0
+    nblk, nder = mesh.derived_blocks()
     prog = mb.PrognosticVars(ssh.astype(npdt), u.astype(npdt), h.astype(npdt), 2, mesh)
     diag, tend = mb.DiagnosticVars(prog), mb.TendencyVars(prog)
     K, W = args.steps, max(args.warmup, 3)
@@ -156,9 +165,10 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel (k_rk_stage) -----------------------------------------------------------
     peak, peak_src = measured_peak_gbs()
-    algo_bytes_per_launch = ALGO_BYTES_PER_CELL_STEP[args.dtype] / 4.0 * nC
+    algo_bytes_per_launch = algo_bytes_per_cell_step(args.dtype, nder / nblk) / 4.0 * nC
     avg_launch_s = (ms * 1e-3) / stage_launches
     achieved = algo_bytes_per_launch / avg_launch_s / 1e9
+    survey_rate = ALGO_BYTES_PER_CELL_STEP[args.dtype] / 4.0 * nC / avg_launch_s / 1e9
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
@@ -174,7 +184,8 @@ def run_b200(args):
                                 f"inertial gravity wave, {nx}x{nx} periodic planar hex mesh") + f" ({nC} cells, {nE} edges), "
                                f"{'Float64' if args.dtype == 'f64' else 'Float32'} RK4, dt={dt:.4g}s",
                    "name": args.workload, "l2": "inputs larger than L2 (no flush)" if nx >= 1024 else "fits in L2",
-                   "mesh_gen_s": round(t_gen, 2), "mesh_upload_s": round(t_mesh, 2)},
+                   "mesh_gen_s": round(t_gen, 2), "mesh_upload_s": round(t_mesh, 2),
+                   "blocks_rebuilding_edgesOnEdge": [int(nder), int(nblk)]},
         "clocks": clocks,
         "e2e": {"value": nC / e2e_s, "unit": "cell-steps/s", "h2d_bytes_per_step": int((nE + nC) * item),
                 "d2h_bytes_per_step": int(nC * item), "ms_per_step": e2e_s * 1e3, "steps": Ke,
@@ -182,7 +193,12 @@ def run_b200(args):
         "gpu_launches": int(launches_total),
         "roofline": {"bound": "hbm", "kernel": "k_rk_stage", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": algo_bytes_per_launch, "avg_launch_ms": avg_launch_s * 1e3},
+                     "algorithmic_bytes_per_launch": algo_bytes_per_launch, "avg_launch_ms": avg_launch_s * 1e3,
+                     "bytes_per_cell_step": algo_bytes_per_launch * 4.0 / nC,
+                     "rate_if_edgesOnEdge_were_read": survey_rate,
+                     "note": "achieved = bytes this kernel must move (edgesOnEdge rebuilt from edgesOnCell where the mesh allows, "
+                             "DESIGN.md section 5) / launch time; rate_if_edgesOnEdge_were_read applies SURVEY.md 8d's 2400 B (F64) "
+                             "/ 1536 B (F32) per cell-step to the same time"},
     }
     if not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline(m, (ssh, u, h), dt, budget_s=args.cpu_budget, kelvin=kelvin)
@@ -265,6 +281,8 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-overlap", dest="no_overlap", action="store_true", help="multi-GPU: exchange after each full stage")
     ap.add_argument("--no-graph", dest="no_graph", action="store_true", help="multi-GPU: do not capture steps into a CUDA graph")
+    ap.add_argument("--explicit-eoe", dest="explicit_eoe", action="store_true",
+                    help="read edgesOnEdge from memory instead of rebuilding it from edgesOnCell (ablation)")
     ap.add_argument("--quick", action="store_true", help="profiling runs: no clock-sampling load loop, one e2e step")
     args = ap.parse_args()
     if args.workload is None:

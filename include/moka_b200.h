@@ -78,7 +78,9 @@ enum {
 
 /* mesh_create flags */
 enum {
-    MOKAB_MESH_RENUMBER = 1u  /* locality renumbering (space-filling curve); 0 keeps the caller's order */
+    MOKAB_MESH_RENUMBER = 1u, /* locality renumbering (space-filling curve); 0 keeps the caller's order */
+    MOKAB_MESH_EXPLICIT_EOE = 2u /* always read edgesOnEdge from memory; default: rebuild it in the fused kernel from
+                                    edgesOnCell wherever the mesh follows the MPAS ordering (verified per edge) */
 };
 
 /* Host view of the reference mesh structs.  Pointers marked (opt) may be NULL.
@@ -233,6 +235,8 @@ int  mokab_rk4_finish_step(mokab_state *state);
 int  mokab_refresh_ssh(mokab_state *state, void *cuda_stream);
 /* number of interior / boundary blocks of the fused kernel (diagnostic) */
 int  mokab_mesh_block_counts(const mokab_mesh *mesh, int64_t *interior, int64_t *boundary);
+/* number of fused-kernel blocks, and how many of them rebuild edgesOnEdge from edgesOnCell (diagnostic) */
+int  mokab_mesh_derived_blocks(const mokab_mesh *mesh, int64_t *blocks, int64_t *derived);
 
 #ifdef __cplusplus
 }

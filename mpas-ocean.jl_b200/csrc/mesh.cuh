@@ -54,6 +54,9 @@ struct HostMesh {
     int64_t nC = 0, nE = 0, nV = 0;
     int64_t nCo = 0, nEo = 0;                  // owned (computed) cells / edges; the rest are halo copies
     std::vector<int32_t> blkEdgeStart, blkInterior, blkBoundary;  // fused-kernel blocks (kBlockCells cells each)
+    // derived edgesOnEdge (see below): position of each edge in the edgesOnCell rows of its two cells, and the
+    // blocks in which every edge's edgesOnEdge row equals the row derived from edgesOnCell
+    std::vector<uint8_t> posE, blkDerived;
     int S = 0, S2 = 0, D = 0;  // maxEdges, maxEdges2, vertexDegree
     std::vector<int32_t> permC, permE, permV;  // perm[new] = old
     std::vector<int32_t> ce;                   // (nE, 2) c1, c2 (c2 = c1 on masked edges)
@@ -274,6 +277,38 @@ static void build_host_mesh(const mokab_mesh_desc &d, uint32_t flags, HostMesh &
             }
         (halo ? m.blkBoundary : m.blkInterior).push_back(b);
     }
+    // ---- derived edgesOnEdge -----------------------------------------------------------------------------------------
+    // MPAS builds edgesOnEdge[:, e] as: the other edges of cellsOnEdge[1, e] in edgesOnCell order starting after e,
+    // then the same for cellsOnEdge[2, e].  Where that holds, the 4*nEdgesOnEdge index bytes per edge (20 % of the
+    // fused stage's HBM traffic in Float64) need not be read: the kernel rebuilds the row from the edgesOnCell rows
+    // it already stages in shared memory plus one byte per edge (its position in the two rows).  Verified edge by
+    // edge here, never assumed; a block with any non-conforming edge (or a halo cell, whose rows are not stored)
+    // keeps reading the explicit array.
+    m.posE.assign(nE, 0);
+    m.blkDerived.assign(nb, 0);
+    if (!(flags & MOKAB_MESH_EXPLICIT_EOE) && S <= 15) {
+#pragma omp parallel for schedule(static)
+        for (int b = 0; b < nb; ++b) {
+            bool ok = true;
+            for (int64_t e = m.blkEdgeStart[b]; e < m.blkEdgeStart[b + 1]; ++e) {
+                const int32_t c1 = m.ce[2 * e], c2 = m.ce[2 * e + 1];
+                const bool masked = c1 == c2;
+                const int n1 = m.nEoC[c1], n2 = masked ? 1 : m.nEoC[c2];
+                int p1 = -1, p2 = masked ? 0 : -1;
+                for (int i = 0; i < n1; ++i) if (m.eoc[(size_t)i * nC + c1] == e) p1 = i;
+                if (!masked) for (int i = 0; i < n2; ++i) if (m.eoc[(size_t)i * nC + c2] == e) p2 = i;
+                if (c1 / kBlockCells != b || p1 < 0 || p2 < 0 || n1 + n2 - 2 != m.nEoE[e]) { ok = false; continue; }
+                m.posE[e] = (uint8_t)(p1 | (p2 << 4));
+                for (int j = 0; j < m.nEoE[e] && ok; ++j) {
+                    int32_t want;
+                    if (j < n1 - 1) { int r = p1 + 1 + j; r -= r >= n1 ? n1 : 0; want = m.eoc[(size_t)r * nC + c1]; }
+                    else { int r = p2 + 1 + (j - (n1 - 1)); r -= r >= n2 ? n2 : 0; want = m.eoc[(size_t)r * nC + c2]; }
+                    ok = m.eoe[(size_t)j * nE + e] == want;
+                }
+            }
+            m.blkDerived[b] = ok ? 1 : 0;
+        }
+    }
 }
 
 // Arrays of the fused RK4 path in precision R: f folded into the weights, g/dc and 1/area
@@ -301,6 +336,8 @@ struct mokab_mesh {
     mokab::DevBuf<int32_t> eoeF, eocF;   // absent -> self / sign in bit 0
     mokab::DevBuf<int32_t> blkEdgeStart; // per block of kBlockCells cells: first owned edge
     mokab::DevBuf<int32_t> blkInterior, blkBoundary;  // block ids by part
+    mokab::DevBuf<uint8_t> posE, blkDerived;          // derived edgesOnEdge (mesh.cuh: build_host_mesh)
+    int nDerivedBlocks = 0;
     int64_t nCo = 0, nEo = 0;            // owned cells / edges (== nC / nE without decomposition)
     int fusedBlocks = 0, nInterior = 0, nBoundary = 0;
     bool uniformF = true; double f0 = 0.0;

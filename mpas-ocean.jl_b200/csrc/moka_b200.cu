@@ -118,6 +118,10 @@ static void upload_mesh(mokab_ctx *ctx, HostMesh &hm, mokab_mesh *m)
     m->blkEdgeStart.upload(hm.blkEdgeStart, s);
     m->blkInterior.upload(hm.blkInterior, s);
     m->blkBoundary.upload(hm.blkBoundary, s);
+    m->posE.upload(hm.posE, s);
+    m->blkDerived.upload(hm.blkDerived, s);
+    m->nDerivedBlocks = 0;
+    for (uint8_t d : hm.blkDerived) m->nDerivedBlocks += d;
     m->fusedBlocks = (int)hm.blkEdgeStart.size() - 1;
     m->nInterior = (int)hm.blkInterior.size();
     m->nBoundary = (int)hm.blkBoundary.size();
@@ -439,6 +443,7 @@ static fused::StageArgs<R> stage_args(mokab_state *st, double dt, int p, int sta
     A.nE = (int)m->nE; A.nC = (int)m->nC; A.nCown = (int)m->nCo; A.blockList = nullptr;
     A.ce = m->ce.p; A.eoe = m->eoeF.p; A.eoc = m->eocF.p; A.nEoE = m->nEoE.p; A.nEoC = m->nEoC.p;
     A.blkEdgeStart = m->blkEdgeStart.p;
+    A.posE = m->posE.p; A.blkDerived = m->nDerivedBlocks ? m->blkDerived.p : nullptr;
     A.gdc = fm.gdc.p; A.wf = fm.wf.p; A.dv = fm.dv.p; A.invArea = fm.invArea.p; A.H = fm.H.p;
     A.uCur = t->u[p].p; A.hCur = t->h[p].p; A.uAcc = t->u[1 - p].p; A.hAcc = t->h[1 - p].p;
     const double a[4] = {dt / 2.0, dt / 2.0, dt, 0.0};                  // time_integration.jl:77
@@ -1330,6 +1335,15 @@ int mokab_refresh_ssh(mokab_state *state, void *cuda_stream)
         state->ctx->bind();
         if (state->dtype == MOKAB_F64) refresh_ssh<double>(state, (cudaStream_t)cuda_stream);
         else refresh_ssh<float>(state, (cudaStream_t)cuda_stream);
+    });
+}
+
+int mokab_mesh_derived_blocks(const mokab_mesh *mesh, int64_t *blocks, int64_t *derived)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(mesh && blocks && derived, "mesh_derived_blocks: NULL argument");
+        *blocks = mesh->fusedBlocks;
+        *derived = mesh->nDerivedBlocks;
     });
 }
 

@@ -18,7 +18,7 @@ SUM_SSH2, SUM_MASS, SUM_ENERGY = range(3)
 CELLS, EDGES, VERTICES = range(3)
 RK4_FUSED, RK4_UNFUSED = 0, 1
 PART_ALL, PART_INTERIOR, PART_BOUNDARY = 0, 1, 2
-MESH_RENUMBER = 1
+MESH_RENUMBER, MESH_EXPLICIT_EOE = 1, 2
 
 _I32P, _F64P = C.POINTER(C.c_int32), C.POINTER(C.c_double)
 
@@ -58,7 +58,7 @@ SYMBOLS = [
     "mokab_timestep_forward_euler", "mokab_timestep_rk4", "mokab_reduce",
     "mokab_tape_begin", "mokab_tape_length", "mokab_adjoint_seed", "mokab_adjoint_rk4",
     "mokab_halo_setup", "mokab_halo_pack", "mokab_halo_unpack", "mokab_rk4_stage", "mokab_rk4_finish_step",
-    "mokab_refresh_ssh", "mokab_mesh_block_counts",
+    "mokab_refresh_ssh", "mokab_mesh_block_counts", "mokab_mesh_derived_blocks",
 ]
 
 
@@ -94,6 +94,7 @@ def lib():
             "mokab_halo_unpack": [vp, C.c_int, vp, vp], "mokab_rk4_stage": [vp, dbl, C.c_int, C.c_int, vp],
             "mokab_rk4_finish_step": [vp], "mokab_refresh_ssh": [vp, vp],
             "mokab_mesh_block_counts": [vp, C.POINTER(i64), C.POINTER(i64)],
+            "mokab_mesh_derived_blocks": [vp, C.POINTER(i64), C.POINTER(i64)],
         }
         for name, args in sig.items():
             fn = getattr(L, name)

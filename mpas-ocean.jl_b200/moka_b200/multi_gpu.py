@@ -159,6 +159,7 @@ class DecomposedModel:
         it is alive) and drain both streams."""
         self.compute.synchronize()
         self.halo.synchronize()
+        self.backend.set_stream(None)                            # the context goes back to its own stream
         self._graph = None
         import gc
         gc.collect()
@@ -243,7 +244,7 @@ def _share_locals(args, rank, world, nx, dtype):
 def bench_main(args, rank, world, local):
     import torch
     import torch.distributed as dist
-    from bench import ALGO_BYTES_PER_CELL_STEP, WORKLOADS, ClockSampler, measured_peak_gbs
+    from bench import WORKLOADS, ClockSampler, algo_bytes_per_cell_step, measured_peak_gbs
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     nx = WORKLOADS[args.workload]
@@ -317,7 +318,8 @@ def bench_main(args, rank, world, local):
         item = np.dtype(npdt).itemsize
         peak, peak_src = measured_peak_gbs()
         value = nC_glob * K / (ms * 1e-3)
-        algo_per_launch = ALGO_BYTES_PER_CELL_STEP[args.dtype] / 4.0 * loc["nCellsOwned"]
+        nblk, nder = model.mesh.derived_blocks()
+        algo_per_launch = algo_bytes_per_cell_step(args.dtype, nder / max(nblk, 1)) / 4.0 * loc["nCellsOwned"]
         achieved = algo_per_launch / ((ms * 1e-3) / (4 * K)) / 1e9
         print(json.dumps({
             "metric": "RK4 cell-steps/sec", "value": value, "unit": "cell-steps/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -330,7 +332,8 @@ def bench_main(args, rank, world, local):
                                    f"{'overlapped with interior blocks' if model.overlap else '(no overlap)'}"
                                    f"{', 2-step CUDA graph incl. NCCL' if model.use_graph else ''}",
                        "name": args.workload, "l2": "inputs larger than L2 (no flush)", "setup_s": round(t_setup, 1),
-                       "rank0_blocks_interior_boundary": list(blocks), "rank0_halo_bytes_per_stage": int(halo_bytes)},
+                       "rank0_blocks_interior_boundary": list(blocks), "rank0_halo_bytes_per_stage": int(halo_bytes),
+                       "rank0_blocks_rebuilding_edgesOnEdge": [int(nder), int(nblk)]},
             "clocks": clocks,
             "e2e": {"value": nC_glob / e2e_s, "unit": "cell-steps/s", "h2d_bytes_per_step": int(cnt[0].item() * item),
                     "d2h_bytes_per_step": int(cnt[1].item() * item), "ms_per_step": e2e_s * 1e3, "steps": Ke,

@@ -269,3 +269,45 @@ def test_pipelined_upload_download_matches_blocking_path(backend, dtype):
         assert rel_l2(outs[-1][0], om.ssh[1]) <= TOL64 and rel_l2(outs[-1][1], om.normalVelocity[1]) <= TOL64
     with pytest.raises(mb.MokaError):
         prog.dev.set_async(mb._lib.SSH, np.zeros(3, dtype))
+
+
+def test_derived_edges_on_edge_path_is_bit_identical_to_the_explicit_one(backend):
+    """The fused kernel rebuilds edgesOnEdge from edgesOnCell where the mesh follows the MPAS ordering (verified per
+    edge at mesh_create).  Same gather order => the same bits as reading the array (MOKAB_MESH_EXPLICIT_EOE), in both
+    precisions, with and without renumbering; and a mesh whose rows are NOT in that order falls back block by block."""
+    m = hex_mesh(40)
+    ssh, u, h = mb.inertialGravityWave(m).initial_state()
+    dt = mb.cfl_dt(m["dc"])
+    for dtype in (np.float64, np.float32):
+        res = []
+        for explicit in (False, True):
+            mesh = mb.Mesh(m, backend, explicit_eoe=explicit)
+            nb, nd = mesh.derived_blocks()
+            assert nd == (0 if explicit else nb) and nb == (m["nCells"] + 255) // 256
+            prog = mb.PrognosticVars(ssh.astype(dtype), u.astype(dtype), h.astype(dtype), 2, mesh)
+            mb.ocn_timestep(dt, prog, None, None, None, mb.RungeKutta4, nsteps=7)
+            res.append((prog.normalVelocity, prog.layerThickness))
+        assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    om = OC.OracleModel(m, ssh, u, h)
+    om.run_loop(dt, 7, "RungeKutta4")
+    assert rel_l2(res[0][0], om.normalVelocity[1]) <= TOL32                     # res holds the Float32 run here
+    # non-conforming rows: swap two slots (index and weight together) on a band of edges -> those blocks read the array
+    m2 = dict(m)
+    eoe, w = m["edgesOnEdge"].copy(), m["weightsOnEdge"].copy()
+    band = np.arange(m["nEdges"] // 3, m["nEdges"] // 3 + 40)
+    eoe[band, 0], eoe[band, 1] = m["edgesOnEdge"][band, 1], m["edgesOnEdge"][band, 0]
+    w[band, 0], w[band, 1] = m["weightsOnEdge"][band, 1], m["weightsOnEdge"][band, 0]
+    m2["edgesOnEdge"], m2["weightsOnEdge"] = eoe, w
+    mesh2 = mb.Mesh(m2, backend)
+    nb, nd = mesh2.derived_blocks()
+    assert 0 < nd < nb
+    prog = mb.PrognosticVars(ssh, u, h, 2, mesh2)
+    mb.ocn_timestep(dt, prog, None, None, None, mb.RungeKutta4, nsteps=7)
+    om2 = OC.OracleModel(m2, ssh, u, h)
+    om2.run_loop(dt, 7, "RungeKutta4")
+    assert np.array_equal(prog.normalVelocity, om2.normalVelocity[1]) and np.array_equal(prog.layerThickness, om2.layerThickness[1])
+    # and the unmodified mesh through the derived path is bit-identical to the oracle too
+    mesh = mb.Mesh(m, backend)
+    prog = mb.PrognosticVars(ssh, u, h, 2, mesh)
+    mb.ocn_timestep(dt, prog, None, None, None, mb.RungeKutta4, nsteps=7)
+    assert np.array_equal(prog.normalVelocity, om.normalVelocity[1]) and np.array_equal(prog.layerThickness, om.layerThickness[1])
