@@ -282,7 +282,7 @@ def main():
     ap.add_argument("--no-overlap", dest="no_overlap", action="store_true", help="multi-GPU: exchange after each full stage")
     ap.add_argument("--no-graph", dest="no_graph", action="store_true", help="multi-GPU: do not capture steps into a CUDA graph")
     ap.add_argument("--explicit-eoe", dest="explicit_eoe", action="store_true",
-                    help="read edgesOnEdge from memory instead of rebuilding it from edgesOnCell (ablation)")
+                    help="ablation: read edgesOnEdge from memory instead of rebuilding it from edgesOnCell")
     ap.add_argument("--quick", action="store_true", help="profiling runs: no clock-sampling load loop, one e2e step")
     args = ap.parse_args()
     if args.workload is None:

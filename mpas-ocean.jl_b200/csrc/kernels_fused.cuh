@@ -14,12 +14,16 @@
 //   stage 4:                      acc += b*k             (acc is the other time level: no copy-back)
 // Neither tend*, thicknessFlux, layerThicknessEdge nor ssh ever touch HBM.
 //
-// v2: edgesOnEdge is not read where it can be rebuilt.  MPAS orders edgesOnEdge[:, e] as "the other edges of cell 1
+// DER = true (the default; MOKAB_MESH_EXPLICIT_EOE turns it off): edgesOnEdge is not read where it can be rebuilt.  MPAS orders edgesOnEdge[:, e] as "the other edges of cell 1
 // in edgesOnCell order starting after e, then the same for cell 2"; mesh.cuh verifies that per edge and flags the
-// blocks where it holds everywhere.  Those blocks stage their cells' edgesOnCell rows in shared memory (the cell phase
-// needs them anyway), read one position byte per edge and pick the ten indices out of the two rows -- 40 B of index
-// traffic per edge (20 % of the Float64 stage's HBM bytes, 31 % in Float32) become 1 B.  The gather order, and with
-// it every floating-point operation, is unchanged.
+// blocks where it holds everywhere.  Those blocks read one position byte per edge and pick the ten indices out of the
+// two edgesOnCell rows through L1 (the rows of a block's cells are 6 KB, resident after the first touch; the cell
+// phase needs them anyway) -- 40 B of index traffic per edge (20 % of the Float64 stage's HBM bytes, 31 % in Float32) become 1 B.  The gather order, and with
+// it every floating-point operation, is unchanged (bit-identical results, tested).  Measured on B200 at 2048x2048
+// (profiles/README.md): +5.7 % (Float64, 2.81 vs 2.66 G cell-steps/s) and +10.6 % (Float32, 4.05 vs 3.66).  A first
+// version that staged the rows in shared memory behind a block-wide barrier moved the same 16 % fewer DRAM bytes but
+// ran SLOWER (2.11 G): the kernel is latency-bound, the barrier and the dependent shared-memory hop cost more than the
+// bytes saved; reading the rows through L1 without a barrier is what made it pay.
 //
 // v1 data path: static connectivity / weights are slot-major and streamed with L1::no_allocate loads
 // (read once per stage), the provisional state is gathered through L1/L2 -- after the Hilbert
@@ -67,14 +71,15 @@ struct StageArgs {
 };
 
 // STAGE: 1 = first, 2 = middle (2 and 3), 4 = last.  S2/S: compile-time maxEdges2/maxEdges (0 = runtime).
-#ifndef MOKAB_W_LATE
-#define MOKAB_W_UPFRONT 1   // issue the weight loads together with the index loads (measured +5 % over loading at use)
-#endif
 #ifndef MOKAB_MINBLOCKS
 #define MOKAB_MINBLOCKS 5   // <= 48 registers, 5 blocks (40 warps) per SM: measured best of 4/5/6 (profiles/README.md)
 #endif
-template <class R, int STAGE, int S2T, int ST, bool FOLD>
-__global__ void __launch_bounds__(kThreads, MOKAB_MINBLOCKS)
+// resident blocks per SM of the edgesOnEdge-rebuilding variant: Float64 needs 64 registers to hold the ten weights
+// across the index reconstruction without spilling (4 blocks), Float32 fits in 48 (5 blocks) -- measured r01h:
+// F64 2.81 / 2.49 / 2.09 G cell-steps/s at 4 / 5 / 6 blocks, F32 3.62 / 4.05 / 3.83
+template <class R> constexpr int der_minblocks() { return sizeof(R) == 8 ? 4 : 5; }
+template <class R, int STAGE, int S2T, int ST, bool FOLD, bool DER>
+__global__ void __launch_bounds__(kThreads, DER ? der_minblocks<R>() : MOKAB_MINBLOCKS)
 k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
 {
     const int S2 = S2T ? S2T : S2rt;
@@ -83,86 +88,88 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
     const int b = A.blockList ? A.blockList[blockIdx.x] : blockIdx.x;
     const int cBase = b * kTC;
 
-    // ---- stage this block's edgesOnCell rows (compile-time row width only) ---------------------------------------
-    __shared__ int sEoc[ST ? ST : 1][kTC + 1];
-    __shared__ unsigned char sN[kTC];
-    bool derived = false;
-    if constexpr (ST != 0 && S2T != 0) {
-        const int cc0 = cBase + threadIdx.x;
-        int n0 = 0;
-        if (cc0 < A.nCown) n0 = ld_stream(A.nEoC + cc0);
-#pragma unroll
-        for (int i = 0; i < ST; ++i) sEoc[i][threadIdx.x] = i < n0 ? ld_stream(A.eoc + (size_t)i * nC + cc0) : -1;
-        sN[threadIdx.x] = (unsigned char)n0;
-        derived = A.blkDerived && A.blkDerived[b];
-        __syncthreads();
-    }
+    constexpr bool kDer = DER && ST != 0 && S2T != 0;
+    const bool derived = kDer && A.blkDerived && A.blkDerived[b];
 
     // ---- edges owned by this block's cells ----------------------------------------------------------
     const int e0 = A.blkEdgeStart[b], e1 = A.blkEdgeStart[b + 1];
     for (int e = e0 + threadIdx.x; e < e1; e += kThreads) {
         const int2 c = ld_stream(A.ce + e);
-        int n = derived ? 0 : ld_stream(A.nEoE + e);
-        // the RK operands are independent of the tendency: issue their loads now (they may alias the
-        // stores below, so the compiler cannot hoist them itself)
-        const R cur = (STAGE == 4) ? R(0) : A.uCur[e];
-        const R accIn = (STAGE == 1) ? R(0) : A.uAcc[e];
         R k;
-        const R h1 = __ldg(A.hOld + c.x), h2 = __ldg(A.hOld + c.y);
-        const R H1 = __ldg(A.H + c.x), H2 = __ldg(A.H + c.y);
         if constexpr (S2T != 0) {
+            // Every streaming load of this edge is issued before anything waits on one of them: the padded slots of
+            // the slot-major arrays are defined (index = the edge itself, weight = 0; k_build_fused_edges), so neither
+            // the index nor the weight loads depend on nEdgesOnEdge, and one DRAM latency covers them all.
             int idx[S2T ? S2T : 1];
-            if (ST != 0 && derived) {
-                const unsigned pp = ld_stream(A.posE + e);
-                const int p1 = pp & 15, p2 = pp >> 4;
-                const int l1 = c.x - cBase, l2 = c.y - cBase;
-                const bool in2 = (unsigned)l2 < (unsigned)kTC;
-                const int n1 = sN[l1];
-                const int n2 = c.x == c.y ? 1 : (in2 ? (int)sN[l2] : (int)__ldg(A.nEoC + c.y));
-                n = n1 + n2 - 2;
-#pragma unroll
-                for (int i = 0; i < S2T; ++i) {
-                    int id = e;
-                    if (i < n1 - 1) {
-                        int r = p1 + 1 + i;
-                        r -= r >= n1 ? n1 : 0;
-                        id = sEoc[r][l1] >> 1;
-                    } else if (i < n) {
-                        int r = p2 + 1 + i - (n1 - 1);
-                        r -= r >= n2 ? n2 : 0;
-                        id = (in2 ? sEoc[r][l2] : __ldg(A.eoc + (size_t)r * nC + c.y)) >> 1;
-                    }
-                    idx[i] = id;
-                }
+            R w[S2T ? S2T : 1];
+            unsigned pp = 0;
+            if (kDer && derived) {
+                pp = ld_stream(A.posE + e);
             } else {
 #pragma unroll
-                for (int i = 0; i < S2T; ++i) idx[i] = i < n ? ld_stream(A.eoe + (size_t)i * nE + e) : e;
+                for (int i = 0; i < S2T; ++i) idx[i] = ld_stream(A.eoe + (size_t)i * nE + e);
             }
-#ifdef MOKAB_W_UPFRONT
-            R w[S2T ? S2T : 1];
 #pragma unroll
-            for (int i = 0; i < S2T; ++i) w[i] = i < n ? ld_stream(A.wf + (size_t)i * nE + e) : R(0);
-#endif
+            for (int i = 0; i < S2T; ++i) w[i] = ld_stream(A.wf + (size_t)i * nE + e);
+            const R g = ld_stream(A.gdc + e);
+            // the RK operands are independent of the tendency: issue their loads now (they may alias the stores
+            // below, so the compiler cannot hoist them itself)
+            const R cur = (STAGE == 4) ? R(0) : A.uCur[e];
+            const R accIn = (STAGE == 1) ? R(0) : A.uAcc[e];
+            const R h1 = __ldg(A.hOld + c.x), h2 = __ldg(A.hOld + c.y);
+            const R H1 = __ldg(A.H + c.x), H2 = __ldg(A.H + c.y);
+            if (kDer && derived) {
+                // posE: bits 0-2 position of e in the row of cell 1, bits 3-5 in the row of cell 2, bit 7 = both rows
+                // have ST entries and the edge is not masked (the branch-free common case)
+                const int p1 = pp & 7, p2 = (pp >> 3) & 7;
+                if (pp & 128u) {
+                    constexpr int H = ST - 1;
+#pragma unroll
+                    for (int i = 0; i < S2T; ++i) {
+                        int r = (i < H ? p1 : p2) + 1 + (i < H ? i : i - H);
+                        r -= r >= ST ? ST : 0;
+                        idx[i] = i < 2 * H ? (__ldg(A.eoc + (size_t)r * nC + (i < H ? c.x : c.y)) >> 1) : e;
+                    }
+                } else {
+                    const int n1 = __ldg(A.nEoC + c.x);
+                    const int n2 = c.x == c.y ? 1 : (int)__ldg(A.nEoC + c.y);
+#pragma unroll
+                    for (int i = 0; i < S2T; ++i) {
+                        int id = e;
+                        if (i < n1 - 1) {
+                            int r = p1 + 1 + i;
+                            r -= r >= n1 ? n1 : 0;
+                            id = __ldg(A.eoc + (size_t)r * nC + c.x) >> 1;
+                        } else if (i < n1 + n2 - 2) {
+                            int r = p2 + 1 + i - (n1 - 1);
+                            r -= r >= n2 ? n2 : 0;
+                            id = __ldg(A.eoc + (size_t)r * nC + c.y) >> 1;
+                        }
+                        idx[i] = id;
+                    }
+                }
+            }
             R uu[S2T ? S2T : 1];
 #pragma unroll
             for (int i = 0; i < S2T; ++i) uu[i] = __ldg(A.uOld + idx[i]);
             // tend = 0 - (g/dc)*(ssh2 - ssh1), then += (w*u)*f slot by slot (pressure_gradient.jl:63, coriolis :70-72)
-            k = -mul_rn(ld_stream(A.gdc + e), add_rn(add_rn(h2, -H2), -add_rn(h1, -H1)));
+            k = -mul_rn(g, add_rn(add_rn(h2, -H2), -add_rn(h1, -H1)));
 #pragma unroll
-            for (int i = 0; i < S2T; ++i) {
-#ifdef MOKAB_W_UPFRONT
-                const R wi = w[i];
-#else
-                const R wi = i < n ? ld_stream(A.wf + (size_t)i * nE + e) : R(0);
-#endif
-                k = add_rn(k, FOLD ? mul_rn(wi, uu[i]) : mul_rn(mul_rn(wi, uu[i]), A.f0));
-            }
-        } else {
-            k = -mul_rn(ld_stream(A.gdc + e), add_rn(add_rn(h2, -H2), -add_rn(h1, -H1)));
-            for (int i = 0; i < n; ++i) {
-                const R wu = mul_rn(ld_stream(A.wf + (size_t)i * nE + e), __ldg(A.uOld + ld_stream(A.eoe + (size_t)i * nE + e)));
-                k = add_rn(k, FOLD ? wu : mul_rn(wu, A.f0));
-            }
+            for (int i = 0; i < S2T; ++i) k = add_rn(k, FOLD ? mul_rn(w[i], uu[i]) : mul_rn(mul_rn(w[i], uu[i]), A.f0));
+            if (STAGE != 4) A.uOut[e] = add_rn(cur, mul_rn(A.a, k));       // Provis = Curr + a*tend (time_integration.jl:124)
+            if (STAGE == 1) A.uAcc[e] = add_rn(cur, mul_rn(A.b, k));       // New = Curr + b1*tend    (:108-110, :134)
+            else            A.uAcc[e] = add_rn(accIn, mul_rn(A.b, k));     // New += b*tend           (:134)
+            continue;
+        }
+        const int n = ld_stream(A.nEoE + e);
+        const R cur = (STAGE == 4) ? R(0) : A.uCur[e];
+        const R accIn = (STAGE == 1) ? R(0) : A.uAcc[e];
+        const R h1 = __ldg(A.hOld + c.x), h2 = __ldg(A.hOld + c.y);
+        const R H1 = __ldg(A.H + c.x), H2 = __ldg(A.H + c.y);
+        k = -mul_rn(ld_stream(A.gdc + e), add_rn(add_rn(h2, -H2), -add_rn(h1, -H1)));
+        for (int i = 0; i < n; ++i) {
+            const R wu = mul_rn(ld_stream(A.wf + (size_t)i * nE + e), __ldg(A.uOld + ld_stream(A.eoe + (size_t)i * nE + e)));
+            k = add_rn(k, FOLD ? wu : mul_rn(wu, A.f0));
         }
         if (STAGE != 4) A.uOut[e] = add_rn(cur, mul_rn(A.a, k));       // Provis = Curr + a*tend (time_integration.jl:124)
         if (STAGE == 1) A.uAcc[e] = add_rn(cur, mul_rn(A.b, k));       // New = Curr + b1*tend    (:108-110, :134)
@@ -172,7 +179,7 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
     // ---- cells of this block ----------------------------------------------------------------------------
     const int cc = cBase + threadIdx.x;
     if (cc < A.nCown) {
-        const int n = (ST != 0 && S2T != 0) ? (int)sN[threadIdx.x] : (int)ld_stream(A.nEoC + cc);
+        const int n = ld_stream(A.nEoC + cc);
         const R hc = __ldg(A.hOld + cc);
         const R cur = (STAGE == 4) ? R(0) : A.hCur[cc];
         const R accIn = (STAGE == 1) ? R(0) : A.hAcc[cc];
@@ -180,7 +187,7 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
         if constexpr (ST != 0) {
             int ee[ST ? ST : 1];
 #pragma unroll
-            for (int i = 0; i < ST; ++i) ee[i] = S2T != 0 ? sEoc[i][threadIdx.x] : (i < n ? ld_stream(A.eoc + (size_t)i * nC + cc) : -1);
+            for (int i = 0; i < ST; ++i) ee[i] = i < n ? (kDer ? __ldg(A.eoc + (size_t)i * nC + cc) : ld_stream(A.eoc + (size_t)i * nC + cc)) : -1;
             int2 cs[ST ? ST : 1];
             R uu[ST ? ST : 1], dd[ST ? ST : 1];
 #pragma unroll

@@ -281,12 +281,12 @@ static void build_host_mesh(const mokab_mesh_desc &d, uint32_t flags, HostMesh &
     // MPAS builds edgesOnEdge[:, e] as: the other edges of cellsOnEdge[1, e] in edgesOnCell order starting after e,
     // then the same for cellsOnEdge[2, e].  Where that holds, the 4*nEdgesOnEdge index bytes per edge (20 % of the
     // fused stage's HBM traffic in Float64) need not be read: the kernel rebuilds the row from the edgesOnCell rows
-    // it already stages in shared memory plus one byte per edge (its position in the two rows).  Verified edge by
-    // edge here, never assumed; a block with any non-conforming edge (or a halo cell, whose rows are not stored)
-    // keeps reading the explicit array.
+    // (L1-resident, the cell phase reads them anyway) plus one byte per edge (its position in the two rows).  Verified edge by edge
+    // here, never assumed; a block with any non-conforming edge (or a halo cell, whose rows are not stored) keeps
+    // reading the explicit array (MOKAB_MESH_EXPLICIT_EOE forces that everywhere).
     m.posE.assign(nE, 0);
     m.blkDerived.assign(nb, 0);
-    if (!(flags & MOKAB_MESH_EXPLICIT_EOE) && S <= 15) {
+    if (!(flags & MOKAB_MESH_EXPLICIT_EOE) && S <= 8) {
 #pragma omp parallel for schedule(static)
         for (int b = 0; b < nb; ++b) {
             bool ok = true;
@@ -298,7 +298,7 @@ static void build_host_mesh(const mokab_mesh_desc &d, uint32_t flags, HostMesh &
                 for (int i = 0; i < n1; ++i) if (m.eoc[(size_t)i * nC + c1] == e) p1 = i;
                 if (!masked) for (int i = 0; i < n2; ++i) if (m.eoc[(size_t)i * nC + c2] == e) p2 = i;
                 if (c1 / kBlockCells != b || p1 < 0 || p2 < 0 || n1 + n2 - 2 != m.nEoE[e]) { ok = false; continue; }
-                m.posE[e] = (uint8_t)(p1 | (p2 << 4));
+                m.posE[e] = (uint8_t)(p1 | (p2 << 3) | ((!masked && n1 == S && n2 == S) ? 128 : 0));
                 for (int j = 0; j < m.nEoE[e] && ok; ++j) {
                     int32_t want;
                     if (j < n1 - 1) { int r = p1 + 1 + j; r -= r >= n1 ? n1 : 0; want = m.eoc[(size_t)r * nC + c1]; }

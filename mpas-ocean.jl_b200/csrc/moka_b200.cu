@@ -342,6 +342,22 @@ static void diag_compute(mokab_state *st, const double *u, const double *h)
                t->relVort.p);
 }
 
+// Diagnostics of the given state taken at face value: hEdge and flux of the SAME state (no lag) and relativeVorticity
+// zeroed before the curl accumulates into it (the line the reference has commented out, Operators.jl:135).
+static void diag_consistent(mokab_state *st, const double *u, const double *h)
+{
+    mokab_ctx *ctx = st->ctx; const mokab_mesh *m = st->mesh; StateT<double> *t = st->d;
+    LAUNCH(ctx, ref::k_interpolate_cell2edge, nblk(m->nE), 256, (int)m->nE, m->ce.p, h, t->hEdge.p);
+    LAUNCH(ctx, ref::k_mul, nblk(m->nE), 256, m->nE, u, (const double *)t->hEdge.p, t->flux.p);
+    LAUNCH(ctx, ref::k_divergence_on_cell, nblk(m->nC), 256, (int)m->nC, m->eoc.p, m->sgnC.p, m->nEoC.p, m->area.p, m->dv.p, u,
+           t->divC.p);
+    if (m->nV) {
+        t->relVort.zero(ctx->stream);
+        LAUNCH(ctx, ref::k_curl_on_vertex, nblk(m->nV), 256, (int)m->nV, m->D, m->eov.p, m->sgnV.p, m->areaTri.p, m->dc.p, u,
+               t->relVort.p);
+    }
+}
+
 static void tend_u(mokab_state *st, const double *ssh, const double *u)
 {
     mokab_ctx *ctx = st->ctx; const mokab_mesh *m = st->mesh;
@@ -425,10 +441,15 @@ static void launch_stage(mokab_ctx *ctx, const mokab_mesh *m, fused::StageArgs<R
     if (grid == 0) return;
     cudaStream_t s = stream ? stream : ctx->stream;
     const bool hex = m->S2 == 10 && m->S == 6;
-    if (hex && m->uniformF)        fused::k_rk_stage<R, STAGE, 10, 6, false><<<grid, fused::kThreads, 0, s>>>(A, m->S2, m->S);
-    else if (hex)                  fused::k_rk_stage<R, STAGE, 10, 6, true><<<grid, fused::kThreads, 0, s>>>(A, m->S2, m->S);
-    else if (m->uniformF)          fused::k_rk_stage<R, STAGE, 0, 0, false><<<grid, fused::kThreads, 0, s>>>(A, m->S2, m->S);
-    else                           fused::k_rk_stage<R, STAGE, 0, 0, true><<<grid, fused::kThreads, 0, s>>>(A, m->S2, m->S);
+    const bool der = hex && m->nDerivedBlocks > 0;
+#define MOKAB_STAGE(S2T, ST, FOLD, DER) fused::k_rk_stage<R, STAGE, S2T, ST, FOLD, DER><<<grid, fused::kThreads, 0, s>>>(A, m->S2, m->S)
+    if (der && m->uniformF)        MOKAB_STAGE(10, 6, false, true);
+    else if (der)                  MOKAB_STAGE(10, 6, true, true);
+    else if (hex && m->uniformF)   MOKAB_STAGE(10, 6, false, false);
+    else if (hex)                  MOKAB_STAGE(10, 6, true, false);
+    else if (m->uniformF)          MOKAB_STAGE(0, 0, false, false);
+    else                           MOKAB_STAGE(0, 0, true, false);
+#undef MOKAB_STAGE
     MOKAB_CUDA(cudaGetLastError());
     ctx->launches++;
 }
@@ -1044,6 +1065,16 @@ int mokab_diagnostic_compute(mokab_state *state)
         require_f64(state, "diagnostic_compute");
         state->ctx->bind();
         diag_compute(state, state->d->u[state->cur].p, state->d->h[state->cur].p);
+    });
+}
+
+int mokab_diagnostic_compute_consistent(mokab_state *state)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(state, "diagnostic_compute_consistent: state is NULL");
+        require_f64(state, "diagnostic_compute_consistent");
+        state->ctx->bind();
+        diag_consistent(state, state->d->u[state->cur].p, state->d->h[state->cur].p);
     });
 }
 

@@ -41,6 +41,8 @@ const F64, F32 = Cint(0), Cint(1)
 const SSH, NORMAL_VELOCITY, LAYER_THICKNESS = Cint(0), Cint(1), Cint(2)
 const LAYER_THICKNESS_EDGE, THICKNESS_FLUX, VELOCITY_DIV_CELL, RELATIVE_VORTICITY = Cint(6), Cint(7), Cint(8), Cint(9)
 const TEND_NORMAL_VELOCITY, TEND_LAYER_THICKNESS = Cint(10), Cint(11)
+const D_SSH, D_NORMAL_VELOCITY, D_LAYER_THICKNESS = Cint(12), Cint(13), Cint(14)      # shadow state d_Prog
+const SUM_SSH2 = Cint(0)
 const RK4_FUSED, RK4_UNFUSED = Cint(0), Cint(1)
 
 # struct mokab_mesh_desc, field for field
@@ -101,6 +103,11 @@ function get!(a::Array{Float64}, s::B200State, field::Cint)       # write_netcdf
     check(ccall((:mokab_state_get, libmoka), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}), s.handle, field, a)); a
 end
 
+# Pipelined transfers: `a` must be page-locked (mokab_host_alloc) and stay valid until synchronize(s).
+set_async!(s::B200State, field::Cint, a::Array{Float64}) = check(ccall((:mokab_state_set_async, libmoka), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}), s.handle, field, a))
+get_async!(a::Array{Float64}, s::B200State, field::Cint) = check(ccall((:mokab_state_get_async, libmoka), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}), s.handle, field, a))
+synchronize(s::B200State) = check(ccall((:mokab_state_synchronize, libmoka), Cint, (Ptr{Cvoid},), s.handle))
+
 # ---- src/ocn entry points ---------------------------------------------------------------------------------------
 diagnostic_compute!(s::B200State) = check(ccall((:mokab_diagnostic_compute, libmoka), Cint, (Ptr{Cvoid},), s.handle))                      # DiagnosticVars.jl:108
 computeNormalVelocityTendency!(s::B200State) = check(ccall((:mokab_compute_normal_velocity_tendency, libmoka), Cint, (Ptr{Cvoid},), s.handle))  # normalVelocity.jl:21
@@ -134,5 +141,24 @@ function sum_ssh2(s::B200State)
     check(ccall((:mokab_reduce, libmoka), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}), s.handle, 0, r)); r[]
 end
 
-export B200, B200Mesh, B200State, on_architecture, synchronize, sum_ssh2
+# ---- reverse mode: stands in for `autodiff(Enzyme.Reverse, ocn_run_loop, ..., Duplicated(Prog, d_Prog), ...)` --------------
+# (test/enzyme/test_Enzyme_end2end.jl:78-96).  Runs `nsteps` RungeKutta4 steps recording the trajectory, seeds
+# d_ssh = 2 ssh (J = sum ssh^2, run_loop.jl:47-51) and sweeps back; returns J and fills the shadow arrays.
+function autodiff_reverse_run_loop!(d_normalVelocity::Array{Float64}, d_layerThickness::Array{Float64},
+                                    dt::Float64, s::B200State, nsteps::Integer)
+    check(ccall((:mokab_tape_begin, libmoka), Cint, (Ptr{Cvoid}, Int64), s.handle, nsteps))
+    ocn_timestep(dt, s, RungeKutta4; nsteps = nsteps)
+    J = sum_ssh2(s)
+    check(ccall((:mokab_adjoint_seed, libmoka), Cint, (Ptr{Cvoid}, Cint), s.handle, SUM_SSH2))
+    check(ccall((:mokab_adjoint_rk4, libmoka), Cint, (Ptr{Cvoid},), s.handle))
+    get!(d_normalVelocity, s, D_NORMAL_VELOCITY); get!(d_layerThickness, s, D_LAYER_THICKNESS)
+    J
+end
+# adjoints of the two operators test/enzyme/test_Enzyme_Operators.jl differentiates
+GradientOnEdge_vjp!(d_scalar::Array{Float64}, d_grad::Array{Float64}, m::B200Mesh) =
+    check(ccall((:mokab_gradient_on_edge_vjp, libmoka), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), m.backend.ctx, m.handle, d_grad, d_scalar))
+DivergenceOnCell_vjp!(d_vec::Array{Float64}, d_div::Array{Float64}, m::B200Mesh) =
+    check(ccall((:mokab_divergence_on_cell_vjp, libmoka), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), m.backend.ctx, m.handle, d_div, d_vec))
+
+export B200, B200Mesh, B200State, on_architecture, synchronize, sum_ssh2, autodiff_reverse_run_loop!
 end # module

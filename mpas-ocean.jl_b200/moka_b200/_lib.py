@@ -52,7 +52,7 @@ SYMBOLS = [
     "mokab_mesh_create", "mokab_mesh_destroy", "mokab_mesh_get_perm", "mokab_mesh_device_bytes",
     "mokab_state_create", "mokab_state_destroy", "mokab_state_set", "mokab_state_get",
     "mokab_state_set_async", "mokab_state_get_async", "mokab_state_synchronize",
-    "mokab_diagnostic_compute", "mokab_compute_normal_velocity_tendency", "mokab_compute_layer_thickness_tendency",
+    "mokab_diagnostic_compute", "mokab_diagnostic_compute_consistent", "mokab_compute_normal_velocity_tendency", "mokab_compute_layer_thickness_tendency",
     "mokab_gradient_on_edge", "mokab_divergence_on_cell", "mokab_curl_on_vertex", "mokab_interpolate_cell2edge",
     "mokab_gradient_on_edge_vjp", "mokab_divergence_on_cell_vjp",
     "mokab_timestep_forward_euler", "mokab_timestep_rk4", "mokab_reduce",
@@ -81,7 +81,7 @@ def lib():
             "mokab_state_set": [vp, C.c_int, vp], "mokab_state_get": [vp, C.c_int, vp],
             "mokab_state_set_async": [vp, C.c_int, vp], "mokab_state_get_async": [vp, C.c_int, vp],
             "mokab_state_synchronize": [vp],
-            "mokab_diagnostic_compute": [vp], "mokab_compute_normal_velocity_tendency": [vp],
+            "mokab_diagnostic_compute": [vp], "mokab_diagnostic_compute_consistent": [vp], "mokab_compute_normal_velocity_tendency": [vp],
             "mokab_compute_layer_thickness_tendency": [vp],
             "mokab_gradient_on_edge": [vp, vp, _F64P, _F64P], "mokab_divergence_on_cell": [vp, vp, _F64P, _F64P],
             "mokab_gradient_on_edge_vjp": [vp, vp, _F64P, _F64P], "mokab_divergence_on_cell_vjp": [vp, vp, _F64P, _F64P],

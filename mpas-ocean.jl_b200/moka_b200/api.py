@@ -278,9 +278,11 @@ class TendencyVars:
 
 
 # ---- src/ocn ----------------------------------------------------------------------------------------------
-def diagnostic_compute(Mesh_, Diag: DiagnosticVars, Prog: PrognosticVars) -> None:
-    """diagnostic_compute!(Mesh, Diag, Prog; backend) (DiagnosticVars.jl:108-117)."""
-    L.check(L.lib().mokab_diagnostic_compute(Prog.dev.handle))
+def diagnostic_compute(Mesh_, Diag: DiagnosticVars, Prog: PrognosticVars, consistent: bool = False) -> None:
+    """diagnostic_compute!(Mesh, Diag, Prog; backend) (DiagnosticVars.jl:108-117).  `consistent=True` computes the same
+    four fields of the current state without the reference's ordering artefacts (lagged flux, never-zeroed vorticity)."""
+    fn = L.lib().mokab_diagnostic_compute_consistent if consistent else L.lib().mokab_diagnostic_compute
+    L.check(fn(Prog.dev.handle))
 
 
 def computeNormalVelocityTendency(Tend, Prog, Diag, Mesh_, Config=None) -> None:

@@ -108,11 +108,13 @@ def ocn_init_alarms(Setup: ModelSetup, dt_seconds: float | None = None):
 
 
 def ocn_run_loop(timestep, Prog, Diag, Tend, Setup, stepper, clock: Clock, simulationAlarm, outputAlarm, sum_ssh2: bool = False,
-                 on_output=None):
+                 on_output=None, series: list | None = None):
     """run_loop.jl:8-45: `while !isRinging(simulationAlarm): advance!(clock); ocn_timestep(...); outputAlarm handling`.
     Steps between two alarm events run as one device-resident call.  `on_output(clock)` is called where the reference
     has its "should be doing i/o in here" placeholder (run_loop.jl:16-19).  With `sum_ssh2` the second method's
-    squared-SSH sum is returned (run_loop.jl:24-44).  Returns the number of steps taken (the reference's global `i`)."""
+    squared-SSH sum is returned (run_loop.jl:24-44).  When `series` is a list, one record {time, steps, mass, energy,
+    ssh2} (device reductions over the current state) is appended at every output alarm.  Returns the number of steps
+    taken (the reference's global `i`)."""
     dt = float(np.asarray(timestep).reshape(-1)[0]) if not isinstance(timestep, (int, float)) else float(timestep)
     i = 0
     while not isRinging(simulationAlarm):
@@ -128,6 +130,9 @@ def ocn_run_loop(timestep, Prog, Diag, Tend, Setup, stepper, clock: Clock, simul
         api.ocn_timestep(dt, Prog, Diag, Tend, Setup, stepper, nsteps=n)
         i += n
         if isRinging(outputAlarm):
+            if series is not None:
+                series.append({"time": clock.currTime, "steps": i, "mass": api.reduce_sum(Prog, "mass"),
+                               "energy": api.reduce_sum(Prog, "energy"), "ssh2": api.reduce_sum(Prog, "ssh2")})
             if on_output is not None:
                 on_output(clock)
             reset(outputAlarm)

@@ -96,3 +96,31 @@ def test_clocked_run_loop_batches_between_alarms(backend, tmp_path):
         driver.ocn_run_loop(7000.0, Prog2, Diag2, Tend2, Setup2, mb.RungeKutta4, clock2, sim2, out2)
     with pytest.raises(mb.MokaError):
         mb.ocn_init_alarms(Setup2, dt_seconds=0.5)
+
+
+def test_consistent_diagnostics_and_conservation_series(backend, tmp_path):
+    """diagnostics at face value (flux of the same state, vorticity zeroed) against the oracle's
+    operators, and a mass / energy time series recorded at the output alarms."""
+    import moka_oracle as O
+    m, (ssh, u, h), cfg, out_fp = _stage(tmp_path, "RK4")
+    Setup, Diag, Tend, Prog = mb.ocn_init(cfg, backend=backend)
+    clock, sim, outp = mb.ocn_init_alarms(Setup)
+    series = []
+    driver.ocn_run_loop(900.0, Prog, Diag, Tend, Setup, mb.RungeKutta4, clock, sim, outp, series=series)
+    assert [r["steps"] for r in series] == [4, 8, 12]
+    mass0 = float(np.sum(m["areaCell"] * h))
+    assert all(abs(r["mass"] - mass0) <= 1e-13 * mass0 for r in series)          # flux form: mass to round-off
+    e = [r["energy"] for r in series]
+    assert e[0] > e[1] > e[2] and e[0] - e[2] <= 1e-4 * e[0]                     # RK4 damps slightly (2.5e-5 over 8 steps)
+    om = OC.OracleModel(m, ssh, u, h)
+    om.run_loop(900.0, 12, "RungeKutta4")
+    he = O.interpolate_cell2edge(m, om.layerThickness[1])
+    want = float(np.sum(m["areaCell"] * 0.5 * 9.80616 * om.ssh[1] ** 2) + np.sum(0.5 * m["dcEdge"] * m["dvEdge"] * he * om.normalVelocity[1] ** 2))
+    assert abs(e[2] - want) <= 1e-12 * want
+    for _ in range(2):                                                           # twice: nothing accumulates
+        mb.diagnostic_compute(Setup.mesh, Diag, Prog, consistent=True)
+    un, hn = Prog.normalVelocity, Prog.layerThickness
+    hedge = O.interpolate_cell2edge(m, hn)
+    assert np.array_equal(Diag.layerThicknessEdge, hedge) and np.array_equal(Diag.thicknessFlux, un * hedge)
+    assert np.array_equal(Diag.velocityDivCell, O.divergence_on_cell(m, un)[0])
+    assert np.array_equal(Diag.relativeVorticity, O.curl_on_vertex(m, un))

@@ -10,6 +10,8 @@ python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke_$tag.log 2>&1; e
 python bench.py > $out/bench_$tag.json 2> $out/bench_$tag.err; echo "bench rc=$?"; cat $out/bench_$tag.json
 python bench.py --workload igw2048 --no-cpu > $out/bench_${tag}_igw2048.json 2>> $out/bench_$tag.err; cat $out/bench_${tag}_igw2048.json
 python bench.py --workload igw2048 --dtype f32 --no-cpu > $out/bench_${tag}_igw2048_f32.json 2>> $out/bench_$tag.err; cat $out/bench_${tag}_igw2048_f32.json
+python bench.py --workload kelvin1024 --no-cpu > $out/bench_${tag}_kelvin1024.json 2>> $out/bench_$tag.err; cat $out/bench_${tag}_kelvin1024.json
+python bench.py --explicit-eoe --no-cpu > $out/bench_${tag}_explicit_eoe.json 2>> $out/bench_$tag.err; cat $out/bench_${tag}_explicit_eoe.json
 python bench.py --impl reference --steps 5 --warmup 1 > $out/bench_${tag}_reference.json 2>> $out/bench_$tag.err; cat $out/bench_${tag}_reference.json
 # launch list of the default bench command (short), then one full capture of the four stage launches of a step
 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $out/launches_$tag.csv \
