@@ -172,7 +172,8 @@ def run_b200(args):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = (json.load(f).get(f"{args.workload}_{args.dtype}") or {}).get("bytes_per_launch")
+            key = f"{args.workload}_{args.dtype}" + ("_explicit" if args.explicit_eoe else "")
+            traffic = (json.load(f).get(key) or {}).get("bytes_per_launch")
     except Exception:
         pass
 
@@ -219,12 +220,16 @@ def cpu_baseline(m, state, dt, budget_s=15.0, kelvin=False):
     om.run_loop(dt, 1, "RungeKutta4")
     t1 = time.perf_counter() - t0
     n = int(max(1, min(50, budget_s / max(t1, 1e-6))))
-    t0 = time.perf_counter()
-    om.run_loop(dt, n, "RungeKutta4")
-    tt = time.perf_counter() - t0
-    return {"value": m["nCells"] * n / tt, "unit": "cell-steps/s", "cores": om.num_threads(), "kind": "port",
-            "sample": f"{n} RK4 steps of the same {m['nCells']}-cell mesh, C/OpenMP restatement of the reference's unfused "
-                      f"per-stage kernel sequence (no Julia in this image), {tt:.1f} s"}
+    chunk, best, tt, done = max(1, n // 3), 0.0, 0.0, 0
+    while done < n:                                          # best chunk: the host is shared with the GPU process's threads
+        k = min(chunk, n - done)
+        t0 = time.perf_counter()
+        om.run_loop(dt, k, "RungeKutta4")
+        t = time.perf_counter() - t0
+        best, tt, done = max(best, m["nCells"] * k / t), tt + t, done + k
+    return {"value": best, "unit": "cell-steps/s", "cores": om.num_threads(), "kind": "port",
+            "sample": f"{n} RK4 steps of the same {m['nCells']}-cell mesh in chunks of {chunk} (best chunk reported), C/OpenMP "
+                      f"restatement of the reference's unfused per-stage kernel sequence (no Julia in this image), {tt:.1f} s"}
 
 
 def run_reference(args):
