@@ -94,7 +94,10 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
     // ---- edges owned by this block's cells ----------------------------------------------------------
     const int e0 = A.blkEdgeStart[b], e1 = A.blkEdgeStart[b + 1];
     for (int e = e0 + threadIdx.x; e < e1; e += kThreads) {
+        // (fetching cellsOnEdge / the position byte of the thread's next edge one iteration ahead was measured slower:
+        //  2.68 vs 2.81 G cell-steps/s, the extra live registers spill -- profiles/README.md r01j)
         const int2 c = ld_stream(A.ce + e);
+        const unsigned ppCur = (kDer && derived) ? ld_stream(A.posE + e) : 0u;
         R k;
         if constexpr (S2T != 0) {
             // Every streaming load of this edge is issued before anything waits on one of them: the padded slots of
@@ -102,10 +105,8 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
             // the index nor the weight loads depend on nEdgesOnEdge, and one DRAM latency covers them all.
             int idx[S2T ? S2T : 1];
             R w[S2T ? S2T : 1];
-            unsigned pp = 0;
-            if (kDer && derived) {
-                pp = ld_stream(A.posE + e);
-            } else {
+            const unsigned pp = ppCur;
+            if (!(kDer && derived)) {
 #pragma unroll
                 for (int i = 0; i < S2T; ++i) idx[i] = ld_stream(A.eoe + (size_t)i * nE + e);
             }

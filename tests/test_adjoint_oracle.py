@@ -116,3 +116,16 @@ def test_gather_form_of_the_cuda_adjoint_equals_the_scatter_oracle():
         gu, gh = _gather_form_step_vjp(m, u, h, dt, lu, lh)
         su, sh = A.rk4_step_vjp(m, u, h, dt, lu, lh)
         assert O.rel_l2(gu, su) < 1e-13 and O.rel_l2(gh, sh) < 1e-13
+
+
+def test_committed_adjoint_fixture_is_reproduced_by_the_oracle():
+    import json
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "igw16_adjoint.npz"))
+    meta = json.loads(str(g["meta"]))
+    m = hex_mesh(16)
+    ssh, u, h = mb.inertialGravityWave(m).initial_state()
+    J, gu, gh = A.gradient_sum_ssh2(m, u, h, meta["dt"], meta["nsteps"])
+    assert J == float(g["J"]) and np.array_equal(gu, g["d_normalVelocity"]) and np.array_equal(gh, g["d_layerThickness"])
+    k = meta["fd_index"]
+    assert abs(gh[k] - float(g["fd_layerThickness"])) < 1e-4 and abs(gu[k] - float(g["fd_normalVelocity"])) < 1e-2

@@ -137,3 +137,22 @@ def test_operator_adjoints_like_test_Enzyme_Operators(backend):
     assert abs(lhs - rhs) <= 1e-12 * abs(lhs)
     lhs, rhs = mb.DivergenceOnCell(None, y, None, mesh) @ x, y @ mb.DivergenceOnCell_vjp(x, mesh)
     assert abs(lhs - rhs) <= 1e-12 * abs(lhs)
+
+
+def test_committed_adjoint_fixture(backend):
+    """tests/golden/igw16_adjoint.npz (made by tests/golden/make_golden_adjoint.py from the adjoint oracle)."""
+    import json
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "igw16_adjoint.npz"))
+    meta = json.loads(str(g["meta"]))
+    m = hex_mesh(16)
+    ssh, u, h = mb.inertialGravityWave(m).initial_state()
+    mesh = mb.Mesh(m, backend)
+    prog = mb.PrognosticVars(ssh, u, h, 2, mesh)
+    d_prog = mb.ocn_init_shadows(prog)
+    J = mb.autodiff_reverse_run_loop(meta["dt"], prog, d_prog, None, None, None, mb.RungeKutta4, meta["nsteps"])
+    assert abs(J - float(g["J"])) <= 1e-12 * J
+    assert rel_l2(d_prog.normalVelocity, g["d_normalVelocity"]) <= TOL64 and rel_l2(d_prog.layerThickness, g["d_layerThickness"]) <= TOL64
+    k = meta["fd_index"]
+    assert abs(d_prog.layerThickness[k] - float(g["fd_layerThickness"])) < 1e-4          # test_Enzyme_end2end.jl:176
+    assert abs(d_prog.normalVelocity[k] - float(g["fd_normalVelocity"])) < 1e-2          # :177

@@ -310,3 +310,54 @@ def test_derived_edges_on_edge_path_is_bit_identical_to_the_explicit_one(backend
     prog = mb.PrognosticVars(ssh, u, h, 2, mesh)
     mb.ocn_timestep(dt, prog, None, None, None, mb.RungeKutta4, nsteps=7)
     assert np.array_equal(prog.normalVelocity, om.normalVelocity[1]) and np.array_equal(prog.layerThickness, om.layerThickness[1])
+
+
+def _padded(m, S=8, S2=13):
+    """The same mesh with wider, zero-padded connectivity rows (maxEdges = S, maxEdges2 = S2): ragged rows as on
+    meshes that mix pentagons / hexagons / heptagons -- the kernels must honour nEdgesOnCell / nEdgesOnEdge."""
+    out = dict(m)
+    out["maxEdges"], out["maxEdges2"] = S, S2
+    for k in ("edgesOnCell", "cellsOnCell", "verticesOnCell", "edgeSignOnCell"):
+        if k in m:
+            a = np.zeros((m["nCells"], S), m[k].dtype)
+            a[:, :m[k].shape[1]] = m[k]
+            out[k] = a
+    for k in ("edgesOnEdge", "weightsOnEdge"):
+        a = np.zeros((m["nEdges"], S2), m[k].dtype)
+        a[:, :m[k].shape[1]] = m[k]
+        out[k] = a
+    if "edgeSignOnVertex" in m:                                # (nVertices, maxEdges) in the reference (HorzMesh.jl:228)
+        a = np.zeros((m["nVertices"], S), m["edgeSignOnVertex"].dtype)
+        a[:, :m["edgeSignOnVertex"].shape[1]] = m["edgeSignOnVertex"]
+        out["edgeSignOnVertex"] = a
+    return out
+
+
+def test_ragged_rows_take_the_runtime_width_kernels(backend):
+    """maxEdges = 8 / maxEdges2 = 13 with 6 / 10 live entries per row: the kernels with run-time row widths (forward,
+    reference-order and adjoint) must give the bits of the compile-time hex path and match the oracle on the padded mesh."""
+    import adjoint_oracle as A
+    m = hex_mesh(24)
+    mp = _padded(m)
+    ssh, u, h = mb.inertialGravityWave(m).initial_state()
+    dt = mb.cfl_dt(m["dc"])
+    mesh, meshp = mb.Mesh(m, backend), mb.Mesh(mp, backend)
+    assert meshp.derived_blocks()[1] == 0                      # the rebuild is a compile-time-width specialisation
+    out = []
+    for me in (mesh, meshp):
+        prog = mb.PrognosticVars(ssh, u, h, 2, me)
+        mb.ocn_timestep(dt, prog, None, None, None, mb.RungeKutta4, nsteps=9)
+        pfe = mb.PrognosticVars(ssh, u, h, 2, me)
+        mb.ocn_timestep(dt, pfe, None, None, None, mb.ForwardEuler, nsteps=5)
+        pad = mb.PrognosticVars(ssh, u, h, 2, me)
+        d_prog = mb.ocn_init_shadows(pad)
+        mb.autodiff_reverse_run_loop(dt, pad, d_prog, None, None, None, mb.RungeKutta4, 4)
+        out.append((prog.normalVelocity, prog.layerThickness, pfe.normalVelocity, pfe.layerThickness, d_prog.normalVelocity, d_prog.layerThickness))
+    for a, b in zip(out[0][:4], out[1][:4]):
+        assert np.array_equal(a, b)
+    assert rel_l2(out[1][4], out[0][4]) <= 1e-13 and rel_l2(out[1][5], out[0][5]) <= 1e-13
+    om = OC.OracleModel(mp, ssh, u, h)
+    om.run_loop(dt, 9, "RungeKutta4")
+    assert np.array_equal(out[1][0], om.normalVelocity[1]) and np.array_equal(out[1][1], om.layerThickness[1])
+    _, gu, gh = A.gradient_sum_ssh2(mp, u, h, dt, 4)
+    assert rel_l2(out[1][4], gu) <= TOL64 and rel_l2(out[1][5], gh) <= TOL64
