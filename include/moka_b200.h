@@ -79,9 +79,12 @@ enum {
 /* mesh_create flags */
 enum {
     MOKAB_MESH_RENUMBER = 1u, /* locality renumbering (space-filling curve); 0 keeps the caller's order */
-    MOKAB_MESH_EXPLICIT_EOE = 2u /* always read edgesOnEdge from memory.  Default: the fused kernel rebuilds it from
+    MOKAB_MESH_EXPLICIT_EOE = 2u,/* always read edgesOnEdge from memory.  Default: the fused kernel rebuilds it from
                                     edgesOnCell wherever the mesh follows the MPAS ordering (verified per edge at
                                     mesh_create, per-block fallback); bit-identical results, 16 % fewer DRAM bytes */
+    MOKAB_MESH_KEEP_WIDTHS = 4u  /* keep device rows as wide as the caller's maxEdges / maxEdges2.  Default: as wide as
+                                    the longest live row (nEdgesOnCell / nEdgesOnEdge), so padded files of hexagons
+                                    still take the compile-time-width kernels */
 };
 
 /* Host view of the reference mesh structs.  Pointers marked (opt) may be NULL.

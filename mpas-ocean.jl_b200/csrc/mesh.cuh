@@ -92,9 +92,18 @@ static void build_host_mesh(const mokab_mesh_desc &d, uint32_t flags, HostMesh &
                       "mesh_create: nVertices > 0 needs edgesOnVertex, areaTriangle and edgeSignOnVertex or verticesOnEdge");
 
     const int64_t nC = d.nCells, nE = d.nEdges, nV = d.nVertices;
-    const int S = (int)d.maxEdges, S2 = (int)d.maxEdges2, D = nV ? (int)d.vertexDegree : 0;
+    const int Sf = (int)d.maxEdges, S2f = (int)d.maxEdges2, D = nV ? (int)d.vertexDegree : 0;   // row widths of the caller's arrays
     const int64_t nCo = d.nCellsOwned > 0 ? d.nCellsOwned : nC, nEo = d.nEdgesOwned > 0 ? d.nEdgesOwned : nE;
     MOKAB_REQUIRE(nCo <= nC && nEo <= nE, "mesh_create: nCellsOwned/nEdgesOwned exceed nCells/nEdges");
+    // Device rows are as wide as the longest live row, not as the file's maxEdges / maxEdges2 (MPAS files often
+    // carry padding): a mesh of hexagons stored with maxEdges = 7 still gets the compile-time (10, 6) kernels.
+    int S = Sf, S2 = S2f;
+    if (!(flags & MOKAB_MESH_KEEP_WIDTHS)) {
+        int s = 1, s2 = 1;
+        for (int64_t c = 0; c < nCo; ++c) s = std::max(s, std::min((int)d.nEdgesOnCell[c], Sf));
+        for (int64_t e = 0; e < nEo; ++e) s2 = std::max(s2, std::min((int)d.nEdgesOnEdge[e], S2f));
+        S = s; S2 = s2;
+    }
     MOKAB_REQUIRE((nCo == nC && nEo == nE) || nV == 0, "mesh_create: decomposed meshes carry no vertex arrays");
     m.nC = nC; m.nE = nE; m.nV = nV; m.S = S; m.S2 = S2; m.D = D; m.nCo = nCo; m.nEo = nEo;
 
@@ -111,18 +120,18 @@ static void build_host_mesh(const mokab_mesh_desc &d, uint32_t flags, HostMesh &
         MOKAB_REQUIRE((c2 >= 1 && c2 <= nC) || (bnd && c2 == 0),
                       "mesh_create: cellsOnEdge[2, e] out of range (0 is allowed only on boundaryEdge edges)");
         int32_t n = d.nEdgesOnEdge[e];
-        MOKAB_REQUIRE(n >= 0 && n <= S2, "mesh_create: nEdgesOnEdge out of range");
+        MOKAB_REQUIRE(n >= 0 && n <= S2f, "mesh_create: nEdgesOnEdge out of range");
         for (int i = 0; i < n; ++i) {
-            int32_t x = d.edgesOnEdge[(int64_t)S2 * e + i];
+            int32_t x = d.edgesOnEdge[(int64_t)S2f * e + i];
             MOKAB_REQUIRE(x >= 0 && x <= nE, "mesh_create: edgesOnEdge out of range");
         }
         if (bnd) m.any_boundary = true;
     }
     for (int64_t c = 0; c < nCo; ++c) {
         int32_t n = d.nEdgesOnCell[c];
-        MOKAB_REQUIRE(n >= 1 && n <= S, "mesh_create: nEdgesOnCell out of range");
+        MOKAB_REQUIRE(n >= 1 && n <= Sf, "mesh_create: nEdgesOnCell out of range");
         for (int i = 0; i < n; ++i) {
-            int32_t x = d.edgesOnCell[(int64_t)S * c + i];
+            int32_t x = d.edgesOnCell[(int64_t)Sf * c + i];
             MOKAB_REQUIRE(x >= 1 && x <= nE, "mesh_create: edgesOnCell out of range");
         }
     }
@@ -214,9 +223,9 @@ static void build_host_mesh(const mokab_mesh_desc &d, uint32_t flags, HostMesh &
         const int n = eo < nEo ? d.nEdgesOnEdge[eo] : 0;                       // halo rows are never read
         m.nEoE[en] = (uint8_t)n;
         for (int i = 0; i < n; ++i) {
-            int32_t x = d.edgesOnEdge[(int64_t)S2 * eo + i];
+            int32_t x = d.edgesOnEdge[(int64_t)S2f * eo + i];
             m.eoe[(size_t)i * nE + en] = x ? invE[x - 1] : -1;  // 0 entries are skipped (coriolis kernel :67)
-            m.woe[(size_t)i * nE + en] = bnd ? 0.0 : d.weightsOnEdge[(int64_t)S2 * eo + i];
+            m.woe[(size_t)i * nE + en] = bnd ? 0.0 : d.weightsOnEdge[(int64_t)S2f * eo + i];
         }
     }
     m.f0 = m.fE[0];
@@ -231,9 +240,9 @@ static void build_host_mesh(const mokab_mesh_desc &d, uint32_t flags, HostMesh &
         const int n = co < nCo ? d.nEdgesOnCell[co] : 0;                       // halo rows are never read
         m.nEoC[cn] = (uint8_t)n; m.area[cn] = d.areaCell[co]; m.H[cn] = d.restingThicknessSum[co];
         for (int i = 0; i < n; ++i) {
-            int32_t e = d.edgesOnCell[(int64_t)S * co + i];
+            int32_t e = d.edgesOnCell[(int64_t)Sf * co + i];
             m.eoc[(size_t)i * nC + cn] = invE[e - 1];
-            m.sgnC[(size_t)i * nC + cn] = d.edgeSignOnCell ? d.edgeSignOnCell[(int64_t)S * co + i]
+            m.sgnC[(size_t)i * nC + cn] = d.edgeSignOnCell ? d.edgeSignOnCell[(int64_t)Sf * co + i]
                                                            : ((int32_t)(co + 1) == d.cellsOnEdge[2 * (int64_t)(e - 1)] ? -1 : 1);
         }
     }

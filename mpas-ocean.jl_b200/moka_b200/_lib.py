@@ -18,7 +18,7 @@ SUM_SSH2, SUM_MASS, SUM_ENERGY = range(3)
 CELLS, EDGES, VERTICES = range(3)
 RK4_FUSED, RK4_UNFUSED = 0, 1
 PART_ALL, PART_INTERIOR, PART_BOUNDARY = 0, 1, 2
-MESH_RENUMBER, MESH_EXPLICIT_EOE = 1, 2
+MESH_RENUMBER, MESH_EXPLICIT_EOE, MESH_KEEP_WIDTHS = 1, 2, 4
 
 _I32P, _F64P = C.POINTER(C.c_int32), C.POINTER(C.c_double)
 

@@ -90,7 +90,7 @@ class Mesh:
     HorzMesh.jl:292-332 (computed by the library when `edgeSignOnCell` is not supplied).
     """
 
-    def __init__(self, fields: dict, backend: B200, renumber: bool = True, explicit_eoe: bool = False):
+    def __init__(self, fields: dict, backend: B200, renumber: bool = True, explicit_eoe: bool = False, keep_widths: bool = False):
         if not isinstance(backend, B200):
             raise MokaError("Mesh: backend must be a B200 architecture")
         self.backend = backend
@@ -126,7 +126,7 @@ class Mesh:
             keep.append(a)
             setattr(d, name, a.ctypes.data_as(ptype))
         h = C.c_void_p()
-        L.check(L.lib().mokab_mesh_create(backend.handle, C.byref(d), (L.MESH_RENUMBER if renumber else 0) | (L.MESH_EXPLICIT_EOE if explicit_eoe else 0), C.byref(h)))
+        L.check(L.lib().mokab_mesh_create(backend.handle, C.byref(d), (L.MESH_RENUMBER if renumber else 0) | (L.MESH_EXPLICIT_EOE if explicit_eoe else 0) | (L.MESH_KEEP_WIDTHS if keep_widths else 0), C.byref(h)))
         self.handle = h
         self._fin = weakref.finalize(self, L.lib().mokab_mesh_destroy, h)
         self.dcEdge_mean = float(np.mean(fields["dcEdge"]))

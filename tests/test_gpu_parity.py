@@ -334,17 +334,20 @@ def _padded(m, S=8, S2=13):
 
 
 def test_ragged_rows_take_the_runtime_width_kernels(backend):
-    """maxEdges = 8 / maxEdges2 = 13 with 6 / 10 live entries per row: the kernels with run-time row widths (forward,
-    reference-order and adjoint) must give the bits of the compile-time hex path and match the oracle on the padded mesh."""
+    """maxEdges = 8 / maxEdges2 = 13 with 6 / 10 live entries per row.  By default the device rows shrink to the longest
+    live row (the compile-time hex kernels apply again); with MOKAB_MESH_KEEP_WIDTHS the kernels with run-time row
+    widths run (forward, reference-order and adjoint).  Both must give the bits of the unpadded mesh and match the
+    oracle stepping the padded arrays."""
     import adjoint_oracle as A
     m = hex_mesh(24)
     mp = _padded(m)
     ssh, u, h = mb.inertialGravityWave(m).initial_state()
     dt = mb.cfl_dt(m["dc"])
-    mesh, meshp = mb.Mesh(m, backend), mb.Mesh(mp, backend)
-    assert meshp.derived_blocks()[1] == 0                      # the rebuild is a compile-time-width specialisation
+    meshes = [mb.Mesh(m, backend), mb.Mesh(mp, backend), mb.Mesh(mp, backend, keep_widths=True)]
+    nb = (m["nCells"] + 255) // 256
+    assert [me.derived_blocks()[1] for me in meshes] == [nb, nb, 0]   # the rebuild is a compile-time-width specialisation
     out = []
-    for me in (mesh, meshp):
+    for me in meshes:
         prog = mb.PrognosticVars(ssh, u, h, 2, me)
         mb.ocn_timestep(dt, prog, None, None, None, mb.RungeKutta4, nsteps=9)
         pfe = mb.PrognosticVars(ssh, u, h, 2, me)
@@ -353,11 +356,48 @@ def test_ragged_rows_take_the_runtime_width_kernels(backend):
         d_prog = mb.ocn_init_shadows(pad)
         mb.autodiff_reverse_run_loop(dt, pad, d_prog, None, None, None, mb.RungeKutta4, 4)
         out.append((prog.normalVelocity, prog.layerThickness, pfe.normalVelocity, pfe.layerThickness, d_prog.normalVelocity, d_prog.layerThickness))
-    for a, b in zip(out[0][:4], out[1][:4]):
-        assert np.array_equal(a, b)
-    assert rel_l2(out[1][4], out[0][4]) <= 1e-13 and rel_l2(out[1][5], out[0][5]) <= 1e-13
+    for o in out[1:]:
+        for a, b in zip(out[0][:4], o[:4]):
+            assert np.array_equal(a, b)
+        assert rel_l2(o[4], out[0][4]) <= 1e-13 and rel_l2(o[5], out[0][5]) <= 1e-13
     om = OC.OracleModel(mp, ssh, u, h)
     om.run_loop(dt, 9, "RungeKutta4")
-    assert np.array_equal(out[1][0], om.normalVelocity[1]) and np.array_equal(out[1][1], om.layerThickness[1])
+    assert np.array_equal(out[2][0], om.normalVelocity[1]) and np.array_equal(out[2][1], om.layerThickness[1])
     _, gu, gh = A.gradient_sum_ssh2(mp, u, h, dt, 4)
-    assert rel_l2(out[1][4], gu) <= TOL64 and rel_l2(out[1][5], gh) <= TOL64
+    assert rel_l2(out[2][4], gu) <= TOL64 and rel_l2(out[2][5], gh) <= TOL64
+
+
+def test_truly_ragged_rows_match_the_oracle(backend):
+    """Rows of different live length (as on meshes mixing pentagons, hexagons and heptagons): a third of the cells lose
+    their last edgesOnCell entry, a third of the edges their last one or two edgesOnEdge entries.  Not a physical mesh,
+    but the kernels and the oracle must walk exactly nEdgesOnCell / nEdgesOnEdge entries -- bit-identical results in
+    the compile-time-width and the run-time-width kernels; the adjoint refuses the structurally inconsistent mesh."""
+    m = dict(hex_mesh(24))
+    rng = np.random.default_rng(11)
+    nC, nE = m["nCells"], m["nEdges"]
+    nec, nee = m["nEdgesOnCell"].copy(), m["nEdgesOnEdge"].copy()
+    nec[rng.random(nC) < 0.33] = 5
+    nee[rng.random(nE) < 0.33] -= rng.integers(1, 3)
+    eoc, eoe, w = m["edgesOnCell"].copy(), m["edgesOnEdge"].copy(), m["weightsOnEdge"].copy()
+    eoc[np.arange(6)[None, :] >= nec[:, None]] = 0
+    dead = np.arange(10)[None, :] >= nee[:, None]
+    eoe[dead], w[dead] = 0, 0.0
+    m.update(nEdgesOnCell=nec, nEdgesOnEdge=nee, edgesOnCell=eoc, edgesOnEdge=eoe, weightsOnEdge=w)
+    m["edgeSignOnCell"] = np.where(np.arange(6)[None, :] < nec[:, None], m["edgeSignOnCell"], 0).astype(np.int32)
+    ssh, u, h = mb.inertialGravityWave(m).initial_state()
+    dt = 0.5 * mb.cfl_dt(m["dc"])
+    om = OC.OracleModel(m, ssh, u, h)
+    om.run_loop(dt, 6, "RungeKutta4")
+    ofe = OC.OracleModel(m, ssh, u, h)
+    ofe.run_loop(dt, 6, "ForwardEuler")
+    for keep in (False, True):
+        mesh = mb.Mesh(m, backend, keep_widths=keep)
+        assert mesh.derived_blocks()[1] == 0                       # no block has only conforming rows
+        prog = mb.PrognosticVars(ssh, u, h, 2, mesh)
+        mb.ocn_timestep(dt, prog, None, None, None, mb.RungeKutta4, nsteps=6)
+        assert np.array_equal(prog.normalVelocity, om.normalVelocity[1]) and np.array_equal(prog.layerThickness, om.layerThickness[1])
+        pfe = mb.PrognosticVars(ssh, u, h, 2, mesh)
+        mb.ocn_timestep(dt, pfe, None, None, None, mb.ForwardEuler, nsteps=6)
+        assert np.array_equal(pfe.normalVelocity, ofe.normalVelocity[1]) and np.array_equal(pfe.layerThickness, ofe.layerThickness[1])
+    with pytest.raises(mb.MokaError, match="adjoint"):
+        mb.autodiff_reverse_run_loop(dt, prog, mb.ocn_init_shadows(prog), None, None, None, mb.RungeKutta4, 2)
