@@ -401,3 +401,45 @@ def test_truly_ragged_rows_match_the_oracle(backend):
         assert np.array_equal(pfe.normalVelocity, ofe.normalVelocity[1]) and np.array_equal(pfe.layerThickness, ofe.layerThickness[1])
     with pytest.raises(mb.MokaError, match="adjoint"):
         mb.autodiff_reverse_run_loop(dt, prog, mb.ocn_init_shadows(prog), None, None, None, mb.RungeKutta4, 2)
+
+
+def test_full_size_config2_properties(backend):
+    """configs[2] size (2048x2048, 4.2 M cells), size-independent checks: the fused kernel (edgesOnEdge rebuilt) against
+    the explicit variant and the unfused reference-order sequence bit for bit, two steps against the C oracle bit for
+    bit, mass to round-off, and the reverse-mode gradient against a central directional difference of J = sum ssh^2."""
+    m = hex_mesh(2048, with_dual=False)
+    dt = mb.cfl_dt(m["dc"])
+    ssh, u, h = mb.inertialGravityWave(m).initial_state()
+    mesh = mb.Mesh(m, backend)
+    assert mesh.derived_blocks() == (m["nCells"] // 256, m["nCells"] // 256)
+    prog = mb.PrognosticVars(ssh, u, h, 2, mesh)
+    mass0 = mb.reduce_sum(prog, "mass")
+    mb.ocn_timestep(dt, prog, None, None, None, mb.RungeKutta4, nsteps=2)
+    om = OC.OracleModel(m, ssh, u, h)
+    om.run_loop(dt, 2, "RungeKutta4")
+    assert np.array_equal(prog.normalVelocity, om.normalVelocity[1]) and np.array_equal(prog.layerThickness, om.layerThickness[1])
+    mb.ocn_timestep(dt, prog, None, None, None, mb.RungeKutta4, nsteps=9)
+    assert abs(mb.reduce_sum(prog, "mass") - mass0) <= 1e-13 * mass0
+    pu = mb.PrognosticVars(ssh, u, h, 2, mesh)
+    mb.ocn_timestep(dt, pu, None, None, None, mb.RungeKutta4, nsteps=11, fused=False)
+    assert np.array_equal(prog.normalVelocity, pu.normalVelocity) and np.array_equal(prog.layerThickness, pu.layerThickness)
+    del pu
+    mesh_x = mb.Mesh(m, backend, explicit_eoe=True)
+    px = mb.PrognosticVars(ssh, u, h, 2, mesh_x)
+    mb.ocn_timestep(dt, px, None, None, None, mb.RungeKutta4, nsteps=11)
+    assert np.array_equal(prog.normalVelocity, px.normalVelocity) and np.array_equal(prog.ssh, px.ssh)
+    del px, mesh_x
+    # gradient: <grad J, delta> against (J(x + eps delta) - J(x - eps delta)) / (2 eps), 4 steps
+    pa = mb.PrognosticVars(ssh, u, h, 2, mesh)
+    d_prog = mb.ocn_init_shadows(pa)
+    mb.autodiff_reverse_run_loop(dt, pa, d_prog, None, None, None, mb.RungeKutta4, 4)
+    rng = np.random.default_rng(4)
+    du, dh = 1e-2 * rng.standard_normal(m["nEdges"]), rng.standard_normal(m["nCells"])
+    lhs = float(d_prog.normalVelocity @ du + d_prog.layerThickness @ dh)
+    eps = 1e-3
+
+    def J(sign):
+        p = mb.PrognosticVars(ssh + sign * eps * dh, u + sign * eps * du, h + sign * eps * dh, 2, mesh)
+        return mb.ocn_run_loop(dt, p, None, None, None, mb.RungeKutta4, 4, sum_ssh2=True)
+    rhs = (J(1.0) - J(-1.0)) / (2 * eps)
+    assert abs(lhs - rhs) <= 1e-6 * abs(rhs)
