@@ -195,8 +195,12 @@ int  mokab_divergence_on_cell_vjp(mokab_ctx *ctx, const mokab_mesh *mesh, const 
 
 /* ---- src/forward entry points ------------------------------------------------------------------ */
 /* ocn_run_loop + ocn_timestep(::ForwardEuler): `nsteps` steps of src/forward/time_integration.jl:
- * 150-193 in the reference's order (lagged hEdge, scratch aliasing, accumulating vorticity). */
+ * 150-193 with the reference's semantics (lagged hEdge, accumulating vorticity), Float64 bit-faithful.  On hexagonal
+ * single-domain meshes one fused kernel per step (+ the curl when the mesh has vertex arrays): the new state goes to the
+ * other time level, thicknessFlux / velocityDivCell / tend* are re-created on demand when read; elsewhere, and in the
+ * _unfused variant, the reference's kernel sequence (one kernel per reference kernel). */
 int  mokab_timestep_forward_euler(mokab_state *state, double dt, int64_t nsteps);
+int  mokab_timestep_forward_euler_unfused(mokab_state *state, double dt, int64_t nsteps);
 /* ocn_run_loop + ocn_timestep(::RungeKutta4) as intended by time_integration.jl:61-148; `impl` is
  * MOKAB_RK4_FUSED or MOKAB_RK4_UNFUSED.  On return Prog.*[end] is the new state, Prog.*[1] the state
  * one step earlier, ssh = layerThickness - restingThicknessSum. */

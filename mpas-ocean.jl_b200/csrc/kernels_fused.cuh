@@ -226,6 +226,94 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
     }
 }
 
+// ---- fused ForwardEuler step (the reference's live stepper) ----------------------------------------------------
+// One kernel per step instead of the reference's 16 launches + 3 full-state copies (time_integration.jl:150-193,
+// SURVEY.md section 2a), bit-identical to the reference-order kernel sequence INCLUDING its ordering artefact:
+//   flux_n = u_n * hEdge_{n-1}   (diagnostic_compute! forms the flux before it refreshes layerThicknessEdge,
+//                                 DiagnosticVars.jl:112-116; hEdge starts as zeros)
+//   tendU  = 0 - (g/dc)(ssh2 - ssh1) + sum_i (w_i * u[eoe_i]) * f[eoe_i]      (normalVelocity.jl:21-53)
+//   tendH  = sum_i ((flux[e_i] * dv[e_i]) * sign_i) * invArea                 (layerThickness.jl:14-28)
+//   u' = u + dt tendU ; h' = h + dt tendH ; ssh' = h' - H ; hEdge_n = (h[c1] + h[c2]) / 2 of the OLD h
+// The new state goes to the other time level (so "previous" holds the old state exactly as advanceTimeLevels! leaves
+// it, without copying) and hEdge ping-pongs with it.  thicknessFlux, velocityDivCell and the tendency arrays are not
+// written per step: the old state and the old hEdge stay resident, and the host side re-creates those arrays with the
+// reference-order kernels when somebody asks for them (moka_b200.cu: fe_materialize).  relativeVorticity accumulates
+// over the steps in the reference (Operators.jl:135), so on meshes with vertex arrays the curl kernel still runs
+// every step.
+struct FeArgs {
+    int nE, nC, nCown;
+    const int2 *ce;
+    const int32_t *eoe;        // (S2, nE) absent -> self
+    const int32_t *eoc;        // (S, nC)  (edge << 1) | (sign > 0)
+    const uint8_t *nEoC;
+    const int32_t *blkEdgeStart;
+    const double *gdc, *woe, *fE, *dv, *invArea, *H;
+    const double *u, *h, *ssh, *hEold;
+    double *uNew, *hNew, *sshNew, *hEnew;
+    double dt, f0;
+};
+
+template <int S2T, int ST, bool UNIF>
+__global__ void __launch_bounds__(kThreads, 4)
+k_fe_step(const FeArgs A)
+{
+    const int nE = A.nE, nC = A.nC;
+    const int b = blockIdx.x;
+    const int e0 = A.blkEdgeStart[b], e1 = A.blkEdgeStart[b + 1];
+    for (int e = e0 + threadIdx.x; e < e1; e += kThreads) {
+        const int2 c = ld_stream(A.ce + e);
+        int idx[S2T];
+        double w[S2T];
+#pragma unroll
+        for (int i = 0; i < S2T; ++i) idx[i] = ld_stream(A.eoe + (size_t)i * nE + e);
+#pragma unroll
+        for (int i = 0; i < S2T; ++i) w[i] = ld_stream(A.woe + (size_t)i * nE + e);
+        const double g = ld_stream(A.gdc + e);
+        const double uo = A.u[e];
+        const double s1 = __ldg(A.ssh + c.x), s2 = __ldg(A.ssh + c.y);
+        const double h1 = __ldg(A.h + c.x), h2 = __ldg(A.h + c.y);
+        double uu[S2T], ff[S2T];
+#pragma unroll
+        for (int i = 0; i < S2T; ++i) uu[i] = __ldg(A.u + idx[i]);
+        if (!UNIF) {
+#pragma unroll
+            for (int i = 0; i < S2T; ++i) ff[i] = __ldg(A.fE + idx[i]);
+        }
+        double t = add_rn(0.0, -mul_rn(g, add_rn(s2, -s1)));
+#pragma unroll
+        for (int i = 0; i < S2T; ++i) t = add_rn(t, mul_rn(mul_rn(w[i], uu[i]), UNIF ? A.f0 : ff[i]));
+        A.uNew[e] = add_rn(uo, mul_rn(A.dt, t));                     // UpdateStateVariable!, time_integration.jl:196-202
+        A.hEnew[e] = mul_rn(0.5, add_rn(h1, h2));                    // interpolateCell2Edge!, Operators.jl:201-222
+    }
+
+    const int cc = b * kTC + threadIdx.x;
+    if (cc < A.nCown) {
+        const int n = ld_stream(A.nEoC + cc);
+        int ee[ST];
+#pragma unroll
+        for (int i = 0; i < ST; ++i) ee[i] = i < n ? ld_stream(A.eoc + (size_t)i * nC + cc) : -1;
+        double uu[ST], he[ST], dd[ST];
+#pragma unroll
+        for (int i = 0; i < ST; ++i) {
+            const int e = ee[i] >= 0 ? (ee[i] >> 1) : 0;
+            uu[i] = __ldg(A.u + e);
+            he[i] = __ldg(A.hEold + e);
+            dd[i] = __ldg(A.dv + e);
+        }
+        const double invA = ld_stream(A.invArea + cc);
+        const double ho = A.h[cc];
+        double t = 0.0;
+#pragma unroll
+        for (int i = 0; i < ST; ++i) {
+            const double fd = mul_rn(mul_rn(uu[i], he[i]), dd[i]);   // (flux * dv), flux = u * hEdge_old
+            if (ee[i] >= 0) t = add_rn(t, mul_rn((ee[i] & 1) ? fd : -fd, invA));
+        }
+        const double hn = add_rn(ho, mul_rn(A.dt, t));
+        A.hNew[cc] = hn;
+        A.sshNew[cc] = add_rn(hn, -ld_stream(A.H + cc));             // Update_ssh!, time_integration.jl:205-212
+    }
+}
+
 // ---- construction of the fused-form arrays from the reference-form device arrays ---------------------
 template <class R>
 __global__ void __launch_bounds__(256)

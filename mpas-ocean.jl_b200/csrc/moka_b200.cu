@@ -23,6 +23,7 @@ struct StateT {
     DevBuf<R> u[2], h[2], ssh[2];          // two time levels; `cur` holds Prog.*[end]
     DevBuf<R> uP[2], hP[2];                // RK provisional ping-pong
     DevBuf<R> hEdge, flux, divC, relVort, tendU, tendH, sshProv;
+    DevBuf<R> hE[2];                       // fused ForwardEuler: layerThicknessEdge ping-pong, indexed like the time levels
     DevBuf<R> staging;
     DevBuf<double> partial, result;
     // fused RK4 graphs: [parity] one step starting with cur == parity; pair = two steps
@@ -81,6 +82,9 @@ struct mokab_state {
     const mokab_mesh *mesh = nullptr;
     int dtype = MOKAB_F64;
     int cur = 1;  // index of the time level holding Prog.*[end]
+    // fused ForwardEuler leaves thicknessFlux / velocityDivCell / tend* / layerThicknessEdge to be re-created on demand
+    // from the previous time level and hE[] (fe_materialize); true while those arrays are stale
+    bool fe_lazy = false;
     mokab::StateT<double> *d = nullptr;
     mokab::StateT<float> *f = nullptr;
     ~mokab_state()
@@ -394,6 +398,59 @@ static void step_forward_euler(mokab_state *st, double dt)
     LAUNCH(ctx, ref::k_axpy, nblk(m->nE), 256, m->nE, (const double *)t->u[c].p, dt, (const double *)t->tendU.p, t->u[c].p);
     LAUNCH(ctx, ref::k_axpy, nblk(m->nC), 256, m->nC, (const double *)t->h[c].p, dt, (const double *)t->tendH.p, t->h[c].p);
     LAUNCH(ctx, k_update_ssh<double>, nblk(m->nC), 256, m->nC, (const double *)t->h[c].p, (const double *)m->H.p, t->ssh[c].p);
+}
+
+// ---- fused ForwardEuler ----------------------------------------------------------------------------------------------
+static bool fe_fusable(const mokab_state *st)
+{
+    const mokab_mesh *m = st->mesh;
+    return st->dtype == MOKAB_F64 && m->S2 == 10 && m->S == 6 && m->nCo == m->nC && m->nEo == m->nE;
+}
+
+// Re-create the Diag / Tend arrays the unfused step would have left behind, from the state before the last fused step
+// (time level 1 - cur) and the hEdge that step consumed (hE[1 - cur]); layerThicknessEdge is the hEdge it produced.
+static void fe_materialize(mokab_state *st)
+{
+    if (!st->fe_lazy) return;
+    st->fe_lazy = false;
+    mokab_ctx *ctx = st->ctx; const mokab_mesh *m = st->mesh; StateT<double> *t = st->d;
+    const int p = st->cur, o = 1 - p;
+    LAUNCH(ctx, ref::k_mul, nblk(m->nE), 256, m->nE, (const double *)t->u[o].p, (const double *)t->hE[o].p, t->flux.p);
+    LAUNCH(ctx, ref::k_divergence_on_cell, nblk(m->nC), 256, (int)m->nC, m->eoc.p, m->sgnC.p, m->nEoC.p, m->area.p, m->dv.p,
+           (const double *)t->u[o].p, t->divC.p);
+    tend_u(st, t->ssh[o].p, t->u[o].p);
+    tend_h(st, t->flux.p);
+    MOKAB_CUDA(cudaMemcpyAsync(t->hEdge.p, t->hE[p].p, m->nE * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+}
+
+static void run_fe_fused(mokab_state *st, double dt, int64_t nsteps)
+{
+    mokab_ctx *ctx = st->ctx; mokab_mesh *m = const_cast<mokab_mesh *>(st->mesh); StateT<double> *t = st->d;
+    if (nsteps <= 0) return;
+    ensure_fused<double>(m);
+    FusedMesh<double> &fm = fused_of<double>(m);
+    if (t->hE[0].n == 0) { t->hE[0].alloc(m->nE); t->hE[1].alloc(m->nE); }
+    if (!st->fe_lazy)   // entering from the other entry points: the canonical layerThicknessEdge is what the next flux uses
+        MOKAB_CUDA(cudaMemcpyAsync(t->hE[st->cur].p, t->hEdge.p, m->nE * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    fused::FeArgs A;
+    A.nE = (int)m->nE; A.nC = (int)m->nC; A.nCown = (int)m->nCo;
+    A.ce = m->ce.p; A.eoe = m->eoeF.p; A.eoc = m->eocF.p; A.nEoC = m->nEoC.p; A.blkEdgeStart = m->blkEdgeStart.p;
+    A.gdc = fm.gdc.p; A.woe = m->woe.p; A.fE = m->fE.p; A.dv = m->dv.p; A.invArea = fm.invArea.p; A.H = m->H.p;
+    A.dt = dt; A.f0 = m->f0;
+    for (int64_t i = 0; i < nsteps; ++i) {
+        const int p = st->cur, q = 1 - p;
+        A.u = t->u[p].p; A.h = t->h[p].p; A.ssh = t->ssh[p].p; A.hEold = t->hE[p].p;
+        A.uNew = t->u[q].p; A.hNew = t->h[q].p; A.sshNew = t->ssh[q].p; A.hEnew = t->hE[q].p;
+        if (m->uniformF) fused::k_fe_step<10, 6, true><<<m->fusedBlocks, fused::kThreads, 0, ctx->stream>>>(A);
+        else             fused::k_fe_step<10, 6, false><<<m->fusedBlocks, fused::kThreads, 0, ctx->stream>>>(A);
+        MOKAB_CUDA(cudaGetLastError());
+        ctx->launches++;
+        if (m->nV)      // relativeVorticity accumulates step by step in the reference (Operators.jl:135)
+            LAUNCH(ctx, ref::k_curl_on_vertex, nblk(m->nV), 256, (int)m->nV, m->D, m->eov.p, m->sgnV.p, m->areaTri.p, m->dc.p,
+                   (const double *)t->u[p].p, t->relVort.p);
+        st->cur = q;
+    }
+    st->fe_lazy = true;
 }
 
 // ocn_timestep(::RungeKutta4) with the reference's per-stage kernel sequence (time_integration.jl:112-137)
@@ -1012,6 +1069,7 @@ int mokab_state_set(mokab_state *state, int field, const void *host)
         MOKAB_REQUIRE(state && host, "state_set: NULL argument");
         MOKAB_REQUIRE(field >= MOKAB_SSH && field <= MOKAB_D_LAYER_THICKNESS, "state_set: unknown field id");
         state->ctx->bind();
+        fe_materialize(state);
         if (state->dtype == MOKAB_F64) state_set<double>(state, field, host); else state_set<float>(state, field, host);
     });
 }
@@ -1022,6 +1080,7 @@ int mokab_state_get(mokab_state *state, int field, void *host)
         MOKAB_REQUIRE(state && host, "state_get: NULL argument");
         MOKAB_REQUIRE(field >= MOKAB_SSH && field <= MOKAB_D_LAYER_THICKNESS, "state_get: unknown field id");
         state->ctx->bind();
+        if (field >= MOKAB_LAYER_THICKNESS_EDGE && field <= MOKAB_TEND_LAYER_THICKNESS) fe_materialize(state);
         if (state->dtype == MOKAB_F64) state_get<double>(state, field, host); else state_get<float>(state, field, host);
     });
 }
@@ -1032,6 +1091,7 @@ int mokab_state_set_async(mokab_state *state, int field, const void *host_pinned
         MOKAB_REQUIRE(state && host_pinned, "state_set_async: NULL argument");
         MOKAB_REQUIRE(field >= MOKAB_SSH && field <= MOKAB_D_LAYER_THICKNESS, "state_set_async: unknown field id");
         state->ctx->bind();
+        fe_materialize(state);
         if (state->dtype == MOKAB_F64) state_set_async<double>(state, field, host_pinned);
         else state_set_async<float>(state, field, host_pinned);
     });
@@ -1043,6 +1103,7 @@ int mokab_state_get_async(mokab_state *state, int field, void *host_pinned)
         MOKAB_REQUIRE(state && host_pinned, "state_get_async: NULL argument");
         MOKAB_REQUIRE(field >= MOKAB_SSH && field <= MOKAB_D_LAYER_THICKNESS, "state_get_async: unknown field id");
         state->ctx->bind();
+        if (field >= MOKAB_LAYER_THICKNESS_EDGE && field <= MOKAB_TEND_LAYER_THICKNESS) fe_materialize(state);
         if (state->dtype == MOKAB_F64) state_get_async<double>(state, field, host_pinned);
         else state_get_async<float>(state, field, host_pinned);
     });
@@ -1064,6 +1125,7 @@ int mokab_diagnostic_compute(mokab_state *state)
         MOKAB_REQUIRE(state, "diagnostic_compute: state is NULL");
         require_f64(state, "diagnostic_compute");
         state->ctx->bind();
+        fe_materialize(state);
         diag_compute(state, state->d->u[state->cur].p, state->d->h[state->cur].p);
     });
 }
@@ -1074,6 +1136,7 @@ int mokab_diagnostic_compute_consistent(mokab_state *state)
         MOKAB_REQUIRE(state, "diagnostic_compute_consistent: state is NULL");
         require_f64(state, "diagnostic_compute_consistent");
         state->ctx->bind();
+        fe_materialize(state);
         diag_consistent(state, state->d->u[state->cur].p, state->d->h[state->cur].p);
     });
 }
@@ -1084,6 +1147,7 @@ int mokab_compute_normal_velocity_tendency(mokab_state *state)
         MOKAB_REQUIRE(state, "compute_normal_velocity_tendency: state is NULL");
         require_f64(state, "compute_normal_velocity_tendency");
         state->ctx->bind();
+        fe_materialize(state);
         tend_u(state, state->d->ssh[state->cur].p, state->d->u[state->cur].p);
     });
 }
@@ -1094,6 +1158,7 @@ int mokab_compute_layer_thickness_tendency(mokab_state *state)
         MOKAB_REQUIRE(state, "compute_layer_thickness_tendency: state is NULL");
         require_f64(state, "compute_layer_thickness_tendency");
         state->ctx->bind();
+        fe_materialize(state);
         tend_h(state, state->d->flux.p);
     });
 }
@@ -1202,6 +1267,22 @@ int mokab_timestep_forward_euler(mokab_state *state, double dt, int64_t nsteps)
         MOKAB_REQUIRE(nsteps >= 0, "timestep_forward_euler: nsteps must be >= 0");
         require_f64(state, "timestep_forward_euler");
         state->ctx->bind();
+        if (fe_fusable(state)) {
+            run_fe_fused(state, dt, nsteps);
+        } else {
+            for (int64_t i = 0; i < nsteps; ++i) step_forward_euler(state, dt);
+        }
+    });
+}
+
+int mokab_timestep_forward_euler_unfused(mokab_state *state, double dt, int64_t nsteps)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(state, "timestep_forward_euler_unfused: state is NULL");
+        MOKAB_REQUIRE(nsteps >= 0, "timestep_forward_euler_unfused: nsteps must be >= 0");
+        require_f64(state, "timestep_forward_euler_unfused");
+        state->ctx->bind();
+        fe_materialize(state);
         for (int64_t i = 0; i < nsteps; ++i) step_forward_euler(state, dt);
     });
 }
@@ -1213,6 +1294,7 @@ int mokab_timestep_rk4(mokab_state *state, double dt, int64_t nsteps, int impl)
         MOKAB_REQUIRE(nsteps >= 0, "timestep_rk4: nsteps must be >= 0");
         MOKAB_REQUIRE(impl == MOKAB_RK4_FUSED || impl == MOKAB_RK4_UNFUSED, "timestep_rk4: unknown impl");
         state->ctx->bind();
+        fe_materialize(state);
         if (impl == MOKAB_RK4_UNFUSED) {
             require_f64(state, "timestep_rk4(MOKAB_RK4_UNFUSED)");
             for (int64_t i = 0; i < nsteps; ++i) step_rk4_unfused(state, dt);

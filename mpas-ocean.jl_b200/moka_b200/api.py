@@ -347,7 +347,8 @@ def ocn_timestep(timestep: float, Prog, Diag, Tend, Setup=None, stepper=RungeKut
     """ocn_timestep(timestep, Prog, Diag, Tend, Setup, ::Type{ForwardEuler|RungeKutta4}; backend)
     (time_integration.jl:61-66,150-156).  `nsteps` > 1 keeps the loop on the device."""
     if stepper is ForwardEuler:
-        L.check(L.lib().mokab_timestep_forward_euler(Prog.dev.handle, float(timestep), int(nsteps)))
+        fn = L.lib().mokab_timestep_forward_euler if fused else L.lib().mokab_timestep_forward_euler_unfused
+        L.check(fn(Prog.dev.handle, float(timestep), int(nsteps)))
     elif stepper is RungeKutta4:
         L.check(L.lib().mokab_timestep_rk4(Prog.dev.handle, float(timestep), int(nsteps), L.RK4_FUSED if fused else L.RK4_UNFUSED))
     else:

@@ -443,3 +443,43 @@ def test_full_size_config2_properties(backend):
         return mb.ocn_run_loop(dt, p, None, None, None, mb.RungeKutta4, 4, sum_ssh2=True)
     rhs = (J(1.0) - J(-1.0)) / (2 * eps)
     assert abs(lhs - rhs) <= 1e-6 * abs(rhs)
+
+
+def test_fused_forward_euler_is_the_reference_sequence_bit_for_bit(backend):
+    """The one-kernel-per-step ForwardEuler against the oracle's reference-order sequence: prognostic fields of both
+    time levels, and every Diag / Tend array (re-created on demand from the retained old state), at several points of
+    a run that interleaves reads, more steps, the explicit entry points and the unfused variant."""
+    m = dict(hex_mesh(32))
+    m["fEdge"] = 1.0e-4 * (1.0 + 0.3 * np.cos(2 * np.pi * m["xEdge"] / m["x_period"]))   # per-edge f gathers (UNIF = false)
+    for mesh_fields in (hex_mesh(32), m):
+        ssh, u, h = mb.inertialGravityWave(mesh_fields).initial_state()
+        dt = 0.3 * mb.cfl_dt(mesh_fields["dc"])
+        mesh = mb.Mesh(mesh_fields, backend)
+        prog = mb.PrognosticVars(ssh, u, h, 2, mesh)
+        diag, tend = mb.DiagnosticVars(prog), mb.TendencyVars(prog)
+        om = OC.OracleModel(mesh_fields, ssh, u, h)
+
+        def check():
+            assert np.array_equal(prog.normalVelocity, om.normalVelocity[1]) and np.array_equal(prog.layerThickness, om.layerThickness[1])
+            assert np.array_equal(prog.ssh, om.ssh[1])
+            assert np.array_equal(prog.normalVelocity_prev, om.normalVelocity[0]) and np.array_equal(prog.ssh_prev, om.ssh[0])
+            assert np.array_equal(diag.layerThicknessEdge, om.layerThicknessEdge) and np.array_equal(diag.thicknessFlux, om.thicknessFlux)
+            assert np.array_equal(diag.velocityDivCell, om.velocityDivCell)
+            assert np.array_equal(diag.relativeVorticity, om.relativeVorticity[:mesh_fields["nVertices"]])
+            assert np.array_equal(tend.tendNormalVelocity, om.tendNormalVelocity) and np.array_equal(tend.tendLayerThickness, om.tendLayerThickness)
+
+        for n in (1, 4, 3):                                      # step 1 alone shows the zero-flux quirk (h unchanged)
+            mb.ocn_timestep(dt, prog, diag, tend, None, mb.ForwardEuler, nsteps=n)
+            om.run_loop(dt, n, "ForwardEuler")
+            check()
+        assert np.array_equal(prog.layerThickness_prev, om.layerThickness[0])
+        mb.ocn_timestep(dt, prog, diag, tend, None, mb.ForwardEuler, nsteps=2, fused=False)     # the kernel-per-kernel variant continues
+        om.run_loop(dt, 2, "ForwardEuler")
+        check()
+        mb.diagnostic_compute(mesh, diag, prog)                  # explicit entry points in between
+        mb.computeNormalVelocityTendency(tend, prog, diag, mesh)
+        om.diagnostic_compute()
+        om.compute_normal_velocity_tendency()
+        mb.ocn_timestep(dt, prog, diag, tend, None, mb.ForwardEuler, nsteps=5)
+        om.run_loop(dt, 5, "ForwardEuler")
+        check()
