@@ -89,6 +89,7 @@ class DecomposedModel:
         backend.set_stream(self.compute.cuda_stream)
         self.handle = self.prog.dev.handle
         self._graph, self._graph_dt = None, None
+        self._validated, self.graph_status = False, "not used"
 
     def _stage(self, dt, s, part, stream):
         L.check(L.lib().mokab_rk4_stage(self.handle, float(dt), s, part, C.c_void_p(stream.cuda_stream)))
@@ -124,21 +125,64 @@ class DecomposedModel:
             L.check(L.lib().mokab_rk4_finish_step(self.handle))
         self.compute.wait_stream(self.halo)                      # join
 
-    def step(self, dt: float, nsteps: int = 1) -> None:
+    def _build_graph(self, dt: float) -> None:
+        """Capture two consecutive steps (one per time-level parity), NCCL calls included, into one CUDA graph."""
         torch = self.torch
+        self.compute.synchronize()
+        self.halo.synchronize()
+        self._enqueue_steps(dt, 2)                               # warm up NCCL + lazy library state outside capture
+        self.compute.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=self.compute):
+            self._enqueue_steps(dt, 2)
+        self._graph, self._graph_dt = g, dt
+
+    def _snapshot(self):
+        return [self.prog.dev.get(f) for f in (L.SSH, L.NORMAL_VELOCITY, L.LAYER_THICKNESS)]
+
+    def _restore(self, snap) -> None:
+        for f, a in zip((L.SSH, L.NORMAL_VELOCITY, L.LAYER_THICKNESS), snap):
+            self.prog.dev.set(f, a)
+
+    def validate_graph(self, dt: float, nsteps: int = 8) -> bool:
+        """Build the 2-step graph and accept it only if replaying it reproduces, bit for bit on every rank, what the
+        stream-launched schedule computes from the same state (`nsteps` even; the state is restored afterwards).
+        A captured schedule that also contains NCCL traffic is not something to trust unchecked: on rejection the
+        model keeps launching from the host (`use_graph` False, reason in `graph_status`)."""
+        import torch.distributed as dist
+        snap = self._snapshot()
+        self._enqueue_steps(dt, nsteps)
+        self.finish()
+        want = self._snapshot()
+        self._restore(snap)
+        self._build_graph(dt)                                    # advances the state by its two warm-up steps
+        with self.torch.cuda.stream(self.compute):
+            for _ in range((nsteps - 2) // 2):
+                self._graph.replay()
+        self.finish()
+        got = self._snapshot()
+        self._restore(snap)
+        ok = all(np.array_equal(a, b) for a, b in zip(want, got))
+        flag = self.torch.tensor([1 if ok else 0], dtype=self.torch.int32, device=self.dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.ex.group)
+        self.compute.synchronize()
+        self._validated = True
+        if int(flag.item()) == 0:
+            self._graph, self._graph_dt, self.use_graph = None, None, False
+            self.graph_status = "rejected: graph replay did not reproduce the stream-launched schedule; launching from the host"
+            import gc
+            gc.collect()
+            return False
+        self.graph_status = f"validated against the stream-launched schedule over {nsteps} steps"
+        return True
+
+    def step(self, dt: float, nsteps: int = 1) -> None:
         if self.use_graph and nsteps >= 2:
             if self._graph is None or self._graph_dt != dt:
-                self.compute.synchronize()
-                self.halo.synchronize()
-                self._enqueue_steps(dt, 2)                       # warm up NCCL + lazy library state outside capture
-                self.compute.synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=self.compute):
-                    self._enqueue_steps(dt, 2)
-                self._graph, self._graph_dt = g, dt
-                self._warm = 2
-                nsteps -= 2
-            with torch.cuda.stream(self.compute):
+                if not self.validate_graph(dt):
+                    self._enqueue_steps(dt, nsteps)
+                    return
+            with self.torch.cuda.stream(self.compute):
                 for _ in range(nsteps // 2):
                     self._graph.replay()
             nsteps = nsteps % 2
@@ -330,7 +374,7 @@ def bench_main(args, rank, world, local):
                                    f"{'Float64' if args.dtype == 'f64' else 'Float32'} RK4, dt={dt:.4g}s, recursive-coordinate-bisection "
                                    f"into {world} parts, 1 halo layer, NCCL all-to-all per stage "
                                    f"{'overlapped with interior blocks' if model.overlap else '(no overlap)'}"
-                                   f"{', 2-step CUDA graph incl. NCCL' if model.use_graph else ''}",
+                                   f"{', 2-step CUDA graph incl. NCCL (' + model.graph_status + ')' if model.use_graph else ', CUDA graph ' + model.graph_status}",
                        "name": args.workload, "l2": "inputs larger than L2 (no flush)", "setup_s": round(t_setup, 1),
                        "rank0_blocks_interior_boundary": list(blocks), "rank0_halo_bytes_per_stage": int(halo_bytes),
                        "rank0_blocks_rebuilding_edgesOnEdge": [int(nder), int(nblk)]},

@@ -33,6 +33,7 @@ def main():
         model.finish()
         gs, gu, gh = multi_gpu.gather_owned(model, m["nCells"], m["nEdges"])
         mass = model.reduce("mass")
+        status = model.graph_status
         model.close()
         del model
         if rank == 0:
@@ -42,10 +43,10 @@ def main():
             rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))
             e = (rel(gs, om.ssh[1]), rel(gu, om.normalVelocity[1]), rel(gh, om.layerThickness[1]))
             m0 = float(np.sum(m["areaCell"] * om.layerThickness[1]))
-            errs.append(((overlap, graph), e, abs(mass - m0) / m0))
+            errs.append(((overlap, graph), e, abs(mass - m0) / m0, status))
     if rank == 0:
         print(errs)
-        ok = all(max(e) <= 1e-12 and dm <= 1e-13 for _, e, dm in errs)
+        ok = all(max(e) <= 1e-12 and dm <= 1e-13 for _, e, dm, _ in errs)
         print("MULTI_GPU_CHECK_OK" if ok else "MULTI_GPU_CHECK_FAILED")
     sys.stdout.flush()
     dist.barrier()
