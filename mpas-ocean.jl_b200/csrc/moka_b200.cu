@@ -151,6 +151,10 @@ static void ensure_fused(mokab_mesh *m)
            m->woe.p, m->nEoE.p, f.gdc.p, f.dv.p, f.wf.p, need_idx ? m->eoeF.p : nullptr, m->uniformF ? 0 : 1);
     LAUNCH(ctx, fused::k_build_fused_cells<R>, nblk(m->nC), 256, (int)m->nC, m->S, m->area.p, m->H.p, m->eoc.p, m->sgnC.p,
            m->nEoC.p, f.invArea.p, f.H.p, need_idx ? m->eocF.p : nullptr);
+    // The staged entry points (mokab_rk4_stage / mokab_refresh_ssh) launch on CALLER streams that are not ordered
+    // with the context's stream: the arrays built above must be complete before anybody can read them.  One host
+    // synchronisation per (mesh, precision); mokab_state_create builds them up front so it never lands in a step.
+    MOKAB_CUDA(cudaStreamSynchronize(ctx->stream));
     f.ready = true;
 }
 
@@ -1045,6 +1049,9 @@ int mokab_state_create(mokab_ctx *ctx, const mokab_mesh *mesh, int dtype, mokab_
         st->ctx = ctx; st->mesh = mesh; st->dtype = dtype;
         try {
             if (dtype == MOKAB_F64) alloc_state<double>(st); else alloc_state<float>(st);
+            // the fused-form mesh arrays of this precision, complete before any stepper can be launched on any stream
+            if (dtype == MOKAB_F64) ensure_fused<double>(const_cast<mokab_mesh *>(mesh));
+            else ensure_fused<float>(const_cast<mokab_mesh *>(mesh));
         } catch (...) {
             delete st;
             throw;

@@ -56,6 +56,16 @@ class HaloExchanger:
                 w.wait()
 
 
+def plan_steps(nsteps: int, parity: int, graph_parity: int):
+    """How `nsteps` steps are issued when a 2-step graph captured at time-level parity `graph_parity` exists and the
+    state currently has parity `parity` (steps taken so far mod 2): (stream-launched steps first, graph replays,
+    stream-launched steps after).  The graph's kernels have the time-level buffers of its capture parity baked in, so
+    it may only be replayed from that parity."""
+    pre = 1 if (parity & 1) != (graph_parity & 1) and nsteps >= 1 else 0
+    rest = nsteps - pre
+    return pre, rest // 2, rest % 2
+
+
 class DecomposedModel:
     """This rank's share of the mesh on its GPU + the stage/exchange schedule.
 
@@ -90,6 +100,7 @@ class DecomposedModel:
         self.handle = self.prog.dev.handle
         self._graph, self._graph_dt = None, None
         self._validated, self.graph_status = False, "not used"
+        self._parity, self._graph_parity = 0, 0                  # steps taken so far mod 2; the same at graph capture
 
     def _stage(self, dt, s, part, stream):
         L.check(L.lib().mokab_rk4_stage(self.handle, float(dt), s, part, C.c_void_p(stream.cuda_stream)))
@@ -135,7 +146,7 @@ class DecomposedModel:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=self.compute):
             self._enqueue_steps(dt, 2)
-        self._graph, self._graph_dt = g, dt
+        self._graph, self._graph_dt, self._graph_parity = g, dt, self._parity
 
     def _snapshot(self):
         return [self.prog.dev.get(f) for f in (L.SSH, L.NORMAL_VELOCITY, L.LAYER_THICKNESS)]
@@ -176,18 +187,25 @@ class DecomposedModel:
         self.graph_status = f"validated against the stream-launched schedule over {nsteps} steps"
         return True
 
+    def _run(self, dt: float, nsteps: int) -> None:
+        """Stream-launched steps (outside any capture), keeping track of the time-level parity."""
+        self._enqueue_steps(dt, nsteps)
+        self._parity ^= nsteps & 1
+
     def step(self, dt: float, nsteps: int = 1) -> None:
         if self.use_graph and nsteps >= 2:
             if self._graph is None or self._graph_dt != dt:
                 if not self.validate_graph(dt):
-                    self._enqueue_steps(dt, nsteps)
+                    self._run(dt, nsteps)
                     return
+            pre, replays, nsteps = plan_steps(nsteps, self._parity, self._graph_parity)
+            if pre:
+                self._run(dt, pre)
             with self.torch.cuda.stream(self.compute):
-                for _ in range(nsteps // 2):
+                for _ in range(replays):
                     self._graph.replay()
-            nsteps = nsteps % 2
         if nsteps:
-            self._enqueue_steps(dt, nsteps)
+            self._run(dt, nsteps)
 
     def refresh_ssh(self) -> None:
         """ssh = layerThickness - restingThicknessSum on the compute stream (asynchronous)."""

@@ -119,3 +119,16 @@ def test_two_rank_gloo_halo_exchange_matches_single_domain(tmp_path, world):
         assert np.array_equal(z["halo_u"], prog["normalVelocity"][-1][z["halo_e"]])     # halos hold the owners' values
     assert np.array_equal(gu, prog["normalVelocity"][-1])         # bit-exact: same arithmetic per entity
     assert np.array_equal(gh, prog["layerThickness"][-1])
+
+
+def test_graph_replay_plan_respects_time_level_parity():
+    """multi_gpu.plan_steps: a 2-step graph may only be replayed from the parity it was captured at; any number of steps
+    from any parity is covered exactly once, and the parity after the plan is what the step count implies."""
+    from moka_b200.multi_gpu import plan_steps
+    for graph_parity in (0, 1):
+        for parity in (0, 1):
+            for n in range(2, 12):
+                pre, replays, post = plan_steps(n, parity, graph_parity)
+                assert pre + 2 * replays + post == n and pre in (0, 1) and post in (0, 1) and replays >= 0
+                assert (parity + pre) % 2 == graph_parity or replays == 0      # replays start at the capture parity
+                assert pre == (1 if parity != graph_parity else 0)

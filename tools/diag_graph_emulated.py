@@ -38,7 +38,10 @@ def main():
     sp = C.c_void_p(stream.cuda_stream)
 
     def make():
-        return [_Rank(backend, loc, state, args.parts) for loc in locs]
+        ranks = [_Rank(backend, loc, state, args.parts) for loc in locs]
+        backend.synchronize()       # `stream` below is not ordered with the context's stream the uploads ran on
+        torch.cuda.synchronize()
+        return ranks
 
     def enqueue(ranks, nsteps):
         with torch.cuda.stream(stream):
