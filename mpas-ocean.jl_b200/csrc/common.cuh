@@ -97,6 +97,10 @@ namespace mokab {
 
 // ---- device helpers -----------------------------------------------------------------------------
 // Streaming (read-once) loads: keep them out of L1 so the gathered state stays resident there.
+#ifdef MOKAB_SIM   // host build of the simulation tests (tests/sim): a plain load
+template <class T>
+__device__ __forceinline__ T ld_stream(const T *p) { return *p; }
+#else
 template <class T>
 __device__ __forceinline__ T ld_stream(const T *p);
 template <>
@@ -141,5 +145,6 @@ __device__ __forceinline__ float ld_stream<float>(const float *p)
     asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
 }
+#endif
 
 }  // namespace mokab

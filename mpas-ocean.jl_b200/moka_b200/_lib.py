@@ -62,45 +62,52 @@ SYMBOLS = [
 ]
 
 
-def lib():
+def bind(L):
+    """Declare the argument / result types of every entry point on the loaded library `L` and make it THE library of
+    this process.  `lib()` calls this with libmoka_b200.so; the simulation tests (tests/sim) call it with their host
+    build of the same sources."""
     global _lib
+    L.mokab_last_error.restype = C.c_char_p
+    vp, i64, dbl = C.c_void_p, C.c_int64, C.c_double
+    sig = {
+        "mokab_init": [C.c_int, C.POINTER(vp)], "mokab_finalize": [vp], "mokab_synchronize": [vp],
+        "mokab_set_stream": [vp, vp], "mokab_timer_start": [vp], "mokab_timer_stop": [vp, C.POINTER(dbl)],
+        "mokab_launch_count": [vp, C.POINTER(i64)], "mokab_host_alloc": [C.POINTER(vp), i64], "mokab_host_free": [vp],
+        "mokab_mesh_create": [vp, C.POINTER(MeshDesc), C.c_uint32, C.POINTER(vp)], "mokab_mesh_destroy": [vp],
+        "mokab_mesh_get_perm": [vp, C.c_int, _I32P], "mokab_mesh_device_bytes": [vp, C.POINTER(i64)],
+        "mokab_state_create": [vp, vp, C.c_int, C.POINTER(vp)], "mokab_state_destroy": [vp],
+        "mokab_state_set": [vp, C.c_int, vp], "mokab_state_get": [vp, C.c_int, vp],
+        "mokab_state_set_async": [vp, C.c_int, vp], "mokab_state_get_async": [vp, C.c_int, vp],
+        "mokab_state_synchronize": [vp],
+        "mokab_diagnostic_compute": [vp], "mokab_diagnostic_compute_consistent": [vp], "mokab_compute_normal_velocity_tendency": [vp],
+        "mokab_compute_layer_thickness_tendency": [vp],
+        "mokab_gradient_on_edge": [vp, vp, _F64P, _F64P], "mokab_divergence_on_cell": [vp, vp, _F64P, _F64P],
+        "mokab_gradient_on_edge_vjp": [vp, vp, _F64P, _F64P], "mokab_divergence_on_cell_vjp": [vp, vp, _F64P, _F64P],
+        "mokab_curl_on_vertex": [vp, vp, _F64P, _F64P], "mokab_interpolate_cell2edge": [vp, vp, _F64P, _F64P],
+        "mokab_timestep_forward_euler": [vp, dbl, i64], "mokab_timestep_forward_euler_unfused": [vp, dbl, i64], "mokab_timestep_rk4": [vp, dbl, i64, C.c_int],
+        "mokab_reduce": [vp, C.c_int, C.POINTER(dbl)],
+        "mokab_tape_begin": [vp, i64], "mokab_tape_length": [vp, C.POINTER(i64)],
+        "mokab_adjoint_seed": [vp, C.c_int], "mokab_adjoint_rk4": [vp],
+        "mokab_halo_setup": [vp, i64, _I32P, i64, _I32P], "mokab_halo_pack": [vp, C.c_int, vp, vp],
+        "mokab_halo_unpack": [vp, C.c_int, vp, vp], "mokab_rk4_stage": [vp, dbl, C.c_int, C.c_int, vp],
+        "mokab_rk4_finish_step": [vp], "mokab_refresh_ssh": [vp, vp],
+        "mokab_mesh_block_counts": [vp, C.POINTER(i64), C.POINTER(i64)],
+        "mokab_mesh_derived_blocks": [vp, C.POINTER(i64), C.POINTER(i64)],
+    }
+    for name, args in sig.items():
+        fn = getattr(L, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    _lib = L
+    return L
+
+
+def lib():
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise MokaError(f"{LIB_PATH} is missing: build it with `make -C {os.path.dirname(LIB_PATH)}` "
                             "(python __graft_entry__.py build); there is no CPU fallback")
-        L = C.CDLL(LIB_PATH)
-        L.mokab_last_error.restype = C.c_char_p
-        vp, i64, dbl = C.c_void_p, C.c_int64, C.c_double
-        sig = {
-            "mokab_init": [C.c_int, C.POINTER(vp)], "mokab_finalize": [vp], "mokab_synchronize": [vp],
-            "mokab_set_stream": [vp, vp], "mokab_timer_start": [vp], "mokab_timer_stop": [vp, C.POINTER(dbl)],
-            "mokab_launch_count": [vp, C.POINTER(i64)], "mokab_host_alloc": [C.POINTER(vp), i64], "mokab_host_free": [vp],
-            "mokab_mesh_create": [vp, C.POINTER(MeshDesc), C.c_uint32, C.POINTER(vp)], "mokab_mesh_destroy": [vp],
-            "mokab_mesh_get_perm": [vp, C.c_int, _I32P], "mokab_mesh_device_bytes": [vp, C.POINTER(i64)],
-            "mokab_state_create": [vp, vp, C.c_int, C.POINTER(vp)], "mokab_state_destroy": [vp],
-            "mokab_state_set": [vp, C.c_int, vp], "mokab_state_get": [vp, C.c_int, vp],
-            "mokab_state_set_async": [vp, C.c_int, vp], "mokab_state_get_async": [vp, C.c_int, vp],
-            "mokab_state_synchronize": [vp],
-            "mokab_diagnostic_compute": [vp], "mokab_diagnostic_compute_consistent": [vp], "mokab_compute_normal_velocity_tendency": [vp],
-            "mokab_compute_layer_thickness_tendency": [vp],
-            "mokab_gradient_on_edge": [vp, vp, _F64P, _F64P], "mokab_divergence_on_cell": [vp, vp, _F64P, _F64P],
-            "mokab_gradient_on_edge_vjp": [vp, vp, _F64P, _F64P], "mokab_divergence_on_cell_vjp": [vp, vp, _F64P, _F64P],
-            "mokab_curl_on_vertex": [vp, vp, _F64P, _F64P], "mokab_interpolate_cell2edge": [vp, vp, _F64P, _F64P],
-            "mokab_timestep_forward_euler": [vp, dbl, i64], "mokab_timestep_forward_euler_unfused": [vp, dbl, i64], "mokab_timestep_rk4": [vp, dbl, i64, C.c_int],
-            "mokab_reduce": [vp, C.c_int, C.POINTER(dbl)],
-            "mokab_tape_begin": [vp, i64], "mokab_tape_length": [vp, C.POINTER(i64)],
-            "mokab_adjoint_seed": [vp, C.c_int], "mokab_adjoint_rk4": [vp],
-            "mokab_halo_setup": [vp, i64, _I32P, i64, _I32P], "mokab_halo_pack": [vp, C.c_int, vp, vp],
-            "mokab_halo_unpack": [vp, C.c_int, vp, vp], "mokab_rk4_stage": [vp, dbl, C.c_int, C.c_int, vp],
-            "mokab_rk4_finish_step": [vp], "mokab_refresh_ssh": [vp, vp],
-            "mokab_mesh_block_counts": [vp, C.POINTER(i64), C.POINTER(i64)],
-            "mokab_mesh_derived_blocks": [vp, C.POINTER(i64), C.POINTER(i64)],
-        }
-        for name, args in sig.items():
-            fn = getattr(L, name)
-            fn.argtypes = args
-            fn.restype = C.c_int
-        _lib = L
+        bind(C.CDLL(LIB_PATH))
     return _lib
 
 

@@ -56,6 +56,37 @@ class HaloExchanger:
                 w.wait()
 
 
+class TorchRuntime:
+    """What DecomposedModel needs from the device runtime and the process group: streams / events / graph capture
+    (`cuda`: torch.cuda), the halo all-to-all and two scalar reductions (torch.distributed, NCCL).  The simulation tests
+    (tests/sim) pass an object of the same shape backed by their host runtime, so the schedule below is exercised
+    under adversarial stream interleavings without a GPU."""
+
+    def __init__(self, device_index: int, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group = torch, dist, group
+        self.cuda = torch.cuda
+        self.dev = torch.device("cuda", device_index)
+
+    def stream(self, priority: int = 0):
+        return self.torch.cuda.Stream(self.dev, priority=priority)
+
+    def exchanger(self, send_counts, recv_counts, npdtype):
+        tdt = self.torch.float64 if np.dtype(npdtype) == np.float64 else self.torch.float32
+        return HaloExchanger(send_counts, recv_counts, tdt, self.dev, self.group)
+
+    def all_reduce_min(self, value: int) -> int:
+        t = self.torch.tensor([int(value)], dtype=self.torch.int32, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN, group=self.group)
+        return int(t.item())
+
+    def all_reduce_sum(self, value: float) -> float:
+        t = self.torch.tensor([float(value)], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, group=self.group)
+        return float(t.item())
+
+
 def plan_steps(nsteps: int, parity: int, graph_parity: int):
     """How `nsteps` steps are issued when a 2-step graph captured at time-level parity `graph_parity` exists and the
     state currently has parity `parity` (steps taken so far mod 2): (stream-launched steps first, graph replays,
@@ -78,9 +109,9 @@ class DecomposedModel:
     """
 
     def __init__(self, loc: dict, state, backend: api.B200, device_index: int, dtype=np.float64, group=None, overlap=True,
-                 graph=False):
-        import torch
-        self.torch = torch
+                 graph=False, runtime=None):
+        self.rt = runtime if runtime is not None else TorchRuntime(device_index, group)
+        self.cuda = self.rt.cuda
         self.loc, self.backend, self.overlap, self.use_graph = loc, backend, overlap, graph
         self.nparts = loc["nparts"]
         self.mesh = api.Mesh(loc, backend)
@@ -88,11 +119,10 @@ class DecomposedModel:
         self.mesh.halo_setup(sidx, ridx)
         ssh, u, h = state
         self.prog = api.PrognosticVars(np.asarray(ssh, dtype), np.asarray(u, dtype), np.asarray(h, dtype), 2, self.mesh)
-        tdt = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
-        self.dev = torch.device("cuda", device_index)
-        self.ex = HaloExchanger(scnt, rcnt, tdt, self.dev, group)
-        self.compute = torch.cuda.Stream(self.dev)
-        self.halo = torch.cuda.Stream(self.dev, priority=-1)
+        self.dev = getattr(self.rt, "dev", None)
+        self.ex = self.rt.exchanger(scnt, rcnt, dtype)
+        self.compute = self.rt.stream()
+        self.halo = self.rt.stream(priority=-1)
         self.comm = self.halo
         # the context's own work (state set/get permutes, reductions, ssh refresh) joins the compute stream, so the
         # pipelined upload/download of the API orders itself with the steps without host synchronisation
@@ -107,14 +137,14 @@ class DecomposedModel:
 
     def _exchange(self, s, stream):
         lib = L.lib()
-        with self.torch.cuda.stream(stream):
+        with self.cuda.stream(stream):
             L.check(lib.mokab_halo_pack(self.handle, s, C.c_void_p(self.ex.send.data_ptr()), C.c_void_p(stream.cuda_stream)))
             self.ex.exchange()
             L.check(lib.mokab_halo_unpack(self.handle, s, C.c_void_p(self.ex.recv.data_ptr()), C.c_void_p(stream.cuda_stream)))
 
     def _enqueue_steps(self, dt: float, nsteps: int) -> None:
         """Enqueue `nsteps` RK4 steps; on entry and exit both streams are joined on `compute`."""
-        torch = self.torch
+        cuda = self.cuda
         if not self.overlap:
             for _ in range(nsteps):
                 for s in (1, 2, 3, 4):
@@ -125,7 +155,7 @@ class DecomposedModel:
         self.halo.wait_stream(self.compute)                      # fork
         for _ in range(nsteps):
             for s in (1, 2, 3, 4):
-                ev_i, ev_b = torch.cuda.Event(), torch.cuda.Event()
+                ev_i, ev_b = cuda.Event(), cuda.Event()
                 self._stage(dt, s, L.PART_BOUNDARY, self.halo)
                 ev_b.record(self.halo)
                 self._stage(dt, s, L.PART_INTERIOR, self.compute)
@@ -138,13 +168,13 @@ class DecomposedModel:
 
     def _build_graph(self, dt: float) -> None:
         """Capture two consecutive steps (one per time-level parity), NCCL calls included, into one CUDA graph."""
-        torch = self.torch
+        cuda = self.cuda
         self.compute.synchronize()
         self.halo.synchronize()
         self._enqueue_steps(dt, 2)                               # warm up NCCL + lazy library state outside capture
         self.compute.synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, stream=self.compute):
+        g = cuda.CUDAGraph()
+        with cuda.graph(g, stream=self.compute):
             self._enqueue_steps(dt, 2)
         self._graph, self._graph_dt, self._graph_parity = g, dt, self._parity
 
@@ -160,25 +190,23 @@ class DecomposedModel:
         stream-launched schedule computes from the same state (`nsteps` even; the state is restored afterwards).
         A captured schedule that also contains NCCL traffic is not something to trust unchecked: on rejection the
         model keeps launching from the host (`use_graph` False, reason in `graph_status`)."""
-        import torch.distributed as dist
         snap = self._snapshot()
         self._enqueue_steps(dt, nsteps)
         self.finish()
         want = self._snapshot()
         self._restore(snap)
         self._build_graph(dt)                                    # advances the state by its two warm-up steps
-        with self.torch.cuda.stream(self.compute):
+        with self.cuda.stream(self.compute):
             for _ in range((nsteps - 2) // 2):
                 self._graph.replay()
         self.finish()
         got = self._snapshot()
         self._restore(snap)
         ok = all(np.array_equal(a, b) for a, b in zip(want, got))
-        flag = self.torch.tensor([1 if ok else 0], dtype=self.torch.int32, device=self.dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.ex.group)
+        flag = self.rt.all_reduce_min(1 if ok else 0)
         self.compute.synchronize()
         self._validated = True
-        if int(flag.item()) == 0:
+        if flag == 0:
             self._graph, self._graph_dt, self.use_graph = None, None, False
             self.graph_status = "rejected: graph replay did not reproduce the stream-launched schedule; launching from the host"
             import gc
@@ -201,7 +229,7 @@ class DecomposedModel:
             pre, replays, nsteps = plan_steps(nsteps, self._parity, self._graph_parity)
             if pre:
                 self._run(dt, pre)
-            with self.torch.cuda.stream(self.compute):
+            with self.cuda.stream(self.compute):
                 for _ in range(replays):
                     self._graph.replay()
         if nsteps:
@@ -225,7 +253,7 @@ class DecomposedModel:
         self._graph = None
         import gc
         gc.collect()
-        self.torch.cuda.synchronize()
+        self.cuda.synchronize()
 
     def owned(self, field: str) -> np.ndarray:
         a = getattr(self.prog, field)
@@ -233,10 +261,7 @@ class DecomposedModel:
         return a[:n]
 
     def reduce(self, which: str) -> float:
-        import torch.distributed as dist
-        v = self.torch.tensor([api.reduce_sum(self.prog, which)], dtype=self.torch.float64, device=self.dev)
-        dist.all_reduce(v)
-        return float(v.item())
+        return self.rt.all_reduce_sum(api.reduce_sum(self.prog, which))
 
 
 def local_state(loc: dict, ssh, u, h):

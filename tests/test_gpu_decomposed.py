@@ -12,7 +12,7 @@ import pytest
 
 import moka_b200 as mb
 import moka_oracle_c as OC
-from conftest import hex_mesh, rel_l2
+from conftest import DevBuf, device_synchronize, hex_mesh, rel_l2
 from moka_b200 import _lib as L
 from moka_b200 import multi_gpu, partition
 
@@ -22,21 +22,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 class _Rank:
     def __init__(self, backend, loc, state, nparts, dtype=np.float64):
-        import torch
         self.loc = loc
         self.mesh = mb.Mesh(loc, backend)
         self.sidx, self.scnt, self.ridx, self.rcnt = partition.flat_halo(loc, nparts)
         self.mesh.halo_setup(self.sidx, self.ridx)
         ssh, u, h = multi_gpu.local_state(loc, *state)
         self.prog = mb.PrognosticVars(ssh.astype(dtype), u.astype(dtype), h.astype(dtype), 2, self.mesh)
-        tdt = torch.float64 if dtype == np.float64 else torch.float32
-        self.send = torch.zeros(max(1, len(self.sidx)), dtype=tdt, device="cuda")
-        self.recv = torch.zeros(max(1, len(self.ridx)), dtype=tdt, device="cuda")
+        self.send = DevBuf(len(self.sidx), dtype)
+        self.recv = DevBuf(len(self.ridx), dtype)
         self.h = self.prog.dev.handle
 
 
 def _run_emulated(backend, m, state, nparts, dt, nsteps, split_parts=True, dtype=np.float64):
-    import torch
     locs = partition.decompose(m, nparts)
     ranks = [_Rank(backend, loc, state, nparts, dtype) for loc in locs]
     lib = L.lib()
@@ -56,9 +53,9 @@ def _run_emulated(backend, m, state, nparts, dt, nsteps, split_parts=True, dtype
                 for q, cr in enumerate(r.rcnt):
                     if cr:
                         so = sum(ranks[q].scnt[:r.loc["rank"]])
-                        r.recv[ro:ro + cr] = ranks[q].send[so:so + cr]
+                        r.recv.copy_from(ro, ranks[q].send, so, cr)
                     ro += cr
-            torch.cuda.synchronize()
+            device_synchronize()
             for r in ranks:
                 L.check(lib.mokab_halo_unpack(r.h, s, C.c_void_p(r.recv.data_ptr()), None))
         for r in ranks:

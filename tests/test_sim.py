@@ -1,0 +1,144 @@
+"""CPU suite: the library's own sources on the SIMULATED CUDA runtime (tests/sim).
+
+No GPU in this container, so the `gpu` tests cannot run here; what can run is a HOST build of exactly the sources
+libmoka_b200.so is built from (kernels included, only the <<<>>> launch syntax rewritten) against a simulated runtime
+whose streams execute in adversarial orders.  That checks the host logic and every index computation bit for bit
+against the oracle, and -- what a real device only shows as a rare race -- that every cross-stream dependency the
+code relies on is expressed.  Three parts: (1) the simulator detects what it is meant to detect; (2) the `gpu` tests
+themselves under MOKAB_SIM=1; (3) the domain-decomposed product path with emulated ranks (threads), in-stream
+collectives and graph capture.  The simulated runs happen in subprocesses (a detected deadlock aborts the process)."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SIM = os.path.join(ROOT, "tests", "sim")
+sys.path.insert(0, SIM)
+
+
+@pytest.fixture(scope="module")
+def simcuda():
+    import simcuda as sc
+    sc.runtime()
+    yield sc
+    sc.set_policy("fifo")
+
+
+def test_sim_library_exports_the_whole_abi(simcuda):
+    from moka_b200 import SYMBOLS
+    L = C.CDLL(simcuda._build.LIB)
+    missing = [s for s in SYMBOLS if not hasattr(L, s)]
+    assert not missing, missing
+
+
+def _two_stream_copy(sc, policy, with_event):
+    """Stream A fills a buffer, stream B copies it out: only an event orders them."""
+    rt = sc.runtime()
+    sc.set_policy(policy, 3)
+    a, b = sc.Stream(), sc.Stream()
+    src, dst = sc.DeviceBuffer(1024, np.float64), sc.DeviceBuffer(1024, np.float64)
+    assert rt.cudaMemsetAsync(src.data_ptr(), 0, 8192, a.cuda_stream) == 0
+    if with_event:
+        ev = sc.Event()
+        ev.record(a)
+        b.wait_event(ev)
+    assert rt.cudaMemcpyAsync(dst.data_ptr(), src.data_ptr(), 8192, 3, b.cuda_stream) == 0
+    b.synchronize()
+    out = dst.numpy().copy()
+    a.synchronize()
+    return out
+
+
+def test_simulator_exposes_a_missing_stream_dependency(simcuda):
+    """Without the event the copy may run before the fill: the synchronous order (FIFO) hides it -- as hardware mostly
+    does -- the LAZY order shows the poison (fresh allocations are 0xFF = NaN); with the event every order is right."""
+    assert np.all(_two_stream_copy(simcuda, "fifo", False) == 0.0)
+    assert np.all(np.isnan(_two_stream_copy(simcuda, "lazy", False)))
+    for policy in ("fifo", "lazy", "others_first", "random"):
+        assert np.all(_two_stream_copy(simcuda, policy, True) == 0.0), policy
+
+
+def test_simulator_exposes_a_write_after_read_hazard(simcuda):
+    """Stream B reads a buffer that stream A overwrites later without waiting for B's read: OTHERS_FIRST runs A ahead."""
+    rt = simcuda.runtime()
+
+    def run(policy, guarded):
+        simcuda.set_policy(policy, 5)
+        a, b = simcuda.Stream(), simcuda.Stream()
+        buf, out = simcuda.DeviceBuffer(64, np.float64), simcuda.DeviceBuffer(64, np.float64)
+        rt.cudaMemsetAsync(buf.data_ptr(), 0, 512, a.cuda_stream)
+        ev = simcuda.Event()
+        ev.record(a)
+        b.wait_event(ev)
+        rt.cudaMemcpyAsync(out.data_ptr(), buf.data_ptr(), 512, 3, b.cuda_stream)       # B reads the zeros
+        if guarded:
+            done = simcuda.Event()
+            done.record(b)
+            a.wait_event(done)
+        rt.cudaMemsetAsync(buf.data_ptr(), 0xFF, 512, a.cuda_stream)                     # A overwrites them
+        b.synchronize()
+        res = out.numpy().copy()
+        a.synchronize()
+        return res
+
+    assert np.all(run("fifo", False) == 0.0)
+    assert np.all(np.isnan(run("others_first", False)))
+    for policy in ("fifo", "lazy", "others_first", "random"):
+        assert np.all(run(policy, True) == 0.0), policy
+
+
+def test_capture_keeps_only_captured_dependencies_and_rejects_unjoined_forks(simcuda):
+    rt = simcuda.runtime()
+    simcuda.set_policy("lazy")
+    a, b = simcuda.Stream(), simcuda.Stream()
+    x, y = simcuda.DeviceBuffer(16, np.float64), simcuda.DeviceBuffer(16, np.float64)
+    g = simcuda.CUDAGraph()
+    with simcuda.graph(g, stream=a):
+        rt.cudaMemsetAsync(x.data_ptr(), 0, 128, a.cuda_stream)
+        b.wait_stream(a)                                                                 # fork
+        rt.cudaMemcpyAsync(y.data_ptr(), x.data_ptr(), 128, 3, b.cuda_stream)
+        a.wait_stream(b)                                                                 # join
+    assert np.all(np.isnan(y.numpy()))                                                   # capturing executes nothing
+    with simcuda.stream(a):
+        g.replay()
+    a.synchronize()
+    assert np.all(y.numpy() == 0.0)
+    g2 = simcuda.CUDAGraph()
+    with pytest.raises(simcuda.SimCudaError, match="unjoined"):
+        with simcuda.graph(g2, stream=a):
+            b.wait_stream(a)
+            rt.cudaMemsetAsync(x.data_ptr(), 0, 128, b.cuda_stream)                      # forked work never joined back
+    with pytest.raises(simcuda.SimCudaError, match="capturing"):
+        with simcuda.graph(g2, stream=a):
+            a.synchronize()                                                              # illegal during capture
+
+
+def _run(cmd, env=None, timeout=900):
+    e = dict(os.environ, OMP_NUM_THREADS="2")
+    e.update(env or {})
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=e, cwd=ROOT)
+    return out.returncode, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+# the `gpu` tests that finish in seconds on the simulated device (the rest run with `MOKAB_SIM=1 pytest -m gpu` by hand)
+FAST = ("goldens or roundtrip or tendency_entry or first_step_quirk or rk4_unfused or config1_f64 or variable_coriolis or "
+        "fused_f32 or no_renumbering or committed_golden or error_paths or pipelined or derived_edges or "
+        "reference_sequence_bit_for_bit or emulated_ranks or refuses_single or kelvin or user_seed or tape_overflow or "
+        "operator_adjoints or ocn_run_from_yaml")
+
+
+@pytest.mark.parametrize("policy", ["lazy", "random"])
+def test_gpu_tests_pass_on_the_simulated_runtime(policy):
+    rc, tail = _run([sys.executable, "-m", "pytest", "tests", "-x", "-q", "-m", "gpu", "-k", FAST, "-p", "no:cacheprovider"],
+                    env={"MOKAB_SIM": "1", "MOKAB_SIM_POLICY": policy, "MOKAB_SIM_SEED": "11"})
+    assert rc == 0, tail
+    assert " passed" in tail and "failed" not in tail, tail
+
+
+def test_decomposed_model_with_emulated_ranks_is_exact_under_every_interleaving():
+    rc, tail = _run([sys.executable, os.path.join(SIM, "check_decomposed.py"), "--seeds", "1"])
+    assert rc == 0 and "SIM_DECOMPOSED_OK" in tail, tail

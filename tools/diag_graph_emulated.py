@@ -56,7 +56,7 @@ def main():
                         for q, cr in enumerate(r.rcnt):
                             if cr:
                                 so = sum(ranks[q].scnt[:r.loc["rank"]])
-                                r.recv[ro:ro + cr].copy_(ranks[q].send[so:so + cr])
+                                r.recv.t[ro:ro + cr].copy_(ranks[q].send.t[so:so + cr])
                             ro += cr
                     for r in ranks:
                         L.check(lib.mokab_halo_unpack(r.h, s, C.c_void_p(r.recv.data_ptr()), sp))
