@@ -124,16 +124,13 @@ def _run(cmd, env=None, timeout=900):
     return out.returncode, out.stdout[-3000:] + out.stderr[-3000:]
 
 
-# the `gpu` tests that finish in seconds on the simulated device (the rest run with `MOKAB_SIM=1 pytest -m gpu` by hand)
-FAST = ("goldens or roundtrip or tendency_entry or first_step_quirk or rk4_unfused or config1_f64 or variable_coriolis or "
-        "fused_f32 or no_renumbering or committed_golden or error_paths or pipelined or derived_edges or "
-        "reference_sequence_bit_for_bit or emulated_ranks or refuses_single or kelvin or user_seed or tape_overflow or "
-        "operator_adjoints or ocn_run_from_yaml")
+# every `gpu` test except the two multi-million-cell property tests (minutes on one host core)
+SELECT = "not full_size and not large_mesh"
 
 
-@pytest.mark.parametrize("policy", ["lazy", "random"])
+@pytest.mark.parametrize("policy", ["lazy", "others_first", "random"])
 def test_gpu_tests_pass_on_the_simulated_runtime(policy):
-    rc, tail = _run([sys.executable, "-m", "pytest", "tests", "-x", "-q", "-m", "gpu", "-k", FAST, "-p", "no:cacheprovider"],
+    rc, tail = _run([sys.executable, "-m", "pytest", "tests", "-x", "-q", "-m", "gpu", "-k", SELECT, "-p", "no:cacheprovider"],
                     env={"MOKAB_SIM": "1", "MOKAB_SIM_POLICY": policy, "MOKAB_SIM_SEED": "11"})
     assert rc == 0, tail
     assert " passed" in tail and "failed" not in tail, tail
