@@ -224,6 +224,13 @@ int  mokab_adjoint_seed(mokab_state *state, int which);
 /* Reverse sweep over the recorded steps (newest first); stops recording and empties the tape.  d_ssh is folded
  * into d_layerThickness first (ssh = layerThickness - restingThicknessSum, time_integration.jl:205-212). */
 int  mokab_adjoint_rk4(mokab_state *state);
+/* The same for ForwardEuler -- the stepper test_Enzyme_end2end.jl:78-96 actually differentiates -- including its ordering
+ * artefact (the thickness flux of step n uses the layerThicknessEdge left by step n-1, DiagnosticVars.jl:112-116).  While
+ * recording, every mokab_timestep_forward_euler step stores its normalVelocity and the lagged layerThicknessEdge
+ * (2 * max_steps * nEdges elements).  On return MOKAB_D_NORMAL_VELOCITY / MOKAB_D_LAYER_THICKNESS / MOKAB_D_SSH hold
+ * dJ/d(initial normalVelocity, layerThickness, ssh): ssh is an input of its own here (only the first step's pressure
+ * gradient reads the array), exactly as in Enzyme's d_Prog.ssh[end].  A tape holds steps of one stepper only. */
+int  mokab_adjoint_forward_euler(mokab_state *state);
 
 /* ---- staged RungeKutta4 for domain-decomposed runs (one process per GPU) --------------------------
  * The same fused stage kernel, launched per stage and per part so the host can overlap the halo

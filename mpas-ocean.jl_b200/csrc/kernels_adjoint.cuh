@@ -153,6 +153,124 @@ k_rk_stage_adj(const AdjArgs<R> A)
     }
 }
 
+// ---- adjoint of the ForwardEuler step (the stepper the reference differentiates, test_Enzyme_end2end.jl:78-96) ------
+// Forward (fused::k_fe_step; u, h, ssh, hE = the step's inputs, hE the LAGGED layerThicknessEdge):
+//   u'[e] = u[e] + dt * (-(g/dc[e]) (ssh[c2] - ssh[c1]) + sum_i w[i,e] u[x_i] f[x_i])
+//   h'[c] = h[c] + dt * invArea[c] * sum_i sign[i,c] dv[e_i] u[e_i] hE[e_i]
+//   ssh'  = h' - H ;  hE'[e] = (h[c1] + h[c2]) / 2
+// Reverse, gather form (lam* = adjoints of the step's outputs, q = invArea * (lamH + lamS) carried from the previous call):
+//   G[e]    = dt * dv[e] * (q[c2] - q[c1])                                  (adjoint of the thickness flux)
+//   outU[e] = lamU[e] + dt * sum_j wT[j,e] lamU[xT_j] + hE[e] * G[e]        (wT: transposed Coriolis stencil, f folded)
+//   outE[e] = u[e] * G[e]
+//   outS[c] = -dt * sum_i sign[i,c] (g/dc[e_i]) lamU[e_i]                   (ssh is a separate input: only step 1 reads the array)
+//   outH[c] = lamH[c] + lamS[c] + sum_i lamE[e_i] / 2
+//   qOut[c] = invArea[c] * (outH[c] + outS[c])
+// The Jacobian depends on the trajectory only through (u, hE): those two edge arrays are what the tape holds per step.
+struct FeAdjArgs {
+    int nE, nC, nCown, S2T, S;
+    const int2 *ce;
+    const int32_t *eoeT, *eoc;
+    const uint8_t *nEoET, *nEoC;
+    const int32_t *blkEdgeStart;
+    const double *gdc, *wT, *dv, *invArea;
+    const double *uN, *hEN;                        // taped inputs of the step being reversed
+    const double *lamU, *lamH, *lamS, *lamE, *qIn;
+    double *outU, *outH, *outS, *outE, *qOut;
+    double dt;
+};
+
+template <int S2TT, int ST>
+__global__ void __launch_bounds__(kThreads, MOKAB_ADJ_MINBLOCKS)
+k_fe_step_adj(const FeAdjArgs A)
+{
+    const int nE = A.nE, nC = A.nC;
+    const int b = blockIdx.x;
+    const int e0 = A.blkEdgeStart[b], e1 = A.blkEdgeStart[b + 1];
+    for (int e = e0 + threadIdx.x; e < e1; e += kThreads) {
+        const int2 c = ld_stream(A.ce + e);
+        const int n = ld_stream(A.nEoET + e);
+        const bool masked = c.x == c.y;
+        const double lam = A.lamU[e], un = ld_stream(A.uN + e), he = ld_stream(A.hEN + e);
+        double cor = 0.0;
+        if constexpr (S2TT != 0) {
+            int idx[S2TT ? S2TT : 1];
+            double w[S2TT ? S2TT : 1], kk[S2TT ? S2TT : 1];
+#pragma unroll
+            for (int j = 0; j < S2TT; ++j) idx[j] = j < n ? ld_stream(A.eoeT + (size_t)j * nE + e) : e;
+#pragma unroll
+            for (int j = 0; j < S2TT; ++j) w[j] = j < n ? ld_stream(A.wT + (size_t)j * nE + e) : 0.0;
+#pragma unroll
+            for (int j = 0; j < S2TT; ++j) kk[j] = __ldg(A.lamU + idx[j]);
+#pragma unroll
+            for (int j = 0; j < S2TT; ++j) cor += w[j] * kk[j];
+        } else {
+            for (int j = 0; j < n; ++j)
+                cor += ld_stream(A.wT + (size_t)j * nE + e) * __ldg(A.lamU + ld_stream(A.eoeT + (size_t)j * nE + e));
+        }
+        const double q1 = __ldg(A.qIn + c.x), q2 = masked ? 0.0 : __ldg(A.qIn + c.y);
+        const double G = A.dt * (ld_stream(A.dv + e) * (q2 - q1));
+        A.outU[e] = lam + A.dt * cor + he * G;
+        A.outE[e] = un * G;
+    }
+
+    const int cc = b * kThreads + threadIdx.x;
+    if (cc < A.nCown) {
+        const int n = ld_stream(A.nEoC + cc);
+        const double mu = A.lamH[cc] + A.lamS[cc];
+        double sbar = 0.0, avg = 0.0;
+        if constexpr (ST != 0) {
+            int ee[ST ? ST : 1];
+#pragma unroll
+            for (int i = 0; i < ST; ++i) ee[i] = i < n ? ld_stream(A.eoc + (size_t)i * nC + cc) : -1;
+            int2 cs[ST ? ST : 1];
+            double lu[ST ? ST : 1], le[ST ? ST : 1], gg[ST ? ST : 1];
+#pragma unroll
+            for (int i = 0; i < ST; ++i) {
+                const int e = ee[i] >= 0 ? (ee[i] >> 1) : 0;
+                cs[i] = __ldg(A.ce + e);
+                lu[i] = __ldg(A.lamU + e);
+                le[i] = __ldg(A.lamE + e);
+                gg[i] = __ldg(A.gdc + e);
+            }
+#pragma unroll
+            for (int i = 0; i < ST; ++i) {
+                if (ee[i] < 0) continue;
+                const bool masked = cs[i].x == cs[i].y;
+                const double sgn = (ee[i] & 1) ? 1.0 : -1.0;
+                if (!masked) sbar -= sgn * gg[i] * lu[i];
+                avg += (masked ? 1.0 : 0.5) * le[i];
+            }
+        } else {
+            for (int i = 0; i < n; ++i) {
+                const int ex = ld_stream(A.eoc + (size_t)i * nC + cc);
+                const int e = ex >> 1;
+                const int2 cs = __ldg(A.ce + e);
+                const bool masked = cs.x == cs.y;
+                const double sgn = (ex & 1) ? 1.0 : -1.0;
+                if (!masked) sbar -= sgn * __ldg(A.gdc + e) * __ldg(A.lamU + e);
+                avg += (masked ? 1.0 : 0.5) * __ldg(A.lamE + e);
+            }
+        }
+        const double oS = A.dt * sbar, oH = mu + avg;
+        A.outS[cc] = oS;
+        A.outH[cc] = oH;
+        A.qOut[cc] = ld_stream(A.invArea + cc) * (oH + oS);
+    }
+}
+
+// start of the ForwardEuler reverse sweep: lamS <- the seed on ssh, lamE <- 0 (d_Diag.layerThicknessEdge), q <- invArea (lamH + lamS)
+__global__ void __launch_bounds__(256)
+k_fe_adj_begin(int64_t nC, int64_t nE, const double *__restrict__ invArea, const double *__restrict__ dssh,
+               const double *__restrict__ lamH, double *__restrict__ lamS, double *__restrict__ lamE, double *__restrict__ q)
+{
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < nC) {
+        lamS[i] = dssh[i];
+        q[i] = invArea[i] * (lamH[i] + dssh[i]);
+    }
+    if (i < nE) lamE[i] = 0.0;
+}
+
 // d_h += d_ssh (ssh = h - restingThicknessSum, Update_ssh! time_integration.jl:205-212), d_ssh <- 0
 template <class R>
 __global__ void __launch_bounds__(256) k_fold_dssh(int64_t n, R *__restrict__ dssh, R *__restrict__ dh)
@@ -171,6 +289,14 @@ k_seed_ssh2(int64_t n, const R *__restrict__ h, const R *__restrict__ H, R *__re
 {
     const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (c < n) dssh[c] = R(2) * (h[c] - H[c]);
+}
+
+// the same seed from the ssh ARRAY (ForwardEuler: ssh is a prognostic array of its own, equal to h - H only after a step)
+template <class R>
+__global__ void __launch_bounds__(256) k_seed_ssh2_array(int64_t n, const R *__restrict__ ssh, R *__restrict__ dssh)
+{
+    const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (c < n) dssh[c] = R(2) * ssh[c];
 }
 
 // ---- operator-level transposes (test/enzyme/test_Enzyme_Operators.jl differentiates exactly these two) -------

@@ -41,9 +41,12 @@ struct StateT {
     bool async_ready = false;
     // reverse mode (mokab_tape_* / mokab_adjoint_*): trajectory tape, stage states, adjoint ping-pong buffers
     DevBuf<R> tapeU, tapeH;                 // (tapeCap, nE), (tapeCap, nC): the state before each recorded step
+    DevBuf<R> tapeE;                        // ForwardEuler: (tapeCap, nE) the lagged layerThicknessEdge each step consumed
     std::vector<double> tapeDt;             // dt of every recorded step
     int64_t tapeCap = 0;
     bool taping = false;
+    int tapeKind = 0;                       // 0 = empty, 1 = RungeKutta4 steps, 2 = ForwardEuler steps (never mixed)
+    DevBuf<R> lamS[2], lamE[2], lamQ[2];    // ForwardEuler adjoint: adjoints of ssh / hEdge, invArea * (lamH + lamS)
     DevBuf<R> yU[3], yH[3];                 // y_2, y_3, y_4 of the step being reversed
     DevBuf<R> kbU[2], kbH[2];               // kbar ping-pong (kbH carries invArea * kbar_h)
     DevBuf<R> lamU[2], lamH[2], dSsh;       // lam' / lam, swapped every reversed step; seed on ssh
@@ -427,6 +430,20 @@ static void fe_materialize(mokab_state *st)
     MOKAB_CUDA(cudaMemcpyAsync(t->hEdge.p, t->hE[p].p, m->nE * 8, cudaMemcpyDeviceToDevice, ctx->stream));
 }
 
+// Record what the adjoint of a ForwardEuler step needs of its input: u and the LAGGED layerThicknessEdge (`hE_lagged`).
+static void fe_tape_record(mokab_state *st, double dt, const double *u, const double *hE_lagged)
+{
+    mokab_ctx *ctx = st->ctx; const mokab_mesh *m = st->mesh; StateT<double> *t = st->d;
+    MOKAB_REQUIRE(t->tapeKind != 1, "timestep_forward_euler: the tape already holds RungeKutta4 steps");
+    MOKAB_REQUIRE((int64_t)t->tapeDt.size() < t->tapeCap, "timestep_forward_euler: the tape is full (mokab_tape_begin max_steps)");
+    if (t->tapeE.n < (size_t)t->tapeCap * m->nE) t->tapeE.alloc((size_t)t->tapeCap * m->nE);
+    t->tapeKind = 2;
+    const size_t k = t->tapeDt.size();
+    MOKAB_CUDA(cudaMemcpyAsync(t->tapeU.p + k * m->nE, u, m->nE * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    MOKAB_CUDA(cudaMemcpyAsync(t->tapeE.p + k * m->nE, hE_lagged, m->nE * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    t->tapeDt.push_back(dt);
+}
+
 static void run_fe_fused(mokab_state *st, double dt, int64_t nsteps)
 {
     mokab_ctx *ctx = st->ctx; mokab_mesh *m = const_cast<mokab_mesh *>(st->mesh); StateT<double> *t = st->d;
@@ -443,6 +460,7 @@ static void run_fe_fused(mokab_state *st, double dt, int64_t nsteps)
     A.dt = dt; A.f0 = m->f0;
     for (int64_t i = 0; i < nsteps; ++i) {
         const int p = st->cur, q = 1 - p;
+        if (t->taping) fe_tape_record(st, dt, t->u[p].p, t->hE[p].p);
         A.u = t->u[p].p; A.h = t->h[p].p; A.ssh = t->ssh[p].p; A.hEold = t->hE[p].p;
         A.uNew = t->u[q].p; A.hNew = t->h[q].p; A.sshNew = t->ssh[q].p; A.hEnew = t->hE[q].p;
         if (m->uniformF) fused::k_fe_step<10, 6, true><<<m->fusedBlocks, fused::kThreads, 0, ctx->stream>>>(A);
@@ -654,6 +672,8 @@ static void run_rk4_fused(mokab_state *st, double dt, int64_t nsteps)
     if (t->taping) {  // record the state before every step (plain launches: the tape slot changes per step)
         const mokab_mesh *m = st->mesh;
         MOKAB_REQUIRE((int64_t)t->tapeDt.size() + nsteps <= t->tapeCap, "timestep_rk4: the tape is full (mokab_tape_begin max_steps)");
+        MOKAB_REQUIRE(t->tapeKind != 2, "timestep_rk4: the tape already holds ForwardEuler steps");
+        if (nsteps > 0) t->tapeKind = 1;
         for (int64_t i = 0; i < nsteps; ++i) {
             const size_t k = t->tapeDt.size();
             MOKAB_CUDA(cudaMemcpyAsync(t->tapeU.p + k * m->nE, t->u[st->cur].p, m->nE * sizeof(R), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -843,6 +863,7 @@ static void tape_begin(mokab_state *st, int64_t max_steps)
         t->tapeCap = max_steps;
     }
     t->tapeDt.clear();
+    t->tapeKind = 0;
     t->taping = true;
 }
 
@@ -856,7 +877,10 @@ static void adjoint_seed(mokab_state *st, int which)
     FusedMesh<R> &fm = fused_of<R>(m);
     t->lamU[t->lamCur].zero(ctx->stream);
     t->lamH[t->lamCur].zero(ctx->stream);
-    LAUNCH(ctx, adjoint::k_seed_ssh2<R>, nblk(m->nC), 256, m->nC, (const R *)t->h[st->cur].p, (const R *)fm.H.p, t->dSsh.p);
+    if (t->tapeKind == 2)
+        LAUNCH(ctx, adjoint::k_seed_ssh2_array<R>, nblk(m->nC), 256, m->nC, (const R *)t->ssh[st->cur].p, t->dSsh.p);
+    else
+        LAUNCH(ctx, adjoint::k_seed_ssh2<R>, nblk(m->nC), 256, m->nC, (const R *)t->h[st->cur].p, (const R *)fm.H.p, t->dSsh.p);
 }
 
 template <class R>
@@ -864,11 +888,54 @@ static void adjoint_run(mokab_state *st)
 {
     mokab_ctx *ctx = st->ctx; const mokab_mesh *m = st->mesh;
     StateT<R> *t = typed<R>(st);
+    MOKAB_REQUIRE(t->tapeKind != 2, "adjoint_rk4: the tape holds ForwardEuler steps (use mokab_adjoint_forward_euler)");
     ensure_adjoint<R>(st);
     t->taping = false;
+    t->tapeKind = 0;
     LAUNCH(ctx, adjoint::k_fold_dssh<R>, nblk(m->nC), 256, m->nC, t->dSsh.p, t->lamH[t->lamCur].p);
     for (int64_t k = (int64_t)t->tapeDt.size() - 1; k >= 0; --k) adjoint_step<R>(st, k);
     t->tapeDt.clear();
+}
+
+// Reverse sweep over recorded ForwardEuler steps (adjoint::k_fe_step_adj): one launch per reversed step.
+static void adjoint_run_fe(mokab_state *st)
+{
+    mokab_ctx *ctx = st->ctx; mokab_mesh *m = const_cast<mokab_mesh *>(st->mesh);
+    MOKAB_REQUIRE(st->dtype == MOKAB_F64, "adjoint_forward_euler: ForwardEuler is Float64 only (PrognosticVars.jl:91-93)");
+    StateT<double> *t = st->d;
+    MOKAB_REQUIRE(t->tapeKind != 1, "adjoint_forward_euler: the tape holds RungeKutta4 steps (use mokab_adjoint_rk4)");
+    ensure_adjoint<double>(st);
+    FusedMesh<double> &fm = fused_of<double>(m);
+    for (int i = 0; i < 2; ++i)
+        if (t->lamS[i].n == 0) { t->lamS[i].alloc(m->nC); t->lamE[i].alloc(m->nE); t->lamQ[i].alloc(m->nC); }
+    t->taping = false;
+    int p = t->lamCur;
+    const int64_t nmax = std::max(m->nC, m->nE);
+    LAUNCH(ctx, adjoint::k_fe_adj_begin, nblk(nmax), 256, m->nC, m->nE, (const double *)fm.invArea.p, (const double *)t->dSsh.p,
+           (const double *)t->lamH[p].p, t->lamS[p].p, t->lamE[p].p, t->lamQ[p].p);
+    adjoint::FeAdjArgs A;
+    A.nE = (int)m->nE; A.nC = (int)m->nC; A.nCown = (int)m->nCo; A.S2T = m->S2T; A.S = m->S;
+    A.ce = m->ce.p; A.eoeT = m->eoeT.p; A.eoc = m->eocF.p; A.nEoET = m->nEoET.p; A.nEoC = m->nEoC.p;
+    A.blkEdgeStart = m->blkEdgeStart.p;
+    A.gdc = fm.gdc.p; A.wT = m->woeT.p; A.dv = m->dv.p; A.invArea = fm.invArea.p;
+    const bool hex = m->S2T == 10 && m->S == 6;
+    for (int64_t k = (int64_t)t->tapeDt.size() - 1; k >= 0; --k) {
+        A.dt = t->tapeDt[k];
+        A.uN = t->tapeU.p + (size_t)k * m->nE; A.hEN = t->tapeE.p + (size_t)k * m->nE;
+        A.lamU = t->lamU[p].p; A.lamH = t->lamH[p].p; A.lamS = t->lamS[p].p; A.lamE = t->lamE[p].p; A.qIn = t->lamQ[p].p;
+        A.outU = t->lamU[1 - p].p; A.outH = t->lamH[1 - p].p; A.outS = t->lamS[1 - p].p; A.outE = t->lamE[1 - p].p;
+        A.qOut = t->lamQ[1 - p].p;
+        if (hex) adjoint::k_fe_step_adj<10, 6><<<m->fusedBlocks, adjoint::kThreads, 0, ctx->stream>>>(A);
+        else adjoint::k_fe_step_adj<0, 0><<<m->fusedBlocks, adjoint::kThreads, 0, ctx->stream>>>(A);
+        MOKAB_CUDA(cudaGetLastError());
+        ctx->launches++;
+        p = 1 - p;
+    }
+    t->lamCur = p;
+    // d_Prog.ssh[end]: the gradient with respect to the initial ssh array (read by the first step's pressure gradient only)
+    MOKAB_CUDA(cudaMemcpyAsync(t->dSsh.p, t->lamS[p].p, m->nC * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    t->tapeDt.clear();
+    t->tapeKind = 0;
 }
 
 // stand-alone operators on host arrays -------------------------------------------------------------------
@@ -1277,7 +1344,10 @@ int mokab_timestep_forward_euler(mokab_state *state, double dt, int64_t nsteps)
         if (fe_fusable(state)) {
             run_fe_fused(state, dt, nsteps);
         } else {
-            for (int64_t i = 0; i < nsteps; ++i) step_forward_euler(state, dt);
+            for (int64_t i = 0; i < nsteps; ++i) {
+                if (state->d->taping) fe_tape_record(state, dt, state->d->u[state->cur].p, state->d->hEdge.p);
+                step_forward_euler(state, dt);
+            }
         }
     });
 }
@@ -1355,6 +1425,15 @@ int mokab_adjoint_rk4(mokab_state *state)
         MOKAB_REQUIRE(state, "adjoint_rk4: state is NULL");
         state->ctx->bind();
         if (state->dtype == MOKAB_F64) adjoint_run<double>(state); else adjoint_run<float>(state);
+    });
+}
+
+int mokab_adjoint_forward_euler(mokab_state *state)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(state, "adjoint_forward_euler: state is NULL");
+        state->ctx->bind();
+        adjoint_run_fe(state);
     });
 }
 

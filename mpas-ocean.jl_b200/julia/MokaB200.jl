@@ -142,16 +142,24 @@ function sum_ssh2(s::B200State)
 end
 
 # ---- reverse mode: stands in for `autodiff(Enzyme.Reverse, ocn_run_loop, ..., Duplicated(Prog, d_Prog), ...)` --------------
-# (test/enzyme/test_Enzyme_end2end.jl:78-96).  Runs `nsteps` RungeKutta4 steps recording the trajectory, seeds
+# (test/enzyme/test_Enzyme_end2end.jl:78-96).  Runs `nsteps` steps of `Stepper` recording the trajectory, seeds
 # d_ssh = 2 ssh (J = sum ssh^2, run_loop.jl:47-51) and sweeps back; returns J and fills the shadow arrays.
+# ForwardEuler is the stepper the reference differentiates (its lagged thickness flux included); `d_ssh`, when given,
+# receives d_Prog.ssh[end] (ssh is an input of its own for ForwardEuler; zero for RungeKutta4, where it is folded into h).
 function autodiff_reverse_run_loop!(d_normalVelocity::Array{Float64}, d_layerThickness::Array{Float64},
-                                    dt::Float64, s::B200State, nsteps::Integer)
+                                    dt::Float64, s::B200State, nsteps::Integer;
+                                    Stepper = RungeKutta4, d_ssh::Union{Nothing, Array{Float64}} = nothing)
     check(ccall((:mokab_tape_begin, libmoka), Cint, (Ptr{Cvoid}, Int64), s.handle, nsteps))
-    ocn_timestep(dt, s, RungeKutta4; nsteps = nsteps)
+    ocn_timestep(dt, s, Stepper; nsteps = nsteps)
     J = sum_ssh2(s)
     check(ccall((:mokab_adjoint_seed, libmoka), Cint, (Ptr{Cvoid}, Cint), s.handle, SUM_SSH2))
-    check(ccall((:mokab_adjoint_rk4, libmoka), Cint, (Ptr{Cvoid},), s.handle))
+    if Stepper === ForwardEuler
+        check(ccall((:mokab_adjoint_forward_euler, libmoka), Cint, (Ptr{Cvoid},), s.handle))
+    else
+        check(ccall((:mokab_adjoint_rk4, libmoka), Cint, (Ptr{Cvoid},), s.handle))
+    end
     get!(d_normalVelocity, s, D_NORMAL_VELOCITY); get!(d_layerThickness, s, D_LAYER_THICKNESS)
+    d_ssh === nothing || get!(d_ssh, s, D_SSH)
     J
 end
 # adjoints of the two operators test/enzyme/test_Enzyme_Operators.jl differentiates

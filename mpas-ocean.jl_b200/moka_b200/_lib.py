@@ -56,7 +56,7 @@ SYMBOLS = [
     "mokab_gradient_on_edge", "mokab_divergence_on_cell", "mokab_curl_on_vertex", "mokab_interpolate_cell2edge",
     "mokab_gradient_on_edge_vjp", "mokab_divergence_on_cell_vjp",
     "mokab_timestep_forward_euler", "mokab_timestep_forward_euler_unfused", "mokab_timestep_rk4", "mokab_reduce",
-    "mokab_tape_begin", "mokab_tape_length", "mokab_adjoint_seed", "mokab_adjoint_rk4",
+    "mokab_tape_begin", "mokab_tape_length", "mokab_adjoint_seed", "mokab_adjoint_rk4", "mokab_adjoint_forward_euler",
     "mokab_halo_setup", "mokab_halo_pack", "mokab_halo_unpack", "mokab_rk4_stage", "mokab_rk4_finish_step",
     "mokab_refresh_ssh", "mokab_mesh_block_counts", "mokab_mesh_derived_blocks",
 ]
@@ -87,7 +87,7 @@ def bind(L):
         "mokab_timestep_forward_euler": [vp, dbl, i64], "mokab_timestep_forward_euler_unfused": [vp, dbl, i64], "mokab_timestep_rk4": [vp, dbl, i64, C.c_int],
         "mokab_reduce": [vp, C.c_int, C.POINTER(dbl)],
         "mokab_tape_begin": [vp, i64], "mokab_tape_length": [vp, C.POINTER(i64)],
-        "mokab_adjoint_seed": [vp, C.c_int], "mokab_adjoint_rk4": [vp],
+        "mokab_adjoint_seed": [vp, C.c_int], "mokab_adjoint_rk4": [vp], "mokab_adjoint_forward_euler": [vp],
         "mokab_halo_setup": [vp, i64, _I32P, i64, _I32P], "mokab_halo_pack": [vp, C.c_int, vp, vp],
         "mokab_halo_unpack": [vp, C.c_int, vp, vp], "mokab_rk4_stage": [vp, dbl, C.c_int, C.c_int, vp],
         "mokab_rk4_finish_step": [vp], "mokab_refresh_ssh": [vp, vp],

@@ -395,14 +395,25 @@ def ocn_init_shadows(Prog: PrognosticVars, Diag=None, Tend=None) -> ShadowProgno
 def autodiff_reverse_run_loop(timestep: float, Prog: PrognosticVars, d_Prog: ShadowPrognosticVars, Diag, Tend, Setup,
                               stepper, nsteps: int, seed: str | None = "ssh2") -> float:
     """`autodiff(Enzyme.Reverse, ocn_run_loop, Duplicated(sumCPU, ..), .., Duplicated(Prog, d_Prog), ..)`
-    (test_Enzyme_end2end.jl:78-96): runs `nsteps` RungeKutta4 steps recording the trajectory, then the reverse
+    (test_Enzyme_end2end.jl:78-96): runs `nsteps` steps of `stepper` recording the trajectory, then the reverse
     sweep.  With `seed="ssh2"` the objective is the run loop's sum of squared SSH (run_loop.jl:24-44) and its
     value is returned; with `seed=None` whatever the caller stored in `d_Prog` is the adjoint of the final state.
-    On return d_Prog holds dJ/d(initial normalVelocity, layerThickness)."""
-    if stepper is not RungeKutta4:
-        raise MokaError("autodiff_reverse_run_loop: the hand-written adjoint covers the fused RungeKutta4 stepper")
+    On return d_Prog holds dJ/d(initial normalVelocity, layerThickness) -- and, for ForwardEuler (the stepper the
+    reference differentiates), d_Prog.ssh = dJ/d(initial ssh), an input of its own there."""
+    if stepper not in (RungeKutta4, ForwardEuler):
+        raise MokaError("autodiff_reverse_run_loop: unknown stepper")
     h = Prog.dev.handle
     L.check(L.lib().mokab_tape_begin(h, int(nsteps)))
+    if stepper is ForwardEuler:
+        L.check(L.lib().mokab_timestep_forward_euler(h, float(timestep), int(nsteps)))
+        J = float("nan")
+        if seed is not None:
+            if seed != "ssh2":
+                raise MokaError("autodiff_reverse_run_loop: unknown seed")
+            J = float(np.sum(np.asarray(Prog.ssh, np.float64) ** 2)) if nsteps == 0 else reduce_sum(Prog, "ssh2")
+            L.check(L.lib().mokab_adjoint_seed(h, L.SUM_SSH2))
+        L.check(L.lib().mokab_adjoint_forward_euler(h))
+        return J
     L.check(L.lib().mokab_timestep_rk4(h, float(timestep), int(nsteps), L.RK4_FUSED))
     J = float("nan")
     if seed is not None:

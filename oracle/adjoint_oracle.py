@@ -138,3 +138,91 @@ def finite_difference(m, u0, h0, dt, nsteps, kind, k, eps=1e-8):
     jp = objective_sum_ssh2(m, run_forward(m, up, hp, dt, nsteps)[-1][1])
     jm = objective_sum_ssh2(m, run_forward(m, um, hm, dt, nsteps)[-1][1])
     return (jp - jm) / dist
+
+
+# ---- ForwardEuler: the stepper the reference actually differentiates (test_Enzyme_end2end.jl:78-96) ---------------
+# One step of moka_oracle.timestep_forward_euler maps (u, h, ssh, hE) -> (u', h', ssh', hE'), hE = Diag.layerThicknessEdge:
+#   flux = u * hE                       (the LAGGED hEdge: diagnostic_compute! forms the flux before it refreshes hEdge,
+#                                        DiagnosticVars.jl:112-116; zeros on the first step)
+#   hE'  = interpolateCell2Edge(h)      (Operators.jl:201-222)
+#   u'   = u + dt * (-(g/dc) (ssh[c2] - ssh[c1]) + sum_i w_i u[eoe_i] f[eoe_i])
+#   h'   = h + dt * (1/area) sum_i flux[e_i] dv[e_i] sign_i
+#   ssh' = h' - restingThicknessSum
+# so ssh is an independent input of the FIRST step only, and Enzyme's d_Prog.ssh[end] is the gradient with respect to it.
+def fe_step(m, u, h, ssh, hE, dt):
+    flux = u * hE
+    tu = O.compute_normal_velocity_tendency(m, ssh, u)
+    th = O.compute_layer_thickness_tendency(m, flux)
+    h_new = h + dt * th
+    return u + dt * tu, h_new, h_new - O.resting_thickness_sum(m), O.interpolate_cell2edge(m, h)
+
+
+def fe_step_vjp(m, u, hE, dt, lam_u, lam_h, lam_s, lam_e):
+    """Adjoint of one ForwardEuler step in SCATTER form, statement by statement in reverse order.  (u, hE) are the step's
+    inputs the Jacobian depends on; returns the adjoints of (u, h, ssh, hE)."""
+    nC, nE = m["nCells"], m["nEdges"]
+    c1 = m["cellsOnEdge"][:, 0] - 1
+    c2 = m["cellsOnEdge"][:, 1] - 1
+    out_u, out_h, out_s, out_e = lam_u.copy(), np.zeros(nC), np.zeros(nC), np.zeros(nE)
+    # hE' = 0.5 * (h[c1] + h[c2])
+    np.add.at(out_h, c1, 0.5 * lam_e)
+    np.add.at(out_h, c2, 0.5 * lam_e)
+    # ssh' = h' - H ; h' = h + dt * th
+    mu = lam_h + lam_s
+    out_h += mu
+    # th[c] = invArea[c] * sum_i flux[e_i] * dv[e_i] * sign[i, c]
+    inv_area = 1.0 / m["areaCell"]
+    eoc, sgn, n = m["edgesOnCell"], m["edgeSignOnCell"], m["nEdgesOnCell"]
+    flux_bar = np.zeros(nE)
+    for i in range(m["maxEdges"]):
+        act = i < n
+        e = eoc[act, i] - 1
+        np.add.at(flux_bar, e, dt * m["dvEdge"][e] * sgn[act, i] * inv_area[act] * mu[act])
+    # flux = u * hE
+    out_u += flux_bar * hE
+    out_e += flux_bar * u
+    # tu: Coriolis (horizontal_advection_and_coriolis.jl:70-72)
+    eoe, w, ne, f = m["edgesOnEdge"], m["weightsOnEdge"], m["nEdgesOnEdge"], m["fEdge"]
+    for i in range(eoe.shape[1]):
+        act = (i < ne) & (eoe[:, i] != 0)
+        j = eoe[act, i] - 1
+        np.add.at(out_u, j, dt * w[act, i] * f[j] * lam_u[act])
+    # tu: pressure gradient (pressure_gradient.jl:63) on the ssh ARRAY
+    gk = dt * O.GRAVITY * (1.0 / m["dcEdge"]) * lam_u
+    np.add.at(out_s, c2, -gk)
+    np.add.at(out_s, c1, gk)
+    return out_u, out_h, out_s, out_e
+
+
+def run_forward_fe(m, ssh0, u0, h0, dt, nsteps, hE0=None):
+    hE = np.zeros(m["nEdges"]) if hE0 is None else hE0                    # DiagnosticVars.jl:90-93
+    traj = [(u0, h0, ssh0, hE)]
+    for _ in range(nsteps):
+        traj.append(fe_step(m, *traj[-1], dt))
+    return traj
+
+
+def gradient_sum_ssh2_fe(m, ssh0, u0, h0, dt, nsteps, hE0=None):
+    """(J, dJ/du0, dJ/dh0, dJ/dssh0, dJ/dhE0) for J = sum ssh_N^2 after `nsteps` ForwardEuler steps: what
+    `autodiff(Reverse, ocn_run_loop, ..., Duplicated(Prog, d_Prog), Duplicated(Diag, d_Diag), ...)` leaves in
+    d_Prog.{normalVelocity, layerThickness, ssh}[end] and d_Diag.layerThicknessEdge (test_Enzyme_end2end.jl:78-96)."""
+    traj = run_forward_fe(m, ssh0, u0, h0, dt, nsteps, hE0)
+    sshN = traj[-1][2]
+    lam = (np.zeros(m["nEdges"]), np.zeros(m["nCells"]), 2.0 * sshN, np.zeros(m["nEdges"]))
+    for n in range(nsteps - 1, -1, -1):
+        lam = fe_step_vjp(m, traj[n][0], traj[n][3], dt, *lam)
+    return (float(np.sum(sshN * sshN)),) + tuple(lam)
+
+
+def finite_difference_fe(m, ssh0, u0, h0, dt, nsteps, kind, k, eps=1e-8):
+    """Central difference of J in one component of layerThickness ("h"), normalVelocity ("u") or ssh ("s"), with the
+    relative step of test_Enzyme_end2end.jl:112-170."""
+    x = {"h": h0, "u": u0, "s": ssh0}[kind]
+    step = abs(x[k]) * eps if x[k] != 0.0 else eps
+    out = []
+    for sgn in (1.0, -1.0):
+        a = {"h": h0.copy(), "u": u0.copy(), "s": ssh0.copy()}
+        a[kind][k] += sgn * step
+        sshN = run_forward_fe(m, a["s"], a["u"], a["h"], dt, nsteps)[-1][2]
+        out.append((float(np.sum(sshN * sshN)), a[kind][k]))
+    return (out[0][0] - out[1][0]) / (out[0][1] - out[1][1])

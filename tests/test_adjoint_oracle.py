@@ -129,3 +129,58 @@ def test_committed_adjoint_fixture_is_reproduced_by_the_oracle():
     assert J == float(g["J"]) and np.array_equal(gu, g["d_normalVelocity"]) and np.array_equal(gh, g["d_layerThickness"])
     k = meta["fd_index"]
     assert abs(gh[k] - float(g["fd_layerThickness"])) < 1e-4 and abs(gu[k] - float(g["fd_normalVelocity"])) < 1e-2
+
+
+# ---- ForwardEuler adjoint oracle (the stepper test_Enzyme_end2end.jl differentiates) --------------------------------
+def _fe_case(nx=16, kelvin=False):
+    if kelvin:
+        m = OC.apply_boundary_mask(mb.channel_hex(nx, nx, 1.0e7 / nx))
+        OC.sign_index_fields(m)
+        ssh, u, h = mb.kelvinWave(m).initial_state()
+    else:
+        m = hex_mesh(nx)
+        ssh, u, h = mb.inertialGravityWave(m).initial_state()
+    return m, ssh, u, h, mb.cfl_dt(m["dc"])
+
+
+def test_fe_oracle_step_is_the_reference_order_forward_euler():
+    m, ssh, u, h, dt = _fe_case(12)
+    om = OC.OracleModel(m, ssh, u, h)
+    om.run_loop(dt, 4, "ForwardEuler")
+    u4, h4, s4, _ = A.run_forward_fe(m, ssh, u, h, dt, 4)[-1]
+    assert np.array_equal(u4, om.normalVelocity[1]) and np.array_equal(h4, om.layerThickness[1]) and np.array_equal(s4, om.ssh[1])
+
+
+def test_fe_step_vjp_dot_product_identity():
+    for kelvin in (False, True):
+        m, ssh, u, h, dt = _fe_case(12, kelvin)
+        rng = np.random.default_rng(2)
+        hE = O.interpolate_cell2edge(m, h)
+        d = [1e-3 * rng.standard_normal(m["nEdges"]), rng.standard_normal(m["nCells"]), rng.standard_normal(m["nCells"]),
+             rng.standard_normal(m["nEdges"])]
+        lam = [rng.standard_normal(m["nEdges"]), rng.standard_normal(m["nCells"]), rng.standard_normal(m["nCells"]),
+               rng.standard_normal(m["nEdges"])]
+        e = 1e-4
+        p = A.fe_step(m, u + e * d[0], h + e * d[1], ssh + e * d[2], hE + e * d[3], dt)
+        q = A.fe_step(m, u - e * d[0], h - e * d[1], ssh - e * d[2], hE - e * d[3], dt)
+        lhs = sum(((a - b) / (2 * e)) @ l for a, b, l in zip(p, q, lam))
+        bar = A.fe_step_vjp(m, u, hE, dt, *lam)
+        rhs = sum(x @ y for x, y in zip(d, bar))
+        assert abs(lhs - rhs) <= 1e-7 * max(abs(lhs), abs(rhs))
+
+
+def test_fe_gradient_matches_finite_differences_like_the_reference_test():
+    m, ssh, u, h, dt = _fe_case(16)
+    J, gu, gh, gs, ge = A.gradient_sum_ssh2_fe(m, ssh, u, h, dt, 6)
+    assert J > 0 and np.all(np.isfinite(gu)) and np.all(np.isfinite(gh))
+    for k in (4, 77, 200):                                               # the reference checks index 5 (1-based)
+        fd_h = A.finite_difference_fe(m, ssh, u, h, dt, 6, "h", k, eps=1e-7)
+        fd_u = A.finite_difference_fe(m, ssh, u, h, dt, 6, "u", k, eps=1e-4)
+        fd_s = A.finite_difference_fe(m, ssh, u, h, dt, 6, "s", k, eps=1e-4)
+        assert abs(gh[k] - fd_h) < 1e-4                                  # atol of test_Enzyme_end2end.jl:176
+        assert abs(gu[k] - fd_u) < 1e-2                                  # atol of :177
+        assert abs(gh[k] - fd_h) < 1e-5 * abs(gh[k]) + 1e-7 and abs(gu[k] - fd_u) < 1e-5 * abs(gu[k]) + 1e-5
+        assert abs(gs[k] - fd_s) < 1e-5 * abs(gs[k]) + 1e-7
+    # the first step's thickness flux is zero (hEdge starts as zeros), so nothing depends on u through it there; and ssh
+    # enters only through the first step's pressure gradient
+    assert np.linalg.norm(gs) > 0 and np.linalg.norm(ge) > 0

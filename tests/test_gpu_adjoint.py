@@ -97,12 +97,28 @@ def test_tape_overflow_and_stepper_errors(backend):
     mesh = mb.Mesh(m, backend)
     prog = mb.PrognosticVars(ssh, u, h, 2, mesh)
     d_prog = mb.ocn_init_shadows(prog)
-    with pytest.raises(mb.MokaError):
-        mb.autodiff_reverse_run_loop(dt, prog, d_prog, None, None, None, mb.ForwardEuler, 2)
+    with pytest.raises(mb.MokaError, match="unknown stepper"):
+        mb.autodiff_reverse_run_loop(dt, prog, d_prog, None, None, None, object, 2)
     from moka_b200 import _lib as L
     L.check(L.lib().mokab_tape_begin(prog.dev.handle, 2))
     with pytest.raises(mb.MokaError, match="tape is full"):
         mb.ocn_timestep(dt, prog, None, None, None, mb.RungeKutta4, nsteps=3)
+    # a tape holds steps of one stepper only, and each reverse sweep refuses the other's tape
+    L.check(L.lib().mokab_tape_begin(prog.dev.handle, 4))
+    mb.ocn_timestep(dt, prog, None, None, None, mb.RungeKutta4, nsteps=1)
+    with pytest.raises(mb.MokaError, match="already holds RungeKutta4"):
+        mb.ocn_timestep(dt, prog, None, None, None, mb.ForwardEuler)
+    with pytest.raises(mb.MokaError, match="holds RungeKutta4"):
+        L.check(L.lib().mokab_adjoint_forward_euler(prog.dev.handle))
+    L.check(L.lib().mokab_tape_begin(prog.dev.handle, 4))
+    mb.ocn_timestep(dt, prog, None, None, None, mb.ForwardEuler)
+    with pytest.raises(mb.MokaError, match="already holds ForwardEuler"):
+        mb.ocn_timestep(dt, prog, None, None, None, mb.RungeKutta4, nsteps=1)
+    with pytest.raises(mb.MokaError, match="holds ForwardEuler"):
+        L.check(L.lib().mokab_adjoint_rk4(prog.dev.handle))
+    with pytest.raises(mb.MokaError, match="tape is full"):
+        for _ in range(4):
+            mb.ocn_timestep(dt, prog, None, None, None, mb.ForwardEuler)
 
 
 def test_operator_adjoints_like_test_Enzyme_Operators(backend):
@@ -156,3 +172,65 @@ def test_committed_adjoint_fixture(backend):
     k = meta["fd_index"]
     assert abs(d_prog.layerThickness[k] - float(g["fd_layerThickness"])) < 1e-4          # test_Enzyme_end2end.jl:176
     assert abs(d_prog.normalVelocity[k] - float(g["fd_normalVelocity"])) < 1e-2          # :177
+
+
+# ---- ForwardEuler: the stepper the reference differentiates (test_Enzyme_end2end.jl:78-96) ---------------------------
+@pytest.mark.parametrize("kelvin,renumber,nx", [(False, True, 16), (False, False, 12), (True, True, 16)])
+def test_forward_euler_gradient_matches_adjoint_oracle(backend, kelvin, renumber, nx):
+    m, mo, ssh, u, h, dt = _case(nx, kelvin)
+    mesh = mb.Mesh(m, backend, renumber=renumber)
+    prog = mb.PrognosticVars(ssh, u, h, 2, mesh)
+    d_prog = mb.ocn_init_shadows(prog)
+    J = mb.autodiff_reverse_run_loop(dt, prog, d_prog, None, None, None, mb.ForwardEuler, 7)
+    Jo, gu, gh, gs, _ = A.gradient_sum_ssh2_fe(mo, ssh, u, h, dt, 7)
+    assert abs(J - Jo) <= 1e-12 * abs(Jo)
+    assert rel_l2(d_prog.normalVelocity, gu) <= TOL64
+    assert rel_l2(d_prog.layerThickness, gh) <= TOL64
+    assert rel_l2(d_prog.ssh, gs) <= TOL64
+    # the forward run under the tape is the ordinary ForwardEuler run, bit for bit
+    om = OC.OracleModel(mo, ssh, u, h)
+    om.run_loop(dt, 7, "ForwardEuler")
+    assert np.array_equal(prog.normalVelocity, om.normalVelocity[1]) and np.array_equal(prog.ssh, om.ssh[1])
+
+
+def test_forward_euler_gradient_like_test_Enzyme_end2end(backend):
+    """The reference's own acceptance test (test_Enzyme_end2end.jl:112-180): AD value at one cell / edge against central
+    finite differences of the forward run, atol 1e-4 (layerThickness) and 1e-2 (normalVelocity) -- its CUDA result is NaN."""
+    m, mo, ssh, u, h, dt = _case(16, False)
+    mesh = mb.Mesh(m, backend)
+    nsteps, k = 6, 4                                                     # the reference checks index 5 (1-based)
+
+    def J_of(u0, h0):
+        p = mb.PrognosticVars(ssh, u0, h0, 2, mesh)
+        mb.ocn_run_loop(dt, p, None, None, None, mb.ForwardEuler, nsteps)
+        return mb.reduce_sum(p, "ssh2")
+
+    prog = mb.PrognosticVars(ssh, u, h, 2, mesh)
+    d_prog = mb.ocn_init_shadows(prog)
+    mb.autodiff_reverse_run_loop(dt, prog, d_prog, None, None, None, mb.ForwardEuler, nsteps)
+    gh, gu = d_prog.layerThickness, d_prog.normalVelocity
+    assert np.all(np.isfinite(gh)) and np.all(np.isfinite(gu))
+    hp, hm = h.copy(), h.copy()
+    hp[k] += abs(h[k]) * 1e-7
+    hm[k] -= abs(h[k]) * 1e-7
+    fd_h = (J_of(u, hp) - J_of(u, hm)) / (hp[k] - hm[k])
+    up, um = u.copy(), u.copy()
+    up[k] += abs(u[k]) * 1e-4
+    um[k] -= abs(u[k]) * 1e-4
+    fd_u = (J_of(up, h) - J_of(um, h)) / (up[k] - um[k])
+    assert abs(gh[k] - fd_h) < 1e-4 and abs(gu[k] - fd_u) < 1e-2
+    assert abs(gh[k] - fd_h) < 1e-5 * abs(gh[k]) + 1e-7
+
+
+def test_forward_euler_adjoint_on_runtime_width_rows(backend):
+    """Padded rows with MOKAB_MESH_KEEP_WIDTHS: the unfused ForwardEuler steps record the tape and the run-time-width
+    adjoint kernel reverses them."""
+    from test_gpu_parity import _padded
+    m, mo, ssh, u, h, dt = _case(12, False)
+    mesh = mb.Mesh(_padded(m), backend, keep_widths=True)
+    prog = mb.PrognosticVars(ssh, u, h, 2, mesh)
+    d_prog = mb.ocn_init_shadows(prog)
+    mb.autodiff_reverse_run_loop(dt, prog, d_prog, None, None, None, mb.ForwardEuler, 5)
+    _, gu, gh, gs, _ = A.gradient_sum_ssh2_fe(mo, ssh, u, h, dt, 5)
+    assert rel_l2(d_prog.normalVelocity, gu) <= TOL64 and rel_l2(d_prog.layerThickness, gh) <= TOL64
+    assert rel_l2(d_prog.ssh, gs) <= TOL64
