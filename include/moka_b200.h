@@ -252,6 +252,29 @@ int  mokab_rk4_stage(mokab_state *state, double dt, int stage, int part, void *c
 int  mokab_rk4_finish_step(mokab_state *state);
 /* ssh = layerThickness - restingThicknessSum on both time levels (Update_ssh!, time_integration.jl:205-212) */
 int  mokab_refresh_ssh(mokab_state *state, void *cuda_stream);
+/* ---- halo exchange by direct stores into the peers' memory (csrc/kernels_p2p.cuh) ---------------------------------------
+ * The alternative to pack -> all-to-all -> unpack named by BASELINE.json's north_star ("or direct P2P stores"): per RK stage
+ * the sender writes its halo values straight into the receivers' state arrays over NVLink and bumps a per-sender arrival
+ * counter there (mokab_halo_push); the receiver's next boundary launch is preceded by a one-warp kernel that waits for the
+ * counters of the ranks it receives from (mokab_halo_wait).  No message buffers, no collective, graph-capturable.  Set-up,
+ * once per state, after mokab_halo_setup:
+ *   1. every rank:  mokab_halo_recv_device_indices(mesh, idx)  -- where its halo entities live in ITS arrays, message order
+ *      (c >= 0: cell c; d < 0: edge -d - 1), and hands each sender the segment that sender fills;
+ *   2. every rank:  mokab_p2p_export(state, rank, blob)  (mokab_p2p_blob_size bytes: addresses + CUDA IPC handles of the
+ *      state arrays and the arrival counters), all blobs gathered on every rank;
+ *   3. every rank:  mokab_p2p_setup(state, rank, nranks, blobs, receivers..., push_counts, dst_idx, senders...) with, per
+ *      receiver in message order, the indices obtained in step 1.
+ * Ranks of other processes are mapped with cudaIpcOpenMemHandle, ranks emulated inside one process use the addresses. */
+int  mokab_halo_recv_device_indices(const mokab_mesh *mesh, int32_t *out);
+int  mokab_p2p_blob_size(int64_t *out);
+int  mokab_p2p_export(mokab_state *state, int rank, void *blob);
+int  mokab_p2p_setup(mokab_state *state, int rank, int nranks, const void *blobs, int n_receivers, const int32_t *receiver_ranks,
+                     const int64_t *push_counts, const int32_t *dst_idx, int n_senders, const int32_t *sender_ranks);
+/* stage as in mokab_halo_pack */
+int  mokab_halo_push(mokab_state *state, int stage, void *cuda_stream);
+int  mokab_halo_wait(mokab_state *state, void *cuda_stream);
+/* 1 if a wait ever timed out (~2 s: a peer died or the ranks' schedules diverged); the GPU is never left spinning */
+int  mokab_p2p_error(mokab_state *state, int *out);
 /* number of interior / boundary blocks of the fused kernel (diagnostic) */
 int  mokab_mesh_block_counts(const mokab_mesh *mesh, int64_t *interior, int64_t *boundary);
 /* number of fused-kernel blocks, and how many of them rebuild edgesOnEdge from edgesOnCell (diagnostic) */

@@ -53,15 +53,24 @@ template <class T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
+    bool owned = true;   // false: a window into somebody else's allocation (view)
     DevBuf() = default;
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() { release(); }
     void release()
     {
-        if (p) cudaFree(p);
+        if (p && owned) cudaFree(p);
         p = nullptr;
         n = 0;
+        owned = true;
+    }
+    void view(T *ptr, size_t count)
+    {
+        release();
+        p = ptr;
+        n = count;
+        owned = false;
     }
     void alloc(size_t count)
     {

@@ -3,7 +3,10 @@
 #include "kernels_fused.cuh"
 #include "kernels_adjoint.cuh"
 #include "kernels_ref.cuh"
+#include "kernels_p2p.cuh"
 #include "mesh.cuh"
+
+#include <unistd.h>
 
 namespace mokab {
 thread_local std::string g_last_error;
@@ -16,12 +19,18 @@ thread_local std::string g_last_error;
     } while (0)
 
 static inline int nblk(int64_t n, int t = 256) { return (int)((n + t - 1) / t); }
+constexpr int kP2PCounters = 1024;   // arrival counters of the direct-store halo exchange, indexed by sender rank
 
 // ---- typed state ----------------------------------------------------------------------------------------
 template <class R>
 struct StateT {
-    DevBuf<R> u[2], h[2], ssh[2];          // two time levels; `cur` holds Prog.*[end]
-    DevBuf<R> uP[2], hP[2];                // RK provisional ping-pong
+    // Everything a peer GPU may write -- the halo slots of the two time levels and of the provisional buffers, and the
+    // arrival counters of the direct-store halo exchange -- lives in ONE allocation, so one CUDA IPC handle maps it
+    // (several small cudaMalloc blocks can share a physical chunk, which IPC cannot map twice).
+    DevBuf<unsigned char> slab;
+    size_t slabOff[9] = {};                // byte offsets: u0 u1 uP0 uP1 h0 h1 hP0 hP1 counters
+    DevBuf<R> u[2], h[2], ssh[2];          // two time levels; `cur` holds Prog.*[end]  (u, h: views into the slab)
+    DevBuf<R> uP[2], hP[2];                // RK provisional ping-pong (views into the slab)
     DevBuf<R> hEdge, flux, divC, relVort, tendU, tendH, sshProv;
     DevBuf<R> hE[2];                       // fused ForwardEuler: layerThicknessEdge ping-pong, indexed like the time levels
     DevBuf<R> staging;
@@ -90,8 +99,25 @@ struct mokab_state {
     bool fe_lazy = false;
     mokab::StateT<double> *d = nullptr;
     mokab::StateT<float> *f = nullptr;
+    // halo exchange by direct peer stores (kernels_p2p.cuh); set up by mokab_p2p_setup
+    struct P2P {
+        bool exported = false, ready = false;
+        int rank = 0, nranks = 0;
+        unsigned long long *arrival = nullptr;               // per sender rank: pushes arrived (in the state's slab: peers write it)
+        mokab::DevBuf<unsigned long long> expect;            // per sender rank: waits completed
+        mokab::DevBuf<unsigned int> done;
+        mokab::DevBuf<int> error;
+        std::vector<int> recvRanks, sendRanks;               // ranks this one pushes to / waits for
+        mokab::DevBuf<int32_t> dst, senders;
+        mokab::DevBuf<uint8_t> slot;
+        mokab::DevBuf<void *> peerH, peerU;                  // [4 targets][nrecv]: hP0, hP1, h0, h1 on every receiver
+        mokab::DevBuf<unsigned long long *> arrivalAt;       // [nrecv]: this rank's slot in the receiver's arrival array
+        std::vector<void *> opened;                          // cudaIpcOpenMemHandle mappings to close
+        int64_t nPush = 0;
+    } p2p;
     ~mokab_state()
     {
+        for (void *q : p2p.opened) cudaIpcCloseMemHandle(q);
         delete d;
         delete f;
     }
@@ -169,13 +195,21 @@ static void alloc_state(mokab_state *st)
     cudaStream_t s = st->ctx->stream;
     auto *t = new StateT<R>();
     if (sizeof(R) == 8) st->d = (StateT<double> *)(void *)t; else st->f = (StateT<float> *)(void *)t;
-    for (int l = 0; l < 2; ++l) {
-        t->u[l].alloc(m->nE); t->u[l].zero(s);
-        t->h[l].alloc(m->nC); t->h[l].zero(s);
-        t->ssh[l].alloc(m->nC); t->ssh[l].zero(s);
-        t->uP[l].alloc(m->nE); t->uP[l].zero(s);
-        t->hP[l].alloc(m->nC); t->hP[l].zero(s);
+    {
+        auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
+        const size_t eb = pad((size_t)m->nE * sizeof(R)), cb = pad((size_t)m->nC * sizeof(R));
+        size_t off = 0;
+        for (int i = 0; i < 4; ++i) { t->slabOff[i] = off; off += eb; }
+        for (int i = 4; i < 8; ++i) { t->slabOff[i] = off; off += cb; }
+        t->slabOff[8] = off; off += pad((size_t)kP2PCounters * sizeof(unsigned long long));
+        t->slab.alloc(off); t->slab.zero(s);
+        unsigned char *b = t->slab.p;
+        t->u[0].view((R *)(b + t->slabOff[0]), m->nE); t->u[1].view((R *)(b + t->slabOff[1]), m->nE);
+        t->uP[0].view((R *)(b + t->slabOff[2]), m->nE); t->uP[1].view((R *)(b + t->slabOff[3]), m->nE);
+        t->h[0].view((R *)(b + t->slabOff[4]), m->nC); t->h[1].view((R *)(b + t->slabOff[5]), m->nC);
+        t->hP[0].view((R *)(b + t->slabOff[6]), m->nC); t->hP[1].view((R *)(b + t->slabOff[7]), m->nC);
     }
+    for (int l = 0; l < 2; ++l) { t->ssh[l].alloc(m->nC); t->ssh[l].zero(s); }
     t->hEdge.alloc(m->nE); t->hEdge.zero(s);      // DiagnosticVars.jl:90-93
     t->flux.alloc(m->nE); t->flux.zero(s);
     t->divC.alloc(m->nC); t->divC.zero(s);
@@ -938,6 +972,153 @@ static void adjoint_run_fe(mokab_state *st)
     t->tapeKind = 0;
 }
 
+// ---- halo exchange by direct peer stores ------------------------------------------------------------------------
+// What one rank tells the others (mokab_p2p_export): where its state arrays and its arrival counters live.  Ranks in
+// other processes map them with CUDA IPC; ranks emulated inside one process (tests) use the addresses as they are.
+struct P2PBlob {
+    int64_t pid;
+    int32_t rank, dtype;
+    void *base;                       // the state's slab
+    uint64_t off[9];                  // u0 u1 uP0 uP1 h0 h1 hP0 hP1 arrival counters
+    cudaIpcMemHandle_t handle;
+};
+
+template <class R>
+static void p2p_export(mokab_state *st, P2PBlob *b)
+{
+    StateT<R> *t = typed<R>(st);
+    mokab_state::P2P &x = st->p2p;
+    memset(b, 0, sizeof(*b));
+    b->pid = (int64_t)getpid();
+    b->dtype = st->dtype;
+    if (!x.exported) {
+        x.arrival = (unsigned long long *)(t->slab.p + t->slabOff[8]);       // zeroed with the slab
+        x.expect.alloc(kP2PCounters); x.expect.zero(st->ctx->stream);
+        x.done.alloc(1); x.done.zero(st->ctx->stream);
+        x.error.alloc(1); x.error.zero(st->ctx->stream);
+        MOKAB_CUDA(cudaStreamSynchronize(st->ctx->stream));
+        x.exported = true;
+    }
+    b->base = t->slab.p;
+    for (int i = 0; i < 9; ++i) b->off[i] = t->slabOff[i];
+#ifndef MOKAB_SIM
+    MOKAB_CUDA(cudaIpcGetMemHandle(&b->handle, t->slab.p));
+#endif
+}
+
+template <class R>
+static void p2p_setup(mokab_state *st, int rank, int nranks, const P2PBlob *blobs, int nrecv, const int32_t *recv_ranks,
+                      const int64_t *counts, const int32_t *dst_idx, int nsend, const int32_t *send_ranks)
+{
+    mokab_ctx *ctx = st->ctx; const mokab_mesh *m = st->mesh;
+    mokab_state::P2P &x = st->p2p;
+    MOKAB_REQUIRE(x.exported, "p2p_setup: call mokab_p2p_export first");
+    MOKAB_REQUIRE(nranks >= 1 && nranks <= kP2PCounters && rank >= 0 && rank < nranks, "p2p_setup: bad rank / nranks");
+    MOKAB_REQUIRE(nrecv >= 0 && nrecv <= p2p::kMaxPeers && nsend >= 0 && nsend <= p2p::kMaxPeers, "p2p_setup: too many peers");
+    int64_t total = 0;
+    for (int i = 0; i < nrecv; ++i) total += counts[i];
+    MOKAB_REQUIRE(total == (int64_t)m->haloSend.n, "p2p_setup: push counts do not add up to the send list of mokab_halo_setup");
+    x.rank = rank; x.nranks = nranks; x.nPush = total;
+    x.recvRanks.assign(recv_ranks, recv_ranks + nrecv);
+    x.sendRanks.assign(send_ranks, send_ranks + nsend);
+    // peer pointers: targets 0/1 = provisional buffers P0/P1, 2/3 = time levels 0/1
+    std::vector<void *> pH((size_t)4 * std::max(nrecv, 1), nullptr), pU((size_t)4 * std::max(nrecv, 1), nullptr);
+    std::vector<unsigned long long *> arr(std::max(nrecv, 1), nullptr);
+    const int64_t me = (int64_t)getpid();
+    for (int i = 0; i < nrecv; ++i) {
+        const P2PBlob &b = blobs[recv_ranks[i]];
+        MOKAB_REQUIRE(b.rank == recv_ranks[i] && b.dtype == st->dtype, "p2p_setup: blob does not belong to the rank / precision it is filed under");
+        void *base = b.base;                         // same process (emulated ranks): the address is valid as it is
+        if (b.pid != me) {
+#ifdef MOKAB_SIM
+            throw Error("p2p_setup: the simulated runtime has no inter-process mappings");
+#else
+            MOKAB_CUDA(cudaIpcOpenMemHandle(&base, b.handle, cudaIpcMemLazyEnablePeerAccess));
+            x.opened.push_back(base);
+#endif
+        }
+        void *ptr[9];
+        for (int k = 0; k < 9; ++k) ptr[k] = (unsigned char *)base + b.off[k];
+        pU[0 * nrecv + i] = ptr[2]; pU[1 * nrecv + i] = ptr[3]; pU[2 * nrecv + i] = ptr[0]; pU[3 * nrecv + i] = ptr[1];
+        pH[0 * nrecv + i] = ptr[6]; pH[1 * nrecv + i] = ptr[7]; pH[2 * nrecv + i] = ptr[4]; pH[3 * nrecv + i] = ptr[5];
+        arr[i] = (unsigned long long *)ptr[8] + rank;
+    }
+    std::vector<uint8_t> slot((size_t)total);
+    {
+        int64_t k = 0;
+        for (int i = 0; i < nrecv; ++i)
+            for (int64_t j = 0; j < counts[i]; ++j) slot[k++] = (uint8_t)i;
+    }
+    std::vector<int32_t> dst(dst_idx, dst_idx + total), snd(send_ranks, send_ranks + nsend);
+    x.peerH.upload(pH, ctx->stream); x.peerU.upload(pU, ctx->stream); x.arrivalAt.upload(arr, ctx->stream);
+    x.slot.upload(slot, ctx->stream); x.dst.upload(dst, ctx->stream); x.senders.upload(snd, ctx->stream);
+    MOKAB_CUDA(cudaStreamSynchronize(ctx->stream));
+    x.ready = true;
+}
+
+// which of the four peer targets holds the output of RK stage `stage` (cf. stage_output)
+static int p2p_target(const mokab_state *st, int stage)
+{
+    switch (stage) {
+    case 1: case 3: return 0;
+    case 2: return 1;
+    case 0: return 2 + st->cur;
+    default: return 2 + (1 - st->cur);
+    }
+}
+
+template <class R>
+static void p2p_push(mokab_state *st, int stage, cudaStream_t stream)
+{
+    mokab_ctx *ctx = st->ctx; const mokab_mesh *m = st->mesh;
+    mokab_state::P2P &x = st->p2p;
+    const int nrecv = (int)x.recvRanks.size();
+    if (nrecv == 0) return;
+    cudaStream_t s = stream ? stream : ctx->stream;
+    if (x.nPush == 0) {
+        p2p::k_halo_signal<<<1, 32, 0, s>>>(nrecv, (unsigned long long *const *)x.arrivalAt.p);
+    } else {
+        R *u, *h;
+        stage_output<R>(st, stage, &u, &h);
+        const int tgt = p2p_target(st, stage);
+        p2p::PushArgs<R> A;
+        A.n = (int)x.nPush; A.nC = (int)m->nC; A.src = m->haloSend.p; A.dst = x.dst.p; A.slot = x.slot.p;
+        A.h = h; A.u = u;
+        A.peerH = (R *const *)x.peerH.p + (size_t)tgt * nrecv; A.peerU = (R *const *)x.peerU.p + (size_t)tgt * nrecv;
+        A.done = x.done.p; A.arrival = (unsigned long long *const *)x.arrivalAt.p; A.nrecv = nrecv;
+        p2p::k_halo_push<R><<<nblk(A.n), 256, 0, s>>>(A);
+    }
+    MOKAB_CUDA(cudaGetLastError());
+    ctx->launches++;
+}
+
+static void p2p_wait(mokab_state *st, cudaStream_t stream)
+{
+    mokab_ctx *ctx = st->ctx;
+    mokab_state::P2P &x = st->p2p;
+    const int nsend = (int)x.sendRanks.size();
+    if (nsend == 0) return;
+    cudaStream_t s = stream ? stream : ctx->stream;
+#ifdef MOKAB_SIM
+    // a spinning kernel cannot run on a simulator that executes kernels to completion: the same predicate becomes a
+    // stream operation that is retried until it holds
+    const int32_t *senders = x.senders.p;
+    const unsigned long long *arrival = x.arrival;
+    unsigned long long *expect = x.expect.p;
+    mokab_sim::enqueue_try(s, "p2p::k_halo_wait", [=]() {
+        for (int i = 0; i < nsend; ++i)
+            if (!p2p::sender_ready(arrival, expect, senders[i])) return false;
+        for (int i = 0; i < nsend; ++i) expect[senders[i]] += 1ull;
+        return true;
+    });
+#else
+    p2p::k_halo_wait<<<1, p2p::kMaxPeers, 0, s>>>(nsend, (const int32_t *)x.senders.p, (const unsigned long long *)x.arrival,
+                                                   x.expect.p, x.error.p, 4000000000ll);
+    MOKAB_CUDA(cudaGetLastError());
+#endif
+    ctx->launches++;
+}
+
 // stand-alone operators on host arrays -------------------------------------------------------------------
 struct OpBufs {
     DevBuf<double> in, in_p, out, out_p;
@@ -1534,6 +1715,85 @@ int mokab_refresh_ssh(mokab_state *state, void *cuda_stream)
         state->ctx->bind();
         if (state->dtype == MOKAB_F64) refresh_ssh<double>(state, (cudaStream_t)cuda_stream);
         else refresh_ssh<float>(state, (cudaStream_t)cuda_stream);
+    });
+}
+
+// ---- halo exchange by direct peer stores (kernels_p2p.cuh) -------------------------------------------------------------
+int mokab_halo_recv_device_indices(const mokab_mesh *mesh, int32_t *out)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(mesh && mesh->halo_ready && (out || mesh->haloRecv.n == 0), "halo_recv_device_indices: call mokab_halo_setup first");
+        mesh->ctx->bind();
+        std::vector<int32_t> r(mesh->haloRecv.n);
+        if (!r.empty()) {
+            MOKAB_CUDA(cudaStreamSynchronize(mesh->ctx->stream));
+            MOKAB_CUDA(cudaMemcpy(r.data(), mesh->haloRecv.p, r.size() * 4, cudaMemcpyDeviceToHost));
+        }
+        for (size_t k = 0; k < r.size(); ++k) out[k] = r[k] < mesh->nC ? r[k] : -(int32_t)(r[k] - mesh->nC) - 1;
+    });
+}
+
+int mokab_p2p_blob_size(int64_t *out)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(out, "p2p_blob_size: NULL argument");
+        *out = (int64_t)sizeof(P2PBlob);
+    });
+}
+
+int mokab_p2p_export(mokab_state *state, int rank, void *blob)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(state && blob, "p2p_export: NULL argument");
+        state->ctx->bind();
+        if (state->dtype == MOKAB_F64) p2p_export<double>(state, (P2PBlob *)blob); else p2p_export<float>(state, (P2PBlob *)blob);
+        ((P2PBlob *)blob)->rank = rank;
+    });
+}
+
+int mokab_p2p_setup(mokab_state *state, int rank, int nranks, const void *blobs, int n_receivers, const int32_t *receiver_ranks,
+                    const int64_t *push_counts, const int32_t *dst_idx, int n_senders, const int32_t *sender_ranks)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(state && blobs && state->mesh->halo_ready, "p2p_setup: NULL argument or mokab_halo_setup not called");
+        MOKAB_REQUIRE((n_receivers == 0 || (receiver_ranks && push_counts)) && (n_senders == 0 || sender_ranks), "p2p_setup: NULL list");
+        state->ctx->bind();
+        if (state->dtype == MOKAB_F64)
+            p2p_setup<double>(state, rank, nranks, (const P2PBlob *)blobs, n_receivers, receiver_ranks, push_counts, dst_idx, n_senders, sender_ranks);
+        else
+            p2p_setup<float>(state, rank, nranks, (const P2PBlob *)blobs, n_receivers, receiver_ranks, push_counts, dst_idx, n_senders, sender_ranks);
+    });
+}
+
+int mokab_halo_push(mokab_state *state, int stage, void *cuda_stream)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(state && state->p2p.ready, "halo_push: call mokab_p2p_setup first");
+        MOKAB_REQUIRE(stage >= 0 && stage <= 4, "halo_push: stage must be 0..4");
+        state->ctx->bind();
+        if (state->dtype == MOKAB_F64) p2p_push<double>(state, stage, (cudaStream_t)cuda_stream);
+        else p2p_push<float>(state, stage, (cudaStream_t)cuda_stream);
+    });
+}
+
+int mokab_halo_wait(mokab_state *state, void *cuda_stream)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(state && state->p2p.ready, "halo_wait: call mokab_p2p_setup first");
+        state->ctx->bind();
+        p2p_wait(state, (cudaStream_t)cuda_stream);
+    });
+}
+
+int mokab_p2p_error(mokab_state *state, int *out)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(state && out, "p2p_error: NULL argument");
+        *out = 0;
+        if (!state->p2p.exported) return;
+        state->ctx->bind();
+        MOKAB_CUDA(cudaStreamSynchronize(state->ctx->stream));
+        MOKAB_CUDA(cudaMemcpy(out, state->p2p.error.p, sizeof(int), cudaMemcpyDeviceToHost));
     });
 }
 

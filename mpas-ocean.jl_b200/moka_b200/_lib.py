@@ -59,6 +59,8 @@ SYMBOLS = [
     "mokab_tape_begin", "mokab_tape_length", "mokab_adjoint_seed", "mokab_adjoint_rk4", "mokab_adjoint_forward_euler",
     "mokab_halo_setup", "mokab_halo_pack", "mokab_halo_unpack", "mokab_rk4_stage", "mokab_rk4_finish_step",
     "mokab_refresh_ssh", "mokab_mesh_block_counts", "mokab_mesh_derived_blocks",
+    "mokab_halo_recv_device_indices", "mokab_p2p_blob_size", "mokab_p2p_export", "mokab_p2p_setup", "mokab_halo_push",
+    "mokab_halo_wait", "mokab_p2p_error",
 ]
 
 
@@ -93,6 +95,10 @@ def bind(L):
         "mokab_rk4_finish_step": [vp], "mokab_refresh_ssh": [vp, vp],
         "mokab_mesh_block_counts": [vp, C.POINTER(i64), C.POINTER(i64)],
         "mokab_mesh_derived_blocks": [vp, C.POINTER(i64), C.POINTER(i64)],
+        "mokab_halo_recv_device_indices": [vp, _I32P], "mokab_p2p_blob_size": [C.POINTER(i64)],
+        "mokab_p2p_export": [vp, C.c_int, vp],
+        "mokab_p2p_setup": [vp, C.c_int, C.c_int, vp, C.c_int, _I32P, C.POINTER(i64), _I32P, C.c_int, _I32P],
+        "mokab_halo_push": [vp, C.c_int, vp], "mokab_halo_wait": [vp, vp], "mokab_p2p_error": [vp, C.POINTER(C.c_int)],
     }
     for name, args in sig.items():
         fn = getattr(L, name)

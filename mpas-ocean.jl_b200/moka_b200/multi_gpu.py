@@ -86,6 +86,24 @@ class TorchRuntime:
         self.dist.all_reduce(t, group=self.group)
         return float(t.item())
 
+    # set-up traffic of the direct-store halo exchange (once per model; tiny)
+    def all_gather_bytes(self, blob: bytes) -> list:
+        n = self.dist.get_world_size(self.group)
+        mine = self.torch.frombuffer(bytearray(blob), dtype=self.torch.uint8).to(self.dev)
+        out = [self.torch.empty_like(mine) for _ in range(n)]
+        self.dist.all_gather(out, mine, group=self.group)
+        return [bytes(t.cpu().numpy().tobytes()) for t in out]
+
+    def all_to_all_int32(self, send: list, recv_counts: list) -> list:
+        """send[q]: int32 array for rank q; returns the arrays received from every rank (recv_counts[q] elements)."""
+        torch = self.torch
+        s = torch.from_numpy(np.concatenate([np.asarray(a, np.int32) for a in send] + [np.zeros(0, np.int32)])).to(self.dev)
+        r = torch.empty(int(sum(recv_counts)), dtype=torch.int32, device=self.dev)
+        self.dist.all_to_all_single(r, s, [int(c) for c in recv_counts], [int(np.asarray(a).size) for a in send], group=self.group)
+        r = r.cpu().numpy()
+        offs = np.concatenate([[0], np.cumsum(recv_counts)]).astype(np.int64)
+        return [r[offs[q]:offs[q + 1]].copy() for q in range(len(recv_counts))]
+
 
 def plan_steps(nsteps: int, parity: int, graph_parity: int):
     """How `nsteps` steps are issued when a 2-step graph captured at time-level parity `graph_parity` exists and the
@@ -109,7 +127,10 @@ class DecomposedModel:
     """
 
     def __init__(self, loc: dict, state, backend: api.B200, device_index: int, dtype=np.float64, group=None, overlap=True,
-                 graph=False, runtime=None):
+                 graph=False, runtime=None, halo="nccl"):
+        if halo not in ("nccl", "p2p"):
+            raise api.MokaError("DecomposedModel: halo must be 'nccl' (packed all-to-all) or 'p2p' (direct peer stores)")
+        self.halo_mode = halo
         self.rt = runtime if runtime is not None else TorchRuntime(device_index, group)
         self.cuda = self.rt.cuda
         self.loc, self.backend, self.overlap, self.use_graph = loc, backend, overlap, graph
@@ -131,12 +152,43 @@ class DecomposedModel:
         self._graph, self._graph_dt = None, None
         self._validated, self.graph_status = False, "not used"
         self._parity, self._graph_parity = 0, 0                  # steps taken so far mod 2; the same at graph capture
+        if halo == "p2p":
+            self._setup_p2p(scnt, rcnt)
+
+    def _setup_p2p(self, scnt, rcnt) -> None:
+        """Direct-store halo exchange (csrc/kernels_p2p.cuh): tell every sender where its values live in this rank's
+        arrays, exchange the addresses / IPC handles of the state arrays, and build the push tables."""
+        lib, rank = L.lib(), int(self.loc["rank"])
+        nrecv_total = int(sum(rcnt))
+        mine = np.zeros(max(1, nrecv_total), np.int32)
+        L.check(lib.mokab_halo_recv_device_indices(self.mesh.handle, mine.ctypes.data_as(L._I32P)))
+        offs = np.concatenate([[0], np.cumsum(rcnt)]).astype(np.int64)
+        # rank q fills my segment q: it needs those indices; I need, from every rank I send to, its segment for me
+        got = self.rt.all_to_all_int32([mine[offs[q]:offs[q + 1]] for q in range(self.nparts)], list(scnt))
+        size = C.c_int64()
+        L.check(lib.mokab_p2p_blob_size(C.byref(size)))
+        blob = C.create_string_buffer(size.value)
+        L.check(lib.mokab_p2p_export(self.handle, rank, blob))
+        blobs = b"".join(self.rt.all_gather_bytes(blob.raw))
+        receivers = [q for q in range(self.nparts) if scnt[q] > 0]
+        senders = [q for q in range(self.nparts) if rcnt[q] > 0]
+        dst = np.ascontiguousarray(np.concatenate([got[q] for q in receivers] + [np.zeros(0, np.int32)]), np.int32)
+        rr, sr = np.asarray(receivers, np.int32), np.asarray(senders, np.int32)
+        cnt = np.asarray([scnt[q] for q in receivers], np.int64)
+        L.check(lib.mokab_p2p_setup(self.handle, rank, self.nparts, blobs, len(receivers), rr.ctypes.data_as(L._I32P),
+                                    cnt.ctypes.data_as(C.POINTER(C.c_int64)), dst.ctypes.data_as(L._I32P), len(senders),
+                                    sr.ctypes.data_as(L._I32P)))
+        self.rt.all_reduce_min(1)                                # nobody pushes before everybody is mapped
 
     def _stage(self, dt, s, part, stream):
         L.check(L.lib().mokab_rk4_stage(self.handle, float(dt), s, part, C.c_void_p(stream.cuda_stream)))
 
     def _exchange(self, s, stream):
         lib = L.lib()
+        if self.halo_mode == "p2p":
+            L.check(lib.mokab_halo_push(self.handle, s, C.c_void_p(stream.cuda_stream)))
+            L.check(lib.mokab_halo_wait(self.handle, C.c_void_p(stream.cuda_stream)))
+            return
         with self.cuda.stream(stream):
             L.check(lib.mokab_halo_pack(self.handle, s, C.c_void_p(self.ex.send.data_ptr()), C.c_void_p(stream.cuda_stream)))
             self.ex.exchange()
@@ -243,6 +295,11 @@ class DecomposedModel:
         self.refresh_ssh()
         self.compute.synchronize()
         self.halo.synchronize()
+        if self.halo_mode == "p2p":
+            err = C.c_int()
+            L.check(L.lib().mokab_p2p_error(self.handle, C.byref(err)))
+            if err.value:
+                raise api.MokaError("DecomposedModel: a halo wait timed out (a peer died or the ranks' schedules diverged)")
 
     def close(self) -> None:
         """Drop the captured graph (it pins NCCL resources: the process group cannot be destroyed while
@@ -341,7 +398,7 @@ def bench_main(args, rank, world, local):
     dt = api.cfl_dt(1.0e7 / nx)
     backend = api.B200(local)
     model = DecomposedModel(loc, state, backend, local, dtype=npdt, overlap=not getattr(args, "no_overlap", False),
-                            graph=not getattr(args, "no_graph", False))
+                            graph=not getattr(args, "no_graph", False), halo=getattr(args, "halo", "nccl"))
     K, W = args.steps, max(args.warmup, 3)
     model.step(dt, W)
     model.finish()
@@ -415,9 +472,10 @@ def bench_main(args, rank, world, local):
             "config": {"workload": ("coastal Kelvin wave, %dx%d channel hex mesh with boundary-edge masks" % (nx, nx) if args.workload.startswith("kelvin")
                                     else f"inertial gravity wave, {nx}x{nx} periodic planar hex mesh") + f" ({nC_glob} cells), "
                                    f"{'Float64' if args.dtype == 'f64' else 'Float32'} RK4, dt={dt:.4g}s, recursive-coordinate-bisection "
-                                   f"into {world} parts, 1 halo layer, NCCL all-to-all per stage "
+                                   f"into {world} parts, 1 halo layer, "
+                                   f"{'NCCL all-to-all' if model.halo_mode == 'nccl' else 'direct peer stores + arrival counters'} per stage "
                                    f"{'overlapped with interior blocks' if model.overlap else '(no overlap)'}"
-                                   f"{', 2-step CUDA graph incl. NCCL (' + model.graph_status + ')' if model.use_graph else ', CUDA graph ' + model.graph_status}",
+                                   f"{', 2-step CUDA graph incl. the exchange (' + model.graph_status + ')' if model.use_graph else ', CUDA graph ' + model.graph_status}",
                        "name": args.workload, "l2": "inputs larger than L2 (no flush)", "setup_s": round(t_setup, 1),
                        "rank0_blocks_interior_boundary": list(blocks), "rank0_halo_bytes_per_stage": int(halo_bytes),
                        "rank0_blocks_rebuilding_edgesOnEdge": [int(nder), int(nblk)]},

@@ -48,7 +48,7 @@ def case(kind, nx):
     return _CASES[(kind, nx)]
 
 
-def run(kind, nx, nparts, step_calls, overlap, graph, policy, seed, dtype=np.float64):
+def run(kind, nx, nparts, step_calls, overlap, graph, policy, seed, dtype=np.float64, halo="nccl"):
     """`step_calls`: the sequence of model.step(dt, n) calls (odd counts move the time-level parity between them)."""
     simcuda.set_policy(policy, seed)
     m, mo, state, dt = case(kind, nx)
@@ -57,7 +57,7 @@ def run(kind, nx, nparts, step_calls, overlap, graph, policy, seed, dtype=np.flo
     def body(r, comm):
         backend = mb.B200(0)
         model = multi_gpu.DecomposedModel(locs[r], multi_gpu.local_state(locs[r], *state), backend, 0, dtype=dtype, overlap=overlap,
-                                          graph=graph, runtime=simcuda.SimRuntime(comm, r))
+                                          graph=graph, runtime=simcuda.SimRuntime(comm, r), halo=halo)
         for n in step_calls:
             model.step(dt, n)
         model.finish()
@@ -93,6 +93,7 @@ def main():
     ap.add_argument("--cases", default="small")
     ap.add_argument("--policies", default="fifo,lazy,others_first,random")
     ap.add_argument("--seeds", type=int, default=2)
+    ap.add_argument("--halo", default="nccl,p2p", help="halo exchange paths to check: the packed all-to-all and/or the direct peer stores")
     args = ap.parse_args()
     # (kind, nx, ranks, step calls): 96x96 over 8 ranks is the decomposition on which the B200 run exposed the ordering
     # bug (every block a boundary block, a partly filled last block); [3, 6, 1, 4] replays the graph from both parities
@@ -103,19 +104,21 @@ def main():
     for kind, nx, P, calls in cases:
         for policy in args.policies.split(","):
             for seed in range(1, (args.seeds if policy == "random" else 1) + 1):
-                for overlap, graph in ((True, False), (False, False), (True, True)):
-                    t0 = time.time()
-                    ok, status = run(kind, nx, P, calls, overlap, graph, policy, seed)
-                    bad += not ok
-                    if graph and not status.startswith("validated"):
-                        bad += 1
-                        ok = False
-                    print(f"{kind}{nx} ranks={P} steps={calls} {policy}{'/' + str(seed) if policy == 'random' else ''} "
-                          f"{'overlap' if overlap else 'serial'} {'graph' if graph else 'stream'}: {'OK' if ok else 'MISMATCH'}"
-                          f"{' [' + status + ']' if graph else ''} {time.time() - t0:.1f}s", flush=True)
-    ok, _ = run("igw", 48, 4, [4, 3], True, True, "random", 7, dtype=np.float32)
-    bad += not ok
-    print(f"igw48 ranks=4 Float32 random/7 overlap graph: {'OK' if ok else 'MISMATCH'}", flush=True)
+                for halo in args.halo.split(","):
+                    for overlap, graph in ((True, False), (False, False), (True, True)):
+                        t0 = time.time()
+                        ok, status = run(kind, nx, P, calls, overlap, graph, policy, seed, halo=halo)
+                        bad += not ok
+                        if graph and not status.startswith("validated"):
+                            bad += 1
+                            ok = False
+                        print(f"{kind}{nx} ranks={P} steps={calls} {halo} {policy}{'/' + str(seed) if policy == 'random' else ''} "
+                              f"{'overlap' if overlap else 'serial'} {'graph' if graph else 'stream'}: {'OK' if ok else 'MISMATCH'}"
+                              f"{' [' + status + ']' if graph else ''} {time.time() - t0:.1f}s", flush=True)
+    for halo in args.halo.split(","):
+        ok, _ = run("igw", 48, 4, [4, 3], True, True, "random", 7, dtype=np.float32, halo=halo)
+        bad += not ok
+        print(f"igw48 ranks=4 Float32 {halo} random/7 overlap graph: {'OK' if ok else 'MISMATCH'}", flush=True)
     print("SIM_DECOMPOSED_OK" if bad == 0 else f"SIM_DECOMPOSED_FAILED ({bad})", flush=True)
     sys.exit(0 if bad == 0 else 1)
 

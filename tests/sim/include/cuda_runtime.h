@@ -74,6 +74,9 @@ enum cudaStreamCaptureMode { cudaStreamCaptureModeGlobal = 0, cudaStreamCaptureM
 #define cudaEventDisableTiming 0x02
 #define cudaHostAllocDefault 0x00
 
+struct cudaIpcMemHandle_t { char reserved[64]; };
+#define cudaIpcMemLazyEnablePeerAccess 0x01
+
 struct cudaDeviceProp {
     char name[256];
     int major, minor, multiProcessorCount;
@@ -110,6 +113,9 @@ cudaError_t cudaGraphInstantiate(cudaGraphExec_t *ge, cudaGraph_t g, unsigned lo
 cudaError_t cudaGraphDestroy(cudaGraph_t g);
 cudaError_t cudaGraphExecDestroy(cudaGraphExec_t ge);
 cudaError_t cudaGraphLaunch(cudaGraphExec_t ge, cudaStream_t s);
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p);
+cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned flags);
+cudaError_t cudaIpcCloseMemHandle(void *p);
 }
 // the toolkit's C++ convenience overload
 template <class T> static inline cudaError_t cudaMalloc(T **p, size_t bytes) { return cudaMalloc((void **)(void *)p, bytes); }
@@ -127,7 +133,12 @@ namespace mokab_sim {
 // completion one after another and a call to either primitive aborts the launch with an error
 void enqueue_kernel(cudaStream_t s, unsigned grid, unsigned block, bool coop, const char *name, std::function<void()> body);
 
-static inline bool is_coop_name(const char *kernel) { return __builtin_strstr(kernel, "reduce::k_") != nullptr; }
+static inline bool is_coop_name(const char *kernel)
+{
+    return __builtin_strstr(kernel, "reduce::k_") != nullptr || __builtin_strstr(kernel, "k_halo_push") != nullptr;
+}
+// a device-side wait on memory that another stream (or rank) writes: retried by the scheduler until `ready` returns true
+void enqueue_try(cudaStream_t s, const char *name, std::function<bool()> ready);
 
 template <class... P, class... A>
 static inline void launch_impl(bool coop, const char *name, void (*k)(P...), unsigned grid, unsigned block, cudaStream_t s, A &&...a)

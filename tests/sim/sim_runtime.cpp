@@ -50,7 +50,7 @@ thread_local dim3 t_blockDim, t_gridDim;
 struct Comm;
 struct GraphRun;
 
-enum OpKind { OP_WORK, OP_RECORD, OP_WAIT, OP_COLL, OP_GRAPH };
+enum OpKind { OP_WORK, OP_RECORD, OP_WAIT, OP_COLL, OP_GRAPH, OP_TRY };
 
 struct CollArgs {
     Comm *comm = nullptr;
@@ -64,6 +64,7 @@ struct CollArgs {
 struct Op {
     OpKind kind = OP_WORK;
     std::function<void()> fn;
+    std::function<bool()> try_fn;  // OP_TRY: retried until it returns true (a device-side wait on memory another stream writes)
     cudaEvent_t ev = nullptr;
     uint64_t ticket = 0;
     cudaStream_t src = nullptr;  // OP_WAIT: the stream the awaited record was enqueued on
@@ -92,6 +93,7 @@ struct mokab_sim_event {
 struct Node {
     OpKind kind = OP_WORK;
     std::function<void()> fn;
+    std::function<bool()> try_fn;
     CollArgs coll;
     std::vector<int> deps;
     std::string name;
@@ -374,6 +376,8 @@ StepResult step_graph(Op &op, std::vector<cudaStream_t> *blockers)
             CollArgs a = n.coll;
             a.seq = run.seq[i];
             if (!try_coll(a, blockers)) continue;
+        } else if (n.kind == OP_TRY) {
+            if (!n.try_fn()) continue;
         } else {
             n.fn();
         }
@@ -406,6 +410,9 @@ StepResult try_step(cudaStream_t s, std::vector<cudaStream_t> *blockers)
     case OP_COLL:
         if (!try_coll(op.coll, blockers)) return STEP_BLOCKED;
         break;
+    case OP_TRY:
+        if (!op.try_fn()) return STEP_BLOCKED;
+        break;
     case OP_GRAPH: {
         StepResult r = step_graph(op, blockers);
         if (r == STEP_BLOCKED) return r;
@@ -418,17 +425,30 @@ StepResult try_step(cudaStream_t s, std::vector<cudaStream_t> *blockers)
     return STEP_DONE;
 }
 
-// one unit of progress on `s`, or on something it is blocked on
-bool progress(cudaStream_t s, int depth)
+// one unit of progress on `s`, or on something it is blocked on (`seen`: the streams already tried in this attempt --
+// each is tried once, so mutually blocked streams terminate and the search is linear)
+bool progress_in(cudaStream_t s, std::vector<cudaStream_t> &seen)
 {
+    seen.push_back(s);
     std::vector<cudaStream_t> blockers;
     StepResult r = try_step(s, &blockers);
     if (r == STEP_DONE) return true;
-    if (r == STEP_EMPTY || depth > 64) return false;
+    if (r == STEP_EMPTY) return false;
+    if (blockers.empty())      // a wait on memory (OP_TRY): whoever writes it is unknown -- any other stream may be the one
+        for (auto it = R.streams.rbegin(); it != R.streams.rend(); ++it)
+            if (!(*it)->cap) blockers.push_back(*it);
     if (R.policy == RANDOM) std::shuffle(blockers.begin(), blockers.end(), R.rng);
-    for (cudaStream_t b : blockers)
-        if (b != s && progress(b, depth + 1)) return true;
+    for (cudaStream_t b : blockers) {
+        if (std::find(seen.begin(), seen.end(), b) != seen.end()) continue;
+        if (progress_in(b, seen)) return true;
+    }
     return false;
+}
+
+bool progress(cudaStream_t s, int)
+{
+    std::vector<cudaStream_t> seen;
+    return progress_in(s, seen);
 }
 
 std::vector<cudaStream_t> others_order(cudaStream_t except)
@@ -487,7 +507,7 @@ cudaError_t wait_until(std::unique_lock<std::mutex> &lk, cudaStream_t target, Pr
         R.cv.wait_for(lk, std::chrono::milliseconds(20), [&] { return R.enqueue_epoch != epoch; });
         if (R.enqueue_epoch != epoch) { last_progress = std::chrono::steady_clock::now(); continue; }
         if (std::chrono::duration<double>(std::chrono::steady_clock::now() - last_progress).count() > R.deadlock_s) {
-            static const char *kinds[] = {"work", "record", "wait", "collective", "graph"};
+            static const char *kinds[] = {"work", "record", "wait", "collective", "graph", "wait-on-memory"};
             for (cudaStream_t x : R.streams) {
                 fprintf(stderr, "mokab_sim:   stream %d%s: %zu pending", x->id, x == target ? " (awaited)" : "", x->q.size());
                 if (!x->q.empty()) {
@@ -540,7 +560,7 @@ void enqueue(cudaStream_t s, Op &&op)
         mokab_sim_graph *g = s->cap;
         if (op.kind == OP_RECORD || op.kind == OP_WAIT || op.kind == OP_GRAPH) die("internal: record/wait/graph op reached a capturing stream");
         Node n;
-        n.kind = op.kind; n.fn = std::move(op.fn); n.coll = op.coll; n.deps = s->frontier; n.name = op.name;
+        n.kind = op.kind; n.fn = std::move(op.fn); n.try_fn = std::move(op.try_fn); n.coll = op.coll; n.deps = s->frontier; n.name = op.name;
         g->nodes.push_back(std::move(n));
         s->frontier.assign(1, (int)g->nodes.size() - 1);
         return;
@@ -602,6 +622,16 @@ double shfl_down(double v, unsigned delta)
     const double r = (src < 32 && (t / 32) * 32 + src < b->nthreads) ? w.buf[src] : v;
     warp_barrier(b, w);
     return r;
+}
+
+void enqueue_try(cudaStream_t s, const char *name, std::function<bool()> ready)
+{
+    std::unique_lock<std::mutex> lk(R.mu);
+    Op op;
+    op.kind = OP_TRY;
+    op.name = name;
+    op.try_fn = std::move(ready);
+    enqueue(resolve(s), std::move(op));
 }
 
 void enqueue_kernel(cudaStream_t s, unsigned grid, unsigned block, bool coop, const char *name, std::function<void()> body)
@@ -963,6 +993,10 @@ cudaError_t cudaGraphLaunch(cudaGraphExec_t ge, cudaStream_t s_)
     enqueue(s, std::move(op));
     return cudaSuccess;
 }
+
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return fail(cudaErrorUnknown); }       // one process: never needed
+cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return fail(cudaErrorUnknown); }
+cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
 
 // ---- simulation controls (tests/sim/simcuda.py) ----------------------------------------------------------------------
 void mokab_sim_set_policy(int policy, uint64_t seed)

@@ -205,6 +205,14 @@ class Comm:
         _ck(runtime().mokab_sim_all_to_all(self.handle, rank, current_stream().cuda_stream, send.data_ptr(), recv.data_ptr(), sc, rc,
                                            send.dtype.itemsize))
 
+    def exchange_host(self, rank: int, value) -> list:
+        """Every rank thread contributes a value; all get the list (a host-side all-gather)."""
+        self._slots[rank] = value
+        self._barrier.wait()
+        out = list(self._slots)
+        self._barrier.wait()
+        return out
+
     def all_reduce_host(self, rank: int, value, op=min):
         """Host-side reduction between the rank threads (stands in for a blocking all_reduce of a scalar)."""
         self._slots[rank] = value
@@ -249,6 +257,15 @@ class SimRuntime:
 
     def all_reduce_sum(self, value: float) -> float:
         return float(self.comm.all_reduce_host(self.rank, float(value), lambda a, b: a + b))
+
+    def all_gather_bytes(self, blob: bytes) -> list:
+        return self.comm.exchange_host(self.rank, blob)
+
+    def all_to_all_int32(self, send: list, recv_counts: list) -> list:
+        everybody = self.comm.exchange_host(self.rank, [np.array(a, np.int32) for a in send])
+        out = [everybody[q][self.rank] for q in range(self.comm.n)]
+        assert [a.size for a in out] == [int(c) for c in recv_counts], "all_to_all_int32: counts do not match"
+        return out
 
 
 def run_ranks(nranks: int, body):
