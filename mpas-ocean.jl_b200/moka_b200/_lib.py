@@ -8,7 +8,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), os.environ.get("MOKAB_LIB", "libmoka_b200.so"))
+# MOKAB_LIB selects a tuning variant built next to the default one (Makefile: libmoka_b200_mb8.so); a file name, never a path
+LIB_PATH = os.path.join(os.path.dirname(_HERE), os.path.basename(os.environ.get("MOKAB_LIB", "libmoka_b200.so")))
 
 F64, F32 = 0, 1
 (SSH, NORMAL_VELOCITY, LAYER_THICKNESS, SSH_PREV, NORMAL_VELOCITY_PREV, LAYER_THICKNESS_PREV,

@@ -62,12 +62,12 @@ class TorchRuntime:
     (tests/sim) pass an object of the same shape backed by their host runtime, so the schedule below is exercised
     under adversarial stream interleavings without a GPU."""
 
-    def __init__(self, device_index: int, group=None):
+    def __init__(self, device_index: int, group=None, device=None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist, self.group = torch, dist, group
         self.cuda = torch.cuda
-        self.dev = torch.device("cuda", device_index)
+        self.dev = torch.device("cuda", device_index) if device is None else torch.device(device)   # "cpu": gloo tests of the host exchanges
 
     def stream(self, priority: int = 0):
         return self.torch.cuda.Stream(self.dev, priority=priority)

@@ -184,3 +184,17 @@ def test_fe_gradient_matches_finite_differences_like_the_reference_test():
     # the first step's thickness flux is zero (hEdge starts as zeros), so nothing depends on u through it there; and ssh
     # enters only through the first step's pressure gradient
     assert np.linalg.norm(gs) > 0 and np.linalg.norm(ge) > 0
+
+
+def test_committed_forward_euler_adjoint_fixture_is_reproduced_by_the_oracle():
+    import json
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "igw16_adjoint_fe.npz"))
+    meta = json.loads(str(g["meta"]))
+    m = hex_mesh(16)
+    ssh, u, h = mb.inertialGravityWave(m).initial_state()
+    J, gu, gh, gs, ge = A.gradient_sum_ssh2_fe(m, ssh, u, h, meta["dt"], meta["nsteps"])
+    assert J == float(g["J"]) and np.array_equal(gu, g["d_normalVelocity"]) and np.array_equal(gh, g["d_layerThickness"])
+    assert np.array_equal(gs, g["d_ssh"]) and np.array_equal(ge, g["d_layerThicknessEdge"])
+    k = meta["fd_index"]
+    assert abs(gh[k] - float(g["fd_layerThickness"])) < 1e-4 and abs(gu[k] - float(g["fd_normalVelocity"])) < 1e-2

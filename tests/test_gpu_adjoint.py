@@ -234,3 +234,22 @@ def test_forward_euler_adjoint_on_runtime_width_rows(backend):
     _, gu, gh, gs, _ = A.gradient_sum_ssh2_fe(mo, ssh, u, h, dt, 5)
     assert rel_l2(d_prog.normalVelocity, gu) <= TOL64 and rel_l2(d_prog.layerThickness, gh) <= TOL64
     assert rel_l2(d_prog.ssh, gs) <= TOL64
+
+
+def test_committed_forward_euler_adjoint_fixture(backend):
+    """tests/golden/igw16_adjoint_fe.npz (made by tests/golden/make_golden_adjoint.py from the adjoint oracle)."""
+    import json
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "igw16_adjoint_fe.npz"))
+    meta = json.loads(str(g["meta"]))
+    m = hex_mesh(16)
+    ssh, u, h = mb.inertialGravityWave(m).initial_state()
+    prog = mb.PrognosticVars(ssh, u, h, 2, mb.Mesh(m, backend))
+    d_prog = mb.ocn_init_shadows(prog)
+    J = mb.autodiff_reverse_run_loop(meta["dt"], prog, d_prog, None, None, None, mb.ForwardEuler, meta["nsteps"])
+    assert abs(J - float(g["J"])) <= 1e-12 * J
+    assert rel_l2(d_prog.normalVelocity, g["d_normalVelocity"]) <= TOL64 and rel_l2(d_prog.layerThickness, g["d_layerThickness"]) <= TOL64
+    assert rel_l2(d_prog.ssh, g["d_ssh"]) <= TOL64
+    k = meta["fd_index"]
+    assert abs(d_prog.layerThickness[k] - float(g["fd_layerThickness"])) < 1e-4          # test_Enzyme_end2end.jl:176
+    assert abs(d_prog.normalVelocity[k] - float(g["fd_normalVelocity"])) < 1e-2          # :177

@@ -132,3 +132,34 @@ def test_graph_replay_plan_respects_time_level_parity():
                 assert pre + 2 * replays + post == n and pre in (0, 1) and post in (0, 1) and replays >= 0
                 assert (parity + pre) % 2 == graph_parity or replays == 0      # replays start at the capture parity
                 assert pre == (1 if parity != graph_parity else 0)
+
+
+def _exchange_worker(rank, world, port, out_dir):
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path[:0] = [here, os.path.join(os.path.dirname(here), "mpas-ocean.jl_b200")]
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from moka_b200 import multi_gpu
+    rt = multi_gpu.TorchRuntime(0, device="cpu")
+    # rank r sends q the array [100 r + q] * (r + 2 q) (lengths differ per pair, some are empty)
+    send = [np.full((rank + 2 * q) % 4, 100 * rank + q, np.int32) for q in range(world)]
+    recv_counts = [(q + 2 * rank) % 4 for q in range(world)]
+    got = rt.all_to_all_int32(send, recv_counts)
+    blobs = rt.all_gather_bytes(bytes([rank]) * 7)
+    ok = all(np.array_equal(got[q], np.full(recv_counts[q], 100 * q + rank, np.int32)) for q in range(world))
+    ok = ok and blobs == [bytes([q]) * 7 for q in range(world)]
+    ok = ok and rt.all_reduce_min(rank + 5) == 5 and rt.all_reduce_sum(float(rank)) == float(sum(range(world)))
+    open(os.path.join(out_dir, f"ok{rank}"), "w").write("1" if ok else "0")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_runtime_host_exchanges_over_gloo(tmp_path):
+    """multi_gpu.TorchRuntime's set-up exchanges of the direct-store halo path (who needs which index list, whose blob is
+    whose) and its scalar reductions, on 3 gloo ranks."""
+    import torch.multiprocessing as mp
+    world = 3
+    mp.spawn(_exchange_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert [open(tmp_path / f"ok{r}").read() for r in range(world)] == ["1"] * world
