@@ -88,13 +88,106 @@ def run(kind, nx, nparts, step_calls, overlap, graph, policy, seed, dtype=np.flo
     return ok, outs[0][1]
 
 
+def run_e2e(kind, nx, nparts, iters, policy, seed, halo):
+    """bench.py's end-to-end leg at N > 1 (multi_gpu.bench_main.e2e_steps): every iteration uploads this rank's (u, h) from
+    page-locked memory through the pipelined transfers, takes ONE step, refreshes ssh and downloads it -- copy streams, the
+    compute stream and the halo stream all in play.  Iteration i uploads the state scaled by (1 + i/8), so a download that
+    overtakes its step, or an upload that lands on a level a kernel still reads, shows up as the wrong iteration's result."""
+    simcuda.set_policy(policy, seed)
+    m, mo, state, dt = case(kind, nx)
+    locs = partition.decompose(m, nparts)
+    H = float(np.mean(state[2] - state[0]))
+
+    def scaled(i):       # a different, still consistent, initial state per iteration: ssh scaled, h = H + ssh
+        f = 1.0 + i / 8.0
+        return state[0] * f, state[1] * f, H + state[0] * f
+
+    def body(r, comm):
+        backend = mb.B200(0)
+        loc = locs[r]
+        model = multi_gpu.DecomposedModel(loc, multi_gpu.local_state(loc, *state), backend, 0, overlap=True, graph=False,
+                                          runtime=simcuda.SimRuntime(comm, r), halo=halo)
+        nCl, nEl = loc["nCells"], loc["nEdges"]
+        hin = [(backend.pinned(nEl), backend.pinned(nCl)) for _ in range(2)]
+        hout = [backend.pinned(nCl) for _ in range(iters)]
+        for i in range(iters):
+            _, lu, lh = multi_gpu.local_state(loc, *scaled(i))
+            if i >= 2:
+                model.prog.synchronize()          # the slot's previous upload must have left before the host refills it
+            hin[i & 1][0][:], hin[i & 1][1][:] = lu, lh
+            model.prog.upload_async(normalVelocity=hin[i & 1][0], layerThickness=hin[i & 1][1])
+            model.step(dt, 1)
+            model.refresh_ssh()
+            model.prog.download_async(ssh=hout[i])
+        model.prog.synchronize()
+        model.halo.synchronize()
+        res = [np.array(a[:loc["nCellsOwned"]]) for a in hout]
+        model.close()
+        return res
+
+    outs = simcuda.run_ranks(nparts, body)
+    ok = True
+    for i in range(iters):
+        gs = np.full(m["nCells"], np.nan)
+        for loc, res in zip(locs, outs):
+            gs[loc["cellsGlobal"][:loc["nCellsOwned"]]] = res[i]
+        om = OC.OracleModel(mo, *scaled(i))
+        om.run_loop(dt, 1, "RungeKutta4")
+        ok = ok and np.array_equal(gs, om.ssh[1])
+    return ok
+
+
+def run_mutations():
+    """Does this checker have teeth?  Re-run one case with each of the schedule's two cross-stream events removed
+    (DecomposedModel._enqueue_steps: interior(s+1) after boundary(s), boundary(s+1) after interior(s)): the synchronous
+    order (FIFO) must still pass -- the bug is a race, as on hardware -- and the adversarial orders must catch it."""
+    from moka_b200 import _lib as L
+
+    def variant(drop):
+        def _enqueue_steps(self, dt, nsteps):
+            cuda = self.cuda
+            self.halo.wait_stream(self.compute)
+            for _ in range(nsteps):
+                for s in (1, 2, 3, 4):
+                    ev_i, ev_b = cuda.Event(), cuda.Event()
+                    self._stage(dt, s, L.PART_BOUNDARY, self.halo)
+                    ev_b.record(self.halo)
+                    self._stage(dt, s, L.PART_INTERIOR, self.compute)
+                    ev_i.record(self.compute)
+                    self._exchange(s, self.halo)
+                    if drop != "ev_b":
+                        self.compute.wait_event(ev_b)
+                    if drop != "ev_i":
+                        self.halo.wait_event(ev_i)
+                L.check(L.lib().mokab_rk4_finish_step(self.handle))
+            self.compute.wait_stream(self.halo)
+        return _enqueue_steps
+
+    original = multi_gpu.DecomposedModel._enqueue_steps
+    bad = 0
+    try:
+        for drop in (None, "ev_b", "ev_i"):
+            multi_gpu.DecomposedModel._enqueue_steps = variant(drop)
+            got = {pol: run("igw", 128, 2, [3], True, False, pol, 2)[0] for pol in ("fifo", "lazy", "others_first")}
+            want = {"fifo": True, "lazy": drop is None, "others_first": drop is None}
+            bad += got != want
+            print(f"schedule without {drop or 'nothing'}: {got} {'as expected' if got == want else 'UNEXPECTED'}", flush=True)
+    finally:
+        multi_gpu.DecomposedModel._enqueue_steps = original
+    print("SIM_MUTATIONS_DETECTED" if bad == 0 else "SIM_MUTATIONS_MISSED", flush=True)
+    sys.exit(0 if bad == 0 else 1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", default="small")
     ap.add_argument("--policies", default="fifo,lazy,others_first,random")
     ap.add_argument("--seeds", type=int, default=2)
     ap.add_argument("--halo", default="nccl,p2p", help="halo exchange paths to check: the packed all-to-all and/or the direct peer stores")
+    ap.add_argument("--mutations", action="store_true", help="check that removing a cross-stream dependency of the schedule is detected")
     args = ap.parse_args()
+    if args.mutations:
+        run_mutations()
     # (kind, nx, ranks, step calls): 96x96 over 8 ranks is the decomposition on which the B200 run exposed the ordering
     # bug (every block a boundary block, a partly filled last block); [3, 6, 1, 4] replays the graph from both parities
     cases = [("igw", 32, 2, [6]), ("igw", 96, 8, [6]), ("igw", 48, 4, [3, 6, 1, 4]), ("kelvin", 48, 4, [5, 4])]
@@ -119,6 +212,12 @@ def main():
         ok, _ = run("igw", 48, 4, [4, 3], True, True, "random", 7, dtype=np.float32, halo=halo)
         bad += not ok
         print(f"igw48 ranks=4 Float32 {halo} random/7 overlap graph: {'OK' if ok else 'MISMATCH'}", flush=True)
+    for halo in args.halo.split(","):
+        for policy in args.policies.split(","):
+            t0 = time.time()
+            ok = run_e2e("igw", 48, 4, 5, policy, 3, halo)
+            bad += not ok
+            print(f"igw48 ranks=4 end-to-end leg (upload / step / download x5) {halo} {policy}: {'OK' if ok else 'MISMATCH'} {time.time() - t0:.1f}s", flush=True)
     print("SIM_DECOMPOSED_OK" if bad == 0 else f"SIM_DECOMPOSED_FAILED ({bad})", flush=True)
     sys.exit(0 if bad == 0 else 1)
 
