@@ -237,7 +237,10 @@ int  mokab_adjoint_forward_euler(mokab_state *state);
  * exchange of stage s with the interior of stage s.  `cuda_stream` NULL = the
  * context's stream.  Entities are addressed in the combined local index space [cells | edges]
  * (edge k -> nCells + k), caller numbering, 0-based. */
-enum { MOKAB_PART_ALL = 0, MOKAB_PART_INTERIOR = 1, MOKAB_PART_BOUNDARY = 2 };
+enum { MOKAB_PART_ALL = 0, MOKAB_PART_INTERIOR = 1, MOKAB_PART_BOUNDARY = 2,
+       /* the boundary blocks with the direct-store halo exchange folded in (after mokab_p2p_setup): wait for the neighbours'
+        * previous stage, compute, store every value a neighbour needs into its memory, tick its arrival counter */
+       MOKAB_PART_BOUNDARY_PUSH = 3 };
 /* send_idx: owned entities whose values neighbours need; recv_idx: halo entities, in message order.
  * Blocks that hold a send entity join the BOUNDARY part, so a message can be packed as soon as the
  * boundary launch of a stage has finished.  Call before creating states on the mesh. */
@@ -273,6 +276,9 @@ int  mokab_p2p_setup(mokab_state *state, int rank, int nranks, const void *blobs
 /* stage as in mokab_halo_pack */
 int  mokab_halo_push(mokab_state *state, int stage, void *cuda_stream);
 int  mokab_halo_wait(mokab_state *state, void *cuda_stream);
+/* With MOKAB_PART_BOUNDARY_PUSH launches there is nothing else to call per stage; after the LAST stage enqueued (before the
+ * host, an upload or anything else touches the halo slots) this waits until the neighbours' last stores have arrived. */
+int  mokab_halo_wait_arrivals(mokab_state *state, void *cuda_stream);
 /* 1 if a wait ever timed out (~2 s: a peer died or the ranks' schedules diverged); the GPU is never left spinning */
 int  mokab_p2p_error(mokab_state *state, int *out);
 /* number of interior / boundary blocks of the fused kernel (diagnostic) */

@@ -32,6 +32,7 @@
 // so the two halves of the block share their working set in L1.
 #pragma once
 #include "common.cuh"
+#include "kernels_p2p.cuh"
 
 namespace mokab {
 namespace fused {
@@ -45,6 +46,28 @@ __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(
 __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+
+// Direct-store halo exchange folded into the BOUNDARY launch of a stage (PUSH = true; protocol and ordering argument in
+// kernels_p2p.cuh, which holds the stand-alone variant): a block first waits until every sender's arrival counter has
+// reached this rank's count of completed boundary launches, computes, stores each value a neighbour needs straight into
+// that neighbour's array (CSR over the local entities: almost always empty), and the last block to finish bumps the
+// expectations and ticks this rank's arrival counter on every receiver.  One launch per stage on the halo stream.
+template <class R>
+struct PushStage {
+    const int32_t *startE, *startC;        // CSR over local edges / cells into dst / slot (size nE + 1 / nC + 1)
+    const int32_t *dstE, *dstC;            // the entity's index in the receiver's arrays
+    const uint8_t *slotE, *slotC;          // which receiver
+    R *const *peerU, *const *peerH;        // per receiver: this stage's output arrays in its memory
+    unsigned long long *const *arrivalAt;  // per receiver: this rank's arrival counter there
+    int nrecv;
+    const int32_t *senders;                // ranks this one receives from
+    int nsend;
+    const unsigned long long *arrival;     // local arrival counters, indexed by sender rank
+    unsigned long long *expect;            // boundary launches completed so far, per sender rank
+    unsigned int *done;
+    int *error;
+    long long timeout_cycles;
+};
 
 template <class R>
 struct StageArgs {
@@ -68,6 +91,7 @@ struct StageArgs {
     R a, b;
     R f0;                    // uniform fEdge (FOLD = false): weights stay unfolded, (w*u)*f0 formed as the reference does;
                              // FOLD = true: wf already holds weightsOnEdge*fEdge[eoe] (variable f; differs by round-off)
+    const PushStage<R> *push;  // PUSH launches only (device memory); nullptr otherwise
 };
 
 // STAGE: 1 = first, 2 = middle (2 and 3), 4 = last.  S2/S: compile-time maxEdges2/maxEdges (0 = runtime).
@@ -78,7 +102,7 @@ struct StageArgs {
 // across the index reconstruction without spilling (4 blocks), Float32 fits in 48 (5 blocks) -- measured r01h:
 // F64 2.81 / 2.49 / 2.09 G cell-steps/s at 4 / 5 / 6 blocks, F32 3.62 / 4.05 / 3.83
 template <class R> constexpr int der_minblocks() { return sizeof(R) == 8 ? 4 : 5; }
-template <class R, int STAGE, int S2T, int ST, bool FOLD, bool DER>
+template <class R, int STAGE, int S2T, int ST, bool FOLD, bool DER, bool PUSH = false>
 __global__ void __launch_bounds__(kThreads, DER ? der_minblocks<R>() : MOKAB_MINBLOCKS)
 k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
 {
@@ -87,6 +111,23 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
     const int nE = A.nE, nC = A.nC;
     const int b = A.blockList ? A.blockList[blockIdx.x] : blockIdx.x;
     const int cBase = b * kTC;
+    if constexpr (PUSH) {
+#ifndef MOKAB_SIM   // (the simulated runtime cannot spin inside a kernel: the host enqueues the same predicate before the launch)
+        const PushStage<R> &P = *A.push;
+        if ((int)threadIdx.x < P.nsend) {
+            const int q = P.senders[threadIdx.x];
+            const long long t0 = clock64();
+            while (p2p::load_acquire_system(P.arrival + q) < P.expect[q]) {
+                if (clock64() - t0 > P.timeout_cycles) {
+                    atomicExch(P.error, 1);
+                    break;
+                }
+                __nanosleep(64);
+            }
+        }
+#endif
+        __syncthreads();
+    }
 
     constexpr bool kDer = DER && ST != 0 && S2T != 0;
     const bool derived = kDer && A.blkDerived && A.blkDerived[b];
@@ -160,6 +201,11 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
             if (STAGE != 4) A.uOut[e] = add_rn(cur, mul_rn(A.a, k));       // Provis = Curr + a*tend (time_integration.jl:124)
             if (STAGE == 1) A.uAcc[e] = add_rn(cur, mul_rn(A.b, k));       // New = Curr + b1*tend    (:108-110, :134)
             else            A.uAcc[e] = add_rn(accIn, mul_rn(A.b, k));     // New += b*tend           (:134)
+            if constexpr (PUSH) {   // this stage's output value, straight into the arrays of whoever holds this edge as a halo copy
+                const PushStage<R> &P = *A.push;
+                const R v = (STAGE != 4) ? add_rn(cur, mul_rn(A.a, k)) : add_rn(accIn, mul_rn(A.b, k));
+                for (int j = P.startE[e]; j < P.startE[e + 1]; ++j) P.peerU[P.slotE[j]][P.dstE[j]] = v;
+            }
             continue;
         }
         const int n = ld_stream(A.nEoE + e);
@@ -175,6 +221,11 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
         if (STAGE != 4) A.uOut[e] = add_rn(cur, mul_rn(A.a, k));       // Provis = Curr + a*tend (time_integration.jl:124)
         if (STAGE == 1) A.uAcc[e] = add_rn(cur, mul_rn(A.b, k));       // New = Curr + b1*tend    (:108-110, :134)
         else            A.uAcc[e] = add_rn(accIn, mul_rn(A.b, k));     // New += b*tend           (:134)
+        if constexpr (PUSH) {
+            const PushStage<R> &P = *A.push;
+            const R v = (STAGE != 4) ? add_rn(cur, mul_rn(A.a, k)) : add_rn(accIn, mul_rn(A.b, k));
+            for (int j = P.startE[e]; j < P.startE[e + 1]; ++j) P.peerU[P.slotE[j]][P.dstE[j]] = v;
+        }
     }
 
     // ---- cells of this block ----------------------------------------------------------------------------
@@ -223,6 +274,26 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
         if (STAGE != 4) A.hOut[cc] = add_rn(cur, mul_rn(A.a, k));
         if (STAGE == 1) A.hAcc[cc] = add_rn(cur, mul_rn(A.b, k));
         else            A.hAcc[cc] = add_rn(accIn, mul_rn(A.b, k));
+        if constexpr (PUSH) {
+            const PushStage<R> &P = *A.push;
+            const R v = (STAGE != 4) ? add_rn(cur, mul_rn(A.a, k)) : add_rn(accIn, mul_rn(A.b, k));
+            for (int j = P.startC[cc]; j < P.startC[cc + 1]; ++j) P.peerH[P.slotC[j]][P.dstC[j]] = v;
+        }
+    }
+    if constexpr (PUSH) {   // every storing thread fences, the last block to finish opens the next launch's gate and ticks the receivers
+        const PushStage<R> &P = *A.push;
+        p2p::fence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            p2p::fence_system();
+            const unsigned int ticket = p2p::add_device(P.done, 1u);
+            if (ticket == gridDim.x - 1) {
+                *P.done = 0u;
+                for (int i = 0; i < P.nsend; ++i) P.expect[P.senders[i]] += 1ull;
+                p2p::fence_system();
+                for (int i = 0; i < P.nrecv; ++i) p2p::add_system(P.arrivalAt[i], 1ull);
+            }
+        }
     }
 }
 

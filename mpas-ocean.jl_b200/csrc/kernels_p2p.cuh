@@ -113,5 +113,26 @@ k_halo_wait(int nsend, const int32_t *senders, const unsigned long long *arrival
     expect[q] += 1ull;
 }
 
+// The variant for launches that carry the exchange themselves (fused::k_rk_stage<..., PUSH>): those count their own
+// completions in `expect`, so "everything sent to me so far has arrived" is arrival >= expect, and nothing is bumped here.
+__global__ void __launch_bounds__(kMaxPeers)
+k_halo_wait_arrivals(int nsend, const int32_t *senders, const unsigned long long *arrival, const unsigned long long *expect, int *error,
+                     long long timeout_cycles)
+{
+#ifndef MOKAB_SIM
+    const int i = threadIdx.x;
+    if (i >= nsend) return;
+    const int q = senders[i];
+    const long long t0 = clock64();
+    while (load_acquire_system(arrival + q) < expect[q]) {
+        if (clock64() - t0 > timeout_cycles) {
+            atomicExch(error, 1);
+            break;
+        }
+        __nanosleep(64);
+    }
+#endif
+}
+
 }  // namespace p2p
 }  // namespace mokab

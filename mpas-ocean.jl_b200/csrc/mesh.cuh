@@ -352,6 +352,7 @@ struct mokab_mesh {
     bool uniformF = true; double f0 = 0.0;
     std::vector<int32_t> hBlkEdgeStart, hBlkInterior, hBlkBoundary;  // host copies (halo_setup re-classifies)
     mokab::DevBuf<int32_t> haloSend, haloRecv;  // combined [cells | edges] indices, device numbering
+    std::vector<int32_t> hHaloSend;             // host copy (the push tables of the direct-store exchange are built from it)
     bool halo_ready = false;
     // adjoint: transpose of the Coriolis stencil (built on first use)
     mokab::DevBuf<int32_t> eoeT;

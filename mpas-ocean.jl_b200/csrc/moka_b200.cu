@@ -114,6 +114,10 @@ struct mokab_state {
         mokab::DevBuf<unsigned long long *> arrivalAt;       // [nrecv]: this rank's slot in the receiver's arrival array
         std::vector<void *> opened;                          // cudaIpcOpenMemHandle mappings to close
         int64_t nPush = 0;
+        // the exchange folded into the boundary launch (fused::PushStage): CSR over the local entities + one descriptor per target
+        mokab::DevBuf<int32_t> startE, startC, dstE, dstC;
+        mokab::DevBuf<uint8_t> slotE, slotC;
+        mokab::DevBuf<unsigned char> stageDesc;              // 4 x fused::PushStage<R>
     } p2p;
     ~mokab_state()
     {
@@ -542,6 +546,11 @@ static void step_rk4_unfused(mokab_state *st, double dt)
     LAUNCH(ctx, k_update_ssh<double>, nblk(m->nC), 256, m->nC, (const double *)hNew, (const double *)m->H.p, t->ssh[c].p);
 }
 
+static int p2p_target(const mokab_state *st, int stage);
+#ifdef MOKAB_SIM
+static void p2p_gate_sim(mokab_state *st, cudaStream_t s);
+#endif
+
 // ---- fused RK4 ------------------------------------------------------------------------------------------------
 template <class R, int STAGE>
 static void launch_stage(mokab_ctx *ctx, const mokab_mesh *m, fused::StageArgs<R> A, int part = MOKAB_PART_ALL,
@@ -550,10 +559,21 @@ static void launch_stage(mokab_ctx *ctx, const mokab_mesh *m, fused::StageArgs<R
     int grid = m->fusedBlocks;
     A.blockList = nullptr;
     if (part == MOKAB_PART_INTERIOR) { grid = m->nInterior; A.blockList = m->blkInterior.p; }
-    if (part == MOKAB_PART_BOUNDARY) { grid = m->nBoundary; A.blockList = m->blkBoundary.p; }
+    if (part == MOKAB_PART_BOUNDARY || part == MOKAB_PART_BOUNDARY_PUSH) { grid = m->nBoundary; A.blockList = m->blkBoundary.p; }
     if (grid == 0) return;
     cudaStream_t s = stream ? stream : ctx->stream;
     const bool hex = m->S2 == 10 && m->S == 6;
+    if (part == MOKAB_PART_BOUNDARY_PUSH) {   // explicit edgesOnEdge: a boundary block reads halo rows, which cannot be rebuilt
+#define MOKAB_STAGE_PUSH(S2T, ST, FOLD) fused::k_rk_stage<R, STAGE, S2T, ST, FOLD, false, true><<<grid, fused::kThreads, 0, s>>>(A, m->S2, m->S)
+        if (hex && m->uniformF)      MOKAB_STAGE_PUSH(10, 6, false);
+        else if (hex)                MOKAB_STAGE_PUSH(10, 6, true);
+        else if (m->uniformF)        MOKAB_STAGE_PUSH(0, 0, false);
+        else                         MOKAB_STAGE_PUSH(0, 0, true);
+#undef MOKAB_STAGE_PUSH
+        MOKAB_CUDA(cudaGetLastError());
+        ctx->launches++;
+        return;
+    }
     const bool der = hex && m->nDerivedBlocks > 0;
 #define MOKAB_STAGE(S2T, ST, FOLD, DER) fused::k_rk_stage<R, STAGE, S2T, ST, FOLD, DER><<<grid, fused::kThreads, 0, s>>>(A, m->S2, m->S)
     if (der && m->uniformF)        MOKAB_STAGE(10, 6, false, true);
@@ -584,6 +604,7 @@ static fused::StageArgs<R> stage_args(mokab_state *st, double dt, int p, int sta
     const double b[4] = {dt / 6.0, dt / 3.0, dt / 3.0, dt / 6.0};       // time_integration.jl:78
     A.a = (R)a[stage - 1]; A.b = (R)b[stage - 1];
     A.f0 = (R)m->f0;
+    A.push = nullptr;
     switch (stage) {
     case 1: A.uOld = t->u[p].p;  A.hOld = t->h[p].p;  A.uOut = t->uP[0].p; A.hOut = t->hP[0].p; break;  // provisional == current
     case 2: A.uOld = t->uP[0].p; A.hOld = t->hP[0].p; A.uOut = t->uP[1].p; A.hOut = t->hP[1].p; break;
@@ -613,6 +634,15 @@ static void run_stage(mokab_state *st, double dt, int stage, int part, cudaStrea
     mokab_ctx *ctx = st->ctx; const mokab_mesh *m = st->mesh;
     ensure_fused<R>(const_cast<mokab_mesh *>(m));
     fused::StageArgs<R> A = stage_args<R>(st, dt, st->cur, stage);
+    if (part == MOKAB_PART_BOUNDARY_PUSH) {
+        MOKAB_REQUIRE(st->p2p.ready, "rk4_stage(MOKAB_PART_BOUNDARY_PUSH): call mokab_p2p_setup first");
+        MOKAB_REQUIRE(m->nBoundary > 0 || (st->p2p.recvRanks.empty() && st->p2p.sendRanks.empty()),
+                      "rk4_stage(MOKAB_PART_BOUNDARY_PUSH): a rank with neighbours has no boundary block");
+        A.push = (const fused::PushStage<R> *)st->p2p.stageDesc.p + p2p_target(st, stage);
+#ifdef MOKAB_SIM
+        p2p_gate_sim(st, stream ? stream : ctx->stream);
+#endif
+    }
     switch (stage) {
     case 1: launch_stage<R, 1>(ctx, m, A, part, stream); break;
     case 2: case 3: launch_stage<R, 2>(ctx, m, A, part, stream); break;
@@ -1052,6 +1082,45 @@ static void p2p_setup(mokab_state *st, int rank, int nranks, const P2PBlob *blob
     std::vector<int32_t> dst(dst_idx, dst_idx + total), snd(send_ranks, send_ranks + nsend);
     x.peerH.upload(pH, ctx->stream); x.peerU.upload(pU, ctx->stream); x.arrivalAt.upload(arr, ctx->stream);
     x.slot.upload(slot, ctx->stream); x.dst.upload(dst, ctx->stream); x.senders.upload(snd, ctx->stream);
+    // the same list, entity-major, for the boundary launch that pushes what it has just computed
+    {
+        const int64_t nC = m->nC, nE = m->nE;
+        std::vector<int32_t> sE(nE + 1, 0), sC(nC + 1, 0);
+        for (int64_t k = 0; k < total; ++k) {
+            const int32_t i = m->hHaloSend[k];
+            if (i < nC) sC[i + 1]++; else sE[i - nC + 1]++;
+        }
+        for (int64_t i = 0; i < nC; ++i) sC[i + 1] += sC[i];
+        for (int64_t i = 0; i < nE; ++i) sE[i + 1] += sE[i];
+        std::vector<int32_t> dE(std::max<int64_t>(sE[nE], 1)), dC(std::max<int64_t>(sC[nC], 1)), fillE(sE.begin(), sE.end() - 1), fillC(sC.begin(), sC.end() - 1);
+        std::vector<uint8_t> lE(dE.size()), lC(dC.size());
+        for (int64_t k = 0; k < total; ++k) {
+            const int32_t i = m->hHaloSend[k], d = dst[k];
+            if (i < nC) {
+                MOKAB_REQUIRE(d >= 0, "p2p_setup: a cell is sent to an edge slot");
+                const int32_t at = fillC[i]++;
+                dC[at] = d; lC[at] = slot[k];
+            } else {
+                MOKAB_REQUIRE(d < 0, "p2p_setup: an edge is sent to a cell slot");
+                const int32_t at = fillE[i - nC]++;
+                dE[at] = -d - 1; lE[at] = slot[k];
+            }
+        }
+        x.startE.upload(sE, ctx->stream); x.startC.upload(sC, ctx->stream);
+        x.dstE.upload(dE, ctx->stream); x.dstC.upload(dC, ctx->stream);
+        x.slotE.upload(lE, ctx->stream); x.slotC.upload(lC, ctx->stream);
+        std::vector<unsigned char> desc(4 * sizeof(fused::PushStage<R>));
+        for (int tgt = 0; tgt < 4; ++tgt) {
+            fused::PushStage<R> P;
+            P.startE = x.startE.p; P.startC = x.startC.p; P.dstE = x.dstE.p; P.dstC = x.dstC.p; P.slotE = x.slotE.p; P.slotC = x.slotC.p;
+            P.peerU = (R *const *)x.peerU.p + (size_t)tgt * nrecv; P.peerH = (R *const *)x.peerH.p + (size_t)tgt * nrecv;
+            P.arrivalAt = (unsigned long long *const *)x.arrivalAt.p; P.nrecv = nrecv;
+            P.senders = x.senders.p; P.nsend = nsend; P.arrival = x.arrival; P.expect = x.expect.p;
+            P.done = x.done.p; P.error = x.error.p; P.timeout_cycles = 4000000000ll;
+            memcpy(desc.data() + tgt * sizeof(P), &P, sizeof(P));
+        }
+        x.stageDesc.upload(desc, ctx->stream);
+    }
     MOKAB_CUDA(cudaStreamSynchronize(ctx->stream));
     x.ready = true;
 }
@@ -1089,6 +1158,40 @@ static void p2p_push(mokab_state *st, int stage, cudaStream_t stream)
         p2p::k_halo_push<R><<<nblk(A.n), 256, 0, s>>>(A);
     }
     MOKAB_CUDA(cudaGetLastError());
+    ctx->launches++;
+}
+
+#ifdef MOKAB_SIM
+// the gate a PUSH launch spins in on hardware, as a stream operation of the simulated runtime
+static void p2p_gate_sim(mokab_state *st, cudaStream_t s)
+{
+    mokab_state::P2P &x = st->p2p;
+    const int nsend = (int)x.sendRanks.size();
+    if (nsend == 0) return;
+    const int32_t *senders = x.senders.p;
+    const unsigned long long *arrival = x.arrival, *expect = x.expect.p;
+    mokab_sim::enqueue_try(s, "p2p gate (arrival >= expect)", [=]() {
+        for (int i = 0; i < nsend; ++i)
+            if (arrival[senders[i]] < expect[senders[i]]) return false;
+        return true;
+    });
+}
+#endif
+
+static void p2p_wait_arrivals(mokab_state *st, cudaStream_t stream)
+{
+    mokab_ctx *ctx = st->ctx;
+    mokab_state::P2P &x = st->p2p;
+    const int nsend = (int)x.sendRanks.size();
+    if (nsend == 0) return;
+    cudaStream_t s = stream ? stream : ctx->stream;
+#ifdef MOKAB_SIM
+    p2p_gate_sim(st, s);
+#else
+    p2p::k_halo_wait_arrivals<<<1, p2p::kMaxPeers, 0, s>>>(nsend, (const int32_t *)x.senders.p, (const unsigned long long *)x.arrival,
+                                                            (const unsigned long long *)x.expect.p, x.error.p, 4000000000ll);
+    MOKAB_CUDA(cudaGetLastError());
+#endif
     ctx->launches++;
 }
 
@@ -1658,6 +1761,7 @@ int mokab_halo_setup(mokab_mesh *m, int64_t n_send, const int32_t *send_idx, int
         m->blkInterior.upload(m->hBlkInterior, st); m->blkBoundary.upload(m->hBlkBoundary, st);
         m->nInterior = (int)m->hBlkInterior.size(); m->nBoundary = (int)m->hBlkBoundary.size();
         m->haloSend.upload(s, st);
+        m->hHaloSend = s;
         m->haloRecv.upload(r, st);
         MOKAB_CUDA(cudaStreamSynchronize(st));
         m->halo_ready = true;
@@ -1693,7 +1797,7 @@ int mokab_rk4_stage(mokab_state *state, double dt, int stage, int part, void *cu
     return guarded([&] {
         MOKAB_REQUIRE(state, "rk4_stage: state is NULL");
         MOKAB_REQUIRE(stage >= 1 && stage <= 4, "rk4_stage: stage must be 1..4");
-        MOKAB_REQUIRE(part >= MOKAB_PART_ALL && part <= MOKAB_PART_BOUNDARY, "rk4_stage: unknown part");
+        MOKAB_REQUIRE(part >= MOKAB_PART_ALL && part <= MOKAB_PART_BOUNDARY_PUSH, "rk4_stage: unknown part");
         state->ctx->bind();
         if (state->dtype == MOKAB_F64) run_stage<double>(state, dt, stage, part, (cudaStream_t)cuda_stream);
         else run_stage<float>(state, dt, stage, part, (cudaStream_t)cuda_stream);
@@ -1782,6 +1886,15 @@ int mokab_halo_wait(mokab_state *state, void *cuda_stream)
         MOKAB_REQUIRE(state && state->p2p.ready, "halo_wait: call mokab_p2p_setup first");
         state->ctx->bind();
         p2p_wait(state, (cudaStream_t)cuda_stream);
+    });
+}
+
+int mokab_halo_wait_arrivals(mokab_state *state, void *cuda_stream)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(state && state->p2p.ready, "halo_wait_arrivals: call mokab_p2p_setup first");
+        state->ctx->bind();
+        p2p_wait_arrivals(state, (cudaStream_t)cuda_stream);
     });
 }
 

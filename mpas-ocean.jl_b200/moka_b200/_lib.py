@@ -18,7 +18,7 @@ F64, F32 = 0, 1
 SUM_SSH2, SUM_MASS, SUM_ENERGY = range(3)
 CELLS, EDGES, VERTICES = range(3)
 RK4_FUSED, RK4_UNFUSED = 0, 1
-PART_ALL, PART_INTERIOR, PART_BOUNDARY = 0, 1, 2
+PART_ALL, PART_INTERIOR, PART_BOUNDARY, PART_BOUNDARY_PUSH = 0, 1, 2, 3
 MESH_RENUMBER, MESH_EXPLICIT_EOE, MESH_KEEP_WIDTHS = 1, 2, 4
 
 _I32P, _F64P = C.POINTER(C.c_int32), C.POINTER(C.c_double)
@@ -61,7 +61,7 @@ SYMBOLS = [
     "mokab_halo_setup", "mokab_halo_pack", "mokab_halo_unpack", "mokab_rk4_stage", "mokab_rk4_finish_step",
     "mokab_refresh_ssh", "mokab_mesh_block_counts", "mokab_mesh_derived_blocks",
     "mokab_halo_recv_device_indices", "mokab_p2p_blob_size", "mokab_p2p_export", "mokab_p2p_setup", "mokab_halo_push",
-    "mokab_halo_wait", "mokab_p2p_error",
+    "mokab_halo_wait", "mokab_halo_wait_arrivals", "mokab_p2p_error",
 ]
 
 
@@ -99,7 +99,7 @@ def bind(L):
         "mokab_halo_recv_device_indices": [vp, _I32P], "mokab_p2p_blob_size": [C.POINTER(i64)],
         "mokab_p2p_export": [vp, C.c_int, vp],
         "mokab_p2p_setup": [vp, C.c_int, C.c_int, vp, C.c_int, _I32P, C.POINTER(i64), _I32P, C.c_int, _I32P],
-        "mokab_halo_push": [vp, C.c_int, vp], "mokab_halo_wait": [vp, vp], "mokab_p2p_error": [vp, C.POINTER(C.c_int)],
+        "mokab_halo_push": [vp, C.c_int, vp], "mokab_halo_wait": [vp, vp], "mokab_halo_wait_arrivals": [vp, vp], "mokab_p2p_error": [vp, C.POINTER(C.c_int)],
     }
     for name, args in sig.items():
         fn = getattr(L, name)

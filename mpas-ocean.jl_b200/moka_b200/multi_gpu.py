@@ -128,8 +128,9 @@ class DecomposedModel:
 
     def __init__(self, loc: dict, state, backend: api.B200, device_index: int, dtype=np.float64, group=None, overlap=True,
                  graph=False, runtime=None, halo="nccl"):
-        if halo not in ("nccl", "p2p"):
-            raise api.MokaError("DecomposedModel: halo must be 'nccl' (packed all-to-all) or 'p2p' (direct peer stores)")
+        if halo not in ("nccl", "p2p", "p2p_fused"):
+            raise api.MokaError("DecomposedModel: halo must be 'nccl' (packed all-to-all), 'p2p' (direct peer stores, push and wait "
+                                "kernels) or 'p2p_fused' (direct peer stores from inside the boundary launch)")
         self.halo_mode = halo
         self.rt = runtime if runtime is not None else TorchRuntime(device_index, group)
         self.cuda = self.rt.cuda
@@ -152,7 +153,7 @@ class DecomposedModel:
         self._graph, self._graph_dt = None, None
         self._validated, self.graph_status = False, "not used"
         self._parity, self._graph_parity = 0, 0                  # steps taken so far mod 2; the same at graph capture
-        if halo == "p2p":
+        if halo != "nccl":
             self._setup_p2p(scnt, rcnt)
 
     def _setup_p2p(self, scnt, rcnt) -> None:
@@ -194,28 +195,42 @@ class DecomposedModel:
             self.ex.exchange()
             L.check(lib.mokab_halo_unpack(self.handle, s, C.c_void_p(self.ex.recv.data_ptr()), C.c_void_p(stream.cuda_stream)))
 
+    def _wait_arrivals(self, stream) -> None:
+        L.check(L.lib().mokab_halo_wait_arrivals(self.handle, C.c_void_p(stream.cuda_stream)))
+
     def _enqueue_steps(self, dt: float, nsteps: int) -> None:
         """Enqueue `nsteps` RK4 steps; on entry and exit both streams are joined on `compute`."""
         cuda = self.cuda
+        fused = self.halo_mode == "p2p_fused"                    # the boundary launch carries the exchange itself
+        boundary = L.PART_BOUNDARY_PUSH if fused else L.PART_BOUNDARY
         if not self.overlap:
             for _ in range(nsteps):
                 for s in (1, 2, 3, 4):
-                    self._stage(dt, s, L.PART_ALL, self.compute)
-                    self._exchange(s, self.compute)
+                    if fused:
+                        self._stage(dt, s, boundary, self.compute)
+                        self._stage(dt, s, L.PART_INTERIOR, self.compute)
+                    else:
+                        self._stage(dt, s, L.PART_ALL, self.compute)
+                        self._exchange(s, self.compute)
                 L.check(L.lib().mokab_rk4_finish_step(self.handle))
+            if fused:
+                self._wait_arrivals(self.compute)
             return
         self.halo.wait_stream(self.compute)                      # fork
         for _ in range(nsteps):
             for s in (1, 2, 3, 4):
                 ev_i, ev_b = cuda.Event(), cuda.Event()
-                self._stage(dt, s, L.PART_BOUNDARY, self.halo)
+                self._stage(dt, s, boundary, self.halo)
                 ev_b.record(self.halo)
                 self._stage(dt, s, L.PART_INTERIOR, self.compute)
                 ev_i.record(self.compute)
-                self._exchange(s, self.halo)
+                if not fused:
+                    self._exchange(s, self.halo)
                 self.compute.wait_event(ev_b)                    # stage s+1 interior reads stage s boundary output
                 self.halo.wait_event(ev_i)                       # stage s+1 boundary reads stage s interior output
             L.check(L.lib().mokab_rk4_finish_step(self.handle))
+        if fused:
+            self._wait_arrivals(self.halo)                       # the neighbours' last stores, before anything else touches the halo slots
         self.compute.wait_stream(self.halo)                      # join
 
     def _build_graph(self, dt: float) -> None:
@@ -295,7 +310,7 @@ class DecomposedModel:
         self.refresh_ssh()
         self.compute.synchronize()
         self.halo.synchronize()
-        if self.halo_mode == "p2p":
+        if self.halo_mode != "nccl":
             err = C.c_int()
             L.check(L.lib().mokab_p2p_error(self.handle, C.byref(err)))
             if err.value:
@@ -473,7 +488,7 @@ def bench_main(args, rank, world, local):
                                     else f"inertial gravity wave, {nx}x{nx} periodic planar hex mesh") + f" ({nC_glob} cells), "
                                    f"{'Float64' if args.dtype == 'f64' else 'Float32'} RK4, dt={dt:.4g}s, recursive-coordinate-bisection "
                                    f"into {world} parts, 1 halo layer, "
-                                   f"{'NCCL all-to-all' if model.halo_mode == 'nccl' else 'direct peer stores + arrival counters'} per stage "
+                                   f"{ {'nccl': 'NCCL all-to-all', 'p2p': 'direct peer stores + arrival counters (push / wait kernels)', 'p2p_fused': 'direct peer stores from inside the boundary launch'}[model.halo_mode]} per stage "
                                    f"{'overlapped with interior blocks' if model.overlap else '(no overlap)'}"
                                    f"{', 2-step CUDA graph incl. the exchange (' + model.graph_status + ')' if model.use_graph else ', CUDA graph ' + model.graph_status}",
                        "name": args.workload, "l2": "inputs larger than L2 (no flush)", "setup_s": round(t_setup, 1),

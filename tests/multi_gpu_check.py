@@ -31,7 +31,7 @@ def main():
     # (csrc/kernels_p2p.cuh -- checked on the simulated runtime only so far, so it is not part of the default run yet)
     cases = [(True, False, "nccl"), (False, False, "nccl"), (True, True, "nccl")]
     if os.environ.get("MOKAB_CHECK_P2P", "0") == "1":
-        cases += [(True, False, "p2p"), (True, True, "p2p")]
+        cases += [(True, False, "p2p"), (True, True, "p2p"), (True, False, "p2p_fused"), (True, True, "p2p_fused")]
     for overlap, graph, halo in cases:
         model = multi_gpu.DecomposedModel(loc, multi_gpu.local_state(loc, *state), backend, local, overlap=overlap, graph=graph, halo=halo)
         model.step(dt, nsteps)

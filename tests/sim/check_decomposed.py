@@ -183,14 +183,18 @@ def main():
     ap.add_argument("--cases", default="small")
     ap.add_argument("--policies", default="fifo,lazy,others_first,random")
     ap.add_argument("--seeds", type=int, default=2)
-    ap.add_argument("--halo", default="nccl,p2p", help="halo exchange paths to check: the packed all-to-all and/or the direct peer stores")
+    ap.add_argument("--halo", default="nccl,p2p,p2p_fused",
+                    help="halo exchange paths to check: the packed all-to-all, the direct peer stores (push / wait kernels), the "
+                         "direct peer stores from inside the boundary launch")
     ap.add_argument("--mutations", action="store_true", help="check that removing a cross-stream dependency of the schedule is detected")
     args = ap.parse_args()
     if args.mutations:
         run_mutations()
     # (kind, nx, ranks, step calls): 96x96 over 8 ranks is the decomposition on which the B200 run exposed the ordering
     # bug (every block a boundary block, a partly filled last block); [3, 6, 1, 4] replays the graph from both parities
-    cases = [("igw", 32, 2, [6]), ("igw", 96, 8, [6]), ("igw", 48, 4, [3, 6, 1, 4]), ("kelvin", 48, 4, [5, 4])]
+    cases = [("igw", 96, 8, [6]), ("igw", 48, 4, [3, 6, 1, 4]), ("kelvin", 48, 4, [5, 4])]
+    if args.cases != "suite":
+        cases += [("igw", 32, 2, [6]), ("igw", 128, 2, [3])]                 # 128 / 2: most blocks are interior
     if args.cases == "all":
         cases += [("igw", 64, 3, [7, 2]), ("igw", 128, 8, [4]), ("kelvin", 64, 8, [6])]
     bad = 0
@@ -208,7 +212,7 @@ def main():
                         print(f"{kind}{nx} ranks={P} steps={calls} {halo} {policy}{'/' + str(seed) if policy == 'random' else ''} "
                               f"{'overlap' if overlap else 'serial'} {'graph' if graph else 'stream'}: {'OK' if ok else 'MISMATCH'}"
                               f"{' [' + status + ']' if graph else ''} {time.time() - t0:.1f}s", flush=True)
-    for halo in args.halo.split(","):
+    for halo in (args.halo.split(",") if args.cases != "suite" else []):
         ok, _ = run("igw", 48, 4, [4, 3], True, True, "random", 7, dtype=np.float32, halo=halo)
         bad += not ok
         print(f"igw48 ranks=4 Float32 {halo} random/7 overlap graph: {'OK' if ok else 'MISMATCH'}", flush=True)

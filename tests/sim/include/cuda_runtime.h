@@ -135,7 +135,8 @@ void enqueue_kernel(cudaStream_t s, unsigned grid, unsigned block, bool coop, co
 
 static inline bool is_coop_name(const char *kernel)
 {
-    return __builtin_strstr(kernel, "reduce::k_") != nullptr || __builtin_strstr(kernel, "k_halo_push") != nullptr;
+    return __builtin_strstr(kernel, "reduce::k_") != nullptr || __builtin_strstr(kernel, "k_halo_push") != nullptr ||
+           (__builtin_strstr(kernel, "k_rk_stage") != nullptr && __builtin_strstr(kernel, ", true>") != nullptr);   // the PUSH variant
 }
 // a device-side wait on memory that another stream (or rank) writes: retried by the scheduler until `ready` returns true
 void enqueue_try(cudaStream_t s, const char *name, std::function<bool()> ready);

@@ -69,8 +69,18 @@ def _run_emulated(backend, m, state, nparts, dt, nsteps, split_parts=True, dtype
     locs = partition.decompose(m, nparts)
     ranks = [_Rank(backend, loc, state, nparts, dtype) for loc in locs]
     lib = L.lib()
-    if halo == "p2p":
+    if halo != "nccl":
         _setup_p2p(ranks, nparts)
+    for _ in range(nsteps if halo == "p2p_fused" else 0):
+        for s in (1, 2, 3, 4):                   # the boundary launch waits, computes, stores into the neighbours and ticks them
+            for r in ranks:
+                L.check(lib.mokab_rk4_stage(r.h, dt, s, L.PART_BOUNDARY_PUSH, None))
+                L.check(lib.mokab_rk4_stage(r.h, dt, s, L.PART_INTERIOR, None))
+        for r in ranks:
+            L.check(lib.mokab_rk4_finish_step(r.h))
+    if halo == "p2p_fused":
+        for r in ranks:
+            L.check(lib.mokab_halo_wait_arrivals(r.h, None))
     for _ in range(nsteps if halo == "p2p" else 0):
         for s in (1, 2, 3, 4):
             for r in ranks:                      # every rank's stores (and arrival ticks) are enqueued before anybody waits
@@ -82,7 +92,7 @@ def _run_emulated(backend, m, state, nparts, dt, nsteps, split_parts=True, dtype
                 L.check(lib.mokab_halo_wait(r.h, None))
         for r in ranks:
             L.check(lib.mokab_rk4_finish_step(r.h))
-    for _ in range(0 if halo == "p2p" else nsteps):
+    for _ in range(nsteps if halo == "nccl" else 0):
         for s in (1, 2, 3, 4):
             for r in ranks:
                 if split_parts:
@@ -107,7 +117,7 @@ def _run_emulated(backend, m, state, nparts, dt, nsteps, split_parts=True, dtype
             L.check(lib.mokab_rk4_finish_step(r.h))
     gu, gh, gs = np.full(m["nEdges"], np.nan), np.full(m["nCells"], np.nan), np.full(m["nCells"], np.nan)
     for r in ranks:
-        if halo == "p2p":
+        if halo != "nccl":
             err = C.c_int(1)
             L.check(lib.mokab_p2p_error(r.h, C.byref(err)))
             assert err.value == 0, "a halo wait timed out"
@@ -159,6 +169,9 @@ def test_direct_store_halo_exchange_matches_the_packed_one(backend, nx, nparts, 
     gu0, gh0, gs0, _ = _run_emulated(backend, m, state, nparts, dt, 7, split_parts=split, dtype=dtype)
     gu1, gh1, gs1, _ = _run_emulated(backend, m, state, nparts, dt, 7, split_parts=split, dtype=dtype, halo="p2p")
     assert np.array_equal(gu0, gu1) and np.array_equal(gh0, gh1) and np.array_equal(gs0, gs1)
+    if split:                                    # and with the exchange folded into the boundary launch
+        gu2, gh2, gs2, _ = _run_emulated(backend, m, state, nparts, dt, 7, dtype=dtype, halo="p2p_fused")
+        assert np.array_equal(gu0, gu2) and np.array_equal(gh0, gh2) and np.array_equal(gs0, gs2)
     if dtype == np.float64:
         om = OC.OracleModel(m, *state)
         om.run_loop(dt, 7, "RungeKutta4")

@@ -137,7 +137,7 @@ def test_gpu_tests_pass_on_the_simulated_runtime(policy):
 
 
 def test_decomposed_model_with_emulated_ranks_is_exact_under_every_interleaving():
-    rc, tail = _run([sys.executable, os.path.join(SIM, "check_decomposed.py"), "--seeds", "1", "--policies", "lazy,others_first"])
+    rc, tail = _run([sys.executable, os.path.join(SIM, "check_decomposed.py"), "--cases", "suite", "--seeds", "1", "--policies", "lazy,others_first"])
     assert rc == 0 and "SIM_DECOMPOSED_OK" in tail, tail
 
 
