@@ -39,12 +39,20 @@ def case(kind, nx):
             m = mb.channel_hex(nx, nx, 1.0e7 / nx)
             state = mb.kelvinWave(m).initial_state()
             mo = OC.apply_boundary_mask(m)       # the oracle masks in its mesh preprocessing, the library at upload
+        elif kind == "voronoi":              # pentagons / hexagons / heptagons: run-time row widths, irregular cell graph
+            from moka_b200.planar_voronoi import periodic_voronoi
+            m = periodic_voronoi(nx, nx, 1.0e7 / nx, jitter=0.3, seed=2)
+            m = {k: v for k, v in m.items() if k not in ("edgesOnVertex", "cellsOnVertex", "verticesOnEdge", "kiteAreasOnVertex",
+                                                         "areaTriangle", "verticesOnCell")}
+            m["nVertices"] = 0               # decomposed meshes carry no vertex arrays
+            state = mb.inertialGravityWave(m).initial_state()
+            mo = m
         else:
             m = mb.periodic_hex(nx, nx, 1.0e7 / nx, with_dual=False)
             state = mb.inertialGravityWave(m).initial_state()
             mo = m
         OC.sign_index_fields(mo)
-        _CASES[(kind, nx)] = (m, mo, state, mb.cfl_dt(m["dc"]))
+        _CASES[(kind, nx)] = (m, mo, state, (0.25 if kind == "voronoi" else 1.0) * mb.cfl_dt(m["dc"]))
     return _CASES[(kind, nx)]
 
 
@@ -194,7 +202,7 @@ def main():
     # bug (every block a boundary block, a partly filled last block); [3, 6, 1, 4] replays the graph from both parities
     cases = [("igw", 96, 8, [6]), ("igw", 48, 4, [3, 6, 1, 4]), ("kelvin", 48, 4, [5, 4])]
     if args.cases != "suite":
-        cases += [("igw", 32, 2, [6]), ("igw", 128, 2, [3])]                 # 128 / 2: most blocks are interior
+        cases += [("igw", 32, 2, [6]), ("igw", 128, 2, [3]), ("voronoi", 24, 4, [5])]     # 128 / 2: most blocks are interior
     if args.cases == "all":
         cases += [("igw", 64, 3, [7, 2]), ("igw", 128, 8, [4]), ("kelvin", 64, 8, [6])]
     bad = 0
