@@ -279,6 +279,9 @@ int  mokab_halo_wait(mokab_state *state, void *cuda_stream);
 /* With MOKAB_PART_BOUNDARY_PUSH launches there is nothing else to call per stage; after the LAST stage enqueued (before the
  * host, an upload or anything else touches the halo slots) this waits until the neighbours' last stores have arrived. */
 int  mokab_halo_wait_arrivals(mokab_state *state, void *cuda_stream);
+/* Unmap the peers' memory (every rank, after the last step and before any rank destroys its state: a mapping must not
+ * outlive the allocation it maps).  The state is usable again after another mokab_p2p_setup. */
+int  mokab_p2p_close(mokab_state *state);
 /* 1 if a wait ever timed out (~2 s: a peer died or the ranks' schedules diverged); the GPU is never left spinning */
 int  mokab_p2p_error(mokab_state *state, int *out);
 /* number of interior / boundary blocks of the fused kernel (diagnostic) */

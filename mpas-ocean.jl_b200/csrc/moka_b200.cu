@@ -1898,6 +1898,18 @@ int mokab_halo_wait_arrivals(mokab_state *state, void *cuda_stream)
     });
 }
 
+int mokab_p2p_close(mokab_state *state)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(state, "p2p_close: state is NULL");
+        state->ctx->bind();
+        MOKAB_CUDA(cudaStreamSynchronize(state->ctx->stream));
+        for (void *q : state->p2p.opened) MOKAB_CUDA(cudaIpcCloseMemHandle(q));
+        state->p2p.opened.clear();
+        state->p2p.ready = false;
+    });
+}
+
 int mokab_p2p_error(mokab_state *state, int *out)
 {
     return guarded([&] {

@@ -61,7 +61,7 @@ SYMBOLS = [
     "mokab_halo_setup", "mokab_halo_pack", "mokab_halo_unpack", "mokab_rk4_stage", "mokab_rk4_finish_step",
     "mokab_refresh_ssh", "mokab_mesh_block_counts", "mokab_mesh_derived_blocks",
     "mokab_halo_recv_device_indices", "mokab_p2p_blob_size", "mokab_p2p_export", "mokab_p2p_setup", "mokab_halo_push",
-    "mokab_halo_wait", "mokab_halo_wait_arrivals", "mokab_p2p_error",
+    "mokab_halo_wait", "mokab_halo_wait_arrivals", "mokab_p2p_error", "mokab_p2p_close",
 ]
 
 
@@ -99,7 +99,7 @@ def bind(L):
         "mokab_halo_recv_device_indices": [vp, _I32P], "mokab_p2p_blob_size": [C.POINTER(i64)],
         "mokab_p2p_export": [vp, C.c_int, vp],
         "mokab_p2p_setup": [vp, C.c_int, C.c_int, vp, C.c_int, _I32P, C.POINTER(i64), _I32P, C.c_int, _I32P],
-        "mokab_halo_push": [vp, C.c_int, vp], "mokab_halo_wait": [vp, vp], "mokab_halo_wait_arrivals": [vp, vp], "mokab_p2p_error": [vp, C.POINTER(C.c_int)],
+        "mokab_halo_push": [vp, C.c_int, vp], "mokab_halo_wait": [vp, vp], "mokab_halo_wait_arrivals": [vp, vp], "mokab_p2p_error": [vp, C.POINTER(C.c_int)], "mokab_p2p_close": [vp],
     }
     for name, args in sig.items():
         fn = getattr(L, name)

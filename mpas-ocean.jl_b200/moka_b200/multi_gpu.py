@@ -321,6 +321,10 @@ class DecomposedModel:
         it is alive) and drain both streams."""
         self.compute.synchronize()
         self.halo.synchronize()
+        if self.halo_mode != "nccl":                             # nobody unmaps while a neighbour may still store, nobody frees while mapped
+            self.rt.all_reduce_min(1)
+            L.check(L.lib().mokab_p2p_close(self.handle))
+            self.rt.all_reduce_min(1)
         self.backend.set_stream(None)                            # the context goes back to its own stream
         self._graph = None
         import gc

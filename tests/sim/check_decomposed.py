@@ -147,8 +147,8 @@ def run_e2e(kind, nx, nparts, iters, policy, seed, halo):
 
 def run_mutations():
     """Does this checker have teeth?  Re-run one case with each of the schedule's two cross-stream events removed
-    (DecomposedModel._enqueue_steps: interior(s+1) after boundary(s), boundary(s+1) after interior(s)): the synchronous
-    order (FIFO) must still pass -- the bug is a race, as on hardware -- and the adversarial orders must catch it."""
+    (DecomposedModel._enqueue_steps: interior(s+1) after boundary(s), boundary(s+1) after interior(s)): the intact schedule
+    passes under every policy, and LAZY must catch each removal (the other policies may or may not -- the bug is a race)."""
     from moka_b200 import _lib as L
 
     def variant(drop):
@@ -177,9 +177,12 @@ def run_mutations():
         for drop in (None, "ev_b", "ev_i"):
             multi_gpu.DecomposedModel._enqueue_steps = variant(drop)
             got = {pol: run("igw", 128, 2, [3], True, False, pol, 2)[0] for pol in ("fifo", "lazy", "others_first")}
-            want = {"fifo": True, "lazy": drop is None, "others_first": drop is None}
-            bad += got != want
-            print(f"schedule without {drop or 'nothing'}: {got} {'as expected' if got == want else 'UNEXPECTED'}", flush=True)
+            # LAZY is deterministic about a missing wait (the producer has not run).  What FIFO and OTHERS_FIRST make of it depends
+            # on how far the other rank's host thread has got (a stream parked in a collective delays what is queued behind
+            # it), as on hardware: they are reported, and only have to pass on the intact schedule
+            ok = all(got.values()) if drop is None else not got["lazy"]
+            bad += not ok
+            print(f"schedule without {drop or 'nothing'}: {got} {'as expected' if ok else 'UNEXPECTED'}", flush=True)
     finally:
         multi_gpu.DecomposedModel._enqueue_steps = original
     print("SIM_MUTATIONS_DETECTED" if bad == 0 else "SIM_MUTATIONS_MISSED", flush=True)
