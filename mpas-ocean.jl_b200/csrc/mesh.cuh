@@ -295,7 +295,8 @@ static void build_host_mesh(const mokab_mesh_desc &d, uint32_t flags, HostMesh &
     // reading the explicit array (MOKAB_MESH_EXPLICIT_EOE forces that everywhere).
     m.posE.assign(nE, 0);
     m.blkDerived.assign(nb, 0);
-    if (!(flags & MOKAB_MESH_EXPLICIT_EOE) && S == 6 && S2 == 10) {  // the rebuild lives in the compile-time-width kernel
+    // the rebuild lives in the compile-time-width kernels: (10, 6) hexagon meshes and (12, 7) meshes that mix in heptagons
+    if (!(flags & MOKAB_MESH_EXPLICIT_EOE) && ((S == 6 && S2 == 10) || (S == 7 && S2 == 12))) {
 #pragma omp parallel for schedule(static)
         for (int b = 0; b < nb; ++b) {
             bool ok = true;

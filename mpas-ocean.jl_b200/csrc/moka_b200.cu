@@ -563,6 +563,7 @@ static void launch_stage(mokab_ctx *ctx, const mokab_mesh *m, fused::StageArgs<R
     if (grid == 0) return;
     cudaStream_t s = stream ? stream : ctx->stream;
     const bool hex = m->S2 == 10 && m->S == 6;
+    const bool hept = m->S2 == 12 && m->S == 7;   // pentagons / hexagons / heptagons (quasi-uniform MPAS meshes): rows padded to 12 / 7
     if (part == MOKAB_PART_BOUNDARY_PUSH) {   // explicit edgesOnEdge: a boundary block reads halo rows, which cannot be rebuilt
 #define MOKAB_STAGE_PUSH(S2T, ST, FOLD) fused::k_rk_stage<R, STAGE, S2T, ST, FOLD, false, true><<<grid, fused::kThreads, 0, s>>>(A, m->S2, m->S)
         if (hex && m->uniformF)      MOKAB_STAGE_PUSH(10, 6, false);
@@ -574,12 +575,16 @@ static void launch_stage(mokab_ctx *ctx, const mokab_mesh *m, fused::StageArgs<R
         ctx->launches++;
         return;
     }
-    const bool der = hex && m->nDerivedBlocks > 0;
+    const bool der = (hex || hept) && m->nDerivedBlocks > 0;
 #define MOKAB_STAGE(S2T, ST, FOLD, DER) fused::k_rk_stage<R, STAGE, S2T, ST, FOLD, DER><<<grid, fused::kThreads, 0, s>>>(A, m->S2, m->S)
-    if (der && m->uniformF)        MOKAB_STAGE(10, 6, false, true);
-    else if (der)                  MOKAB_STAGE(10, 6, true, true);
-    else if (hex && m->uniformF)   MOKAB_STAGE(10, 6, false, false);
-    else if (hex)                  MOKAB_STAGE(10, 6, true, false);
+    if (hex && der && m->uniformF)  MOKAB_STAGE(10, 6, false, true);
+    else if (hex && der)            MOKAB_STAGE(10, 6, true, true);
+    else if (hex && m->uniformF)    MOKAB_STAGE(10, 6, false, false);
+    else if (hex)                   MOKAB_STAGE(10, 6, true, false);
+    else if (hept && der && m->uniformF) MOKAB_STAGE(12, 7, false, true);
+    else if (hept && der)           MOKAB_STAGE(12, 7, true, true);
+    else if (hept && m->uniformF)   MOKAB_STAGE(12, 7, false, false);
+    else if (hept)                  MOKAB_STAGE(12, 7, true, false);
     else if (m->uniformF)          MOKAB_STAGE(0, 0, false, false);
     else                           MOKAB_STAGE(0, 0, true, false);
 #undef MOKAB_STAGE

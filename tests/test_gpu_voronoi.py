@@ -30,7 +30,9 @@ def case():
 def test_rk4_and_forward_euler_bit_exact_on_a_voronoi_mesh(backend, case, renumber):
     m, ssh, u, h, dt = case
     mesh = mb.Mesh(m, backend, renumber=renumber)
-    assert mesh.derived_blocks()[1] == 0                          # the edgesOnEdge rebuild is a hexagon specialisation
+    assert (mesh.maxEdges, mesh.maxEdges2) == (7, 12)             # the compile-time (12, 7) kernels; rows of 8..12 / 5..7 live entries
+    nblk, nder = mesh.derived_blocks()
+    assert nder == nblk > 0                                       # the generator follows the MPAS edgesOnEdge ordering: rebuilt everywhere
     prog = mb.PrognosticVars(ssh, u, h, 2, mesh)
     mass0 = mb.reduce_sum(prog, "mass")
     mb.ocn_timestep(dt, prog, None, None, None, mb.RungeKutta4, nsteps=25)
@@ -42,6 +44,17 @@ def test_rk4_and_forward_euler_bit_exact_on_a_voronoi_mesh(backend, case, renumb
     unf = mb.PrognosticVars(ssh, u, h, 2, mesh)
     mb.ocn_timestep(dt, unf, None, None, None, mb.RungeKutta4, nsteps=25, fused=False)
     assert np.array_equal(unf.normalVelocity, prog.normalVelocity) and np.array_equal(unf.layerThickness, prog.layerThickness)
+    # reading edgesOnEdge instead of rebuilding it, and the run-time-width kernels (wider device rows kept): the same bits
+    for kw in (dict(explicit_eoe=True), dict(keep_widths=True)):
+        mk = dict(m)
+        if "keep_widths" in kw:
+            from test_gpu_parity import _padded
+            mk = _padded(m, S=8, S2=14)
+        other = mb.Mesh(mk, backend, renumber=renumber, **kw)
+        assert other.derived_blocks()[1] == 0
+        p2 = mb.PrognosticVars(ssh, u, h, 2, other)
+        mb.ocn_timestep(dt, p2, None, None, None, mb.RungeKutta4, nsteps=25)
+        assert np.array_equal(p2.normalVelocity, prog.normalVelocity) and np.array_equal(p2.layerThickness, prog.layerThickness)
     pfe = mb.PrognosticVars(ssh, u, h, 2, mesh)
     diag, tend = mb.DiagnosticVars(pfe), mb.TendencyVars(pfe)
     mb.ocn_timestep(dt, pfe, diag, tend, None, mb.ForwardEuler, nsteps=12)
