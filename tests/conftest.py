@@ -10,8 +10,15 @@ for p in (os.path.join(ROOT, "mpas-ocean.jl_b200"), os.path.join(ROOT, "oracle")
         sys.path.insert(0, p)
 
 
+def pytest_collection_modifyitems(config, items):
+    """Tests of code that has not run on hardware yet (written on the simulated runtime after a round's GPU budget was spent)
+    go LAST, so that on a GPU box the verified suite has reported before anything untested gets its first run."""
+    items.sort(key=lambda it: 1 if it.get_closest_marker("hw_pending") else 0)
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "hw_pending: exercises device code whose first hardware run is still pending (sorted last)")
     if os.environ.get("MOKAB_SIM"):
         # MOKAB_SIM=1 python -m pytest tests -m gpu: the `gpu` tests run against the HOST build of the library's own
         # sources on the simulated CUDA runtime (tests/sim) -- a logic / ordering check for containers without a GPU,

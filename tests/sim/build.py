@@ -118,6 +118,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     h = hashlib.sha256()
     for p in srcs + extra:
         h.update(open(p, "rb").read())
+    h.update(os.environ.get("MOKAB_SIM_ASAN", "").encode())
     stamp = os.path.join(BUILD, "stamp")
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == h.hexdigest():
         return LIB
@@ -133,7 +134,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         out = os.path.join(gen, os.path.basename(p).replace(".cu", ".cpp") if p.endswith(".cu") else os.path.basename(p))
         with open(out, "w") as f:
             f.write(text)
-    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off", "-fno-fast-math", "-DMOKAB_SIM", "-U_FORTIFY_SOURCE",
+    # MOKAB_SIM_ASAN=1: AddressSanitizer build -- every out-of-bounds access of a kernel or of the host code is reported (run with
+    # LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0)
+    asan = ["-fsanitize=address", "-fno-omit-frame-pointer"] if os.environ.get("MOKAB_SIM_ASAN") else []
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", *asan, "-fopenmp", "-ffp-contract=off", "-fno-fast-math", "-DMOKAB_SIM", "-U_FORTIFY_SOURCE",
            "-Wno-unknown-pragmas", "-I", os.path.join(HERE, "include"), os.path.join(gen, "moka_b200.cpp"),
            os.path.join(HERE, "sim_runtime.cpp"), "-o", LIB,
            "-Wl,-Bsymbolic",      # the cuda* symbols defined here must win over a real libcudart that torch may have loaded

@@ -158,6 +158,7 @@ _P2P_OPT_IN = pytest.mark.skipif(not os.environ.get("MOKAB_SIM") and os.environ.
 
 
 @_P2P_OPT_IN
+@pytest.mark.hw_pending
 @pytest.mark.parametrize("nx,nparts,split,dtype", [(32, 2, True, np.float64), (96, 8, True, np.float64), (64, 3, False, np.float64),
                                                    (48, 4, True, np.float32)])
 def test_direct_store_halo_exchange_matches_the_packed_one(backend, nx, nparts, split, dtype):
