@@ -136,7 +136,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
             f.write(text)
     # MOKAB_SIM_ASAN=1: AddressSanitizer build -- every out-of-bounds access of a kernel or of the host code is reported (run with
     # LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0)
-    asan = ["-fsanitize=address", "-fno-omit-frame-pointer"] if os.environ.get("MOKAB_SIM_ASAN") else []
+    asan = ["-fsanitize=address", "-fno-omit-frame-pointer"] if os.environ.get("MOKAB_SIM_ASAN") == "1" else []
+    if os.environ.get("MOKAB_SIM_ASAN") == "undefined":       # UndefinedBehaviorSanitizer instead (shifts, signed overflow, misaligned access)
+        asan = ["-fsanitize=undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer"]
     cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", *asan, "-fopenmp", "-ffp-contract=off", "-fno-fast-math", "-DMOKAB_SIM", "-U_FORTIFY_SOURCE",
            "-Wno-unknown-pragmas", "-I", os.path.join(HERE, "include"), os.path.join(gen, "moka_b200.cpp"),
            os.path.join(HERE, "sim_runtime.cpp"), "-o", LIB,
