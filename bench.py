@@ -25,7 +25,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "mpas-ocean.jl_b200"))
 
-WORKLOADS = {"igw64": 64, "igw512": 512, "igw1024": 1024, "igw2048": 2048, "igw4096": 4096, "kelvin1024": 1024}
+WORKLOADS = {"igw64": 64, "igw512": 512, "igw1024": 1024, "igw2048": 2048, "igw4096": 4096, "kelvin1024": 1024,
+             # unstructured: periodic Voronoi mesh of a jittered lattice (~0.5 % pentagons, ~0.5 % heptagons, all metrics different)
+             "voronoi64": 64, "voronoi1024": 1024, "voronoi2048": 2048}
 # algorithmic bytes per cell per RK4 step on a planar hex mesh (SURVEY.md 8d / BASELINE.md section 3): every distinct
 # array element moved once per stage, edgesOnEdge included
 ALGO_BYTES_PER_CELL_STEP = {"f64": 2400.0, "f32": 1536.0}
@@ -36,6 +38,18 @@ ALGO_BYTES_PER_CELL_STEP_DERIVED = {"f64": 2400.0 - 4 * 3 * 39, "f32": 1536.0 - 
 
 def algo_bytes_per_cell_step(dtype: str, derived_fraction: float) -> float:
     return derived_fraction * ALGO_BYTES_PER_CELL_STEP_DERIVED[dtype] + (1.0 - derived_fraction) * ALGO_BYTES_PER_CELL_STEP[dtype]
+
+
+def algo_bytes_per_cell_step_general(m: dict, dtype: str, derived_fraction: float) -> float:
+    """The same tally for an arbitrary mesh, from its live row lengths: per RK stage every edge moves
+    cellsOnEdge 8 + g/dc R + dvEdge R + nEdgesOnEdge x (weight R + index 4, or 1 position byte where the row is rebuilt), every
+    cell nEdgesOnCell x 4 + 1/area R + restingThickness R, every degree of freedom 4R on average over the four stages."""
+    R = 8.0 if dtype == "f64" else 4.0
+    nee, nec = float(np.sum(m["nEdgesOnEdge"])), float(np.sum(m["nEdgesOnCell"]))
+    nE, nC = float(m["nEdges"]), float(m["nCells"])
+    idx = derived_fraction * nE * 1.0 + (1.0 - derived_fraction) * 4.0 * nee
+    per_stage = nE * (8.0 + 2.0 * R) + R * nee + idx + 4.0 * nec + 2.0 * R * nC + 4.0 * R * (nE + nC)
+    return 4.0 * per_stage / nC
 
 
 def measured_peak_gbs():
@@ -88,6 +102,10 @@ def build_case(nx: int, dtype: str):
     if dtype == "kelvin":
         m = mb.channel_hex(nx, nx, 1.0e7 / nx)
         ssh, u, h = mb.kelvinWave(m).initial_state()
+    elif dtype == "voronoi":
+        m = mb.periodic_voronoi(nx, nx, 1.0e7 / nx, jitter=0.25, seed=2, allow_obtuse=True, with_dual=False)
+        ssh, u, h = mb.inertialGravityWave(m).initial_state()
+        return m, (ssh, u, h), 0.25 * mb.cfl_dt(m["dc"]), time.time() - t0      # the shortest dcEdge is about half the mean
     else:
         m = mb.periodic_hex(nx, nx, 1.0e7 / nx, with_dual=False)
         ssh, u, h = mb.inertialGravityWave(m).initial_state()
@@ -105,8 +123,8 @@ def run_b200(args):
 
     nx = WORKLOADS[args.workload]
     npdt = np.float64 if args.dtype == "f64" else np.float32
-    kelvin = args.workload.startswith("kelvin")
-    m, (ssh, u, h), dt, t_gen = build_case(nx, "kelvin" if kelvin else args.dtype)
+    kelvin, voronoi = args.workload.startswith("kelvin"), args.workload.startswith("voronoi")
+    m, (ssh, u, h), dt, t_gen = build_case(nx, "kelvin" if kelvin else "voronoi" if voronoi else args.dtype)
     nC, nE = m["nCells"], m["nEdges"]
     backend = mb.B200(local)
     t0 = time.time()
@@ -165,7 +183,9 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel (k_rk_stage) -----------------------------------------------------------
     peak, peak_src = measured_peak_gbs()
-    algo_bytes_per_launch = algo_bytes_per_cell_step(args.dtype, nder / nblk) / 4.0 * nC
+    per_cell_step = (algo_bytes_per_cell_step_general(m, args.dtype, nder / nblk) if voronoi
+                     else algo_bytes_per_cell_step(args.dtype, nder / nblk))
+    algo_bytes_per_launch = per_cell_step / 4.0 * nC
     avg_launch_s = (ms * 1e-3) / stage_launches
     achieved = algo_bytes_per_launch / avg_launch_s / 1e9
     survey_rate = ALGO_BYTES_PER_CELL_STEP[args.dtype] / 4.0 * nC / avg_launch_s / 1e9
@@ -182,6 +202,9 @@ def run_b200(args):
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": (f"coastal Kelvin wave, {nx}x{nx} channel hex mesh with boundary-edge masks" if kelvin else
+                                f"inertial gravity wave, {nx}x{nx} periodic planar Voronoi mesh of a jittered lattice "
+                                f"(polygons by side count from 5: {np.bincount(m['nEdgesOnCell'])[5:].tolist()}; device rows "
+                                f"{mesh.maxEdges2} / {mesh.maxEdges})" if voronoi else
                                 f"inertial gravity wave, {nx}x{nx} periodic planar hex mesh") + f" ({nC} cells, {nE} edges), "
                                f"{'Float64' if args.dtype == 'f64' else 'Float32'} RK4, dt={dt:.4g}s",
                    "name": args.workload, "l2": "inputs larger than L2 (no flush)" if nx >= 1024 else "fits in L2",

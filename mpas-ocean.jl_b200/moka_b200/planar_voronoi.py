@@ -48,12 +48,7 @@ def _lloyd(pts: np.ndarray, Lx: float, Ly: float, iterations: int) -> np.ndarray
     return pts
 
 
-def periodic_voronoi(nx: int, ny: int, dc: float, jitter: float = 0.25, seed: int = 0, f0: float = 1.0e-4,
-                     resting_thickness: float = 1000.0, lloyd: int = 0) -> dict:
-    """`nx` x `ny` cells (ny even, both >= 4) with mean spacing `dc`; `jitter` = maximal displacement of a centre from the
-    hex lattice in units of dc (0.3 gives a few per cent of pentagons and heptagons; 0 reproduces the hexagons); `lloyd`
-    relaxation sweeps afterwards (large jitter + a few sweeps: many defects, well-shaped cells, at any mesh size)."""
-    from scipy.spatial import Voronoi
+def _generators(nx: int, ny: int, dc: float, jitter: float, seed: int, lloyd: int):
     if ny % 2 or nx < 4 or ny < 4:
         raise ValueError("periodic_voronoi: nx, ny >= 4 and ny even")
     N = nx * ny
@@ -65,6 +60,17 @@ def periodic_voronoi(nx: int, ny: int, dc: float, jitter: float = 0.25, seed: in
     pts = base + np.stack([r * np.cos(a), r * np.sin(a)], axis=1)
     if lloyd:
         pts = _lloyd(pts, Lx, Ly, lloyd)
+    return pts, Lx, Ly
+
+
+def periodic_voronoi_loops(nx: int, ny: int, dc: float, jitter: float = 0.25, seed: int = 0, f0: float = 1.0e-4,
+                           resting_thickness: float = 1000.0, lloyd: int = 0) -> dict:
+    """The same mesh as `periodic_voronoi`, built entity by entity in Python loops from scipy's Voronoi diagram of a 3x3
+    tiling: slow, obvious, independent of the vectorised construction below -- the tests hold the two against each other.
+    (Edge / vertex numbering and edge orientation differ between the two; cells are numbered alike.)"""
+    from scipy.spatial import Voronoi
+    pts, Lx, Ly = _generators(nx, ny, dc, jitter, seed, lloyd)
+    N = nx * ny
     tiles = [(ox, oy) for oy in (-1, 0, 1) for ox in (-1, 0, 1)]
     allp = np.concatenate([pts + np.array([ox * Lx, oy * Ly]) for ox, oy in tiles])
     vor = Voronoi(allp)
@@ -198,6 +204,157 @@ def periodic_voronoi(nx: int, ny: int, dc: float, jitter: float = 0.25, seed: in
     vx = np.array([vpos[v] for v in range(nV)])
     m["xVertex"], m["yVertex"], m["zVertex"], m["fVertex"] = vx[:, 0], vx[:, 1], np.zeros(nV), np.full(nV, f0)
     m["areaTriangle"], m["edgesOnVertex"], m["cellsOnVertex"], m["kiteAreasOnVertex"] = area_tri, eov, cov, kites
+    m["minLevelCell"] = np.ones(N, np.int32)
+    m["maxLevelCell"] = np.ones(N, np.int32)
+    m["restingThickness"] = np.full((N, 1), float(resting_thickness))
+    m["boundaryEdge"] = np.zeros(nE, np.int32)
+    return m
+
+
+def periodic_voronoi(nx: int, ny: int, dc: float, jitter: float = 0.25, seed: int = 0, f0: float = 1.0e-4,
+                     resting_thickness: float = 1000.0, lloyd: int = 0, allow_obtuse: bool = False, with_dual: bool = True) -> dict:
+    """`nx` x `ny` cells (ny even, both >= 4) with mean spacing `dc`; `jitter` = maximal displacement of a centre from the
+    hex lattice in units of dc (0.3 gives a few per cent of pentagons and heptagons; 0 reproduces the hexagons); `lloyd`
+    relaxation sweeps afterwards (large jitter + a few sweeps: many defects, well-shaped cells).  `allow_obtuse`: keep
+    meshes in which a Delaunay triangle is obtuse (its circumcentre falls outside, a kite area turns negative -- the
+    identities the weights rest on still hold, the cells are just badly shaped); needed for large un-relaxed meshes.
+
+    Vectorised: the Voronoi diagram is read off the Delaunay triangulation of the generators plus a margin of periodic
+    images (a triangle = a vertex at its circumcentre, a triangle side = an edge), every array is built with sorts and
+    segment operations -- a million cells in about a minute."""
+    from scipy.spatial import Delaunay
+    pts, Lx, Ly = _generators(nx, ny, dc, jitter, seed, lloyd)
+    N = nx * ny
+    # ---- generators + the periodic images within a margin of the tile ---------------------------------------------------
+    w = 3.0 * dc
+    P, B = [pts], [np.arange(N)]
+    for oy in (-1, 0, 1):
+        for ox in (-1, 0, 1):
+            if ox == 0 and oy == 0:
+                continue
+            q = pts + np.array([ox * Lx, oy * Ly])
+            keep = (q[:, 0] > -w) & (q[:, 0] < Lx + w) & (q[:, 1] > -w) & (q[:, 1] < Ly + w)
+            P.append(q[keep])
+            B.append(np.nonzero(keep)[0])
+    allp, base = np.concatenate(P), np.concatenate(B)
+    tri = Delaunay(allp).simplices.astype(np.int64)
+    a, b, c = allp[tri[:, 0]], allp[tri[:, 1]], allp[tri[:, 2]]
+    flip = (b[:, 0] - a[:, 0]) * (c[:, 1] - a[:, 1]) - (b[:, 1] - a[:, 1]) * (c[:, 0] - a[:, 0]) < 0
+    tri[flip] = tri[flip][:, [0, 2, 1]]                                            # counter-clockwise
+    tri = tri[(tri < N).any(axis=1)]                                                # touching the tile
+    a, b, c = allp[tri[:, 0]], allp[tri[:, 1]], allp[tri[:, 2]]
+    # circumcentre relative to corner a
+    ab, ac = b - a, c - a
+    d2 = 2.0 * (ab[:, 0] * ac[:, 1] - ab[:, 1] * ac[:, 0])
+    lab, lac = (ab * ab).sum(axis=1), (ac * ac).sum(axis=1)
+    cc = np.stack([(ac[:, 1] * lab - ab[:, 1] * lac) / d2, (ab[:, 0] * lac - ac[:, 0] * lab) / d2], axis=1)
+    # ---- vertices: triangles up to periodic images (the sorted triple of cells identifies one) ------------------------
+    tb = base[tri]
+    key = np.sort(tb, axis=1)
+    if (key[:, 0] == key[:, 1]).any() or (key[:, 1] == key[:, 2]).any():
+        raise RuntimeError("periodic_voronoi: a cell meets its own image (mesh too small)")
+    k1 = (key[:, 0] * N + key[:, 1]) * N + key[:, 2]
+    uk, first, vid_of_tri = np.unique(k1, return_index=True, return_inverse=True)
+    nV = len(uk)
+    # ---- directed sides: a -> b of a counter-clockwise triangle has that triangle's vertex on its LEFT -------------------
+    da = np.concatenate([tb[:, 0], tb[:, 1], tb[:, 2]])
+    db = np.concatenate([tb[:, 1], tb[:, 2], tb[:, 0]])
+    disp = np.concatenate([b - a, c - b, a - c])                                    # x(b image) - x(a)
+    vleft = np.concatenate([vid_of_tri] * 3)
+    rleft = np.concatenate([cc, cc - ab, cc - ac])                                  # the vertex relative to the side's start cell
+    _, fi = np.unique(da * N + db, return_index=True)                               # once per physical directed side
+    da, db, disp, vleft, rleft = da[fi], db[fi], disp[fi], vleft[fi], rleft[fi]
+    # sort the sides by (start cell, angle): the neighbours of every cell counter-clockwise
+    ang = np.arctan2(disp[:, 1], disp[:, 0])
+    o = np.lexsort((ang, da))
+    da, db, disp, vleft, rleft, ang = da[o], db[o], disp[o], vleft[o], rleft[o], ang[o]
+    nD = len(da)
+    nEoC = np.bincount(da, minlength=N).astype(np.int32)
+    start = np.concatenate([[0], np.cumsum(nEoC)]).astype(np.int64)
+    if nEoC.min() < 3:
+        raise RuntimeError("periodic_voronoi: a cell with fewer than three sides")
+    posn = np.arange(nD) - start[da]                                                # position of the side in its cell's row
+    nxt = start[da] + (posn + 1) % nEoC[da]                                         # the next side counter-clockwise
+    # ---- edges: undirected sides, cellsOnEdge = (smaller id, larger id) --------------------------------------------------
+    lo, hi = np.minimum(da, db), np.maximum(da, db)
+    ekeys, eid = np.unique(lo * N + hi, return_inverse=True)                        # edge of every directed side
+    nE = len(ekeys)
+    if nV - nE + N != 0:
+        raise RuntimeError(f"periodic_voronoi: Euler characteristic of the torus violated (V - E + F = {nV - nE + N})")
+    fwd = da < db                                                                   # the side runs c1 -> c2
+    e_of_fwd = eid[fwd]
+    coe = np.zeros((nE, 2), np.int32)
+    coe[e_of_fwd, 0], coe[e_of_fwd, 1] = da[fwd] + 1, db[fwd] + 1
+    dvec = np.zeros((nE, 2))
+    dvec[e_of_fwd] = disp[fwd]
+    dcE = np.hypot(dvec[:, 0], dvec[:, 1])
+    angE = np.arctan2(dvec[:, 1], dvec[:, 0])
+    mid = pts[coe[:, 0] - 1] + 0.5 * dvec
+    # verticesOnEdge along t = k x n: from the vertex on the right of c1 -> c2 (= left of c2 -> c1) to the one on its left
+    voe = np.zeros((nE, 2), np.int32)
+    voe[e_of_fwd, 1] = vleft[fwd] + 1
+    voe[eid[~fwd], 0] = vleft[~fwd] + 1
+    vL, vR = np.zeros((nE, 2)), np.zeros((nE, 2))
+    vL[e_of_fwd] = rleft[fwd]                                                       # relative to c1
+    # the right vertex seen from c1: the left vertex of c2 -> c1 is given relative to c2; c2 sits at c1 + dvec
+    vR[eid[~fwd]] = rleft[~fwd] + dvec[eid[~fwd]]
+    dvE = np.hypot(vL[:, 0] - vR[:, 0], vL[:, 1] - vR[:, 1])
+    # ---- per cell rows ---------------------------------------------------------------------------------------------------
+    S = int(nEoC.max())
+    eoc, coc, voc = (np.zeros((N, S), np.int32) for _ in range(3))
+    eoc[da, posn], coc[da, posn], voc[da, posn] = eid + 1, db + 1, vleft + 1
+    # kite of (cell, vertex to the left of side k): (centre, midpoint of side k, vertex, midpoint of side k + 1)
+    m0, m1, rv = 0.5 * disp, 0.5 * disp[nxt], rleft
+    kite = 0.5 * ((m0[:, 0] * rv[:, 1] - rv[:, 0] * m0[:, 1]) + (rv[:, 0] * m1[:, 1] - m1[:, 0] * rv[:, 1]))
+    if not allow_obtuse and kite.min() <= 0.0:
+        raise RuntimeError("periodic_voronoi: non-positive kite area (an obtuse Delaunay triangle: reduce the jitter, relax, or allow_obtuse)")
+    area = np.bincount(da, weights=kite, minlength=N)
+    # ---- TRiSK: for the edge of side (c, position k), walk c's other sides counter-clockwise ------------------------------
+    S2 = 2 * S - 2
+    eoe = np.zeros((nE, S2), np.int32)
+    woe = np.zeros((nE, S2))
+    n_c = nEoC[da].astype(np.int64)
+    n1 = nEoC[coe[:, 0] - 1].astype(np.int64)
+    slot0 = np.where(fwd, 0, n1[eid] - 1)                                           # cell 1's entries first, then cell 2's
+    sigma = np.where(fwd, 1.0, -1.0)
+    rsum = np.zeros(nD)
+    for kk in range(1, S):
+        act = kk < n_c
+        passed = start[da] + (posn + kk - 1) % n_c                                  # the side whose left vertex is passed on the way
+        rsum = rsum + kite[passed] / area[da]
+        tgt = start[da] + (posn + kk) % n_c                                         # the side of the edge e'
+        e2 = eid[tgt]
+        owner = np.where(coe[e2, 0] - 1 == da, 1.0, -1.0)
+        wv = sigma * (0.5 - rsum) * owner * dvE[e2] / dcE[eid]
+        sl = slot0 + kk - 1
+        eoe[eid[act], sl[act]] = e2[act] + 1
+        woe[eid[act], sl[act]] = wv[act]
+    nEoE = (n1 + nEoC[coe[:, 1] - 1] - 2).astype(np.int32)
+
+    m: dict = {"nCells": N, "nEdges": nE, "nVertices": nV if with_dual else 0, "maxEdges": S, "maxEdges2": S2, "vertexDegree": 3,
+               "nVertLevels": 1, "is_periodic": "YES", "x_period": Lx, "y_period": Ly, "dc": float(dc), "nx": nx, "ny": ny}
+    m["xCell"], m["yCell"], m["zCell"] = pts[:, 0] % Lx, pts[:, 1] % Ly, np.zeros(N)
+    m["fCell"], m["areaCell"], m["nEdgesOnCell"] = np.full(N, f0), area, nEoC
+    m["cellsOnEdge"], m["angleEdge"] = coe, angE
+    m["xEdge"], m["yEdge"], m["zEdge"], m["fEdge"] = mid[:, 0] % Lx, mid[:, 1] % Ly, np.zeros(nE), np.full(nE, f0)
+    m["dcEdge"], m["dvEdge"] = dcE, dvE
+    m["edgesOnCell"], m["cellsOnCell"] = eoc, coc
+    m["edgesOnEdge"], m["weightsOnEdge"], m["nEdgesOnEdge"] = eoe, woe, nEoE
+    if with_dual:
+        m["verticesOnEdge"], m["verticesOnCell"] = voe, voc
+        t0 = tri[first]                                                             # one triangle per vertex
+        vx = allp[t0[:, 0]] + cc[first]
+        m["xVertex"], m["yVertex"], m["zVertex"], m["fVertex"] = vx[:, 0] % Lx, vx[:, 1] % Ly, np.zeros(nV), np.full(nV, f0)
+        cov = base[t0]                                                              # counter-clockwise
+        m["cellsOnVertex"] = (cov + 1).astype(np.int32)
+        # kiteAreasOnVertex[v, j] belongs to cellsOnVertex[v, j]; edgesOnVertex[v, j] joins cellsOnVertex[v, j] and [v, j + 1]
+        kv = np.zeros((nV, 3))
+        eov = np.zeros((nV, 3), np.int32)
+        for j in range(3):
+            sel = np.nonzero(cov[vleft, j] == da)[0]                                 # the side leaving corner j with v on its left
+            kv[vleft[sel], j] = kite[sel]
+            eov[vleft[sel], j] = eid[sel] + 1
+        m["kiteAreasOnVertex"], m["edgesOnVertex"], m["areaTriangle"] = kv, eov, kv.sum(axis=1)
     m["minLevelCell"] = np.ones(N, np.int32)
     m["maxLevelCell"] = np.ones(N, np.int32)
     m["restingThickness"] = np.full((N, 1), float(resting_thickness))

@@ -138,3 +138,46 @@ def test_lloyd_relaxed_mesh_keeps_its_defects_and_satisfies_the_identities():
     ut = -np.sin(m["angleEdge"]) * U[0] + np.cos(m["angleEdge"]) * U[1]
     rec = np.sum(np.where(eoe >= 0, w * un[np.maximum(eoe, 0)], 0.0), axis=1)
     assert np.sqrt(np.mean((rec - ut) ** 2)) < 0.05
+
+
+def test_vectorised_and_loop_constructions_agree():
+    """periodic_voronoi (Delaunay-based, vectorised) against periodic_voronoi_loops (entity by entity from scipy's Voronoi
+    diagram).  Cells are numbered alike; edges are matched through their pair of cells (numbering and orientation differ)."""
+    from moka_b200.planar_voronoi import periodic_voronoi_loops
+    a = periodic_voronoi(14, 12, 1000.0, jitter=0.3, seed=5)
+    b = periodic_voronoi_loops(14, 12, 1000.0, jitter=0.3, seed=5)
+    assert (a["nCells"], a["nEdges"], a["nVertices"]) == (b["nCells"], b["nEdges"], b["nVertices"])
+    assert np.array_equal(a["nEdgesOnCell"], b["nEdgesOnCell"]) and np.allclose(a["areaCell"], b["areaCell"], rtol=1e-12)
+    assert np.allclose(a["xCell"], b["xCell"]) and np.allclose(a["yCell"], b["yCell"])
+    for c in range(a["nCells"]):                                  # the same neighbours in the same cyclic order
+        n = a["nEdgesOnCell"][c]
+        ra, rb = a["cellsOnCell"][c, :n].tolist(), b["cellsOnCell"][c, :n].tolist()
+        k = rb.index(ra[0])
+        assert ra == rb[k:] + rb[:k]
+    key = lambda m: {tuple(sorted(ce)): e for e, ce in enumerate(m["cellsOnEdge"].tolist())}      # noqa: E731
+    ka, kb = key(a), key(b)
+    assert ka.keys() == kb.keys()
+    ea = np.array([ka[k] for k in ka])
+    eb = np.array([kb[k] for k in ka])
+    assert np.allclose(a["dcEdge"][ea], b["dcEdge"][eb], rtol=1e-12) and np.allclose(a["dvEdge"][ea], b["dvEdge"][eb], rtol=1e-9, atol=1e-9)
+    assert np.array_equal(a["nEdgesOnEdge"][ea], b["nEdgesOnEdge"][eb])
+    # weights: the same multiset of |w| per edge (orientation flips signs and swaps the two halves of a row)
+    wa = np.sort(np.abs(a["weightsOnEdge"][ea]), axis=1)
+    wb = np.sort(np.abs(b["weightsOnEdge"][eb]), axis=1)
+    assert np.allclose(wa, wb, rtol=1e-9, atol=1e-12)
+    assert np.allclose(np.sort(a["areaTriangle"]), np.sort(b["areaTriangle"]), rtol=1e-10)
+
+
+def test_large_voronoi_mesh_with_obtuse_triangles_keeps_the_identities():
+    m = periodic_voronoi(96, 96, 1000.0, jitter=0.3, seed=2, allow_obtuse=True)
+    assert m["kiteAreasOnVertex"].min() < 0                                       # the un-relaxed mesh does have obtuse triangles at this size
+    A = m["x_period"] * m["y_period"]
+    assert abs(m["areaCell"].sum() - A) <= 1e-12 * A and m["areaCell"].min() > 0
+    eoe, w, ne = m["edgesOnEdge"].astype(np.int64) - 1, m["weightsOnEdge"], m["nEdgesOnEdge"]
+    nE = m["nEdges"]
+    rows = np.repeat(np.arange(nE), eoe.shape[1]).reshape(eoe.shape)
+    live = np.arange(eoe.shape[1])[None, :] < ne[:, None]
+    wt = w * m["dcEdge"][:, None] / m["dvEdge"][np.maximum(eoe, 0)]
+    import scipy.sparse as sp
+    W = sp.coo_matrix((wt[live], (rows[live], eoe[live])), shape=(nE, nE)).tocsr()
+    assert abs(W + W.T).max() < 1e-12                                             # energy-neutral Coriolis on any such mesh

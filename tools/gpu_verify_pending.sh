@@ -15,6 +15,9 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke_$tag
 timeout 300 python tools/diag_graph_emulated.py > $out/diag_emulated_$tag.log 2>&1; echo "diag rc=$?"; cat $out/diag_emulated_$tag.log
 # 3. bench lines (default workload; the reverse modes incl. the new ForwardEuler adjoint)
 python bench.py > $out/bench_$tag.json 2> $out/bench_$tag.err; echo "bench rc=$?"; cat $out/bench_$tag.json
+# unstructured mesh (pentagons / hexagons / heptagons): the compile-time (12, 7) kernels with and without the edgesOnEdge rebuild
+python bench.py --workload voronoi1024 --no-cpu > $out/bench_voronoi1024_$tag.json 2>> $out/bench_$tag.err; cat $out/bench_voronoi1024_$tag.json
+python bench.py --workload voronoi1024 --no-cpu --explicit-eoe > $out/bench_voronoi1024_explicit_$tag.json 2>> $out/bench_$tag.err; cat $out/bench_voronoi1024_explicit_$tag.json
 python tools/bench_adjoint.py --stepper fe > $out/adjoint_fe_$tag.json 2>> $out/bench_$tag.err; cat $out/adjoint_fe_$tag.json
 python tools/bench_adjoint.py > $out/adjoint_rk4_$tag.json 2>> $out/bench_$tag.err; cat $out/adjoint_rk4_$tag.json
 if [ "$ngpu" -ge 2 ]; then
