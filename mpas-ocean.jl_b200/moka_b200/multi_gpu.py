@@ -371,6 +371,10 @@ def _share_locals(args, rank, world, nx, dtype):
         if args.workload.startswith("kelvin"):
             m = planar_hex.channel_hex(nx, nx, 1.0e7 / nx)
             ssh, u, h = api.kelvinWave(m).initial_state()
+        elif args.workload.startswith("voronoi"):
+            from . import planar_voronoi
+            m = planar_voronoi.periodic_voronoi(nx, nx, 1.0e7 / nx, jitter=0.25, seed=2, allow_obtuse=True, with_dual=False)
+            ssh, u, h = api.inertialGravityWave(m).initial_state()
         else:
             m = planar_hex.periodic_hex(nx, nx, 1.0e7 / nx, with_dual=False)
             ssh, u, h = api.inertialGravityWave(m).initial_state()
@@ -407,14 +411,15 @@ def _share_locals(args, rank, world, nx, dtype):
 def bench_main(args, rank, world, local):
     import torch
     import torch.distributed as dist
-    from bench import WORKLOADS, ClockSampler, algo_bytes_per_cell_step, measured_peak_gbs
+    from bench import WORKLOADS, ClockSampler, algo_bytes_per_cell_step, algo_bytes_per_cell_step_general, measured_peak_gbs
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     nx = WORKLOADS[args.workload]
     npdt = np.float64 if args.dtype == "f64" else np.float32
     loc, state, t_setup = _share_locals(args, rank, world, nx, npdt)
     nC_glob = nx * nx
-    dt = api.cfl_dt(1.0e7 / nx)
+    voronoi = args.workload.startswith("voronoi")
+    dt = (0.25 if voronoi else 1.0) * api.cfl_dt(1.0e7 / nx)
     backend = api.B200(local)
     model = DecomposedModel(loc, state, backend, local, dtype=npdt, overlap=not getattr(args, "no_overlap", False),
                             graph=not getattr(args, "no_graph", False), halo=getattr(args, "halo", "nccl"))
@@ -482,13 +487,20 @@ def bench_main(args, rank, world, local):
         peak, peak_src = measured_peak_gbs()
         value = nC_glob * K / (ms * 1e-3)
         nblk, nder = model.mesh.derived_blocks()
-        algo_per_launch = algo_bytes_per_cell_step(args.dtype, nder / max(nblk, 1)) / 4.0 * loc["nCellsOwned"]
+        if voronoi:
+            nco, neo = loc["nCellsOwned"], loc["nEdgesOwned"]
+            owned = {"nCells": nco, "nEdges": neo, "nEdgesOnCell": loc["nEdgesOnCell"][:nco], "nEdgesOnEdge": loc["nEdgesOnEdge"][:neo]}
+            per_cell_step = algo_bytes_per_cell_step_general(owned, args.dtype, nder / max(nblk, 1))
+        else:
+            per_cell_step = algo_bytes_per_cell_step(args.dtype, nder / max(nblk, 1))
+        algo_per_launch = per_cell_step / 4.0 * loc["nCellsOwned"]
         achieved = algo_per_launch / ((ms * 1e-3) / (4 * K)) / 1e9
         print(json.dumps({
             "metric": "RK4 cell-steps/sec", "value": value, "unit": "cell-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype,
             "data": "synthetic",
             "config": {"workload": ("coastal Kelvin wave, %dx%d channel hex mesh with boundary-edge masks" % (nx, nx) if args.workload.startswith("kelvin")
+                                    else f"inertial gravity wave, {nx}x{nx} periodic planar Voronoi mesh of a jittered lattice" if voronoi
                                     else f"inertial gravity wave, {nx}x{nx} periodic planar hex mesh") + f" ({nC_glob} cells), "
                                    f"{'Float64' if args.dtype == 'f64' else 'Float32'} RK4, dt={dt:.4g}s, recursive-coordinate-bisection "
                                    f"into {world} parts, 1 halo layer, "
