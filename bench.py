@@ -27,7 +27,9 @@ sys.path.insert(0, os.path.join(ROOT, "mpas-ocean.jl_b200"))
 
 WORKLOADS = {"igw64": 64, "igw512": 512, "igw1024": 1024, "igw2048": 2048, "igw4096": 4096, "kelvin1024": 1024,
              # unstructured: periodic Voronoi mesh of a jittered lattice (~0.5 % pentagons, ~0.5 % heptagons, all metrics different)
-             "voronoi64": 64, "voronoi1024": 1024, "voronoi2048": 2048}
+             "voronoi64": 64, "voronoi1024": 1024, "voronoi2048": 2048,
+             # spherical: quasi-uniform Voronoi mesh of the sphere (nx*nx cells), fEdge = 2 Omega sin(lat), geostrophic zonal flow + noise
+             "sphere64": 64, "sphere1024": 1024, "sphere2048": 2048}
 # algorithmic bytes per cell per RK4 step on a planar hex mesh (SURVEY.md 8d / BASELINE.md section 3): every distinct
 # array element moved once per stage, edgesOnEdge included
 ALGO_BYTES_PER_CELL_STEP = {"f64": 2400.0, "f32": 1536.0}
@@ -102,6 +104,11 @@ def build_case(nx: int, dtype: str):
     if dtype == "kelvin":
         m = mb.channel_hex(nx, nx, 1.0e7 / nx)
         ssh, u, h = mb.kelvinWave(m).initial_state()
+    elif dtype == "sphere":
+        m = mb.spherical_voronoi(nx * nx, with_dual=False)
+        ssh, u, h = mb.geostrophic_zonal_flow(m)
+        u = u + 0.1 * np.random.default_rng(0).standard_normal(m["nEdges"])
+        return m, (ssh, u, h), 0.25 * float(m["dcEdge"].min()) / float(np.sqrt(9.80616 * 1000.0)), time.time() - t0
     elif dtype == "voronoi":
         m = mb.periodic_voronoi(nx, nx, 1.0e7 / nx, jitter=0.25, seed=2, allow_obtuse=True, with_dual=False)
         ssh, u, h = mb.inertialGravityWave(m).initial_state()
@@ -123,8 +130,9 @@ def run_b200(args):
 
     nx = WORKLOADS[args.workload]
     npdt = np.float64 if args.dtype == "f64" else np.float32
-    kelvin, voronoi = args.workload.startswith("kelvin"), args.workload.startswith("voronoi")
-    m, (ssh, u, h), dt, t_gen = build_case(nx, "kelvin" if kelvin else "voronoi" if voronoi else args.dtype)
+    kelvin, sphere = args.workload.startswith("kelvin"), args.workload.startswith("sphere")
+    voronoi = args.workload.startswith("voronoi") or sphere           # unstructured: byte accounting from the actual rows
+    m, (ssh, u, h), dt, t_gen = build_case(nx, "kelvin" if kelvin else "sphere" if sphere else "voronoi" if voronoi else args.dtype)
     nC, nE = m["nCells"], m["nEdges"]
     backend = mb.B200(local)
     t0 = time.time()
@@ -202,6 +210,9 @@ def run_b200(args):
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": (f"coastal Kelvin wave, {nx}x{nx} channel hex mesh with boundary-edge masks" if kelvin else
+                                f"geostrophic zonal flow + noise, spherical Voronoi mesh, fEdge = 2 Omega sin(lat) "
+                                f"(polygons by side count from 5: {np.bincount(m['nEdgesOnCell'])[5:].tolist()}; device rows "
+                                f"{mesh.maxEdges2} / {mesh.maxEdges})" if sphere else
                                 f"inertial gravity wave, {nx}x{nx} periodic planar Voronoi mesh of a jittered lattice "
                                 f"(polygons by side count from 5: {np.bincount(m['nEdgesOnCell'])[5:].tolist()}; device rows "
                                 f"{mesh.maxEdges2} / {mesh.maxEdges})" if voronoi else

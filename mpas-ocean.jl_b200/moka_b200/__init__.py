@@ -6,6 +6,7 @@ from .api import (B200, CurlOnVertex, DivergenceOnCell_vjp, GradientOnEdge_vjp, 
                   inertialGravityWave, interpolateCell2Edge, kelvinWave, ocn_run_loop, ocn_timestep, reduce_sum, reference_dt)
 from .planar_hex import channel_hex, periodic_hex  # noqa: F401
 from .planar_voronoi import periodic_voronoi  # noqa: F401
+from .spherical_voronoi import geostrophic_zonal_flow, spherical_voronoi  # noqa: F401
 from . import config, driver, io_netcdf, time_manager  # noqa: F401,E402
 from .config import ConfigAdd, ConfigGet, ConfigRead, ConfigSet, GlobalConfig, yaml_config  # noqa: F401,E402
 from .driver import ModelSetup, ocn_init, ocn_init_alarms, ocn_run  # noqa: F401,E402

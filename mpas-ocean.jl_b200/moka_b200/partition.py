@@ -3,9 +3,9 @@
 The reference has no multi-device code at all, so the algorithm is defined
 here and pinned bit-exactly by an independent loop implementation in oracle/partition_oracle.py:
 
-cell -> part   recursive coordinate bisection of the cell centres: split the longer extent
-               (ties -> x), order by (coordinate, global id), left gets floor(n*pl/p) cells with
-               pl = p // 2 parts, recurse.
+cell -> part   recursive coordinate bisection of the cell centres: split the longest extent among
+               x, y (and z when the mesh is not planar; ties -> x, then y), order by (coordinate, global id),
+               left gets floor(n*pl/p) cells with pl = p // 2 parts, recurse.
 edge owner     owner of cellsOnEdge[1, e].
 local sets     cells = [owned (by global id) | halo = not-owned cells sharing an edge with an owned
                cell (by global id)]; edges = [owned (by global id) | halo = every other edge of a
@@ -23,17 +23,20 @@ from __future__ import annotations
 import numpy as np
 
 
-def rcb_partition(x: np.ndarray, y: np.ndarray, nparts: int) -> np.ndarray:
-    """cell -> part (int32) by recursive coordinate bisection."""
+def rcb_partition(x: np.ndarray, y: np.ndarray, nparts: int, z: np.ndarray | None = None) -> np.ndarray:
+    """cell -> part (int32) by recursive coordinate bisection (`z`: spherical meshes -- without it the two hemispheres
+    would be cut as one disc and every part would come in two far-apart pieces)."""
     n = x.shape[0]
     part = np.zeros(n, np.int32)
+    coords = [x, y] + ([z] if z is not None else [])
 
     def rec(ids: np.ndarray, p: int, base: int) -> None:
         if p == 1:
             part[ids] = base
             return
-        xs, ys = x[ids], y[ids]
-        axis_vals = xs if (xs.max() - xs.min()) >= (ys.max() - ys.min()) else ys
+        vals = [c[ids] for c in coords]
+        ext = [v.max() - v.min() for v in vals]
+        axis_vals = vals[int(np.argmax(ext))]         # the first of equal extents: x before y before z
         order = np.lexsort((ids, axis_vals))          # by coordinate, ties by global id
         pl = p // 2
         nleft = (ids.shape[0] * pl) // p
@@ -114,7 +117,8 @@ def recv_lists(loc: dict, nparts: int):
 def decompose(m: dict, nparts: int, part: np.ndarray | None = None) -> list[dict]:
     """All local meshes with their halo send/recv lists (`halo` key) -- what rank 0 prepares."""
     if part is None:
-        part = rcb_partition(m["xCell"], m["yCell"], nparts)
+        z = m.get("zCell")
+        part = rcb_partition(m["xCell"], m["yCell"], nparts, z if z is not None and np.ptp(z) > 0 else None)
     locs = [build_local_mesh(m, part, r) for r in range(nparts)]
     recvs = [recv_lists(loc, nparts) for loc in locs]
     for r, loc in enumerate(locs):

@@ -9,19 +9,24 @@ lists can be compared bit for bit.  Small meshes only.
 from __future__ import annotations
 
 
-def rcb_partition(x, y, nparts):
+def rcb_partition(x, y, nparts, z=None):
     n = len(x)
     part = [0] * n
+    coords = [x, y] + ([z] if z is not None else [])
 
     def rec(ids, p, base):
         if p == 1:
             for i in ids:
                 part[i] = base
             return
-        xs = [x[i] for i in ids]
-        ys = [y[i] for i in ids]
-        use_x = (max(xs) - min(xs)) >= (max(ys) - min(ys))
-        srt = sorted(ids, key=(lambda i: (x[i], i)) if use_x else (lambda i: (y[i], i)))
+        best, best_ext = 0, None
+        for k, c in enumerate(coords):                     # the longest extent, the earliest coordinate among equals
+            vals = [c[i] for i in ids]
+            ext = max(vals) - min(vals)
+            if best_ext is None or ext > best_ext:
+                best, best_ext = k, ext
+        c = coords[best]
+        srt = sorted(ids, key=lambda i: (c[i], i))
         pl = p // 2
         nleft = (len(ids) * pl) // p
         rec(srt[:nleft], pl, base)

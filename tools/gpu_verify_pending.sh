@@ -18,6 +18,8 @@ python bench.py > $out/bench_$tag.json 2> $out/bench_$tag.err; echo "bench rc=$?
 # unstructured mesh (pentagons / hexagons / heptagons): the compile-time (12, 7) kernels with and without the edgesOnEdge rebuild
 python bench.py --workload voronoi1024 --no-cpu > $out/bench_voronoi1024_$tag.json 2>> $out/bench_$tag.err; cat $out/bench_voronoi1024_$tag.json
 python bench.py --workload voronoi1024 --no-cpu --explicit-eoe > $out/bench_voronoi1024_explicit_$tag.json 2>> $out/bench_$tag.err; cat $out/bench_voronoi1024_explicit_$tag.json
+# the sphere: quasi-uniform spherical Voronoi mesh, variable Coriolis parameter (folded (12, 7) kernels)
+python bench.py --workload sphere1024 --no-cpu > $out/bench_sphere1024_$tag.json 2>> $out/bench_$tag.err; cat $out/bench_sphere1024_$tag.json
 python tools/bench_adjoint.py --stepper fe > $out/adjoint_fe_$tag.json 2>> $out/bench_$tag.err; cat $out/adjoint_fe_$tag.json
 python tools/bench_adjoint.py > $out/adjoint_rk4_$tag.json 2>> $out/bench_$tag.err; cat $out/adjoint_rk4_$tag.json
 if [ "$ngpu" -ge 2 ]; then
