@@ -449,7 +449,8 @@ static void step_forward_euler(mokab_state *st, double dt)
 static bool fe_fusable(const mokab_state *st)
 {
     const mokab_mesh *m = st->mesh;
-    return st->dtype == MOKAB_F64 && m->S2 == 10 && m->S == 6 && m->nCo == m->nC && m->nEo == m->nE;
+    const bool widths = (m->S2 == 10 && m->S == 6) || (m->S2 == 12 && m->S == 7);   // the compile-time row widths of k_fe_step
+    return st->dtype == MOKAB_F64 && widths && m->nCo == m->nC && m->nEo == m->nE;
 }
 
 // Re-create the Diag / Tend arrays the unfused step would have left behind, from the state before the last fused step
@@ -501,8 +502,13 @@ static void run_fe_fused(mokab_state *st, double dt, int64_t nsteps)
         if (t->taping) fe_tape_record(st, dt, t->u[p].p, t->hE[p].p);
         A.u = t->u[p].p; A.h = t->h[p].p; A.ssh = t->ssh[p].p; A.hEold = t->hE[p].p;
         A.uNew = t->u[q].p; A.hNew = t->h[q].p; A.sshNew = t->ssh[q].p; A.hEnew = t->hE[q].p;
-        if (m->uniformF) fused::k_fe_step<10, 6, true><<<m->fusedBlocks, fused::kThreads, 0, ctx->stream>>>(A);
-        else             fused::k_fe_step<10, 6, false><<<m->fusedBlocks, fused::kThreads, 0, ctx->stream>>>(A);
+        if (m->S == 6) {
+            if (m->uniformF) fused::k_fe_step<10, 6, true><<<m->fusedBlocks, fused::kThreads, 0, ctx->stream>>>(A);
+            else             fused::k_fe_step<10, 6, false><<<m->fusedBlocks, fused::kThreads, 0, ctx->stream>>>(A);
+        } else {             // pentagons / hexagons / heptagons: rows padded to 12 / 7 (index = self, weight 0)
+            if (m->uniformF) fused::k_fe_step<12, 7, true><<<m->fusedBlocks, fused::kThreads, 0, ctx->stream>>>(A);
+            else             fused::k_fe_step<12, 7, false><<<m->fusedBlocks, fused::kThreads, 0, ctx->stream>>>(A);
+        }
         MOKAB_CUDA(cudaGetLastError());
         ctx->launches++;
         if (m->nV)      // relativeVorticity accumulates step by step in the reference (Operators.jl:135)
