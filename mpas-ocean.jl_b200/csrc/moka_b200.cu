@@ -911,10 +911,12 @@ static void adjoint_step(mokab_state *st, int64_t k)
         B.kuOut = t->kbU[(s - 1) & 1].p; B.kqOut = t->kbH[(s - 1) & 1].p;
         B.aPrev = s > 1 ? (R)a[s - 2] : R(0); B.bPrev = s > 1 ? (R)b[s - 2] : R(0);
         const bool hex = m->S2T == 10 && m->S == 6;
+        const bool hept = m->S2T == 12 && m->S == 7;
         const int mode = s == 4 ? 0 : s > 1 ? 1 : 2;
 #define MOKAB_ADJ_LAUNCH(MODE)                                                                                         \
     do {                                                                                                               \
         if (hex) adjoint::k_rk_stage_adj<R, MODE, 10, 6><<<grid, adjoint::kThreads, 0, ctx->stream>>>(B);              \
+        else if (hept) adjoint::k_rk_stage_adj<R, MODE, 12, 7><<<grid, adjoint::kThreads, 0, ctx->stream>>>(B);        \
         else adjoint::k_rk_stage_adj<R, MODE, 0, 0><<<grid, adjoint::kThreads, 0, ctx->stream>>>(B);                   \
     } while (0)
         if (mode == 0) MOKAB_ADJ_LAUNCH(0);
@@ -993,7 +995,7 @@ static void adjoint_run_fe(mokab_state *st)
     A.ce = m->ce.p; A.eoeT = m->eoeT.p; A.eoc = m->eocF.p; A.nEoET = m->nEoET.p; A.nEoC = m->nEoC.p;
     A.blkEdgeStart = m->blkEdgeStart.p;
     A.gdc = fm.gdc.p; A.wT = m->woeT.p; A.dv = m->dv.p; A.invArea = fm.invArea.p;
-    const bool hex = m->S2T == 10 && m->S == 6;
+    const bool hex = m->S2T == 10 && m->S == 6, hept = m->S2T == 12 && m->S == 7;
     for (int64_t k = (int64_t)t->tapeDt.size() - 1; k >= 0; --k) {
         A.dt = t->tapeDt[k];
         A.uN = t->tapeU.p + (size_t)k * m->nE; A.hEN = t->tapeE.p + (size_t)k * m->nE;
@@ -1001,6 +1003,7 @@ static void adjoint_run_fe(mokab_state *st)
         A.outU = t->lamU[1 - p].p; A.outH = t->lamH[1 - p].p; A.outS = t->lamS[1 - p].p; A.outE = t->lamE[1 - p].p;
         A.qOut = t->lamQ[1 - p].p;
         if (hex) adjoint::k_fe_step_adj<10, 6><<<m->fusedBlocks, adjoint::kThreads, 0, ctx->stream>>>(A);
+        else if (hept) adjoint::k_fe_step_adj<12, 7><<<m->fusedBlocks, adjoint::kThreads, 0, ctx->stream>>>(A);
         else adjoint::k_fe_step_adj<0, 0><<<m->fusedBlocks, adjoint::kThreads, 0, ctx->stream>>>(A);
         MOKAB_CUDA(cudaGetLastError());
         ctx->launches++;
