@@ -274,12 +274,14 @@ def run_reference(args):
         return
     world = int(os.environ.get("WORLD_SIZE", "1"))
     nx = WORKLOADS[args.workload]
-    kelvin = args.workload.startswith("kelvin")
-    m, (ssh, u, h), dt, _ = build_case(nx, "kelvin" if kelvin else "f64")
+    kelvin, sphere, voronoi = (args.workload.startswith(k) for k in ("kelvin", "sphere", "voronoi"))
+    m, (ssh, u, h), dt, _ = build_case(nx, "kelvin" if kelvin else "sphere" if sphere else "voronoi" if voronoi else "f64")
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import moka_oracle_c as OC
     if kelvin:
         m = OC.apply_boundary_mask(m)
+    if sphere or voronoi:
+        OC.sign_index_fields(m)
     # each "step" is a bounded sample: one RK4 step on the workload mesh (capped so the run ends in minutes)
     om = OC.OracleModel(m, ssh, u, h)
     K, W = args.steps, args.warmup
@@ -299,7 +301,10 @@ def run_reference(args):
         "impl": "reference", "metric": "RK4 cell-steps/sec", "value": v, "unit": "cell-steps/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": tt / K * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"inertial gravity wave, {nx}x{nx} periodic planar hex mesh ({m['nCells']} cells), Float64 RK4",
+        "config": {"workload": ("coastal Kelvin wave, channel hex mesh with boundary-edge masks" if kelvin else
+                                "geostrophic zonal flow + noise, spherical Voronoi mesh" if sphere else
+                                f"inertial gravity wave, {nx}x{nx} periodic planar Voronoi mesh" if voronoi else
+                                f"inertial gravity wave, {nx}x{nx} periodic planar hex mesh") + f" ({m['nCells']} cells), Float64 RK4",
                    "name": args.workload},
         "cpu_baseline": {"value": v, "unit": "cell-steps/s", "cores": om.num_threads(), "kind": "port",
                          "sample": f"{K} RK4 steps on the full {m['nCells']}-cell mesh, C/OpenMP restatement of the "
