@@ -1638,6 +1638,9 @@ int mokab_timestep_forward_euler(mokab_state *state, double dt, int64_t nsteps)
         MOKAB_REQUIRE(state, "timestep_forward_euler: state is NULL");
         MOKAB_REQUIRE(nsteps >= 0, "timestep_forward_euler: nsteps must be >= 0");
         require_f64(state, "timestep_forward_euler");
+        MOKAB_REQUIRE(state->mesh->nCo == state->mesh->nC && state->mesh->nEo == state->mesh->nE,
+                      "timestep_forward_euler: this mesh has halo entities and ForwardEuler has no staged form; domain-decomposed runs "
+                      "step with mokab_rk4_stage + the halo exchange");
         state->ctx->bind();
         if (fe_fusable(state)) {
             run_fe_fused(state, dt, nsteps);
@@ -1656,6 +1659,8 @@ int mokab_timestep_forward_euler_unfused(mokab_state *state, double dt, int64_t 
         MOKAB_REQUIRE(state, "timestep_forward_euler_unfused: state is NULL");
         MOKAB_REQUIRE(nsteps >= 0, "timestep_forward_euler_unfused: nsteps must be >= 0");
         require_f64(state, "timestep_forward_euler_unfused");
+        MOKAB_REQUIRE(state->mesh->nCo == state->mesh->nC && state->mesh->nEo == state->mesh->nE,
+                      "timestep_forward_euler_unfused: this mesh has halo entities and ForwardEuler has no staged form");
         state->ctx->bind();
         fe_materialize(state);
         for (int64_t i = 0; i < nsteps; ++i) step_forward_euler(state, dt);

@@ -204,6 +204,8 @@ def test_decomposed_state_refuses_single_domain_stepper(backend):
     prog = mb.PrognosticVars(ssh, u, h, 2, mesh)
     with pytest.raises(mb.MokaError, match="halo"):
         mb.ocn_timestep(1.0, prog, None, None, None, mb.RungeKutta4)
+    with pytest.raises(mb.MokaError, match="halo"):              # nor would ForwardEuler see its neighbours' values
+        mb.ocn_timestep(1.0, prog, None, None, None, mb.ForwardEuler)
     with pytest.raises(mb.MokaError, match="halo_setup"):
         L.check(L.lib().mokab_halo_pack(prog.dev.handle, 1, None, None))
 
