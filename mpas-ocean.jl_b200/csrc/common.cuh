@@ -12,6 +12,14 @@
 
 #include "../../include/moka_b200.h"
 
+// Cells per block (= threads per block) of the fused stage / step kernels and their adjoints: a block owns this many
+// consecutive (space-filling-curve ordered) cells and the edges they own.  256 is what every measurement so far used; the
+// resident-blocks hints of the kernels scale with it so that the register budget per thread stays the same.
+#ifndef MOKAB_BLOCK_CELLS
+#define MOKAB_BLOCK_CELLS 256
+#endif
+#define MOKAB_BLOCKS_SCALED(n) ((n) * 256 / MOKAB_BLOCK_CELLS)
+
 namespace mokab {
 
 extern thread_local std::string g_last_error;

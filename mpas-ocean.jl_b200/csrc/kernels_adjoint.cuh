@@ -24,7 +24,7 @@
 namespace mokab {
 namespace adjoint {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = MOKAB_BLOCK_CELLS;
 
 template <class R>
 struct AdjArgs {
@@ -53,7 +53,7 @@ struct AdjArgs {
 #define MOKAB_ADJ_MINBLOCKS 4
 #endif
 template <class R, int MODE, int S2TT, int ST>
-__global__ void __launch_bounds__(kThreads, MOKAB_ADJ_MINBLOCKS)
+__global__ void __launch_bounds__(kThreads, MOKAB_BLOCKS_SCALED(MOKAB_ADJ_MINBLOCKS))
 k_rk_stage_adj(const AdjArgs<R> A)
 {
     const int nE = A.nE, nC = A.nC;
@@ -180,7 +180,7 @@ struct FeAdjArgs {
 };
 
 template <int S2TT, int ST>
-__global__ void __launch_bounds__(kThreads, MOKAB_ADJ_MINBLOCKS)
+__global__ void __launch_bounds__(kThreads, MOKAB_BLOCKS_SCALED(MOKAB_ADJ_MINBLOCKS))
 k_fe_step_adj(const FeAdjArgs A)
 {
     const int nE = A.nE, nC = A.nC;

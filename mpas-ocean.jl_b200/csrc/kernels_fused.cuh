@@ -37,8 +37,8 @@
 namespace mokab {
 namespace fused {
 
-constexpr int kTC = 256;       // cells per block
-constexpr int kThreads = 256;
+constexpr int kTC = MOKAB_BLOCK_CELLS;       // cells per block
+constexpr int kThreads = MOKAB_BLOCK_CELLS;
 
 // Round-to-nearest multiply/add that the compiler may not contract into FMA: the fused kernel keeps the
 // reference's operation order so that Float64 results are bit-identical to the oracle.
@@ -103,7 +103,7 @@ struct StageArgs {
 // F64 2.81 / 2.49 / 2.09 G cell-steps/s at 4 / 5 / 6 blocks, F32 3.62 / 4.05 / 3.83
 template <class R> constexpr int der_minblocks() { return sizeof(R) == 8 ? 4 : 5; }
 template <class R, int STAGE, int S2T, int ST, bool FOLD, bool DER, bool PUSH = false>
-__global__ void __launch_bounds__(kThreads, DER ? der_minblocks<R>() : MOKAB_MINBLOCKS)
+__global__ void __launch_bounds__(kThreads, MOKAB_BLOCKS_SCALED(DER ? der_minblocks<R>() : MOKAB_MINBLOCKS))
 k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
 {
     const int S2 = S2T ? S2T : S2rt;
@@ -325,7 +325,7 @@ struct FeArgs {
 };
 
 template <int S2T, int ST, bool UNIF>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, MOKAB_BLOCKS_SCALED(4))
 k_fe_step(const FeArgs A)
 {
     const int nE = A.nE, nC = A.nC;

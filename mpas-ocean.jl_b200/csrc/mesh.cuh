@@ -74,7 +74,7 @@ struct HostMesh {
     double f0 = 0.0;
 };
 
-constexpr int kBlockCells = 256;  // cells per block of the fused kernel (fused::kTC)
+constexpr int kBlockCells = MOKAB_BLOCK_CELLS;  // cells per block of the fused kernel (fused::kTC)
 
 static void build_host_mesh(const mokab_mesh_desc &d, uint32_t flags, HostMesh &m)
 {

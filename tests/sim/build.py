@@ -119,6 +119,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for p in srcs + extra:
         h.update(open(p, "rb").read())
     h.update(os.environ.get("MOKAB_SIM_ASAN", "").encode())
+    extra_flags = os.environ.get("MOKAB_SIM_CFLAGS", "").split()          # e.g. -DMOKAB_BLOCK_CELLS=128: a tuning variant of the kernels
+    h.update(" ".join(extra_flags).encode())
     stamp = os.path.join(BUILD, "stamp")
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == h.hexdigest():
         return LIB
@@ -139,7 +141,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     asan = ["-fsanitize=address", "-fno-omit-frame-pointer"] if os.environ.get("MOKAB_SIM_ASAN") == "1" else []
     if os.environ.get("MOKAB_SIM_ASAN") == "undefined":       # UndefinedBehaviorSanitizer instead (shifts, signed overflow, misaligned access)
         asan = ["-fsanitize=undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer"]
-    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", *asan, "-fopenmp", "-ffp-contract=off", "-fno-fast-math", "-DMOKAB_SIM", "-U_FORTIFY_SOURCE",
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", *asan, *extra_flags, "-fopenmp", "-ffp-contract=off", "-fno-fast-math", "-DMOKAB_SIM", "-U_FORTIFY_SOURCE",
            "-Wno-unknown-pragmas", "-I", os.path.join(HERE, "include"), os.path.join(gen, "moka_b200.cpp"),
            os.path.join(HERE, "sim_runtime.cpp"), "-o", LIB,
            "-Wl,-Bsymbolic",      # the cuda* symbols defined here must win over a real libcudart that torch may have loaded
