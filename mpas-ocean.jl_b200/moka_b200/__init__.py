@@ -9,5 +9,5 @@ from .planar_voronoi import periodic_voronoi  # noqa: F401
 from .spherical_voronoi import geostrophic_zonal_flow, spherical_voronoi  # noqa: F401
 from . import config, driver, io_netcdf, time_manager  # noqa: F401,E402
 from .config import ConfigAdd, ConfigGet, ConfigRead, ConfigSet, GlobalConfig, yaml_config  # noqa: F401,E402
-from .driver import ModelSetup, ocn_init, ocn_init_alarms, ocn_run  # noqa: F401,E402
+from .driver import ModelSetup, ocn_init, ocn_init_alarms, ocn_run, ocn_run_decomposed  # noqa: F401,E402
 from .io_netcdf import ReadHorzMesh, VerticalMesh, write_mesh_netcdf, write_netcdf  # noqa: F401,E402

@@ -150,3 +150,65 @@ def ocn_run(config_fp: str, backend: api.B200 | None = None, stepper=None, dt_se
     print("Moka.jl ran on GPU")                                         # mpas_ocean.jl:48-51
     print(clock.currTime)
     return Setup, Diag, Tend, Prog, nsteps
+
+
+class _GatheredProg:
+    """What write_netcdf reads of a PrognosticVars, filled from the ranks' owned parts."""
+
+    def __init__(self, end, prev):
+        (self.ssh, self.normalVelocity, self.layerThickness), (self.ssh_prev, self.normalVelocity_prev, self.layerThickness_prev) = end, prev
+
+
+def ocn_run_decomposed(config_fp: str, backend: api.B200, device_index: int = 0, runtime=None, dt_seconds: float | None = None,
+                       halo: str = "nccl", graph: bool = True, series: list | None = None):
+    """`ocn_run` with the mesh decomposed over the ranks of a process group (one process per GPU; under torchrun every rank
+    calls this with its own `B200(LOCAL_RANK)`): the same YAML, the same NetCDF mesh / initial state, the same clock and
+    alarms, RungeKutta4 through multi_gpu.DecomposedModel (halo exchange per stage overlapped with the interior blocks), and
+    on rank 0 the same output file as the single-device run writes -- bit for bit.  The reference has no multi-device
+    driver.  Every rank reads the mesh and derives the same partition from it (deterministic), then keeps
+    only its own part.  Returns (Setup, model, nsteps)."""
+    from . import multi_gpu, partition
+    Config = ConfigRead(config_fp)
+    if _stepper_from_config(Config) is not api.RungeKutta4:
+        raise MokaError("ocn_run_decomposed: domain-decomposed runs step with RungeKutta4 (config_time_integrator: RK4); "
+                        "ForwardEuler has no staged form")
+    rt = runtime if runtime is not None else multi_gpu.TorchRuntime(device_index)
+    rank, world = rt.rank_and_size()
+    mesh_fp = ConfigGet(ConfigGet(Config.streams, "mesh"), "filename_template")
+    fields = io_netcdf.read_mesh_fields(mesh_fp)
+    clock = ocn_setup_clock(Config)
+    input_filename = ConfigGet(ConfigGet(Config.streams, "input"), "filename_template")
+    ssh, u, h = io_netcdf.read_initial_state(input_filename, fields["nCells"], fields["nEdges"], int(fields.get("nVertLevels", 1)))
+    loc = partition.decompose(fields, world)[rank]
+    model = multi_gpu.DecomposedModel(loc, multi_gpu.local_state(loc, ssh, u, h), backend, device_index, graph=graph, runtime=rt, halo=halo)
+    Setup = ModelSetup(Config, model.mesh, clock, fields)
+    dt = float(np.floor(2 * (np.mean(fields["dcEdge"]) / 1e3) * np.mean(fields["dcEdge"]) / 200e3)) if dt_seconds is None else float(dt_seconds)
+    if dt <= 0 or dt != np.floor(dt):
+        raise MokaError(f"ocn_run_decomposed: time step {dt} s is not a positive whole number of seconds (pass dt_seconds)")
+    changeTimeStep(clock, Second(int(dt)))                              # ocn_init_alarms, init.jl:111-127 (the GLOBAL mean of dcEdge)
+    simulationAlarm, outputAlarm = clock.alarms["simulation_end"], clock.alarms["outputAlarm"]
+    i = 0
+    while not isRinging(simulationAlarm):                               # ocn_run_loop, run_loop.jl:8-22, in batches between alarms
+        n = 0
+        while True:
+            advance(clock)
+            n += 1
+            if isRinging(simulationAlarm) or isRinging(outputAlarm):
+                break
+            if clock.currTime > simulationAlarm.ringTime:
+                raise MokaError("ocn_run_decomposed: the clock stepped over the simulation_end alarm without hitting it")
+        model.step(dt, n)
+        i += n
+        if isRinging(outputAlarm):
+            if series is not None:
+                model.finish()
+                series.append({"time": clock.currTime, "steps": i, "mass": model.reduce("mass"), "energy": model.reduce("energy"),
+                               "ssh2": model.reduce("ssh2")})
+            reset(outputAlarm)
+    model.finish()
+    end, prev = model.gather(fields["nCells"], fields["nEdges"]), model.gather(fields["nCells"], fields["nEdges"], previous=True)
+    if rank == 0:
+        io_netcdf.write_netcdf(Setup, None, _GatheredProg(end, prev))
+        print(f"Moka.jl ran on {world} GPUs")
+        print(clock.currTime)
+    return Setup, model, i

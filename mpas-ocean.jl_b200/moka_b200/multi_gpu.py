@@ -86,6 +86,15 @@ class TorchRuntime:
         self.dist.all_reduce(t, group=self.group)
         return float(t.item())
 
+    def rank_and_size(self):
+        return self.dist.get_rank(self.group), self.dist.get_world_size(self.group)
+
+    def sum_arrays(self, a: np.ndarray) -> np.ndarray:
+        """Element-wise sum of a host array over the ranks (output gathering: every rank fills its owned entries of a zero array)."""
+        t = self.torch.from_numpy(np.ascontiguousarray(a, np.float64)).to(self.dev)
+        self.dist.all_reduce(t, group=self.group)
+        return t.cpu().numpy()
+
     # set-up traffic of the direct-store halo exchange (once per model; tiny)
     def all_gather_bytes(self, blob: bytes) -> list:
         n = self.dist.get_world_size(self.group)
@@ -338,6 +347,18 @@ class DecomposedModel:
 
     def reduce(self, which: str) -> float:
         return self.rt.all_reduce_sum(api.reduce_sum(self.prog, which))
+
+    def gather(self, nC: int, nE: int, previous: bool = False):
+        """The global (ssh, normalVelocity, layerThickness) on every rank, assembled from the owned parts (`previous`: the
+        time level one step back, which is what the reference's write_netcdf writes, PrognosticVars.jl:108-113)."""
+        loc, out = self.loc, []
+        names = (("ssh_prev", "normalVelocity_prev", "layerThickness_prev") if previous else ("ssh", "normalVelocity", "layerThickness"))
+        for name, n, ids, no in ((names[0], nC, loc["cellsGlobal"], loc["nCellsOwned"]), (names[1], nE, loc["edgesGlobal"], loc["nEdgesOwned"]),
+                                 (names[2], nC, loc["cellsGlobal"], loc["nCellsOwned"])):
+            g = np.zeros(n, np.float64)
+            g[ids[:no]] = np.asarray(getattr(self.prog, name), np.float64)[:no]
+            out.append(self.rt.sum_arrays(g))
+        return out
 
 
 def local_state(loc: dict, ssh, u, h):

@@ -189,6 +189,68 @@ def run_mutations():
     sys.exit(0 if bad == 0 else 1)
 
 
+DRIVER_YAML = """
+omega:
+  time_management:
+    config_start_time: 0001-01-01_00:00:00
+    config_stop_time: none
+    config_run_duration: 0000-00-00_03:00:00
+    config_restart_timestamp_name: Restart_timestamp
+    config_do_restart: false
+  time_integration:
+    config_dt: 0000-00-00_00:15:00
+    config_number_of_time_levels: 2
+    config_time_integrator: RK4
+  streams:
+    mesh:
+      filename_template: {mesh}
+    input:
+      filename_template: {mesh}
+    output:
+      filename_template: {out}
+      reference_time: 0001-01-01_00:00:00
+      output_interval: 0000-00-00_01:00:00
+"""
+
+
+def run_driver(nparts, policy, halo):
+    """YAML -> NetCDF mesh -> decomposed run -> NetCDF output (driver.ocn_run_decomposed) against the single-device ocn_run:
+    the two output files must hold the same bits, and so must the conservation series taken at the output alarms."""
+    import tempfile
+
+    from scipy.io import netcdf_file
+    simcuda.set_policy(policy, 5)
+    with tempfile.TemporaryDirectory() as tmp:
+        m = mb.periodic_hex(24, 24, 300.0e3)             # dc = 300 km: the reference's dt rule gives 900 s (init.jl:118)
+        state = mb.inertialGravityWave(m).initial_state()
+        mesh_fp = os.path.join(tmp, "mesh.nc")
+        mb.write_mesh_netcdf(mesh_fp, m, state)
+        cfgs = {}
+        for tag in ("one", "many"):
+            cfgs[tag] = os.path.join(tmp, f"cfg_{tag}.yml")
+            with open(cfgs[tag], "w") as f:
+                f.write(DRIVER_YAML.format(mesh=mesh_fp, out=os.path.join(tmp, f"out_{tag}.nc")))
+        simcuda.set_policy("fifo")
+        _, _, _, prog1, n1 = mb.ocn_run(cfgs["one"], backend=mb.B200(0))
+        mass1 = mb.reduce_sum(prog1, "mass")
+        simcuda.set_policy(policy, 5)
+
+        def body(r, comm):
+            series = []
+            _, model, n = mb.driver.ocn_run_decomposed(cfgs["many"], mb.B200(0), 0, runtime=simcuda.SimRuntime(comm, r), halo=halo, series=series)
+            mass = model.reduce("mass")
+            model.close()
+            return n, series, mass
+
+        outs = simcuda.run_ranks(nparts, body)
+        ok = all(o[0] == n1 == 12 for o in outs) and len(outs[0][1]) == 3 and abs(outs[0][2] - mass1) <= 1e-13 * mass1
+        with netcdf_file(os.path.join(tmp, "out_one.nc"), "r", mmap=False) as a, netcdf_file(os.path.join(tmp, "out_many.nc"), "r", mmap=False) as b:
+            for k in ("ssh", "layerThickness", "normalVelocity", "xCell", "dcEdge", "time"):
+                ok = ok and np.array_equal(np.array(a.variables[k][:]), np.array(b.variables[k][:]))
+            ok = ok and float(a.dt) == float(b.dt) == 900.0
+    return ok
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", default="small")
@@ -233,6 +295,11 @@ def main():
             ok = run_e2e("igw", 48, 4, 5, policy, 3, halo)
             bad += not ok
             print(f"igw48 ranks=4 end-to-end leg (upload / step / download x5) {halo} {policy}: {'OK' if ok else 'MISMATCH'} {time.time() - t0:.1f}s", flush=True)
+    for halo in args.halo.split(","):
+        t0 = time.time()
+        ok = run_driver(3, args.policies.split(",")[0], halo)
+        bad += not ok
+        print(f"driver: YAML -> NetCDF -> 3 ranks -> NetCDF equals the single-device ocn_run, {halo}: {'OK' if ok else 'MISMATCH'} {time.time() - t0:.1f}s", flush=True)
     print("SIM_DECOMPOSED_OK" if bad == 0 else f"SIM_DECOMPOSED_FAILED ({bad})", flush=True)
     sys.exit(0 if bad == 0 else 1)
 

@@ -258,6 +258,16 @@ class SimRuntime:
     def all_reduce_sum(self, value: float) -> float:
         return float(self.comm.all_reduce_host(self.rank, float(value), lambda a, b: a + b))
 
+    def rank_and_size(self):
+        return self.rank, self.comm.n
+
+    def sum_arrays(self, a):
+        parts = self.comm.exchange_host(self.rank, np.array(a, np.float64))
+        out = parts[0].copy()
+        for p in parts[1:]:
+            out = out + p
+        return out
+
     def all_gather_bytes(self, blob: bytes) -> list:
         return self.comm.exchange_host(self.rank, blob)
 
