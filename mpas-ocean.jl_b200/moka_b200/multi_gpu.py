@@ -396,6 +396,12 @@ def _share_locals(args, rank, world, nx, dtype):
             from . import planar_voronoi
             m = planar_voronoi.periodic_voronoi(nx, nx, 1.0e7 / nx, jitter=0.25, seed=2, allow_obtuse=True, with_dual=False)
             ssh, u, h = api.inertialGravityWave(m).initial_state()
+        elif args.workload.startswith("sphere"):
+            from . import spherical_voronoi
+            m = spherical_voronoi.spherical_voronoi(nx * nx, with_dual=False)
+            ssh, u, h = spherical_voronoi.geostrophic_zonal_flow(m)
+            u = u + 0.1 * np.random.default_rng(0).standard_normal(m["nEdges"])
+            m["bench_dt"] = 0.25 * float(m["dcEdge"].min()) / float(np.sqrt(api.GRAVITY * 1000.0))
         else:
             m = planar_hex.periodic_hex(nx, nx, 1.0e7 / nx, with_dual=False)
             ssh, u, h = api.inertialGravityWave(m).initial_state()
@@ -404,6 +410,8 @@ def _share_locals(args, rank, world, nx, dtype):
             ls = local_state(loc, ssh, u, h)
             flat = {k: v for k, v in loc.items() if isinstance(v, np.ndarray)}
             meta = {k: v for k, v in loc.items() if not isinstance(v, (np.ndarray, dict))}
+            if "bench_dt" in m:
+                meta["bench_dt"] = m["bench_dt"]
             halo = loc["halo"]
             for q in halo["peers"]:
                 flat[f"halo_send_{q}"], flat[f"halo_recv_{q}"] = halo["send"][q], halo["recv"][q]
@@ -439,8 +447,9 @@ def bench_main(args, rank, world, local):
     npdt = np.float64 if args.dtype == "f64" else np.float32
     loc, state, t_setup = _share_locals(args, rank, world, nx, npdt)
     nC_glob = nx * nx
-    voronoi = args.workload.startswith("voronoi")
-    dt = (0.25 if voronoi else 1.0) * api.cfl_dt(1.0e7 / nx)
+    sphere = args.workload.startswith("sphere")
+    voronoi = args.workload.startswith("voronoi") or sphere      # unstructured: byte accounting from the actual rows
+    dt = float(loc["bench_dt"]) if sphere else (0.25 if voronoi else 1.0) * api.cfl_dt(1.0e7 / nx)
     backend = api.B200(local)
     model = DecomposedModel(loc, state, backend, local, dtype=npdt, overlap=not getattr(args, "no_overlap", False),
                             graph=not getattr(args, "no_graph", False), halo=getattr(args, "halo", "nccl"))
@@ -521,6 +530,7 @@ def bench_main(args, rank, world, local):
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype,
             "data": "synthetic",
             "config": {"workload": ("coastal Kelvin wave, %dx%d channel hex mesh with boundary-edge masks" % (nx, nx) if args.workload.startswith("kelvin")
+                                    else "geostrophic zonal flow + noise, spherical Voronoi mesh, fEdge = 2 Omega sin(lat)" if sphere
                                     else f"inertial gravity wave, {nx}x{nx} periodic planar Voronoi mesh of a jittered lattice" if voronoi
                                     else f"inertial gravity wave, {nx}x{nx} periodic planar hex mesh") + f" ({nC_glob} cells), "
                                    f"{'Float64' if args.dtype == 'f64' else 'Float32'} RK4, dt={dt:.4g}s, recursive-coordinate-bisection "
