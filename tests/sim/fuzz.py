@@ -28,6 +28,7 @@ _lib.bind(ctypes.CDLL(simcuda._build.LIB))
 import adjoint_oracle as A  # noqa: E402
 import moka_b200 as mb  # noqa: E402
 import moka_oracle_c as OC  # noqa: E402
+from moka_b200 import multi_gpu, partition  # noqa: E402
 from test_gpu_decomposed import _run_emulated  # noqa: E402
 
 G, DEPTH = 9.80616, 1000.0
@@ -127,6 +128,33 @@ def one_case(rng, backend):
         if not (np.array_equal(gu, base.normalVelocity) and np.array_equal(gh, base.layerThickness)):
             problems.append(f"decomposed {nparts} ranks {halo}")
         desc += f"; {nparts} ranks {halo}"
+        # and, now and then, the product's DecomposedModel itself: one host thread per rank, two streams per rank, in-stream
+        # exchange, a random sequence of step() calls (graph replays from both parities), against the same single-domain bits
+        if rng.integers(0, 3) == 0:
+            calls = [int(x) for x in rng.integers(1, 5, size=int(rng.integers(1, 4)))]
+            overlap, graph = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+            locs = partition.decompose(md, nparts)
+
+            def body(r, comm):
+                model = multi_gpu.DecomposedModel(locs[r], multi_gpu.local_state(locs[r], ssh, u, h), mb.B200(0), 0, overlap=overlap,
+                                                  graph=graph, runtime=simcuda.SimRuntime(comm, r), halo=halo)
+                for n in calls:
+                    model.step(dt, n)
+                model.finish()
+                res = (np.array(model.owned("normalVelocity")), np.array(model.owned("layerThickness")))
+                model.close()
+                return res
+
+            outs = simcuda.run_ranks(nparts, body)
+            gu2, gh2 = np.full(m["nEdges"], np.nan), np.full(m["nCells"], np.nan)
+            for loc, (ru, rh) in zip(locs, outs):
+                gu2[loc["edgesGlobal"][:loc["nEdgesOwned"]]] = ru
+                gh2[loc["cellsGlobal"][:loc["nCellsOwned"]]] = rh
+            ref = mb.PrognosticVars(ssh, u, h, 2, mb.Mesh(m, backend))
+            mb.ocn_timestep(dt, ref, None, None, None, mb.RungeKutta4, nsteps=sum(calls))
+            if not (np.array_equal(gu2, ref.normalVelocity) and np.array_equal(gh2, ref.layerThickness)):
+                problems.append(f"DecomposedModel {nparts} ranks {halo} overlap={overlap} graph={graph} calls={calls}")
+            desc += f" + threads {calls} overlap={overlap} graph={graph}"
     return f"{desc}; {nsteps} steps; renumber={renumber}; {policy}", problems
 
 
