@@ -33,6 +33,9 @@
 #pragma once
 #include "common.cuh"
 #include "kernels_p2p.cuh"
+#ifndef MOKAB_SIM
+#include <cuda/barrier>
+#endif
 
 namespace mokab {
 namespace fused {
@@ -92,6 +95,7 @@ struct StageArgs {
     R f0;                    // uniform fEdge (FOLD = false): weights stay unfolded, (w*u)*f0 formed as the reference does;
                              // FOLD = true: wf already holds weightsOnEdge*fEdge[eoe] (variable f; differs by round-off)
     const PushStage<R> *push;  // PUSH launches only (device memory); nullptr otherwise
+    int wStride;               // TMA launches only: elements between the staged weight rows in shared memory
 };
 
 // STAGE: 1 = first, 2 = middle (2 and 3), 4 = last.  S2/S: compile-time maxEdges2/maxEdges (0 = runtime).
@@ -102,8 +106,22 @@ struct StageArgs {
 // across the index reconstruction without spilling (4 blocks), Float32 fits in 48 (5 blocks) -- measured r01h:
 // F64 2.81 / 2.49 / 2.09 G cell-steps/s at 4 / 5 / 6 blocks, F32 3.62 / 4.05 / 3.83
 template <class R> constexpr int der_minblocks() { return sizeof(R) == 8 ? 4 : 5; }
-template <class R, int STAGE, int S2T, int ST, bool FOLD, bool DER, bool PUSH = false>
-__global__ void __launch_bounds__(kThreads, MOKAB_BLOCKS_SCALED(DER ? der_minblocks<R>() : MOKAB_MINBLOCKS))
+// TMA = true (opt-in, MOKAB_STAGE_TMA=1; compile-time row widths only): the Coriolis weights of the block's edges -- ten
+// contiguous runs, 80 of the ~160 streamed bytes per edge in Float64 -- are fetched by ONE thread with bulk asynchronous copies
+// (cp.async.bulk, the 1-D TMA path) into shared memory behind an mbarrier, at the very top of the kernel; the threads meanwhile
+// issue their index loads and gathers and wait on the barrier only where the first weighted sum starts.  The DRAM latency of
+// the bulk of the bytes is thereby decoupled from the register file, which is what limits the resident warps of the plain
+// kernel.  A bulk copy needs 16-byte aligned addresses and sizes: each row is fetched from the aligned address below its
+// first element (`shift` elements early) and rounded up, the arrays carry a few elements of padding at the end.
+template <class R> __host__ __device__ constexpr int tma_align() { return 16 / (int)sizeof(R); }
+#ifdef MOKAB_SIM
+#define MOKAB_DYN_SMEM(name) unsigned char *name = ::mokab_sim::dynamic_smem()
+#else
+#define MOKAB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
+template <class R, int STAGE, int S2T, int ST, bool FOLD, bool DER, bool PUSH = false, bool TMA = false>
+__global__ void __launch_bounds__(kThreads, MOKAB_BLOCKS_SCALED(TMA ? 3 : DER ? der_minblocks<R>() : MOKAB_MINBLOCKS))
 k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
 {
     const int S2 = S2T ? S2T : S2rt;
@@ -111,6 +129,52 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
     const int nE = A.nE, nC = A.nC;
     const int b = A.blockList ? A.blockList[blockIdx.x] : blockIdx.x;
     const int cBase = b * kTC;
+    static_assert(!TMA || (S2T != 0 && ST != 0), "the TMA variant stages compile-time many weight rows");
+    [[maybe_unused]] const R *sw = nullptr;
+    [[maybe_unused]] bool weights_landed = false;
+#ifndef MOKAB_SIM
+    [[maybe_unused]] typename cuda::barrier<cuda::thread_scope_block>::arrival_token tma_token;
+    [[maybe_unused]] cuda::barrier<cuda::thread_scope_block> *tma_bar = nullptr;
+#endif
+    if constexpr (TMA) {
+        MOKAB_DYN_SMEM(dyn);
+        R *dst = reinterpret_cast<R *>(dyn);
+        sw = dst;
+        constexpr int AL = tma_align<R>();
+        const int eb0 = A.blkEdgeStart[b], nb = A.blkEdgeStart[b + 1] - eb0;
+#ifdef MOKAB_SIM
+        if (threadIdx.x == 0)
+            for (int i = 0; i < S2T; ++i) {
+                const size_t g0 = (size_t)i * nE + eb0, a0 = g0 & ~(size_t)(AL - 1);
+                const size_t cnt = (g0 - a0 + nb + AL - 1) / AL * AL;
+                for (size_t k = 0; k < cnt; ++k) dst[(size_t)i * A.wStride + k] = A.wf[a0 + k];
+            }
+        __syncthreads();
+        weights_landed = true;
+#else
+#pragma nv_diag_suppress static_var_with_dynamic_init
+        __shared__ cuda::barrier<cuda::thread_scope_block> bar;
+        tma_bar = &bar;
+        if (threadIdx.x == 0) {
+            init(&bar, blockDim.x);
+            cuda::device::experimental::fence_proxy_async_shared_cta();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int bytes = 0;
+            for (int i = 0; i < S2T; ++i) {
+                const size_t g0 = (size_t)i * nE + eb0, a0 = g0 & ~(size_t)(AL - 1);
+                const unsigned int cnt = (unsigned int)((g0 - a0 + nb + AL - 1) / AL * AL);
+                if (cnt == 0) continue;                                      // a block that owns no edge
+                cuda::device::experimental::cp_async_bulk_global_to_shared(dst + (size_t)i * A.wStride, A.wf + a0, cnt * (unsigned int)sizeof(R), bar);
+                bytes += cnt * (unsigned int)sizeof(R);
+            }
+            tma_token = cuda::device::barrier_arrive_tx(bar, 1, bytes);
+        } else {
+            tma_token = bar.arrive();
+        }
+#endif
+    }
     if constexpr (PUSH) {
 #ifndef MOKAB_SIM   // (the simulated runtime cannot spin inside a kernel: the host enqueues the same predicate before the launch)
         const PushStage<R> &P = *A.push;
@@ -151,8 +215,10 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
 #pragma unroll
                 for (int i = 0; i < S2T; ++i) idx[i] = ld_stream(A.eoe + (size_t)i * nE + e);
             }
+            if constexpr (!TMA) {
 #pragma unroll
-            for (int i = 0; i < S2T; ++i) w[i] = ld_stream(A.wf + (size_t)i * nE + e);
+                for (int i = 0; i < S2T; ++i) w[i] = ld_stream(A.wf + (size_t)i * nE + e);
+            }
             const R g = ld_stream(A.gdc + e);
             // the RK operands are independent of the tendency: issue their loads now (they may alias the stores
             // below, so the compiler cannot hoist them itself)
@@ -194,6 +260,17 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
             R uu[S2T ? S2T : 1];
 #pragma unroll
             for (int i = 0; i < S2T; ++i) uu[i] = __ldg(A.uOld + idx[i]);
+            if constexpr (TMA) {   // the staged rows: wait for the bulk copies once, then plain shared-memory reads (conflict-free: edge-major)
+#ifndef MOKAB_SIM
+                if (!weights_landed) {
+                    tma_bar->wait(std::move(tma_token));
+                    weights_landed = true;
+                }
+#endif
+                constexpr int AL = tma_align<R>();
+#pragma unroll
+                for (int i = 0; i < S2T; ++i) w[i] = sw[(size_t)i * A.wStride + (((size_t)i * nE + e0) & (size_t)(AL - 1)) + (e - e0)];
+            }
             // tend = 0 - (g/dc)*(ssh2 - ssh1), then += (w*u)*f slot by slot (pressure_gradient.jl:63, coriolis :70-72)
             k = -mul_rn(g, add_rn(add_rn(h2, -H2), -add_rn(h1, -H1)));
 #pragma unroll

@@ -350,6 +350,7 @@ struct mokab_mesh {
     int nDerivedBlocks = 0;
     int64_t nCo = 0, nEo = 0;            // owned cells / edges (== nC / nE without decomposition)
     int fusedBlocks = 0, nInterior = 0, nBoundary = 0;
+    int maxBlockEdges = 0;               // the most edges any block owns (sizes the shared-memory rows of the TMA stage variant)
     bool uniformF = true; double f0 = 0.0;
     std::vector<int32_t> hBlkEdgeStart, hBlkInterior, hBlkBoundary;  // host copies (halo_setup re-classifies)
     mokab::DevBuf<int32_t> haloSend, haloRecv;  // combined [cells | edges] indices, device numbering

@@ -160,6 +160,8 @@ static void upload_mesh(mokab_ctx *ctx, HostMesh &hm, mokab_mesh *m)
     m->nDerivedBlocks = 0;
     for (uint8_t d : hm.blkDerived) m->nDerivedBlocks += d;
     m->fusedBlocks = (int)hm.blkEdgeStart.size() - 1;
+    m->maxBlockEdges = 0;
+    for (int b = 0; b < m->fusedBlocks; ++b) m->maxBlockEdges = std::max(m->maxBlockEdges, hm.blkEdgeStart[b + 1] - hm.blkEdgeStart[b]);
     m->nInterior = (int)hm.blkInterior.size();
     m->nBoundary = (int)hm.blkBoundary.size();
     m->hBlkEdgeStart.swap(hm.blkEdgeStart); m->hBlkInterior.swap(hm.blkInterior); m->hBlkBoundary.swap(hm.blkBoundary);
@@ -178,7 +180,9 @@ static void ensure_fused(mokab_mesh *m)
         m->eoeF.alloc((size_t)m->S2 * m->nE);
         m->eocF.alloc((size_t)m->S * m->nC);
     }
-    f.gdc.alloc(m->nE); f.dv.alloc(m->nE); f.wf.alloc((size_t)m->S2 * m->nE);
+    f.gdc.alloc(m->nE); f.dv.alloc(m->nE);
+    f.wf.alloc((size_t)m->S2 * m->nE + 16);       // + padding: the bulk copies of the TMA stage variant round their rows up to 16 bytes
+    f.wf.zero(ctx->stream);
     f.invArea.alloc(m->nC); f.H.alloc(m->nC);
     LAUNCH(ctx, fused::k_build_fused_edges<R>, nblk(m->nE), 256, (int)m->nE, m->S2, m->dc.p, m->dv.p, m->fE.p, m->eoe.p,
            m->woe.p, m->nEoE.p, f.gdc.p, f.dv.p, f.wf.p, need_idx ? m->eoeF.p : nullptr, m->uniformF ? 0 : 1);
@@ -553,6 +557,12 @@ static void step_rk4_unfused(mokab_state *st, double dt)
 }
 
 static int p2p_target(const mokab_state *st, int stage);
+// MOKAB_STAGE_TMA=1 selects the TMA variant of the fused stage kernel on hexagon meshes (not yet measured on hardware)
+static bool stage_tma_enabled()
+{
+    static const bool on = [] { const char *e = getenv("MOKAB_STAGE_TMA"); return e && e[0] == '1'; }();
+    return on;
+}
 #ifdef MOKAB_SIM
 static void p2p_gate_sim(mokab_state *st, cudaStream_t s);
 #endif
@@ -582,6 +592,32 @@ static void launch_stage(mokab_ctx *ctx, const mokab_mesh *m, fused::StageArgs<R
         return;
     }
     const bool der = (hex || hept) && m->nDerivedBlocks > 0;
+    if (hex && stage_tma_enabled()) {   // opt-in: the weight rows of a block through bulk asynchronous copies (kernels_fused.cuh)
+        constexpr int AL = fused::tma_align<R>();
+        A.wStride = (m->maxBlockEdges + AL + AL - 1) / AL * AL;
+        const size_t smem = (size_t)10 * A.wStride * sizeof(R);
+        if (smem <= 72 * 1024) {        // three blocks per SM; meshes whose blocks own more edges than that keep the plain kernel
+#define MOKAB_STAGE_TMA(FOLD, DER)                                                                                                  \
+    do {                                                                                                                            \
+        auto k_rk_stage_tma = fused::k_rk_stage<R, STAGE, 10, 6, FOLD, DER, false, true>;                                                     \
+        static bool attr_set = false;                                                                                               \
+        if (!attr_set) {                                                                                                            \
+            MOKAB_CUDA(cudaFuncSetAttribute(k_rk_stage_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));                         \
+            attr_set = true;                                                                                                        \
+        }                                                                                                                           \
+        k_rk_stage_tma<<<grid, fused::kThreads, smem, s>>>(A, m->S2, m->S);                                                                \
+    } while (0)
+            if (der && m->uniformF)      MOKAB_STAGE_TMA(false, true);
+            else if (der)                MOKAB_STAGE_TMA(true, true);
+            else if (m->uniformF)        MOKAB_STAGE_TMA(false, false);
+            else                         MOKAB_STAGE_TMA(true, false);
+#undef MOKAB_STAGE_TMA
+            MOKAB_CUDA(cudaGetLastError());
+            ctx->launches++;
+            return;
+        }
+        A.wStride = 0;
+    }
 #define MOKAB_STAGE(S2T, ST, FOLD, DER) fused::k_rk_stage<R, STAGE, S2T, ST, FOLD, DER><<<grid, fused::kThreads, 0, s>>>(A, m->S2, m->S)
     if (hex && der && m->uniformF)  MOKAB_STAGE(10, 6, false, true);
     else if (hex && der)            MOKAB_STAGE(10, 6, true, true);
@@ -616,6 +652,7 @@ static fused::StageArgs<R> stage_args(mokab_state *st, double dt, int p, int sta
     A.a = (R)a[stage - 1]; A.b = (R)b[stage - 1];
     A.f0 = (R)m->f0;
     A.push = nullptr;
+    A.wStride = 0;
     switch (stage) {
     case 1: A.uOld = t->u[p].p;  A.hOld = t->h[p].p;  A.uOut = t->uP[0].p; A.hOut = t->hP[0].p; break;  // provisional == current
     case 2: A.uOld = t->uP[0].p; A.hOld = t->hP[0].p; A.uOut = t->uP[1].p; A.hOut = t->hP[1].p; break;

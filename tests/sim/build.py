@@ -2,7 +2,7 @@
 shim (tests/sim/include/cuda_runtime.h + sim_runtime.cpp).  TEST INFRASTRUCTURE -- see the shim's header.
 
 The only source transformation is the kernel-launch syntax, which g++ cannot parse:
-    K<<<grid, block, smem, stream>>>(args...)   ->   ::mokab_sim::launch_impl(coop, "K", K, grid, block, stream, args...)
+    K<<<grid, block, smem, stream>>>(args...)   ->   ::mokab_sim::launch_impl(coop, "K", K, grid, block, smem, stream, args...)
 Everything else (host logic, kernels, templates) is compiled as written, with MOKAB_SIM defined
 (csrc/common.cuh swaps its inline-PTX streaming loads for plain loads under that macro)."""
 from __future__ import annotations
@@ -92,6 +92,7 @@ def rewrite_launches(src: str) -> tuple[str, int]:
         cfg = _split_top(src[k + 3:end_cfg].replace("\\\n", " "))
         assert len(cfg) in (2, 3, 4), cfg
         grid, block = cfg[0], cfg[1]
+        smem = cfg[2] if len(cfg) >= 3 else "0"
         stream = cfg[3] if len(cfg) == 4 else "nullptr"
         a0 = end_cfg + 3
         while src[a0].isspace():
@@ -101,7 +102,7 @@ def rewrite_launches(src: str) -> tuple[str, int]:
         args = src[a0 + 1:a1]
         name = "#" + kernel if re.fullmatch(r"[A-Za-z_]\w*", kernel) and kernel == "kernel" else '"' + kernel.replace('"', "'") + '"'
         coop = "::mokab_sim::is_coop_name(%s)" % name
-        repl = f"::mokab_sim::launch_impl({coop}, {name}, {kernel}, (unsigned)({grid}), (unsigned)({block}), ({stream}), {args})"
+        repl = f"::mokab_sim::launch_impl({coop}, {name}, {kernel}, (unsigned)({grid}), (unsigned)({block}), (size_t)({smem}), ({stream}), {args})"
         src = src[:start] + repl + src[a1 + 1:]
         n += 1
 

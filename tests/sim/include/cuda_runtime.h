@@ -113,9 +113,15 @@ cudaError_t cudaGraphInstantiate(cudaGraphExec_t *ge, cudaGraph_t g, unsigned lo
 cudaError_t cudaGraphDestroy(cudaGraph_t g);
 cudaError_t cudaGraphExecDestroy(cudaGraphExec_t ge);
 cudaError_t cudaGraphLaunch(cudaGraphExec_t ge, cudaStream_t s);
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+cudaError_t cudaFuncSetAttribute(const void *func, enum cudaFuncAttribute attr, int value);
 cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p);
 cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned flags);
 cudaError_t cudaIpcCloseMemHandle(void *p);
+}
+template <class F> static inline cudaError_t cudaFuncSetAttribute(F *func, enum cudaFuncAttribute attr, int value)
+{
+    return cudaFuncSetAttribute((const void *)func, attr, value);
 }
 // the toolkit's C++ convenience overload
 template <class T> static inline cudaError_t cudaMalloc(T **p, size_t bytes) { return cudaMalloc((void **)(void *)p, bytes); }
@@ -131,20 +137,24 @@ template <class T> static inline cudaError_t cudaMalloc(T **p, size_t bytes) { r
 namespace mokab_sim {
 // `coop`: the kernel uses __syncthreads / warp shuffles (its threads run as fibers); otherwise threads run to
 // completion one after another and a call to either primitive aborts the launch with an error
-void enqueue_kernel(cudaStream_t s, unsigned grid, unsigned block, bool coop, const char *name, std::function<void()> body);
+void enqueue_kernel(cudaStream_t s, unsigned grid, unsigned block, size_t smem, bool coop, const char *name, std::function<void()> body);
+// the dynamic shared memory of the block that is executing (size given at launch; one buffer per host thread, reused)
+unsigned char *dynamic_smem();
 
 static inline bool is_coop_name(const char *kernel)
 {
     return __builtin_strstr(kernel, "reduce::k_") != nullptr || __builtin_strstr(kernel, "k_halo_push") != nullptr ||
-           (__builtin_strstr(kernel, "k_rk_stage") != nullptr && __builtin_strstr(kernel, ", true>") != nullptr);   // the PUSH variant
+           (__builtin_strstr(kernel, "k_rk_stage") != nullptr && __builtin_strstr(kernel, ", true>") != nullptr) ||   // the PUSH variant
+           __builtin_strstr(kernel, "k_rk_stage_tma") != nullptr;                                                    // the TMA variant
 }
 // a device-side wait on memory that another stream (or rank) writes: retried by the scheduler until `ready` returns true
 void enqueue_try(cudaStream_t s, const char *name, std::function<bool()> ready);
 
 template <class... P, class... A>
-static inline void launch_impl(bool coop, const char *name, void (*k)(P...), unsigned grid, unsigned block, cudaStream_t s, A &&...a)
+static inline void launch_impl(bool coop, const char *name, void (*k)(P...), unsigned grid, unsigned block, size_t smem, cudaStream_t s,
+                               A &&...a)
 {
     std::tuple<std::decay_t<P>...> args(static_cast<P>(std::forward<A>(a))...);
-    enqueue_kernel(s, grid, block, coop, name, [k, args]() { std::apply(k, args); });
+    enqueue_kernel(s, grid, block, smem, coop, name, [k, args]() { std::apply(k, args); });
 }
 }  // namespace mokab_sim

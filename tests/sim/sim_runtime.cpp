@@ -212,6 +212,7 @@ struct CoopBlock {
 };
 thread_local CoopBlock *t_coop = nullptr;
 thread_local bool t_in_kernel = false;
+thread_local std::vector<unsigned char> t_dyn_smem;
 
 void coop_to_main(CoopBlock *b)
 {
@@ -293,14 +294,16 @@ void run_block_coop(unsigned nthreads, const std::function<void()> &body)
     t_coop = nullptr;
 }
 
-void run_kernel(unsigned grid, unsigned block, bool coop, const std::function<void()> &body)
+void run_kernel(unsigned grid, unsigned block, size_t smem, bool coop, const std::function<void()> &body)
 {
     using namespace mokab_sim;
+    if (t_dyn_smem.size() < smem + 16) t_dyn_smem.resize(smem + 16);
     t_gridDim = dim3{grid, 1, 1};
     t_blockDim = dim3{block, 1, 1};
     t_in_kernel = true;
     for (unsigned b = 0; b < grid; ++b) {
         t_blockIdx = uint3{b, 0, 0};
+        if (smem) memset(t_dyn_smem.data(), 0xFF, smem);                  // shared memory starts undefined in every block
         if (coop) {
             run_block_coop(block, body);
         } else {
@@ -634,7 +637,12 @@ void enqueue_try(cudaStream_t s, const char *name, std::function<bool()> ready)
     enqueue(resolve(s), std::move(op));
 }
 
-void enqueue_kernel(cudaStream_t s, unsigned grid, unsigned block, bool coop, const char *name, std::function<void()> body)
+unsigned char *dynamic_smem()
+{
+    return (unsigned char *)(((uintptr_t)t_dyn_smem.data() + 15) & ~(uintptr_t)15);
+}
+
+void enqueue_kernel(cudaStream_t s, unsigned grid, unsigned block, size_t smem, bool coop, const char *name, std::function<void()> body)
 {
     std::unique_lock<std::mutex> lk(R.mu);
     if (grid == 0 || block == 0 || block > 1024) {  // cudaErrorInvalidConfiguration on hardware
@@ -644,7 +652,11 @@ void enqueue_kernel(cudaStream_t s, unsigned grid, unsigned block, bool coop, co
     Op op;
     op.kind = OP_WORK;
     op.name = name;
-    op.fn = [grid, block, coop, body = std::move(body)]() { run_kernel(grid, block, coop, body); };
+    if (smem > 227 * 1024) {                         // more than an SM has
+        t_last = cudaErrorInvalidValue;
+        return;
+    }
+    op.fn = [grid, block, smem, coop, body = std::move(body)]() { run_kernel(grid, block, smem, coop, body); };
     enqueue(resolve(s), std::move(op));
 }
 }  // namespace mokab_sim
@@ -994,6 +1006,7 @@ cudaError_t cudaGraphLaunch(cudaGraphExec_t ge, cudaStream_t s_)
     return cudaSuccess;
 }
 
+cudaError_t cudaFuncSetAttribute(const void *, enum cudaFuncAttribute, int) { return cudaSuccess; }
 cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return fail(cudaErrorUnknown); }       // one process: never needed
 cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return fail(cudaErrorUnknown); }
 cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }

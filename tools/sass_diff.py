@@ -26,8 +26,10 @@ def sass(lib):
 
 
 def norm(name):
-    # k_rk_stage gained a trailing template flag (PUSH = false for every pre-existing instantiation)
-    return name.replace("Lb0EEEvNS0_9StageArgs", "EEvNS0_9StageArgs")
+    # k_rk_stage gained trailing template flags (PUSH = false, TMA = false for every pre-existing instantiation)
+    if "k_rk_stage" in name and name.count("StageArgs") and "Lb0ELb0EEEvNS0_9StageArgs" in name:
+        return name.replace("Lb0ELb0EEEvNS0_9StageArgs", "EEvNS0_9StageArgs")
+    return name
 
 
 def main():
