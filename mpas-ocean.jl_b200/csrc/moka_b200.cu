@@ -567,6 +567,22 @@ static bool stage_tma_enabled()
 static void p2p_gate_sim(mokab_state *st, cudaStream_t s);
 #endif
 
+// The TMA stage variant needs more dynamic shared memory than the default limit: opt every instantiation in once, OUTSIDE
+// any stream capture (the graphs of run_rk4_fused capture the launches themselves).
+template <class R>
+static void stage_tma_prepare()
+{
+    static bool done = false;
+    if (done || !stage_tma_enabled()) return;
+#define MOKAB_TMA_ATTR(STAGE, FOLD, DER) \
+    MOKAB_CUDA(cudaFuncSetAttribute(fused::k_rk_stage<R, STAGE, 10, 6, FOLD, DER, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024))
+    MOKAB_TMA_ATTR(1, false, false); MOKAB_TMA_ATTR(1, false, true); MOKAB_TMA_ATTR(1, true, false); MOKAB_TMA_ATTR(1, true, true);
+    MOKAB_TMA_ATTR(2, false, false); MOKAB_TMA_ATTR(2, false, true); MOKAB_TMA_ATTR(2, true, false); MOKAB_TMA_ATTR(2, true, true);
+    MOKAB_TMA_ATTR(4, false, false); MOKAB_TMA_ATTR(4, false, true); MOKAB_TMA_ATTR(4, true, false); MOKAB_TMA_ATTR(4, true, true);
+#undef MOKAB_TMA_ATTR
+    done = true;
+}
+
 // ---- fused RK4 ------------------------------------------------------------------------------------------------
 template <class R, int STAGE>
 static void launch_stage(mokab_ctx *ctx, const mokab_mesh *m, fused::StageArgs<R> A, int part = MOKAB_PART_ALL,
@@ -599,13 +615,8 @@ static void launch_stage(mokab_ctx *ctx, const mokab_mesh *m, fused::StageArgs<R
         if (smem <= 72 * 1024) {        // three blocks per SM; meshes whose blocks own more edges than that keep the plain kernel
 #define MOKAB_STAGE_TMA(FOLD, DER)                                                                                                  \
     do {                                                                                                                            \
-        auto k_rk_stage_tma = fused::k_rk_stage<R, STAGE, 10, 6, FOLD, DER, false, true>;                                                     \
-        static bool attr_set = false;                                                                                               \
-        if (!attr_set) {                                                                                                            \
-            MOKAB_CUDA(cudaFuncSetAttribute(k_rk_stage_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));                         \
-            attr_set = true;                                                                                                        \
-        }                                                                                                                           \
-        k_rk_stage_tma<<<grid, fused::kThreads, smem, s>>>(A, m->S2, m->S);                                                                \
+        auto k_rk_stage_tma = fused::k_rk_stage<R, STAGE, 10, 6, FOLD, DER, false, true>;                                           \
+        k_rk_stage_tma<<<grid, fused::kThreads, smem, s>>>(A, m->S2, m->S);                                                         \
     } while (0)
             if (der && m->uniformF)      MOKAB_STAGE_TMA(false, true);
             else if (der)                MOKAB_STAGE_TMA(true, true);
@@ -681,6 +692,7 @@ static void run_stage(mokab_state *st, double dt, int stage, int part, cudaStrea
 {
     mokab_ctx *ctx = st->ctx; const mokab_mesh *m = st->mesh;
     ensure_fused<R>(const_cast<mokab_mesh *>(m));
+    stage_tma_prepare<R>();
     fused::StageArgs<R> A = stage_args<R>(st, dt, st->cur, stage);
     if (part == MOKAB_PART_BOUNDARY_PUSH) {
         MOKAB_REQUIRE(st->p2p.ready, "rk4_stage(MOKAB_PART_BOUNDARY_PUSH): call mokab_p2p_setup first");
@@ -781,6 +793,7 @@ static void run_rk4_fused(mokab_state *st, double dt, int64_t nsteps)
     MOKAB_REQUIRE(st->mesh->nCo == st->mesh->nC && st->mesh->nEo == st->mesh->nE,
                   "timestep_rk4: this mesh has halo entities; drive it with mokab_rk4_stage + mokab_halo_pack/unpack");
     ensure_fused<R>(const_cast<mokab_mesh *>(st->mesh));
+    stage_tma_prepare<R>();
     if (t->taping) {  // record the state before every step (plain launches: the tape slot changes per step)
         const mokab_mesh *m = st->mesh;
         MOKAB_REQUIRE((int64_t)t->tapeDt.size() + nsteps <= t->tapeCap, "timestep_rk4: the tape is full (mokab_tape_begin max_steps)");
@@ -903,6 +916,7 @@ static void ensure_adjoint(mokab_state *st)
     mokab_mesh *m = const_cast<mokab_mesh *>(st->mesh);
     mokab_ctx *ctx = st->ctx;
     ensure_fused<R>(m);
+    stage_tma_prepare<R>();
     ensure_adjoint_mesh(m);
     ensure_adj_state<R>(st);
     FusedMesh<R> &f = fused_of<R>(m);
