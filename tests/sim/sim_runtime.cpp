@@ -142,7 +142,7 @@ struct Runtime {
     uint64_t enqueue_epoch = 0;  // bumped by every enqueue (lets blocked waiters notice new work)
     int64_t n_kernels = 0, n_ops = 0, n_graph_nodes = 0, n_colls = 0;
     std::string fatal;
-    double deadlock_s = 5.0;
+    double deadlock_s = 60.0;   // a blocked wait gives other host threads (emulated ranks still setting up) this long to enqueue what it waits for
 };
 Runtime R;
 thread_local cudaError_t t_last = cudaSuccess;
