@@ -220,7 +220,10 @@ def run_b200(args):
                                f"{'Float64' if args.dtype == 'f64' else 'Float32'} RK4, dt={dt:.4g}s",
                    "name": args.workload, "l2": "inputs larger than L2 (no flush)" if nx >= 1024 else "fits in L2",
                    "mesh_gen_s": round(t_gen, 2), "mesh_upload_s": round(t_mesh, 2),
-                   "blocks_rebuilding_edgesOnEdge": [int(nder), int(nblk)]},
+                   "blocks_rebuilding_edgesOnEdge": [int(nder), int(nblk)],
+                   # which build / stage-kernel variant ran (tools/gpu_sweep_variants.sh; the defaults when unset)
+                   "variant": {"lib": os.environ.get("MOKAB_LIB", "libmoka_b200.so"),
+                               "stage_tma": int(os.environ.get("MOKAB_STAGE_TMA", "0") or 0)}},
         "clocks": clocks,
         "e2e": {"value": nC / e2e_s, "unit": "cell-steps/s", "h2d_bytes_per_step": int((nE + nC) * item),
                 "d2h_bytes_per_step": int(nC * item), "ms_per_step": e2e_s * 1e3, "steps": Ke,

@@ -95,7 +95,9 @@ struct StageArgs {
     R f0;                    // uniform fEdge (FOLD = false): weights stay unfolded, (w*u)*f0 formed as the reference does;
                              // FOLD = true: wf already holds weightsOnEdge*fEdge[eoe] (variable f; differs by round-off)
     const PushStage<R> *push;  // PUSH launches only (device memory); nullptr otherwise
-    int wStride;               // TMA launches only: elements between the staged weight rows in shared memory
+    int wStride;               // TMA = 1 launches only: elements between the staged weight rows in shared memory
+    const R *wfB;              // TMA = 2: the weights again, BLOCK-major -- block b's S2 rows back to back, each padded to 16 bytes,
+    const long long *wfBOff;   //          starting at element wfBOff[b] (16-byte aligned): one contiguous run, one bulk copy per block
 };
 
 // STAGE: 1 = first, 2 = middle (2 and 3), 4 = last.  S2/S: compile-time maxEdges2/maxEdges (0 = runtime).
@@ -106,13 +108,15 @@ struct StageArgs {
 // across the index reconstruction without spilling (4 blocks), Float32 fits in 48 (5 blocks) -- measured r01h:
 // F64 2.81 / 2.49 / 2.09 G cell-steps/s at 4 / 5 / 6 blocks, F32 3.62 / 4.05 / 3.83
 template <class R> constexpr int der_minblocks() { return sizeof(R) == 8 ? 4 : 5; }
-// TMA = true (opt-in, MOKAB_STAGE_TMA=1; compile-time row widths only): the Coriolis weights of the block's edges -- ten
+// TMA = 1 (opt-in, MOKAB_STAGE_TMA=1; compile-time row widths only): the Coriolis weights of the block's edges -- ten
 // contiguous runs, 80 of the ~160 streamed bytes per edge in Float64 -- are fetched by ONE thread with bulk asynchronous copies
 // (cp.async.bulk, the 1-D TMA path) into shared memory behind an mbarrier, at the very top of the kernel; the threads meanwhile
 // issue their index loads and gathers and wait on the barrier only where the first weighted sum starts.  The DRAM latency of
 // the bulk of the bytes is thereby decoupled from the register file, which is what limits the resident warps of the plain
 // kernel.  A bulk copy needs 16-byte aligned addresses and sizes: each row is fetched from the aligned address below its
 // first element (`shift` elements early) and rounded up, the arrays carry a few elements of padding at the end.
+// TMA = 2 (MOKAB_STAGE_TMA=2): the same over a block-major copy of the weights (wfB) -- the block's rows are one contiguous,
+// aligned run, ONE bulk copy, no shifts.
 template <class R> __host__ __device__ constexpr int tma_align() { return 16 / (int)sizeof(R); }
 #ifdef MOKAB_SIM
 #define MOKAB_DYN_SMEM(name) unsigned char *name = ::mokab_sim::dynamic_smem()
@@ -120,8 +124,8 @@ template <class R> __host__ __device__ constexpr int tma_align() { return 16 / (
 #define MOKAB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
 
-template <class R, int STAGE, int S2T, int ST, bool FOLD, bool DER, bool PUSH = false, bool TMA = false>
-__global__ void __launch_bounds__(kThreads, MOKAB_BLOCKS_SCALED(TMA ? 3 : DER ? der_minblocks<R>() : MOKAB_MINBLOCKS))
+template <class R, int STAGE, int S2T, int ST, bool FOLD, bool DER, bool PUSH = false, int TMA = 0>
+__global__ void __launch_bounds__(kThreads, MOKAB_BLOCKS_SCALED(TMA != 0 ? 3 : DER ? der_minblocks<R>() : MOKAB_MINBLOCKS))
 k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
 {
     const int S2 = S2T ? S2T : S2rt;
@@ -129,26 +133,32 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
     const int nE = A.nE, nC = A.nC;
     const int b = A.blockList ? A.blockList[blockIdx.x] : blockIdx.x;
     const int cBase = b * kTC;
-    static_assert(!TMA || (S2T != 0 && ST != 0), "the TMA variant stages compile-time many weight rows");
+    static_assert(TMA == 0 || (S2T != 0 && ST != 0), "the TMA variants stage compile-time many weight rows");
     [[maybe_unused]] const R *sw = nullptr;
     [[maybe_unused]] bool weights_landed = false;
 #ifndef MOKAB_SIM
     [[maybe_unused]] typename cuda::barrier<cuda::thread_scope_block>::arrival_token tma_token;
     [[maybe_unused]] cuda::barrier<cuda::thread_scope_block> *tma_bar = nullptr;
 #endif
-    if constexpr (TMA) {
+    if constexpr (TMA != 0) {
         MOKAB_DYN_SMEM(dyn);
         R *dst = reinterpret_cast<R *>(dyn);
         sw = dst;
         constexpr int AL = tma_align<R>();
         const int eb0 = A.blkEdgeStart[b], nb = A.blkEdgeStart[b + 1] - eb0;
+        [[maybe_unused]] const int nbp = (nb + AL - 1) / AL * AL;              // TMA = 2: padded row length of this block
 #ifdef MOKAB_SIM
-        if (threadIdx.x == 0)
-            for (int i = 0; i < S2T; ++i) {
-                const size_t g0 = (size_t)i * nE + eb0, a0 = g0 & ~(size_t)(AL - 1);
-                const size_t cnt = (g0 - a0 + nb + AL - 1) / AL * AL;
-                for (size_t k = 0; k < cnt; ++k) dst[(size_t)i * A.wStride + k] = A.wf[a0 + k];
+        if (threadIdx.x == 0) {
+            if constexpr (TMA == 2) {
+                for (size_t k = 0; k < (size_t)S2T * nbp; ++k) dst[k] = A.wfB[A.wfBOff[b] + k];
+            } else {
+                for (int i = 0; i < S2T; ++i) {
+                    const size_t g0 = (size_t)i * nE + eb0, a0 = g0 & ~(size_t)(AL - 1);
+                    const size_t cnt = (g0 - a0 + nb + AL - 1) / AL * AL;
+                    for (size_t k = 0; k < cnt; ++k) dst[(size_t)i * A.wStride + k] = A.wf[a0 + k];
+                }
             }
+        }
         __syncthreads();
         weights_landed = true;
 #else
@@ -162,6 +172,10 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
         __syncthreads();
         if (threadIdx.x == 0) {
             unsigned int bytes = 0;
+            if constexpr (TMA == 2) {
+                bytes = (unsigned int)((size_t)S2T * nbp * sizeof(R));
+                if (bytes) cuda::device::experimental::cp_async_bulk_global_to_shared(dst, A.wfB + A.wfBOff[b], bytes, bar);
+            } else
             for (int i = 0; i < S2T; ++i) {
                 const size_t g0 = (size_t)i * nE + eb0, a0 = g0 & ~(size_t)(AL - 1);
                 const unsigned int cnt = (unsigned int)((g0 - a0 + nb + AL - 1) / AL * AL);
@@ -215,7 +229,7 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
 #pragma unroll
                 for (int i = 0; i < S2T; ++i) idx[i] = ld_stream(A.eoe + (size_t)i * nE + e);
             }
-            if constexpr (!TMA) {
+            if constexpr (TMA == 0) {
 #pragma unroll
                 for (int i = 0; i < S2T; ++i) w[i] = ld_stream(A.wf + (size_t)i * nE + e);
             }
@@ -260,7 +274,7 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
             R uu[S2T ? S2T : 1];
 #pragma unroll
             for (int i = 0; i < S2T; ++i) uu[i] = __ldg(A.uOld + idx[i]);
-            if constexpr (TMA) {   // the staged rows: wait for the bulk copies once, then plain shared-memory reads (conflict-free: edge-major)
+            if constexpr (TMA != 0) {   // the staged rows: wait for the bulk copies once, then plain shared-memory reads (conflict-free: edge-major)
 #ifndef MOKAB_SIM
                 if (!weights_landed) {
                     tma_bar->wait(std::move(tma_token));
@@ -268,8 +282,14 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
                 }
 #endif
                 constexpr int AL = tma_align<R>();
+                if constexpr (TMA == 2) {
+                    const int nbp = (e1 - e0 + AL - 1) / AL * AL;
 #pragma unroll
-                for (int i = 0; i < S2T; ++i) w[i] = sw[(size_t)i * A.wStride + (((size_t)i * nE + e0) & (size_t)(AL - 1)) + (e - e0)];
+                    for (int i = 0; i < S2T; ++i) w[i] = sw[i * nbp + (e - e0)];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < S2T; ++i) w[i] = sw[(size_t)i * A.wStride + (((size_t)i * nE + e0) & (size_t)(AL - 1)) + (e - e0)];
+                }
             }
             // tend = 0 - (g/dc)*(ssh2 - ssh1), then += (w*u)*f slot by slot (pressure_gradient.jl:63, coriolis :70-72)
             k = -mul_rn(g, add_rn(add_rn(h2, -H2), -add_rn(h1, -H1)));
@@ -480,6 +500,22 @@ k_build_fused_edges(int nE, int S2, const double *__restrict__ dc, const double 
         const int x = i < n ? eoe[k] : -1;
         wf[k] = x >= 0 ? (foldF ? (R)__dmul_rn(woe[k], fE[x]) : (R)woe[k]) : R(0);
         if (eoeF) eoeF[k] = x >= 0 ? x : e;
+    }
+}
+
+// the weights once more, block-major (TMA = 2): block b's S2 rows back to back at wfBOff[b], each padded to a multiple of 16 bytes
+template <class R>
+__global__ void __launch_bounds__(256)
+k_build_wf_block_major(int nE, int S2, const int32_t *__restrict__ blkEdgeStart, const long long *__restrict__ off,
+                       const R *__restrict__ wf, R *__restrict__ wfB)
+{
+    const int b = blockIdx.x;
+    const int e0 = blkEdgeStart[b], nb = blkEdgeStart[b + 1] - e0;
+    constexpr int AL = 16 / (int)sizeof(R);
+    const int nbp = (nb + AL - 1) / AL * AL;
+    for (int k = threadIdx.x; k < S2 * nbp; k += 256) {
+        const int i = k / nbp, j = k - i * nbp;
+        wfB[off[b] + k] = j < nb ? wf[(size_t)i * nE + e0 + j] : R(0);
     }
 }
 

@@ -557,12 +557,14 @@ static void step_rk4_unfused(mokab_state *st, double dt)
 }
 
 static int p2p_target(const mokab_state *st, int stage);
-// MOKAB_STAGE_TMA=1 selects the TMA variant of the fused stage kernel on hexagon meshes (not yet measured on hardware)
-static bool stage_tma_enabled()
+// MOKAB_STAGE_TMA=1|2 selects a TMA variant of the fused stage kernel on hexagon meshes (not yet measured on hardware)
+// (1: the slot-major rows, ten bulk copies per block; 2: a block-major copy of the weights, one bulk copy per block)
+static int stage_tma_mode()
 {
-    static const bool on = [] { const char *e = getenv("MOKAB_STAGE_TMA"); return e && e[0] == '1'; }();
-    return on;
+    static const int mode = [] { const char *e = getenv("MOKAB_STAGE_TMA"); return e && (e[0] == '1' || e[0] == '2') ? e[0] - '0' : 0; }();
+    return mode;
 }
+static bool stage_tma_enabled() { return stage_tma_mode() != 0; }
 #ifdef MOKAB_SIM
 static void p2p_gate_sim(mokab_state *st, cudaStream_t s);
 #endif
@@ -574,13 +576,34 @@ static void stage_tma_prepare()
 {
     static bool done = false;
     if (done || !stage_tma_enabled()) return;
-#define MOKAB_TMA_ATTR(STAGE, FOLD, DER) \
-    MOKAB_CUDA(cudaFuncSetAttribute(fused::k_rk_stage<R, STAGE, 10, 6, FOLD, DER, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024))
+#define MOKAB_TMA_ATTR(STAGE, FOLD, DER)                                                                                                          \
+    MOKAB_CUDA(cudaFuncSetAttribute(fused::k_rk_stage<R, STAGE, 10, 6, FOLD, DER, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024)); \
+    MOKAB_CUDA(cudaFuncSetAttribute(fused::k_rk_stage<R, STAGE, 10, 6, FOLD, DER, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024))
     MOKAB_TMA_ATTR(1, false, false); MOKAB_TMA_ATTR(1, false, true); MOKAB_TMA_ATTR(1, true, false); MOKAB_TMA_ATTR(1, true, true);
     MOKAB_TMA_ATTR(2, false, false); MOKAB_TMA_ATTR(2, false, true); MOKAB_TMA_ATTR(2, true, false); MOKAB_TMA_ATTR(2, true, true);
     MOKAB_TMA_ATTR(4, false, false); MOKAB_TMA_ATTR(4, false, true); MOKAB_TMA_ATTR(4, true, false); MOKAB_TMA_ATTR(4, true, true);
 #undef MOKAB_TMA_ATTR
     done = true;
+}
+
+// TMA = 2: the block-major copy of the weights (built once per mesh and precision, synchronised like ensure_fused)
+template <class R>
+static void ensure_wf_block_major(mokab_mesh *m)
+{
+    FusedMesh<R> &f = fused_of<R>(m);
+    if (stage_tma_mode() != 2 || f.wfB.n || !(m->S2 == 10 && m->S == 6)) return;
+    mokab_ctx *ctx = m->ctx;
+    constexpr int AL = 16 / (int)sizeof(R);
+    std::vector<long long> off(m->fusedBlocks + 1, 0);
+    for (int b = 0; b < m->fusedBlocks; ++b) {
+        const long long nbp = (m->hBlkEdgeStart[b + 1] - m->hBlkEdgeStart[b] + AL - 1) / AL * AL;
+        off[b + 1] = off[b] + (long long)m->S2 * nbp;
+    }
+    f.wfB.alloc((size_t)std::max<long long>(off[m->fusedBlocks], 1) + 16);
+    f.wfBOff.upload(off, ctx->stream);
+    LAUNCH(ctx, fused::k_build_wf_block_major<R>, m->fusedBlocks, 256, (int)m->nE, m->S2, (const int32_t *)m->blkEdgeStart.p,
+           (const long long *)f.wfBOff.p, (const R *)f.wf.p, f.wfB.p);
+    MOKAB_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
 // ---- fused RK4 ------------------------------------------------------------------------------------------------
@@ -612,11 +635,20 @@ static void launch_stage(mokab_ctx *ctx, const mokab_mesh *m, fused::StageArgs<R
         constexpr int AL = fused::tma_align<R>();
         A.wStride = (m->maxBlockEdges + AL + AL - 1) / AL * AL;
         const size_t smem = (size_t)10 * A.wStride * sizeof(R);
+        if (stage_tma_mode() == 2) {
+            FusedMesh<R> &fm = fused_of<R>(const_cast<mokab_mesh *>(m));
+            A.wfB = fm.wfB.p; A.wfBOff = fm.wfBOff.p;
+        }
         if (smem <= 72 * 1024) {        // three blocks per SM; meshes whose blocks own more edges than that keep the plain kernel
 #define MOKAB_STAGE_TMA(FOLD, DER)                                                                                                  \
     do {                                                                                                                            \
-        auto k_rk_stage_tma = fused::k_rk_stage<R, STAGE, 10, 6, FOLD, DER, false, true>;                                           \
-        k_rk_stage_tma<<<grid, fused::kThreads, smem, s>>>(A, m->S2, m->S);                                                         \
+        if (stage_tma_mode() == 2) {                                                                                                \
+            auto k_rk_stage_tma = fused::k_rk_stage<R, STAGE, 10, 6, FOLD, DER, false, 2>;                                          \
+            k_rk_stage_tma<<<grid, fused::kThreads, smem, s>>>(A, m->S2, m->S);                                                     \
+        } else {                                                                                                                    \
+            auto k_rk_stage_tma = fused::k_rk_stage<R, STAGE, 10, 6, FOLD, DER, false, 1>;                                          \
+            k_rk_stage_tma<<<grid, fused::kThreads, smem, s>>>(A, m->S2, m->S);                                                     \
+        }                                                                                                                           \
     } while (0)
             if (der && m->uniformF)      MOKAB_STAGE_TMA(false, true);
             else if (der)                MOKAB_STAGE_TMA(true, true);
@@ -663,7 +695,7 @@ static fused::StageArgs<R> stage_args(mokab_state *st, double dt, int p, int sta
     A.a = (R)a[stage - 1]; A.b = (R)b[stage - 1];
     A.f0 = (R)m->f0;
     A.push = nullptr;
-    A.wStride = 0;
+    A.wStride = 0; A.wfB = nullptr; A.wfBOff = nullptr;
     switch (stage) {
     case 1: A.uOld = t->u[p].p;  A.hOld = t->h[p].p;  A.uOut = t->uP[0].p; A.hOut = t->hP[0].p; break;  // provisional == current
     case 2: A.uOld = t->uP[0].p; A.hOld = t->hP[0].p; A.uOut = t->uP[1].p; A.hOut = t->hP[1].p; break;
@@ -693,6 +725,7 @@ static void run_stage(mokab_state *st, double dt, int stage, int part, cudaStrea
     mokab_ctx *ctx = st->ctx; const mokab_mesh *m = st->mesh;
     ensure_fused<R>(const_cast<mokab_mesh *>(m));
     stage_tma_prepare<R>();
+    ensure_wf_block_major<R>(const_cast<mokab_mesh *>(m));
     fused::StageArgs<R> A = stage_args<R>(st, dt, st->cur, stage);
     if (part == MOKAB_PART_BOUNDARY_PUSH) {
         MOKAB_REQUIRE(st->p2p.ready, "rk4_stage(MOKAB_PART_BOUNDARY_PUSH): call mokab_p2p_setup first");
@@ -794,6 +827,7 @@ static void run_rk4_fused(mokab_state *st, double dt, int64_t nsteps)
                   "timestep_rk4: this mesh has halo entities; drive it with mokab_rk4_stage + mokab_halo_pack/unpack");
     ensure_fused<R>(const_cast<mokab_mesh *>(st->mesh));
     stage_tma_prepare<R>();
+    ensure_wf_block_major<R>(const_cast<mokab_mesh *>(st->mesh));
     if (t->taping) {  // record the state before every step (plain launches: the tape slot changes per step)
         const mokab_mesh *m = st->mesh;
         MOKAB_REQUIRE((int64_t)t->tapeDt.size() + nsteps <= t->tapeCap, "timestep_rk4: the tape is full (mokab_tape_begin max_steps)");
@@ -917,6 +951,7 @@ static void ensure_adjoint(mokab_state *st)
     mokab_ctx *ctx = st->ctx;
     ensure_fused<R>(m);
     stage_tma_prepare<R>();
+    ensure_wf_block_major<R>(m);
     ensure_adjoint_mesh(m);
     ensure_adj_state<R>(st);
     FusedMesh<R> &f = fused_of<R>(m);

@@ -11,7 +11,7 @@ ngpu=$(nvidia-smi -L | wc -l)
 timeout 1500 python -m pytest tests -m gpu -x -q > $out/pytest_$tag.log 2>&1; echo "pytest rc=$?"; tail -n 3 $out/pytest_$tag.log
 MOKAB_TEST_P2P=1 timeout 600 python -m pytest tests -m gpu -q -k direct_store > $out/pytest_p2p_$tag.log 2>&1; echo "pytest p2p rc=$?"; tail -n 3 $out/pytest_p2p_$tag.log
 # the TMA variant of the stage kernel (a run-time switch; bit-identical results expected); under its own timeout: first hardware run
-MOKAB_STAGE_TMA=1 timeout 300 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "config1_f64 or derived_edges or fused_f32 or variable_coriolis" > $out/pytest_tma_$tag.log 2>&1; echo "pytest tma rc=$?"; tail -n 2 $out/pytest_tma_$tag.log
+for tma in 1 2; do MOKAB_STAGE_TMA=$tma timeout 300 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "config1_f64 or derived_edges or fused_f32 or variable_coriolis" > $out/pytest_tma${tma}_$tag.log 2>&1; echo "pytest tma=$tma rc=$?"; tail -n 2 $out/pytest_tma${tma}_$tag.log; done
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke_$tag.log 2>&1; echo "smoke rc=$?"; tail -n 2 $out/smoke_$tag.log
 # 2. the one-GPU reproduction of last round's "graph mismatch" (expected now: identical)
 timeout 300 python tools/diag_graph_emulated.py > $out/diag_emulated_$tag.log 2>&1; echo "diag rc=$?"; cat $out/diag_emulated_$tag.log

@@ -26,9 +26,9 @@ def sass(lib):
 
 
 def norm(name):
-    # k_rk_stage gained trailing template flags (PUSH = false, TMA = false for every pre-existing instantiation)
-    if "k_rk_stage" in name and name.count("StageArgs") and "Lb0ELb0EEEvNS0_9StageArgs" in name:
-        return name.replace("Lb0ELb0EEEvNS0_9StageArgs", "EEvNS0_9StageArgs")
+    # k_rk_stage gained trailing template parameters (bool PUSH = false, int TMA = 0 for every pre-existing instantiation)
+    if "k_rk_stage" in name and "Lb0ELi0EEEvNS0_9StageArgs" in name:
+        return name.replace("Lb0ELi0EEEvNS0_9StageArgs", "EEvNS0_9StageArgs")
     return name
 
 
