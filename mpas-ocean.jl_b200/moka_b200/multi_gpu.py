@@ -540,7 +540,9 @@ def bench_main(args, rank, world, local):
                                    f"{', 2-step CUDA graph incl. the exchange (' + model.graph_status + ')' if model.use_graph else ', CUDA graph ' + model.graph_status}",
                        "name": args.workload, "l2": "inputs larger than L2 (no flush)", "setup_s": round(t_setup, 1),
                        "rank0_blocks_interior_boundary": list(blocks), "rank0_halo_bytes_per_stage": int(halo_bytes),
-                       "rank0_blocks_rebuilding_edgesOnEdge": [int(nder), int(nblk)]},
+                       "rank0_blocks_rebuilding_edgesOnEdge": [int(nder), int(nblk)],
+                       "variant": {"lib": os.environ.get("MOKAB_LIB", "libmoka_b200.so"),
+                                   "stage_tma": int(os.environ.get("MOKAB_STAGE_TMA", "0") or 0)}},
             "clocks": clocks,
             "e2e": {"value": nC_glob / e2e_s, "unit": "cell-steps/s", "h2d_bytes_per_step": int(cnt[0].item() * item),
                     "d2h_bytes_per_step": int(cnt[1].item() * item), "ms_per_step": e2e_s * 1e3, "steps": Ke,
