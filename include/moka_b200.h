@@ -216,7 +216,9 @@ int  mokab_reduce(mokab_state *state, int which, double *out);
  *   mokab_adjoint_seed(state, MOKAB_SUM_SSH2)      (or mokab_state_set of the MOKAB_D_* fields);
  *   mokab_adjoint_rk4(state);  mokab_state_get(state, MOKAB_D_NORMAL_VELOCITY / MOKAB_D_LAYER_THICKNESS, ...)
  * leaves dJ/d(initial normalVelocity, layerThickness) in the shadow fields. */
-/* Start recording: every following RK4_FUSED step stores its input state (max_steps * (nEdges + nCells) elements). */
+/* Start recording: every following RK4_FUSED step stores its input state (max_steps * (nEdges + nCells) elements).
+ * max_steps = 0 is allowed: the reverse sweep of an empty tape returns the seed (the gradient of the objective at the
+ * initial state). */
 int  mokab_tape_begin(mokab_state *state, int64_t max_steps);
 int  mokab_tape_length(mokab_state *state, int64_t *out);
 /* d_ssh = dJ/dssh of the current state for J = `which` (MOKAB_SUM_SSH2: sumArray, run_loop.jl:47-51); d_u = d_h = 0 */

@@ -832,7 +832,7 @@ static void run_rk4_fused(mokab_state *st, double dt, int64_t nsteps)
         const mokab_mesh *m = st->mesh;
         MOKAB_REQUIRE((int64_t)t->tapeDt.size() + nsteps <= t->tapeCap, "timestep_rk4: the tape is full (mokab_tape_begin max_steps)");
         MOKAB_REQUIRE(t->tapeKind != 2, "timestep_rk4: the tape already holds ForwardEuler steps");
-        if (nsteps > 0) t->tapeKind = 1;
+        t->tapeKind = 1;                    // (also a call with nsteps = 0: the seed then follows this stepper's state definition)
         for (int64_t i = 0; i < nsteps; ++i) {
             const size_t k = t->tapeDt.size();
             MOKAB_CUDA(cudaMemcpyAsync(t->tapeU.p + k * m->nE, t->u[st->cur].p, m->nE * sizeof(R), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -1728,6 +1728,10 @@ int mokab_timestep_forward_euler(mokab_state *state, double dt, int64_t nsteps)
                       "timestep_forward_euler: this mesh has halo entities and ForwardEuler has no staged form; domain-decomposed runs "
                       "step with mokab_rk4_stage + the halo exchange");
         state->ctx->bind();
+        if (state->d->taping) {             // also a call with nsteps = 0: ssh is an input of its own for this stepper's seed
+            MOKAB_REQUIRE(state->d->tapeKind != 1, "timestep_forward_euler: the tape already holds RungeKutta4 steps");
+            state->d->tapeKind = 2;
+        }
         if (fe_fusable(state)) {
             run_fe_fused(state, dt, nsteps);
         } else {
@@ -1785,7 +1789,8 @@ int mokab_reduce(mokab_state *state, int which, double *out)
 int mokab_tape_begin(mokab_state *state, int64_t max_steps)
 {
     return guarded([&] {
-        MOKAB_REQUIRE(state && max_steps > 0, "tape_begin: bad argument");
+        MOKAB_REQUIRE(state, "tape_begin: state is NULL");
+        MOKAB_REQUIRE(max_steps >= 0, "tape_begin: max_steps must be >= 0");
         state->ctx->bind();
         if (state->dtype == MOKAB_F64) tape_begin<double>(state, max_steps); else tape_begin<float>(state, max_steps);
     });

@@ -257,3 +257,24 @@ def test_committed_forward_euler_adjoint_fixture(backend):
     k = meta["fd_index"]
     assert abs(d_prog.layerThickness[k] - float(g["fd_layerThickness"])) < 1e-4          # test_Enzyme_end2end.jl:176
     assert abs(d_prog.normalVelocity[k] - float(g["fd_normalVelocity"])) < 1e-2          # :177
+
+
+def test_reverse_sweep_of_an_empty_tape_returns_the_seed(backend):
+    """nsteps = 0: the gradient of J = sum ssh^2 at the initial state itself.  RungeKutta4 defines ssh = h - H, so dJ/dh =
+    2 (h - H); for ForwardEuler ssh is an input of its own: dJ/dssh = 2 ssh, dJ/dh = 0.  dJ/du = 0 either way."""
+    m, mo, ssh, u, h, dt = _case(12, False)
+    ssh = ssh + 0.25                      # ssh != h - H: the two definitions must give different answers
+    mesh = mb.Mesh(m, backend)
+    prog = mb.PrognosticVars(ssh, u, h, 2, mesh)
+    d = mb.ocn_init_shadows(prog)
+    mb.autodiff_reverse_run_loop(dt, prog, d, None, None, None, mb.RungeKutta4, 0)
+    _, gu, gh = A.gradient_sum_ssh2(mo, u, h, dt, 0)
+    assert np.array_equal(d.normalVelocity, gu) and not gu.any()
+    assert rel_l2(d.layerThickness, gh) <= TOL64
+    prog = mb.PrognosticVars(ssh, u, h, 2, mesh)
+    d = mb.ocn_init_shadows(prog)
+    J = mb.autodiff_reverse_run_loop(dt, prog, d, None, None, None, mb.ForwardEuler, 0)
+    Jo, gu, gh, gs, _ = A.gradient_sum_ssh2_fe(mo, ssh, u, h, dt, 0)
+    assert abs(J - Jo) <= 1e-12 * Jo
+    assert not np.asarray(d.normalVelocity).any() and not np.asarray(d.layerThickness).any() and not gh.any()
+    assert np.array_equal(d.ssh, gs) and np.array_equal(gs, 2.0 * ssh)

@@ -483,3 +483,25 @@ def test_fused_forward_euler_is_the_reference_sequence_bit_for_bit(backend):
         mb.ocn_timestep(dt, prog, diag, tend, None, mb.ForwardEuler, nsteps=5)
         om.run_loop(dt, 5, "ForwardEuler")
         check()
+
+
+@pytest.mark.parametrize("nx,ny", [(1, 2), (2, 2), (3, 2), (2, 4), (5, 4)])
+def test_degenerate_periodic_meshes_and_zero_steps(backend, nx, ny):
+    """The smallest periodic meshes the generator makes -- a cell is its own neighbour, one edge appears several times in a
+    row of edgesOnEdge, the whole mesh is a fraction of one thread block -- and a call with nsteps = 0 (a no-op that must not
+    touch the state): both steppers, bit for bit against the oracle."""
+    m = mb.periodic_hex(nx, ny, 1.0e7 / max(nx, 2))
+    OC.sign_index_fields(m)
+    ssh, u, h = mb.inertialGravityWave(m).initial_state()
+    dt = mb.cfl_dt(m["dc"])
+    mesh = mb.Mesh(m, backend)
+    for stepper, name in ((mb.RungeKutta4, "RungeKutta4"), (mb.ForwardEuler, "ForwardEuler")):
+        for nsteps in (0, 1, 3):
+            om = OC.OracleModel(m, ssh, u, h)
+            if nsteps:
+                om.run_loop(dt, nsteps, name)
+            prog = mb.PrognosticVars(ssh, u, h, 2, mesh)
+            mb.ocn_timestep(dt, prog, None, None, None, stepper, nsteps=nsteps)
+            want_u, want_h = (om.normalVelocity[1], om.layerThickness[1]) if nsteps else (u, h)
+            assert np.array_equal(prog.normalVelocity, want_u), (name, nsteps)
+            assert np.array_equal(prog.layerThickness, want_h), (name, nsteps)
