@@ -27,6 +27,8 @@ def rcb_partition(x: np.ndarray, y: np.ndarray, nparts: int, z: np.ndarray | Non
     """cell -> part (int32) by recursive coordinate bisection (`z`: spherical meshes -- without it the two hemispheres
     would be cut as one disc and every part would come in two far-apart pieces)."""
     n = x.shape[0]
+    if not 1 <= int(nparts) <= n:
+        raise ValueError(f"rcb_partition: nparts = {nparts} must be between 1 and the number of cells ({n}): every part owns at least one cell")
     part = np.zeros(n, np.int32)
     coords = [x, y] + ([z] if z is not None else [])
 

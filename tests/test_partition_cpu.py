@@ -121,6 +121,19 @@ def test_two_rank_gloo_halo_exchange_matches_single_domain(tmp_path, world):
     assert np.array_equal(gh, prog["layerThickness"][-1])
 
 
+def test_as_many_parts_as_cells_and_one_more():
+    """One cell per part is the limit: every rank must own a cell (an empty rank would launch empty grids); beyond it the
+    partitioner refuses with a message instead of failing somewhere inside numpy."""
+    m = hex_mesh(4)
+    locs = partition.decompose(m, m["nCells"])
+    assert sorted(int(loc["cellsGlobal"][0]) for loc in locs) == list(range(m["nCells"]))
+    assert all(loc["nCellsOwned"] == 1 for loc in locs)
+    with pytest.raises(ValueError, match="must be between 1 and the number of cells"):
+        partition.decompose(m, m["nCells"] + 1)
+    with pytest.raises(ValueError, match="must be between 1"):
+        partition.rcb_partition(m["xCell"], m["yCell"], 0)
+
+
 def test_graph_replay_plan_respects_time_level_parity():
     """multi_gpu.plan_steps: a 2-step graph may only be replayed from the parity it was captured at; any number of steps
     from any parity is covered exactly once, and the parity after the plan is what the step count implies."""
