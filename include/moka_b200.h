@@ -247,7 +247,8 @@ enum { MOKAB_PART_ALL = 0, MOKAB_PART_INTERIOR = 1, MOKAB_PART_BOUNDARY = 2,
  * Blocks that hold a send entity join the BOUNDARY part, so a message can be packed as soon as the
  * boundary launch of a stage has finished.  Call before creating states on the mesh. */
 int  mokab_halo_setup(mokab_mesh *mesh, int64_t n_send, const int32_t *send_idx, int64_t n_recv, const int32_t *recv_idx);
-/* stage 0 = the current state Prog.*[end]; stage s = 1..4 = the output of RK stage s of the step in flight.
+/* stage 0 = the current state Prog.*[end]; stage s = 1..4 = the output of RK stage s of the step in flight (4 is also the
+ * (layerThickness, normalVelocity) a staged ForwardEuler step wrote); stage 5 = the (ssh, layerThicknessEdge) it wrote.
  * pack: device message buffer (state dtype, n_send elements) <- values; unpack: halo slots <- message. */
 int  mokab_halo_pack(mokab_state *state, int stage, void *send_buf_device, void *cuda_stream);
 int  mokab_halo_unpack(mokab_state *state, int stage, const void *recv_buf_device, void *cuda_stream);
@@ -255,6 +256,14 @@ int  mokab_halo_unpack(mokab_state *state, int stage, const void *recv_buf_devic
 int  mokab_rk4_stage(mokab_state *state, double dt, int stage, int part, void *cuda_stream);
 /* after stage 4 (and its exchange): the other time level becomes Prog.*[end] */
 int  mokab_rk4_finish_step(mokab_state *state);
+/* ---- staged ForwardEuler for domain-decomposed runs: ocn_timestep(::ForwardEuler) `time_integration.jl:150-193` ----------
+ * One step of the fused ForwardEuler kernel over the selected blocks (MOKAB_PART_ALL / _INTERIOR / _BOUNDARY), reading
+ * Prog.*[end] and writing the other time level for the OWNED cells and edges: normalVelocity, layerThickness, ssh and the
+ * layerThicknessEdge of the state it read (the lagged value the next step's thicknessFlux uses, DiagnosticVars.jl:108-117).
+ * Then: mokab_halo_pack/unpack with stage 4 and stage 5 (exchange in between), then mokab_forward_euler_finish_step.
+ * Float64; connectivity rows of at most (10, 6) or (12, 7) entries; same bits as mokab_timestep_forward_euler on the whole mesh. */
+int  mokab_forward_euler_stage(mokab_state *state, double dt, int part, void *cuda_stream);
+int  mokab_forward_euler_finish_step(mokab_state *state);
 /* ssh = layerThickness - restingThicknessSum on both time levels (Update_ssh!, time_integration.jl:205-212) */
 int  mokab_refresh_ssh(mokab_state *state, void *cuda_stream);
 /* ---- halo exchange by direct stores into the peers' memory (csrc/kernels_p2p.cuh) ---------------------------------------

@@ -419,14 +419,16 @@ struct FeArgs {
     const double *u, *h, *ssh, *hEold;
     double *uNew, *hNew, *sshNew, *hEnew;
     double dt, f0;
+    const int32_t *blockList;  // LIST launches (domain-decomposed runs: interior / boundary blocks): the blocks to process
 };
 
-template <int S2T, int ST, bool UNIF>
+template <int S2T, int ST, bool UNIF, bool LIST = false>
 __global__ void __launch_bounds__(kThreads, MOKAB_BLOCKS_SCALED(4))
 k_fe_step(const FeArgs A)
 {
     const int nE = A.nE, nC = A.nC;
-    const int b = blockIdx.x;
+    int b = blockIdx.x;
+    if constexpr (LIST) b = A.blockList[blockIdx.x];
     const int e0 = A.blkEdgeStart[b], e1 = A.blkEdgeStart[b + 1];
     for (int e = e0 + threadIdx.x; e < e1; e += kThreads) {
         const int2 c = ld_stream(A.ce + e);

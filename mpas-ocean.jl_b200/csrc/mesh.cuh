@@ -102,6 +102,11 @@ static void build_host_mesh(const mokab_mesh_desc &d, uint32_t flags, HostMesh &
         int s = 1, s2 = 1;
         for (int64_t c = 0; c < nCo; ++c) s = std::max(s, std::min((int)d.nEdgesOnCell[c], Sf));
         for (int64_t e = 0; e < nEo; ++e) s2 = std::max(s2, std::min((int)d.nEdgesOnEdge[e], S2f));
+        // ... rounded up to the next pair the compile-time kernels exist for (padding slots: index = self, weight 0, sign 0), so
+        // that e.g. a part of a decomposed pentagon / hexagon / heptagon mesh whose longest rows happen to be (11, 7) gets the
+        // (12, 7) kernels like its neighbours, and a mesh of squares the (10, 6) ones
+        if (s <= 6 && s2 <= 10) { s = 6; s2 = 10; }
+        else if (s <= 7 && s2 <= 12) { s = 7; s2 = 12; }
         S = s; S2 = s2;
     }
     MOKAB_REQUIRE((nCo == nC && nEo == nE) || nV == 0, "mesh_create: decomposed meshes carry no vertex arrays");

@@ -500,7 +500,7 @@ static void run_fe_fused(mokab_state *st, double dt, int64_t nsteps)
     A.nE = (int)m->nE; A.nC = (int)m->nC; A.nCown = (int)m->nCo;
     A.ce = m->ce.p; A.eoe = m->eoeF.p; A.eoc = m->eocF.p; A.nEoC = m->nEoC.p; A.blkEdgeStart = m->blkEdgeStart.p;
     A.gdc = fm.gdc.p; A.woe = m->woe.p; A.fE = m->fE.p; A.dv = m->dv.p; A.invArea = fm.invArea.p; A.H = m->H.p;
-    A.dt = dt; A.f0 = m->f0;
+    A.dt = dt; A.f0 = m->f0; A.blockList = nullptr;
     for (int64_t i = 0; i < nsteps; ++i) {
         const int p = st->cur, q = 1 - p;
         if (t->taping) fe_tape_record(st, dt, t->u[p].p, t->hE[p].p);
@@ -521,6 +521,52 @@ static void run_fe_fused(mokab_state *st, double dt, int64_t nsteps)
         st->cur = q;
     }
     st->fe_lazy = true;
+}
+
+// One ForwardEuler step of a domain-decomposed run, staged like mokab_rk4_stage: the selected blocks read time level cur and
+// write level 1 - cur for their OWNED cells and edges (u, h, ssh and the layerThicknessEdge of the state they read, which the
+// next step's flux uses -- the reference's lag, DiagnosticVars.jl:108-117).  The caller then exchanges the halo copies of all
+// four arrays (mokab_halo_pack/unpack stage 4: (h, u)[new]; stage 5: (ssh, layerThicknessEdge)[new]) and calls
+// mokab_forward_euler_finish_step.  Same kernel, same bits as the single-domain fused step.
+static void run_fe_stage(mokab_state *st, double dt, int part, cudaStream_t stream)
+{
+    mokab_ctx *ctx = st->ctx; mokab_mesh *m = const_cast<mokab_mesh *>(st->mesh); StateT<double> *t = st->d;
+    const bool widths = (m->S2 == 10 && m->S == 6) || (m->S2 == 12 && m->S == 7);
+    MOKAB_REQUIRE(widths, "forward_euler_stage: needs connectivity rows of at most (10, 6) or (12, 7) entries");
+    MOKAB_REQUIRE(!t->taping, "forward_euler_stage: recording a tape is not supported on decomposed meshes");
+    MOKAB_REQUIRE(m->nV == 0, "forward_euler_stage: local meshes carry no vertices (relativeVorticity is not advanced)");
+    ensure_fused<double>(m);
+    FusedMesh<double> &fm = fused_of<double>(m);
+    cudaStream_t s = stream ? stream : ctx->stream;
+    if (t->hE[0].n == 0) { t->hE[0].alloc(m->nE); t->hE[1].alloc(m->nE); }
+    if (!st->fe_lazy) {       // first staged step: the canonical layerThicknessEdge is what the first flux uses
+        MOKAB_CUDA(cudaMemcpyAsync(t->hE[st->cur].p, t->hEdge.p, m->nE * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        MOKAB_CUDA(cudaStreamSynchronize(ctx->stream));          // the launches below may be on other streams
+        st->fe_lazy = true;
+    }
+    int grid = m->fusedBlocks;
+    fused::FeArgs A;
+    A.blockList = nullptr;
+    if (part == MOKAB_PART_INTERIOR) { grid = m->nInterior; A.blockList = m->blkInterior.p; }
+    if (part == MOKAB_PART_BOUNDARY) { grid = m->nBoundary; A.blockList = m->blkBoundary.p; }
+    if (grid == 0) return;
+    const int p = st->cur, q = 1 - p;
+    A.nE = (int)m->nE; A.nC = (int)m->nC; A.nCown = (int)m->nCo;
+    A.ce = m->ce.p; A.eoe = m->eoeF.p; A.eoc = m->eocF.p; A.nEoC = m->nEoC.p; A.blkEdgeStart = m->blkEdgeStart.p;
+    A.gdc = fm.gdc.p; A.woe = m->woe.p; A.fE = m->fE.p; A.dv = m->dv.p; A.invArea = fm.invArea.p; A.H = m->H.p;
+    A.dt = dt; A.f0 = m->f0;
+    A.u = t->u[p].p; A.h = t->h[p].p; A.ssh = t->ssh[p].p; A.hEold = t->hE[p].p;
+    A.uNew = t->u[q].p; A.hNew = t->h[q].p; A.sshNew = t->ssh[q].p; A.hEnew = t->hE[q].p;
+#define MOKAB_FE_STAGE(S2T, ST, UNIF)                                                                   \
+    do {                                                                                                \
+        if (A.blockList) fused::k_fe_step<S2T, ST, UNIF, true><<<grid, fused::kThreads, 0, s>>>(A);     \
+        else             fused::k_fe_step<S2T, ST, UNIF, false><<<grid, fused::kThreads, 0, s>>>(A);    \
+    } while (0)
+    if (m->S == 6) { if (m->uniformF) MOKAB_FE_STAGE(10, 6, true); else MOKAB_FE_STAGE(10, 6, false); }
+    else           { if (m->uniformF) MOKAB_FE_STAGE(12, 7, true); else MOKAB_FE_STAGE(12, 7, false); }
+#undef MOKAB_FE_STAGE
+    MOKAB_CUDA(cudaGetLastError());
+    ctx->launches++;
 }
 
 // ocn_timestep(::RungeKutta4) with the reference's per-stage kernel sequence (time_integration.jl:112-137)
@@ -715,6 +761,14 @@ static void stage_output(mokab_state *st, int stage, R **u, R **h)
     case 0: *u = t->u[p].p; *h = t->h[p].p; break;
     case 1: case 3: *u = t->uP[0].p; *h = t->hP[0].p; break;
     case 2: *u = t->uP[1].p; *h = t->hP[1].p; break;
+    case 5:             // staged ForwardEuler (Float64): the other two arrays a step writes -- (layerThicknessEdge, ssh)[new]
+        if constexpr (sizeof(R) == 8) {
+            MOKAB_REQUIRE(t->hE[0].n, "halo_pack/unpack stage 5: no staged ForwardEuler step has run");
+            *u = t->hE[1 - p].p; *h = t->ssh[1 - p].p;
+        } else {
+            MOKAB_REQUIRE(false, "halo_pack/unpack stage 5: ForwardEuler is Float64 only");
+        }
+        break;
     default: *u = t->u[1 - p].p; *h = t->h[1 - p].p; break;
     }
 }
@@ -1882,7 +1936,7 @@ int mokab_halo_pack(mokab_state *state, int stage, void *send_buf_device, void *
 {
     return guarded([&] {
         MOKAB_REQUIRE(state && state->mesh->halo_ready, "halo_pack: call mokab_halo_setup first");
-        MOKAB_REQUIRE(stage >= 0 && stage <= 4, "halo_pack: stage must be 0..4");
+        MOKAB_REQUIRE(stage >= 0 && stage <= 5, "halo_pack: stage must be 0..5");
         MOKAB_REQUIRE(send_buf_device || state->mesh->haloSend.n == 0, "halo_pack: NULL buffer");
         state->ctx->bind();
         if (state->dtype == MOKAB_F64) halo_pack<double>(state, stage, send_buf_device, (cudaStream_t)cuda_stream, false);
@@ -1894,7 +1948,7 @@ int mokab_halo_unpack(mokab_state *state, int stage, const void *recv_buf_device
 {
     return guarded([&] {
         MOKAB_REQUIRE(state && state->mesh->halo_ready, "halo_unpack: call mokab_halo_setup first");
-        MOKAB_REQUIRE(stage >= 0 && stage <= 4, "halo_unpack: stage must be 0..4");
+        MOKAB_REQUIRE(stage >= 0 && stage <= 5, "halo_unpack: stage must be 0..5");
         MOKAB_REQUIRE(recv_buf_device || state->mesh->haloRecv.n == 0, "halo_unpack: NULL buffer");
         state->ctx->bind();
         if (state->dtype == MOKAB_F64) halo_pack<double>(state, stage, const_cast<void *>(recv_buf_device), (cudaStream_t)cuda_stream, true);
@@ -1911,6 +1965,27 @@ int mokab_rk4_stage(mokab_state *state, double dt, int stage, int part, void *cu
         state->ctx->bind();
         if (state->dtype == MOKAB_F64) run_stage<double>(state, dt, stage, part, (cudaStream_t)cuda_stream);
         else run_stage<float>(state, dt, stage, part, (cudaStream_t)cuda_stream);
+    });
+}
+
+int mokab_forward_euler_stage(mokab_state *state, double dt, int part, void *cuda_stream)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(state, "forward_euler_stage: state is NULL");
+        MOKAB_REQUIRE(part >= MOKAB_PART_ALL && part <= MOKAB_PART_BOUNDARY, "forward_euler_stage: part must be ALL, INTERIOR or BOUNDARY");
+        require_f64(state, "forward_euler_stage");
+        state->ctx->bind();
+        run_fe_stage(state, dt, part, (cudaStream_t)cuda_stream);
+    });
+}
+
+int mokab_forward_euler_finish_step(mokab_state *state)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(state, "forward_euler_finish_step: state is NULL");
+        require_f64(state, "forward_euler_finish_step");
+        MOKAB_REQUIRE(state->fe_lazy, "forward_euler_finish_step: no staged ForwardEuler step has run");
+        state->cur = 1 - state->cur;
     });
 }
 

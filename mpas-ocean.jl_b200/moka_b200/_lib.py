@@ -59,6 +59,7 @@ SYMBOLS = [
     "mokab_timestep_forward_euler", "mokab_timestep_forward_euler_unfused", "mokab_timestep_rk4", "mokab_reduce",
     "mokab_tape_begin", "mokab_tape_length", "mokab_adjoint_seed", "mokab_adjoint_rk4", "mokab_adjoint_forward_euler",
     "mokab_halo_setup", "mokab_halo_pack", "mokab_halo_unpack", "mokab_rk4_stage", "mokab_rk4_finish_step",
+    "mokab_forward_euler_stage", "mokab_forward_euler_finish_step",
     "mokab_refresh_ssh", "mokab_mesh_block_counts", "mokab_mesh_derived_blocks",
     "mokab_halo_recv_device_indices", "mokab_p2p_blob_size", "mokab_p2p_export", "mokab_p2p_setup", "mokab_halo_push",
     "mokab_halo_wait", "mokab_halo_wait_arrivals", "mokab_p2p_error", "mokab_p2p_close",
@@ -94,6 +95,7 @@ def bind(L):
         "mokab_halo_setup": [vp, i64, _I32P, i64, _I32P], "mokab_halo_pack": [vp, C.c_int, vp, vp],
         "mokab_halo_unpack": [vp, C.c_int, vp, vp], "mokab_rk4_stage": [vp, dbl, C.c_int, C.c_int, vp],
         "mokab_rk4_finish_step": [vp], "mokab_refresh_ssh": [vp, vp],
+        "mokab_forward_euler_stage": [vp, C.c_double, C.c_int, vp], "mokab_forward_euler_finish_step": [vp],
         "mokab_mesh_block_counts": [vp, C.POINTER(i64), C.POINTER(i64)],
         "mokab_mesh_derived_blocks": [vp, C.POINTER(i64), C.POINTER(i64)],
         "mokab_halo_recv_device_indices": [vp, _I32P], "mokab_p2p_blob_size": [C.POINTER(i64)],

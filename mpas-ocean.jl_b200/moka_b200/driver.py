@@ -163,15 +163,15 @@ def ocn_run_decomposed(config_fp: str, backend: api.B200, device_index: int = 0,
                        halo: str = "nccl", graph: bool = True, series: list | None = None):
     """`ocn_run` with the mesh decomposed over the ranks of a process group (one process per GPU; under torchrun every rank
     calls this with its own `B200(LOCAL_RANK)`): the same YAML, the same NetCDF mesh / initial state, the same clock and
-    alarms, RungeKutta4 through multi_gpu.DecomposedModel (halo exchange per stage overlapped with the interior blocks), and
-    on rank 0 the same output file as the single-device run writes -- bit for bit.  The reference has no multi-device
+    alarms, the configured stepper (ForwardEuler, the reference driver's, or RungeKutta4) through multi_gpu.DecomposedModel
+    (halo exchange per stage / per step overlapped with the interior blocks), and on rank 0 the same output file as the single-device run writes -- bit for bit.  The reference has no multi-device
     driver.  Every rank reads the mesh and derives the same partition from it (deterministic), then keeps
     only its own part.  Returns (Setup, model, nsteps)."""
     from . import multi_gpu, partition
     Config = ConfigRead(config_fp)
-    if _stepper_from_config(Config) is not api.RungeKutta4:
-        raise MokaError("ocn_run_decomposed: domain-decomposed runs step with RungeKutta4 (config_time_integrator: RK4); "
-                        "ForwardEuler has no staged form")
+    stepper = _stepper_from_config(Config)
+    if stepper is api.ForwardEuler and halo != "nccl":
+        raise MokaError("ocn_run_decomposed: ForwardEuler steps use the packed exchange (halo='nccl')")
     rt = runtime if runtime is not None else multi_gpu.TorchRuntime(device_index)
     rank, world = rt.rank_and_size()
     mesh_fp = ConfigGet(ConfigGet(Config.streams, "mesh"), "filename_template")
@@ -197,7 +197,7 @@ def ocn_run_decomposed(config_fp: str, backend: api.B200, device_index: int = 0,
                 break
             if clock.currTime > simulationAlarm.ringTime:
                 raise MokaError("ocn_run_decomposed: the clock stepped over the simulation_end alarm without hitting it")
-        model.step(dt, n)
+        model.step(dt, n, stepper=stepper)
         i += n
         if isRinging(outputAlarm):
             if series is not None:

@@ -162,6 +162,7 @@ class DecomposedModel:
         self._graph, self._graph_dt = None, None
         self._validated, self.graph_status = False, "not used"
         self._parity, self._graph_parity = 0, 0                  # steps taken so far mod 2; the same at graph capture
+        self._fe = False                                         # the last steps were ForwardEuler
         if halo != "nccl":
             self._setup_p2p(scnt, rcnt)
 
@@ -242,6 +243,39 @@ class DecomposedModel:
             self._wait_arrivals(self.halo)                       # the neighbours' last stores, before anything else touches the halo slots
         self.compute.wait_stream(self.halo)                      # join
 
+    def _enqueue_fe_steps(self, dt: float, nsteps: int) -> None:
+        """Enqueue `nsteps` ForwardEuler steps (the reference's live stepper, time_integration.jl:150-193): one launch per part,
+        then the halo copies of everything the step wrote -- (h, u) and (ssh, layerThicknessEdge), two messages -- while the
+        interior blocks run.  Stream-launched (one exchange pair per step instead of RK4's four; no captured graph)."""
+        if self.halo_mode != "nccl":
+            raise api.MokaError("DecomposedModel: ForwardEuler steps use the packed exchange (halo='nccl')")
+        lib, cuda = L.lib(), self.cuda
+        self._fe = True
+
+        def stage(part, stream):
+            L.check(lib.mokab_forward_euler_stage(self.handle, float(dt), part, C.c_void_p(stream.cuda_stream)))
+
+        if not self.overlap:
+            for _ in range(nsteps):
+                stage(L.PART_ALL, self.compute)
+                self._exchange(4, self.compute)
+                self._exchange(5, self.compute)
+                L.check(lib.mokab_forward_euler_finish_step(self.handle))
+            return
+        self.halo.wait_stream(self.compute)                      # fork
+        for _ in range(nsteps):
+            ev_i, ev_b = cuda.Event(), cuda.Event()
+            stage(L.PART_BOUNDARY, self.halo)
+            ev_b.record(self.halo)
+            stage(L.PART_INTERIOR, self.compute)
+            ev_i.record(self.compute)
+            self._exchange(4, self.halo)
+            self._exchange(5, self.halo)
+            self.compute.wait_event(ev_b)                        # the next interior launch overwrites what this boundary launch read
+            self.halo.wait_event(ev_i)                           # the next boundary launch reads (and overwrites the inputs of) this interior launch
+            L.check(lib.mokab_forward_euler_finish_step(self.handle))
+        self.compute.wait_stream(self.halo)                      # join
+
     def _build_graph(self, dt: float) -> None:
         """Capture two consecutive steps (one per time-level parity), NCCL calls included, into one CUDA graph."""
         cuda = self.cuda
@@ -296,7 +330,16 @@ class DecomposedModel:
         self._enqueue_steps(dt, nsteps)
         self._parity ^= nsteps & 1
 
-    def step(self, dt: float, nsteps: int = 1) -> None:
+    def step(self, dt: float, nsteps: int = 1, stepper=None) -> None:
+        """`nsteps` steps of `stepper` (api.RungeKutta4, the default, or api.ForwardEuler)."""
+        if stepper is api.ForwardEuler:
+            if nsteps > 0:
+                self._enqueue_fe_steps(dt, nsteps)
+                self._parity ^= nsteps & 1
+            return
+        if stepper not in (None, api.RungeKutta4):
+            raise api.MokaError("DecomposedModel.step: unknown stepper")
+        self._fe = False
         if self.use_graph and nsteps >= 2:
             if self._graph is None or self._graph_dt != dt:
                 if not self.validate_graph(dt):
@@ -316,7 +359,8 @@ class DecomposedModel:
         L.check(L.lib().mokab_refresh_ssh(self.handle, C.c_void_p(self.compute.cuda_stream)))
 
     def finish(self) -> None:
-        self.refresh_ssh()
+        if not self._fe:                                         # (ForwardEuler carries ssh as a state of its own)
+            self.refresh_ssh()
         self.compute.synchronize()
         self.halo.synchronize()
         if self.halo_mode != "nccl":

@@ -1,6 +1,6 @@
 """torchrun entry: the decomposed DRIVER path (driver.ocn_run_decomposed: YAML -> NetCDF mesh / initial state -> clock and
 alarms -> RK4 over the ranks -> NetCDF output on rank 0) against the single-domain CPU oracle.
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29614 tests/multi_gpu_driver_check.py [halo]"""
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29614 tests/multi_gpu_driver_check.py [halo] [RK4|ForwardEuler]"""
 import os
 import sys
 
@@ -26,7 +26,7 @@ omega:
   time_integration:
     config_dt: 0000-00-00_00:15:00
     config_number_of_time_levels: 2
-    config_time_integrator: RK4
+    config_time_integrator: {stepper}
   streams:
     mesh:
       filename_template: {mesh}
@@ -43,6 +43,7 @@ def main():
     from scipy.io import netcdf_file
     rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
     halo = sys.argv[1] if len(sys.argv) > 1 else "nccl"
+    stepper = sys.argv[2] if len(sys.argv) > 2 else "RK4"
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     tag = f"/dev/shm/mokab_driver_{os.environ.get('MASTER_PORT', '0')}"
@@ -52,7 +53,7 @@ def main():
     if rank == 0:
         mb.write_mesh_netcdf(mesh_fp, m, state)
         with open(cfg, "w") as f:
-            f.write(YAML.format(mesh=mesh_fp, out=out_fp))
+            f.write(YAML.format(mesh=mesh_fp, out=out_fp, stepper=stepper))
     dist.barrier()
     series = []
     Setup, model, nsteps = mb.driver.ocn_run_decomposed(cfg, mb.B200(local), local, halo=halo, series=series)
@@ -62,14 +63,14 @@ def main():
     if rank == 0:
         OC.sign_index_fields(m)
         om = OC.OracleModel(m, *state)
-        om.run_loop(900.0, nsteps, "RungeKutta4")
+        om.run_loop(900.0, nsteps, "RungeKutta4" if stepper == "RK4" else "ForwardEuler")
         with netcdf_file(out_fp, "r", mmap=False) as ds:
             f_u, f_h = np.array(ds.variables["normalVelocity"][:]).reshape(-1), np.array(ds.variables["layerThickness"][:]).reshape(-1)
         rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))          # noqa: E731
         e = (rel(f_u, om.normalVelocity[0]), rel(f_h, om.layerThickness[0]))         # the file holds the state one step before the last
         drift = abs(series[-1]["mass"] - series[0]["mass"]) / series[0]["mass"]
         ok = nsteps == 12 and max(e) <= 1e-12 and len(series) == 3 and drift <= 1e-13
-        print(f"halo={halo} steps={nsteps} rel-L2 of the output file vs the oracle {e} mass drift {drift:.1e} graph: {status}")
+        print(f"halo={halo} stepper={stepper} steps={nsteps} rel-L2 of the output file vs the oracle {e} mass drift {drift:.1e} graph: {status}")
         print("MULTI_GPU_DRIVER_OK" if ok else "MULTI_GPU_DRIVER_FAILED")
         for p in (mesh_fp, out_fp, cfg):
             try:

@@ -56,8 +56,9 @@ def case(kind, nx):
     return _CASES[(kind, nx)]
 
 
-def run(kind, nx, nparts, step_calls, overlap, graph, policy, seed, dtype=np.float64, halo="nccl"):
+def run(kind, nx, nparts, step_calls, overlap, graph, policy, seed, dtype=np.float64, halo="nccl", stepper="RungeKutta4"):
     """`step_calls`: the sequence of model.step(dt, n) calls (odd counts move the time-level parity between them)."""
+    step_type = mb.ForwardEuler if stepper == "ForwardEuler" else mb.RungeKutta4
     simcuda.set_policy(policy, seed)
     m, mo, state, dt = case(kind, nx)
     locs = partition.decompose(m, nparts)
@@ -67,7 +68,7 @@ def run(kind, nx, nparts, step_calls, overlap, graph, policy, seed, dtype=np.flo
         model = multi_gpu.DecomposedModel(locs[r], multi_gpu.local_state(locs[r], *state), backend, 0, dtype=dtype, overlap=overlap,
                                           graph=graph, runtime=simcuda.SimRuntime(comm, r), halo=halo)
         for n in step_calls:
-            model.step(dt, n)
+            model.step(dt, n, stepper=step_type)
         model.finish()
         res = {f: np.array(model.owned(f)) for f in ("ssh", "normalVelocity", "layerThickness")}
         mass = model.reduce("mass")
@@ -82,7 +83,7 @@ def run(kind, nx, nparts, step_calls, overlap, graph, policy, seed, dtype=np.flo
         gh[loc["cellsGlobal"][:loc["nCellsOwned"]]] = res["layerThickness"]
         gs[loc["cellsGlobal"][:loc["nCellsOwned"]]] = res["ssh"]
     om = OC.OracleModel(mo, *state)
-    om.run_loop(dt, sum(step_calls), "RungeKutta4")
+    om.run_loop(dt, sum(step_calls), stepper)
     if dtype == np.float64:
         ok = np.array_equal(gu, om.normalVelocity[1]) and np.array_equal(gh, om.layerThickness[1]) and np.array_equal(gs, om.ssh[1])
     else:   # Float32: bit-identical to the single-domain Float32 run of the same library (same arithmetic per entity)
@@ -200,7 +201,7 @@ omega:
   time_integration:
     config_dt: 0000-00-00_00:15:00
     config_number_of_time_levels: 2
-    config_time_integrator: RK4
+    config_time_integrator: {stepper}
   streams:
     mesh:
       filename_template: {mesh}
@@ -213,7 +214,7 @@ omega:
 """
 
 
-def run_driver(nparts, policy, halo):
+def run_driver(nparts, policy, halo, stepper="RK4"):
     """YAML -> NetCDF mesh -> decomposed run -> NetCDF output (driver.ocn_run_decomposed) against the single-device ocn_run:
     the two output files must hold the same bits, and so must the conservation series taken at the output alarms."""
     import tempfile
@@ -229,7 +230,7 @@ def run_driver(nparts, policy, halo):
         for tag in ("one", "many"):
             cfgs[tag] = os.path.join(tmp, f"cfg_{tag}.yml")
             with open(cfgs[tag], "w") as f:
-                f.write(DRIVER_YAML.format(mesh=mesh_fp, out=os.path.join(tmp, f"out_{tag}.nc")))
+                f.write(DRIVER_YAML.format(mesh=mesh_fp, out=os.path.join(tmp, f"out_{tag}.nc"), stepper=stepper))
         simcuda.set_policy("fifo")
         _, _, _, prog1, n1 = mb.ocn_run(cfgs["one"], backend=mb.B200(0))
         mass1 = mb.reduce_sum(prog1, "mass")
@@ -285,6 +286,16 @@ def main():
                         print(f"{kind}{nx} ranks={P} steps={calls} {halo} {policy}{'/' + str(seed) if policy == 'random' else ''} "
                               f"{'overlap' if overlap else 'serial'} {'graph' if graph else 'stream'}: {'OK' if ok else 'MISMATCH'}"
                               f"{' [' + status + ']' if graph else ''} {time.time() - t0:.1f}s", flush=True)
+    # the reference's live stepper, ForwardEuler, on the decomposed mesh (packed exchange, two messages per step)
+    if "nccl" in args.halo.split(","):
+        for kind, nx, P, calls in [("igw", 96, 8, [5]), ("kelvin", 48, 4, [3, 4]), ("igw", 128, 2, [1, 2])] + ([("voronoi", 24, 4, [5])] if args.cases != "suite" else []):
+            for policy in args.policies.split(","):
+                for overlap in (True, False):
+                    t0 = time.time()
+                    ok, _ = run(kind, nx, P, calls, overlap, False, policy, 5, stepper="ForwardEuler")
+                    bad += not ok
+                    print(f"{kind}{nx} ranks={P} steps={calls} ForwardEuler nccl {policy} {'overlap' if overlap else 'serial'} stream: "
+                          f"{'OK' if ok else 'MISMATCH'} {time.time() - t0:.1f}s", flush=True)
     for halo in (args.halo.split(",") if args.cases != "suite" else []):
         ok, _ = run("igw", 48, 4, [4, 3], True, True, "random", 7, dtype=np.float32, halo=halo)
         bad += not ok
@@ -300,6 +311,10 @@ def main():
         ok = run_driver(3, args.policies.split(",")[0], halo)
         bad += not ok
         print(f"driver: YAML -> NetCDF -> 3 ranks -> NetCDF equals the single-device ocn_run, {halo}: {'OK' if ok else 'MISMATCH'} {time.time() - t0:.1f}s", flush=True)
+    t0 = time.time()
+    ok = run_driver(3, args.policies.split(",")[0], "nccl", stepper="ForwardEuler")
+    bad += not ok
+    print(f"driver: the same with ForwardEuler (the reference driver's stepper), nccl: {'OK' if ok else 'MISMATCH'} {time.time() - t0:.1f}s", flush=True)
     print("SIM_DECOMPOSED_OK" if bad == 0 else f"SIM_DECOMPOSED_FAILED ({bad})", flush=True)
     sys.exit(0 if bad == 0 else 1)
 

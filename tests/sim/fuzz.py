@@ -29,7 +29,7 @@ import adjoint_oracle as A  # noqa: E402
 import moka_b200 as mb  # noqa: E402
 import moka_oracle_c as OC  # noqa: E402
 from moka_b200 import multi_gpu, partition  # noqa: E402
-from test_gpu_decomposed import _run_emulated  # noqa: E402
+from test_gpu_decomposed import _run_emulated, _run_emulated_fe  # noqa: E402
 
 G, DEPTH = 9.80616, 1000.0
 
@@ -128,18 +128,25 @@ def one_case(rng, backend):
         if not (np.array_equal(gu, base.normalVelocity) and np.array_equal(gh, base.layerThickness)):
             problems.append(f"decomposed {nparts} ranks {halo}")
         desc += f"; {nparts} ranks {halo}"
+        # the reference's live stepper on the same decomposition (compile-time row widths only): the single-domain bits
+        if int(m["nEdgesOnCell"].max()) <= 7:
+            fu, fh, fs = _run_emulated_fe(backend, md, (ssh, u, h), nparts, dt, nsteps, split_parts=bool(rng.integers(0, 2)))
+            if not (np.array_equal(fu, pfe.normalVelocity) and np.array_equal(fh, pfe.layerThickness) and np.array_equal(fs, pfe.ssh)):
+                problems.append(f"decomposed ForwardEuler {nparts} ranks")
         # and, now and then, the product's DecomposedModel itself: one host thread per rank, two streams per rank, in-stream
         # exchange, a random sequence of step() calls (graph replays from both parities), against the same single-domain bits
         if rng.integers(0, 3) == 0:
             calls = [int(x) for x in rng.integers(1, 5, size=int(rng.integers(1, 4)))]
             overlap, graph = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+            fe = halo == "nccl" and int(m["nEdgesOnCell"].max()) <= 7 and bool(rng.integers(0, 2))
+            step_type = mb.ForwardEuler if fe else mb.RungeKutta4
             locs = partition.decompose(md, nparts)
 
             def body(r, comm):
                 model = multi_gpu.DecomposedModel(locs[r], multi_gpu.local_state(locs[r], ssh, u, h), mb.B200(0), 0, overlap=overlap,
                                                   graph=graph, runtime=simcuda.SimRuntime(comm, r), halo=halo)
                 for n in calls:
-                    model.step(dt, n)
+                    model.step(dt, n, stepper=step_type)
                 model.finish()
                 res = (np.array(model.owned("normalVelocity")), np.array(model.owned("layerThickness")))
                 model.close()
@@ -151,10 +158,10 @@ def one_case(rng, backend):
                 gu2[loc["edgesGlobal"][:loc["nEdgesOwned"]]] = ru
                 gh2[loc["cellsGlobal"][:loc["nCellsOwned"]]] = rh
             ref = mb.PrognosticVars(ssh, u, h, 2, mb.Mesh(m, backend))
-            mb.ocn_timestep(dt, ref, None, None, None, mb.RungeKutta4, nsteps=sum(calls))
+            mb.ocn_timestep(dt, ref, None, None, None, step_type, nsteps=sum(calls))
             if not (np.array_equal(gu2, ref.normalVelocity) and np.array_equal(gh2, ref.layerThickness)):
-                problems.append(f"DecomposedModel {nparts} ranks {halo} overlap={overlap} graph={graph} calls={calls}")
-            desc += f" + threads {calls} overlap={overlap} graph={graph}"
+                problems.append(f"DecomposedModel {nparts} ranks {halo} overlap={overlap} graph={graph} calls={calls} {step_type.__name__}")
+            desc += f" + threads {calls} overlap={overlap} graph={graph}{' ForwardEuler' if fe else ''}"
     return f"{desc}; {nsteps} steps; renumber={renumber}; {policy}", problems
 
 

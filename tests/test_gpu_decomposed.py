@@ -219,3 +219,66 @@ def test_nccl_two_ranks_torchrun():
                           os.path.join(ROOT, "tests", "multi_gpu_check.py")], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "MULTI_GPU_CHECK_OK" in out.stdout
+
+
+def _run_emulated_fe(backend, m, state, nparts, dt, nsteps, split_parts=True):
+    """ForwardEuler over ranks emulated in one process: mokab_forward_euler_stage per part, the two exchanges of a step
+    (stage 4: (h, u)[new]; stage 5: (ssh, layerThicknessEdge)[new]) as device copies, then the finish call."""
+    locs = partition.decompose(m, nparts)
+    ranks = [_Rank(backend, loc, state, nparts) for loc in locs]
+    lib = L.lib()
+    for _ in range(nsteps):
+        for r in ranks:
+            if split_parts:
+                L.check(lib.mokab_forward_euler_stage(r.h, dt, L.PART_BOUNDARY, None))
+                L.check(lib.mokab_forward_euler_stage(r.h, dt, L.PART_INTERIOR, None))
+            else:
+                L.check(lib.mokab_forward_euler_stage(r.h, dt, L.PART_ALL, None))
+        for s in (4, 5):
+            for r in ranks:
+                L.check(lib.mokab_halo_pack(r.h, s, C.c_void_p(r.send.data_ptr()), None))
+            backend.synchronize()
+            for r in ranks:
+                ro = 0
+                for q, cr in enumerate(r.rcnt):
+                    if cr:
+                        so = sum(ranks[q].scnt[:r.loc["rank"]])
+                        r.recv.copy_from(ro, ranks[q].send, so, cr)
+                    ro += cr
+            device_synchronize()
+            for r in ranks:
+                L.check(lib.mokab_halo_unpack(r.h, s, C.c_void_p(r.recv.data_ptr()), None))
+        for r in ranks:
+            L.check(lib.mokab_forward_euler_finish_step(r.h))
+    gu, gh, gs = np.full(m["nEdges"], np.nan), np.full(m["nCells"], np.nan), np.full(m["nCells"], np.nan)
+    for r in ranks:
+        no, ne = r.loc["nCellsOwned"], r.loc["nEdgesOwned"]
+        gu[r.loc["edgesGlobal"][:ne]] = r.prog.normalVelocity[:ne]
+        gh[r.loc["cellsGlobal"][:no]] = r.prog.layerThickness[:no]
+        gs[r.loc["cellsGlobal"][:no]] = r.prog.ssh[:no]
+    return gu, gh, gs
+
+
+@pytest.mark.hw_pending
+@pytest.mark.parametrize("nx,nparts,split,kelvin", [(32, 2, True, False), (48, 8, True, False), (40, 3, False, False), (32, 4, True, True)])
+def test_staged_forward_euler_on_emulated_ranks_is_the_reference_sequence(backend, nx, nparts, split, kelvin):
+    """The reference's live stepper on a decomposed mesh: bit for bit the oracle's ForwardEuler (first-step quirk and lagged
+    layerThicknessEdge included), which is what the single-domain fused step gives."""
+    if kelvin:
+        m = mb.channel_hex(nx, nx, 1.0e7 / nx)
+        state = mb.kelvinWave(m).initial_state()
+        mo = OC.apply_boundary_mask(m)
+    else:
+        m = mo = hex_mesh(nx)
+        state = mb.inertialGravityWave(m).initial_state()
+    OC.sign_index_fields(mo)
+    dt, nsteps = mb.cfl_dt(m["dc"]), 7
+    om = OC.OracleModel(mo, *state)
+    om.run_loop(dt, nsteps, "ForwardEuler")
+    md = {k: v for k, v in m.items() if k not in ("edgesOnVertex", "cellsOnVertex", "verticesOnEdge", "kiteAreasOnVertex",
+                                                  "areaTriangle", "verticesOnCell", "edgeSignOnVertex")}
+    md["nVertices"] = 0
+    gu, gh, gs = _run_emulated_fe(backend, md, state, nparts, dt, nsteps, split_parts=split)
+    assert np.array_equal(gu, om.normalVelocity[1])
+    assert np.array_equal(gh, om.layerThickness[1])
+    assert np.array_equal(gs, om.ssh[1])

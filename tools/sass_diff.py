@@ -29,6 +29,10 @@ def norm(name):
     # k_rk_stage gained trailing template parameters (bool PUSH = false, int TMA = 0 for every pre-existing instantiation)
     if "k_rk_stage" in name and "Lb0ELi0EEEvNS0_9StageArgs" in name:
         return name.replace("Lb0ELi0EEEvNS0_9StageArgs", "EEvNS0_9StageArgs")
+    # k_fe_step gained a trailing bool LIST = false
+    m = re.match(r"(_ZN5mokab5fused9k_fe_stepILi\d+ELi\d+ELb[01]E)Lb0E(EEvNS0_6FeArgsE)$", name)
+    if m:
+        return m.group(1) + m.group(2)
     return name
 
 
