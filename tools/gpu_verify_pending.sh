@@ -32,6 +32,7 @@ if [ "$ngpu" -ge 2 ]; then
     MOKAB_CHECK_P2P=1 timeout 600 $run --master-port 29611 tests/multi_gpu_check.py > $out/mgcheck_$tag.log 2>&1; echo "mgcheck rc=$?"; tail -n 3 $out/mgcheck_$tag.log
     timeout 300 $run --master-port 29614 tests/multi_gpu_driver_check.py nccl > $out/mgdriver_$tag.log 2>&1; echo "driver rc=$?"; tail -n 2 $out/mgdriver_$tag.log
     timeout 300 $run --master-port 29615 tests/multi_gpu_driver_check.py nccl ForwardEuler > $out/mgdriver_fe_$tag.log 2>&1; echo "driver (ForwardEuler) rc=$?"; tail -n 2 $out/mgdriver_fe_$tag.log
+    timeout 600 $run --master-port 29616 tools/bench_fe_decomposed.py --steps 100 > $out/bench_fe_n${n}_$tag.json 2>> $out/bench_$tag.err; cat $out/bench_fe_n${n}_$tag.json
     for halo in nccl p2p p2p_fused; do
         timeout 900 $run --master-port 29612 bench.py --gpus $n --steps 50 --warmup 5 --halo $halo > $out/bench_n${n}_${halo}_$tag.json 2>> $out/bench_$tag.err
         cat $out/bench_n${n}_${halo}_$tag.json
