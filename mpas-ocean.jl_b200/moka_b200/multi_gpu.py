@@ -162,7 +162,7 @@ class DecomposedModel:
         self._graph, self._graph_dt = None, None
         self._validated, self.graph_status = False, "not used"
         self._parity, self._graph_parity = 0, 0                  # steps taken so far mod 2; the same at graph capture
-        self._fe = False                                         # the last steps were ForwardEuler
+        self._fe, self._stepped = False, False                   # the model steps with ForwardEuler; it has stepped
         if halo != "nccl":
             self._setup_p2p(scnt, rcnt)
 
@@ -332,14 +332,17 @@ class DecomposedModel:
 
     def step(self, dt: float, nsteps: int = 1, stepper=None) -> None:
         """`nsteps` steps of `stepper` (api.RungeKutta4, the default, or api.ForwardEuler)."""
-        if stepper is api.ForwardEuler:
+        if stepper not in (None, api.RungeKutta4, api.ForwardEuler):
+            raise api.MokaError("DecomposedModel.step: unknown stepper")
+        fe = stepper is api.ForwardEuler
+        if self._stepped and fe != self._fe:                     # (ForwardEuler carries a lagged layerThicknessEdge between its steps)
+            raise api.MokaError("DecomposedModel.step: one stepper per model -- build another DecomposedModel to change it")
+        self._stepped = self._stepped or nsteps > 0
+        if fe:
             if nsteps > 0:
                 self._enqueue_fe_steps(dt, nsteps)
                 self._parity ^= nsteps & 1
             return
-        if stepper not in (None, api.RungeKutta4):
-            raise api.MokaError("DecomposedModel.step: unknown stepper")
-        self._fe = False
         if self.use_graph and nsteps >= 2:
             if self._graph is None or self._graph_dt != dt:
                 if not self.validate_graph(dt):
