@@ -233,18 +233,20 @@ def run_driver(nparts, policy, halo, stepper="RK4"):
                 f.write(DRIVER_YAML.format(mesh=mesh_fp, out=os.path.join(tmp, f"out_{tag}.nc"), stepper=stepper))
         simcuda.set_policy("fifo")
         _, _, _, prog1, n1 = mb.ocn_run(cfgs["one"], backend=mb.B200(0))
-        mass1 = mb.reduce_sum(prog1, "mass")
+        mass1, energy1, ssh21 = (mb.reduce_sum(prog1, k) for k in ("mass", "energy", "ssh2"))
         simcuda.set_policy(policy, 5)
 
         def body(r, comm):
             series = []
             _, model, n = mb.driver.ocn_run_decomposed(cfgs["many"], mb.B200(0), 0, runtime=simcuda.SimRuntime(comm, r), halo=halo, series=series)
-            mass = model.reduce("mass")
+            mass, energy, ssh2 = (model.reduce(k) for k in ("mass", "energy", "ssh2"))
             model.close()
-            return n, series, mass
+            return n, series, mass, energy, ssh2
 
         outs = simcuda.run_ranks(nparts, body)
         ok = all(o[0] == n1 == 12 for o in outs) and len(outs[0][1]) == 3 and abs(outs[0][2] - mass1) <= 1e-13 * mass1
+        ok = ok and abs(outs[0][3] - energy1) <= 1e-13 * abs(energy1) and abs(outs[0][4] - ssh21) <= 1e-13 * ssh21
+        ok = ok and abs(outs[0][1][-1]["energy"] - energy1) <= 1e-13 * abs(energy1)        # the series entry of the last output alarm
         with netcdf_file(os.path.join(tmp, "out_one.nc"), "r", mmap=False) as a, netcdf_file(os.path.join(tmp, "out_many.nc"), "r", mmap=False) as b:
             for k in ("ssh", "layerThickness", "normalVelocity", "xCell", "dcEdge", "time"):
                 ok = ok and np.array_equal(np.array(a.variables[k][:]), np.array(b.variables[k][:]))
