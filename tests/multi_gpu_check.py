@@ -29,12 +29,16 @@ def main():
     errs = []
     # the packed NCCL all-to-all in its three schedules; with MOKAB_CHECK_P2P=1 also the direct-store exchange
     # (csrc/kernels_p2p.cuh -- checked on the simulated runtime only so far, so it is not part of the default run yet)
-    cases = [(True, False, "nccl"), (False, False, "nccl"), (True, True, "nccl")]
+    cases = [(True, False, "nccl", "RungeKutta4"), (False, False, "nccl", "RungeKutta4"), (True, True, "nccl", "RungeKutta4")]
     if os.environ.get("MOKAB_CHECK_P2P", "0") == "1":
-        cases += [(True, False, "p2p"), (True, True, "p2p"), (True, False, "p2p_fused"), (True, True, "p2p_fused")]
-    for overlap, graph, halo in cases:
+        cases += [(True, False, "p2p", "RungeKutta4"), (True, True, "p2p", "RungeKutta4"), (True, False, "p2p_fused", "RungeKutta4"),
+                  (True, True, "p2p_fused", "RungeKutta4")]
+    # with MOKAB_CHECK_FE=1 the staged ForwardEuler as well (same status: simulated runtime only so far)
+    if os.environ.get("MOKAB_CHECK_FE", "0") == "1":
+        cases += [(True, False, "nccl", "ForwardEuler"), (False, False, "nccl", "ForwardEuler")]
+    for overlap, graph, halo, stepper in cases:
         model = multi_gpu.DecomposedModel(loc, multi_gpu.local_state(loc, *state), backend, local, overlap=overlap, graph=graph, halo=halo)
-        model.step(dt, nsteps)
+        model.step(dt, nsteps, stepper=getattr(mb, stepper))
         model.finish()
         gs, gu, gh = multi_gpu.gather_owned(model, m["nCells"], m["nEdges"])
         mass = model.reduce("mass")
@@ -44,11 +48,11 @@ def main():
         if rank == 0:
             OC.sign_index_fields(m)
             om = OC.OracleModel(m, *state)
-            om.run_loop(dt, nsteps, "RungeKutta4")
+            om.run_loop(dt, nsteps, stepper)
             rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))
             e = (rel(gs, om.ssh[1]), rel(gu, om.normalVelocity[1]), rel(gh, om.layerThickness[1]))
             m0 = float(np.sum(m["areaCell"] * om.layerThickness[1]))
-            errs.append(((overlap, graph, halo), e, abs(mass - m0) / m0, status))
+            errs.append(((overlap, graph, halo, stepper), e, abs(mass - m0) / m0, status))
     if rank == 0:
         print(errs)
         ok = all(max(e) <= 1e-12 and dm <= 1e-13 for _, e, dm, _ in errs)

@@ -29,7 +29,7 @@ if [ "$ngpu" -ge 2 ]; then
     run="python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1"
     # 4. real NCCL + real IPC: all schedules of both halo paths against the single-domain oracle (96x96: at 8 ranks every block
     #    is a boundary block -- the decomposition that exposed the unordered initialisation)
-    MOKAB_CHECK_P2P=1 timeout 600 $run --master-port 29611 tests/multi_gpu_check.py > $out/mgcheck_$tag.log 2>&1; echo "mgcheck rc=$?"; tail -n 3 $out/mgcheck_$tag.log
+    MOKAB_CHECK_P2P=1 MOKAB_CHECK_FE=1 timeout 600 $run --master-port 29611 tests/multi_gpu_check.py > $out/mgcheck_$tag.log 2>&1; echo "mgcheck rc=$?"; tail -n 3 $out/mgcheck_$tag.log
     timeout 300 $run --master-port 29614 tests/multi_gpu_driver_check.py nccl > $out/mgdriver_$tag.log 2>&1; echo "driver rc=$?"; tail -n 2 $out/mgdriver_$tag.log
     timeout 300 $run --master-port 29615 tests/multi_gpu_driver_check.py nccl ForwardEuler > $out/mgdriver_fe_$tag.log 2>&1; echo "driver (ForwardEuler) rc=$?"; tail -n 2 $out/mgdriver_fe_$tag.log
     timeout 600 $run --master-port 29616 tools/bench_fe_decomposed.py --steps 100 > $out/bench_fe_n${n}_$tag.json 2>> $out/bench_$tag.err; cat $out/bench_fe_n${n}_$tag.json
