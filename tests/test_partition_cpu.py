@@ -121,6 +121,72 @@ def test_two_rank_gloo_halo_exchange_matches_single_domain(tmp_path, world):
     assert np.array_equal(gh, prog["layerThickness"][-1])
 
 
+def _worker_fe(rank, world, port, nx, nsteps, out_dir):
+    """ForwardEuler over two gloo ranks with the numpy oracle as the per-rank compute: the halo copies of (h, u) and of
+    (ssh, layerThicknessEdge) after every step are all a rank needs -- first-step quirk and lagged
+    layerThicknessEdge included."""
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path[:0] = [here, os.path.join(os.path.dirname(here), "mpas-ocean.jl_b200"), os.path.join(os.path.dirname(here), "oracle")]
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import moka_b200.planar_hex as ph
+    import moka_oracle_c as OC
+    from moka_b200 import multi_gpu
+    m = ph.periodic_hex(nx, nx, 1.0e7 / nx, with_dual=False)
+    OC.sign_index_fields(m)
+    ssh, u, h = O.InertialGravityWave(m).initial_state()
+    loc = partition.decompose(m, world)[rank]
+    OC.sign_index_fields(loc)
+    sidx, scnt, ridx, rcnt = partition.flat_halo(loc, world)
+    ex = multi_gpu.HaloExchanger(scnt, rcnt, torch.float64, "cpu")
+    nCl = loc["nCells"]
+    ls, lu, lh = multi_gpu.local_state(loc, ssh, u, h)
+    dt = 0.5 * (1.0e7 / nx) / np.sqrt(O.GRAVITY * 1000.0)
+
+    def exchange(edge_values, cell_values):
+        comb = np.concatenate([cell_values, edge_values])
+        ex.send[:len(sidx)] = torch.from_numpy(comb[sidx])
+        ex.exchange()
+        comb[ridx] = ex.recv[:len(ridx)].numpy()
+        return comb[nCl:], comb[:nCl]
+
+    hE = np.zeros(loc["nEdges"])                                          # DiagnosticVars start at zero: no flux in the first step
+    H = O.resting_thickness_sum(loc)
+    for _ in range(nsteps):
+        flux = lu * hE                                                   # the lagged layerThicknessEdge (DiagnosticVars.jl:141-173)
+        hE_new = O.interpolate_cell2edge(loc, lh)
+        tu = O.compute_normal_velocity_tendency(loc, ls, lu)
+        th = O.compute_layer_thickness_tendency(loc, flux)
+        lu, lh = exchange(lu + dt * tu, lh + dt * th)
+        hE, ls = exchange(hE_new, lh - H)
+    no, ne = loc["nCellsOwned"], loc["nEdgesOwned"]
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), u=lu[:ne], h=lh[:no], ssh=ls[:no], ce=loc["cellsGlobal"][:no], ee=loc["edgesGlobal"][:ne])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_forward_euler_matches_single_domain(tmp_path):
+    import torch.multiprocessing as mp
+    nx, nsteps, world = 16, 6, 2
+    mp.spawn(_worker_fe, args=(world, _free_port(), nx, nsteps, str(tmp_path)), nprocs=world, join=True)
+    m = hex_mesh(nx)
+    ssh, u, h = O.InertialGravityWave(m).initial_state()
+    prog, diag = O.new_state(m, ssh, u, h), O.new_diag(m)
+    dt = 0.5 * (1.0e7 / nx) / np.sqrt(O.GRAVITY * 1000.0)
+    for _ in range(nsteps):
+        O.timestep_forward_euler(m, prog, diag, dt)
+    gu, gh, gs = np.full(m["nEdges"], np.nan), np.full(m["nCells"], np.nan), np.full(m["nCells"], np.nan)
+    for r in range(world):
+        z = np.load(tmp_path / f"r{r}.npz")
+        gu[z["ee"]], gh[z["ce"]], gs[z["ce"]] = z["u"], z["h"], z["ssh"]
+    assert np.array_equal(gu, prog["normalVelocity"][-1])         # bit-exact: same arithmetic per entity
+    assert np.array_equal(gh, prog["layerThickness"][-1])
+    assert np.array_equal(gs, prog["ssh"][-1])
+
+
 def test_as_many_parts_as_cells_and_one_more():
     """One cell per part is the limit: every rank must own a cell (an empty rank would launch empty grids); beyond it the
     partitioner refuses with a message instead of failing somewhere inside numpy."""
