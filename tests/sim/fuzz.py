@@ -1,6 +1,6 @@
 """Randomised sweep of the library on the simulated runtime: random meshes (regular hexagons of odd shapes, channel meshes with
 wall masks, periodic Voronoi meshes from squares to octagons, spheres), random decompositions (2..9 ranks, all three halo
-paths), every stepper and both adjoints, a random scheduling policy -- each compared with the CPU oracle (bit for bit where
+paths; RungeKutta4 and, on the packed path, the staged ForwardEuler), every stepper and both adjoints, a random scheduling policy -- each compared with the CPU oracle (bit for bit where
 the operation order is the reference's, rel-L2 <= 1e-12 where weights are folded or sums reassociated).  Test infrastructure.
 
   python tests/sim/fuzz.py [--iterations 30] [--seed 0]
