@@ -282,3 +282,36 @@ def test_staged_forward_euler_on_emulated_ranks_is_the_reference_sequence(backen
     assert np.array_equal(gu, om.normalVelocity[1])
     assert np.array_equal(gh, om.layerThickness[1])
     assert np.array_equal(gs, om.ssh[1])
+
+
+@pytest.mark.hw_pending
+@pytest.mark.parametrize("parts", [(L.PART_ALL,), (L.PART_BOUNDARY, L.PART_INTERIOR)])
+def test_staged_forward_euler_on_an_undecomposed_mesh_interoperates_with_the_whole_mesh_entry_point(backend, parts):
+    """No halo at all: five staged steps are five ocn_timestep(ForwardEuler) steps, and three more through the whole-mesh entry
+    point continue the same trajectory (the lagged layerThicknessEdge is handed over).  Meshes with vertex arrays are refused
+    (the staged step does not advance relativeVorticity), and so is a finish call without a stage."""
+    m = hex_mesh(20)
+    ssh, u, h = mb.inertialGravityWave(m).initial_state()
+    dt = mb.cfl_dt(m["dc"])
+    lib = L.lib()
+    ref5 = mb.PrognosticVars(ssh, u, h, 2, mb.Mesh(m, backend))
+    mb.ocn_timestep(dt, ref5, None, None, None, mb.ForwardEuler, nsteps=5)
+    ref8 = mb.PrognosticVars(ssh, u, h, 2, mb.Mesh(m, backend))
+    mb.ocn_timestep(dt, ref8, None, None, None, mb.ForwardEuler, nsteps=8)
+    with_vertices = mb.PrognosticVars(ssh, u, h, 2, mb.Mesh(m, backend))
+    with pytest.raises(mb.MokaError, match="carry no vertices"):
+        L.check(lib.mokab_forward_euler_stage(with_vertices.dev.handle, dt, L.PART_ALL, None))
+    md = {k: v for k, v in m.items() if k not in ("edgesOnVertex", "cellsOnVertex", "verticesOnEdge", "kiteAreasOnVertex",
+                                                  "areaTriangle", "verticesOnCell", "edgeSignOnVertex")}
+    md["nVertices"] = 0
+    prog = mb.PrognosticVars(ssh, u, h, 2, mb.Mesh(md, backend))
+    with pytest.raises(mb.MokaError, match="no staged ForwardEuler step has run"):
+        L.check(lib.mokab_forward_euler_finish_step(prog.dev.handle))
+    for _ in range(5):
+        for part in parts:
+            L.check(lib.mokab_forward_euler_stage(prog.dev.handle, dt, part, None))
+        L.check(lib.mokab_forward_euler_finish_step(prog.dev.handle))
+    assert np.array_equal(prog.normalVelocity, ref5.normalVelocity) and np.array_equal(prog.layerThickness, ref5.layerThickness)
+    assert np.array_equal(prog.ssh, ref5.ssh)
+    mb.ocn_timestep(dt, prog, None, None, None, mb.ForwardEuler, nsteps=3)
+    assert np.array_equal(prog.normalVelocity, ref8.normalVelocity) and np.array_equal(prog.layerThickness, ref8.layerThickness)
