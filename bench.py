@@ -54,6 +54,39 @@ def algo_bytes_per_cell_step_general(m: dict, dtype: str, derived_fraction: floa
     return 4.0 * per_stage / nC
 
 
+def workload_label(name: str, nx: int) -> str:
+    """config.workload: the SAME string in both arms (--impl b200 / reference), one per BASELINE.json config."""
+    if name.startswith("kelvin"):
+        return f"coastal Kelvin wave, {nx}x{nx} channel hex mesh with boundary-edge masks, RK4"
+    if name.startswith("sphere"):
+        return f"geostrophic zonal flow + noise, quasi-uniform spherical Voronoi mesh of {nx * nx} cells, fEdge = 2 Omega sin(lat), RK4"
+    if name.startswith("voronoi"):
+        return f"inertial gravity wave, {nx}x{nx} periodic planar Voronoi mesh of a jittered lattice, RK4"
+    return f"inertial gravity wave, {nx}x{nx} periodic planar hex mesh, RK4"
+
+
+def parity_against_oracle(m, state, dt, nsteps, got_ssh, got_u, dtype, workload):
+    """The bench line's `parity` object: the result of `nsteps` RK4 steps from the initial state, as this run's GPU path
+    computed it, against the C oracle (oracle/moka_oracle.c, the CPU restatement of the reference path -- here only as the
+    checker) on the same undecomposed mesh.  Tolerance: BASELINE.json's relative L2 1e-12 (Float64) / 1e-5 (Float32)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import moka_oracle_c as OC
+    mm = OC.apply_boundary_mask(m) if workload.startswith("kelvin") else m
+    if "edgeSignOnCell" not in mm:
+        OC.sign_index_fields(mm)
+    ssh, u, h = state
+    om = OC.OracleModel(mm, ssh, u, h)
+    om.run_loop(dt, nsteps, "RungeKutta4")
+    rel = lambda a, b: float(np.linalg.norm(np.asarray(a, np.float64) - b) / np.linalg.norm(b))
+    tol = 1e-12 if dtype == "f64" else 1e-5
+    e_ssh, e_u = rel(got_ssh, om.ssh[1]), rel(got_u, om.normalVelocity[1])
+    return {"vs": "C oracle (oracle/moka_oracle.c: CPU restatement of the reference path) on the undecomposed mesh",
+            "steps": nsteps, "rel_l2_ssh": e_ssh, "rel_l2_normalVelocity": e_u, "tolerance": tol,
+            "bit_identical": bool(dtype == "f64" and np.array_equal(got_ssh, om.ssh[1]) and np.array_equal(got_u, om.normalVelocity[1])),
+            "ok": bool(e_ssh <= tol and e_u <= tol),
+            "oracle_pinning": "operators pinned by the reference's six golden vectors; tendency / RK4 field values unpinned by the reference (DESIGN.md section 8)"}
+
+
 def measured_peak_gbs():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -121,6 +154,7 @@ def build_case(nx: int, dtype: str):
 
 def run_b200(args):
     import moka_b200 as mb
+    from moka_b200 import _lib as L
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -146,36 +180,49 @@ def run_b200(args):
     # ---- device-resident throughput (inputs already in HBM) -----------------------------------------
     mb.ocn_run_loop(dt, prog, diag, tend, None, mb.RungeKutta4, W)
     backend.synchronize()
+    # the timed region is K steps repeated until it lasts >= 0.5 s (at 6 ms/step 20 steps are 0.12 s: one hiccup would be 5 %)
+    backend.timer_start()
+    mb.ocn_timestep(dt, prog, diag, tend, None, mb.RungeKutta4, nsteps=K)
+    reps = 1 if args.quick else int(max(1, np.ceil(500.0 / max(backend.timer_stop(), 1e-3))))
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
     l0 = backend.launch_count()
     backend.timer_start()
-    mb.ocn_timestep(dt, prog, diag, tend, None, mb.RungeKutta4, nsteps=K)
+    for _ in range(reps):
+        mb.ocn_timestep(dt, prog, diag, tend, None, mb.RungeKutta4, nsteps=K)
     ms = backend.timer_stop()
     launches_total = backend.launch_count() - l0
-    stage_launches = 4 * K                                  # + 2 ssh refresh kernels at the end of the call
+    steps_timed = K * reps
+    stage_launches = 4 * steps_timed                        # + 2 ssh refresh kernels at the end of every call
     # keep the GPU under the same load while nvidia-smi gets its samples (not part of the number)
     t_end = time.time() + (0.0 if args.quick else 1.0)
     while time.time() < t_end:
         mb.ocn_timestep(dt, prog, diag, tend, None, mb.RungeKutta4, nsteps=10)
         backend.synchronize()
     clocks = sampler.stop()
-    value = nC * K / (ms * 1e-3)
+    value = nC * steps_timed / (ms * 1e-3)
 
     # ---- end to end through the public API with HOST buffers ----------------------------------------------
     # every step: H2D of that step's (normalVelocity, layerThickness) from pinned memory, one RK4 step, D2H of ssh.
     # The copies go through the pipelined upload/download of the API, so the PCIe transfer of step n+1 and
     # n-1 overlap the kernels of step n; two alternating sets of host buffers stand for distinct inputs.
+    # The step's result that comes back is (ssh, normalVelocity) of the new state; layerThickness = ssh + restingThicknessSum is
+    # redundant with ssh (restingThicknessSum is static and already on the host) and stays on the device.  Float32 states
+    # upload ssh instead of layerThickness (the perturbation is their prognostic variable, include/moka_b200.h).
+    f32 = npdt == np.float32
     hin = [(backend.pinned(nE, npdt), backend.pinned(nC, npdt)) for _ in range(2)]
-    hout = [backend.pinned(nC, npdt) for _ in range(2)]
+    hout = [(backend.pinned(nC, npdt), backend.pinned(nE, npdt)) for _ in range(2)]
     for hu, hh in hin:
-        hu[:], hh[:] = u.astype(npdt), h.astype(npdt)
+        hu[:], hh[:] = u.astype(npdt), (ssh if f32 else h).astype(npdt)
     def e2e_steps(n):
         for i in range(n):
-            prog.upload_async(normalVelocity=hin[i & 1][0], layerThickness=hin[i & 1][1])
+            if f32:
+                prog.upload_async(normalVelocity=hin[i & 1][0], ssh=hin[i & 1][1])
+            else:
+                prog.upload_async(normalVelocity=hin[i & 1][0], layerThickness=hin[i & 1][1])
             mb.ocn_timestep(dt, prog, diag, tend, None, mb.RungeKutta4, nsteps=1)
-            prog.download_async(ssh=hout[i & 1])
+            prog.download_async(ssh=hout[i & 1][0], normalVelocity=hout[i & 1][1])
         prog.synchronize()
     e2e_steps(1 if args.quick else 3)
     Ke = 2 if args.quick else max(3, min(K, 50))
@@ -186,7 +233,12 @@ def run_b200(args):
     # the result of the last e2e step is one RK4 step from the uploaded state: check it against a device-resident step
     prog_chk = mb.PrognosticVars(ssh.astype(npdt), u.astype(npdt), h.astype(npdt), 2, mesh)
     mb.ocn_timestep(dt, prog_chk, diag, tend, None, mb.RungeKutta4, nsteps=1)
-    e2e_ok = bool(np.array_equal(prog_chk.ssh, hout[(Ke - 1) & 1]))
+    e2e_ok = bool(np.array_equal(prog_chk.ssh, hout[(Ke - 1) & 1][0]) and np.array_equal(prog_chk.normalVelocity, hout[(Ke - 1) & 1][1]))
+    # ---- parity: two RK4 steps from the initial state against the C oracle (checker only) --------------------------------
+    parity = None
+    if not args.no_parity:
+        mb.ocn_timestep(dt, prog_chk, diag, tend, None, mb.RungeKutta4, nsteps=1)
+        parity = parity_against_oracle(m, (ssh, u, h), dt, 2, prog_chk.ssh, prog_chk.normalVelocity, args.dtype, args.workload)
     del prog_chk
 
     # ---- roofline of the dominant kernel (k_rk_stage) -----------------------------------------------------------
@@ -209,28 +261,28 @@ def run_b200(args):
         "metric": "RK4 cell-steps/sec", "value": value, "unit": "cell-steps/s", "n_gpus": 1, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": (f"coastal Kelvin wave, {nx}x{nx} channel hex mesh with boundary-edge masks" if kelvin else
-                                f"geostrophic zonal flow + noise, spherical Voronoi mesh, fEdge = 2 Omega sin(lat) "
-                                f"(polygons by side count from 5: {np.bincount(m['nEdgesOnCell'])[5:].tolist()}; device rows "
-                                f"{mesh.maxEdges2} / {mesh.maxEdges})" if sphere else
-                                f"inertial gravity wave, {nx}x{nx} periodic planar Voronoi mesh of a jittered lattice "
-                                f"(polygons by side count from 5: {np.bincount(m['nEdgesOnCell'])[5:].tolist()}; device rows "
-                                f"{mesh.maxEdges2} / {mesh.maxEdges})" if voronoi else
-                                f"inertial gravity wave, {nx}x{nx} periodic planar hex mesh") + f" ({nC} cells, {nE} edges), "
-                               f"{'Float64' if args.dtype == 'f64' else 'Float32'} RK4, dt={dt:.4g}s",
+        "config": {"workload": workload_label(args.workload, nx),
+                   "detail": f"{nC} cells, {nE} edges, {'Float64' if args.dtype == 'f64' else 'Float32'}, dt={dt:.4g}s"
+                             + (f", polygons by side count from 5: {np.bincount(m['nEdgesOnCell'])[5:].tolist()}; device rows "
+                                f"{mesh.maxEdges2} / {mesh.maxEdges}" if voronoi else ""),
+                   "timed_steps": steps_timed, "repeats_of_steps": reps,
                    "name": args.workload, "l2": "inputs larger than L2 (no flush)" if nx >= 1024 else "fits in L2",
                    "mesh_gen_s": round(t_gen, 2), "mesh_upload_s": round(t_mesh, 2),
                    "blocks_rebuilding_edgesOnEdge": [int(nder), int(nblk)],
                    # which build / stage-kernel variant ran (tools/gpu_sweep_variants.sh; the defaults when unset)
                    "variant": {"lib": os.environ.get("MOKAB_LIB", "libmoka_b200.so"),
-                               "stage_tma": int(os.environ.get("MOKAB_STAGE_TMA", "0") or 0)}},
+                               "stage_tma": L.get_option("stage_tma"), "stage_prefetch": L.get_option("stage_prefetch"),
+                               "stage_prefetch_distance": L.get_option("stage_prefetch_distance")}},
         "clocks": clocks,
         "e2e": {"value": nC / e2e_s, "unit": "cell-steps/s", "h2d_bytes_per_step": int((nE + nC) * item),
-                "d2h_bytes_per_step": int(nC * item), "ms_per_step": e2e_s * 1e3, "steps": Ke,
-                "pipelined": True, "matches_device_resident_step": e2e_ok},
+                "d2h_bytes_per_step": int((nC + nE) * item), "ms_per_step": e2e_s * 1e3, "steps": Ke,
+                "pipelined": True, "matches_device_resident_step": e2e_ok,
+                "returns": "ssh + normalVelocity of the new state (layerThickness = ssh + restingThicknessSum stays on the device)"},
         "gpu_launches": int(launches_total),
+        "parity": parity,
         "roofline": {"bound": "hbm", "kernel": "k_rk_stage", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "traffic_source": "profiles/traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one committed `ncu --set full` capture, per launch; not measured in this run)" if traffic else None,
                      "algorithmic_bytes_per_launch": algo_bytes_per_launch, "avg_launch_ms": avg_launch_s * 1e3,
                      "bytes_per_cell_step": algo_bytes_per_launch * 4.0 / nC,
                      "rate_if_edgesOnEdge_were_read": survey_rate,
@@ -251,6 +303,7 @@ def cpu_baseline(m, state, dt, budget_s=15.0, kelvin=False):
     ssh, u, h = state
     if kelvin:
         m = OC.apply_boundary_mask(m)
+    OC.set_num_threads(os.cpu_count() or 1)
     om = OC.OracleModel(m, ssh, u, h)
     om.run_loop(dt, 1, "RungeKutta4")                       # warm-up (thread pool, page faults)
     t0 = time.perf_counter()
@@ -286,6 +339,8 @@ def run_reference(args):
     if sphere or voronoi:
         OC.sign_index_fields(m)
     # each "step" is a bounded sample: one RK4 step on the workload mesh (capped so the run ends in minutes)
+    # all the host cores, explicitly: under torchrun the environment carries OMP_NUM_THREADS=1
+    OC.set_num_threads(os.cpu_count() or 1)
     om = OC.OracleModel(m, ssh, u, h)
     K, W = args.steps, args.warmup
     om.run_loop(dt, 1, "RungeKutta4")
@@ -304,10 +359,7 @@ def run_reference(args):
         "impl": "reference", "metric": "RK4 cell-steps/sec", "value": v, "unit": "cell-steps/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": tt / K * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": ("coastal Kelvin wave, channel hex mesh with boundary-edge masks" if kelvin else
-                                "geostrophic zonal flow + noise, spherical Voronoi mesh" if sphere else
-                                f"inertial gravity wave, {nx}x{nx} periodic planar Voronoi mesh" if voronoi else
-                                f"inertial gravity wave, {nx}x{nx} periodic planar hex mesh") + f" ({m['nCells']} cells), Float64 RK4",
+        "config": {"workload": workload_label(args.workload, nx), "detail": f"{m['nCells']} cells, Float64",
                    "name": args.workload},
         "cpu_baseline": {"value": v, "unit": "cell-steps/s", "cores": om.num_threads(), "kind": "port",
                          "sample": f"{K} RK4 steps on the full {m['nCells']}-cell mesh, C/OpenMP restatement of the "
@@ -325,6 +377,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-parity", dest="no_parity", action="store_true", help="skip the parity check against the C oracle")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-overlap", dest="no_overlap", action="store_true", help="multi-GPU: exchange after each full stage")
     ap.add_argument("--no-graph", dest="no_graph", action="store_true", help="multi-GPU: do not capture steps into a CUDA graph")

@@ -295,6 +295,59 @@ int  mokab_halo_wait_arrivals(mokab_state *state, void *cuda_stream);
 int  mokab_p2p_close(mokab_state *state);
 /* 1 if a wait ever timed out (~2 s: a peer died or the ranks' schedules diverged); the GPU is never left spinning */
 int  mokab_p2p_error(mokab_state *state, int *out);
+/* ---- domain-decomposed stepping inside the library (csrc/comm.cuh, csrc/decomposed.cuh) --------------------------------------
+ * One process per GPU.  The reference has no multi-device path (its driver builds one backend, src/driver/mpas_ocean.jl:28);
+ * this stands behind BASELINE.json's north_star: "halo exchange runs as NCCL send/recv (or direct P2P stores) over NVLink,
+ * overlapped with interior-cell compute".  The library owns the exchange, the two streams, the events and the captured step
+ * graphs; the host program only brings the ranks together, the way NCCL itself asks:
+ *   rank 0:      mokab_comm_get_unique_id(id)           (MOKAB_COMM_ID_BYTES bytes; hand them to every rank: MPI.jl, a file, ...)
+ *   every rank:  mokab_comm_init(ctx, id, rank, nranks, &comm)
+ *                mokab_mesh_create(local mesh, nCellsOwned / nEdgesOwned) ; mokab_halo_setup(mesh, send list, recv list)
+ *                mokab_state_create ; mokab_state_set ...
+ *                mokab_decomp_setup(state, comm, send_counts, recv_counts, MOKAB_HALO_NCCL, 0)
+ *                mokab_timestep_rk4_decomposed(state, dt, nsteps)   |   mokab_timestep_forward_euler_decomposed(...)
+ *                mokab_reduce_decomposed(state, MOKAB_SUM_SSH2, &s) ;  mokab_state_get ...
+ *                mokab_decomp_close(state) ; mokab_state_destroy ; mokab_comm_destroy(comm)
+ * send_counts[q] / recv_counts[q]: how many consecutive entries of the send / recv list of mokab_halo_setup go to / come from
+ * rank q (the lists are ordered by rank).  Collective calls: comm_init, decomp_setup, the timestep calls, reduce_decomposed,
+ * comm_barrier / allreduce / allgather, decomp_close -- every rank makes them in the same order. */
+#define MOKAB_COMM_ID_BYTES 128
+typedef struct mokab_comm mokab_comm;
+enum { MOKAB_HALO_NCCL = 0,       /* pack -> ncclSend/ncclRecv per neighbour (one group) -> unpack, on the halo stream             */
+       MOKAB_HALO_P2P = 1,        /* direct stores into the neighbours' state arrays (CUDA IPC) + arrival counters: push / wait kernels */
+       MOKAB_HALO_P2P_FUSED = 2   /* the same stores issued by the boundary blocks themselves (MOKAB_PART_BOUNDARY_PUSH)            */ };
+enum { MOKAB_DECOMP_NO_OVERLAP = 1u, /* exchange after each whole stage on one stream (diagnostic)                                   */
+       MOKAB_DECOMP_NO_GRAPH = 2u    /* launch every step from the host instead of replaying captured 1- / 2-step graphs (diagnostic) */ };
+int  mokab_comm_get_unique_id(void *id_out);
+int  mokab_comm_init(mokab_ctx *ctx, const void *id, int rank, int nranks, mokab_comm **out);
+int  mokab_comm_destroy(mokab_comm *comm);
+int  mokab_comm_rank(const mokab_comm *comm, int *rank, int *nranks);
+/* host-level collectives for the driver around the steps (synchronous): op 0 = sum (in rank order: the same bits on every
+ * rank), 1 = max, 2 = min; allgather: `bytes` bytes from every rank, rank-major */
+int  mokab_comm_barrier(mokab_comm *comm);
+int  mokab_comm_allreduce_f64(mokab_comm *comm, double *inout, int64_t n, int op);
+int  mokab_comm_allgather_bytes(mokab_comm *comm, const void *mine, int64_t bytes, void *all);
+int  mokab_decomp_setup(mokab_state *state, mokab_comm *comm, const int64_t *send_counts, const int64_t *recv_counts, int halo_mode,
+                        uint32_t flags);
+int  mokab_decomp_set_flags(mokab_state *state, uint32_t flags);
+/* ocn_run_loop + ocn_timestep over the ranks of `comm`: the same results, bit for bit, as the single-domain entry points on
+ * the undecomposed mesh (time_integration.jl:61-148 / :150-193).  Asynchronous like their single-domain counterparts. */
+int  mokab_timestep_rk4_decomposed(mokab_state *state, double dt, int64_t nsteps);
+int  mokab_timestep_forward_euler_decomposed(mokab_state *state, double dt, int64_t nsteps);
+/* mokab_reduce over the owned entities of every rank, summed in rank order (sumArray, run_loop.jl:47-51) */
+int  mokab_reduce_decomposed(mokab_state *state, int which, double *out);
+/* drain both streams of the state; fails if a direct-store halo wait timed out (MOKAB_P2P_TIMEOUT_S, default 20 s) */
+int  mokab_decomp_synchronize(mokab_state *state);
+int  mokab_decomp_close(mokab_state *state);
+
+/* Tuning switches of the fused stage kernel (process-wide; no reference counterpart -- the reference's only knob is the
+ * workgroup size hard-coded at each launch, e.g. src/forward/time_integration.jl:181).  Results are bit-identical under every
+ * setting.  "stage_prefetch": bit 0 = a block pulls the streams of its later iterations into L2 at entry, bit 1 = those of
+ * the block launched "stage_prefetch_distance" blocks later (0 = one wave of resident blocks); "stage_tma": 1 / 2 = the
+ * Coriolis weights through bulk asynchronous copies (slot-major rows / a block-major copy).  Initial values come from the
+ * environment (MOKAB_STAGE_PREFETCH, MOKAB_STAGE_PREFETCH_DISTANCE, MOKAB_STAGE_TMA). */
+int  mokab_set_option(const char *name, int64_t value);
+int  mokab_get_option(const char *name, int64_t *value);
 /* number of interior / boundary blocks of the fused kernel (diagnostic) */
 int  mokab_mesh_block_counts(const mokab_mesh *mesh, int64_t *interior, int64_t *boundary);
 /* number of fused-kernel blocks, and how many of them rebuild edgesOnEdge from edgesOnCell (diagnostic) */

@@ -117,7 +117,10 @@ namespace mokab {
 #ifdef MOKAB_SIM   // host build of the simulation tests (tests/sim): a plain load
 template <class T>
 __device__ __forceinline__ T ld_stream(const T *p) { return *p; }
+__device__ __forceinline__ void prefetch_l2(const void *) {}
 #else
+// pull the line holding *p into L2 (no register, no fault on a bad address)
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 template <class T>
 __device__ __forceinline__ T ld_stream(const T *p);
 template <>

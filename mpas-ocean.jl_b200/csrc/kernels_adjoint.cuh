@@ -36,6 +36,7 @@ struct AdjArgs {
     const uint8_t *nEoET, *nEoC;
     const int32_t *blkEdgeStart;
     const R *gdc, *wfT, *dv, *invArea;
+    const R *H;               // Float32 only: hY holds h - H (kernels_fused.cuh: kPert), the flux Jacobian needs the whole thickness
     const R *uY, *hY;         // the state y_s the Jacobian is taken at
     const R *kuIn, *kqIn;     // kbar_u[e], invArea[c]*kbar_h[c] of this stage (FIRST: lam' itself, scaled on the fly)
     const R *lamU, *lamH;     // lam'
@@ -59,6 +60,7 @@ k_rk_stage_adj(const AdjArgs<R> A)
     const int nE = A.nE, nC = A.nC;
     const int b = blockIdx.x;
     auto ku = [&](int e) -> R { return MODE == 0 ? A.bThis * __ldg(A.lamU + e) : __ldg(A.kuIn + e); };
+    auto hTot = [&](int c) -> R { return sizeof(R) == 4 ? __ldg(A.hY + c) + __ldg(A.H + c) : __ldg(A.hY + c); };
     auto kq = [&](int c) -> R { return MODE == 0 ? A.bThis * __ldg(A.invArea + c) * __ldg(A.lamH + c) : __ldg(A.kqIn + c); };
 
     const int e0 = A.blkEdgeStart[b], e1 = A.blkEdgeStart[b + 1];
@@ -78,14 +80,14 @@ k_rk_stage_adj(const AdjArgs<R> A)
             for (int j = 0; j < S2TT; ++j) w[j] = j < n ? ld_stream(A.wfT + (size_t)j * nE + e) : R(0);
 #pragma unroll
             for (int j = 0; j < S2TT; ++j) kk[j] = ku(idx[j]);
-            const R q1 = kq(c.x), h1 = __ldg(A.hY + c.x);
-            const R q2 = masked ? R(0) : kq(c.y), h2 = masked ? h1 : __ldg(A.hY + c.y);
+            const R q1 = kq(c.x), h1 = hTot(c.x);
+            const R q2 = masked ? R(0) : kq(c.y), h2 = masked ? h1 : hTot(c.y);
             yb = R(0.5) * (h1 + h2) * (ld_stream(A.dv + e) * (q2 - q1));
 #pragma unroll
             for (int j = 0; j < S2TT; ++j) yb += w[j] * kk[j];
         } else {
-            const R q1 = kq(c.x), h1 = __ldg(A.hY + c.x);
-            const R q2 = masked ? R(0) : kq(c.y), h2 = masked ? h1 : __ldg(A.hY + c.y);
+            const R q1 = kq(c.x), h1 = hTot(c.x);
+            const R q2 = masked ? R(0) : kq(c.y), h2 = masked ? h1 : hTot(c.y);
             yb = R(0.5) * (h1 + h2) * (ld_stream(A.dv + e) * (q2 - q1));
             for (int j = 0; j < n; ++j) {
                 const int x = ld_stream(A.eoeT + (size_t)j * nE + e);
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(256)
 k_seed_ssh2(int64_t n, const R *__restrict__ h, const R *__restrict__ H, R *__restrict__ dssh)
 {
     const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (c < n) dssh[c] = R(2) * (h[c] - H[c]);
+    if (c < n) dssh[c] = sizeof(R) == 4 ? R(2) * h[c] : R(2) * (h[c] - H[c]);   // Float32 `h` arrays hold h - H
 }
 
 // the same seed from the ssh ARRAY (ForwardEuler: ssh is a prognostic array of its own, equal to h - H only after a step)

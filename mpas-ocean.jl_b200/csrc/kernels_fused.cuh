@@ -50,6 +50,13 @@ __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(
 __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
 
+// Float32 states carry the PERTURBATION of the layer thickness, h - restingThicknessSum (= ssh on this single-layer path), in
+// their `h` arrays: around h ~ 1000 m a Float32 resolves 6e-5 m, which is 6e-5 of the 1 m wave signal and far from
+// BASELINE.json's 1e-5 tolerance, while the perturbation itself keeps the full 24-bit significand for the pressure gradient
+// and for the RK accumulation.  The whole thickness H + (h - H) is formed only where the thickness flux needs it.  Float64
+// states keep the reference's variable (layerThickness) and operation order bit for bit.
+template <class R> constexpr bool kPert = sizeof(R) == 4;
+
 // Direct-store halo exchange folded into the BOUNDARY launch of a stage (PUSH = true; protocol and ordering argument in
 // kernels_p2p.cuh, which holds the stand-alone variant): a block first waits until every sender's arrival counter has
 // reached this rank's count of completed boundary launches, computes, stores each value a neighbour needs straight into
@@ -95,6 +102,7 @@ struct StageArgs {
     R f0;                    // uniform fEdge (FOLD = false): weights stay unfolded, (w*u)*f0 formed as the reference does;
                              // FOLD = true: wf already holds weightsOnEdge*fEdge[eoe] (variable f; differs by round-off)
     const PushStage<R> *push;  // PUSH launches only (device memory); nullptr otherwise
+    int pf, pfDist;            // L2 prefetch of the streaming operands (moka_b200.cu: Options::stage_prefetch), distance in launched blocks
     int wStride;               // TMA = 1 launches only: elements between the staged weight rows in shared memory
     const R *wfB;              // TMA = 2: the weights again, BLOCK-major -- block b's S2 rows back to back, each padded to 16 bytes,
     const long long *wfBOff;   //          starting at element wfBOff[b] (16-byte aligned): one contiguous run, one bulk copy per block
@@ -196,7 +204,7 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
             const int q = P.senders[threadIdx.x];
             const long long t0 = clock64();
             while (p2p::load_acquire_system(P.arrival + q) < P.expect[q]) {
-                if (clock64() - t0 > P.timeout_cycles) {
+                if (*(volatile int *)P.error || clock64() - t0 > P.timeout_cycles) {
                     atomicExch(P.error, 1);
                     break;
                 }
@@ -209,6 +217,55 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
 
     constexpr bool kDer = DER && ST != 0 && S2T != 0;
     const bool derived = kDer && A.blkDerived && A.blkDerived[b];
+
+    // ---- L2 prefetch of the streaming operands (opt-in, A.pf) ----------------------------------------------------------------
+    // The kernel is bound by dependent DRAM latencies (stream -> index -> gather) at the occupancy its registers allow, not by
+    // bytes.  `prefetch.global.L2` costs no register and no shared memory: (bit 0) at entry a block pulls the streams of its
+    // own second and third edge iteration and of its cell phase into L2 while the first iteration waits on DRAM, so three of
+    // its four streaming hops become L2 hits; (bit 1) it does the same for the whole working set of the block that is
+    // launched A.pfDist blocks later -- about one wave of resident blocks, i.e. the block that takes over this block's slot.
+    if constexpr (S2T != 0 && !PUSH) {
+        if (A.pf) {
+            auto pf_edges = [&](int ea, int eb, bool far) {
+                for (int e = ea + (int)threadIdx.x; e < eb; e += kThreads) {
+                    prefetch_l2(A.ce + e);
+                    prefetch_l2(A.gdc + e);
+                    if (kDer && A.blkDerived) prefetch_l2(A.posE + e);
+                    else {
+#pragma unroll
+                        for (int i = 0; i < S2T; ++i) prefetch_l2(A.eoe + (size_t)i * nE + e);
+                    }
+                    if constexpr (TMA == 0) {
+#pragma unroll
+                        for (int i = 0; i < S2T; ++i) prefetch_l2(A.wf + (size_t)i * nE + e);
+                    }
+                    if (STAGE != 4) prefetch_l2(A.uCur + e);
+                    if (STAGE != 1) prefetch_l2(A.uAcc + e);
+                    if (far && STAGE != 1) prefetch_l2(A.uOld + e);      // most of the gathers of a block land in its own index range
+                }
+            };
+            auto pf_cells = [&](int c, bool far) {
+                if (c >= A.nCown) return;
+#pragma unroll
+                for (int i = 0; i < ST; ++i) prefetch_l2(A.eoc + (size_t)i * nC + c);
+                prefetch_l2(A.invArea + c);
+                prefetch_l2(A.H + c);
+                if (STAGE != 4) prefetch_l2(A.hCur + c);
+                if (STAGE != 1) prefetch_l2(A.hAcc + c);
+                if (far && STAGE != 1) prefetch_l2(A.hOld + c);
+            };
+            if (A.pf & 1) {
+                pf_edges(A.blkEdgeStart[b] + kThreads, A.blkEdgeStart[b + 1], false);
+                pf_cells(cBase + (int)threadIdx.x, false);
+            }
+            if ((A.pf & 2) && blockIdx.x + (unsigned)A.pfDist < gridDim.x) {
+                const int bn = A.blockList ? A.blockList[blockIdx.x + A.pfDist] : (int)blockIdx.x + A.pfDist;
+                const int ea = A.blkEdgeStart[bn], eb = A.blkEdgeStart[bn + 1];
+                pf_edges(ea, ((A.pf & 1) && eb > ea + kThreads) ? ea + kThreads : eb, true);
+                pf_cells(bn * kTC + (int)threadIdx.x, true);
+            }
+        }
+    }
 
     // ---- edges owned by this block's cells ----------------------------------------------------------
     const int e0 = A.blkEdgeStart[b], e1 = A.blkEdgeStart[b + 1];
@@ -239,7 +296,7 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
             const R cur = (STAGE == 4) ? R(0) : A.uCur[e];
             const R accIn = (STAGE == 1) ? R(0) : A.uAcc[e];
             const R h1 = __ldg(A.hOld + c.x), h2 = __ldg(A.hOld + c.y);
-            const R H1 = __ldg(A.H + c.x), H2 = __ldg(A.H + c.y);
+            const R H1 = kPert<R> ? R(0) : __ldg(A.H + c.x), H2 = kPert<R> ? R(0) : __ldg(A.H + c.y);
             if (kDer && derived) {
                 // posE: bits 0-2 position of e in the row of cell 1, bits 3-5 in the row of cell 2, bit 7 = both rows
                 // have ST entries and the edge is not masked (the branch-free common case)
@@ -292,7 +349,7 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
                 }
             }
             // tend = 0 - (g/dc)*(ssh2 - ssh1), then += (w*u)*f slot by slot (pressure_gradient.jl:63, coriolis :70-72)
-            k = -mul_rn(g, add_rn(add_rn(h2, -H2), -add_rn(h1, -H1)));
+            k = kPert<R> ? -mul_rn(g, add_rn(h2, -h1)) : -mul_rn(g, add_rn(add_rn(h2, -H2), -add_rn(h1, -H1)));
 #pragma unroll
             for (int i = 0; i < S2T; ++i) k = add_rn(k, FOLD ? mul_rn(w[i], uu[i]) : mul_rn(mul_rn(w[i], uu[i]), A.f0));
             if (STAGE != 4) A.uOut[e] = add_rn(cur, mul_rn(A.a, k));       // Provis = Curr + a*tend (time_integration.jl:124)
@@ -309,8 +366,9 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
         const R cur = (STAGE == 4) ? R(0) : A.uCur[e];
         const R accIn = (STAGE == 1) ? R(0) : A.uAcc[e];
         const R h1 = __ldg(A.hOld + c.x), h2 = __ldg(A.hOld + c.y);
-        const R H1 = __ldg(A.H + c.x), H2 = __ldg(A.H + c.y);
-        k = -mul_rn(ld_stream(A.gdc + e), add_rn(add_rn(h2, -H2), -add_rn(h1, -H1)));
+        const R H1 = kPert<R> ? R(0) : __ldg(A.H + c.x), H2 = kPert<R> ? R(0) : __ldg(A.H + c.y);
+        k = kPert<R> ? -mul_rn(ld_stream(A.gdc + e), add_rn(h2, -h1))
+                     : -mul_rn(ld_stream(A.gdc + e), add_rn(add_rn(h2, -H2), -add_rn(h1, -H1)));
         for (int i = 0; i < n; ++i) {
             const R wu = mul_rn(ld_stream(A.wf + (size_t)i * nE + e), __ldg(A.uOld + ld_stream(A.eoe + (size_t)i * nE + e)));
             k = add_rn(k, FOLD ? wu : mul_rn(wu, A.f0));
@@ -329,7 +387,8 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
     const int cc = cBase + threadIdx.x;
     if (cc < A.nCown) {
         const int n = ld_stream(A.nEoC + cc);
-        const R hc = __ldg(A.hOld + cc);
+        // Float32: the arrays hold the perturbation h - H (see kPert); the flux needs the whole thickness
+        const R hc = kPert<R> ? add_rn(__ldg(A.hOld + cc), __ldg(A.H + cc)) : __ldg(A.hOld + cc);
         const R cur = (STAGE == 4) ? R(0) : A.hCur[cc];
         const R accIn = (STAGE == 1) ? R(0) : A.hAcc[cc];
         R acc = R(0);
@@ -350,7 +409,7 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
 #pragma unroll
             for (int i = 0; i < ST; ++i) {
                 const int other = cs[i].x == cc ? cs[i].y : cs[i].x;
-                const R ho = __ldg(A.hOld + other);
+                const R ho = kPert<R> ? add_rn(__ldg(A.hOld + other), __ldg(A.H + other)) : __ldg(A.hOld + other);
                 // flux = u*hEdge (DiagnosticVars.jl:158-173), hEdge = 0.5*(h1+h2) (Operators.jl:201-222),
                 // tend += flux*dv*sign*invArea (horizontal_advection.jl:64-65)
                 const R f = mul_rn(mul_rn(mul_rn(uu[i], mul_rn(R(0.5), add_rn(hc, ho))), dd[i]), invA);
@@ -363,7 +422,8 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
                 const int e = ex >> 1;
                 const int2 cs = __ldg(A.ce + e);
                 const int other = cs.x == cc ? cs.y : cs.x;
-                const R f = mul_rn(mul_rn(mul_rn(__ldg(A.uOld + e), mul_rn(R(0.5), add_rn(hc, __ldg(A.hOld + other)))), __ldg(A.dv + e)), invA);
+                const R ho = kPert<R> ? add_rn(__ldg(A.hOld + other), __ldg(A.H + other)) : __ldg(A.hOld + other);
+                const R f = mul_rn(mul_rn(mul_rn(__ldg(A.uOld + e), mul_rn(R(0.5), add_rn(hc, ho))), __ldg(A.dv + e)), invA);
                 acc = add_rn(acc, (ex & 1) ? f : -f);
             }
         }
@@ -589,9 +649,10 @@ k_cells(int which, int64_t nC, const R *__restrict__ h, const R *__restrict__ H,
 {
     double s = 0.0;
     for (int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x; c < nC; c += (int64_t)kBlocks * kThreads) {
-        const double ssh = (double)(h[c] - H[c]);
+        const double ssh = fused::kPert<R> ? (double)h[c] : (double)(h[c] - H[c]);
+        const double htot = fused::kPert<R> ? (double)H[c] + (double)h[c] : (double)h[c];
         if (which == 0) s += ssh * ssh;
-        else if (which == 1) s += area[c] * (double)h[c];
+        else if (which == 1) s += area[c] * htot;
         else s += area[c] * (0.5 * 9.80616) * ssh * ssh;
     }
     s = block_sum(s);
@@ -602,12 +663,14 @@ k_cells(int which, int64_t nC, const R *__restrict__ h, const R *__restrict__ H,
 template <class R>
 __global__ void __launch_bounds__(kThreads)
 k_edges_ke(int64_t nE, const int2 *__restrict__ ce, const double *__restrict__ dc, const double *__restrict__ dv,
-           const R *__restrict__ u, const R *__restrict__ h, double *__restrict__ partial)
+           const R *__restrict__ u, const R *__restrict__ h, const R *__restrict__ H, double *__restrict__ partial)
 {
     double s = 0.0;
     for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < nE; e += (int64_t)kBlocks * kThreads) {
         const int2 c = ce[e];
-        const double he = 0.5 * ((double)h[c.x] + (double)h[c.y]), ue = (double)u[e];
+        double he = 0.5 * ((double)h[c.x] + (double)h[c.y]);
+        if (fused::kPert<R>) he += 0.5 * ((double)H[c.x] + (double)H[c.y]);
+        const double ue = (double)u[e];
         s += 0.5 * dc[e] * dv[e] * he * ue * ue;
     }
     s = block_sum(s);

@@ -103,7 +103,7 @@ k_halo_wait(int nsend, const int32_t *senders, const unsigned long long *arrival
 #ifndef MOKAB_SIM
     const long long t0 = clock64();
     while (!sender_ready(arrival, expect, q)) {
-        if (clock64() - t0 > timeout_cycles) {       // a peer died or the schedules diverged: never hang the GPU
+        if (*(volatile int *)error || clock64() - t0 > timeout_cycles) {       // a peer died or the schedules diverged: never hang the GPU
             atomicExch(error, 1);
             break;
         }
@@ -125,7 +125,7 @@ k_halo_wait_arrivals(int nsend, const int32_t *senders, const unsigned long long
     const int q = senders[i];
     const long long t0 = clock64();
     while (load_acquire_system(arrival + q) < expect[q]) {
-        if (clock64() - t0 > timeout_cycles) {
+        if (*(volatile int *)error || clock64() - t0 > timeout_cycles) {
             atomicExch(error, 1);
             break;
         }

@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256)
 k_update_ssh(int64_t n, const R *__restrict__ h, const R *__restrict__ H, R *__restrict__ ssh)
 {
     const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (j < n) ssh[j] = h[j] - H[j];
+    if (j < n) ssh[j] = sizeof(R) == 4 ? h[j] : h[j] - H[j];   // Float32 `h` arrays hold h - H already (kernels_fused.cuh: kPert)
 }
 
 // caller order -> device order (dst[new] = src[perm[new]]) and back
@@ -168,6 +168,20 @@ k_permute_out(int64_t n, const int32_t *__restrict__ perm, const R *__restrict__
 {
     const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (j < n) dst[perm[j]] = src[j];
+}
+
+// Float32 states: layerThickness crosses the boundary as the whole thickness, the device arrays hold h - H (kernels_fused.cuh: kPert)
+__global__ void __launch_bounds__(256)
+k_permute_in_pert(int64_t n, const int32_t *__restrict__ perm, const float *__restrict__ src, const double *__restrict__ H, float *__restrict__ dst)
+{
+    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (j < n) dst[j] = (float)((double)src[perm[j]] - H[j]);
+}
+__global__ void __launch_bounds__(256)
+k_permute_out_pert(int64_t n, const int32_t *__restrict__ perm, const float *__restrict__ src, const double *__restrict__ H, float *__restrict__ dst)
+{
+    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (j < n) dst[perm[j]] = (float)(H[j] + (double)src[j]);
 }
 
 template <class T, class U>

@@ -230,7 +230,9 @@ static void build_host_mesh(const mokab_mesh_desc &d, uint32_t flags, HostMesh &
         for (int i = 0; i < n; ++i) {
             int32_t x = d.edgesOnEdge[(int64_t)S2f * eo + i];
             m.eoe[(size_t)i * nE + en] = x ? invE[x - 1] : -1;  // 0 entries are skipped (coriolis kernel :67)
-            m.woe[(size_t)i * nE + en] = bnd ? 0.0 : d.weightsOnEdge[(int64_t)S2f * eo + i];
+            // absent slots (0 entries) carry weight 0 like the padding: every kernel -- fused ForwardEuler reads the raw weights
+            // with the padded index rows -- then agrees with the reference kernel, which skips them (coriolis kernel :67)
+            m.woe[(size_t)i * nE + en] = (bnd || x == 0) ? 0.0 : d.weightsOnEdge[(int64_t)S2f * eo + i];
         }
     }
     m.f0 = m.fE[0];

@@ -5,6 +5,7 @@
 #include "kernels_ref.cuh"
 #include "kernels_p2p.cuh"
 #include "mesh.cuh"
+#include "comm.cuh"
 
 #include <unistd.h>
 
@@ -39,6 +40,7 @@ struct StateT {
     cudaGraphExec_t gStep[2] = {nullptr, nullptr};
     cudaGraphExec_t gPair[2] = {nullptr, nullptr};
     double graph_dt = 0.0;
+    int64_t graph_epoch = -1;              // options().epoch the graphs were captured under
     bool graphs_ready = false;
     // asynchronous host transfers (mokab_state_set_async / _get_async): rings of staging slots, one copy
     // stream per direction, events ordering copy <-> permute kernels
@@ -119,8 +121,32 @@ struct mokab_state {
         mokab::DevBuf<uint8_t> slotE, slotC;
         mokab::DevBuf<unsigned char> stageDesc;              // 4 x fused::PushStage<R>
     } p2p;
+    // domain-decomposed stepping inside the library (csrc/decomposed.cuh); set up by mokab_decomp_setup
+    struct Decomp {
+        bool ready = false;
+        mokab_comm *comm = nullptr;
+        int mode = MOKAB_HALO_NCCL;
+        uint32_t flags = 0;
+        std::vector<int64_t> scnt, rcnt;                     // halo elements sent to / received from every rank
+        mokab::DevBuf<unsigned char> sendBuf, recvBuf;       // packed messages (state dtype)
+        cudaStream_t halo = nullptr;                         // high-priority stream: boundary blocks + the exchange
+        std::vector<cudaEvent_t> events;
+        cudaGraphExec_t graph[2][2][2] = {};                 // [RungeKutta4 | ForwardEuler][time-level parity][one | two steps]
+        int64_t graph_launches[2][2] = {};
+        double graph_dt[2] = {0.0, 0.0};
+        int64_t graph_epoch[2] = {-1, -1};
+        bool graphs_ready[2] = {false, false};
+        bool overlap() const { return !(flags & MOKAB_DECOMP_NO_OVERLAP); }
+        bool use_graph() const { return !(flags & MOKAB_DECOMP_NO_GRAPH); }
+    } dec;
     ~mokab_state()
     {
+        for (int k = 0; k < 2; ++k)
+            for (int p = 0; p < 2; ++p)
+                for (int n = 0; n < 2; ++n)
+                    if (dec.graph[k][p][n]) cudaGraphExecDestroy(dec.graph[k][p][n]);
+        for (cudaEvent_t e : dec.events) cudaEventDestroy(e);
+        if (dec.halo) cudaStreamDestroy(dec.halo);
         for (void *q : p2p.opened) cudaIpcCloseMemHandle(q);
         delete d;
         delete f;
@@ -230,7 +256,9 @@ static void alloc_state(mokab_state *st)
     MOKAB_CUDA(cudaStreamSynchronize(s));
 }
 
-struct FieldRef { void *p; int64_t n; const int32_t *perm; bool prognostic_end; int prev_of; };
+// pert: a Float32 layerThickness -- the caller sees the whole thickness, the device array holds h - H (kernels_fused.cuh: kPert);
+// alias: Float32 ssh -- the same perturbation is the prognostic variable of the fused path, a `set` also writes it there
+struct FieldRef { void *p; int64_t n; const int32_t *perm; bool prognostic_end; int prev_of; bool pert = false; void *alias = nullptr; };
 
 // shadow state d_Prog (ocn_init_shadows, reference src/forward/init.jl:32-40): zeros
 template <class R>
@@ -256,13 +284,14 @@ static FieldRef field_ref(mokab_state *st, int field)
     StateT<R> *t = typed<R>(st);
     const mokab_mesh *m = st->mesh;
     const int c = st->cur, o = 1 - st->cur;
+    constexpr bool P = fused::kPert<R>;
     switch (field) {
-    case MOKAB_SSH: return {t->ssh[c].p, m->nC, m->dPermC.p, true, field};
+    case MOKAB_SSH: return {t->ssh[c].p, m->nC, m->dPermC.p, true, field, false, P ? t->h[c].p : nullptr};
     case MOKAB_NORMAL_VELOCITY: return {t->u[c].p, m->nE, m->dPermE.p, true, field};
-    case MOKAB_LAYER_THICKNESS: return {t->h[c].p, m->nC, m->dPermC.p, true, field};
-    case MOKAB_SSH_PREV: return {t->ssh[o].p, m->nC, m->dPermC.p, false, 0};
+    case MOKAB_LAYER_THICKNESS: return {t->h[c].p, m->nC, m->dPermC.p, true, field, P};
+    case MOKAB_SSH_PREV: return {t->ssh[o].p, m->nC, m->dPermC.p, false, 0, false, P ? t->h[o].p : nullptr};
     case MOKAB_NORMAL_VELOCITY_PREV: return {t->u[o].p, m->nE, m->dPermE.p, false, 0};
-    case MOKAB_LAYER_THICKNESS_PREV: return {t->h[o].p, m->nC, m->dPermC.p, false, 0};
+    case MOKAB_LAYER_THICKNESS_PREV: return {t->h[o].p, m->nC, m->dPermC.p, false, 0, P};
     case MOKAB_LAYER_THICKNESS_EDGE: return {t->hEdge.p, m->nE, m->dPermE.p, false, 0};
     case MOKAB_THICKNESS_FLUX: return {t->flux.p, m->nE, m->dPermE.p, false, 0};
     case MOKAB_VELOCITY_DIV_CELL: return {t->divC.p, m->nC, m->dPermC.p, false, 0};
@@ -276,6 +305,33 @@ static FieldRef field_ref(mokab_state *st, int field)
     }
 }
 
+// caller order -> device order into `f` (and its alias) from the staging buffer `src`; device order -> caller order into `dst`
+template <class R>
+static void launch_permute_in(mokab_state *st, const FieldRef &f, const R *src)
+{
+    mokab_ctx *ctx = st->ctx;
+    if constexpr (fused::kPert<R>) {
+        if (f.pert) {
+            LAUNCH(ctx, k_permute_in_pert, nblk(f.n), 256, f.n, f.perm, src, (const double *)st->mesh->H.p, (float *)f.p);
+            return;
+        }
+    }
+    LAUNCH(ctx, k_permute_in<R>, nblk(f.n), 256, f.n, f.perm, src, (R *)f.p);
+    if (f.alias) MOKAB_CUDA(cudaMemcpyAsync(f.alias, f.p, f.n * sizeof(R), cudaMemcpyDeviceToDevice, ctx->stream));
+}
+template <class R>
+static void launch_permute_out(mokab_state *st, const FieldRef &f, R *dst)
+{
+    mokab_ctx *ctx = st->ctx;
+    if constexpr (fused::kPert<R>) {
+        if (f.pert) {
+            LAUNCH(ctx, k_permute_out_pert, nblk(f.n), 256, f.n, f.perm, (const float *)f.p, (const double *)st->mesh->H.p, dst);
+            return;
+        }
+    }
+    LAUNCH(ctx, k_permute_out<R>, nblk(f.n), 256, f.n, f.perm, (const R *)f.p, dst);
+}
+
 template <class R>
 static void state_set(mokab_state *st, int field, const void *host)
 {
@@ -284,10 +340,11 @@ static void state_set(mokab_state *st, int field, const void *host)
     FieldRef f = field_ref<R>(st, field);
     if (f.n == 0) return;
     MOKAB_CUDA(cudaMemcpyAsync(t->staging.p, host, f.n * sizeof(R), cudaMemcpyHostToDevice, ctx->stream));
-    LAUNCH(ctx, k_permute_in<R>, nblk(f.n), 256, f.n, f.perm, (const R *)t->staging.p, (R *)f.p);
+    launch_permute_in<R>(st, f, (const R *)t->staging.p);
     if (f.prognostic_end) {  // deepcopy into every time level, PrognosticVars.jl:49-53
         FieldRef prev = field_ref<R>(st, field + 3);
         MOKAB_CUDA(cudaMemcpyAsync(prev.p, f.p, f.n * sizeof(R), cudaMemcpyDeviceToDevice, ctx->stream));
+        if (prev.alias) MOKAB_CUDA(cudaMemcpyAsync(prev.alias, f.p, f.n * sizeof(R), cudaMemcpyDeviceToDevice, ctx->stream));
     }
     MOKAB_CUDA(cudaStreamSynchronize(ctx->stream));  // the caller may reuse `host` immediately
 }
@@ -299,7 +356,7 @@ static void state_get(mokab_state *st, int field, void *host)
     StateT<R> *t = typed<R>(st);
     FieldRef f = field_ref<R>(st, field);
     if (f.n == 0) return;
-    LAUNCH(ctx, k_permute_out<R>, nblk(f.n), 256, f.n, f.perm, (const R *)f.p, (R *)t->staging.p);
+    launch_permute_out<R>(st, f, (R *)t->staging.p);
     MOKAB_CUDA(cudaMemcpyAsync(host, t->staging.p, f.n * sizeof(R), cudaMemcpyDeviceToHost, ctx->stream));
     MOKAB_CUDA(cudaStreamSynchronize(ctx->stream));
 }
@@ -345,7 +402,7 @@ static void state_set_async(mokab_state *st, int field, const void *host)
     MOKAB_CUDA(cudaMemcpyAsync(t->stIn[slot].p, host, f.n * sizeof(R), cudaMemcpyHostToDevice, t->h2d));
     MOKAB_CUDA(cudaEventRecord(t->evInCopied[slot], t->h2d));
     MOKAB_CUDA(cudaStreamWaitEvent(ctx->stream, t->evInCopied[slot], 0));
-    LAUNCH(ctx, k_permute_in<R>, nblk(f.n), 256, f.n, f.perm, (const R *)t->stIn[slot].p, (R *)f.p);
+    launch_permute_in<R>(st, f, (const R *)t->stIn[slot].p);
     MOKAB_CUDA(cudaEventRecord(t->evInFree[slot], ctx->stream));
 }
 
@@ -360,7 +417,7 @@ static void state_get_async(mokab_state *st, int field, void *host)
     const int slot = t->outSlot;
     t->outSlot = (slot + 1) % StateT<R>::kOutSlots;
     MOKAB_CUDA(cudaStreamWaitEvent(ctx->stream, t->evOutCopied[slot], 0));  // the slot's previous D2H has left
-    LAUNCH(ctx, k_permute_out<R>, nblk(f.n), 256, f.n, f.perm, (const R *)f.p, (R *)t->stOut[slot].p);
+    launch_permute_out<R>(st, f, (R *)t->stOut[slot].p);
     MOKAB_CUDA(cudaEventRecord(t->evOutReady[slot], ctx->stream));
     MOKAB_CUDA(cudaStreamWaitEvent(t->d2h, t->evOutReady[slot], 0));
     MOKAB_CUDA(cudaMemcpyAsync(host, t->stOut[slot].p, f.n * sizeof(R), cudaMemcpyDeviceToHost, t->d2h));
@@ -473,6 +530,15 @@ static void fe_materialize(mokab_state *st)
     MOKAB_CUDA(cudaMemcpyAsync(t->hEdge.p, t->hE[p].p, m->nE * 8, cudaMemcpyDeviceToDevice, ctx->stream));
 }
 
+// A staged RungeKutta4 call (or anything else that runs on a caller's stream) after fused / staged ForwardEuler steps: the
+// Diag / Tend arrays those steps left to be re-created are re-created first, and complete before the caller's stream goes on.
+static void leave_forward_euler(mokab_state *st)
+{
+    if (!st->fe_lazy) return;
+    fe_materialize(st);
+    MOKAB_CUDA(cudaStreamSynchronize(st->ctx->stream));
+}
+
 // Record what the adjoint of a ForwardEuler step needs of its input: u and the LAGGED layerThicknessEdge (`hE_lagged`).
 static void fe_tape_record(mokab_state *st, double dt, const double *u, const double *hE_lagged)
 {
@@ -523,6 +589,18 @@ static void run_fe_fused(mokab_state *st, double dt, int64_t nsteps)
     st->fe_lazy = true;
 }
 
+// before the first staged ForwardEuler launch of a state (never inside a stream capture: it allocates and synchronises)
+static void run_fe_stage_prepare(mokab_state *st)
+{
+    mokab_ctx *ctx = st->ctx; const mokab_mesh *m = st->mesh; StateT<double> *t = st->d;
+    if (t->hE[0].n == 0) { t->hE[0].alloc(m->nE); t->hE[1].alloc(m->nE); }
+    if (!st->fe_lazy) {       // first staged step: the canonical layerThicknessEdge is what the first flux uses
+        MOKAB_CUDA(cudaMemcpyAsync(t->hE[st->cur].p, t->hEdge.p, m->nE * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        MOKAB_CUDA(cudaStreamSynchronize(ctx->stream));          // the launches that follow may be on other streams
+        st->fe_lazy = true;
+    }
+}
+
 // One ForwardEuler step of a domain-decomposed run, staged like mokab_rk4_stage: the selected blocks read time level cur and
 // write level 1 - cur for their OWNED cells and edges (u, h, ssh and the layerThicknessEdge of the state they read, which the
 // next step's flux uses -- the reference's lag, DiagnosticVars.jl:108-117).  The caller then exchanges the halo copies of all
@@ -538,12 +616,7 @@ static void run_fe_stage(mokab_state *st, double dt, int part, cudaStream_t stre
     ensure_fused<double>(m);
     FusedMesh<double> &fm = fused_of<double>(m);
     cudaStream_t s = stream ? stream : ctx->stream;
-    if (t->hE[0].n == 0) { t->hE[0].alloc(m->nE); t->hE[1].alloc(m->nE); }
-    if (!st->fe_lazy) {       // first staged step: the canonical layerThicknessEdge is what the first flux uses
-        MOKAB_CUDA(cudaMemcpyAsync(t->hE[st->cur].p, t->hEdge.p, m->nE * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-        MOKAB_CUDA(cudaStreamSynchronize(ctx->stream));          // the launches below may be on other streams
-        st->fe_lazy = true;
-    }
+    run_fe_stage_prepare(st);
     int grid = m->fusedBlocks;
     fused::FeArgs A;
     A.blockList = nullptr;
@@ -605,11 +678,28 @@ static void step_rk4_unfused(mokab_state *st, double dt)
 static int p2p_target(const mokab_state *st, int stage);
 // MOKAB_STAGE_TMA=1|2 selects a TMA variant of the fused stage kernel on hexagon meshes (not yet measured on hardware)
 // (1: the slot-major rows, ten bulk copies per block; 2: a block-major copy of the weights, one bulk copy per block)
-static int stage_tma_mode()
-{
-    static const int mode = [] { const char *e = getenv("MOKAB_STAGE_TMA"); return e && (e[0] == '1' || e[0] == '2') ? e[0] - '0' : 0; }();
-    return mode;
-}
+// ---- tuning options (mokab_set_option; process-wide; the environment gives the initial values) ---------------------------------
+// Captured graphs bake the options into their kernel arguments: every change bumps `epoch` and the graphs are rebuilt on next use.
+struct Options {
+    int stage_tma = 0;            // MOKAB_STAGE_TMA: 1 / 2 = the bulk-copy variants of the stage kernel (kernels_fused.cuh)
+    int stage_prefetch = 0;       // MOKAB_STAGE_PREFETCH: bit 0 = a block prefetches the streams of its own later edge iterations and of
+                                  // its cell phase into L2 at entry; bit 1 = it prefetches the streams of the block launched
+                                  // `stage_prefetch_distance` blocks after it
+    int stage_prefetch_distance = 0;   // MOKAB_STAGE_PREFETCH_DISTANCE: 0 = one wave of resident blocks (SMs x blocks per SM)
+    int test_drop_dependency = 0; // TEST HOOK (tests/sim: does the checker have teeth?): 1 / 2 = leave out one of the two cross-stream
+                                  // waits of the decomposed RK4 schedule (interior after boundary / boundary after interior)
+    int64_t epoch = 0;
+    Options()
+    {
+        auto geti = [](const char *n, int d) { const char *e = getenv(n); return e && *e ? atoi(e) : d; };
+        stage_tma = geti("MOKAB_STAGE_TMA", 0);
+        if (stage_tma < 0 || stage_tma > 2) stage_tma = 0;
+        stage_prefetch = geti("MOKAB_STAGE_PREFETCH", 0) & 3;
+        stage_prefetch_distance = std::max(0, geti("MOKAB_STAGE_PREFETCH_DISTANCE", 0));
+    }
+};
+static Options &options() { static Options o; return o; }
+static int stage_tma_mode() { return options().stage_tma; }
 static bool stage_tma_enabled() { return stage_tma_mode() != 0; }
 #ifdef MOKAB_SIM
 static void p2p_gate_sim(mokab_state *st, cudaStream_t s);
@@ -620,7 +710,7 @@ static void p2p_gate_sim(mokab_state *st, cudaStream_t s);
 template <class R>
 static void stage_tma_prepare()
 {
-    static bool done = false;
+    static bool done = false;     // (per precision: one static per instantiation)
     if (done || !stage_tma_enabled()) return;
 #define MOKAB_TMA_ATTR(STAGE, FOLD, DER)                                                                                                          \
     MOKAB_CUDA(cudaFuncSetAttribute(fused::k_rk_stage<R, STAGE, 10, 6, FOLD, DER, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024)); \
@@ -742,6 +832,9 @@ static fused::StageArgs<R> stage_args(mokab_state *st, double dt, int p, int sta
     A.f0 = (R)m->f0;
     A.push = nullptr;
     A.wStride = 0; A.wfB = nullptr; A.wfBOff = nullptr;
+    A.pf = options().stage_prefetch;
+    A.pfDist = options().stage_prefetch_distance > 0 ? options().stage_prefetch_distance
+                                                       : st->ctx->num_sms * (sizeof(R) == 8 ? 4 : 5);
     switch (stage) {
     case 1: A.uOld = t->u[p].p;  A.hOld = t->h[p].p;  A.uOut = t->uP[0].p; A.hOut = t->hP[0].p; break;  // provisional == current
     case 2: A.uOld = t->uP[0].p; A.hOld = t->hP[0].p; A.uOut = t->uP[1].p; A.hOut = t->hP[1].p; break;
@@ -854,6 +947,7 @@ static void build_graphs(mokab_state *st, double dt)
         }
     ctx->launches = saved;  // capture enqueues are not executions
     t->graph_dt = dt;
+    t->graph_epoch = options().epoch;
     t->graphs_ready = true;
 }
 
@@ -887,6 +981,7 @@ static void run_rk4_fused(mokab_state *st, double dt, int64_t nsteps)
         MOKAB_REQUIRE((int64_t)t->tapeDt.size() + nsteps <= t->tapeCap, "timestep_rk4: the tape is full (mokab_tape_begin max_steps)");
         MOKAB_REQUIRE(t->tapeKind != 2, "timestep_rk4: the tape already holds ForwardEuler steps");
         t->tapeKind = 1;                    // (also a call with nsteps = 0: the seed then follows this stepper's state definition)
+        if (nsteps > 0 && t->tapeH.n < (size_t)t->tapeCap * m->nC) t->tapeH.alloc((size_t)t->tapeCap * m->nC);
         for (int64_t i = 0; i < nsteps; ++i) {
             const size_t k = t->tapeDt.size();
             MOKAB_CUDA(cudaMemcpyAsync(t->tapeU.p + k * m->nE, t->u[st->cur].p, m->nE * sizeof(R), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -898,7 +993,7 @@ static void run_rk4_fused(mokab_state *st, double dt, int64_t nsteps)
         if (nsteps > 0) refresh_ssh<R>(st);
         return;
     }
-    if (!t->graphs_ready || t->graph_dt != dt) build_graphs<R>(st, dt);
+    if (!t->graphs_ready || t->graph_dt != dt || t->graph_epoch != options().epoch) build_graphs<R>(st, dt);
     int64_t left = nsteps;
     while (left >= 2) {
         MOKAB_CUDA(cudaGraphLaunch(t->gPair[st->cur], ctx->stream));
@@ -926,7 +1021,7 @@ static void do_reduce(mokab_state *st, int which, double *out)
            (const double *)m->area.p, t->partial.p);
     if (which == MOKAB_SUM_ENERGY)
         LAUNCH(ctx, reduce::k_edges_ke<R>, reduce::kBlocks, reduce::kThreads, m->nEo, (const int2 *)m->ce.p, (const double *)m->dc.p,
-               (const double *)m->dv.p, (const R *)t->u[c].p, (const R *)t->h[c].p, t->partial.p);
+               (const double *)m->dv.p, (const R *)t->u[c].p, (const R *)t->h[c].p, (const R *)fm.H.p, t->partial.p);
     LAUNCH(ctx, reduce::k_final, 1, reduce::kThreads, (const double *)t->partial.p, t->result.p);
     MOKAB_CUDA(cudaMemcpyAsync(out, t->result.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     MOKAB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1039,7 +1134,7 @@ static void adjoint_step(mokab_state *st, int64_t k)
     B.nE = (int)m->nE; B.nC = (int)m->nC; B.nCown = (int)m->nCo; B.S2T = m->S2T; B.S = m->S;
     B.ce = m->ce.p; B.eoeT = m->eoeT.p; B.eoc = m->eocF.p; B.nEoET = m->nEoET.p; B.nEoC = m->nEoC.p;
     B.blkEdgeStart = m->blkEdgeStart.p;
-    B.gdc = fm.gdc.p; B.wfT = fm.wfT.p; B.dv = fm.dv.p; B.invArea = fm.invArea.p;
+    B.gdc = fm.gdc.p; B.wfT = fm.wfT.p; B.dv = fm.dv.p; B.invArea = fm.invArea.p; B.H = fm.H.p;
     const int p = t->lamCur;
     B.lamU = t->lamU[p].p; B.lamH = t->lamH[p].p; B.accU = t->lamU[1 - p].p; B.accH = t->lamH[1 - p].p;
     B.bThis = (R)b[3];
@@ -1076,7 +1171,8 @@ static void tape_begin(mokab_state *st, int64_t max_steps)
     const mokab_mesh *m = st->mesh;
     if (t->tapeCap < max_steps) {
         t->tapeU.alloc((size_t)max_steps * m->nE);
-        t->tapeH.alloc((size_t)max_steps * m->nC);
+        t->tapeH.release();                 // RungeKutta4 tapes only: allocated by the first recorded RK4 step (run_rk4_fused)
+        t->tapeE.release();                 // ForwardEuler tapes only: allocated by fe_tape_record
         t->tapeCap = max_steps;
     }
     t->tapeDt.clear();
@@ -1166,6 +1262,19 @@ struct P2PBlob {
     uint64_t off[9];                  // u0 u1 uP0 uP1 h0 h1 hP0 hP1 arrival counters
     cudaIpcMemHandle_t handle;
 };
+
+// How long a halo wait spins before it gives up and raises the state's error flag (MOKAB_P2P_TIMEOUT_S, default 20 s -- long
+// enough for rank skew from lazy module loading, graph instantiation or host I/O; a wait that finds the flag already raised
+// does not spin at all, so after one time-out the remaining launches of the call drain quickly).
+static long long p2p_timeout_cycles()
+{
+    static const long long cycles = [] {
+        const char *e = getenv("MOKAB_P2P_TIMEOUT_S");
+        const double s = e && *e ? atof(e) : 20.0;
+        return (long long)(std::max(0.001, s) * 1.9e9);
+    }();
+    return cycles;
+}
 
 template <class R>
 static void p2p_export(mokab_state *st, P2PBlob *b)
@@ -1270,7 +1379,7 @@ static void p2p_setup(mokab_state *st, int rank, int nranks, const P2PBlob *blob
             P.peerU = (R *const *)x.peerU.p + (size_t)tgt * nrecv; P.peerH = (R *const *)x.peerH.p + (size_t)tgt * nrecv;
             P.arrivalAt = (unsigned long long *const *)x.arrivalAt.p; P.nrecv = nrecv;
             P.senders = x.senders.p; P.nsend = nsend; P.arrival = x.arrival; P.expect = x.expect.p;
-            P.done = x.done.p; P.error = x.error.p; P.timeout_cycles = 4000000000ll;
+            P.done = x.done.p; P.error = x.error.p; P.timeout_cycles = p2p_timeout_cycles();
             memcpy(desc.data() + tgt * sizeof(P), &P, sizeof(P));
         }
         x.stageDesc.upload(desc, ctx->stream);
@@ -1343,7 +1452,7 @@ static void p2p_wait_arrivals(mokab_state *st, cudaStream_t stream)
     p2p_gate_sim(st, s);
 #else
     p2p::k_halo_wait_arrivals<<<1, p2p::kMaxPeers, 0, s>>>(nsend, (const int32_t *)x.senders.p, (const unsigned long long *)x.arrival,
-                                                            (const unsigned long long *)x.expect.p, x.error.p, 4000000000ll);
+                                                            (const unsigned long long *)x.expect.p, x.error.p, p2p_timeout_cycles());
     MOKAB_CUDA(cudaGetLastError());
 #endif
     ctx->launches++;
@@ -1370,7 +1479,7 @@ static void p2p_wait(mokab_state *st, cudaStream_t stream)
     });
 #else
     p2p::k_halo_wait<<<1, p2p::kMaxPeers, 0, s>>>(nsend, (const int32_t *)x.senders.p, (const unsigned long long *)x.arrival,
-                                                   x.expect.p, x.error.p, 4000000000ll);
+                                                   x.expect.p, x.error.p, p2p_timeout_cycles());
     MOKAB_CUDA(cudaGetLastError());
 #endif
     ctx->launches++;
@@ -1779,11 +1888,14 @@ int mokab_timestep_forward_euler(mokab_state *state, double dt, int64_t nsteps)
         MOKAB_REQUIRE(nsteps >= 0, "timestep_forward_euler: nsteps must be >= 0");
         require_f64(state, "timestep_forward_euler");
         MOKAB_REQUIRE(state->mesh->nCo == state->mesh->nC && state->mesh->nEo == state->mesh->nE,
-                      "timestep_forward_euler: this mesh has halo entities and ForwardEuler has no staged form; domain-decomposed runs "
-                      "step with mokab_rk4_stage + the halo exchange");
+                      "timestep_forward_euler: this mesh has halo entities; domain-decomposed runs step with "
+                      "mokab_timestep_forward_euler_decomposed (or mokab_forward_euler_stage + the halo exchange)");
         state->ctx->bind();
         if (state->d->taping) {             // also a call with nsteps = 0: ssh is an input of its own for this stepper's seed
             MOKAB_REQUIRE(state->d->tapeKind != 1, "timestep_forward_euler: the tape already holds RungeKutta4 steps");
+            // checked before the first step runs: a call either records all of its steps or leaves the state untouched
+            MOKAB_REQUIRE((int64_t)state->d->tapeDt.size() + nsteps <= state->d->tapeCap,
+                          "timestep_forward_euler: the tape is full (mokab_tape_begin max_steps)");
             state->d->tapeKind = 2;
         }
         if (fe_fusable(state)) {
@@ -1804,7 +1916,7 @@ int mokab_timestep_forward_euler_unfused(mokab_state *state, double dt, int64_t 
         MOKAB_REQUIRE(nsteps >= 0, "timestep_forward_euler_unfused: nsteps must be >= 0");
         require_f64(state, "timestep_forward_euler_unfused");
         MOKAB_REQUIRE(state->mesh->nCo == state->mesh->nC && state->mesh->nEo == state->mesh->nE,
-                      "timestep_forward_euler_unfused: this mesh has halo entities and ForwardEuler has no staged form");
+                      "timestep_forward_euler_unfused: this mesh has halo entities; use mokab_timestep_forward_euler_decomposed");
         state->ctx->bind();
         fe_materialize(state);
         for (int64_t i = 0; i < nsteps; ++i) step_forward_euler(state, dt);
@@ -1963,6 +2075,7 @@ int mokab_rk4_stage(mokab_state *state, double dt, int stage, int part, void *cu
         MOKAB_REQUIRE(stage >= 1 && stage <= 4, "rk4_stage: stage must be 1..4");
         MOKAB_REQUIRE(part >= MOKAB_PART_ALL && part <= MOKAB_PART_BOUNDARY_PUSH, "rk4_stage: unknown part");
         state->ctx->bind();
+        leave_forward_euler(state);
         if (state->dtype == MOKAB_F64) run_stage<double>(state, dt, stage, part, (cudaStream_t)cuda_stream);
         else run_stage<float>(state, dt, stage, part, (cudaStream_t)cuda_stream);
     });
@@ -2002,6 +2115,7 @@ int mokab_refresh_ssh(mokab_state *state, void *cuda_stream)
     return guarded([&] {
         MOKAB_REQUIRE(state, "refresh_ssh: state is NULL");
         state->ctx->bind();
+        leave_forward_euler(state);
         if (state->dtype == MOKAB_F64) refresh_ssh<double>(state, (cudaStream_t)cuda_stream);
         else refresh_ssh<float>(state, (cudaStream_t)cuda_stream);
     });
@@ -2107,6 +2221,34 @@ int mokab_p2p_error(mokab_state *state, int *out)
     });
 }
 
+int mokab_set_option(const char *name, int64_t value)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(name, "set_option: name is NULL");
+        Options &o = options();
+        const std::string n(name);
+        if (n == "stage_tma") { MOKAB_REQUIRE(value >= 0 && value <= 2, "set_option: stage_tma must be 0, 1 or 2"); o.stage_tma = (int)value; }
+        else if (n == "stage_prefetch") { MOKAB_REQUIRE(value >= 0 && value <= 3, "set_option: stage_prefetch must be 0..3"); o.stage_prefetch = (int)value; }
+        else if (n == "stage_prefetch_distance") { MOKAB_REQUIRE(value >= 0 && value < (1 << 30), "set_option: bad stage_prefetch_distance"); o.stage_prefetch_distance = (int)value; }
+        else if (n == "test_drop_dependency") o.test_drop_dependency = (int)value;
+        else throw Error("set_option: unknown option '" + n + "'");
+        o.epoch++;
+    });
+}
+
+int mokab_get_option(const char *name, int64_t *value)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(name && value, "get_option: NULL argument");
+        const Options &o = options();
+        const std::string n(name);
+        if (n == "stage_tma") *value = o.stage_tma;
+        else if (n == "stage_prefetch") *value = o.stage_prefetch;
+        else if (n == "stage_prefetch_distance") *value = o.stage_prefetch_distance;
+        else throw Error("get_option: unknown option '" + n + "'");
+    });
+}
+
 int mokab_mesh_derived_blocks(const mokab_mesh *mesh, int64_t *blocks, int64_t *derived)
 {
     return guarded([&] {
@@ -2126,3 +2268,5 @@ int mokab_mesh_block_counts(const mokab_mesh *mesh, int64_t *interior, int64_t *
 }
 
 }  // extern "C"
+
+#include "decomposed.cuh"

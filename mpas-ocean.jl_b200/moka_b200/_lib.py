@@ -20,6 +20,9 @@ CELLS, EDGES, VERTICES = range(3)
 RK4_FUSED, RK4_UNFUSED = 0, 1
 PART_ALL, PART_INTERIOR, PART_BOUNDARY, PART_BOUNDARY_PUSH = 0, 1, 2, 3
 MESH_RENUMBER, MESH_EXPLICIT_EOE, MESH_KEEP_WIDTHS = 1, 2, 4
+HALO_NCCL, HALO_P2P, HALO_P2P_FUSED = 0, 1, 2
+DECOMP_NO_OVERLAP, DECOMP_NO_GRAPH = 1, 2
+COMM_ID_BYTES = 128
 
 _I32P, _F64P = C.POINTER(C.c_int32), C.POINTER(C.c_double)
 
@@ -63,6 +66,11 @@ SYMBOLS = [
     "mokab_refresh_ssh", "mokab_mesh_block_counts", "mokab_mesh_derived_blocks",
     "mokab_halo_recv_device_indices", "mokab_p2p_blob_size", "mokab_p2p_export", "mokab_p2p_setup", "mokab_halo_push",
     "mokab_halo_wait", "mokab_halo_wait_arrivals", "mokab_p2p_error", "mokab_p2p_close",
+    "mokab_set_option", "mokab_get_option",
+    "mokab_comm_get_unique_id", "mokab_comm_init", "mokab_comm_destroy", "mokab_comm_rank", "mokab_comm_barrier",
+    "mokab_comm_allreduce_f64", "mokab_comm_allgather_bytes", "mokab_decomp_setup", "mokab_decomp_set_flags",
+    "mokab_timestep_rk4_decomposed", "mokab_timestep_forward_euler_decomposed", "mokab_reduce_decomposed",
+    "mokab_decomp_synchronize", "mokab_decomp_close",
 ]
 
 
@@ -101,6 +109,13 @@ def bind(L):
         "mokab_halo_recv_device_indices": [vp, _I32P], "mokab_p2p_blob_size": [C.POINTER(i64)],
         "mokab_p2p_export": [vp, C.c_int, vp],
         "mokab_p2p_setup": [vp, C.c_int, C.c_int, vp, C.c_int, _I32P, C.POINTER(i64), _I32P, C.c_int, _I32P],
+        "mokab_comm_get_unique_id": [vp], "mokab_comm_init": [vp, vp, C.c_int, C.c_int, C.POINTER(vp)], "mokab_comm_destroy": [vp],
+        "mokab_comm_rank": [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)], "mokab_comm_barrier": [vp],
+        "mokab_comm_allreduce_f64": [vp, _F64P, i64, C.c_int], "mokab_comm_allgather_bytes": [vp, vp, i64, vp],
+        "mokab_decomp_setup": [vp, vp, C.POINTER(i64), C.POINTER(i64), C.c_int, C.c_uint32], "mokab_decomp_set_flags": [vp, C.c_uint32],
+        "mokab_timestep_rk4_decomposed": [vp, dbl, i64], "mokab_timestep_forward_euler_decomposed": [vp, dbl, i64],
+        "mokab_reduce_decomposed": [vp, C.c_int, C.POINTER(dbl)], "mokab_decomp_synchronize": [vp], "mokab_decomp_close": [vp],
+        "mokab_set_option": [C.c_char_p, i64], "mokab_get_option": [C.c_char_p, C.POINTER(i64)],
         "mokab_halo_push": [vp, C.c_int, vp], "mokab_halo_wait": [vp, vp], "mokab_halo_wait_arrivals": [vp, vp], "mokab_p2p_error": [vp, C.POINTER(C.c_int)], "mokab_p2p_close": [vp],
     }
     for name, args in sig.items():
@@ -123,6 +138,17 @@ def lib():
 def check(rc: int) -> None:
     if rc != 0:
         raise MokaError(lib().mokab_last_error().decode("utf-8", "replace"))
+
+
+def set_option(name: str, value: int) -> None:
+    """mokab_set_option: tuning switches of the fused stage kernel (include/moka_b200.h)."""
+    check(lib().mokab_set_option(name.encode(), int(value)))
+
+
+def get_option(name: str) -> int:
+    v = C.c_int64()
+    check(lib().mokab_get_option(name.encode(), C.byref(v)))
+    return v.value
 
 
 def fptr(a: np.ndarray):

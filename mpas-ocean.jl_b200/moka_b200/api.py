@@ -228,9 +228,11 @@ class PrognosticVars:
             raise MokaError("nTimeLevels must be <= 2" if nTimeLevels > 2 else "nTimeLevels must be 2")  # time_integration.jl:23
         self.dev = _DeviceState(mesh, dtype or et)
         self.mesh = mesh
-        self.dev.set(L.SSH, ssh)
-        self.dev.set(L.NORMAL_VELOCITY, normalVelocity)
+        # Float32 states carry ONE perturbation variable, ssh = layerThickness - restingThicknessSum (include/moka_b200.h):
+        # layerThickness first (a Float32 1000 m + 1 m has lost the wave's low bits), then ssh, which keeps them
         self.dev.set(L.LAYER_THICKNESS, layerThickness)
+        self.dev.set(L.NORMAL_VELOCITY, normalVelocity)
+        self.dev.set(L.SSH, ssh)
 
     def upload_async(self, normalVelocity=None, layerThickness=None, ssh=None) -> None:
         """Adapt.adapt(backend, host arrays) without stalling the device: pipelined H2D from page-locked arrays."""

@@ -1,17 +1,12 @@
-"""One process per GPU: domain-decomposed RK4 with the halo exchange overlapped with interior compute.
+"""One process per GPU: the host side of domain-decomposed runs.
 
-The reference has no multi-device path; this follows BASELINE.json's north_star:
-owned/halo cell and edge layers (partition.py), one packed message per neighbour and RK stage
-exchanged with NCCL over NVLink (`torch.distributed` is the plumbing), overlapped with the interior
-blocks of the same stage:
-
-    per stage s:   compute stream:  wait X[s-1] -> BOUNDARY blocks(s) -> record B[s] -> INTERIOR blocks(s)
-                   comm stream:     wait B[s] -> pack(s) -> all_to_all -> unpack(s) -> record X[s]
-
-BOUNDARY blocks are those whose stencils read a halo entity or that hold an entity a neighbour needs
-(mokab_halo_setup), so the message of stage s leaves while the bulk of stage s is still computing and
-is in place before stage s+1 touches the halo.  Reductions are per-rank partial sums over owned
-entities + all_reduce.
+The reference has no multi-device path; this follows BASELINE.json's north_star: owned / halo cell and
+edge layers (partition.py), one message per neighbour and RK stage over NVLink -- NCCL send/recv or direct stores into the
+neighbours' memory -- overlapped with the interior blocks of the same stage.  The exchange, the two streams, the events and
+the captured step graphs live INSIDE libmoka_b200.so (csrc/comm.cuh, csrc/decomposed.cuh: mokab_comm_init,
+mokab_decomp_setup, mokab_timestep_*_decomposed, mokab_reduce_decomposed); this module builds the local meshes, brings the
+ranks together (a 128-byte id from rank 0 to the others) and forwards calls.  torch.distributed appears only as that control
+plane (and as the transport of the CPU-only gloo tests, `HaloExchanger`).
 """
 from __future__ import annotations
 
@@ -27,7 +22,9 @@ from . import api, partition
 
 
 class HaloExchanger:
-    """Packed all-to-all of halo messages (works for NCCL/CUDA and gloo/CPU tensors)."""
+    """Packed all-to-all of halo messages over torch.distributed -- the transport of the CPU-only gloo tests
+    (tests/test_partition_cpu.py: numpy oracle as the per-rank compute).  The GPU path does not use it: its exchange is
+    comm::all_to_all inside the library."""
 
     def __init__(self, send_counts, recv_counts, dtype, device, group=None):
         import torch
@@ -57,335 +54,206 @@ class HaloExchanger:
 
 
 class TorchRuntime:
-    """What DecomposedModel needs from the device runtime and the process group: streams / events / graph capture
-    (`cuda`: torch.cuda), the halo all-to-all and two scalar reductions (torch.distributed, NCCL).  The simulation tests
-    (tests/sim) pass an object of the same shape backed by their host runtime, so the schedule below is exercised
-    under adversarial stream interleavings without a GPU."""
+    """The CONTROL plane of a torchrun job: who am I, and a way to hand rank 0's communicator id to the others (any
+    torch.distributed backend; gloo is enough).  The data plane -- halo messages, reductions, set-up exchanges -- is
+    NCCL inside libmoka_b200.so (csrc/comm.cuh).  tests/sim passes an object of the same shape for emulated ranks."""
 
-    def __init__(self, device_index: int, group=None, device=None):
+    def __init__(self, device_index: int = 0, group=None, device=None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist, self.group = torch, dist, group
-        self.cuda = torch.cuda
         self.dev = torch.device("cuda", device_index) if device is None else torch.device(device)   # "cpu": gloo tests of the host exchanges
-
-    def stream(self, priority: int = 0):
-        return self.torch.cuda.Stream(self.dev, priority=priority)
-
-    def exchanger(self, send_counts, recv_counts, npdtype):
-        tdt = self.torch.float64 if np.dtype(npdtype) == np.float64 else self.torch.float32
-        return HaloExchanger(send_counts, recv_counts, tdt, self.dev, self.group)
-
-    def all_reduce_min(self, value: int) -> int:
-        t = self.torch.tensor([int(value)], dtype=self.torch.int32, device=self.dev)
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN, group=self.group)
-        return int(t.item())
-
-    def all_reduce_sum(self, value: float) -> float:
-        t = self.torch.tensor([float(value)], dtype=self.torch.float64, device=self.dev)
-        self.dist.all_reduce(t, group=self.group)
-        return float(t.item())
 
     def rank_and_size(self):
         return self.dist.get_rank(self.group), self.dist.get_world_size(self.group)
 
-    def sum_arrays(self, a: np.ndarray) -> np.ndarray:
-        """Element-wise sum of a host array over the ranks (output gathering: every rank fills its owned entries of a zero array)."""
-        t = self.torch.from_numpy(np.ascontiguousarray(a, np.float64)).to(self.dev)
-        self.dist.all_reduce(t, group=self.group)
-        return t.cpu().numpy()
+    def broadcast_bytes(self, blob, src: int = 0) -> bytes:
+        box = [blob]
+        self.dist.broadcast_object_list(box, src=src, group=self.group)
+        return box[0]
 
-    # set-up traffic of the direct-store halo exchange (once per model; tiny)
-    def all_gather_bytes(self, blob: bytes) -> list:
-        n = self.dist.get_world_size(self.group)
-        mine = self.torch.frombuffer(bytearray(blob), dtype=self.torch.uint8).to(self.dev)
-        out = [self.torch.empty_like(mine) for _ in range(n)]
-        self.dist.all_gather(out, mine, group=self.group)
-        return [bytes(t.cpu().numpy().tobytes()) for t in out]
-
-    def all_to_all_int32(self, send: list, recv_counts: list) -> list:
-        """send[q]: int32 array for rank q; returns the arrays received from every rank (recv_counts[q] elements)."""
-        torch = self.torch
-        s = torch.from_numpy(np.concatenate([np.asarray(a, np.int32) for a in send] + [np.zeros(0, np.int32)])).to(self.dev)
-        r = torch.empty(int(sum(recv_counts)), dtype=torch.int32, device=self.dev)
-        self.dist.all_to_all_single(r, s, [int(c) for c in recv_counts], [int(np.asarray(a).size) for a in send], group=self.group)
-        r = r.cpu().numpy()
-        offs = np.concatenate([[0], np.cumsum(recv_counts)]).astype(np.int64)
-        return [r[offs[q]:offs[q + 1]].copy() for q in range(len(recv_counts))]
+    # host-side exchanges of the gloo tests (tests/test_partition_cpu.py); the GPU path does these inside the library
+    def exchanger(self, send_counts, recv_counts, npdtype):
+        tdt = self.torch.float64 if np.dtype(npdtype) == np.float64 else self.torch.float32
+        return HaloExchanger(send_counts, recv_counts, tdt, self.dev, self.group)
 
 
-def plan_steps(nsteps: int, parity: int, graph_parity: int):
-    """How `nsteps` steps are issued when a 2-step graph captured at time-level parity `graph_parity` exists and the
-    state currently has parity `parity` (steps taken so far mod 2): (stream-launched steps first, graph replays,
-    stream-launched steps after).  The graph's kernels have the time-level buffers of its capture parity baked in, so
-    it may only be replayed from that parity."""
-    pre = 1 if (parity & 1) != (graph_parity & 1) and nsteps >= 1 else 0
-    rest = nsteps - pre
-    return pre, rest // 2, rest % 2
+class StoreRuntime:
+    """The same control plane without a process group: a torch.distributed TCPStore carries the 128-byte id (torchrun's
+    MASTER_ADDR / MASTER_PORT + 1 by default).  What the Julia shim does with MPI.jl or a shared file."""
+
+    def __init__(self, rank: int, world: int, host: str | None = None, port: int | None = None):
+        import torch.distributed as dist
+        self.rank, self.world = rank, world
+        host = host or os.environ.get("MASTER_ADDR", "127.0.0.1")
+        port = port or int(os.environ.get("MASTER_PORT", "29500")) + 1
+        self.store = dist.TCPStore(host, port, world, is_master=(rank == 0))
+        self._n = 0
+
+    def rank_and_size(self):
+        return self.rank, self.world
+
+    def broadcast_bytes(self, blob, src: int = 0) -> bytes:
+        key = f"mokab_bcast_{self._n}"
+        self._n += 1
+        if self.rank == src:
+            self.store.set(key, bytes(blob))
+        return bytes(self.store.get(key))
+
+
+class Communicator:
+    """mokab_comm: the NCCL communicator of the ranks, inside the library.  Rank 0 draws the unique id, `runtime` hands it to
+    the others, every rank joins (collective)."""
+
+    def __init__(self, backend: api.B200, runtime):
+        lib = L.lib()
+        self.backend, self.rt = backend, runtime
+        self.rank, self.nranks = runtime.rank_and_size()
+        blob = None
+        if self.rank == 0:
+            buf = C.create_string_buffer(L.COMM_ID_BYTES)
+            L.check(lib.mokab_comm_get_unique_id(buf))
+            blob = buf.raw
+        blob = runtime.broadcast_bytes(blob, 0)
+        h = C.c_void_p()
+        L.check(lib.mokab_comm_init(backend.handle, blob, self.rank, self.nranks, C.byref(h)))
+        self.handle = h
+
+    def barrier(self) -> None:
+        L.check(L.lib().mokab_comm_barrier(self.handle))
+
+    def allreduce(self, values, op: str = "sum") -> np.ndarray:
+        a = np.ascontiguousarray(np.atleast_1d(values), np.float64).copy()
+        L.check(L.lib().mokab_comm_allreduce_f64(self.handle, a.ctypes.data_as(L._F64P), a.size, {"sum": 0, "max": 1, "min": 2}[op]))
+        return a
+
+    def allgather(self, mine: np.ndarray) -> np.ndarray:
+        """Every rank's array (same shape and dtype on every rank), stacked rank-major."""
+        a = np.ascontiguousarray(mine)
+        out = np.empty((self.nranks,) + a.shape, a.dtype)
+        L.check(L.lib().mokab_comm_allgather_bytes(self.handle, a.ctypes.data_as(C.c_void_p), a.nbytes, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def destroy(self) -> None:
+        if self.handle is not None:
+            L.check(L.lib().mokab_comm_destroy(self.handle))
+            self.handle = None
+
+
+HALO_MODES = {"nccl": L.HALO_NCCL, "p2p": L.HALO_P2P, "p2p_fused": L.HALO_P2P_FUSED}
 
 
 class DecomposedModel:
-    """This rank's share of the mesh on its GPU + the stage/exchange schedule.
+    """This rank's share of the mesh on its GPU, stepped by the library's own decomposed entry points
+    (mokab_decomp_setup / mokab_timestep_*_decomposed, csrc/decomposed.cuh): the halo exchange per RK stage -- NCCL
+    send/recv, or direct stores into the neighbours' memory -- runs on a high-priority stream next to the interior blocks,
+    and one / two consecutive steps are replayed as captured CUDA graphs.  This class only builds the local mesh and state,
+    brings the ranks together and forwards calls; no stream, event or collective is issued from Python.
 
-    Two streams per rank: `compute` runs the INTERIOR blocks, the high-priority `halo` stream runs the
-    BOUNDARY blocks, then pack -> all-to-all -> unpack.  Stage s on either stream needs stage s-1 of BOTH
-    (events `ev_i`, `ev_b`); the unpack of stage s-1 precedes the boundary launch of stage s on the same
-    stream.  Both parts of a stage therefore start together, the boundary blocks win the SMs first, and
-    the message travels while the interior blocks run.  With `graph=True` two consecutive steps (one per
-    time-level parity) are captured -- NCCL calls included -- into one CUDA graph and replayed.
-    """
+    `graph=True` graphs are VALIDATED on first use: replaying them must reproduce, bit for bit on every rank, what the
+    host-launched schedule computes from the same state, else the model keeps launching from the host (`graph_status`)."""
 
-    def __init__(self, loc: dict, state, backend: api.B200, device_index: int, dtype=np.float64, group=None, overlap=True,
-                 graph=False, runtime=None, halo="nccl"):
-        if halo not in ("nccl", "p2p", "p2p_fused"):
-            raise api.MokaError("DecomposedModel: halo must be 'nccl' (packed all-to-all), 'p2p' (direct peer stores, push and wait "
+    def __init__(self, loc: dict, state, backend: api.B200, device_index: int = 0, dtype=np.float64, group=None, overlap=True,
+                 graph=False, runtime=None, halo="nccl", comm: Communicator | None = None):
+        if halo not in HALO_MODES:
+            raise api.MokaError("DecomposedModel: halo must be 'nccl' (packed NCCL send/recv), 'p2p' (direct peer stores, push and wait "
                                 "kernels) or 'p2p_fused' (direct peer stores from inside the boundary launch)")
         self.halo_mode = halo
         self.rt = runtime if runtime is not None else TorchRuntime(device_index, group)
-        self.cuda = self.rt.cuda
         self.loc, self.backend, self.overlap, self.use_graph = loc, backend, overlap, graph
         self.nparts = loc["nparts"]
+        self._own_comm = comm is None
+        self.comm = comm if comm is not None else Communicator(backend, self.rt)
+        if self.comm.nranks != self.nparts:
+            raise api.MokaError("DecomposedModel: the mesh was decomposed for a different number of ranks")
         self.mesh = api.Mesh(loc, backend)
         sidx, scnt, ridx, rcnt = partition.flat_halo(loc, self.nparts)
         self.mesh.halo_setup(sidx, ridx)
+        self.send_counts, self.recv_counts = [int(c) for c in scnt], [int(c) for c in rcnt]
         ssh, u, h = state
         self.prog = api.PrognosticVars(np.asarray(ssh, dtype), np.asarray(u, dtype), np.asarray(h, dtype), 2, self.mesh)
-        self.dev = getattr(self.rt, "dev", None)
-        self.ex = self.rt.exchanger(scnt, rcnt, dtype)
-        self.compute = self.rt.stream()
-        self.halo = self.rt.stream(priority=-1)
-        self.comm = self.halo
-        # the context's own work (state set/get permutes, reductions, ssh refresh) joins the compute stream, so the
-        # pipelined upload/download of the API orders itself with the steps without host synchronisation
-        backend.set_stream(self.compute.cuda_stream)
         self.handle = self.prog.dev.handle
-        self._graph, self._graph_dt = None, None
+        sc, rc = np.asarray(scnt, np.int64), np.asarray(rcnt, np.int64)
+        i64p = C.POINTER(C.c_int64)
+        L.check(L.lib().mokab_decomp_setup(self.handle, self.comm.handle, sc.ctypes.data_as(i64p), rc.ctypes.data_as(i64p),
+                                           HALO_MODES[halo], self._flags(graph)))
         self._validated, self.graph_status = False, "not used"
-        self._parity, self._graph_parity = 0, 0                  # steps taken so far mod 2; the same at graph capture
+        self._graph_dt = None
         self._fe, self._stepped = False, False                   # the model steps with ForwardEuler; it has stepped
-        if halo != "nccl":
-            self._setup_p2p(scnt, rcnt)
+        self._closed = False
 
-    def _setup_p2p(self, scnt, rcnt) -> None:
-        """Direct-store halo exchange (csrc/kernels_p2p.cuh): tell every sender where its values live in this rank's
-        arrays, exchange the addresses / IPC handles of the state arrays, and build the push tables."""
-        lib, rank = L.lib(), int(self.loc["rank"])
-        nrecv_total = int(sum(rcnt))
-        mine = np.zeros(max(1, nrecv_total), np.int32)
-        L.check(lib.mokab_halo_recv_device_indices(self.mesh.handle, mine.ctypes.data_as(L._I32P)))
-        offs = np.concatenate([[0], np.cumsum(rcnt)]).astype(np.int64)
-        # rank q fills my segment q: it needs those indices; I need, from every rank I send to, its segment for me
-        got = self.rt.all_to_all_int32([mine[offs[q]:offs[q + 1]] for q in range(self.nparts)], list(scnt))
-        size = C.c_int64()
-        L.check(lib.mokab_p2p_blob_size(C.byref(size)))
-        blob = C.create_string_buffer(size.value)
-        L.check(lib.mokab_p2p_export(self.handle, rank, blob))
-        blobs = b"".join(self.rt.all_gather_bytes(blob.raw))
-        receivers = [q for q in range(self.nparts) if scnt[q] > 0]
-        senders = [q for q in range(self.nparts) if rcnt[q] > 0]
-        dst = np.ascontiguousarray(np.concatenate([got[q] for q in receivers] + [np.zeros(0, np.int32)]), np.int32)
-        rr, sr = np.asarray(receivers, np.int32), np.asarray(senders, np.int32)
-        cnt = np.asarray([scnt[q] for q in receivers], np.int64)
-        L.check(lib.mokab_p2p_setup(self.handle, rank, self.nparts, blobs, len(receivers), rr.ctypes.data_as(L._I32P),
-                                    cnt.ctypes.data_as(C.POINTER(C.c_int64)), dst.ctypes.data_as(L._I32P), len(senders),
-                                    sr.ctypes.data_as(L._I32P)))
-        self.rt.all_reduce_min(1)                                # nobody pushes before everybody is mapped
+    def _flags(self, graph: bool) -> int:
+        return (0 if self.overlap else L.DECOMP_NO_OVERLAP) | (0 if graph else L.DECOMP_NO_GRAPH)
 
-    def _stage(self, dt, s, part, stream):
-        L.check(L.lib().mokab_rk4_stage(self.handle, float(dt), s, part, C.c_void_p(stream.cuda_stream)))
+    def _set_graph(self, on: bool) -> None:
+        L.check(L.lib().mokab_decomp_set_flags(self.handle, self._flags(on)))
 
-    def _exchange(self, s, stream):
-        lib = L.lib()
-        if self.halo_mode == "p2p":
-            L.check(lib.mokab_halo_push(self.handle, s, C.c_void_p(stream.cuda_stream)))
-            L.check(lib.mokab_halo_wait(self.handle, C.c_void_p(stream.cuda_stream)))
-            return
-        with self.cuda.stream(stream):
-            L.check(lib.mokab_halo_pack(self.handle, s, C.c_void_p(self.ex.send.data_ptr()), C.c_void_p(stream.cuda_stream)))
-            self.ex.exchange()
-            L.check(lib.mokab_halo_unpack(self.handle, s, C.c_void_p(self.ex.recv.data_ptr()), C.c_void_p(stream.cuda_stream)))
-
-    def _wait_arrivals(self, stream) -> None:
-        L.check(L.lib().mokab_halo_wait_arrivals(self.handle, C.c_void_p(stream.cuda_stream)))
-
-    def _enqueue_steps(self, dt: float, nsteps: int) -> None:
-        """Enqueue `nsteps` RK4 steps; on entry and exit both streams are joined on `compute`."""
-        cuda = self.cuda
-        fused = self.halo_mode == "p2p_fused"                    # the boundary launch carries the exchange itself
-        boundary = L.PART_BOUNDARY_PUSH if fused else L.PART_BOUNDARY
-        if not self.overlap:
-            for _ in range(nsteps):
-                for s in (1, 2, 3, 4):
-                    if fused:
-                        self._stage(dt, s, boundary, self.compute)
-                        self._stage(dt, s, L.PART_INTERIOR, self.compute)
-                    else:
-                        self._stage(dt, s, L.PART_ALL, self.compute)
-                        self._exchange(s, self.compute)
-                L.check(L.lib().mokab_rk4_finish_step(self.handle))
-            if fused:
-                self._wait_arrivals(self.compute)
-            return
-        self.halo.wait_stream(self.compute)                      # fork
-        for _ in range(nsteps):
-            for s in (1, 2, 3, 4):
-                ev_i, ev_b = cuda.Event(), cuda.Event()
-                self._stage(dt, s, boundary, self.halo)
-                ev_b.record(self.halo)
-                self._stage(dt, s, L.PART_INTERIOR, self.compute)
-                ev_i.record(self.compute)
-                if not fused:
-                    self._exchange(s, self.halo)
-                self.compute.wait_event(ev_b)                    # stage s+1 interior reads stage s boundary output
-                self.halo.wait_event(ev_i)                       # stage s+1 boundary reads stage s interior output
-            L.check(L.lib().mokab_rk4_finish_step(self.handle))
-        if fused:
-            self._wait_arrivals(self.halo)                       # the neighbours' last stores, before anything else touches the halo slots
-        self.compute.wait_stream(self.halo)                      # join
-
-    def _enqueue_fe_steps(self, dt: float, nsteps: int) -> None:
-        """Enqueue `nsteps` ForwardEuler steps (the reference's live stepper, time_integration.jl:150-193): one launch per part,
-        then the halo copies of everything the step wrote -- (h, u) and (ssh, layerThicknessEdge), two messages -- while the
-        interior blocks run.  Stream-launched (one exchange pair per step instead of RK4's four; no captured graph)."""
-        if self.halo_mode != "nccl":
-            raise api.MokaError("DecomposedModel: ForwardEuler steps use the packed exchange (halo='nccl')")
-        lib, cuda = L.lib(), self.cuda
-        self._fe = True
-
-        def stage(part, stream):
-            L.check(lib.mokab_forward_euler_stage(self.handle, float(dt), part, C.c_void_p(stream.cuda_stream)))
-
-        if not self.overlap:
-            for _ in range(nsteps):
-                stage(L.PART_ALL, self.compute)
-                self._exchange(4, self.compute)
-                self._exchange(5, self.compute)
-                L.check(lib.mokab_forward_euler_finish_step(self.handle))
-            return
-        self.halo.wait_stream(self.compute)                      # fork
-        for _ in range(nsteps):
-            ev_i, ev_b = cuda.Event(), cuda.Event()
-            stage(L.PART_BOUNDARY, self.halo)
-            ev_b.record(self.halo)
-            stage(L.PART_INTERIOR, self.compute)
-            ev_i.record(self.compute)
-            self._exchange(4, self.halo)
-            self._exchange(5, self.halo)
-            self.compute.wait_event(ev_b)                        # the next interior launch overwrites what this boundary launch read
-            self.halo.wait_event(ev_i)                           # the next boundary launch reads (and overwrites the inputs of) this interior launch
-            L.check(lib.mokab_forward_euler_finish_step(self.handle))
-        self.compute.wait_stream(self.halo)                      # join
-
-    def _build_graph(self, dt: float) -> None:
-        """Capture two consecutive steps (one per time-level parity), NCCL calls included, into one CUDA graph."""
-        cuda = self.cuda
-        self.compute.synchronize()
-        self.halo.synchronize()
-        self._enqueue_steps(dt, 2)                               # warm up NCCL + lazy library state outside capture
-        self.compute.synchronize()
-        g = cuda.CUDAGraph()
-        with cuda.graph(g, stream=self.compute):
-            self._enqueue_steps(dt, 2)
-        self._graph, self._graph_dt, self._graph_parity = g, dt, self._parity
+    def _advance(self, dt: float, nsteps: int, fe: bool) -> None:
+        fn = L.lib().mokab_timestep_forward_euler_decomposed if fe else L.lib().mokab_timestep_rk4_decomposed
+        L.check(fn(self.handle, float(dt), int(nsteps)))
 
     def _snapshot(self):
         return [self.prog.dev.get(f) for f in (L.SSH, L.NORMAL_VELOCITY, L.LAYER_THICKNESS)]
 
     def _restore(self, snap) -> None:
-        for f, a in zip((L.SSH, L.NORMAL_VELOCITY, L.LAYER_THICKNESS), snap):
+        for f, a in zip((L.LAYER_THICKNESS, L.NORMAL_VELOCITY, L.SSH), (snap[2], snap[1], snap[0])):
             self.prog.dev.set(f, a)
 
-    def validate_graph(self, dt: float, nsteps: int = 8) -> bool:
-        """Build the 2-step graph and accept it only if replaying it reproduces, bit for bit on every rank, what the
-        stream-launched schedule computes from the same state (`nsteps` even; the state is restored afterwards).
-        A captured schedule that also contains NCCL traffic is not something to trust unchecked: on rejection the
-        model keeps launching from the host (`use_graph` False, reason in `graph_status`)."""
+    def validate_graph(self, dt: float, nsteps: int = 7) -> bool:
+        """Accept the captured graphs only if replaying them (one 2-step graph per time-level parity and the 1-step graph:
+        `nsteps` odd) reproduces what the host-launched schedule computes from the same state; the state is restored."""
         snap = self._snapshot()
-        self._enqueue_steps(dt, nsteps)
+        self._set_graph(False)
+        self._advance(dt, nsteps, False)
         self.finish()
         want = self._snapshot()
         self._restore(snap)
-        self._build_graph(dt)                                    # advances the state by its two warm-up steps
-        with self.cuda.stream(self.compute):
-            for _ in range((nsteps - 2) // 2):
-                self._graph.replay()
+        self._set_graph(True)
+        self._advance(dt, nsteps, False)
         self.finish()
         got = self._snapshot()
         self._restore(snap)
         ok = all(np.array_equal(a, b) for a, b in zip(want, got))
-        flag = self.rt.all_reduce_min(1 if ok else 0)
-        self.compute.synchronize()
-        self._validated = True
+        flag = int(self.comm.allreduce(1.0 if ok else 0.0, "min")[0])
+        self._validated, self._graph_dt = True, dt
         if flag == 0:
-            self._graph, self._graph_dt, self.use_graph = None, None, False
-            self.graph_status = "rejected: graph replay did not reproduce the stream-launched schedule; launching from the host"
-            import gc
-            gc.collect()
+            self.use_graph = False
+            self._set_graph(False)
+            self.graph_status = "rejected: graph replay did not reproduce the host-launched schedule; launching from the host"
             return False
-        self.graph_status = f"validated against the stream-launched schedule over {nsteps} steps"
+        self.graph_status = f"validated against the host-launched schedule over {nsteps} steps"
         return True
 
-    def _run(self, dt: float, nsteps: int) -> None:
-        """Stream-launched steps (outside any capture), keeping track of the time-level parity."""
-        self._enqueue_steps(dt, nsteps)
-        self._parity ^= nsteps & 1
-
     def step(self, dt: float, nsteps: int = 1, stepper=None) -> None:
-        """`nsteps` steps of `stepper` (api.RungeKutta4, the default, or api.ForwardEuler)."""
+        """`nsteps` steps of `stepper` (api.RungeKutta4, the default, or api.ForwardEuler); asynchronous."""
         if stepper not in (None, api.RungeKutta4, api.ForwardEuler):
             raise api.MokaError("DecomposedModel.step: unknown stepper")
         fe = stepper is api.ForwardEuler
         if self._stepped and fe != self._fe:                     # (ForwardEuler carries a lagged layerThicknessEdge between its steps)
             raise api.MokaError("DecomposedModel.step: one stepper per model -- build another DecomposedModel to change it")
         self._stepped = self._stepped or nsteps > 0
-        if fe:
-            if nsteps > 0:
-                self._enqueue_fe_steps(dt, nsteps)
-                self._parity ^= nsteps & 1
-            return
-        if self.use_graph and nsteps >= 2:
-            if self._graph is None or self._graph_dt != dt:
-                if not self.validate_graph(dt):
-                    self._run(dt, nsteps)
-                    return
-            pre, replays, nsteps = plan_steps(nsteps, self._parity, self._graph_parity)
-            if pre:
-                self._run(dt, pre)
-            with self.cuda.stream(self.compute):
-                for _ in range(replays):
-                    self._graph.replay()
-        if nsteps:
-            self._run(dt, nsteps)
+        self._fe = fe
+        if self.use_graph and not fe and nsteps > 0 and (not self._validated or self._graph_dt != dt):
+            self.validate_graph(dt)
+        self._advance(dt, nsteps, fe)
 
     def refresh_ssh(self) -> None:
-        """ssh = layerThickness - restingThicknessSum on the compute stream (asynchronous)."""
-        L.check(L.lib().mokab_refresh_ssh(self.handle, C.c_void_p(self.compute.cuda_stream)))
+        """ssh = layerThickness - restingThicknessSum (the decomposed RK4 entry point leaves it refreshed already)."""
+
+    def synchronize(self) -> None:
+        L.check(L.lib().mokab_decomp_synchronize(self.handle))
 
     def finish(self) -> None:
-        if not self._fe:                                         # (ForwardEuler carries ssh as a state of its own)
-            self.refresh_ssh()
-        self.compute.synchronize()
-        self.halo.synchronize()
-        if self.halo_mode != "nccl":
-            err = C.c_int()
-            L.check(L.lib().mokab_p2p_error(self.handle, C.byref(err)))
-            if err.value:
-                raise api.MokaError("DecomposedModel: a halo wait timed out (a peer died or the ranks' schedules diverged)")
+        self.synchronize()
 
     def close(self) -> None:
-        """Drop the captured graph (it pins NCCL resources: the process group cannot be destroyed while
-        it is alive) and drain both streams."""
-        self.compute.synchronize()
-        self.halo.synchronize()
-        if self.halo_mode != "nccl":                             # nobody unmaps while a neighbour may still store, nobody frees while mapped
-            self.rt.all_reduce_min(1)
-            L.check(L.lib().mokab_p2p_close(self.handle))
-            self.rt.all_reduce_min(1)
-        self.backend.set_stream(None)                            # the context goes back to its own stream
-        self._graph = None
-        import gc
-        gc.collect()
-        self.cuda.synchronize()
+        """Collective: unmap the peers (direct-store paths), drop the graphs and the halo stream, leave the communicator."""
+        if self._closed:
+            return
+        self._closed = True
+        L.check(L.lib().mokab_decomp_close(self.handle))
+        if self._own_comm:
+            self.comm.destroy()
 
     def owned(self, field: str) -> np.ndarray:
         a = getattr(self.prog, field)
@@ -393,7 +261,9 @@ class DecomposedModel:
         return a[:n]
 
     def reduce(self, which: str) -> float:
-        return self.rt.all_reduce_sum(api.reduce_sum(self.prog, which))
+        out = C.c_double()
+        L.check(L.lib().mokab_reduce_decomposed(self.handle, {"ssh2": L.SUM_SSH2, "mass": L.SUM_MASS, "energy": L.SUM_ENERGY}[which], C.byref(out)))
+        return out.value
 
     def gather(self, nC: int, nE: int, previous: bool = False):
         """The global (ssh, normalVelocity, layerThickness) on every rank, assembled from the owned parts (`previous`: the
@@ -402,9 +272,14 @@ class DecomposedModel:
         names = (("ssh_prev", "normalVelocity_prev", "layerThickness_prev") if previous else ("ssh", "normalVelocity", "layerThickness"))
         for name, n, ids, no in ((names[0], nC, loc["cellsGlobal"], loc["nCellsOwned"]), (names[1], nE, loc["edgesGlobal"], loc["nEdgesOwned"]),
                                  (names[2], nC, loc["cellsGlobal"], loc["nCellsOwned"])):
+            nmax = int(self.comm.allreduce(float(no), "max")[0])
+            vals, gid = np.zeros(nmax, np.float64), np.full(nmax, -1, np.int64)
+            vals[:no], gid[:no] = np.asarray(getattr(self.prog, name), np.float64)[:no], ids[:no]
+            allv, alli = self.comm.allgather(vals), self.comm.allgather(gid)
             g = np.zeros(n, np.float64)
-            g[ids[:no]] = np.asarray(getattr(self.prog, name), np.float64)[:no]
-            out.append(self.rt.sum_arrays(g))
+            keep = alli >= 0
+            g[alli[keep]] = allv[keep]
+            out.append(g)
         return out
 
 
@@ -414,26 +289,17 @@ def local_state(loc: dict, ssh, u, h):
 
 def gather_owned(model: DecomposedModel, nC: int, nE: int):
     """Assemble the global (ssh, u, h) on every rank from the owned parts (test/diagnostic helper)."""
-    import torch
-    import torch.distributed as dist
-    loc = model.loc
-    out = []
-    for field, n, ids, no in (("ssh", nC, loc["cellsGlobal"], loc["nCellsOwned"]),
-                              ("normalVelocity", nE, loc["edgesGlobal"], loc["nEdgesOwned"]),
-                              ("layerThickness", nC, loc["cellsGlobal"], loc["nCellsOwned"])):
-        g = torch.zeros(n, dtype=torch.float64, device=model.dev)
-        g[torch.as_tensor(ids[:no], device=model.dev)] = torch.as_tensor(np.asarray(model.owned(field), np.float64), device=model.dev)
-        dist.all_reduce(g)
-        out.append(g.cpu().numpy())
-    return out
+    return model.gather(nC, nE)
 
 
 # ---- bench leg for torchrun (N > 1) -------------------------------------------------------------------------
-def _share_locals(args, rank, world, nx, dtype):
-    """Rank 0 builds the global mesh, decomposes it and hands every rank its local mesh through /dev/shm."""
+def _share_locals(args, rank, world, nx, dtype, keep_global=False):
+    """Rank 0 builds the global mesh, decomposes it and hands every rank its local mesh through /dev/shm.  With
+    `keep_global` rank 0 also returns (mesh, state) for the parity check of the bench line."""
     import torch.distributed as dist
     tag = f"/dev/shm/mokab_{os.environ.get('MASTER_PORT', '0')}_{nx}_{world}"
     t0 = time.time()
+    glob = None
     if rank == 0:
         from . import planar_hex
         if args.workload.startswith("kelvin"):
@@ -465,7 +331,9 @@ def _share_locals(args, rank, world, nx, dtype):
             meta["peers"] = halo["peers"]
             flat["state_ssh"], flat["state_u"], flat["state_h"] = ls
             np.savez(f"{tag}_{r}.npz", meta=json.dumps(meta), **flat)
-        del m, locs
+        if keep_global:
+            glob = (m, (ssh, u, h))
+        del locs
     dist.barrier()
     z = np.load(f"{tag}_{rank}.npz")
     meta = json.loads(str(z["meta"]))
@@ -481,88 +349,129 @@ def _share_locals(args, rank, world, nx, dtype):
                 os.remove(f"{tag}_{r}.npz")
             except OSError:
                 pass
+    if keep_global:
+        return loc, state, time.time() - t0, glob
     return loc, state, time.time() - t0
+
+
+def _collect_on_rank0(model, rank, world, nC, nE, tag):
+    """The owned (ssh, normalVelocity) of every rank assembled into global arrays on rank 0 (through /dev/shm: a one-off
+    check, not a data path)."""
+    import torch.distributed as dist
+    loc = model.loc
+    no, ne = loc["nCellsOwned"], loc["nEdgesOwned"]
+    np.savez(f"{tag}_par_{rank}.npz", ssh=np.asarray(model.prog.ssh, np.float64)[:no], u=np.asarray(model.prog.normalVelocity, np.float64)[:ne],
+             cells=loc["cellsGlobal"][:no], edges=loc["edgesGlobal"][:ne])
+    dist.barrier()
+    out = None
+    if rank == 0:
+        gs, gu = np.full(nC, np.nan), np.full(nE, np.nan)
+        for r in range(world):
+            z = np.load(f"{tag}_par_{r}.npz")
+            gs[z["cells"]], gu[z["edges"]] = z["ssh"], z["u"]
+            os.remove(f"{tag}_par_{r}.npz")
+        out = (gs, gu)
+    dist.barrier()
+    return out
 
 
 def bench_main(args, rank, world, local):
     import torch
     import torch.distributed as dist
-    from bench import WORKLOADS, ClockSampler, algo_bytes_per_cell_step, algo_bytes_per_cell_step_general, measured_peak_gbs
+    from bench import (WORKLOADS, ClockSampler, algo_bytes_per_cell_step, algo_bytes_per_cell_step_general, measured_peak_gbs,
+                       parity_against_oracle, workload_label)
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # torch.distributed is the CONTROL plane only (gloo: sharing the decomposition through /dev/shm, handing out the
+    # communicator id); every byte of halo data and every reduction moves through NCCL inside libmoka_b200.so
+    dist.init_process_group("gloo")
     nx = WORKLOADS[args.workload]
     npdt = np.float64 if args.dtype == "f64" else np.float32
-    loc, state, t_setup = _share_locals(args, rank, world, nx, npdt)
-    nC_glob = nx * nx
+    loc, state, t_setup, glob = _share_locals(args, rank, world, nx, npdt, keep_global=True)
+    nC_glob = loc["nCellsGlobal"] if "nCellsGlobal" in loc else nx * nx
     sphere = args.workload.startswith("sphere")
     voronoi = args.workload.startswith("voronoi") or sphere      # unstructured: byte accounting from the actual rows
     dt = float(loc["bench_dt"]) if sphere else (0.25 if voronoi else 1.0) * api.cfl_dt(1.0e7 / nx)
     backend = api.B200(local)
+    rt = TorchRuntime(local, device="cpu")
+    comm = Communicator(backend, rt)
     model = DecomposedModel(loc, state, backend, local, dtype=npdt, overlap=not getattr(args, "no_overlap", False),
-                            graph=not getattr(args, "no_graph", False), halo=getattr(args, "halo", "nccl"))
+                            graph=not getattr(args, "no_graph", False), runtime=rt, halo=getattr(args, "halo", "nccl"), comm=comm)
     K, W = args.steps, max(args.warmup, 3)
-    model.step(dt, W)
+    model.step(dt, W)                                             # (validates the captured graphs on first use)
     model.finish()
-    dist.barrier()
+    # how many batches of K steps make the timed region >= 0.5 s (one scheduler hiccup must not be 5 % of the number)
+    backend.timer_start()
+    model.step(dt, K)
+    probe_ms = float(comm.allreduce(backend.timer_stop(), "max")[0])
+    reps = int(max(1, np.ceil(500.0 / max(probe_ms, 1e-3))))
+    comm.barrier()
     torch.cuda.synchronize()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    dist.barrier()
+    comm.barrier()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(model.compute)
-    model.step(dt, K)
-    e1.record(model.compute)
-    model.compute.synchronize()
-    model.halo.synchronize()
-    ms_local = e0.elapsed_time(e1)
-    # this library's kernels per step: 4 stages x (boundary + interior + pack + unpack), or 4 x (all + pack + unpack);
-    # graph replays do not pass through the host-side counter, so the count is by construction
-    launches = K * (16 if model.overlap else 12)
-    t = torch.tensor([ms_local], dtype=torch.float64, device=model.dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    dist.barrier()
+    l0 = backend.launch_count()
+    backend.timer_start()                                        # CUDA events on the compute stream; every step call ends with the halo stream joined into it
+    for _ in range(reps):
+        model.step(dt, K)
+    ms_local = backend.timer_stop()
+    model.synchronize()
+    launches = backend.launch_count() - l0
+    ms = float(comm.allreduce(ms_local, "max")[0])
+    comm.barrier()
     torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     model.finish()
+    steps_timed = K * reps
 
-    # end to end with HOST buffers: every step uploads this rank's (u, h) from pinned memory and reads back ssh;
-    # pipelined through the API's copy streams (PCIe transfers of steps n+1 / n-1 overlap the kernels of step n)
+    # end to end with HOST buffers: every step uploads this rank's (normalVelocity, layerThickness | ssh) from pinned memory, takes
+    # one step (a captured 1-step graph, exchange included) and reads back the new (ssh, normalVelocity) -- layerThickness = ssh +
+    # restingThicknessSum is redundant with ssh and stays on the device; pipelined through the API's copy streams
     nCl, nEl = loc["nCells"], loc["nEdges"]
     hin = [(backend.pinned(nEl, npdt), backend.pinned(nCl, npdt)) for _ in range(2)]
-    hout = [backend.pinned(nCl, npdt) for _ in range(2)]
+    hout = [(backend.pinned(nCl, npdt), backend.pinned(nEl, npdt)) for _ in range(2)]
+    f32 = npdt == np.float32
     for hu, hh in hin:
-        hu[:], hh[:] = np.asarray(state[1], npdt), np.asarray(state[2], npdt)
+        hu[:], hh[:] = np.asarray(state[1], npdt), np.asarray(state[0] if f32 else state[2], npdt)
     Ke = max(3, min(K, 20))
 
     def e2e_steps(n):
         for i in range(n):
-            model.prog.upload_async(normalVelocity=hin[i & 1][0], layerThickness=hin[i & 1][1])
+            if f32:
+                model.prog.upload_async(normalVelocity=hin[i & 1][0], ssh=hin[i & 1][1])
+            else:
+                model.prog.upload_async(normalVelocity=hin[i & 1][0], layerThickness=hin[i & 1][1])
             model.step(dt, 1)
-            model.refresh_ssh()
-            model.prog.download_async(ssh=hout[i & 1])
+            model.prog.download_async(ssh=hout[i & 1][0], normalVelocity=hout[i & 1][1])
         model.prog.synchronize()
-        model.halo.synchronize()
+        model.synchronize()
     e2e_steps(2)
-    dist.barrier()
+    comm.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     e2e_steps(Ke)
     torch.cuda.synchronize()
-    te = torch.tensor([(time.perf_counter() - t0) / Ke], dtype=torch.float64, device=model.dev)
-    dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te.item())
-    cnt = torch.tensor([nCl + nEl, nCl, loc["nCellsOwned"], launches], dtype=torch.float64, device=model.dev)
-    dist.all_reduce(cnt)
+    e2e_s = float(comm.allreduce((time.perf_counter() - t0) / Ke, "max")[0])
+    cnt = comm.allreduce([nCl + nEl, nCl + nEl, loc["nCellsOwned"], launches], "sum")
     blocks = model.mesh.block_counts()
-    halo_bytes = (sum(model.ex.send_counts) + sum(model.ex.recv_counts)) * np.dtype(npdt).itemsize
+    halo_bytes = (sum(model.send_counts) + sum(model.recv_counts)) * np.dtype(npdt).itemsize
+
+    # parity: two steps from the initial state, gathered on rank 0, against the C oracle on the undecomposed mesh
+    parity = None
+    if not getattr(args, "no_parity", False):
+        model._restore((state[0], state[1], state[2]))
+        model.step(dt, 2)
+        model.finish()
+        got = _collect_on_rank0(model, rank, world, glob[0]["nCells"] if rank == 0 else 0, glob[0]["nEdges"] if rank == 0 else 0,
+                                f"/dev/shm/mokab_{os.environ.get('MASTER_PORT', '0')}_{nx}_{world}")
+        if rank == 0:
+            parity = parity_against_oracle(glob[0], glob[1], dt, 2, got[0], got[1], args.dtype, args.workload)
     if rank == 0:
         item = np.dtype(npdt).itemsize
         peak, peak_src = measured_peak_gbs()
-        value = nC_glob * K / (ms * 1e-3)
+        value = nC_glob * steps_timed / (ms * 1e-3)
         nblk, nder = model.mesh.derived_blocks()
         if voronoi:
             nco, neo = loc["nCellsOwned"], loc["nEdgesOwned"]
@@ -571,35 +480,37 @@ def bench_main(args, rank, world, local):
         else:
             per_cell_step = algo_bytes_per_cell_step(args.dtype, nder / max(nblk, 1))
         algo_per_launch = per_cell_step / 4.0 * loc["nCellsOwned"]
-        achieved = algo_per_launch / ((ms * 1e-3) / (4 * K)) / 1e9
+        achieved = algo_per_launch / ((ms * 1e-3) / (4 * steps_timed)) / 1e9
+        halo_txt = {"nccl": "NCCL send/recv inside libmoka_b200.so", "p2p": "direct peer stores + arrival counters (push / wait kernels)",
+                    "p2p_fused": "direct peer stores from inside the boundary launch"}[model.halo_mode]
         print(json.dumps({
             "metric": "RK4 cell-steps/sec", "value": value, "unit": "cell-steps/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype,
+            "ms_per_step": ms / steps_timed, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype,
             "data": "synthetic",
-            "config": {"workload": ("coastal Kelvin wave, %dx%d channel hex mesh with boundary-edge masks" % (nx, nx) if args.workload.startswith("kelvin")
-                                    else "geostrophic zonal flow + noise, spherical Voronoi mesh, fEdge = 2 Omega sin(lat)" if sphere
-                                    else f"inertial gravity wave, {nx}x{nx} periodic planar Voronoi mesh of a jittered lattice" if voronoi
-                                    else f"inertial gravity wave, {nx}x{nx} periodic planar hex mesh") + f" ({nC_glob} cells), "
-                                   f"{'Float64' if args.dtype == 'f64' else 'Float32'} RK4, dt={dt:.4g}s, recursive-coordinate-bisection "
-                                   f"into {world} parts, 1 halo layer, "
-                                   f"{ {'nccl': 'NCCL all-to-all', 'p2p': 'direct peer stores + arrival counters (push / wait kernels)', 'p2p_fused': 'direct peer stores from inside the boundary launch'}[model.halo_mode]} per stage "
-                                   f"{'overlapped with interior blocks' if model.overlap else '(no overlap)'}"
-                                   f"{', 2-step CUDA graph incl. the exchange (' + model.graph_status + ')' if model.use_graph else ', CUDA graph ' + model.graph_status}",
-                       "name": args.workload, "l2": "inputs larger than L2 (no flush)", "setup_s": round(t_setup, 1),
+            "config": {"workload": workload_label(args.workload, nx), "name": args.workload,
+                       "detail": f"{nC_glob} cells, {'Float64' if args.dtype == 'f64' else 'Float32'} RK4, dt={dt:.4g}s, recursive-coordinate-bisection "
+                                 f"into {world} parts, 1 halo layer, {halo_txt} per stage "
+                                 f"{'overlapped with interior blocks' if model.overlap else '(no overlap)'}"
+                                 f"{', 1- / 2-step CUDA graphs incl. the exchange (' + model.graph_status + ')' if model.use_graph else ', CUDA graph ' + model.graph_status}",
+                       "timed_steps": steps_timed, "repeats_of_steps": reps,
+                       "l2": "inputs larger than L2 (no flush)", "setup_s": round(t_setup, 1),
                        "rank0_blocks_interior_boundary": list(blocks), "rank0_halo_bytes_per_stage": int(halo_bytes),
                        "rank0_blocks_rebuilding_edgesOnEdge": [int(nder), int(nblk)],
                        "variant": {"lib": os.environ.get("MOKAB_LIB", "libmoka_b200.so"),
-                                   "stage_tma": int(os.environ.get("MOKAB_STAGE_TMA", "0") or 0)}},
+                                   "stage_tma": L.get_option("stage_tma"), "stage_prefetch": L.get_option("stage_prefetch"),
+                                   "stage_prefetch_distance": L.get_option("stage_prefetch_distance")}},
             "clocks": clocks,
-            "e2e": {"value": nC_glob / e2e_s, "unit": "cell-steps/s", "h2d_bytes_per_step": int(cnt[0].item() * item),
-                    "d2h_bytes_per_step": int(cnt[1].item() * item), "ms_per_step": e2e_s * 1e3, "steps": Ke,
-                    "pipelined": True},
-            "gpu_launches": int(cnt[3].item()),
+            "e2e": {"value": nC_glob / e2e_s, "unit": "cell-steps/s", "h2d_bytes_per_step": int(cnt[0] * item),
+                    "d2h_bytes_per_step": int(cnt[1] * item), "ms_per_step": e2e_s * 1e3, "steps": Ke,
+                    "pipelined": True, "returns": "ssh + normalVelocity of the new state (layerThickness = ssh + restingThicknessSum stays on the device)"},
+            "gpu_launches": int(cnt[3]),
+            "parity": parity,
             "roofline": {"bound": "hbm", "kernel": "k_rk_stage", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "note": "per GPU: algorithmic bytes of rank 0's owned cells per stage / (max-over-ranks step time / 4)"},
         }))
     model.close()
+    comm.destroy()
     dist.barrier()
     torch.cuda.synchronize()
     dist.destroy_process_group()

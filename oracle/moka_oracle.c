@@ -55,6 +55,17 @@ typedef struct {
     double *uProvis, *hProvis, *sshProvis, *uNew, *hNew;
 } ora_state;
 
+/* The reference's CPU path fans its workgroups over all Julia threads; under torchrun the environment pins OMP_NUM_THREADS=1,
+ * so the benchmark's reference arm sets the team size explicitly (bench.py: run_reference). */
+void ora_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int ora_num_threads(void)
 {
 #ifdef _OPENMP

@@ -51,6 +51,11 @@ def lib():
     return _LIB
 
 
+def set_num_threads(n: int) -> None:
+    """OpenMP team size of the C oracle (all host cores for the benchmark's reference arm, whatever OMP_NUM_THREADS says)."""
+    lib().ora_set_num_threads(int(n))
+
+
 def _p(a):
     if a is None:
         return None

@@ -129,7 +129,7 @@ def run_e2e(kind, nx, nparts, iters, policy, seed, halo):
             model.refresh_ssh()
             model.prog.download_async(ssh=hout[i])
         model.prog.synchronize()
-        model.halo.synchronize()
+        model.synchronize()
         res = [np.array(a[:loc["nCellsOwned"]]) for a in hout]
         model.close()
         return res
@@ -148,35 +148,13 @@ def run_e2e(kind, nx, nparts, iters, policy, seed, halo):
 
 def run_mutations():
     """Does this checker have teeth?  Re-run one case with each of the schedule's two cross-stream events removed
-    (DecomposedModel._enqueue_steps: interior(s+1) after boundary(s), boundary(s+1) after interior(s)): the intact schedule
+    (csrc/decomposed.cuh, decomp_enqueue_rk4: interior(s+1) after boundary(s), boundary(s+1) after interior(s)): the intact schedule
     passes under every policy, and LAZY must catch each removal (the other policies may or may not -- the bug is a race)."""
     from moka_b200 import _lib as L
-
-    def variant(drop):
-        def _enqueue_steps(self, dt, nsteps):
-            cuda = self.cuda
-            self.halo.wait_stream(self.compute)
-            for _ in range(nsteps):
-                for s in (1, 2, 3, 4):
-                    ev_i, ev_b = cuda.Event(), cuda.Event()
-                    self._stage(dt, s, L.PART_BOUNDARY, self.halo)
-                    ev_b.record(self.halo)
-                    self._stage(dt, s, L.PART_INTERIOR, self.compute)
-                    ev_i.record(self.compute)
-                    self._exchange(s, self.halo)
-                    if drop != "ev_b":
-                        self.compute.wait_event(ev_b)
-                    if drop != "ev_i":
-                        self.halo.wait_event(ev_i)
-                L.check(L.lib().mokab_rk4_finish_step(self.handle))
-            self.compute.wait_stream(self.halo)
-        return _enqueue_steps
-
-    original = multi_gpu.DecomposedModel._enqueue_steps
     bad = 0
     try:
-        for drop in (None, "ev_b", "ev_i"):
-            multi_gpu.DecomposedModel._enqueue_steps = variant(drop)
+        for drop, code in ((None, 0), ("ev_b", 1), ("ev_i", 2)):
+            L.set_option("test_drop_dependency", code)           # the library's test hook: leave out that cross-stream wait
             got = {pol: run("igw", 128, 2, [3], True, False, pol, 2)[0] for pol in ("fifo", "lazy", "others_first")}
             # LAZY is deterministic about a missing wait (the producer has not run).  What FIFO and OTHERS_FIRST make of it depends
             # on how far the other rank's host thread has got (a stream parked in a collective delays what is queued behind
@@ -185,7 +163,7 @@ def run_mutations():
             bad += not ok
             print(f"schedule without {drop or 'nothing'}: {got} {'as expected' if ok else 'UNEXPECTED'}", flush=True)
     finally:
-        multi_gpu.DecomposedModel._enqueue_steps = original
+        L.set_option("test_drop_dependency", 0)
     print("SIM_MUTATIONS_DETECTED" if bad == 0 else "SIM_MUTATIONS_MISSED", flush=True)
     sys.exit(0 if bad == 0 else 1)
 

@@ -261,6 +261,9 @@ class SimRuntime:
     def rank_and_size(self):
         return self.rank, self.comm.n
 
+    def broadcast_bytes(self, blob, src: int = 0):
+        return self.comm.exchange_host(self.rank, blob)[src]
+
     def sum_arrays(self, a):
         parts = self.comm.exchange_host(self.rank, np.array(a, np.float64))
         out = parts[0].copy()

@@ -51,8 +51,7 @@ def _setup_p2p(ranks, nparts):
     blobs = b"".join(blobs)
     for r in ranks:
         me = r.loc["rank"]
-        receivers = [q for q in range(nparts) if r.scnt[q] > 0]
-        senders = [q for q in range(nparts) if r.rcnt[q] > 0]
+        receivers = senders = [q for q in range(nparts) if r.scnt[q] > 0 or r.rcnt[q] > 0]   # symmetric (kernels_p2p.cuh)
         dst = []
         for q in receivers:                      # rank q's halo segment filled by me, in q's own (device) numbering
             o = sum(ranks[q].rcnt[:me])
@@ -150,14 +149,6 @@ def test_emulated_ranks_match_oracle(backend, nx, nparts, split):
         assert ni + nb == r.mesh.derived_blocks()[0] and nb >= 1        # every block of owned cells is in exactly one part
 
 
-# The direct-store exchange was written after the round's GPU budget was spent: it has run on the simulated runtime only
-# (tests/test_sim.py).  Until its first hardware run it is opt-in on a GPU box, so that an untested path cannot take the
-# verified tests of this suite down with it (`MOKAB_TEST_P2P=1 python -m pytest tests -m gpu -k direct_store`).
-_P2P_OPT_IN = pytest.mark.skipif(not os.environ.get("MOKAB_SIM") and os.environ.get("MOKAB_TEST_P2P") != "1",
-                                 reason="direct-store halo exchange: first hardware run pending (set MOKAB_TEST_P2P=1)")
-
-
-@_P2P_OPT_IN
 @pytest.mark.hw_pending
 @pytest.mark.parametrize("nx,nparts,split,dtype", [(32, 2, True, np.float64), (96, 8, True, np.float64), (64, 3, False, np.float64),
                                                    (48, 4, True, np.float32)])

@@ -162,12 +162,21 @@ def test_rk4_fused_f32(backend):
     m = hex_mesh(64)
     mesh, prog, diag, tend, (ssh, u, h) = _setup(backend, m, dtype=np.float32)
     om = OC.OracleModel(m, ssh, u, h)
-    mb.ocn_run_loop(244.0, prog, diag, tend, None, mb.RungeKutta4, 50)
-    om.run_loop(244.0, 50, "RungeKutta4")
+    mb.ocn_run_loop(244.0, prog, diag, tend, None, mb.RungeKutta4, 60)
+    om.run_loop(244.0, 60, "RungeKutta4")
     assert prog.ssh.dtype == np.float32
-    # ssh = h - 1000 in Float32 carries the ulp of 1000 (6e-5 m); compare the prognostic fields
-    assert rel_l2(prog.normalVelocity, om.normalVelocity[1]) <= 5e-4
-    assert rel_l2(prog.layerThickness, om.layerThickness[1]) <= TOL32
+    # BASELINE.json: SSH and normalVelocity within relative L2 1e-5 of the Float64 reference path in Float32.  The state
+    # carries the perturbation h - H (kernels_fused.cuh: kPert), so ssh keeps the full Float32 significand
+    e_ssh, e_u = rel_l2(prog.ssh, om.ssh[1]), rel_l2(prog.normalVelocity, om.normalVelocity[1])
+    assert e_ssh <= TOL32 and e_u <= TOL32, (e_ssh, e_u)
+    assert rel_l2(prog.layerThickness, om.layerThickness[1]) <= 1e-7       # the whole thickness: one Float32 ulp of 1000 m
+    # previous time level: the state one step earlier, same variable
+    om2 = OC.OracleModel(m, ssh, u, h)
+    om2.run_loop(244.0, 59, "RungeKutta4")
+    assert rel_l2(prog.ssh_prev, om2.ssh[1]) <= TOL32 and rel_l2(prog.normalVelocity_prev, om2.normalVelocity[1]) <= TOL32
+    # mass and energy reductions see the whole thickness
+    mass = mb.reduce_sum(prog, "mass")
+    assert abs(mass - float(np.sum(m["areaCell"] * om.layerThickness[1]))) <= 1e-7 * mass
 
 
 def test_rk4_fused_no_renumbering_matches_renumbered(backend):

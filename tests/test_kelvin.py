@@ -86,3 +86,46 @@ def test_kelvin_decomposed_emulated(backend):
     om = OC.OracleModel(mm, *state)
     om.run_loop(dt, 10, "RungeKutta4")
     assert rel_l2(gu, om.normalVelocity[1]) <= 1e-12 and rel_l2(gh, om.layerThickness[1]) <= 1e-12
+
+
+@pytest.mark.gpu
+def test_kelvin_1024_full_size(backend):
+    """BASELINE.json configs[4] at its stated size: coastal Kelvin wave, 1024x1024 channel mesh with boundary-edge masks.
+    Single-domain fused RK4 and ForwardEuler against the C oracle (bit for bit on this f-plane mesh, i.e. within the 1e-12 of
+    the north star), walls closed, mass conserved."""
+    m, mm, kw = _case(1024)
+    ssh, u, h = kw.initial_state()
+    dt = mb.cfl_dt(m["dc"])
+    mesh = mb.Mesh(m, backend)
+    prog = mb.PrognosticVars(ssh, u, h, 2, mesh)
+    mb.ocn_run_loop(dt, prog, None, None, None, mb.RungeKutta4, 3)
+    om = OC.OracleModel(mm, ssh, u, h)
+    om.run_loop(dt, 3, "RungeKutta4")
+    gu, gs = prog.normalVelocity, prog.ssh
+    assert rel_l2(gu, om.normalVelocity[1]) <= 1e-12 and rel_l2(gs, om.ssh[1]) <= 1e-12
+    assert np.array_equal(gu, om.normalVelocity[1]) and np.array_equal(prog.layerThickness, om.layerThickness[1])
+    assert np.all(gu[m["boundaryEdge"] != 0] == 0.0)
+    mass0 = float(np.sum(m["areaCell"] * h))
+    assert abs(mb.reduce_sum(prog, "mass") - mass0) <= 1e-13 * mass0
+    prog = mb.PrognosticVars(ssh, u, h, 2, mesh)
+    mb.ocn_run_loop(dt, prog, None, None, None, mb.ForwardEuler, 3)
+    om = OC.OracleModel(mm, ssh, u, h)
+    om.run_loop(dt, 3, "ForwardEuler")
+    assert np.array_equal(prog.normalVelocity, om.normalVelocity[1]) and np.array_equal(prog.ssh, om.ssh[1])
+
+
+@pytest.mark.gpu
+def test_kelvin_1024_full_size_eight_ranks(backend):
+    """configs[4], "1 and 8 B200": the same mesh decomposed into 8 parts (ranks emulated on one GPU, messages moved by
+    device copies), packed and direct-store halo exchange, against the single-domain C oracle."""
+    from test_gpu_decomposed import _run_emulated
+    m, mm, kw = _case(1024)
+    state = kw.initial_state()
+    dt = mb.cfl_dt(m["dc"])
+    om = OC.OracleModel(mm, *state)
+    om.run_loop(dt, 2, "RungeKutta4")
+    for halo in ("nccl", "p2p_fused"):
+        gu, gh, gs, ranks = _run_emulated(backend, m, state, 8, dt, 2, halo=halo)
+        assert rel_l2(gu, om.normalVelocity[1]) <= 1e-12 and rel_l2(gs, om.ssh[1]) <= 1e-12, halo
+        assert np.array_equal(gu, om.normalVelocity[1]) and np.array_equal(gh, om.layerThickness[1]), halo
+        del ranks

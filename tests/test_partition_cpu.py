@@ -200,19 +200,6 @@ def test_as_many_parts_as_cells_and_one_more():
         partition.rcb_partition(m["xCell"], m["yCell"], 0)
 
 
-def test_graph_replay_plan_respects_time_level_parity():
-    """multi_gpu.plan_steps: a 2-step graph may only be replayed from the parity it was captured at; any number of steps
-    from any parity is covered exactly once, and the parity after the plan is what the step count implies."""
-    from moka_b200.multi_gpu import plan_steps
-    for graph_parity in (0, 1):
-        for parity in (0, 1):
-            for n in range(2, 12):
-                pre, replays, post = plan_steps(n, parity, graph_parity)
-                assert pre + 2 * replays + post == n and pre in (0, 1) and post in (0, 1) and replays >= 0
-                assert (parity + pre) % 2 == graph_parity or replays == 0      # replays start at the capture parity
-                assert pre == (1 if parity != graph_parity else 0)
-
-
 def _exchange_worker(rank, world, port, out_dir):
     import sys
     here = os.path.dirname(os.path.abspath(__file__))
@@ -221,23 +208,23 @@ def _exchange_worker(rank, world, port, out_dir):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from moka_b200 import multi_gpu
+    # the control plane of a decomposed run: rank 0's 128-byte communicator id reaches every rank, through a process group ...
     rt = multi_gpu.TorchRuntime(0, device="cpu")
-    # rank r sends q the array [100 r + q] * (r + 2 q) (lengths differ per pair, some are empty)
-    send = [np.full((rank + 2 * q) % 4, 100 * rank + q, np.int32) for q in range(world)]
-    recv_counts = [(q + 2 * rank) % 4 for q in range(world)]
-    got = rt.all_to_all_int32(send, recv_counts)
-    blobs = rt.all_gather_bytes(bytes([rank]) * 7)
-    ok = all(np.array_equal(got[q], np.full(recv_counts[q], 100 * q + rank, np.int32)) for q in range(world))
-    ok = ok and blobs == [bytes([q]) * 7 for q in range(world)]
-    ok = ok and rt.all_reduce_min(rank + 5) == 5 and rt.all_reduce_sum(float(rank)) == float(sum(range(world)))
+    blob = bytes(range(128)) if rank == 0 else None
+    ok = rt.broadcast_bytes(blob, 0) == bytes(range(128)) and rt.rank_and_size() == (rank, world)
+    # ... or through a bare TCP store (no process group: what a Julia host would do with MPI.jl or a file)
+    st = multi_gpu.StoreRuntime(rank, world, "127.0.0.1", port + 1)
+    ok = ok and st.broadcast_bytes(bytes([7]) * 128 if rank == 0 else None, 0) == bytes([7]) * 128
+    ok = ok and st.broadcast_bytes(bytes([9]) * 128 if rank == 0 else None, 0) == bytes([9]) * 128 and st.rank_and_size() == (rank, world)
     open(os.path.join(out_dir, f"ok{rank}"), "w").write("1" if ok else "0")
     dist.barrier()
     dist.destroy_process_group()
 
 
 def test_runtime_host_exchanges_over_gloo(tmp_path):
-    """multi_gpu.TorchRuntime's set-up exchanges of the direct-store halo path (who needs which index list, whose blob is
-    whose) and its scalar reductions, on 3 gloo ranks."""
+    """What is left of the host side of a decomposed run -- handing rank 0's communicator id to the others -- on 3 ranks
+    (everything else, the set-up exchanges of the direct-store path included, is inside the library: csrc/decomposed.cuh,
+    exercised with emulated ranks by tests/sim/check_decomposed.py)."""
     import torch.multiprocessing as mp
     world = 3
     mp.spawn(_exchange_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)

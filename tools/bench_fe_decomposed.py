@@ -30,35 +30,32 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--no-overlap", dest="no_overlap", action="store_true")
+    ap.add_argument("--no-graph", dest="no_graph", action="store_true")
     args = ap.parse_args()
     args.dtype = "f64"
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dist.init_process_group("gloo")                              # control plane only; the exchange is NCCL inside the library
     nx = WORKLOADS[args.workload]
     loc, state, t_setup = multi_gpu._share_locals(args, rank, world, nx, np.float64)
     dt = 0.2 * mb.cfl_dt(1.0e7 / nx)
-    model = multi_gpu.DecomposedModel(loc, state, mb.B200(local), local, overlap=not args.no_overlap, graph=False)
+    backend = mb.B200(local)
+    model = multi_gpu.DecomposedModel(loc, state, backend, local, overlap=not args.no_overlap, graph=not args.no_graph,
+                                      runtime=multi_gpu.TorchRuntime(local, device="cpu"))
     model.step(dt, max(args.warmup, 3), stepper=mb.ForwardEuler)
     model.finish()
-    dist.barrier()
+    model.comm.barrier()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(model.compute)
+    backend.timer_start()
     model.step(dt, args.steps, stepper=mb.ForwardEuler)
-    e1.record(model.compute)
-    model.compute.synchronize()
-    model.halo.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=model.dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms = float(model.comm.allreduce(backend.timer_stop(), "max")[0])
     model.finish()
     mass = model.reduce("mass")
     nsend = sum(len(v) for v in loc["halo"]["send"].values())
     if rank == 0:
         print(json.dumps({"metric": "ForwardEuler cell-steps/sec", "value": nx * nx * args.steps / (ms * 1e-3), "unit": "cell-steps/s",
                           "n_gpus": world, "steps": args.steps, "ms_per_step": ms / args.steps, "workload": args.workload,
-                          "overlap": model.overlap, "rank0_halo_bytes_per_step": 2 * 8 * nsend, "setup_s": round(t_setup, 1),
+                          "overlap": model.overlap, "graph": model.use_graph, "rank0_halo_bytes_per_step": 2 * 8 * nsend, "setup_s": round(t_setup, 1),
                           "mass": mass}))
     model.close()
     dist.barrier()
