@@ -82,9 +82,12 @@ enum {
     MOKAB_MESH_EXPLICIT_EOE = 2u,/* always read edgesOnEdge from memory.  Default: the fused kernel rebuilds it from
                                     edgesOnCell wherever the mesh follows the MPAS ordering (verified per edge at
                                     mesh_create, per-block fallback); bit-identical results, 16 % fewer DRAM bytes */
-    MOKAB_MESH_KEEP_WIDTHS = 4u  /* keep device rows as wide as the caller's maxEdges / maxEdges2.  Default: as wide as
+    MOKAB_MESH_KEEP_WIDTHS = 4u, /* keep device rows as wide as the caller's maxEdges / maxEdges2.  Default: as wide as
                                     the longest live row (nEdgesOnCell / nEdgesOnEdge), so padded files of hexagons
                                     still take the compile-time-width kernels */
+    MOKAB_MESH_EDGES_BY_CELL = 8u /* number the edges of a block cell by cell (a cell's edges adjacent).  Default: slot-major
+                                    inside every block (every cell's first owned edge, then every cell's second, ...), so
+                                    that a warp works on one kind of edge of 32 consecutive cells and its gathers coalesce */
 };
 
 /* Host view of the reference mesh structs.  Pointers marked (opt) may be NULL.
@@ -155,6 +158,17 @@ int  mokab_mesh_device_bytes(const mokab_mesh *mesh, int64_t *out);
 /* ---- state: PrognosticVars + DiagnosticVars + TendencyVars on the backend ------------------- */
 /* Zero-initialised (DiagnosticVars.jl:90-93, TendencyVars.jl:61-62); two time levels. */
 int  mokab_state_create(mokab_ctx *ctx, const mokab_mesh *mesh, int dtype, mokab_state **out);
+/* The same with nVertLevels >= 1 levels (VerticalMesh.nVertLevels, VertMesh.jl:3-17): layerThickness / normalVelocity and the
+ * Diag / Tend arrays are the reference's (nVertLevels, n) column-major arrays (level fastest, PrognosticVars.jl:10-16), ssh
+ * stays (nCells).  The reference's kernels carry the level loops (pressure_gradient.jl:61-64, horizontal_advection_and_
+ * coriolis.jl:69-73, horizontal_advection.jl:60-66: one pressure gradient for the column, Coriolis and thickness flux per
+ * level) but its drivers fill level 1 only (DiagnosticVars.jl:158-173, time_integration.jl:205-212); for nVertLevels > 1 the
+ * semantics are project-defined: every level is stepped, ssh = sum over the levels of layerThickness -
+ * restingThicknessSum.  Float64, undecomposed meshes; supported: state set/get, the src/ocn entry points, both steppers
+ * (RungeKutta4 fused -- static data read once per column -- and unfused; ForwardEuler as the reference's kernel sequence),
+ * mokab_reduce.  Not supported: the reverse mode, the staged / decomposed entry points. */
+int  mokab_state_create_levels(mokab_ctx *ctx, const mokab_mesh *mesh, int dtype, int nVertLevels, mokab_state **out);
+int  mokab_state_levels(const mokab_state *state, int *nVertLevels);
 int  mokab_state_destroy(mokab_state *state);
 /* Host arrays hold the state's dtype, caller numbering.  Setting MOKAB_LAYER_THICKNESS does NOT touch
  * ssh (the reference reads both from file, PrognosticVars.jl:85-99).  `set` of a time-level-`end`

@@ -115,7 +115,25 @@ struct StageArgs {
 // resident blocks per SM of the edgesOnEdge-rebuilding variant: Float64 needs 64 registers to hold the ten weights
 // across the index reconstruction without spilling (4 blocks), Float32 fits in 48 (5 blocks) -- measured r01h:
 // F64 2.81 / 2.49 / 2.09 G cell-steps/s at 4 / 5 / 6 blocks, F32 3.62 / 4.05 / 3.83
-template <class R> constexpr int der_minblocks() { return sizeof(R) == 8 ? 4 : 5; }
+#ifndef MOKAB_DER_MINBLOCKS_F64
+#define MOKAB_DER_MINBLOCKS_F64 4
+#endif
+#ifndef MOKAB_DER_MINBLOCKS_F32
+#define MOKAB_DER_MINBLOCKS_F32 5
+#endif
+template <class R> constexpr int der_minblocks() { return sizeof(R) == 8 ? MOKAB_DER_MINBLOCKS_F64 : MOKAB_DER_MINBLOCKS_F32; }
+// resident blocks of kThreads threads the stage kernel is compiled for (MOKAB_DER_RAW_BLOCKS_*: tuning builds that want a
+// count the 256-thread scale cannot express, e.g. nine blocks of 128 threads)
+template <class R, bool DER, int TMA> constexpr int stage_blocks()
+{
+#ifdef MOKAB_DER_RAW_BLOCKS_F64
+    if (DER && TMA == 0 && sizeof(R) == 8) return MOKAB_DER_RAW_BLOCKS_F64;
+#endif
+#ifdef MOKAB_DER_RAW_BLOCKS_F32
+    if (DER && TMA == 0 && sizeof(R) == 4) return MOKAB_DER_RAW_BLOCKS_F32;
+#endif
+    return MOKAB_BLOCKS_SCALED(TMA != 0 ? 3 : DER ? der_minblocks<R>() : MOKAB_MINBLOCKS);
+}
 // TMA = 1 (opt-in, MOKAB_STAGE_TMA=1; compile-time row widths only): the Coriolis weights of the block's edges -- ten
 // contiguous runs, 80 of the ~160 streamed bytes per edge in Float64 -- are fetched by ONE thread with bulk asynchronous copies
 // (cp.async.bulk, the 1-D TMA path) into shared memory behind an mbarrier, at the very top of the kernel; the threads meanwhile
@@ -133,7 +151,7 @@ template <class R> __host__ __device__ constexpr int tma_align() { return 16 / (
 #endif
 
 template <class R, int STAGE, int S2T, int ST, bool FOLD, bool DER, bool PUSH = false, int TMA = 0>
-__global__ void __launch_bounds__(kThreads, MOKAB_BLOCKS_SCALED(TMA != 0 ? 3 : DER ? der_minblocks<R>() : MOKAB_MINBLOCKS))
+__global__ void __launch_bounds__(kThreads, (stage_blocks<R, DER, TMA>()))
 k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
 {
     const int S2 = S2T ? S2T : S2rt;
@@ -287,8 +305,19 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
                 for (int i = 0; i < S2T; ++i) idx[i] = ld_stream(A.eoe + (size_t)i * nE + e);
             }
             if constexpr (TMA == 0) {
+#ifdef MOKAB_ENABLE_WF_BLOCK_MAJOR   // tuning build (libmoka_b200_wfb.so; the run-time branch costs the default kernel a spill)
+                if (A.wfB) {    // "stage_wf_block_major": the block's S2T weight rows back to back (one contiguous ~60 KB run per block)
+                    constexpr int AL = tma_align<R>();
+                    const int nbp = (e1 - e0 + AL - 1) / AL * AL;
+                    const R *wb = A.wfB + A.wfBOff[b] + (e - e0);
 #pragma unroll
-                for (int i = 0; i < S2T; ++i) w[i] = ld_stream(A.wf + (size_t)i * nE + e);
+                    for (int i = 0; i < S2T; ++i) w[i] = ld_stream(wb + (size_t)i * nbp);
+                } else
+#endif
+                {
+#pragma unroll
+                    for (int i = 0; i < S2T; ++i) w[i] = ld_stream(A.wf + (size_t)i * nE + e);
+                }
             }
             const R g = ld_stream(A.gdc + e);
             // the RK operands are independent of the tendency: issue their loads now (they may alias the stores
@@ -451,6 +480,108 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
                 for (int i = 0; i < P.nrecv; ++i) p2p::add_system(P.arrivalAt[i], 1ull);
             }
         }
+    }
+}
+
+// ---- fused RungeKutta4 stage for MULTI-LEVEL states (nVertLevels = K > 1) ------------------------------------------------
+// The reference's kernels carry `for k in 1:maxLevelEdgeTop[iEdge]` (pressure_gradient.jl:61-64, horizontal_advection_and_
+// coriolis.jl:69-73, horizontal_advection.jl:60-66) around arithmetic that is independent per level except for the free
+// surface: one pressure gradient, -g/dc (ssh2 - ssh1), for the whole column.  State arrays are level-major (every level a
+// contiguous array over the entities), so a thread loads its edge's / cell's connectivity, weights and metrics ONCE and walks
+// the column with them in registers: the static bytes -- 355 of the 483 B a single-level stage moves per cell -- are
+// amortised over K levels (K = 10: 1 635 B per cell and stage for ten levels, 164 B per level).  ssh of a provisional state is
+// produced by the cell phase of the stage that writes it (sshOut = (h[0] + h[1] + ...) - H, level order; project-defined for
+// K > 1) and gathered by the next stage's edge phase; with K = 1 every value equals the single-level
+// kernel's bit for bit (tested).  Float64, explicit edgesOnEdge, whole mesh (no halo parts).
+struct StageArgsML {
+    int nE, nC, K;
+    const int2 *ce;
+    const int32_t *eoe;      // (S2, nE) absent -> self
+    const int32_t *eoc;      // (S, nC)  (edge << 1) | (sign > 0)
+    const uint8_t *nEoE, *nEoC;
+    const int32_t *blkEdgeStart;
+    const double *gdc, *wf, *dv, *invArea, *H;
+    const double *uOld, *hOld, *sshOld;   // provisional state the tendencies are evaluated at (K levels; ssh one)
+    const double *uCur, *hCur;            // state at the start of the step
+    double *uAcc, *hAcc;                  // accumulator == the other time level
+    double *uOut, *hOut, *sshOut;         // next provisional state (stages 1-3); stage 4: sshOut = ssh of the new state
+    double a, b, f0;
+};
+
+template <int STAGE, int S2T, int ST, bool FOLD>
+__global__ void __launch_bounds__(kThreads, MOKAB_BLOCKS_SCALED(3))
+k_rk_stage_ml(const StageArgsML A, int S2rt, int Srt)
+{
+    const int S2 = S2T ? S2T : S2rt, S = ST ? ST : Srt;
+    const int nE = A.nE, nC = A.nC, K = A.K;
+    const int b = blockIdx.x;
+    constexpr int MAXS2 = S2T ? S2T : 32, MAXS = ST ? ST : 16;       // mesh_create admits maxEdges2 <= 32, maxEdges <= 16
+    const int e0 = A.blkEdgeStart[b], e1 = A.blkEdgeStart[b + 1];
+    for (int e = e0 + threadIdx.x; e < e1; e += kThreads) {
+        const int2 c = ld_stream(A.ce + e);
+        int idx[MAXS2];
+        double w[MAXS2];
+        const int n = S2T ? S2T : (int)ld_stream(A.nEoE + e);
+#pragma unroll
+        for (int i = 0; i < MAXS2; ++i)
+            if (i < S2) { idx[i] = ld_stream(A.eoe + (size_t)i * nE + e); w[i] = ld_stream(A.wf + (size_t)i * nE + e); }
+        const double g = ld_stream(A.gdc + e);
+        // one pressure gradient for the column: 0 - (g/dc) (ssh2 - ssh1)   (pressure_gradient.jl:63)
+        const double p = -mul_rn(g, add_rn(__ldg(A.sshOld + c.y), -__ldg(A.sshOld + c.x)));
+        for (int k = 0; k < K; ++k) {
+            const size_t o = (size_t)k * nE;
+            double t = p;
+#pragma unroll
+            for (int i = 0; i < MAXS2; ++i)
+                if (i < n) {
+                    const double wu = mul_rn(w[i], __ldg(A.uOld + o + idx[i]));
+                    t = add_rn(t, FOLD ? wu : mul_rn(wu, A.f0));
+                }
+            const double cur = (STAGE == 4) ? 0.0 : A.uCur[o + e];
+            const double accIn = (STAGE == 1) ? 0.0 : A.uAcc[o + e];
+            if (STAGE != 4) A.uOut[o + e] = add_rn(cur, mul_rn(A.a, t));
+            if (STAGE == 1) A.uAcc[o + e] = add_rn(cur, mul_rn(A.b, t));
+            else            A.uAcc[o + e] = add_rn(accIn, mul_rn(A.b, t));
+        }
+    }
+    const int cc = b * kTC + threadIdx.x;
+    if (cc < nC) {
+        const int n = ld_stream(A.nEoC + cc);
+        int ed[MAXS], other[MAXS];
+        double dd[MAXS];
+        bool pos[MAXS];
+#pragma unroll
+        for (int i = 0; i < MAXS; ++i)
+            if (i < S) {
+                const int ex = i < n ? ld_stream(A.eoc + (size_t)i * nC + cc) : -1;
+                ed[i] = ex >= 0 ? (ex >> 1) : 0;
+                pos[i] = ex >= 0 && (ex & 1);
+                const int2 cs = __ldg(A.ce + ed[i]);
+                other[i] = cs.x == cc ? cs.y : cs.x;
+                dd[i] = __ldg(A.dv + ed[i]);
+            }
+        const double invA = ld_stream(A.invArea + cc);
+        double col = 0.0;
+        for (int k = 0; k < K; ++k) {
+            const size_t oe = (size_t)k * nE, oc = (size_t)k * nC;
+            const double hc = __ldg(A.hOld + oc + cc);
+            double acc = 0.0;
+#pragma unroll
+            for (int i = 0; i < MAXS; ++i)
+                if (i < n) {
+                    const double f = mul_rn(mul_rn(mul_rn(__ldg(A.uOld + oe + ed[i]), mul_rn(0.5, add_rn(hc, __ldg(A.hOld + oc + other[i])))), dd[i]), invA);
+                    acc = add_rn(acc, pos[i] ? f : -f);
+                }
+            const double cur = (STAGE == 4) ? 0.0 : A.hCur[oc + cc];
+            const double accIn = (STAGE == 1) ? 0.0 : A.hAcc[oc + cc];
+            const double out = add_rn(cur, mul_rn(A.a, acc));
+            const double accOut = (STAGE == 1) ? add_rn(cur, mul_rn(A.b, acc)) : add_rn(accIn, mul_rn(A.b, acc));
+            if (STAGE != 4) A.hOut[oc + cc] = out;
+            A.hAcc[oc + cc] = accOut;
+            const double v = (STAGE != 4) ? out : accOut;            // the thickness whose free surface the next stage / the caller reads
+            col = k == 0 ? v : add_rn(col, v);
+        }
+        A.sshOut[cc] = add_rn(col, -ld_stream(A.H + cc));
     }
 }
 
@@ -644,13 +775,15 @@ __device__ __forceinline__ double block_sum(double v)
 // which: 0 sum ssh^2 ; 1 sum area*h ; 2 potential energy sum area*g/2*ssh^2
 template <class R>
 __global__ void __launch_bounds__(kThreads)
-k_cells(int which, int64_t nC, const R *__restrict__ h, const R *__restrict__ H, const double *__restrict__ area,
+k_cells(int which, int64_t nC, int K, int64_t stride, const R *__restrict__ h, const R *__restrict__ H, const double *__restrict__ area,
         double *__restrict__ partial)
 {
     double s = 0.0;
     for (int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x; c < nC; c += (int64_t)kBlocks * kThreads) {
-        const double ssh = fused::kPert<R> ? (double)h[c] : (double)(h[c] - H[c]);
-        const double htot = fused::kPert<R> ? (double)H[c] + (double)h[c] : (double)h[c];
+        R col = h[c];
+        for (int k = 1; k < K; ++k) col += h[(int64_t)k * stride + c];      // the whole column (K levels, level-major)
+        const double ssh = fused::kPert<R> ? (double)col : (double)(col - H[c]);
+        const double htot = fused::kPert<R> ? (double)H[c] + (double)col : (double)col;
         if (which == 0) s += ssh * ssh;
         else if (which == 1) s += area[c] * htot;
         else s += area[c] * (0.5 * 9.80616) * ssh * ssh;
@@ -662,16 +795,19 @@ k_cells(int which, int64_t nC, const R *__restrict__ h, const R *__restrict__ H,
 // kinetic energy sum_e (dc*dv/2) * hEdge * u^2
 template <class R>
 __global__ void __launch_bounds__(kThreads)
-k_edges_ke(int64_t nE, const int2 *__restrict__ ce, const double *__restrict__ dc, const double *__restrict__ dv,
-           const R *__restrict__ u, const R *__restrict__ h, const R *__restrict__ H, double *__restrict__ partial)
+k_edges_ke(int64_t nE, int K, int64_t strideE, int64_t strideC, const int2 *__restrict__ ce, const double *__restrict__ dc,
+           const double *__restrict__ dv, const R *__restrict__ u, const R *__restrict__ h, const R *__restrict__ H,
+           double *__restrict__ partial)
 {
     double s = 0.0;
     for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < nE; e += (int64_t)kBlocks * kThreads) {
         const int2 c = ce[e];
-        double he = 0.5 * ((double)h[c.x] + (double)h[c.y]);
-        if (fused::kPert<R>) he += 0.5 * ((double)H[c.x] + (double)H[c.y]);
-        const double ue = (double)u[e];
-        s += 0.5 * dc[e] * dv[e] * he * ue * ue;
+        for (int k = 0; k < K; ++k) {
+            double he = 0.5 * ((double)h[(int64_t)k * strideC + c.x] + (double)h[(int64_t)k * strideC + c.y]);
+            if (fused::kPert<R>) he += 0.5 * ((double)H[c.x] + (double)H[c.y]);
+            const double ue = (double)u[(int64_t)k * strideE + e];
+            s += 0.5 * dc[e] * dv[e] * he * ue * ue;
+        }
     }
     s = block_sum(s);
     if (threadIdx.x == 0) partial[blockIdx.x] += s;

@@ -170,6 +170,37 @@ k_permute_out(int64_t n, const int32_t *__restrict__ perm, const R *__restrict__
     if (j < n) dst[perm[j]] = src[j];
 }
 
+// Multi-level fields: the caller's arrays are the reference's (nVertLevels, n) column-major arrays (level fastest,
+// PrognosticVars.jl:10-16), the device keeps every level as one contiguous array over the (renumbered) entities
+template <class R>
+__global__ void __launch_bounds__(256)
+k_permute_in_lv(int64_t n, int K, const int32_t *__restrict__ perm, const R *__restrict__ src, R *__restrict__ dst)
+{
+    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (j >= n) return;
+    const R *col = src + (int64_t)K * perm[j];
+    for (int k = 0; k < K; ++k) dst[(int64_t)k * n + j] = col[k];
+}
+template <class R>
+__global__ void __launch_bounds__(256)
+k_permute_out_lv(int64_t n, int K, const int32_t *__restrict__ perm, const R *__restrict__ src, R *__restrict__ dst)
+{
+    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (j >= n) return;
+    R *col = dst + (int64_t)K * perm[j];
+    for (int k = 0; k < K; ++k) col[k] = src[(int64_t)k * n + j];
+}
+// Update_ssh! for a column of K levels (project-defined for K > 1): ssh = (h[0] + h[1] + ...) - restingThicknessSum
+__global__ void __launch_bounds__(256)
+k_update_ssh_lv(int64_t n, int K, const double *__restrict__ h, const double *__restrict__ H, double *__restrict__ ssh)
+{
+    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (j >= n) return;
+    double col = h[j];
+    for (int k = 1; k < K; ++k) col = __dadd_rn(col, h[(int64_t)k * n + j]);
+    ssh[j] = __dadd_rn(col, -H[j]);
+}
+
 // Float32 states: layerThickness crosses the boundary as the whole thickness, the device arrays hold h - H (kernels_fused.cuh: kPert)
 __global__ void __launch_bounds__(256)
 k_permute_in_pert(int64_t n, const int32_t *__restrict__ perm, const float *__restrict__ src, const double *__restrict__ H, float *__restrict__ dst)

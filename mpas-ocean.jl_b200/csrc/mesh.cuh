@@ -195,6 +195,35 @@ static void build_host_mesh(const mokab_mesh_desc &d, uint32_t flags, HostMesh &
             int64_t pos = start[bucket(e)]++;
             m.permE[pos] = (int32_t)e;
         }
+        // ... then, inside every block of kBlockCells cells, SLOT-MAJOR: first the first edge every cell of the block owns
+        // (in the order of its edgesOnCell row), then every cell's second edge, ...  Thread t of the fused kernels handles
+        // edge blkEdgeStart + t + k * blockDim in its k-th iteration, so a warp now works on the SAME kind of edge of 32
+        // consecutive cells (on a hexagon mesh: 32 east edges, then 32 north-east edges, ...): the neighbour edges and cells
+        // it gathers are then consecutive too -- the ten normalVelocity gathers of the Coriolis sum, the edgesOnCell rows
+        // the edgesOnEdge rebuild reads, and the per-slot gathers of the cell phase all become (nearly) coalesced, instead
+        // of striding by the three edges a cell owns.  ncu (profiles/README.md, r02a): the stage kernel ran at 71 % of the L1
+        // data-pipe wavefront limit against 66 % of DRAM, i.e. it was paying for scattered gathers, not for bytes.
+        if (!(flags & MOKAB_MESH_EDGES_BY_CELL)) {
+            std::vector<uint8_t> rank(nE, 0);
+#pragma omp parallel for schedule(static)
+            for (int64_t co = 0; co < nCo; ++co) {
+                int r = 0;
+                const int n = std::min<int>(d.nEdgesOnCell[co], Sf);
+                for (int i = 0; i < n; ++i) {
+                    const int64_t e = (int64_t)d.edgesOnCell[(int64_t)Sf * co + i] - 1;
+                    if (e >= 0 && e < nE && d.cellsOnEdge[2 * e] == (int32_t)(co + 1)) rank[e] = (uint8_t)(r++);
+                }
+            }
+            const int64_t nblocks = (nCo + kBlockCells - 1) / kBlockCells;
+#pragma omp parallel for schedule(dynamic, 64)
+            for (int64_t b = 0; b < nblocks; ++b) {
+                // the block's edges are the contiguous run of the cell-sorted order whose owner lies in the block
+                const int64_t c0 = b * kBlockCells, c1 = std::min<int64_t>(nCo, c0 + kBlockCells);
+                const int64_t e0 = c0 == 0 ? 0 : start[c0 - 1], e1 = start[c1 - 1];
+                std::stable_sort(m.permE.begin() + e0, m.permE.begin() + e1,
+                                 [&](int32_t a, int32_t bb) { return rank[a] < rank[bb]; });
+            }
+        }
         for (int64_t i = 0; i < nE; ++i) invE[m.permE[i]] = (int32_t)i;
     }
     // ---- vertex permutation: by the smallest new edge id on the vertex ------------------------------

@@ -33,6 +33,7 @@ struct StateT {
     DevBuf<R> u[2], h[2], ssh[2];          // two time levels; `cur` holds Prog.*[end]  (u, h: views into the slab)
     DevBuf<R> uP[2], hP[2];                // RK provisional ping-pong (views into the slab)
     DevBuf<R> hEdge, flux, divC, relVort, tendU, tendH, sshProv;
+    DevBuf<R> sshP[2];                     // multi-level fused RK4: ssh of the two provisional states (uP / hP)
     DevBuf<R> hE[2];                       // fused ForwardEuler: layerThicknessEdge ping-pong, indexed like the time levels
     DevBuf<R> staging;
     DevBuf<double> partial, result;
@@ -95,6 +96,7 @@ struct mokab_state {
     mokab_ctx *ctx = nullptr;
     const mokab_mesh *mesh = nullptr;
     int dtype = MOKAB_F64;
+    int K = 1;    // nVertLevels: layerThickness / normalVelocity (and the Diag / Tend arrays) hold K levels, level-major on the device
     int cur = 1;  // index of the time level holding Prog.*[end]
     // fused ForwardEuler leaves thicknessFlux / velocityDivCell / tend* / layerThicknessEdge to be re-created on demand
     // from the previous time level and hE[] (fe_materialize); true while those arrays are stale
@@ -231,34 +233,37 @@ static void alloc_state(mokab_state *st)
     if (sizeof(R) == 8) st->d = (StateT<double> *)(void *)t; else st->f = (StateT<float> *)(void *)t;
     {
         auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
-        const size_t eb = pad((size_t)m->nE * sizeof(R)), cb = pad((size_t)m->nC * sizeof(R));
+        const size_t K = (size_t)st->K;
+        const size_t eb = pad(K * m->nE * sizeof(R)), cb = pad(K * m->nC * sizeof(R));
         size_t off = 0;
         for (int i = 0; i < 4; ++i) { t->slabOff[i] = off; off += eb; }
         for (int i = 4; i < 8; ++i) { t->slabOff[i] = off; off += cb; }
         t->slabOff[8] = off; off += pad((size_t)kP2PCounters * sizeof(unsigned long long));
         t->slab.alloc(off); t->slab.zero(s);
         unsigned char *b = t->slab.p;
-        t->u[0].view((R *)(b + t->slabOff[0]), m->nE); t->u[1].view((R *)(b + t->slabOff[1]), m->nE);
-        t->uP[0].view((R *)(b + t->slabOff[2]), m->nE); t->uP[1].view((R *)(b + t->slabOff[3]), m->nE);
-        t->h[0].view((R *)(b + t->slabOff[4]), m->nC); t->h[1].view((R *)(b + t->slabOff[5]), m->nC);
-        t->hP[0].view((R *)(b + t->slabOff[6]), m->nC); t->hP[1].view((R *)(b + t->slabOff[7]), m->nC);
+        t->u[0].view((R *)(b + t->slabOff[0]), K * m->nE); t->u[1].view((R *)(b + t->slabOff[1]), K * m->nE);
+        t->uP[0].view((R *)(b + t->slabOff[2]), K * m->nE); t->uP[1].view((R *)(b + t->slabOff[3]), K * m->nE);
+        t->h[0].view((R *)(b + t->slabOff[4]), K * m->nC); t->h[1].view((R *)(b + t->slabOff[5]), K * m->nC);
+        t->hP[0].view((R *)(b + t->slabOff[6]), K * m->nC); t->hP[1].view((R *)(b + t->slabOff[7]), K * m->nC);
     }
+    const size_t K = (size_t)st->K;
     for (int l = 0; l < 2; ++l) { t->ssh[l].alloc(m->nC); t->ssh[l].zero(s); }
-    t->hEdge.alloc(m->nE); t->hEdge.zero(s);      // DiagnosticVars.jl:90-93
-    t->flux.alloc(m->nE); t->flux.zero(s);
-    t->divC.alloc(m->nC); t->divC.zero(s);
-    t->relVort.alloc(std::max<int64_t>(m->nV, 1)); t->relVort.zero(s);
-    t->tendU.alloc(m->nE); t->tendU.zero(s);      // TendencyVars.jl:61-62
-    t->tendH.alloc(m->nC); t->tendH.zero(s);
+    t->hEdge.alloc(K * m->nE); t->hEdge.zero(s);      // DiagnosticVars.jl:90-93
+    t->flux.alloc(K * m->nE); t->flux.zero(s);
+    t->divC.alloc(K * m->nC); t->divC.zero(s);
+    t->relVort.alloc(K * std::max<int64_t>(m->nV, 1)); t->relVort.zero(s);
+    t->tendU.alloc(K * m->nE); t->tendU.zero(s);      // TendencyVars.jl:61-62
+    t->tendH.alloc(K * m->nC); t->tendH.zero(s);
     t->sshProv.alloc(m->nC); t->sshProv.zero(s);
-    t->staging.alloc(std::max(std::max(m->nE, m->nC), std::max<int64_t>(m->nV, 1)));
+    if (K > 1) for (int l = 0; l < 2; ++l) { t->sshP[l].alloc(m->nC); t->sshP[l].zero(s); }
+    t->staging.alloc(K * std::max(std::max(m->nE, m->nC), std::max<int64_t>(m->nV, 1)));
     t->partial.alloc(reduce::kBlocks); t->result.alloc(1);
     MOKAB_CUDA(cudaStreamSynchronize(s));
 }
 
 // pert: a Float32 layerThickness -- the caller sees the whole thickness, the device array holds h - H (kernels_fused.cuh: kPert);
 // alias: Float32 ssh -- the same perturbation is the prognostic variable of the fused path, a `set` also writes it there
-struct FieldRef { void *p; int64_t n; const int32_t *perm; bool prognostic_end; int prev_of; bool pert = false; void *alias = nullptr; };
+struct FieldRef { void *p; int64_t n; const int32_t *perm; bool prognostic_end; int prev_of; bool pert = false; void *alias = nullptr; int levels = 1; };
 
 // shadow state d_Prog (ocn_init_shadows, reference src/forward/init.jl:32-40): zeros
 template <class R>
@@ -278,8 +283,18 @@ static void ensure_adj_state(mokab_state *st)
     t->adj_ready = true;
 }
 
+template <class R> static FieldRef field_ref1(mokab_state *st, int field);
+// a field as the caller sees it: `n` entities x `levels` levels (ssh and its shadow have one level whatever nVertLevels is)
 template <class R>
 static FieldRef field_ref(mokab_state *st, int field)
+{
+    FieldRef f = field_ref1<R>(st, field);
+    const bool single = field == MOKAB_SSH || field == MOKAB_SSH_PREV || field == MOKAB_D_SSH;
+    f.levels = single ? 1 : st->K;
+    return f;
+}
+template <class R>
+static FieldRef field_ref1(mokab_state *st, int field)
 {
     StateT<R> *t = typed<R>(st);
     const mokab_mesh *m = st->mesh;
@@ -316,7 +331,8 @@ static void launch_permute_in(mokab_state *st, const FieldRef &f, const R *src)
             return;
         }
     }
-    LAUNCH(ctx, k_permute_in<R>, nblk(f.n), 256, f.n, f.perm, src, (R *)f.p);
+    if (f.levels > 1) LAUNCH(ctx, k_permute_in_lv<R>, nblk(f.n), 256, f.n, f.levels, f.perm, src, (R *)f.p);
+    else LAUNCH(ctx, k_permute_in<R>, nblk(f.n), 256, f.n, f.perm, src, (R *)f.p);
     if (f.alias) MOKAB_CUDA(cudaMemcpyAsync(f.alias, f.p, f.n * sizeof(R), cudaMemcpyDeviceToDevice, ctx->stream));
 }
 template <class R>
@@ -329,7 +345,8 @@ static void launch_permute_out(mokab_state *st, const FieldRef &f, R *dst)
             return;
         }
     }
-    LAUNCH(ctx, k_permute_out<R>, nblk(f.n), 256, f.n, f.perm, (const R *)f.p, dst);
+    if (f.levels > 1) LAUNCH(ctx, k_permute_out_lv<R>, nblk(f.n), 256, f.n, f.levels, f.perm, (const R *)f.p, dst);
+    else LAUNCH(ctx, k_permute_out<R>, nblk(f.n), 256, f.n, f.perm, (const R *)f.p, dst);
 }
 
 template <class R>
@@ -339,11 +356,11 @@ static void state_set(mokab_state *st, int field, const void *host)
     StateT<R> *t = typed<R>(st);
     FieldRef f = field_ref<R>(st, field);
     if (f.n == 0) return;
-    MOKAB_CUDA(cudaMemcpyAsync(t->staging.p, host, f.n * sizeof(R), cudaMemcpyHostToDevice, ctx->stream));
+    MOKAB_CUDA(cudaMemcpyAsync(t->staging.p, host, f.n * f.levels * sizeof(R), cudaMemcpyHostToDevice, ctx->stream));
     launch_permute_in<R>(st, f, (const R *)t->staging.p);
     if (f.prognostic_end) {  // deepcopy into every time level, PrognosticVars.jl:49-53
         FieldRef prev = field_ref<R>(st, field + 3);
-        MOKAB_CUDA(cudaMemcpyAsync(prev.p, f.p, f.n * sizeof(R), cudaMemcpyDeviceToDevice, ctx->stream));
+        MOKAB_CUDA(cudaMemcpyAsync(prev.p, f.p, f.n * f.levels * sizeof(R), cudaMemcpyDeviceToDevice, ctx->stream));
         if (prev.alias) MOKAB_CUDA(cudaMemcpyAsync(prev.alias, f.p, f.n * sizeof(R), cudaMemcpyDeviceToDevice, ctx->stream));
     }
     MOKAB_CUDA(cudaStreamSynchronize(ctx->stream));  // the caller may reuse `host` immediately
@@ -357,7 +374,7 @@ static void state_get(mokab_state *st, int field, void *host)
     FieldRef f = field_ref<R>(st, field);
     if (f.n == 0) return;
     launch_permute_out<R>(st, f, (R *)t->staging.p);
-    MOKAB_CUDA(cudaMemcpyAsync(host, t->staging.p, f.n * sizeof(R), cudaMemcpyDeviceToHost, ctx->stream));
+    MOKAB_CUDA(cudaMemcpyAsync(host, t->staging.p, f.n * f.levels * sizeof(R), cudaMemcpyDeviceToHost, ctx->stream));
     MOKAB_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
@@ -372,7 +389,7 @@ static void ensure_async(mokab_state *st)
     StateT<R> *t = typed<R>(st);
     if (t->async_ready) return;
     const mokab_mesh *m = st->mesh;
-    const size_t nmax = (size_t)std::max(std::max(m->nE, m->nC), std::max<int64_t>(m->nV, 1));
+    const size_t nmax = (size_t)st->K * (size_t)std::max(std::max(m->nE, m->nC), std::max<int64_t>(m->nV, 1));
     MOKAB_CUDA(cudaStreamCreateWithFlags(&t->h2d, cudaStreamNonBlocking));
     MOKAB_CUDA(cudaStreamCreateWithFlags(&t->d2h, cudaStreamNonBlocking));
     for (int i = 0; i < StateT<R>::kInSlots; ++i) {
@@ -399,7 +416,7 @@ static void state_set_async(mokab_state *st, int field, const void *host)
     const int slot = t->inSlot;
     t->inSlot = (slot + 1) % StateT<R>::kInSlots;
     MOKAB_CUDA(cudaStreamWaitEvent(t->h2d, t->evInFree[slot], 0));      // the slot's previous permute has run
-    MOKAB_CUDA(cudaMemcpyAsync(t->stIn[slot].p, host, f.n * sizeof(R), cudaMemcpyHostToDevice, t->h2d));
+    MOKAB_CUDA(cudaMemcpyAsync(t->stIn[slot].p, host, f.n * f.levels * sizeof(R), cudaMemcpyHostToDevice, t->h2d));
     MOKAB_CUDA(cudaEventRecord(t->evInCopied[slot], t->h2d));
     MOKAB_CUDA(cudaStreamWaitEvent(ctx->stream, t->evInCopied[slot], 0));
     launch_permute_in<R>(st, f, (const R *)t->stIn[slot].p);
@@ -420,7 +437,7 @@ static void state_get_async(mokab_state *st, int field, void *host)
     launch_permute_out<R>(st, f, (R *)t->stOut[slot].p);
     MOKAB_CUDA(cudaEventRecord(t->evOutReady[slot], ctx->stream));
     MOKAB_CUDA(cudaStreamWaitEvent(t->d2h, t->evOutReady[slot], 0));
-    MOKAB_CUDA(cudaMemcpyAsync(host, t->stOut[slot].p, f.n * sizeof(R), cudaMemcpyDeviceToHost, t->d2h));
+    MOKAB_CUDA(cudaMemcpyAsync(host, t->stOut[slot].p, f.n * f.levels * sizeof(R), cudaMemcpyDeviceToHost, t->d2h));
     MOKAB_CUDA(cudaEventRecord(t->evOutCopied[slot], t->d2h));
 }
 
@@ -441,15 +458,20 @@ static void require_f64(mokab_state *st, const char *what)
                                       "Float32 states support mokab_timestep_rk4(MOKAB_RK4_FUSED), set/get and reduce");
 }
 
+// Multi-level states (K > 1): every level is a contiguous array over the entities, and the reference's kernels treat the levels
+// independently (their `k` loops, e.g. Operators.jl:15,29), so the reference-order sequences below run level by level.
 static void diag_compute(mokab_state *st, const double *u, const double *h)
 {
     mokab_ctx *ctx = st->ctx; const mokab_mesh *m = st->mesh; StateT<double> *t = st->d;
-    LAUNCH(ctx, ref::k_diag_edges, nblk(m->nE), 256, (int)m->nE, m->ce.p, u, h, t->hEdge.p, t->flux.p);
-    LAUNCH(ctx, ref::k_divergence_on_cell, nblk(m->nC), 256, (int)m->nC, m->eoc.p, m->sgnC.p, m->nEoC.p, m->area.p, m->dv.p, u,
-           t->divC.p);
-    if (m->nV)
-        LAUNCH(ctx, ref::k_curl_on_vertex, nblk(m->nV), 256, (int)m->nV, m->D, m->eov.p, m->sgnV.p, m->areaTri.p, m->dc.p, u,
-               t->relVort.p);
+    for (int64_t k = 0; k < st->K; ++k) {
+        const double *uk = u + k * m->nE, *hk = h + k * m->nC;
+        LAUNCH(ctx, ref::k_diag_edges, nblk(m->nE), 256, (int)m->nE, m->ce.p, uk, hk, t->hEdge.p + k * m->nE, t->flux.p + k * m->nE);
+        LAUNCH(ctx, ref::k_divergence_on_cell, nblk(m->nC), 256, (int)m->nC, m->eoc.p, m->sgnC.p, m->nEoC.p, m->area.p, m->dv.p, uk,
+               t->divC.p + k * m->nC);
+        if (m->nV)
+            LAUNCH(ctx, ref::k_curl_on_vertex, nblk(m->nV), 256, (int)m->nV, m->D, m->eov.p, m->sgnV.p, m->areaTri.p, m->dc.p, uk,
+                   t->relVort.p + k * m->nV);
+    }
 }
 
 // Diagnostics of the given state taken at face value: hEdge and flux of the SAME state (no lag) and relativeVorticity
@@ -457,29 +479,44 @@ static void diag_compute(mokab_state *st, const double *u, const double *h)
 static void diag_consistent(mokab_state *st, const double *u, const double *h)
 {
     mokab_ctx *ctx = st->ctx; const mokab_mesh *m = st->mesh; StateT<double> *t = st->d;
-    LAUNCH(ctx, ref::k_interpolate_cell2edge, nblk(m->nE), 256, (int)m->nE, m->ce.p, h, t->hEdge.p);
-    LAUNCH(ctx, ref::k_mul, nblk(m->nE), 256, m->nE, u, (const double *)t->hEdge.p, t->flux.p);
-    LAUNCH(ctx, ref::k_divergence_on_cell, nblk(m->nC), 256, (int)m->nC, m->eoc.p, m->sgnC.p, m->nEoC.p, m->area.p, m->dv.p, u,
-           t->divC.p);
-    if (m->nV) {
-        t->relVort.zero(ctx->stream);
-        LAUNCH(ctx, ref::k_curl_on_vertex, nblk(m->nV), 256, (int)m->nV, m->D, m->eov.p, m->sgnV.p, m->areaTri.p, m->dc.p, u,
-               t->relVort.p);
+    if (m->nV) t->relVort.zero(ctx->stream);
+    for (int64_t k = 0; k < st->K; ++k) {
+        const double *uk = u + k * m->nE;
+        LAUNCH(ctx, ref::k_interpolate_cell2edge, nblk(m->nE), 256, (int)m->nE, m->ce.p, h + k * m->nC, t->hEdge.p + k * m->nE);
+        LAUNCH(ctx, ref::k_mul, nblk(m->nE), 256, m->nE, uk, (const double *)(t->hEdge.p + k * m->nE), t->flux.p + k * m->nE);
+        LAUNCH(ctx, ref::k_divergence_on_cell, nblk(m->nC), 256, (int)m->nC, m->eoc.p, m->sgnC.p, m->nEoC.p, m->area.p, m->dv.p, uk,
+               t->divC.p + k * m->nC);
+        if (m->nV)
+            LAUNCH(ctx, ref::k_curl_on_vertex, nblk(m->nV), 256, (int)m->nV, m->D, m->eov.p, m->sgnV.p, m->areaTri.p, m->dc.p, uk,
+                   t->relVort.p + k * m->nV);
     }
 }
 
 static void tend_u(mokab_state *st, const double *ssh, const double *u)
 {
     mokab_ctx *ctx = st->ctx; const mokab_mesh *m = st->mesh;
-    LAUNCH(ctx, ref::k_tend_normal_velocity, nblk(m->nE), 256, (int)m->nE, m->S2, m->ce.p, m->dc.p, m->eoe.p, m->woe.p, m->nEoE.p,
-           m->fE.p, ssh, u, st->d->tendU.p);
+    for (int64_t k = 0; k < st->K; ++k)      // the same pressure gradient for every level (pressure_gradient.jl:61-64), Coriolis per level
+        LAUNCH(ctx, ref::k_tend_normal_velocity, nblk(m->nE), 256, (int)m->nE, m->S2, m->ce.p, m->dc.p, m->eoe.p, m->woe.p, m->nEoE.p,
+               m->fE.p, ssh, u + k * m->nE, st->d->tendU.p + k * m->nE);
 }
 
 static void tend_h(mokab_state *st, const double *flux)
 {
     mokab_ctx *ctx = st->ctx; const mokab_mesh *m = st->mesh;
-    LAUNCH(ctx, ref::k_tend_layer_thickness, nblk(m->nC), 256, (int)m->nC, m->eoc.p, m->sgnC.p, m->nEoC.p, m->area.p, m->dv.p, flux,
-           st->d->tendH.p);
+    for (int64_t k = 0; k < st->K; ++k)
+        LAUNCH(ctx, ref::k_tend_layer_thickness, nblk(m->nC), 256, (int)m->nC, m->eoc.p, m->sgnC.p, m->nEoC.p, m->area.p, m->dv.p,
+               flux + k * m->nE, st->d->tendH.p + k * m->nC);
+}
+
+// Update_ssh! (time_integration.jl:205-212) for a column of st->K levels
+static void update_ssh(mokab_state *st, const double *h, double *ssh, cudaStream_t s = nullptr)
+{
+    mokab_ctx *ctx = st->ctx; const mokab_mesh *m = st->mesh;
+    cudaStream_t q = s ? s : ctx->stream;
+    if (st->K > 1) k_update_ssh_lv<<<nblk(m->nC), 256, 0, q>>>(m->nC, st->K, h, (const double *)m->H.p, ssh);
+    else k_update_ssh<double><<<nblk(m->nC), 256, 0, q>>>(m->nC, h, (const double *)m->H.p, ssh);
+    MOKAB_CUDA(cudaGetLastError());
+    ctx->launches++;
 }
 
 // advanceTimeLevels! (time_integration.jl:10-40): previous <- new
@@ -488,8 +525,8 @@ static void advance_time_levels(mokab_state *st)
     mokab_ctx *ctx = st->ctx; const mokab_mesh *m = st->mesh; StateT<double> *t = st->d;
     const int c = st->cur, o = 1 - c;
     MOKAB_CUDA(cudaMemcpyAsync(t->ssh[o].p, t->ssh[c].p, m->nC * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    MOKAB_CUDA(cudaMemcpyAsync(t->u[o].p, t->u[c].p, m->nE * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    MOKAB_CUDA(cudaMemcpyAsync(t->h[o].p, t->h[c].p, m->nC * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    MOKAB_CUDA(cudaMemcpyAsync(t->u[o].p, t->u[c].p, st->K * m->nE * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    MOKAB_CUDA(cudaMemcpyAsync(t->h[o].p, t->h[c].p, st->K * m->nC * 8, cudaMemcpyDeviceToDevice, ctx->stream));
 }
 
 // ocn_timestep(::ForwardEuler), time_integration.jl:150-193
@@ -501,9 +538,10 @@ static void step_forward_euler(mokab_state *st, double dt)
     diag_compute(st, t->u[c].p, t->h[c].p);
     tend_u(st, t->ssh[c].p, t->u[c].p);
     tend_h(st, t->flux.p);
-    LAUNCH(ctx, ref::k_axpy, nblk(m->nE), 256, m->nE, (const double *)t->u[c].p, dt, (const double *)t->tendU.p, t->u[c].p);
-    LAUNCH(ctx, ref::k_axpy, nblk(m->nC), 256, m->nC, (const double *)t->h[c].p, dt, (const double *)t->tendH.p, t->h[c].p);
-    LAUNCH(ctx, k_update_ssh<double>, nblk(m->nC), 256, m->nC, (const double *)t->h[c].p, (const double *)m->H.p, t->ssh[c].p);
+    const int64_t nEk = st->K * m->nE, nCk = st->K * m->nC;
+    LAUNCH(ctx, ref::k_axpy, nblk(nEk), 256, nEk, (const double *)t->u[c].p, dt, (const double *)t->tendU.p, t->u[c].p);
+    LAUNCH(ctx, ref::k_axpy, nblk(nCk), 256, nCk, (const double *)t->h[c].p, dt, (const double *)t->tendH.p, t->h[c].p);
+    update_ssh(st, t->h[c].p, t->ssh[c].p);
 }
 
 // ---- fused ForwardEuler ----------------------------------------------------------------------------------------------
@@ -511,7 +549,7 @@ static bool fe_fusable(const mokab_state *st)
 {
     const mokab_mesh *m = st->mesh;
     const bool widths = (m->S2 == 10 && m->S == 6) || (m->S2 == 12 && m->S == 7);   // the compile-time row widths of k_fe_step
-    return st->dtype == MOKAB_F64 && widths && m->nCo == m->nC && m->nEo == m->nE;
+    return st->dtype == MOKAB_F64 && st->K == 1 && widths && m->nCo == m->nC && m->nEo == m->nE;
 }
 
 // Re-create the Diag / Tend arrays the unfused step would have left behind, from the state before the last fused step
@@ -653,26 +691,28 @@ static void step_rk4_unfused(mokab_state *st, double dt)
     const double *uCur = t->u[o].p, *hCur = t->h[o].p;
     double *uPro = t->uP[0].p, *hPro = t->hP[0].p, *uNew = t->uP[1].p, *hNew = t->hP[1].p;
     cudaStream_t s = ctx->stream;
-    MOKAB_CUDA(cudaMemcpyAsync(uPro, uCur, m->nE * 8, cudaMemcpyDeviceToDevice, s));
-    MOKAB_CUDA(cudaMemcpyAsync(hPro, hCur, m->nC * 8, cudaMemcpyDeviceToDevice, s));
-    MOKAB_CUDA(cudaMemcpyAsync(uNew, uCur, m->nE * 8, cudaMemcpyDeviceToDevice, s));
-    MOKAB_CUDA(cudaMemcpyAsync(hNew, hCur, m->nC * 8, cudaMemcpyDeviceToDevice, s));
+    const int64_t nEk = st->K * m->nE, nCk = st->K * m->nC;
+    MOKAB_CUDA(cudaMemcpyAsync(uPro, uCur, nEk * 8, cudaMemcpyDeviceToDevice, s));
+    MOKAB_CUDA(cudaMemcpyAsync(hPro, hCur, nCk * 8, cudaMemcpyDeviceToDevice, s));
+    MOKAB_CUDA(cudaMemcpyAsync(uNew, uCur, nEk * 8, cudaMemcpyDeviceToDevice, s));
+    MOKAB_CUDA(cudaMemcpyAsync(hNew, hCur, nCk * 8, cudaMemcpyDeviceToDevice, s));
     for (int sg = 0; sg < 4; ++sg) {
-        LAUNCH(ctx, k_update_ssh<double>, nblk(m->nC), 256, m->nC, (const double *)hPro, (const double *)m->H.p, t->sshProv.p);
-        LAUNCH(ctx, ref::k_interpolate_cell2edge, nblk(m->nE), 256, (int)m->nE, m->ce.p, (const double *)hPro, t->hEdge.p);
-        LAUNCH(ctx, ref::k_mul, nblk(m->nE), 256, m->nE, (const double *)uPro, (const double *)t->hEdge.p, t->flux.p);
+        update_ssh(st, hPro, t->sshProv.p);
+        for (int64_t k = 0; k < st->K; ++k)
+            LAUNCH(ctx, ref::k_interpolate_cell2edge, nblk(m->nE), 256, (int)m->nE, m->ce.p, (const double *)(hPro + k * m->nC), t->hEdge.p + k * m->nE);
+        LAUNCH(ctx, ref::k_mul, nblk(nEk), 256, nEk, (const double *)uPro, (const double *)t->hEdge.p, t->flux.p);
         tend_u(st, t->sshProv.p, uPro);
         tend_h(st, t->flux.p);
         if (sg < 3) {
-            LAUNCH(ctx, ref::k_axpy, nblk(m->nE), 256, m->nE, uCur, a[sg], (const double *)t->tendU.p, uPro);
-            LAUNCH(ctx, ref::k_axpy, nblk(m->nC), 256, m->nC, hCur, a[sg], (const double *)t->tendH.p, hPro);
+            LAUNCH(ctx, ref::k_axpy, nblk(nEk), 256, nEk, uCur, a[sg], (const double *)t->tendU.p, uPro);
+            LAUNCH(ctx, ref::k_axpy, nblk(nCk), 256, nCk, hCur, a[sg], (const double *)t->tendH.p, hPro);
         }
-        LAUNCH(ctx, ref::k_axpy, nblk(m->nE), 256, m->nE, (const double *)uNew, b[sg], (const double *)t->tendU.p, uNew);
-        LAUNCH(ctx, ref::k_axpy, nblk(m->nC), 256, m->nC, (const double *)hNew, b[sg], (const double *)t->tendH.p, hNew);
+        LAUNCH(ctx, ref::k_axpy, nblk(nEk), 256, nEk, (const double *)uNew, b[sg], (const double *)t->tendU.p, uNew);
+        LAUNCH(ctx, ref::k_axpy, nblk(nCk), 256, nCk, (const double *)hNew, b[sg], (const double *)t->tendH.p, hNew);
     }
-    MOKAB_CUDA(cudaMemcpyAsync(t->u[c].p, uNew, m->nE * 8, cudaMemcpyDeviceToDevice, s));
-    MOKAB_CUDA(cudaMemcpyAsync(t->h[c].p, hNew, m->nC * 8, cudaMemcpyDeviceToDevice, s));
-    LAUNCH(ctx, k_update_ssh<double>, nblk(m->nC), 256, m->nC, (const double *)hNew, (const double *)m->H.p, t->ssh[c].p);
+    MOKAB_CUDA(cudaMemcpyAsync(t->u[c].p, uNew, nEk * 8, cudaMemcpyDeviceToDevice, s));
+    MOKAB_CUDA(cudaMemcpyAsync(t->h[c].p, hNew, nCk * 8, cudaMemcpyDeviceToDevice, s));
+    update_ssh(st, hNew, t->ssh[c].p);
 }
 
 static int p2p_target(const mokab_state *st, int stage);
@@ -686,6 +726,7 @@ struct Options {
                                   // its cell phase into L2 at entry; bit 1 = it prefetches the streams of the block launched
                                   // `stage_prefetch_distance` blocks after it
     int stage_prefetch_distance = 0;   // MOKAB_STAGE_PREFETCH_DISTANCE: 0 = one wave of resident blocks (SMs x blocks per SM)
+    int stage_wf_block_major = 0; // MOKAB_STAGE_WF_BLOCK_MAJOR: the plain stage kernel reads the Coriolis weights from the block-major copy
     int test_drop_dependency = 0; // TEST HOOK (tests/sim: does the checker have teeth?): 1 / 2 = leave out one of the two cross-stream
                                   // waits of the decomposed RK4 schedule (interior after boundary / boundary after interior)
     int64_t epoch = 0;
@@ -696,6 +737,7 @@ struct Options {
         if (stage_tma < 0 || stage_tma > 2) stage_tma = 0;
         stage_prefetch = geti("MOKAB_STAGE_PREFETCH", 0) & 3;
         stage_prefetch_distance = std::max(0, geti("MOKAB_STAGE_PREFETCH_DISTANCE", 0));
+        stage_wf_block_major = geti("MOKAB_STAGE_WF_BLOCK_MAJOR", 0) ? 1 : 0;
     }
 };
 static Options &options() { static Options o; return o; }
@@ -727,7 +769,7 @@ template <class R>
 static void ensure_wf_block_major(mokab_mesh *m)
 {
     FusedMesh<R> &f = fused_of<R>(m);
-    if (stage_tma_mode() != 2 || f.wfB.n || !(m->S2 == 10 && m->S == 6)) return;
+    if ((stage_tma_mode() != 2 && !options().stage_wf_block_major) || f.wfB.n || !(m->S2 == 10 && m->S == 6)) return;
     mokab_ctx *ctx = m->ctx;
     constexpr int AL = 16 / (int)sizeof(R);
     std::vector<long long> off(m->fusedBlocks + 1, 0);
@@ -767,6 +809,10 @@ static void launch_stage(mokab_ctx *ctx, const mokab_mesh *m, fused::StageArgs<R
         return;
     }
     const bool der = (hex || hept) && m->nDerivedBlocks > 0;
+    if (hex && !stage_tma_enabled() && options().stage_wf_block_major && part != MOKAB_PART_BOUNDARY_PUSH) {
+        FusedMesh<R> &fm = fused_of<R>(const_cast<mokab_mesh *>(m));
+        if (fm.wfB.n) { A.wfB = fm.wfB.p; A.wfBOff = fm.wfBOff.p; }
+    }
     if (hex && stage_tma_enabled()) {   // opt-in: the weight rows of a block through bulk asynchronous copies (kernels_fused.cuh)
         constexpr int AL = fused::tma_align<R>();
         A.wStride = (m->maxBlockEdges + AL + AL - 1) / AL * AL;
@@ -959,6 +1005,12 @@ static void refresh_ssh(mokab_state *st, cudaStream_t stream = nullptr)
     ensure_fused<R>(m);
     FusedMesh<R> &fm = fused_of<R>(m);
     cudaStream_t s = stream ? stream : ctx->stream;
+    if constexpr (sizeof(R) == 8) {
+        if (st->K > 1) {
+            for (int l = 0; l < 2; ++l) update_ssh(st, t->h[l].p, t->ssh[l].p, s);
+            return;
+        }
+    }
     for (int l = 0; l < 2; ++l) {
         k_update_ssh<R><<<nblk(m->nC), 256, 0, s>>>(m->nC, (const R *)t->h[l].p, (const R *)fm.H.p, t->ssh[l].p);
         MOKAB_CUDA(cudaGetLastError());
@@ -966,11 +1018,101 @@ static void refresh_ssh(mokab_state *st, cudaStream_t stream = nullptr)
     }
 }
 
+// ---- fused RK4 on multi-level states (K > 1; fused::k_rk_stage_ml) ---------------------------------------------------------
+template <int STAGE>
+static void launch_stage_ml(mokab_ctx *ctx, const mokab_mesh *m, const fused::StageArgsML &A)
+{
+    const int grid = m->fusedBlocks;
+    if (grid == 0) return;
+    const bool hex = m->S2 == 10 && m->S == 6, hept = m->S2 == 12 && m->S == 7;
+#define MOKAB_STAGE_ML(S2T, ST, FOLD) fused::k_rk_stage_ml<STAGE, S2T, ST, FOLD><<<grid, fused::kThreads, 0, ctx->stream>>>(A, m->S2, m->S)
+    if (hex && m->uniformF)       MOKAB_STAGE_ML(10, 6, false);
+    else if (hex)                 MOKAB_STAGE_ML(10, 6, true);
+    else if (hept && m->uniformF) MOKAB_STAGE_ML(12, 7, false);
+    else if (hept)                MOKAB_STAGE_ML(12, 7, true);
+    else if (m->uniformF)         MOKAB_STAGE_ML(0, 0, false);
+    else                          MOKAB_STAGE_ML(0, 0, true);
+#undef MOKAB_STAGE_ML
+    MOKAB_CUDA(cudaGetLastError());
+    ctx->launches++;
+}
+
+// one RK4 step of a multi-level state reading time level p, writing level 1 - p (ssh[1 - p] included)
+static void enqueue_rk4_step_ml(mokab_state *st, double dt, int p)
+{
+    mokab_ctx *ctx = st->ctx; mokab_mesh *m = const_cast<mokab_mesh *>(st->mesh);
+    StateT<double> *t = st->d;
+    FusedMesh<double> &fm = fused_of<double>(m);
+    fused::StageArgsML A;
+    A.nE = (int)m->nE; A.nC = (int)m->nC; A.K = st->K;
+    A.ce = m->ce.p; A.eoe = m->eoeF.p; A.eoc = m->eocF.p; A.nEoE = m->nEoE.p; A.nEoC = m->nEoC.p; A.blkEdgeStart = m->blkEdgeStart.p;
+    A.gdc = fm.gdc.p; A.wf = fm.wf.p; A.dv = fm.dv.p; A.invArea = fm.invArea.p; A.H = fm.H.p;
+    A.uCur = t->u[p].p; A.hCur = t->h[p].p; A.uAcc = t->u[1 - p].p; A.hAcc = t->h[1 - p].p;
+    A.f0 = m->f0;
+    const double a[4] = {dt / 2.0, dt / 2.0, dt, 0.0};                  // time_integration.jl:77
+    const double b[4] = {dt / 6.0, dt / 3.0, dt / 3.0, dt / 6.0};       // time_integration.jl:78
+    for (int stage = 1; stage <= 4; ++stage) {
+        A.a = a[stage - 1]; A.b = b[stage - 1];
+        switch (stage) {
+        case 1: A.uOld = t->u[p].p;  A.hOld = t->h[p].p;  A.sshOld = t->ssh[p].p;  A.uOut = t->uP[0].p; A.hOut = t->hP[0].p; A.sshOut = t->sshP[0].p; break;
+        case 2: A.uOld = t->uP[0].p; A.hOld = t->hP[0].p; A.sshOld = t->sshP[0].p; A.uOut = t->uP[1].p; A.hOut = t->hP[1].p; A.sshOut = t->sshP[1].p; break;
+        case 3: A.uOld = t->uP[1].p; A.hOld = t->hP[1].p; A.sshOld = t->sshP[1].p; A.uOut = t->uP[0].p; A.hOut = t->hP[0].p; A.sshOut = t->sshP[0].p; break;
+        default: A.uOld = t->uP[0].p; A.hOld = t->hP[0].p; A.sshOld = t->sshP[0].p; A.uOut = nullptr; A.hOut = nullptr; A.sshOut = t->ssh[1 - p].p; break;
+        }
+        if (stage == 1) launch_stage_ml<1>(ctx, m, A);
+        else if (stage == 4) launch_stage_ml<4>(ctx, m, A);
+        else launch_stage_ml<2>(ctx, m, A);
+    }
+}
+
+static void run_rk4_fused_ml(mokab_state *st, double dt, int64_t nsteps)
+{
+    mokab_ctx *ctx = st->ctx;
+    StateT<double> *t = st->d;
+    MOKAB_REQUIRE(st->dtype == MOKAB_F64, "timestep_rk4: multi-level states are Float64");
+    MOKAB_REQUIRE(!t->taping, "timestep_rk4: the reverse mode records single-level states only");
+    if (nsteps <= 0) return;
+    // the stage kernels gather ssh of the state they read: make ssh[cur] what the current layerThickness implies (every later
+    // step's ssh is written by the stage that produces its layerThickness)
+    update_ssh(st, t->h[st->cur].p, t->ssh[st->cur].p);
+    if (!t->graphs_ready || t->graph_dt != dt || t->graph_epoch != options().epoch) {
+        t->drop_graphs();
+        const int64_t saved = ctx->launches;
+        for (int p = 0; p < 2; ++p)
+            for (int pair = 0; pair < 2; ++pair) {
+                cudaGraph_t g = nullptr;
+                MOKAB_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+                try {
+                    enqueue_rk4_step_ml(st, dt, p);
+                    if (pair) enqueue_rk4_step_ml(st, dt, 1 - p);
+                } catch (...) {
+                    cudaStreamEndCapture(ctx->stream, &g);
+                    if (g) cudaGraphDestroy(g);
+                    throw;
+                }
+                MOKAB_CUDA(cudaStreamEndCapture(ctx->stream, &g));
+                cudaGraphExec_t ge = nullptr;
+                cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
+                cudaGraphDestroy(g);
+                MOKAB_CUDA(e);
+                (pair ? t->gPair : t->gStep)[p] = ge;
+            }
+        ctx->launches = saved;
+        t->graph_dt = dt; t->graph_epoch = options().epoch; t->graphs_ready = true;
+    }
+    int64_t left = nsteps;
+    while (left >= 2) { MOKAB_CUDA(cudaGraphLaunch(t->gPair[st->cur], ctx->stream)); ctx->launches += 8; left -= 2; }
+    if (left) { MOKAB_CUDA(cudaGraphLaunch(t->gStep[st->cur], ctx->stream)); ctx->launches += 4; st->cur = 1 - st->cur; }
+    // Prog.ssh[1] of the reference after its last step: the free surface of the previous state
+    update_ssh(st, t->h[1 - st->cur].p, t->ssh[1 - st->cur].p);
+}
+
 template <class R>
 static void run_rk4_fused(mokab_state *st, double dt, int64_t nsteps)
 {
     mokab_ctx *ctx = st->ctx;
     StateT<R> *t = typed<R>(st);
+    if (st->K > 1) { run_rk4_fused_ml(st, dt, nsteps); return; }
     MOKAB_REQUIRE(st->mesh->nCo == st->mesh->nC && st->mesh->nEo == st->mesh->nE,
                   "timestep_rk4: this mesh has halo entities; drive it with mokab_rk4_stage + mokab_halo_pack/unpack");
     ensure_fused<R>(const_cast<mokab_mesh *>(st->mesh));
@@ -1017,11 +1159,11 @@ static void do_reduce(mokab_state *st, int which, double *out)
     FusedMesh<R> &fm = fused_of<R>(m);
     const int c = st->cur;
     MOKAB_REQUIRE(which >= 0 && which <= 2, "reduce: unknown reduction id");
-    LAUNCH(ctx, reduce::k_cells<R>, reduce::kBlocks, reduce::kThreads, which, m->nCo, (const R *)t->h[c].p, (const R *)fm.H.p,
+    LAUNCH(ctx, reduce::k_cells<R>, reduce::kBlocks, reduce::kThreads, which, m->nCo, st->K, m->nC, (const R *)t->h[c].p, (const R *)fm.H.p,
            (const double *)m->area.p, t->partial.p);
     if (which == MOKAB_SUM_ENERGY)
-        LAUNCH(ctx, reduce::k_edges_ke<R>, reduce::kBlocks, reduce::kThreads, m->nEo, (const int2 *)m->ce.p, (const double *)m->dc.p,
-               (const double *)m->dv.p, (const R *)t->u[c].p, (const R *)t->h[c].p, (const R *)fm.H.p, t->partial.p);
+        LAUNCH(ctx, reduce::k_edges_ke<R>, reduce::kBlocks, reduce::kThreads, m->nEo, st->K, m->nE, m->nC, (const int2 *)m->ce.p,
+               (const double *)m->dc.p, (const double *)m->dv.p, (const R *)t->u[c].p, (const R *)t->h[c].p, (const R *)fm.H.p, t->partial.p);
     LAUNCH(ctx, reduce::k_final, 1, reduce::kThreads, (const double *)t->partial.p, t->result.p);
     MOKAB_CUDA(cudaMemcpyAsync(out, t->result.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     MOKAB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1654,13 +1796,30 @@ int mokab_mesh_device_bytes(const mokab_mesh *mesh, int64_t *out)
 // ---- state -----------------------------------------------------------------------------------------------------
 int mokab_state_create(mokab_ctx *ctx, const mokab_mesh *mesh, int dtype, mokab_state **out)
 {
+    return mokab_state_create_levels(ctx, mesh, dtype, 1, out);
+}
+
+int mokab_state_levels(const mokab_state *state, int *nVertLevels)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(state && nVertLevels, "state_levels: NULL argument");
+        *nVertLevels = state->K;
+    });
+}
+
+int mokab_state_create_levels(mokab_ctx *ctx, const mokab_mesh *mesh, int dtype, int nVertLevels, mokab_state **out)
+{
     return guarded([&] {
         MOKAB_REQUIRE(ctx && mesh && out, "state_create: NULL argument");
+        MOKAB_REQUIRE(nVertLevels >= 1 && nVertLevels <= 1024, "state_create: nVertLevels must be in 1..1024");
+        MOKAB_REQUIRE(nVertLevels == 1 || dtype == MOKAB_F64, "state_create: multi-level states are Float64 (PrognosticVars.jl:91-93)");
+        MOKAB_REQUIRE(nVertLevels == 1 || (mesh->nCo == mesh->nC && mesh->nEo == mesh->nE),
+                      "state_create: multi-level states need an undecomposed mesh");
         MOKAB_REQUIRE(mesh->ctx == ctx, "state_create: mesh belongs to a different context (src/Architectures.jl:27-33)");
         MOKAB_REQUIRE(dtype == MOKAB_F64 || dtype == MOKAB_F32, "state_create: dtype must be MOKAB_F64 or MOKAB_F32");
         ctx->bind();
         auto *st = new mokab_state();
-        st->ctx = ctx; st->mesh = mesh; st->dtype = dtype;
+        st->ctx = ctx; st->mesh = mesh; st->dtype = dtype; st->K = nVertLevels;
         try {
             if (dtype == MOKAB_F64) alloc_state<double>(st); else alloc_state<float>(st);
             // the fused-form mesh arrays of this precision, complete before any stepper can be launched on any stream
@@ -1957,6 +2116,7 @@ int mokab_tape_begin(mokab_state *state, int64_t max_steps)
     return guarded([&] {
         MOKAB_REQUIRE(state, "tape_begin: state is NULL");
         MOKAB_REQUIRE(max_steps >= 0, "tape_begin: max_steps must be >= 0");
+        MOKAB_REQUIRE(state->K == 1, "tape_begin: single-level states only (nVertLevels == 1)");
         state->ctx->bind();
         if (state->dtype == MOKAB_F64) tape_begin<double>(state, max_steps); else tape_begin<float>(state, max_steps);
     });
@@ -1974,6 +2134,7 @@ int mokab_adjoint_seed(mokab_state *state, int which)
 {
     return guarded([&] {
         MOKAB_REQUIRE(state, "adjoint_seed: state is NULL");
+        MOKAB_REQUIRE(state->K == 1, "adjoint_seed: single-level states only (nVertLevels == 1)");
         state->ctx->bind();
         if (state->dtype == MOKAB_F64) adjoint_seed<double>(state, which); else adjoint_seed<float>(state, which);
     });
@@ -2049,6 +2210,7 @@ int mokab_halo_pack(mokab_state *state, int stage, void *send_buf_device, void *
     return guarded([&] {
         MOKAB_REQUIRE(state && state->mesh->halo_ready, "halo_pack: call mokab_halo_setup first");
         MOKAB_REQUIRE(stage >= 0 && stage <= 5, "halo_pack: stage must be 0..5");
+        MOKAB_REQUIRE(state->K == 1, "halo_pack: single-level states only (nVertLevels == 1)");
         MOKAB_REQUIRE(send_buf_device || state->mesh->haloSend.n == 0, "halo_pack: NULL buffer");
         state->ctx->bind();
         if (state->dtype == MOKAB_F64) halo_pack<double>(state, stage, send_buf_device, (cudaStream_t)cuda_stream, false);
@@ -2061,6 +2223,7 @@ int mokab_halo_unpack(mokab_state *state, int stage, const void *recv_buf_device
     return guarded([&] {
         MOKAB_REQUIRE(state && state->mesh->halo_ready, "halo_unpack: call mokab_halo_setup first");
         MOKAB_REQUIRE(stage >= 0 && stage <= 5, "halo_unpack: stage must be 0..5");
+        MOKAB_REQUIRE(state->K == 1, "halo_unpack: single-level states only (nVertLevels == 1)");
         MOKAB_REQUIRE(recv_buf_device || state->mesh->haloRecv.n == 0, "halo_unpack: NULL buffer");
         state->ctx->bind();
         if (state->dtype == MOKAB_F64) halo_pack<double>(state, stage, const_cast<void *>(recv_buf_device), (cudaStream_t)cuda_stream, true);
@@ -2073,6 +2236,7 @@ int mokab_rk4_stage(mokab_state *state, double dt, int stage, int part, void *cu
     return guarded([&] {
         MOKAB_REQUIRE(state, "rk4_stage: state is NULL");
         MOKAB_REQUIRE(stage >= 1 && stage <= 4, "rk4_stage: stage must be 1..4");
+        MOKAB_REQUIRE(state->K == 1, "rk4_stage: single-level states only (nVertLevels == 1)");
         MOKAB_REQUIRE(part >= MOKAB_PART_ALL && part <= MOKAB_PART_BOUNDARY_PUSH, "rk4_stage: unknown part");
         state->ctx->bind();
         leave_forward_euler(state);
@@ -2086,6 +2250,7 @@ int mokab_forward_euler_stage(mokab_state *state, double dt, int part, void *cud
     return guarded([&] {
         MOKAB_REQUIRE(state, "forward_euler_stage: state is NULL");
         MOKAB_REQUIRE(part >= MOKAB_PART_ALL && part <= MOKAB_PART_BOUNDARY, "forward_euler_stage: part must be ALL, INTERIOR or BOUNDARY");
+        MOKAB_REQUIRE(state->K == 1, "forward_euler_stage: single-level states only (nVertLevels == 1)");
         require_f64(state, "forward_euler_stage");
         state->ctx->bind();
         run_fe_stage(state, dt, part, (cudaStream_t)cuda_stream);
@@ -2148,6 +2313,7 @@ int mokab_p2p_export(mokab_state *state, int rank, void *blob)
 {
     return guarded([&] {
         MOKAB_REQUIRE(state && blob, "p2p_export: NULL argument");
+        MOKAB_REQUIRE(state->K == 1, "p2p_export: single-level states only (nVertLevels == 1)");
         state->ctx->bind();
         if (state->dtype == MOKAB_F64) p2p_export<double>(state, (P2PBlob *)blob); else p2p_export<float>(state, (P2PBlob *)blob);
         ((P2PBlob *)blob)->rank = rank;
@@ -2230,6 +2396,7 @@ int mokab_set_option(const char *name, int64_t value)
         if (n == "stage_tma") { MOKAB_REQUIRE(value >= 0 && value <= 2, "set_option: stage_tma must be 0, 1 or 2"); o.stage_tma = (int)value; }
         else if (n == "stage_prefetch") { MOKAB_REQUIRE(value >= 0 && value <= 3, "set_option: stage_prefetch must be 0..3"); o.stage_prefetch = (int)value; }
         else if (n == "stage_prefetch_distance") { MOKAB_REQUIRE(value >= 0 && value < (1 << 30), "set_option: bad stage_prefetch_distance"); o.stage_prefetch_distance = (int)value; }
+        else if (n == "stage_wf_block_major") o.stage_wf_block_major = value ? 1 : 0;
         else if (n == "test_drop_dependency") o.test_drop_dependency = (int)value;
         else throw Error("set_option: unknown option '" + n + "'");
         o.epoch++;
@@ -2245,6 +2412,7 @@ int mokab_get_option(const char *name, int64_t *value)
         if (n == "stage_tma") *value = o.stage_tma;
         else if (n == "stage_prefetch") *value = o.stage_prefetch;
         else if (n == "stage_prefetch_distance") *value = o.stage_prefetch_distance;
+        else if (n == "stage_wf_block_major") *value = o.stage_wf_block_major;
         else throw Error("get_option: unknown option '" + n + "'");
     });
 }

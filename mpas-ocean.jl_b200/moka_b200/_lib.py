@@ -19,7 +19,7 @@ SUM_SSH2, SUM_MASS, SUM_ENERGY = range(3)
 CELLS, EDGES, VERTICES = range(3)
 RK4_FUSED, RK4_UNFUSED = 0, 1
 PART_ALL, PART_INTERIOR, PART_BOUNDARY, PART_BOUNDARY_PUSH = 0, 1, 2, 3
-MESH_RENUMBER, MESH_EXPLICIT_EOE, MESH_KEEP_WIDTHS = 1, 2, 4
+MESH_RENUMBER, MESH_EXPLICIT_EOE, MESH_KEEP_WIDTHS, MESH_EDGES_BY_CELL = 1, 2, 4, 8
 HALO_NCCL, HALO_P2P, HALO_P2P_FUSED = 0, 1, 2
 DECOMP_NO_OVERLAP, DECOMP_NO_GRAPH = 1, 2
 COMM_ID_BYTES = 128
@@ -54,7 +54,7 @@ SYMBOLS = [
     "mokab_init", "mokab_finalize", "mokab_synchronize", "mokab_set_stream", "mokab_timer_start", "mokab_timer_stop",
     "mokab_launch_count", "mokab_host_alloc", "mokab_host_free", "mokab_last_error", "mokab_version",
     "mokab_mesh_create", "mokab_mesh_destroy", "mokab_mesh_get_perm", "mokab_mesh_device_bytes",
-    "mokab_state_create", "mokab_state_destroy", "mokab_state_set", "mokab_state_get",
+    "mokab_state_create", "mokab_state_create_levels", "mokab_state_levels", "mokab_state_destroy", "mokab_state_set", "mokab_state_get",
     "mokab_state_set_async", "mokab_state_get_async", "mokab_state_synchronize",
     "mokab_diagnostic_compute", "mokab_diagnostic_compute_consistent", "mokab_compute_normal_velocity_tendency", "mokab_compute_layer_thickness_tendency",
     "mokab_gradient_on_edge", "mokab_divergence_on_cell", "mokab_curl_on_vertex", "mokab_interpolate_cell2edge",
@@ -88,6 +88,7 @@ def bind(L):
         "mokab_mesh_create": [vp, C.POINTER(MeshDesc), C.c_uint32, C.POINTER(vp)], "mokab_mesh_destroy": [vp],
         "mokab_mesh_get_perm": [vp, C.c_int, _I32P], "mokab_mesh_device_bytes": [vp, C.POINTER(i64)],
         "mokab_state_create": [vp, vp, C.c_int, C.POINTER(vp)], "mokab_state_destroy": [vp],
+        "mokab_state_create_levels": [vp, vp, C.c_int, C.c_int, C.POINTER(vp)], "mokab_state_levels": [vp, C.POINTER(C.c_int)],
         "mokab_state_set": [vp, C.c_int, vp], "mokab_state_get": [vp, C.c_int, vp],
         "mokab_state_set_async": [vp, C.c_int, vp], "mokab_state_get_async": [vp, C.c_int, vp],
         "mokab_state_synchronize": [vp],

@@ -90,7 +90,8 @@ class Mesh:
     HorzMesh.jl:292-332 (computed by the library when `edgeSignOnCell` is not supplied).
     """
 
-    def __init__(self, fields: dict, backend: B200, renumber: bool = True, explicit_eoe: bool = False, keep_widths: bool = False):
+    def __init__(self, fields: dict, backend: B200, renumber: bool = True, explicit_eoe: bool = False, keep_widths: bool = False,
+                 edges_by_cell: bool = False):
         if not isinstance(backend, B200):
             raise MokaError("Mesh: backend must be a B200 architecture")
         self.backend = backend
@@ -98,10 +99,7 @@ class Mesh:
         self.nVertices = int(fields.get("nVertices", 0)) if fields.get("edgesOnVertex") is not None else 0
         self.maxEdges, self.maxEdges2 = int(fields["maxEdges"]), int(fields["maxEdges2"])
         self.vertexDegree = int(fields.get("vertexDegree", 3))
-        self.nVertLevels = int(fields.get("nVertLevels", 1))
-        if self.nVertLevels != 1:
-            raise MokaError("Mesh: only nVertLevels == 1 is supported (the reference's working path "
-                            "computes level 1 only, VertMesh.jl:31-36)")
+        self.nVertLevels = int(fields.get("nVertLevels", 1))          # VertMesh.nVertLevels: the level count of the states on this mesh
         d = L.MeshDesc()
         d.nCells, d.nEdges, d.nVertices = self.nCells, self.nEdges, self.nVertices
         d.maxEdges, d.maxEdges2, d.vertexDegree = self.maxEdges, self.maxEdges2, self.vertexDegree
@@ -126,7 +124,7 @@ class Mesh:
             keep.append(a)
             setattr(d, name, a.ctypes.data_as(ptype))
         h = C.c_void_p()
-        L.check(L.lib().mokab_mesh_create(backend.handle, C.byref(d), (L.MESH_RENUMBER if renumber else 0) | (L.MESH_EXPLICIT_EOE if explicit_eoe else 0) | (L.MESH_KEEP_WIDTHS if keep_widths else 0), C.byref(h)))
+        L.check(L.lib().mokab_mesh_create(backend.handle, C.byref(d), (L.MESH_RENUMBER if renumber else 0) | (L.MESH_EXPLICIT_EOE if explicit_eoe else 0) | (L.MESH_KEEP_WIDTHS if keep_widths else 0) | (L.MESH_EDGES_BY_CELL if edges_by_cell else 0), C.byref(h)))
         self.handle = h
         self._fin = weakref.finalize(self, L.lib().mokab_mesh_destroy, h)
         self.dcEdge_mean = float(np.mean(fields["dcEdge"]))
@@ -163,14 +161,15 @@ class Mesh:
 
 # ---- state structs ------------------------------------------------------------------------------------
 class _DeviceState:
-    def __init__(self, mesh: Mesh, dtype):
+    def __init__(self, mesh: Mesh, dtype, levels: int = 1):
         self.mesh = mesh
+        self.levels = int(levels)
         self.np_dtype = np.dtype(dtype)
         if self.np_dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
             raise MokaError("state eltype must be Float64 or Float32")
         h = C.c_void_p()
-        L.check(L.lib().mokab_state_create(mesh.backend.handle, mesh.handle,
-                                           L.F64 if self.np_dtype == np.float64 else L.F32, C.byref(h)))
+        L.check(L.lib().mokab_state_create_levels(mesh.backend.handle, mesh.handle,
+                                                  L.F64 if self.np_dtype == np.float64 else L.F32, self.levels, C.byref(h)))
         self.handle = h
         self._fin = weakref.finalize(self, L.lib().mokab_state_destroy, h)
 
@@ -186,7 +185,8 @@ class _DeviceState:
         if out is None:
             out = np.empty(n, self.np_dtype)
         L.check(L.lib().mokab_state_get(self.handle, field, out.ctypes.data_as(C.c_void_p)))
-        return out
+        # multi-level fields come back as (n, nVertLevels): the memory of the reference's (nVertLevels, n) column-major array
+        return out.reshape(-1, self.levels) if self.levels > 1 and n != self._entities(field) else out
 
     def set_async(self, field: int, host_pinned: np.ndarray) -> None:
         """Enqueue the upload of a page-locked host array (B200.pinned); returns before the copy has run."""
@@ -203,7 +203,7 @@ class _DeviceState:
     def synchronize(self) -> None:
         L.check(L.lib().mokab_state_synchronize(self.handle))
 
-    def _len(self, field: int) -> int:
+    def _entities(self, field: int) -> int:
         m = self.mesh
         if field in (L.SSH, L.LAYER_THICKNESS, L.SSH_PREV, L.LAYER_THICKNESS_PREV, L.VELOCITY_DIV_CELL, L.TEND_LAYER_THICKNESS,
                      L.D_SSH, L.D_LAYER_THICKNESS):
@@ -211,6 +211,10 @@ class _DeviceState:
         if field == L.RELATIVE_VORTICITY:
             return m.nVertices
         return m.nEdges
+
+    def _len(self, field: int) -> int:
+        n = self._entities(field)
+        return n if field in (L.SSH, L.SSH_PREV, L.D_SSH) else n * self.levels
 
 
 class PrognosticVars:
@@ -226,7 +230,13 @@ class PrognosticVars:
         et = check_eltype_args(args)
         if nTimeLevels != 2:
             raise MokaError("nTimeLevels must be <= 2" if nTimeLevels > 2 else "nTimeLevels must be 2")  # time_integration.jl:23
-        self.dev = _DeviceState(mesh, dtype or et)
+        # multi-level states: normalVelocity / layerThickness of shape (n, nVertLevels) -- the memory of the reference's
+        # (nVertLevels, n) arrays (PrognosticVars.jl:10-16) -- and ssh of shape (nCells)
+        nv = np.asarray(normalVelocity)
+        levels = int(nv.shape[1]) if nv.ndim == 2 else 1
+        if levels != mesh.nVertLevels and not (levels == 1 and mesh.nVertLevels == 1):
+            raise MokaError(f"PrognosticVars: normalVelocity has {levels} levels, the mesh {mesh.nVertLevels}")
+        self.dev = _DeviceState(mesh, dtype or et, levels)
         self.mesh = mesh
         # Float32 states carry ONE perturbation variable, ssh = layerThickness - restingThicknessSum (include/moka_b200.h):
         # layerThickness first (a Float32 1000 m + 1 m has lost the wave's low bits), then ssh, which keeps them

@@ -33,28 +33,28 @@ def gradient_on_edge(m, scalar_cell):
     """GradientOnEdge, Operators.jl:84-100: (s[c2] - s[c1]) / dcEdge."""
     c1 = m["cellsOnEdge"][:, 0] - 1
     c2 = m["cellsOnEdge"][:, 1] - 1
-    return (scalar_cell[c2] - scalar_cell[c1]) / m["dcEdge"]
+    return (scalar_cell[..., c2] - scalar_cell[..., c1]) / m["dcEdge"]
 
 
 def divergence_on_cell(m, vec_edge):
     """DivergenceOnCell_P1 + _P2, Operators.jl:12-44. Returns (div, temp)."""
     temp = vec_edge * m["dvEdge"]                                        # :18
-    div = np.zeros(m["nCells"])                                          # :34
+    div = np.zeros(vec_edge.shape[:-1] + (m["nCells"],))                  # :34
     eoc, sgn, n = m["edgesOnCell"], m["edgeSignOnCell"], m["nEdgesOnCell"]
     for i in range(m["maxEdges"]):
         act = i < n
         e = np.where(act, eoc[:, i] - 1, 0)
-        div = np.where(act, div - temp[e] * sgn[:, i], div)              # :39
+        div = np.where(act, div - temp[..., e] * sgn[:, i], div)         # :39
     return div / m["areaCell"], temp                                     # :42
 
 
 def curl_on_vertex(m, vec_edge, curl_in=None):
     """CurlOnVertex, Operators.jl:122-149. Accumulates into curl_in (never zeroed, :135)."""
-    curl = np.zeros(m["nVertices"]) if curl_in is None else curl_in.copy()
+    curl = np.zeros(vec_edge.shape[:-1] + (m["nVertices"],)) if curl_in is None else curl_in.copy()
     inv = 1.0 / m["areaTriangle"]                                        # :137
     for j in range(m["vertexDegree"]):
         e = m["edgesOnVertex"][:, j] - 1
-        curl = curl + m["dcEdge"][e] * inv * vec_edge[e] * m["edgeSignOnVertex"][:, j]   # :142-145
+        curl = curl + m["dcEdge"][e] * inv * vec_edge[..., e] * m["edgeSignOnVertex"][:, j]   # :142-145
     return curl
 
 
@@ -62,7 +62,7 @@ def interpolate_cell2edge(m, cell_value):
     """interpolateCell2Edge, Operators.jl:201-222."""
     c1 = m["cellsOnEdge"][:, 0] - 1
     c2 = m["cellsOnEdge"][:, 1] - 1
-    return 0.5 * (cell_value[c1] + cell_value[c2])
+    return 0.5 * (cell_value[..., c1] + cell_value[..., c2])
 
 
 # --------------------------------------------------------------------------------------------
@@ -83,7 +83,7 @@ def coriolis_force_tendency(m, tend, u):
     for i in range(eoe.shape[1]):
         act = (i < n) & (eoe[:, i] != 0)                                 # :61, :67
         j = np.where(act, eoe[:, i] - 1, 0)
-        out = np.where(act, out + w[:, i] * u[j] * f[j], out)            # :70-72
+        out = np.where(act, out + w[:, i] * u[..., j] * f[j], out)       # :70-72
     return out
 
 
@@ -95,20 +95,20 @@ def thickness_flux_div_on_cell(m, tend, flux):
     for i in range(m["maxEdges"]):
         act = i < n
         e = np.where(act, eoc[:, i] - 1, 0)
-        out = np.where(act, out + flux[e] * m["dvEdge"][e] * sgn[:, i] * inv_area, out)   # :64-65
+        out = np.where(act, out + flux[..., e] * m["dvEdge"][e] * sgn[:, i] * inv_area, out)   # :64-65
     return out
 
 
 def compute_normal_velocity_tendency(m, ssh, u):
     """computeNormalVelocityTendency!, normalVelocity.jl:21-53 (zero, gradient, Coriolis)."""
-    t = np.zeros(m["nEdges"])
+    t = np.zeros(u.shape[:-1] + (m["nEdges"],))
     t = ssh_grad_on_edge(m, t, ssh)
     return coriolis_force_tendency(m, t, u)
 
 
 def compute_layer_thickness_tendency(m, flux):
     """computeLayerThicknessTendency!, layerThickness.jl:14-28."""
-    return thickness_flux_div_on_cell(m, np.zeros(m["nCells"]), flux)
+    return thickness_flux_div_on_cell(m, np.zeros(flux.shape[:-1] + (m["nCells"],)), flux)
 
 
 # --------------------------------------------------------------------------------------------
@@ -140,6 +140,21 @@ def resting_thickness_sum(m):
     return m["restingThickness"].sum(axis=1)
 
 
+def ssh_from_thickness(m, h):
+    """Update_ssh!, time_integration.jl:205-212: ssh = layerThickness[1, j] - restingThicknessSum[j] for the single layer the
+    reference runs.  MULTI-LEVEL (project-defined; state arrays of shape (nVertLevels, n), level-major): the
+    free surface is the top of the whole column, ssh = (h[0] + h[1] + ... in level order) - restingThicknessSum -- with one
+    level the reference's expression, bit for bit.  Everything else in this file takes the level axis along by broadcasting:
+    the reference's kernels already carry the `for k in 1:maxLevelEdgeTop` loops (pressure_gradient.jl:61-64,
+    horizontal_advection_and_coriolis.jl:69-73, horizontal_advection.jl:60-66) with the SAME pressure gradient for every level."""
+    if h.ndim == 1:
+        return h - resting_thickness_sum(m)
+    col = h[0].copy()
+    for k in range(1, h.shape[0]):
+        col = col + h[k]
+    return col - resting_thickness_sum(m)
+
+
 def new_state(m, ssh, u, h):
     """PrognosticVars(ssh, normalVelocity, layerThickness, 2), PrognosticVars.jl:28-56."""
     return {"ssh": [ssh.copy(), ssh.copy()], "normalVelocity": [u.copy(), u.copy()],
@@ -160,7 +175,7 @@ def timestep_forward_euler(m, prog, diag, dt):
     th = compute_layer_thickness_tendency(m, diag["thicknessFlux"])
     prog["normalVelocity"][-1] = prog["normalVelocity"][-1] + dt * tu    # :196-202
     prog["layerThickness"][-1] = prog["layerThickness"][-1] + dt * th
-    prog["ssh"][-1] = prog["layerThickness"][-1] - resting_thickness_sum(m)   # :205-212
+    prog["ssh"][-1] = ssh_from_thickness(m, prog["layerThickness"][-1])       # :205-212
     return tu, th
 
 
@@ -171,7 +186,7 @@ def tendencies_consistent(m, u, h):
     (interpolateCell2Edge), flux = u*hEdge (compute_thicknessFlux!), then the two tendency
     entry points -- without the ForwardEuler ordering artefact Q1.
     """
-    ssh = h - resting_thickness_sum(m)                                   # :127
+    ssh = ssh_from_thickness(m, h)                                       # :127
     flux = u * interpolate_cell2edge(m, h)
     return compute_normal_velocity_tendency(m, ssh, u), compute_layer_thickness_tendency(m, flux)
 
@@ -198,7 +213,7 @@ def timestep_rk4(m, prog, dt):
         h_new = h_new + b[s] * th
     prog["normalVelocity"][-1] = u_new
     prog["layerThickness"][-1] = h_new
-    prog["ssh"][-1] = h_new - resting_thickness_sum(m)
+    prog["ssh"][-1] = ssh_from_thickness(m, h_new)
 
 
 def sum_array(ssh):

@@ -1,5 +1,7 @@
-"""torchrun entry: one process per GPU, NCCL halo exchange, parity of the gathered result against the
-single-domain CPU oracle (rel-L2 <= 1e-12) with and without compute/communication overlap."""
+"""torchrun entry: one process per GPU, the library's own decomposed stepping (mokab_comm_init / mokab_decomp_setup /
+mokab_timestep_*_decomposed: NCCL send/recv or direct peer stores inside libmoka_b200.so), parity of the gathered result
+against the single-domain CPU oracle (rel-L2 <= 1e-12) for every halo path and schedule.  torch.distributed (gloo) is the
+control plane only."""
 import os
 import sys
 
@@ -19,26 +21,29 @@ from moka_b200 import multi_gpu, partition  # noqa: E402
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    nx, nsteps = 96, 20
+    dist.init_process_group("gloo")
+    nx, nsteps = int(os.environ.get("MOKAB_CHECK_NX", "96")), 21
     m = mb.periodic_hex(nx, nx, 1.0e7 / nx, with_dual=False)
     state = mb.inertialGravityWave(m).initial_state()
     dt = mb.cfl_dt(m["dc"])
     loc = partition.decompose(m, world)[rank]
     backend = mb.B200(local)
+    rt = multi_gpu.TorchRuntime(local, device="cpu")
+    comm = multi_gpu.Communicator(backend, rt)          # one NCCL communicator for all the models below
     errs = []
-    # the packed NCCL all-to-all in its three schedules; with MOKAB_CHECK_P2P=1 also the direct-store exchange
-    # (csrc/kernels_p2p.cuh -- checked on the simulated runtime only so far, so it is not part of the default run yet)
-    cases = [(True, False, "nccl", "RungeKutta4"), (False, False, "nccl", "RungeKutta4"), (True, True, "nccl", "RungeKutta4")]
-    if os.environ.get("MOKAB_CHECK_P2P", "0") == "1":
-        cases += [(True, False, "p2p", "RungeKutta4"), (True, True, "p2p", "RungeKutta4"), (True, False, "p2p_fused", "RungeKutta4"),
-                  (True, True, "p2p_fused", "RungeKutta4")]
-    # with MOKAB_CHECK_FE=1 the staged ForwardEuler as well (same status: simulated runtime only so far)
-    if os.environ.get("MOKAB_CHECK_FE", "0") == "1":
-        cases += [(True, False, "nccl", "ForwardEuler"), (False, False, "nccl", "ForwardEuler")]
+    # (overlap, graph, halo, stepper): the packed NCCL exchange in its three schedules, the direct-store exchange as push / wait
+    # kernels and folded into the boundary launch, ForwardEuler (the reference driver's stepper) host-launched and as graphs
+    cases = [(True, False, "nccl", "RungeKutta4"), (False, False, "nccl", "RungeKutta4"), (True, True, "nccl", "RungeKutta4"),
+             (True, False, "p2p", "RungeKutta4"), (True, True, "p2p", "RungeKutta4"), (True, False, "p2p_fused", "RungeKutta4"),
+             (True, True, "p2p_fused", "RungeKutta4"), (True, False, "nccl", "ForwardEuler"), (False, False, "nccl", "ForwardEuler"),
+             (True, True, "nccl", "ForwardEuler")]
+    if os.environ.get("MOKAB_CHECK_HALO"):
+        cases = [c for c in cases if c[2] in os.environ["MOKAB_CHECK_HALO"].split(",")]
     for overlap, graph, halo, stepper in cases:
-        model = multi_gpu.DecomposedModel(loc, multi_gpu.local_state(loc, *state), backend, local, overlap=overlap, graph=graph, halo=halo)
-        model.step(dt, nsteps, stepper=getattr(mb, stepper))
+        model = multi_gpu.DecomposedModel(loc, multi_gpu.local_state(loc, *state), backend, local, overlap=overlap, graph=graph, halo=halo,
+                                          runtime=rt, comm=comm)
+        for n in (8, 1, 10, 2):                      # 21 steps; the odd call moves the time-level parity between graph replays
+            model.step(dt, n, stepper=getattr(mb, stepper))
         model.finish()
         gs, gu, gh = multi_gpu.gather_owned(model, m["nCells"], m["nEdges"])
         mass = model.reduce("mass")
@@ -58,6 +63,7 @@ def main():
         ok = all(max(e) <= 1e-12 and dm <= 1e-13 for _, e, dm, _ in errs)
         print("MULTI_GPU_CHECK_OK" if ok else "MULTI_GPU_CHECK_FAILED")
     sys.stdout.flush()
+    comm.destroy()
     dist.barrier()
     torch.cuda.synchronize()
     dist.destroy_process_group()

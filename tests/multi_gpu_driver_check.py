@@ -45,7 +45,7 @@ def main():
     halo = sys.argv[1] if len(sys.argv) > 1 else "nccl"
     stepper = sys.argv[2] if len(sys.argv) > 2 else "RK4"
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dist.init_process_group("gloo")                      # control plane only; the exchange is NCCL inside the library
     tag = f"/dev/shm/mokab_driver_{os.environ.get('MASTER_PORT', '0')}"
     mesh_fp, out_fp, cfg = tag + "_mesh.nc", tag + "_out.nc", tag + "_cfg.yml"
     m = mb.periodic_hex(48, 48, 300.0e3)                 # dc = 300 km: the reference's dt rule gives 900 s
@@ -56,7 +56,9 @@ def main():
             f.write(YAML.format(mesh=mesh_fp, out=out_fp, stepper=stepper))
     dist.barrier()
     series = []
-    Setup, model, nsteps = mb.driver.ocn_run_decomposed(cfg, mb.B200(local), local, halo=halo, series=series)
+    from moka_b200 import multi_gpu
+    Setup, model, nsteps = mb.driver.ocn_run_decomposed(cfg, mb.B200(local), local, halo=halo, series=series,
+                                                        runtime=multi_gpu.TorchRuntime(local, device="cpu"))
     status = model.graph_status
     model.close()
     ok = True

@@ -306,3 +306,41 @@ def test_staged_forward_euler_on_an_undecomposed_mesh_interoperates_with_the_who
     assert np.array_equal(prog.ssh, ref5.ssh)
     mb.ocn_timestep(dt, prog, None, None, None, mb.ForwardEuler, nsteps=3)
     assert np.array_equal(prog.normalVelocity, ref8.normalVelocity) and np.array_equal(prog.layerThickness, ref8.layerThickness)
+
+
+class _SoloRuntime:
+    """Control plane of a one-rank "job": nothing to hand to anybody."""
+
+    def rank_and_size(self):
+        return 0, 1
+
+    def broadcast_bytes(self, blob, src=0):
+        return blob
+
+
+@pytest.mark.parametrize("halo,graph,stepper", [("nccl", True, "RungeKutta4"), ("nccl", False, "RungeKutta4"), ("p2p_fused", True, "RungeKutta4"),
+                                                ("nccl", True, "ForwardEuler")])
+def test_in_library_decomposed_entry_points_with_one_rank(backend, halo, graph, stepper):
+    """mokab_comm_init / mokab_decomp_setup / mokab_timestep_*_decomposed (csrc/decomposed.cuh) on a communicator of ONE rank:
+    the real NCCL initialisation, the halo stream fork / join, the captured 1- and 2-step graphs for both time-level parities
+    -- everything but a neighbour -- on a one-GPU box; the multi-rank schedule runs under torchrun (tests/multi_gpu_check.py)
+    and with emulated ranks on the simulated runtime (tests/sim/check_decomposed.py).  Same bits as the single-domain call."""
+    m = hex_mesh(48, with_dual=False)
+    state = mb.inertialGravityWave(m).initial_state()
+    dt = mb.cfl_dt(m["dc"])
+    loc = partition.decompose(m, 1)[0]
+    model = multi_gpu.DecomposedModel(loc, multi_gpu.local_state(loc, *state), backend, 0, graph=graph, runtime=_SoloRuntime(), halo=halo)
+    st = getattr(mb, stepper)
+    for n in (3, 4, 1, 2):                       # odd counts move the time-level parity between the calls
+        model.step(dt, n, stepper=st)
+    model.finish()
+    gs, gu, gh = model.gather(m["nCells"], m["nEdges"])
+    mass = model.reduce("mass")
+    status = model.graph_status
+    model.close()
+    om = OC.OracleModel(m, *state)
+    om.run_loop(dt, 10, stepper)
+    assert np.array_equal(gu, om.normalVelocity[1]) and np.array_equal(gh, om.layerThickness[1]) and np.array_equal(gs, om.ssh[1])
+    assert abs(mass - float(np.sum(m["areaCell"] * om.layerThickness[1]))) <= 1e-13 * mass
+    if graph and stepper == "RungeKutta4":
+        assert status.startswith("validated"), status
