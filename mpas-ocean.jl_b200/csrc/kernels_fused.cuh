@@ -104,6 +104,7 @@ struct StageArgs {
     const PushStage<R> *push;  // PUSH launches only (device memory); nullptr otherwise
     int pf, pfDist;            // L2 prefetch of the streaming operands (moka_b200.cu: Options::stage_prefetch), distance in launched blocks
     int wStride;               // TMA = 1 launches only: elements between the staged weight rows in shared memory
+    const R *wfI;              // TMA = 3: the weights again, slot-INTERLEAVED -- 16 bytes per edge and slot group (k_build_wf_interleaved)
     const R *wfB;              // TMA = 2: the weights again, BLOCK-major -- block b's S2 rows back to back, each padded to 16 bytes,
     const long long *wfBOff;   //          starting at element wfBOff[b] (16-byte aligned): one contiguous run, one bulk copy per block
 };
@@ -121,6 +122,37 @@ struct StageArgs {
 #ifndef MOKAB_DER_MINBLOCKS_F32
 #define MOKAB_DER_MINBLOCKS_F32 5
 #endif
+// TMA = 3 (opt-in, "stage_tma" = 3): the Coriolis weights of an edge -- 80 of the ~100 bytes it streams in Float64 -- land in
+// SHARED memory through per-thread asynchronous copies (cp.async.cg, 16 bytes = the weights of one edge for two (Float64) /
+// four (Float32) consecutive slots of the slot-interleaved copy wfI) instead of in registers.  They are issued first, fly
+// while the thread does its index loads and gathers, and are read back (conflict-free: every thread reads what it copied,
+// no barrier) only where the weighted sum starts.  The ten weights no longer occupy twenty registers across the gather
+// latency, so a Float64 thread fits in 51 registers (5 resident blocks instead of 4) and a Float32 thread in 42 (6 instead of
+// 5): more warps per SM for a kernel that ncu shows latency-bound at 47 % occupancy (profiles/README.md r02b).
+#ifndef MOKAB_CPA_MINBLOCKS_F64
+#define MOKAB_CPA_MINBLOCKS_F64 5
+#endif
+#ifndef MOKAB_CPA_MINBLOCKS_F32
+#define MOKAB_CPA_MINBLOCKS_F32 6
+#endif
+template <class R> __host__ __device__ constexpr int cpa_vec() { return 16 / (int)sizeof(R); }                      // weights per 16-byte copy
+template <class R, int S2T> __host__ __device__ constexpr int cpa_groups() { return (S2T + cpa_vec<R>() - 1) / cpa_vec<R>(); }
+__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src)
+{
+#ifdef MOKAB_SIM
+    memcpy(smem_dst, gmem_src, 16);
+#else
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+#ifndef MOKAB_SIM
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+
 template <class R> constexpr int der_minblocks() { return sizeof(R) == 8 ? MOKAB_DER_MINBLOCKS_F64 : MOKAB_DER_MINBLOCKS_F32; }
 // resident blocks of kThreads threads the stage kernel is compiled for (MOKAB_DER_RAW_BLOCKS_*: tuning builds that want a
 // count the 256-thread scale cannot express, e.g. nine blocks of 128 threads)
@@ -132,6 +164,7 @@ template <class R, bool DER, int TMA> constexpr int stage_blocks()
 #ifdef MOKAB_DER_RAW_BLOCKS_F32
     if (DER && TMA == 0 && sizeof(R) == 4) return MOKAB_DER_RAW_BLOCKS_F32;
 #endif
+    if (TMA == 3) return MOKAB_BLOCKS_SCALED(sizeof(R) == 8 ? MOKAB_CPA_MINBLOCKS_F64 : MOKAB_CPA_MINBLOCKS_F32);
     return MOKAB_BLOCKS_SCALED(TMA != 0 ? 3 : DER ? der_minblocks<R>() : MOKAB_MINBLOCKS);
 }
 // TMA = 1 (opt-in, MOKAB_STAGE_TMA=1; compile-time row widths only): the Coriolis weights of the block's edges -- ten
@@ -160,13 +193,18 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
     const int b = A.blockList ? A.blockList[blockIdx.x] : blockIdx.x;
     const int cBase = b * kTC;
     static_assert(TMA == 0 || (S2T != 0 && ST != 0), "the TMA variants stage compile-time many weight rows");
+    [[maybe_unused]] unsigned char *cpa_slot = nullptr;             // TMA = 3: this thread's 16-byte slots, one per slot group, kThreads * 16 bytes apart
+    if constexpr (TMA == 3) {
+        MOKAB_DYN_SMEM(dyn3);
+        cpa_slot = dyn3 + (size_t)threadIdx.x * 16;
+    }
     [[maybe_unused]] const R *sw = nullptr;
     [[maybe_unused]] bool weights_landed = false;
 #ifndef MOKAB_SIM
     [[maybe_unused]] typename cuda::barrier<cuda::thread_scope_block>::arrival_token tma_token;
     [[maybe_unused]] cuda::barrier<cuda::thread_scope_block> *tma_bar = nullptr;
 #endif
-    if constexpr (TMA != 0) {
+    if constexpr (TMA == 1 || TMA == 2) {
         MOKAB_DYN_SMEM(dyn);
         R *dst = reinterpret_cast<R *>(dyn);
         sw = dst;
@@ -299,6 +337,12 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
             // the index nor the weight loads depend on nEdgesOnEdge, and one DRAM latency covers them all.
             int idx[S2T ? S2T : 1];
             R w[S2T ? S2T : 1];
+            if constexpr (TMA == 3) {
+                constexpr int NG = cpa_groups<R, S2T>();
+#pragma unroll
+                for (int gq = 0; gq < NG; ++gq)
+                    cp_async_16(cpa_slot + (size_t)gq * kThreads * 16, A.wfI + ((size_t)gq * nE + e) * cpa_vec<R>());
+            }
             const unsigned pp = ppCur;
             if (!(kDer && derived)) {
 #pragma unroll
@@ -360,7 +404,18 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
             R uu[S2T ? S2T : 1];
 #pragma unroll
             for (int i = 0; i < S2T; ++i) uu[i] = __ldg(A.uOld + idx[i]);
-            if constexpr (TMA != 0) {   // the staged rows: wait for the bulk copies once, then plain shared-memory reads (conflict-free: edge-major)
+            if constexpr (TMA == 3) {   // this thread's own copies have landed: read them back (16-byte shared-memory loads, no bank conflicts)
+                cp_async_wait_all();
+                constexpr int NG = cpa_groups<R, S2T>(), V = cpa_vec<R>();
+#pragma unroll
+                for (int gq = 0; gq < NG; ++gq) {
+                    const R *q = reinterpret_cast<const R *>(cpa_slot + (size_t)gq * kThreads * 16);
+#pragma unroll
+                    for (int j = 0; j < V; ++j)
+                        if (gq * V + j < S2T) w[gq * V + j] = q[j];
+                }
+            }
+            if constexpr (TMA == 1 || TMA == 2) {   // the staged rows: wait for the bulk copies once, then plain shared-memory reads (conflict-free: edge-major)
 #ifndef MOKAB_SIM
                 if (!weights_landed) {
                     tma_bar->wait(std::move(tma_token));
@@ -509,7 +564,10 @@ struct StageArgsML {
 };
 
 template <int STAGE, int S2T, int ST, bool FOLD>
-__global__ void __launch_bounds__(kThreads, MOKAB_BLOCKS_SCALED(3))
+#ifndef MOKAB_ML_MINBLOCKS
+#define MOKAB_ML_MINBLOCKS 2   // <= 128 registers: the column loop keeps a row of indices, weights and metrics live (3 blocks spill)
+#endif
+__global__ void __launch_bounds__(kThreads, MOKAB_BLOCKS_SCALED(MOKAB_ML_MINBLOCKS))
 k_rk_stage_ml(const StageArgsML A, int S2rt, int Srt)
 {
     const int S2 = S2T ? S2T : S2rt, S = ST ? ST : Srt;
@@ -694,6 +752,22 @@ k_build_fused_edges(int nE, int S2, const double *__restrict__ dc, const double 
         wf[k] = x >= 0 ? (foldF ? (R)__dmul_rn(woe[k], fE[x]) : (R)woe[k]) : R(0);
         if (eoeF) eoeF[k] = x >= 0 ? x : e;
     }
+}
+
+// the weights once more, slot-interleaved (TMA = 3): element ((g * nE + e) * V + j) = weight of slot g * V + j of edge e, V = 16 bytes / sizeof(R)
+template <class R>
+__global__ void __launch_bounds__(256)
+k_build_wf_interleaved(int nE, int S2, const R *__restrict__ wf, R *__restrict__ wfI)
+{
+    constexpr int V = 16 / (int)sizeof(R);
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e >= nE) return;
+    const int NG = (S2 + V - 1) / V;
+    for (int g = 0; g < NG; ++g)
+        for (int j = 0; j < V; ++j) {
+            const int i = g * V + j;
+            wfI[((size_t)g * nE + e) * V + j] = i < S2 ? wf[(size_t)i * nE + e] : R(0);
+        }
 }
 
 // the weights once more, block-major (TMA = 2): block b's S2 rows back to back at wfBOff[b], each padded to a multiple of 16 bytes

@@ -363,6 +363,7 @@ template <class R>
 struct FusedMesh {
     DevBuf<R> gdc, wf, dv, invArea, H;
     DevBuf<R> wfT;             // adjoint: transposed Coriolis weights (see moka_b200.cu: ensure_adjoint_mesh)
+    DevBuf<R> wfI;             // TMA = 3 stage variant: the weights slot-interleaved, 16 bytes per edge and slot group (built on first use)
     DevBuf<R> wfB;             // TMA = 2 stage variant: the weights block-major (built on first use)
     DevBuf<long long> wfBOff;  //                        first element of every block's run
     bool ready = false;

@@ -721,7 +721,7 @@ static int p2p_target(const mokab_state *st, int stage);
 // ---- tuning options (mokab_set_option; process-wide; the environment gives the initial values) ---------------------------------
 // Captured graphs bake the options into their kernel arguments: every change bumps `epoch` and the graphs are rebuilt on next use.
 struct Options {
-    int stage_tma = 0;            // MOKAB_STAGE_TMA: 1 / 2 = the bulk-copy variants of the stage kernel (kernels_fused.cuh)
+    int stage_tma = 0;            // MOKAB_STAGE_TMA: 1 / 2 = the bulk-copy variants of the stage kernel, 3 = weights through per-thread cp.async (kernels_fused.cuh)
     int stage_prefetch = 0;       // MOKAB_STAGE_PREFETCH: bit 0 = a block prefetches the streams of its own later edge iterations and of
                                   // its cell phase into L2 at entry; bit 1 = it prefetches the streams of the block launched
                                   // `stage_prefetch_distance` blocks after it
@@ -734,7 +734,7 @@ struct Options {
     {
         auto geti = [](const char *n, int d) { const char *e = getenv(n); return e && *e ? atoi(e) : d; };
         stage_tma = geti("MOKAB_STAGE_TMA", 0);
-        if (stage_tma < 0 || stage_tma > 2) stage_tma = 0;
+        if (stage_tma < 0 || stage_tma > 3) stage_tma = 0;
         stage_prefetch = geti("MOKAB_STAGE_PREFETCH", 0) & 3;
         stage_prefetch_distance = std::max(0, geti("MOKAB_STAGE_PREFETCH_DISTANCE", 0));
         stage_wf_block_major = geti("MOKAB_STAGE_WF_BLOCK_MAJOR", 0) ? 1 : 0;
@@ -784,6 +784,20 @@ static void ensure_wf_block_major(mokab_mesh *m)
     MOKAB_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
+// TMA = 3: the slot-interleaved copy of the weights (built once per mesh and precision, synchronised like ensure_fused)
+template <class R>
+static void ensure_wf_interleaved(mokab_mesh *m)
+{
+    FusedMesh<R> &f = fused_of<R>(m);
+    if (stage_tma_mode() != 3 || f.wfI.n || !(m->S2 == 10 && m->S == 6)) return;
+    mokab_ctx *ctx = m->ctx;
+    constexpr int V = 16 / (int)sizeof(R);
+    const int NG = (m->S2 + V - 1) / V;
+    f.wfI.alloc((size_t)NG * m->nE * V);
+    LAUNCH(ctx, fused::k_build_wf_interleaved<R>, nblk(m->nE), 256, (int)m->nE, m->S2, (const R *)f.wf.p, f.wfI.p);
+    MOKAB_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
 // ---- fused RK4 ------------------------------------------------------------------------------------------------
 template <class R, int STAGE>
 static void launch_stage(mokab_ctx *ctx, const mokab_mesh *m, fused::StageArgs<R> A, int part = MOKAB_PART_ALL,
@@ -813,7 +827,23 @@ static void launch_stage(mokab_ctx *ctx, const mokab_mesh *m, fused::StageArgs<R
         FusedMesh<R> &fm = fused_of<R>(const_cast<mokab_mesh *>(m));
         if (fm.wfB.n) { A.wfB = fm.wfB.p; A.wfBOff = fm.wfBOff.p; }
     }
-    if (hex && stage_tma_enabled()) {   // opt-in: the weight rows of a block through bulk asynchronous copies (kernels_fused.cuh)
+    if (hex && stage_tma_mode() == 3 && part != MOKAB_PART_BOUNDARY_PUSH) {   // opt-in: weights through per-thread cp.async into shared memory
+        FusedMesh<R> &fm = fused_of<R>(const_cast<mokab_mesh *>(m));
+        if (fm.wfI.n) {
+            A.wfI = fm.wfI.p;
+            const size_t smem = (size_t)fused::cpa_groups<R, 10>() * fused::kThreads * 16;
+#define MOKAB_STAGE_CPA(FOLD, DER) fused::k_rk_stage<R, STAGE, 10, 6, FOLD, DER, false, 3><<<grid, fused::kThreads, smem, s>>>(A, m->S2, m->S)
+            if (der && m->uniformF)      MOKAB_STAGE_CPA(false, true);
+            else if (der)                MOKAB_STAGE_CPA(true, true);
+            else if (m->uniformF)        MOKAB_STAGE_CPA(false, false);
+            else                         MOKAB_STAGE_CPA(true, false);
+#undef MOKAB_STAGE_CPA
+            MOKAB_CUDA(cudaGetLastError());
+            ctx->launches++;
+            return;
+        }
+    }
+    if (hex && (stage_tma_mode() == 1 || stage_tma_mode() == 2)) {   // opt-in: the weight rows of a block through bulk asynchronous copies (kernels_fused.cuh)
         constexpr int AL = fused::tma_align<R>();
         A.wStride = (m->maxBlockEdges + AL + AL - 1) / AL * AL;
         const size_t smem = (size_t)10 * A.wStride * sizeof(R);
@@ -877,7 +907,7 @@ static fused::StageArgs<R> stage_args(mokab_state *st, double dt, int p, int sta
     A.a = (R)a[stage - 1]; A.b = (R)b[stage - 1];
     A.f0 = (R)m->f0;
     A.push = nullptr;
-    A.wStride = 0; A.wfB = nullptr; A.wfBOff = nullptr;
+    A.wStride = 0; A.wfB = nullptr; A.wfBOff = nullptr; A.wfI = nullptr;
     A.pf = options().stage_prefetch;
     A.pfDist = options().stage_prefetch_distance > 0 ? options().stage_prefetch_distance
                                                        : st->ctx->num_sms * (sizeof(R) == 8 ? 4 : 5);
@@ -919,6 +949,7 @@ static void run_stage(mokab_state *st, double dt, int stage, int part, cudaStrea
     ensure_fused<R>(const_cast<mokab_mesh *>(m));
     stage_tma_prepare<R>();
     ensure_wf_block_major<R>(const_cast<mokab_mesh *>(m));
+    ensure_wf_interleaved<R>(const_cast<mokab_mesh *>(m));
     fused::StageArgs<R> A = stage_args<R>(st, dt, st->cur, stage);
     if (part == MOKAB_PART_BOUNDARY_PUSH) {
         MOKAB_REQUIRE(st->p2p.ready, "rk4_stage(MOKAB_PART_BOUNDARY_PUSH): call mokab_p2p_setup first");
@@ -1118,6 +1149,7 @@ static void run_rk4_fused(mokab_state *st, double dt, int64_t nsteps)
     ensure_fused<R>(const_cast<mokab_mesh *>(st->mesh));
     stage_tma_prepare<R>();
     ensure_wf_block_major<R>(const_cast<mokab_mesh *>(st->mesh));
+    ensure_wf_interleaved<R>(const_cast<mokab_mesh *>(st->mesh));
     if (t->taping) {  // record the state before every step (plain launches: the tape slot changes per step)
         const mokab_mesh *m = st->mesh;
         MOKAB_REQUIRE((int64_t)t->tapeDt.size() + nsteps <= t->tapeCap, "timestep_rk4: the tape is full (mokab_tape_begin max_steps)");
@@ -1243,6 +1275,7 @@ static void ensure_adjoint(mokab_state *st)
     ensure_fused<R>(m);
     stage_tma_prepare<R>();
     ensure_wf_block_major<R>(m);
+    ensure_wf_interleaved<R>(m);
     ensure_adjoint_mesh(m);
     ensure_adj_state<R>(st);
     FusedMesh<R> &f = fused_of<R>(m);
@@ -2393,7 +2426,7 @@ int mokab_set_option(const char *name, int64_t value)
         MOKAB_REQUIRE(name, "set_option: name is NULL");
         Options &o = options();
         const std::string n(name);
-        if (n == "stage_tma") { MOKAB_REQUIRE(value >= 0 && value <= 2, "set_option: stage_tma must be 0, 1 or 2"); o.stage_tma = (int)value; }
+        if (n == "stage_tma") { MOKAB_REQUIRE(value >= 0 && value <= 3, "set_option: stage_tma must be 0..3"); o.stage_tma = (int)value; }
         else if (n == "stage_prefetch") { MOKAB_REQUIRE(value >= 0 && value <= 3, "set_option: stage_prefetch must be 0..3"); o.stage_prefetch = (int)value; }
         else if (n == "stage_prefetch_distance") { MOKAB_REQUIRE(value >= 0 && value < (1 << 30), "set_option: bad stage_prefetch_distance"); o.stage_prefetch_distance = (int)value; }
         else if (n == "stage_wf_block_major") o.stage_wf_block_major = value ? 1 : 0;
