@@ -358,8 +358,10 @@ int  mokab_decomp_close(mokab_state *state);
  * workgroup size hard-coded at each launch, e.g. src/forward/time_integration.jl:181).  Results are bit-identical under every
  * setting.  "stage_prefetch": bit 0 = a block pulls the streams of its later iterations into L2 at entry, bit 1 = those of
  * the block launched "stage_prefetch_distance" blocks later (0 = one wave of resident blocks); "stage_tma": 1 / 2 = the
- * Coriolis weights through bulk asynchronous copies (slot-major rows / a block-major copy).  Initial values come from the
- * environment (MOKAB_STAGE_PREFETCH, MOKAB_STAGE_PREFETCH_DISTANCE, MOKAB_STAGE_TMA). */
+ * Coriolis weights through bulk asynchronous copies (slot-major rows / a block-major copy), 3 = through per-thread cp.async into
+ * shared memory (one more resident block per SM).  Defaults: stage_tma = 3, stage_prefetch = 1 (the fastest on B200,
+ * profiles/README.md r02d); the environment overrides them (MOKAB_STAGE_PREFETCH, MOKAB_STAGE_PREFETCH_DISTANCE,
+ * MOKAB_STAGE_TMA). */
 int  mokab_set_option(const char *name, int64_t value);
 int  mokab_get_option(const char *name, int64_t *value);
 /* number of interior / boundary blocks of the fused kernel (diagnostic) */

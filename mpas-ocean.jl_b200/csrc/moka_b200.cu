@@ -721,8 +721,8 @@ static int p2p_target(const mokab_state *st, int stage);
 // ---- tuning options (mokab_set_option; process-wide; the environment gives the initial values) ---------------------------------
 // Captured graphs bake the options into their kernel arguments: every change bumps `epoch` and the graphs are rebuilt on next use.
 struct Options {
-    int stage_tma = 0;            // MOKAB_STAGE_TMA: 1 / 2 = the bulk-copy variants of the stage kernel, 3 = weights through per-thread cp.async (kernels_fused.cuh)
-    int stage_prefetch = 0;       // MOKAB_STAGE_PREFETCH: bit 0 = a block prefetches the streams of its own later edge iterations and of
+    int stage_tma = 3;            // MOKAB_STAGE_TMA: 1 / 2 = the bulk-copy variants of the stage kernel, 3 = weights through per-thread cp.async (kernels_fused.cuh)
+    int stage_prefetch = 1;       // MOKAB_STAGE_PREFETCH: bit 0 = a block prefetches the streams of its own later edge iterations and of
                                   // its cell phase into L2 at entry; bit 1 = it prefetches the streams of the block launched
                                   // `stage_prefetch_distance` blocks after it
     int stage_prefetch_distance = 0;   // MOKAB_STAGE_PREFETCH_DISTANCE: 0 = one wave of resident blocks (SMs x blocks per SM)
@@ -733,9 +733,12 @@ struct Options {
     Options()
     {
         auto geti = [](const char *n, int d) { const char *e = getenv(n); return e && *e ? atoi(e) : d; };
-        stage_tma = geti("MOKAB_STAGE_TMA", 0);
+        // defaults = the fastest bit-identical variant measured on B200 (profiles/README.md r02d): weights through per-thread
+        // cp.async (5 resident blocks instead of 4 in Float64, 6 instead of 5 in Float32) + L2 prefetch of a block's own later
+        // iterations; (10, 6) meshes only, everything else runs the plain kernel whatever the switches say
+        stage_tma = geti("MOKAB_STAGE_TMA", 3);
         if (stage_tma < 0 || stage_tma > 3) stage_tma = 0;
-        stage_prefetch = geti("MOKAB_STAGE_PREFETCH", 0) & 3;
+        stage_prefetch = geti("MOKAB_STAGE_PREFETCH", 1) & 3;
         stage_prefetch_distance = std::max(0, geti("MOKAB_STAGE_PREFETCH_DISTANCE", 0));
         stage_wf_block_major = geti("MOKAB_STAGE_WF_BLOCK_MAJOR", 0) ? 1 : 0;
     }

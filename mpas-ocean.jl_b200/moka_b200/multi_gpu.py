@@ -294,61 +294,40 @@ def gather_owned(model: DecomposedModel, nC: int, nE: int):
 
 # ---- bench leg for torchrun (N > 1) -------------------------------------------------------------------------
 def _share_locals(args, rank, world, nx, dtype, keep_global=False):
-    """Rank 0 builds the global mesh, decomposes it and hands every rank its local mesh through /dev/shm.  With
-    `keep_global` rank 0 also returns (mesh, state) for the parity check of the bench line."""
+    """Every rank generates the (deterministic) global mesh, derives the same partition from it and keeps its own part --
+    no rank waits for another, nothing goes through files.  With `keep_global` rank 0 also returns (mesh, state) for the
+    parity check of the bench line."""
     import torch.distributed as dist
-    tag = f"/dev/shm/mokab_{os.environ.get('MASTER_PORT', '0')}_{nx}_{world}"
     t0 = time.time()
-    glob = None
-    if rank == 0:
-        from . import planar_hex
-        if args.workload.startswith("kelvin"):
-            m = planar_hex.channel_hex(nx, nx, 1.0e7 / nx)
-            ssh, u, h = api.kelvinWave(m).initial_state()
-        elif args.workload.startswith("voronoi"):
-            from . import planar_voronoi
-            m = planar_voronoi.periodic_voronoi(nx, nx, 1.0e7 / nx, jitter=0.25, seed=2, allow_obtuse=True, with_dual=False)
-            ssh, u, h = api.inertialGravityWave(m).initial_state()
-        elif args.workload.startswith("sphere"):
-            from . import spherical_voronoi
-            m = spherical_voronoi.spherical_voronoi(nx * nx, with_dual=False)
-            ssh, u, h = spherical_voronoi.geostrophic_zonal_flow(m)
-            u = u + 0.1 * np.random.default_rng(0).standard_normal(m["nEdges"])
-            m["bench_dt"] = 0.25 * float(m["dcEdge"].min()) / float(np.sqrt(api.GRAVITY * 1000.0))
-        else:
-            m = planar_hex.periodic_hex(nx, nx, 1.0e7 / nx, with_dual=False)
-            ssh, u, h = api.inertialGravityWave(m).initial_state()
-        locs = partition.decompose(m, world)
-        for r, loc in enumerate(locs):
-            ls = local_state(loc, ssh, u, h)
-            flat = {k: v for k, v in loc.items() if isinstance(v, np.ndarray)}
-            meta = {k: v for k, v in loc.items() if not isinstance(v, (np.ndarray, dict))}
-            if "bench_dt" in m:
-                meta["bench_dt"] = m["bench_dt"]
-            halo = loc["halo"]
-            for q in halo["peers"]:
-                flat[f"halo_send_{q}"], flat[f"halo_recv_{q}"] = halo["send"][q], halo["recv"][q]
-            meta["peers"] = halo["peers"]
-            flat["state_ssh"], flat["state_u"], flat["state_h"] = ls
-            np.savez(f"{tag}_{r}.npz", meta=json.dumps(meta), **flat)
-        if keep_global:
-            glob = (m, (ssh, u, h))
-        del locs
+    from . import planar_hex
+    if args.workload.startswith("kelvin"):
+        m = planar_hex.channel_hex(nx, nx, 1.0e7 / nx)
+        ssh, u, h = api.kelvinWave(m).initial_state()
+    elif args.workload.startswith("voronoi"):
+        from . import planar_voronoi
+        m = planar_voronoi.periodic_voronoi(nx, nx, 1.0e7 / nx, jitter=0.25, seed=2, allow_obtuse=True, with_dual=False)
+        ssh, u, h = api.inertialGravityWave(m).initial_state()
+    elif args.workload.startswith("sphere"):
+        from . import spherical_voronoi
+        m = spherical_voronoi.spherical_voronoi(nx * nx, with_dual=False)
+        ssh, u, h = spherical_voronoi.geostrophic_zonal_flow(m)
+        u = u + 0.1 * np.random.default_rng(0).standard_normal(m["nEdges"])
+        m["bench_dt"] = 0.25 * float(m["dcEdge"].min()) / float(np.sqrt(api.GRAVITY * 1000.0))
+    else:
+        m = planar_hex.periodic_hex(nx, nx, 1.0e7 / nx, with_dual=False)
+        ssh, u, h = api.inertialGravityWave(m).initial_state()
+    z = m.get("zCell")
+    part = partition.rcb_partition(m["xCell"], m["yCell"], world, z if z is not None and np.ptp(z) > 0 else None)
+    loc = partition.build_local_mesh(m, part, rank)
+    sets = [None] * world                                        # what every rank holds as halo copies (sorted global ids: small)
+    dist.all_gather_object(sets, (loc["cellsGlobal"][loc["nCellsOwned"]:], loc["edgesGlobal"][loc["nEdgesOwned"]:]))
+    loc = partition.decompose_one(m, world, rank, part=part, loc=loc, halo_sets=sets)
+    if "bench_dt" in m:
+        loc["bench_dt"] = m["bench_dt"]
+    state = local_state(loc, ssh, u, h)
+    glob = (m, (ssh, u, h)) if (keep_global and rank == 0) else None
+    del m
     dist.barrier()
-    z = np.load(f"{tag}_{rank}.npz")
-    meta = json.loads(str(z["meta"]))
-    loc = {k: z[k] for k in z.files if k != "meta" and not k.startswith(("halo_", "state_"))}
-    loc.update({k: v for k, v in meta.items() if k != "peers"})
-    loc["halo"] = {"peers": meta["peers"], "send": {q: z[f"halo_send_{q}"] for q in meta["peers"]},
-                   "recv": {q: z[f"halo_recv_{q}"] for q in meta["peers"]}}
-    state = (z["state_ssh"], z["state_u"], z["state_h"])
-    dist.barrier()
-    if rank == 0:
-        for r in range(world):
-            try:
-                os.remove(f"{tag}_{r}.npz")
-            except OSError:
-                pass
     if keep_global:
         return loc, state, time.time() - t0, glob
     return loc, state, time.time() - t0

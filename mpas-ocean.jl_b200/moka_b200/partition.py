@@ -146,6 +146,53 @@ def decompose(m: dict, nparts: int, part: np.ndarray | None = None) -> list[dict
     return locs
 
 
+def _local_sets(m: dict, part: np.ndarray, rank: int):
+    """(halo cells, halo edges) of `rank` as sorted global ids -- the index sets of build_local_mesh without its arrays."""
+    S = m["maxEdges"]
+    coe = m["cellsOnEdge"].astype(np.int64) - 1
+    eoc = m["edgesOnCell"].astype(np.int64) - 1
+    slot_ok = np.arange(S)[None, :] < m["nEdgesOnCell"].astype(np.int64)[:, None]
+    owned_c = np.nonzero(part == rank)[0]
+    nb = coe[eoc[owned_c][slot_ok[owned_c]]].ravel()
+    nb = nb[nb >= 0]
+    halo_c = np.unique(nb[part[nb] != rank])
+    cells = np.concatenate([owned_c, halo_c])
+    e_all = np.unique(eoc[cells][slot_ok[cells]])
+    halo_e = e_all[part[coe[e_all, 0]] != rank]
+    return halo_c, halo_e
+
+
+def decompose_one(m: dict, nparts: int, rank: int, part: np.ndarray | None = None, loc: dict | None = None, halo_sets=None) -> dict:
+    """decompose(m, nparts)[rank] without building the other ranks' meshes: what every rank of a job computes for itself
+    from the (deterministic) global mesh (`loc`: its build_local_mesh result, when already at hand).  Only the other ranks' halo index sets are needed, to know what they expect from
+    this one -- including the corner case of a rank that needs an edge of this rank without sharing a cell with it."""
+    if part is None:
+        z = m.get("zCell")
+        part = rcb_partition(m["xCell"], m["yCell"], nparts, z if z is not None and np.ptp(z) > 0 else None)
+    if loc is None:
+        loc = build_local_mesh(m, part, rank)
+    recv = {q: v[0] for q, v in recv_lists(loc, nparts).items()}
+    coe0 = m["cellsOnEdge"][:, 0].astype(np.int64) - 1
+    oc_g, oe_g = loc["cellsGlobal"][:loc["nCellsOwned"]], loc["edgesGlobal"][:loc["nEdgesOwned"]]
+    send = {}
+    for q in range(nparts):
+        if q == rank:
+            continue
+        # (`halo_sets`: every rank's (halo cells, halo edges) as sorted global ids, e.g. all-gathered in a job where every rank
+        #  has built its own local mesh -- otherwise recomputed here)
+        hc, he = halo_sets[q] if halo_sets is not None else _local_sets(m, part, q)
+        gc, ge = hc[part[hc] == rank], he[part[coe0[he]] == rank]      # what q holds as halo copies of this rank's entities, in q's recv order
+        if gc.size or ge.size:
+            lc, le = np.searchsorted(oc_g, gc), np.searchsorted(oe_g, ge)
+            assert np.array_equal(oc_g[lc], gc) and np.array_equal(oe_g[le], ge)
+            send[q] = np.concatenate([lc, loc["nCells"] + le]).astype(np.int32)
+    peers = sorted(set(send) | set(recv))
+    loc["halo"] = {"peers": peers, "send": {q: send.get(q, np.zeros(0, np.int32)) for q in peers},
+                   "recv": {q: recv.get(q, np.zeros(0, np.int32)) for q in peers}}
+    loc["rank"], loc["nparts"] = rank, nparts
+    return loc
+
+
 def flat_halo(loc: dict, nparts: int):
     """Flatten the per-peer lists into the all-to-all layout: (send_idx, send_counts, recv_idx, recv_counts)."""
     h = loc["halo"]

@@ -229,3 +229,26 @@ def test_runtime_host_exchanges_over_gloo(tmp_path):
     world = 3
     mp.spawn(_exchange_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert [open(tmp_path / f"ok{r}").read() for r in range(world)] == ["1"] * world
+
+
+def test_decompose_one_equals_the_all_ranks_decomposition():
+    """partition.decompose_one (what every rank of the bench computes for itself) against decompose (all ranks at once), on a
+    hexagon mesh, a channel and a Voronoi mesh, for part counts that produce corner-only neighbours."""
+    import moka_b200 as mb
+    from moka_b200.planar_voronoi import periodic_voronoi
+    meshes = [mb.periodic_hex(24, 24, 1.0e5, with_dual=False), mb.channel_hex(20, 20, 1.0e5),
+              periodic_voronoi(16, 16, 1.0e5, jitter=0.3, seed=4)]
+    for m in meshes:
+        for P in (2, 3, 4, 8):
+            locs = partition.decompose(m, P)
+            sets = [(loc["cellsGlobal"][loc["nCellsOwned"]:], loc["edgesGlobal"][loc["nEdgesOwned"]:]) for loc in locs]
+            for r in range(P):
+                one = partition.decompose_one(m, P, r) if r % 2 else partition.decompose_one(m, P, r, halo_sets=sets)
+                ref = locs[r]
+                assert one["halo"]["peers"] == ref["halo"]["peers"]
+                for q in ref["halo"]["peers"]:
+                    assert np.array_equal(one["halo"]["send"][q], ref["halo"]["send"][q]) and np.array_equal(one["halo"]["recv"][q], ref["halo"]["recv"][q])
+                for k, v in ref.items():
+                    if isinstance(v, np.ndarray):
+                        assert np.array_equal(one[k], v), k
+                assert (one["rank"], one["nparts"], one["nCellsOwned"], one["nEdgesOwned"]) == (r, P, ref["nCellsOwned"], ref["nEdgesOwned"])
