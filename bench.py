@@ -381,9 +381,10 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-overlap", dest="no_overlap", action="store_true", help="multi-GPU: exchange after each full stage")
     ap.add_argument("--no-graph", dest="no_graph", action="store_true", help="multi-GPU: do not capture steps into a CUDA graph")
-    ap.add_argument("--halo", default="nccl", choices=["nccl", "p2p", "p2p_fused"],
-                    help="multi-GPU halo exchange: packed NCCL all-to-all (default) or direct stores into the peers' memory "
-                         "(csrc/kernels_p2p.cuh; not yet measured on hardware)")
+    ap.add_argument("--halo", default="p2p", choices=["nccl", "p2p", "p2p_fused"],
+                    help="multi-GPU halo exchange: direct stores into the peers' memory with push / wait kernels (default: the "
+                         "fastest at N = 2 and N = 8, profiles/README.md r02c / r02e), packed NCCL send/recv, or direct stores "
+                         "from inside the boundary launch")
     ap.add_argument("--explicit-eoe", dest="explicit_eoe", action="store_true",
                     help="ablation: read edgesOnEdge from memory instead of rebuilding it from edgesOnCell")
     ap.add_argument("--quick", action="store_true", help="profiling runs: no clock-sampling load loop, one e2e step")

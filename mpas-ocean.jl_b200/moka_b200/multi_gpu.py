@@ -354,12 +354,38 @@ def _collect_on_rank0(model, rank, world, nC, nE, tag):
     return out
 
 
+def bind_to_gpu_numa_node(device_index: int):
+    """Pin this process (and with it the page-locked buffers it allocates from now on) to the CPUs of the NUMA node the GPU
+    hangs off: with one process per GPU on a two-socket box, host<->device copies otherwise cross the socket interconnect and
+    all ranks' pinned memory can end up on one node.  Best effort -- returns the node id, or None when sysfs says nothing."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = torch.cuda.get_device_properties(device_index).pci_domain_id
+        dev = torch.cuda.get_device_properties(device_index).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def bench_main(args, rank, world, local):
     import torch
     import torch.distributed as dist
     from bench import (WORKLOADS, ClockSampler, algo_bytes_per_cell_step, algo_bytes_per_cell_step_general, measured_peak_gbs,
                        parity_against_oracle, workload_label)
     torch.cuda.set_device(local)
+    numa = None if os.environ.get("MOKAB_NO_NUMA_BIND") else bind_to_gpu_numa_node(local)
     # torch.distributed is the CONTROL plane only (gloo: sharing the decomposition through /dev/shm, handing out the
     # communicator id); every byte of halo data and every reduction moves through NCCL inside libmoka_b200.so
     dist.init_process_group("gloo")
@@ -472,7 +498,7 @@ def bench_main(args, rank, world, local):
                                  f"{'overlapped with interior blocks' if model.overlap else '(no overlap)'}"
                                  f"{', 1- / 2-step CUDA graphs incl. the exchange (' + model.graph_status + ')' if model.use_graph else ', CUDA graph ' + model.graph_status}",
                        "timed_steps": steps_timed, "repeats_of_steps": reps,
-                       "l2": "inputs larger than L2 (no flush)", "setup_s": round(t_setup, 1),
+                       "l2": "inputs larger than L2 (no flush)", "setup_s": round(t_setup, 1), "rank0_numa_node": numa,
                        "rank0_blocks_interior_boundary": list(blocks), "rank0_halo_bytes_per_stage": int(halo_bytes),
                        "rank0_blocks_rebuilding_edgesOnEdge": [int(nder), int(nblk)],
                        "variant": {"lib": os.environ.get("MOKAB_LIB", "libmoka_b200.so"),

@@ -175,7 +175,6 @@ def test_committed_adjoint_fixture(backend):
 
 
 # ---- ForwardEuler: the stepper the reference differentiates (test_Enzyme_end2end.jl:78-96) ---------------------------
-@pytest.mark.hw_pending
 @pytest.mark.parametrize("kelvin,renumber,nx", [(False, True, 16), (False, False, 12), (True, True, 16)])
 def test_forward_euler_gradient_matches_adjoint_oracle(backend, kelvin, renumber, nx):
     m, mo, ssh, u, h, dt = _case(nx, kelvin)
@@ -194,7 +193,6 @@ def test_forward_euler_gradient_matches_adjoint_oracle(backend, kelvin, renumber
     assert np.array_equal(prog.normalVelocity, om.normalVelocity[1]) and np.array_equal(prog.ssh, om.ssh[1])
 
 
-@pytest.mark.hw_pending
 def test_forward_euler_gradient_like_test_Enzyme_end2end(backend):
     """The reference's own acceptance test (test_Enzyme_end2end.jl:112-180): AD value at one cell / edge against central
     finite differences of the forward run, atol 1e-4 (layerThickness) and 1e-2 (normalVelocity) -- its CUDA result is NaN."""
@@ -224,7 +222,6 @@ def test_forward_euler_gradient_like_test_Enzyme_end2end(backend):
     assert abs(gh[k] - fd_h) < 1e-5 * abs(gh[k]) + 1e-7
 
 
-@pytest.mark.hw_pending
 def test_forward_euler_adjoint_on_runtime_width_rows(backend):
     """Padded rows with MOKAB_MESH_KEEP_WIDTHS: the unfused ForwardEuler steps record the tape and the run-time-width
     adjoint kernel reverses them."""
@@ -239,7 +236,6 @@ def test_forward_euler_adjoint_on_runtime_width_rows(backend):
     assert rel_l2(d_prog.ssh, gs) <= TOL64
 
 
-@pytest.mark.hw_pending
 def test_committed_forward_euler_adjoint_fixture(backend):
     """tests/golden/igw16_adjoint_fe.npz (made by tests/golden/make_golden_adjoint.py from the adjoint oracle)."""
     import json
@@ -259,7 +255,6 @@ def test_committed_forward_euler_adjoint_fixture(backend):
     assert abs(d_prog.normalVelocity[k] - float(g["fd_normalVelocity"])) < 1e-2          # :177
 
 
-@pytest.mark.hw_pending
 def test_reverse_sweep_of_an_empty_tape_returns_the_seed(backend):
     """nsteps = 0: the gradient of J = sum ssh^2 at the initial state itself.  RungeKutta4 defines ssh = h - H, so dJ/dh =
     2 (h - H); for ForwardEuler ssh is an input of its own: dJ/dssh = 2 ssh, dJ/dh = 0.  dJ/du = 0 either way."""

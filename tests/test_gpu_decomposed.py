@@ -149,7 +149,6 @@ def test_emulated_ranks_match_oracle(backend, nx, nparts, split):
         assert ni + nb == r.mesh.derived_blocks()[0] and nb >= 1        # every block of owned cells is in exactly one part
 
 
-@pytest.mark.hw_pending
 @pytest.mark.parametrize("nx,nparts,split,dtype", [(32, 2, True, np.float64), (96, 8, True, np.float64), (64, 3, False, np.float64),
                                                    (48, 4, True, np.float32)])
 def test_direct_store_halo_exchange_matches_the_packed_one(backend, nx, nparts, split, dtype):
@@ -250,7 +249,6 @@ def _run_emulated_fe(backend, m, state, nparts, dt, nsteps, split_parts=True):
     return gu, gh, gs
 
 
-@pytest.mark.hw_pending
 @pytest.mark.parametrize("nx,nparts,split,kelvin", [(32, 2, True, False), (48, 8, True, False), (40, 3, False, False), (32, 4, True, True)])
 def test_staged_forward_euler_on_emulated_ranks_is_the_reference_sequence(backend, nx, nparts, split, kelvin):
     """The reference's live stepper on a decomposed mesh: bit for bit the oracle's ForwardEuler (first-step quirk and lagged
@@ -275,7 +273,6 @@ def test_staged_forward_euler_on_emulated_ranks_is_the_reference_sequence(backen
     assert np.array_equal(gs, om.ssh[1])
 
 
-@pytest.mark.hw_pending
 @pytest.mark.parametrize("parts", [(L.PART_ALL,), (L.PART_BOUNDARY, L.PART_INTERIOR)])
 def test_staged_forward_euler_on_an_undecomposed_mesh_interoperates_with_the_whole_mesh_entry_point(backend, parts):
     """No halo at all: five staged steps are five ocn_timestep(ForwardEuler) steps, and three more through the whole-mesh entry

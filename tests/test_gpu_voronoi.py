@@ -13,7 +13,7 @@ import moka_oracle_c as OC
 from conftest import rel_l2
 from moka_b200.planar_voronoi import periodic_voronoi
 
-pytestmark = [pytest.mark.gpu, pytest.mark.hw_pending]     # the (12, 7) kernels have not run on hardware yet
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")
