@@ -256,7 +256,10 @@ int  mokab_adjoint_forward_euler(mokab_state *state);
 enum { MOKAB_PART_ALL = 0, MOKAB_PART_INTERIOR = 1, MOKAB_PART_BOUNDARY = 2,
        /* the boundary blocks with the direct-store halo exchange folded in (after mokab_p2p_setup): wait for the neighbours'
         * previous stage, compute, store every value a neighbour needs into its memory, tick its arrival counter */
-       MOKAB_PART_BOUNDARY_PUSH = 3 };
+       MOKAB_PART_BOUNDARY_PUSH = 3,
+       /* every block, with the direct-store exchange folded in: ONE launch per stage -- for parts so small that launch
+        * latency, not bytes, sets the stage time (after mokab_p2p_setup) */
+       MOKAB_PART_ALL_PUSH = 4 };
 /* send_idx: owned entities whose values neighbours need; recv_idx: halo entities, in message order.
  * Blocks that hold a send entity join the BOUNDARY part, so a message can be packed as soon as the
  * boundary launch of a stage has finished.  Call before creating states on the mesh. */

@@ -52,6 +52,20 @@ static void decomp_enqueue_rk4(mokab_state *st, double dt, int64_t nsteps)
     const bool fused = D.mode == MOKAB_HALO_P2P_FUSED;             // the boundary launch carries the exchange itself
     const int boundary = fused ? MOKAB_PART_BOUNDARY_PUSH : MOKAB_PART_BOUNDARY;
     if (nsteps <= 0) return;
+    // Parts of a few hundred blocks (Kelvin 1024x1024 over 8 GPUs: 512) are a fraction of one wave of resident blocks: a stage
+    // kernel lasts ~12 us and the two-stream schedule's chain of launches and cross-stream waits IS the stage time.  With the
+    // exchange folded into the launch such parts run ONE kernel per stage over all their blocks (it gates on the neighbours'
+    // previous stage at entry, stores what they need, ticks them at exit); same protocol, same hazard argument.
+    const int serial_below = options().decomp_serial_blocks >= 0 ? options().decomp_serial_blocks : 2 * st->ctx->num_sms * 5;
+    const bool one_launch = fused && st->mesh->fusedBlocks < serial_below;
+    if (one_launch) {
+        for (int64_t i = 0; i < nsteps; ++i) {
+            for (int s = 1; s <= 4; ++s) run_stage<R>(st, dt, s, MOKAB_PART_ALL_PUSH, compute);
+            st->cur = 1 - st->cur;
+        }
+        p2p_wait_arrivals(st, compute);
+        return;
+    }
     if (!D.overlap()) {
         for (int64_t i = 0; i < nsteps; ++i) {
             for (int s = 1; s <= 4; ++s) {
@@ -186,12 +200,25 @@ static void decomp_build_graphs(mokab_state *st, double dt, int kind)
     D.graphs_ready[kind] = true;
 }
 
+// everything the stage launches build lazily (derived mesh arrays, the weight copies of the kernel variant in use, shared-memory
+// opt-ins): done here, OUTSIDE any stream capture -- these allocate, launch on the context's stream and synchronise
+template <class R>
+static void decomp_prepare(mokab_state *st)
+{
+    mokab_mesh *m = const_cast<mokab_mesh *>(st->mesh);
+    ensure_fused<R>(m);
+    stage_tma_prepare<R>();
+    ensure_wf_block_major<R>(m);
+    ensure_wf_interleaved<R>(m);
+}
+
 template <class R>
 static void decomp_run(mokab_state *st, double dt, int64_t nsteps, int kind)
 {
     mokab_state::Decomp &D = st->dec;
     mokab_ctx *ctx = st->ctx;
     if (nsteps <= 0) return;
+    decomp_prepare<R>(st);
     if (!D.use_graph()) {
         if (kind == 0) decomp_enqueue_rk4<R>(st, dt, nsteps); else decomp_enqueue_fe(st, dt, nsteps);
         return;

@@ -727,6 +727,9 @@ struct Options {
                                   // `stage_prefetch_distance` blocks after it
     int stage_prefetch_distance = 0;   // MOKAB_STAGE_PREFETCH_DISTANCE: 0 = one wave of resident blocks (SMs x blocks per SM)
     int stage_wf_block_major = 0; // MOKAB_STAGE_WF_BLOCK_MAJOR: the plain stage kernel reads the Coriolis weights from the block-major copy
+    int decomp_serial_blocks = -1; // MOKAB_DECOMP_SERIAL_BLOCKS: with MOKAB_HALO_P2P_FUSED, a rank whose part has fewer blocks than this runs ONE
+                                  // launch per stage (all blocks, exchange folded in) instead of the two-stream overlap schedule;
+                                  // -1 = two waves of resident blocks (2 x SMs x 5)
     int test_drop_dependency = 0; // TEST HOOK (tests/sim: does the checker have teeth?): 1 / 2 = leave out one of the two cross-stream
                                   // waits of the decomposed RK4 schedule (interior after boundary / boundary after interior)
     int64_t epoch = 0;
@@ -741,6 +744,7 @@ struct Options {
         stage_prefetch = geti("MOKAB_STAGE_PREFETCH", 1) & 3;
         stage_prefetch_distance = std::max(0, geti("MOKAB_STAGE_PREFETCH_DISTANCE", 0));
         stage_wf_block_major = geti("MOKAB_STAGE_WF_BLOCK_MAJOR", 0) ? 1 : 0;
+        decomp_serial_blocks = geti("MOKAB_DECOMP_SERIAL_BLOCKS", -1);
     }
 };
 static Options &options() { static Options o; return o; }
@@ -814,7 +818,7 @@ static void launch_stage(mokab_ctx *ctx, const mokab_mesh *m, fused::StageArgs<R
     cudaStream_t s = stream ? stream : ctx->stream;
     const bool hex = m->S2 == 10 && m->S == 6;
     const bool hept = m->S2 == 12 && m->S == 7;   // pentagons / hexagons / heptagons (quasi-uniform MPAS meshes): rows padded to 12 / 7
-    if (part == MOKAB_PART_BOUNDARY_PUSH) {   // explicit edgesOnEdge: a boundary block reads halo rows, which cannot be rebuilt
+    if (part == MOKAB_PART_BOUNDARY_PUSH || part == MOKAB_PART_ALL_PUSH) {   // explicit edgesOnEdge: a boundary block reads halo rows, which cannot be rebuilt
 #define MOKAB_STAGE_PUSH(S2T, ST, FOLD) fused::k_rk_stage<R, STAGE, S2T, ST, FOLD, false, true><<<grid, fused::kThreads, 0, s>>>(A, m->S2, m->S)
         if (hex && m->uniformF)      MOKAB_STAGE_PUSH(10, 6, false);
         else if (hex)                MOKAB_STAGE_PUSH(10, 6, true);
@@ -954,9 +958,9 @@ static void run_stage(mokab_state *st, double dt, int stage, int part, cudaStrea
     ensure_wf_block_major<R>(const_cast<mokab_mesh *>(m));
     ensure_wf_interleaved<R>(const_cast<mokab_mesh *>(m));
     fused::StageArgs<R> A = stage_args<R>(st, dt, st->cur, stage);
-    if (part == MOKAB_PART_BOUNDARY_PUSH) {
-        MOKAB_REQUIRE(st->p2p.ready, "rk4_stage(MOKAB_PART_BOUNDARY_PUSH): call mokab_p2p_setup first");
-        MOKAB_REQUIRE(m->nBoundary > 0 || (st->p2p.recvRanks.empty() && st->p2p.sendRanks.empty()),
+    if (part == MOKAB_PART_BOUNDARY_PUSH || part == MOKAB_PART_ALL_PUSH) {
+        MOKAB_REQUIRE(st->p2p.ready, "rk4_stage(MOKAB_PART_*_PUSH): call mokab_p2p_setup first");
+        MOKAB_REQUIRE(part == MOKAB_PART_ALL_PUSH || m->nBoundary > 0 || (st->p2p.recvRanks.empty() && st->p2p.sendRanks.empty()),
                       "rk4_stage(MOKAB_PART_BOUNDARY_PUSH): a rank with neighbours has no boundary block");
         A.push = (const fused::PushStage<R> *)st->p2p.stageDesc.p + p2p_target(st, stage);
 #ifdef MOKAB_SIM
@@ -2273,7 +2277,7 @@ int mokab_rk4_stage(mokab_state *state, double dt, int stage, int part, void *cu
         MOKAB_REQUIRE(state, "rk4_stage: state is NULL");
         MOKAB_REQUIRE(stage >= 1 && stage <= 4, "rk4_stage: stage must be 1..4");
         MOKAB_REQUIRE(state->K == 1, "rk4_stage: single-level states only (nVertLevels == 1)");
-        MOKAB_REQUIRE(part >= MOKAB_PART_ALL && part <= MOKAB_PART_BOUNDARY_PUSH, "rk4_stage: unknown part");
+        MOKAB_REQUIRE(part >= MOKAB_PART_ALL && part <= MOKAB_PART_ALL_PUSH, "rk4_stage: unknown part");
         state->ctx->bind();
         leave_forward_euler(state);
         if (state->dtype == MOKAB_F64) run_stage<double>(state, dt, stage, part, (cudaStream_t)cuda_stream);
@@ -2433,6 +2437,7 @@ int mokab_set_option(const char *name, int64_t value)
         else if (n == "stage_prefetch") { MOKAB_REQUIRE(value >= 0 && value <= 3, "set_option: stage_prefetch must be 0..3"); o.stage_prefetch = (int)value; }
         else if (n == "stage_prefetch_distance") { MOKAB_REQUIRE(value >= 0 && value < (1 << 30), "set_option: bad stage_prefetch_distance"); o.stage_prefetch_distance = (int)value; }
         else if (n == "stage_wf_block_major") o.stage_wf_block_major = value ? 1 : 0;
+        else if (n == "decomp_serial_blocks") o.decomp_serial_blocks = (int)value;
         else if (n == "test_drop_dependency") o.test_drop_dependency = (int)value;
         else throw Error("set_option: unknown option '" + n + "'");
         o.epoch++;
@@ -2449,6 +2454,7 @@ int mokab_get_option(const char *name, int64_t *value)
         else if (n == "stage_prefetch") *value = o.stage_prefetch;
         else if (n == "stage_prefetch_distance") *value = o.stage_prefetch_distance;
         else if (n == "stage_wf_block_major") *value = o.stage_wf_block_major;
+        else if (n == "decomp_serial_blocks") *value = o.decomp_serial_blocks;
         else throw Error("get_option: unknown option '" + n + "'");
     });
 }

@@ -341,3 +341,21 @@ def test_in_library_decomposed_entry_points_with_one_rank(backend, halo, graph, 
     assert abs(mass - float(np.sum(m["areaCell"] * om.layerThickness[1]))) <= 1e-13 * mass
     if graph and stepper == "RungeKutta4":
         assert status.startswith("validated"), status
+
+
+def test_in_library_decomposed_graphs_on_the_very_first_call(backend):
+    """A C-ABI caller's first call is mokab_timestep_rk4_decomposed with graphs on (no host-launched warm-up, no validation
+    pass): everything the stage launches build lazily -- the interleaved weight copy of the default kernel variant included --
+    must be in place before the capture starts."""
+    m = hex_mesh(48, with_dual=False)
+    state = mb.inertialGravityWave(m).initial_state()
+    dt = mb.cfl_dt(m["dc"])
+    loc = partition.decompose(m, 1)[0]
+    model = multi_gpu.DecomposedModel(loc, multi_gpu.local_state(loc, *state), backend, 0, graph=True, runtime=_SoloRuntime())
+    model._advance(dt, 5, False)                 # straight to the library, past DecomposedModel's validation
+    model.finish()
+    gs, gu, gh = model.gather(m["nCells"], m["nEdges"])
+    model.close()
+    om = OC.OracleModel(m, *state)
+    om.run_loop(dt, 5, "RungeKutta4")
+    assert np.array_equal(gu, om.normalVelocity[1]) and np.array_equal(gs, om.ssh[1])
