@@ -52,12 +52,13 @@ static void decomp_enqueue_rk4(mokab_state *st, double dt, int64_t nsteps)
     const bool fused = D.mode == MOKAB_HALO_P2P_FUSED;             // the boundary launch carries the exchange itself
     const int boundary = fused ? MOKAB_PART_BOUNDARY_PUSH : MOKAB_PART_BOUNDARY;
     if (nsteps <= 0) return;
-    // Parts of a few hundred blocks (Kelvin 1024x1024 over 8 GPUs: 512) are a fraction of one wave of resident blocks: a stage
-    // kernel lasts ~12 us and the two-stream schedule's chain of launches and cross-stream waits IS the stage time.  With the
-    // exchange folded into the launch such parts run ONE kernel per stage over all their blocks (it gates on the neighbours'
-    // previous stage at entry, stores what they need, ticks them at exit); same protocol, same hazard argument.
-    const int serial_below = options().decomp_serial_blocks >= 0 ? options().decomp_serial_blocks : 2 * st->ctx->num_sms * 5;
-    const bool one_launch = fused && st->mesh->fusedBlocks < serial_below;
+    // Experiment (option "decomp_serial_blocks", off by default): parts of a few hundred blocks (Kelvin 1024x1024 over 8 GPUs: 512)
+    // are a fraction of one wave of resident blocks, a stage kernel lasts ~12 us and the two-stream schedule's chain of launches
+    // and cross-stream waits is the stage time; with the exchange folded into the launch such a part can run ONE kernel per
+    // stage over all its blocks (gate on the neighbours' previous stage at entry, store what they need, tick them at exit; same
+    // protocol, same hazard argument).  Measured at N = 2 it is SLOWER (Kelvin 1024x1024: 0.389 vs 0.236 ms/step; 512 blocks per
+    // GPU: 0.136 vs 0.111): every block of stage s + 1 then waits for the neighbours' WHOLE stage s, the interior included.
+    const bool one_launch = fused && st->mesh->fusedBlocks < options().decomp_serial_blocks;
     if (one_launch) {
         for (int64_t i = 0; i < nsteps; ++i) {
             for (int s = 1; s <= 4; ++s) run_stage<R>(st, dt, s, MOKAB_PART_ALL_PUSH, compute);

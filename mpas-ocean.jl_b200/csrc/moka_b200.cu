@@ -727,9 +727,10 @@ struct Options {
                                   // `stage_prefetch_distance` blocks after it
     int stage_prefetch_distance = 0;   // MOKAB_STAGE_PREFETCH_DISTANCE: 0 = one wave of resident blocks (SMs x blocks per SM)
     int stage_wf_block_major = 0; // MOKAB_STAGE_WF_BLOCK_MAJOR: the plain stage kernel reads the Coriolis weights from the block-major copy
-    int decomp_serial_blocks = -1; // MOKAB_DECOMP_SERIAL_BLOCKS: with MOKAB_HALO_P2P_FUSED, a rank whose part has fewer blocks than this runs ONE
-                                  // launch per stage (all blocks, exchange folded in) instead of the two-stream overlap schedule;
-                                  // -1 = two waves of resident blocks (2 x SMs x 5)
+    int decomp_serial_blocks = 0;  // MOKAB_DECOMP_SERIAL_BLOCKS: with MOKAB_HALO_P2P_FUSED, a rank whose part has fewer blocks than this runs ONE
+                                  // launch per stage (all blocks, exchange folded in) instead of the two-stream overlap schedule.
+                                  // Off by default: measured SLOWER at N = 2 (profiles/README.md r02g) -- every block of stage s + 1
+                                  // then waits for the neighbours' whole stage s, where the two-stream schedule lets the interior run
     int test_drop_dependency = 0; // TEST HOOK (tests/sim: does the checker have teeth?): 1 / 2 = leave out one of the two cross-stream
                                   // waits of the decomposed RK4 schedule (interior after boundary / boundary after interior)
     int64_t epoch = 0;
@@ -744,7 +745,7 @@ struct Options {
         stage_prefetch = geti("MOKAB_STAGE_PREFETCH", 1) & 3;
         stage_prefetch_distance = std::max(0, geti("MOKAB_STAGE_PREFETCH_DISTANCE", 0));
         stage_wf_block_major = geti("MOKAB_STAGE_WF_BLOCK_MAJOR", 0) ? 1 : 0;
-        decomp_serial_blocks = geti("MOKAB_DECOMP_SERIAL_BLOCKS", -1);
+        decomp_serial_blocks = std::max(0, geti("MOKAB_DECOMP_SERIAL_BLOCKS", 0));
     }
 };
 static Options &options() { static Options o; return o; }
@@ -796,7 +797,7 @@ template <class R>
 static void ensure_wf_interleaved(mokab_mesh *m)
 {
     FusedMesh<R> &f = fused_of<R>(m);
-    if (stage_tma_mode() != 3 || f.wfI.n || !(m->S2 == 10 && m->S == 6)) return;
+    if (stage_tma_mode() != 3 || f.wfI.n || !((m->S2 == 10 && m->S == 6) || (m->S2 == 12 && m->S == 7))) return;
     mokab_ctx *ctx = m->ctx;
     constexpr int V = 16 / (int)sizeof(R);
     const int NG = (m->S2 + V - 1) / V;
@@ -834,16 +835,23 @@ static void launch_stage(mokab_ctx *ctx, const mokab_mesh *m, fused::StageArgs<R
         FusedMesh<R> &fm = fused_of<R>(const_cast<mokab_mesh *>(m));
         if (fm.wfB.n) { A.wfB = fm.wfB.p; A.wfBOff = fm.wfBOff.p; }
     }
-    if (hex && stage_tma_mode() == 3 && part != MOKAB_PART_BOUNDARY_PUSH) {   // opt-in: weights through per-thread cp.async into shared memory
+    if ((hex || hept) && stage_tma_mode() == 3) {   // the default: weights through per-thread cp.async into shared memory (kernels_fused.cuh)
         FusedMesh<R> &fm = fused_of<R>(const_cast<mokab_mesh *>(m));
         if (fm.wfI.n) {
             A.wfI = fm.wfI.p;
-            const size_t smem = (size_t)fused::cpa_groups<R, 10>() * fused::kThreads * 16;
-#define MOKAB_STAGE_CPA(FOLD, DER) fused::k_rk_stage<R, STAGE, 10, 6, FOLD, DER, false, 3><<<grid, fused::kThreads, smem, s>>>(A, m->S2, m->S)
-            if (der && m->uniformF)      MOKAB_STAGE_CPA(false, true);
-            else if (der)                MOKAB_STAGE_CPA(true, true);
-            else if (m->uniformF)        MOKAB_STAGE_CPA(false, false);
-            else                         MOKAB_STAGE_CPA(true, false);
+            const size_t smem = (size_t)(hex ? fused::cpa_groups<R, 10>() : fused::cpa_groups<R, 12>()) * fused::kThreads * 16;
+#define MOKAB_STAGE_CPA(S2T, ST, FOLD, DER) fused::k_rk_stage<R, STAGE, S2T, ST, FOLD, DER, false, 3><<<grid, fused::kThreads, smem, s>>>(A, m->S2, m->S)
+            if (hex) {
+                if (der && m->uniformF)      MOKAB_STAGE_CPA(10, 6, false, true);
+                else if (der)                MOKAB_STAGE_CPA(10, 6, true, true);
+                else if (m->uniformF)        MOKAB_STAGE_CPA(10, 6, false, false);
+                else                         MOKAB_STAGE_CPA(10, 6, true, false);
+            } else {
+                if (der && m->uniformF)      MOKAB_STAGE_CPA(12, 7, false, true);
+                else if (der)                MOKAB_STAGE_CPA(12, 7, true, true);
+                else if (m->uniformF)        MOKAB_STAGE_CPA(12, 7, false, false);
+                else                         MOKAB_STAGE_CPA(12, 7, true, false);
+            }
 #undef MOKAB_STAGE_CPA
             MOKAB_CUDA(cudaGetLastError());
             ctx->launches++;

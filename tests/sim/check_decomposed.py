@@ -256,14 +256,13 @@ def main():
         for policy in args.policies.split(","):
             for seed in range(1, (args.seeds if policy == "random" else 1) + 1):
                 for halo in args.halo.split(","):
-                    # (p2p_fused: parts this small take the one-launch-per-stage schedule by default; "serial0" forces the
-                    #  two-stream schedule, so both are checked)
-                    for overlap, graph, serial in ((True, False, 0), (False, False, 0), (True, True, 0)) + (((True, False, -1), (True, True, -1)) if halo == "p2p_fused" else ()):
+                    # (p2p_fused: the one-launch-per-stage schedule -- option decomp_serial_blocks, off by default -- is checked too)
+                    for overlap, graph, serial in ((True, False, 0), (False, False, 0), (True, True, 0)) + (((True, False, 1 << 20), (True, True, 1 << 20)) if halo == "p2p_fused" else ()):
                         t0 = time.time()
                         _lib.set_option("decomp_serial_blocks", serial)
                         ok, status = run(kind, nx, P, calls, overlap, graph, policy, seed, halo=halo)
-                        _lib.set_option("decomp_serial_blocks", -1)
-                        halo_txt = halo + ("/one-launch" if serial < 0 and halo == "p2p_fused" else "")
+                        _lib.set_option("decomp_serial_blocks", 0)
+                        halo_txt = halo + ("/one-launch" if serial > 0 and halo == "p2p_fused" else "")
                         bad += not ok
                         if graph and not status.startswith("validated"):
                             bad += 1

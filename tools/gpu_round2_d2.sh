@@ -26,18 +26,16 @@ one() {   # one <label> <env...> -- <bench args...>
 }
 one "igw2048 p2p default"                       X=1 -- --workload igw2048 --steps 50 --warmup 5
 one "igw2048 p2p plain kernel (tma=0 pf=0)"     MOKAB_STAGE_TMA=0 MOKAB_STAGE_PREFETCH=0 -- --workload igw2048 --steps 50 --warmup 5 --no-parity
-one "igw2048 p2p tma=3 pf=0"                    MOKAB_STAGE_PREFETCH=0 -- --workload igw2048 --steps 50 --warmup 5 --no-parity
-one "igw2048 p2p no graph"                      X=1 -- --workload igw2048 --steps 50 --warmup 5 --no-parity --no-graph
 one "igw2048 p2p no overlap"                    X=1 -- --workload igw2048 --steps 50 --warmup 5 --no-parity --no-overlap
 one "igw2048 p2p_fused"                         X=1 -- --workload igw2048 --steps 50 --warmup 5 --no-parity --halo p2p_fused
-one "igw2048 nccl"                              X=1 -- --workload igw2048 --steps 50 --warmup 5 --no-parity --halo nccl
-one "igw2048 nccl plain kernel"                 MOKAB_STAGE_TMA=0 MOKAB_STAGE_PREFETCH=0 -- --workload igw2048 --steps 50 --warmup 5 --no-parity --halo nccl
 one "kelvin1024 p2p"                            X=1 -- --workload kelvin1024 --steps 100 --warmup 5 --no-parity
-one "kelvin1024 p2p_fused (two-stream)"         MOKAB_DECOMP_SERIAL_BLOCKS=0 -- --workload kelvin1024 --steps 100 --warmup 5 --no-parity --halo p2p_fused
 one "kelvin1024 p2p_fused one launch per stage" MOKAB_DECOMP_SERIAL_BLOCKS=1000000 -- --workload kelvin1024 --steps 100 --warmup 5 --halo p2p_fused
 one "igw512 p2p"                                X=1 -- --workload igw512 --steps 200 --warmup 5 --no-parity
 one "igw512 p2p_fused one launch per stage"     X=1 -- --workload igw512 --steps 200 --warmup 5 --halo p2p_fused
 one "igw4096 p2p default (numa bind)"           X=1 -- --steps 20 --warmup 5
 one "igw4096 p2p no numa bind"                  MOKAB_NO_NUMA_BIND=1 -- --steps 20 --warmup 5 --no-parity
+# which of the two default switches costs the extra DRAM traffic (r02f: +7 % over the must-move bytes, r02b: +3.8 %): one capture without the prefetch
+MOKAB_STAGE_PREFETCH=0 ncu --set full --clock-control none -k regex:k_rk_stage -s 12 -c 4 -o /tmp/ncu_pf0 -f python bench.py --workload igw2048 --steps 3 --warmup 3 --no-cpu --no-parity --quick > /dev/null 2>&1
+python tools/ncu_summary.py /tmp/ncu_pf0.ncu-rep > $out/ncu_stage_f64_igw2048_tma3_pf0_summary_$tag.csv; rm -f /tmp/ncu_pf0.ncu-rep
 grep -v "OMP_NUM_THREADS\|^\*\*\*\|^$" $out/bench_$tag.err | tail -n 10
 head -n 20 $out/topo_$tag.txt
