@@ -229,6 +229,20 @@ def run_b200(args):
     t0 = time.perf_counter()
     e2e_steps(Ke)
     e2e_s = (time.perf_counter() - t0) / Ke
+    # what the same transfers cost with no step between them (explains the leg: PCIe-bound when the two agree)
+    def copy_only(n):
+        for i in range(n):
+            if f32:
+                prog.upload_async(normalVelocity=hin[i & 1][0], ssh=hin[i & 1][1])
+            else:
+                prog.upload_async(normalVelocity=hin[i & 1][0], layerThickness=hin[i & 1][1])
+            prog.download_async(ssh=hout[~i & 1][0], normalVelocity=hout[~i & 1][1])
+        prog.synchronize()
+    copy_only(1)
+    t0 = time.perf_counter()
+    copy_only(Ke)
+    copy_s = (time.perf_counter() - t0) / Ke
+    e2e_steps(2)                                            # both result buffers hold a step's output again for the check below
     item = np.dtype(npdt).itemsize
     # the result of the last e2e step is one RK4 step from the uploaded state: check it against a device-resident step
     prog_chk = mb.PrognosticVars(ssh.astype(npdt), u.astype(npdt), h.astype(npdt), 2, mesh)
@@ -272,11 +286,12 @@ def run_b200(args):
                    # which build / stage-kernel variant ran (tools/gpu_sweep_variants.sh; the defaults when unset)
                    "variant": {"lib": os.environ.get("MOKAB_LIB", "libmoka_b200.so"),
                                "stage_tma": L.get_option("stage_tma"), "stage_prefetch": L.get_option("stage_prefetch"),
-                               "stage_prefetch_distance": L.get_option("stage_prefetch_distance")}},
+                               "stage_prefetch_distance": L.get_option("stage_prefetch_distance"),
+                               "stage_flux_smem": L.get_option("stage_flux_smem"), "stage_pdl": L.get_option("stage_pdl")}},
         "clocks": clocks,
         "e2e": {"value": nC / e2e_s, "unit": "cell-steps/s", "h2d_bytes_per_step": int((nE + nC) * item),
                 "d2h_bytes_per_step": int((nC + nE) * item), "ms_per_step": e2e_s * 1e3, "steps": Ke,
-                "pipelined": True, "matches_device_resident_step": e2e_ok,
+                "pipelined": True, "matches_device_resident_step": e2e_ok, "copies_only_ms_per_step": copy_s * 1e3,
                 "returns": "ssh + normalVelocity of the new state (layerThickness = ssh + restingThicknessSum stays on the device)"},
         "gpu_launches": int(launches_total),
         "parity": parity,

@@ -362,9 +362,12 @@ int  mokab_decomp_close(mokab_state *state);
  * setting.  "stage_prefetch": bit 0 = a block pulls the streams of its later iterations into L2 at entry, bit 1 = those of
  * the block launched "stage_prefetch_distance" blocks later (0 = one wave of resident blocks); "stage_tma": 1 / 2 = the
  * Coriolis weights through bulk asynchronous copies (slot-major rows / a block-major copy), 3 = through per-thread cp.async into
- * shared memory (one more resident block per SM).  Defaults: stage_tma = 3, stage_prefetch = 1 (the fastest on B200,
- * profiles/README.md r02d); the environment overrides them (MOKAB_STAGE_PREFETCH, MOKAB_STAGE_PREFETCH_DISTANCE,
- * MOKAB_STAGE_TMA). */
+ * shared memory (one more resident block per SM); "stage_flux_smem": with stage_tma = 3, the edge phase leaves the thickness
+ * flux of the block's own edges in shared memory and the cell phase reads it back after one barrier instead of gathering
+ * cellsOnEdge, u, dvEdge and the neighbour's thickness again; "stage_pdl": stage launches carry the programmatic-stream-
+ * serialization attribute, so the static half of stage s + 1 overlaps the tail of stage s.  Defaults: stage_tma = 3,
+ * stage_prefetch = 1 (the fastest on B200, profiles/README.md r02d); the environment overrides them (MOKAB_STAGE_PREFETCH,
+ * MOKAB_STAGE_PREFETCH_DISTANCE, MOKAB_STAGE_TMA, MOKAB_STAGE_FLUX_SMEM, MOKAB_STAGE_PDL). */
 int  mokab_set_option(const char *name, int64_t value);
 int  mokab_get_option(const char *name, int64_t *value);
 /* number of interior / boundary blocks of the fused kernel (diagnostic) */

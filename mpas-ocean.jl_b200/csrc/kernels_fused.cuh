@@ -183,10 +183,36 @@ template <class R> __host__ __device__ constexpr int tma_align() { return 16 / (
 #define MOKAB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
 
-template <class R, int STAGE, int S2T, int ST, bool FOLD, bool DER, bool PUSH = false, int TMA = 0>
+// Programmatic dependent launch (opt-in, "stage_pdl"): consecutive stage launches of one stream overlap the TAIL of stage s with
+// the static half of stage s + 1.  Every block lets the next launch start as soon as it is resident itself
+// (griddepcontrol.launch_dependents at entry), and waits for the previous launch to have completed and flushed
+// (griddepcontrol.wait) only where it first touches the state -- its connectivity, metrics and weight copies (the L2
+// prefetches, the cp.async weights, cellsOnEdge, g/dc: ~60 % of the bytes of its first edge iteration) are issued before
+// that.  Both instructions are no-ops in a launch without the programmatic attribute.
+__device__ __forceinline__ void pdl_launch_dependents()
+{
+#ifndef MOKAB_SIM
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_wait()
+{
+#ifndef MOKAB_SIM
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
+// FX = true (opt-in, "stage_flux_smem"; cp.async-weights variant only): the edge phase leaves u * hEdge * dv of every edge the
+// block owns in SHARED memory, and the cell phase -- after one block-wide barrier -- takes the flux of a slot from there when the
+// edge is one of the block's own (~90 % of the slots of a 16 x 16 patch) instead of gathering cellsOnEdge, u, dv and the other
+// cell's h again: four gathers per slot become one shared-memory read.  The product is formed with the cell phase's own
+// operation order ((u * (0.5 * (h1 + h2))) * dv; the sum of the two thicknesses commutes), so results stay bit-identical.
+template <class R, int STAGE, int S2T, int ST, bool FOLD, bool DER, bool PUSH = false, int TMA = 0, bool FX = false>
 __global__ void __launch_bounds__(kThreads, (stage_blocks<R, DER, TMA>()))
 k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
 {
+    static_assert(!FX || (TMA == 3 && !PUSH && S2T != 0 && ST != 0), "FX rides on the cp.async-weights variant with compile-time row widths");
+    pdl_launch_dependents();
     const int S2 = S2T ? S2T : S2rt;
     const int S = ST ? ST : Srt;
     const int nE = A.nE, nC = A.nC;
@@ -194,9 +220,11 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
     const int cBase = b * kTC;
     static_assert(TMA == 0 || (S2T != 0 && ST != 0), "the TMA variants stage compile-time many weight rows");
     [[maybe_unused]] unsigned char *cpa_slot = nullptr;             // TMA = 3: this thread's 16-byte slots, one per slot group, kThreads * 16 bytes apart
+    [[maybe_unused]] R *fxs = nullptr;                              // FX: u * hEdge * dv of the block's own edges
     if constexpr (TMA == 3) {
         MOKAB_DYN_SMEM(dyn3);
         cpa_slot = dyn3 + (size_t)threadIdx.x * 16;
+        if constexpr (FX) fxs = reinterpret_cast<R *>(dyn3 + (size_t)cpa_groups<R, S2T>() * kThreads * 16);
     }
     [[maybe_unused]] const R *sw = nullptr;
     [[maybe_unused]] bool weights_landed = false;
@@ -254,6 +282,7 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
 #endif
     }
     if constexpr (PUSH) {
+        pdl_wait();
 #ifndef MOKAB_SIM   // (the simulated runtime cannot spin inside a kernel: the host enqueues the same predicate before the launch)
         const PushStage<R> &P = *A.push;
         if ((int)threadIdx.x < P.nsend) {
@@ -364,12 +393,20 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
                 }
             }
             const R g = ld_stream(A.gdc + e);
+            [[maybe_unused]] R fxD = R(0), fxU = R(0);
+            if constexpr (FX) fxD = ld_stream(A.dv + e);
+            pdl_wait();                                                 // everything above is static; the state comes next
             // the RK operands are independent of the tendency: issue their loads now (they may alias the stores
             // below, so the compiler cannot hoist them itself)
             const R cur = (STAGE == 4) ? R(0) : A.uCur[e];
             const R accIn = (STAGE == 1) ? R(0) : A.uAcc[e];
+            if constexpr (FX) fxU = A.uOld[e];
             const R h1 = __ldg(A.hOld + c.x), h2 = __ldg(A.hOld + c.y);
-            const R H1 = kPert<R> ? R(0) : __ldg(A.H + c.x), H2 = kPert<R> ? R(0) : __ldg(A.H + c.y);
+            const R H1 = (kPert<R> && !FX) ? R(0) : __ldg(A.H + c.x), H2 = (kPert<R> && !FX) ? R(0) : __ldg(A.H + c.y);
+            if constexpr (FX) {   // the flux of this edge through its length, as the cell phase forms it (commutative sum of the two thicknesses)
+                const R ha = kPert<R> ? add_rn(h1, H1) : h1, hb = kPert<R> ? add_rn(h2, H2) : h2;
+                fxs[e - e0] = mul_rn(mul_rn(fxU, mul_rn(R(0.5), add_rn(ha, hb))), fxD);
+            }
             if (kDer && derived) {
                 // posE: bits 0-2 position of e in the row of cell 1, bits 3-5 in the row of cell 2, bit 7 = both rows
                 // have ST entries and the edge is not masked (the branch-free common case)
@@ -447,6 +484,7 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
             continue;
         }
         const int n = ld_stream(A.nEoE + e);
+        pdl_wait();
         const R cur = (STAGE == 4) ? R(0) : A.uCur[e];
         const R accIn = (STAGE == 1) ? R(0) : A.uAcc[e];
         const R h1 = __ldg(A.hOld + c.x), h2 = __ldg(A.hOld + c.y);
@@ -469,6 +507,54 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
 
     // ---- cells of this block ----------------------------------------------------------------------------
     const int cc = cBase + threadIdx.x;
+    pdl_wait();                                                         // (a block that owns no edge has not waited yet)
+    if constexpr (FX) {
+        // Everything the cell needs that is not a flux is requested BEFORE the barrier, so those latencies run while the
+        // block's slower warps finish their edges; after it, a slot whose edge the block owns is one shared-memory read.
+        const bool live = cc < A.nCown;
+        int n = 0;
+        R hc = R(0), cur = R(0), accIn = R(0), invA = R(0);
+        int ee[ST ? ST : 1];
+        if (live) {
+            n = ld_stream(A.nEoC + cc);
+            hc = kPert<R> ? add_rn(__ldg(A.hOld + cc), __ldg(A.H + cc)) : __ldg(A.hOld + cc);
+            cur = (STAGE == 4) ? R(0) : A.hCur[cc];
+            accIn = (STAGE == 1) ? R(0) : A.hAcc[cc];
+#pragma unroll
+            for (int i = 0; i < ST; ++i) ee[i] = i < n ? __ldg(A.eoc + (size_t)i * nC + cc) : -1;
+            invA = ld_stream(A.invArea + cc);
+        }
+        __syncthreads();
+        if (live) {
+            R fl[ST ? ST : 1];
+#pragma unroll
+            for (int i = 0; i < ST; ++i) {
+                fl[i] = R(0);
+                if (ee[i] >= 0) {
+                    const int e = ee[i] >> 1;
+                    if ((unsigned)(e - e0) < (unsigned)(e1 - e0)) {
+                        fl[i] = fxs[e - e0];
+                    } else {   // an edge of a neighbouring block: as the plain kernel does it
+                        const int2 cs = __ldg(A.ce + e);
+                        const int other = cs.x == cc ? cs.y : cs.x;
+                        const R ho = kPert<R> ? add_rn(__ldg(A.hOld + other), __ldg(A.H + other)) : __ldg(A.hOld + other);
+                        fl[i] = mul_rn(mul_rn(__ldg(A.uOld + e), mul_rn(R(0.5), add_rn(hc, ho))), __ldg(A.dv + e));
+                    }
+                }
+            }
+            R acc = R(0);
+#pragma unroll
+            for (int i = 0; i < ST; ++i) {
+                const R f = mul_rn(fl[i], invA);
+                if (ee[i] >= 0) acc = add_rn(acc, (ee[i] & 1) ? f : -f);
+            }
+            const R k = acc;
+            if (STAGE != 4) A.hOut[cc] = add_rn(cur, mul_rn(A.a, k));
+            if (STAGE == 1) A.hAcc[cc] = add_rn(cur, mul_rn(A.b, k));
+            else            A.hAcc[cc] = add_rn(accIn, mul_rn(A.b, k));
+        }
+        return;
+    }
     if (cc < A.nCown) {
         const int n = ld_stream(A.nEoC + cc);
         // Float32: the arrays hold the perturbation h - H (see kPert); the flux needs the whole thickness

@@ -727,6 +727,9 @@ struct Options {
                                   // `stage_prefetch_distance` blocks after it
     int stage_prefetch_distance = 0;   // MOKAB_STAGE_PREFETCH_DISTANCE: 0 = one wave of resident blocks (SMs x blocks per SM)
     int stage_wf_block_major = 0; // MOKAB_STAGE_WF_BLOCK_MAJOR: the plain stage kernel reads the Coriolis weights from the block-major copy
+    int stage_flux_smem = 0;      // MOKAB_STAGE_FLUX_SMEM: the cp.async-weights stage kernel leaves the thickness flux of the block's own edges in
+                                  // shared memory for its cell phase (kernels_fused.cuh: FX)
+    int stage_pdl = 0;            // MOKAB_STAGE_PDL: stage launches carry the programmatic-stream-serialization attribute (kernels_fused.cuh: pdl_*)
     int decomp_serial_blocks = 0;  // MOKAB_DECOMP_SERIAL_BLOCKS: with MOKAB_HALO_P2P_FUSED, a rank whose part has fewer blocks than this runs ONE
                                   // launch per stage (all blocks, exchange folded in) instead of the two-stream overlap schedule.
                                   // Off by default: measured SLOWER at N = 2 (profiles/README.md r02g) -- every block of stage s + 1
@@ -745,6 +748,8 @@ struct Options {
         stage_prefetch = geti("MOKAB_STAGE_PREFETCH", 1) & 3;
         stage_prefetch_distance = std::max(0, geti("MOKAB_STAGE_PREFETCH_DISTANCE", 0));
         stage_wf_block_major = geti("MOKAB_STAGE_WF_BLOCK_MAJOR", 0) ? 1 : 0;
+        stage_flux_smem = geti("MOKAB_STAGE_FLUX_SMEM", 0) ? 1 : 0;
+        stage_pdl = geti("MOKAB_STAGE_PDL", 0) ? 1 : 0;
         decomp_serial_blocks = std::max(0, geti("MOKAB_DECOMP_SERIAL_BLOCKS", 0));
     }
 };
@@ -806,6 +811,34 @@ static void ensure_wf_interleaved(mokab_mesh *m)
     MOKAB_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
+// A stage launch with the programmatic-stream-serialization attribute ("stage_pdl"): the launch may become resident while the
+// previous kernel of the stream drains; the kernel itself waits (griddepcontrol.wait) before it touches the state.  Captured
+// into graphs as a programmatic dependency edge.
+template <class... P, class... A>
+static void launch_pdl(void (*kernel)(P...), int grid, size_t smem, cudaStream_t s, A &&...args)
+{
+#ifdef MOKAB_SIM
+    (void)kernel; (void)grid; (void)smem; (void)s;
+    throw Error("stage_pdl: not available on the simulated runtime");
+#else
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)fused::kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    MOKAB_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(std::forward<A>(args))...));
+#endif
+}
+static bool stage_pdl_enabled()
+{
+#ifdef MOKAB_SIM
+    return false;
+#else
+    return options().stage_pdl != 0;
+#endif
+}
+
 // ---- fused RK4 ------------------------------------------------------------------------------------------------
 template <class R, int STAGE>
 static void launch_stage(mokab_ctx *ctx, const mokab_mesh *m, fused::StageArgs<R> A, int part = MOKAB_PART_ALL,
@@ -839,8 +872,23 @@ static void launch_stage(mokab_ctx *ctx, const mokab_mesh *m, fused::StageArgs<R
         FusedMesh<R> &fm = fused_of<R>(const_cast<mokab_mesh *>(m));
         if (fm.wfI.n) {
             A.wfI = fm.wfI.p;
-            const size_t smem = (size_t)(hex ? fused::cpa_groups<R, 10>() : fused::cpa_groups<R, 12>()) * fused::kThreads * 16;
-#define MOKAB_STAGE_CPA(S2T, ST, FOLD, DER) fused::k_rk_stage<R, STAGE, S2T, ST, FOLD, DER, false, 3><<<grid, fused::kThreads, smem, s>>>(A, m->S2, m->S)
+            size_t smem = (size_t)(hex ? fused::cpa_groups<R, 10>() : fused::cpa_groups<R, 12>()) * fused::kThreads * 16;
+            // "stage_flux_smem": + one value per edge of the largest block (under the 48 KB a launch gets without an opt-in)
+            const bool fx = options().stage_flux_smem && smem + (size_t)m->maxBlockEdges * sizeof(R) <= 48 * 1024;
+            if (fx) smem += (size_t)m->maxBlockEdges * sizeof(R);
+            const bool pdl = stage_pdl_enabled();
+#define MOKAB_STAGE_CPA(S2T, ST, FOLD, DER)                                                                                          \
+    do {                                                                                                                            \
+        if (fx) {                                                                                                                   \
+            auto k_rk_stage_fx = fused::k_rk_stage<R, STAGE, S2T, ST, FOLD, DER, false, 3, true>;                                   \
+            if (pdl) launch_pdl(k_rk_stage_fx, grid, smem, s, A, m->S2, m->S);                                                      \
+            else k_rk_stage_fx<<<grid, fused::kThreads, smem, s>>>(A, m->S2, m->S);                                                 \
+        } else {                                                                                                                    \
+            auto k_rk_stage_cpa = fused::k_rk_stage<R, STAGE, S2T, ST, FOLD, DER, false, 3>;                                        \
+            if (pdl) launch_pdl(k_rk_stage_cpa, grid, smem, s, A, m->S2, m->S);                                                     \
+            else k_rk_stage_cpa<<<grid, fused::kThreads, smem, s>>>(A, m->S2, m->S);                                                \
+        }                                                                                                                           \
+    } while (0)
             if (hex) {
                 if (der && m->uniformF)      MOKAB_STAGE_CPA(10, 6, false, true);
                 else if (der)                MOKAB_STAGE_CPA(10, 6, true, true);
@@ -888,7 +936,13 @@ static void launch_stage(mokab_ctx *ctx, const mokab_mesh *m, fused::StageArgs<R
         }
         A.wStride = 0;
     }
-#define MOKAB_STAGE(S2T, ST, FOLD, DER) fused::k_rk_stage<R, STAGE, S2T, ST, FOLD, DER><<<grid, fused::kThreads, 0, s>>>(A, m->S2, m->S)
+    const bool pdl0 = stage_pdl_enabled();
+#define MOKAB_STAGE(S2T, ST, FOLD, DER)                                                                                              \
+    do {                                                                                                                            \
+        auto k_rk_stage_plain = fused::k_rk_stage<R, STAGE, S2T, ST, FOLD, DER>;                                                    \
+        if (pdl0) launch_pdl(k_rk_stage_plain, grid, 0, s, A, m->S2, m->S);                                                         \
+        else k_rk_stage_plain<<<grid, fused::kThreads, 0, s>>>(A, m->S2, m->S);                                                     \
+    } while (0)
     if (hex && der && m->uniformF)  MOKAB_STAGE(10, 6, false, true);
     else if (hex && der)            MOKAB_STAGE(10, 6, true, true);
     else if (hex && m->uniformF)    MOKAB_STAGE(10, 6, false, false);
@@ -2445,6 +2499,8 @@ int mokab_set_option(const char *name, int64_t value)
         else if (n == "stage_prefetch") { MOKAB_REQUIRE(value >= 0 && value <= 3, "set_option: stage_prefetch must be 0..3"); o.stage_prefetch = (int)value; }
         else if (n == "stage_prefetch_distance") { MOKAB_REQUIRE(value >= 0 && value < (1 << 30), "set_option: bad stage_prefetch_distance"); o.stage_prefetch_distance = (int)value; }
         else if (n == "stage_wf_block_major") o.stage_wf_block_major = value ? 1 : 0;
+        else if (n == "stage_flux_smem") o.stage_flux_smem = value ? 1 : 0;
+        else if (n == "stage_pdl") o.stage_pdl = value ? 1 : 0;
         else if (n == "decomp_serial_blocks") o.decomp_serial_blocks = (int)value;
         else if (n == "test_drop_dependency") o.test_drop_dependency = (int)value;
         else throw Error("set_option: unknown option '" + n + "'");
@@ -2462,6 +2518,8 @@ int mokab_get_option(const char *name, int64_t *value)
         else if (n == "stage_prefetch") *value = o.stage_prefetch;
         else if (n == "stage_prefetch_distance") *value = o.stage_prefetch_distance;
         else if (n == "stage_wf_block_major") *value = o.stage_wf_block_major;
+        else if (n == "stage_flux_smem") *value = o.stage_flux_smem;
+        else if (n == "stage_pdl") *value = o.stage_pdl;
         else if (n == "decomp_serial_blocks") *value = o.decomp_serial_blocks;
         else throw Error("get_option: unknown option '" + n + "'");
     });

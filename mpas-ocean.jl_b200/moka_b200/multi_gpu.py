@@ -459,6 +459,30 @@ def bench_main(args, rank, world, local):
     e2e_steps(Ke)
     torch.cuda.synchronize()
     e2e_s = float(comm.allreduce((time.perf_counter() - t0) / Ke, "max")[0])
+    # the two halves of that leg on their own (explain it: which of them the leg's time follows)
+    def copy_only(n):
+        for i in range(n):
+            if f32:
+                model.prog.upload_async(normalVelocity=hin[i & 1][0], ssh=hin[i & 1][1])
+            else:
+                model.prog.upload_async(normalVelocity=hin[i & 1][0], layerThickness=hin[i & 1][1])
+            model.prog.download_async(ssh=hout[i & 1][0], normalVelocity=hout[i & 1][1])
+        model.prog.synchronize()
+        model.synchronize()
+    copy_only(1)
+    comm.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    copy_only(Ke)
+    torch.cuda.synchronize()
+    copy_s = float(comm.allreduce((time.perf_counter() - t0) / Ke, "max")[0])
+    comm.barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        model.step(dt, 1)
+    model.synchronize()
+    torch.cuda.synchronize()
+    step1_s = float(comm.allreduce((time.perf_counter() - t0) / Ke, "max")[0])
     cnt = comm.allreduce([nCl + nEl, nCl + nEl, loc["nCellsOwned"], launches], "sum")
     blocks = model.mesh.block_counts()
     halo_bytes = (sum(model.send_counts) + sum(model.recv_counts)) * np.dtype(npdt).itemsize
@@ -503,11 +527,13 @@ def bench_main(args, rank, world, local):
                        "rank0_blocks_rebuilding_edgesOnEdge": [int(nder), int(nblk)],
                        "variant": {"lib": os.environ.get("MOKAB_LIB", "libmoka_b200.so"),
                                    "stage_tma": L.get_option("stage_tma"), "stage_prefetch": L.get_option("stage_prefetch"),
-                                   "stage_prefetch_distance": L.get_option("stage_prefetch_distance")}},
+                                   "stage_prefetch_distance": L.get_option("stage_prefetch_distance"),
+                                   "stage_flux_smem": L.get_option("stage_flux_smem"), "stage_pdl": L.get_option("stage_pdl")}},
             "clocks": clocks,
             "e2e": {"value": nC_glob / e2e_s, "unit": "cell-steps/s", "h2d_bytes_per_step": int(cnt[0] * item),
                     "d2h_bytes_per_step": int(cnt[1] * item), "ms_per_step": e2e_s * 1e3, "steps": Ke,
-                    "pipelined": True, "returns": "ssh + normalVelocity of the new state (layerThickness = ssh + restingThicknessSum stays on the device)"},
+                    "pipelined": True, "copies_only_ms_per_step": copy_s * 1e3, "one_step_calls_only_ms_per_step": step1_s * 1e3,
+                    "returns": "ssh + normalVelocity of the new state (layerThickness = ssh + restingThicknessSum stays on the device)"},
             "gpu_launches": int(cnt[3]),
             "parity": parity,
             "roofline": {"bound": "hbm", "kernel": "k_rk_stage", "achieved": achieved, "peak": peak, "unit": "GB/s",
