@@ -189,6 +189,21 @@ template <class R> __host__ __device__ constexpr int tma_align() { return 16 / (
 // (griddepcontrol.wait) only where it first touches the state -- its connectivity, metrics and weight copies (the L2
 // prefetches, the cp.async weights, cellsOnEdge, g/dc: ~60 % of the bytes of its first edge iteration) are issued before
 // that.  Both instructions are no-ops in a launch without the programmatic attribute.
+// Loads of the STATE (the output of the previous launch).  By default through the read-only path (__ldg), which is legal as
+// long as a launch starts after the previous one has completed; a programmatically dependent launch starts EARLIER, so lines
+// of a buffer that an older, still running launch reads can enter L1 after this launch's start-of-grid invalidation and be
+// stale by the time the buffer has been rewritten and this launch reads it (seen on hardware, r02h).  Builds with
+// MOKAB_STATE_LOADS_COHERENT (libmoka_b200_coh.so) use plain coherent loads, which griddepcontrol.wait orders; "stage_pdl" is
+// honoured by those builds only.
+template <class T>
+__device__ __forceinline__ T ld_state(const T *p)
+{
+#ifdef MOKAB_STATE_LOADS_COHERENT
+    return *p;
+#else
+    return __ldg(p);
+#endif
+}
 __device__ __forceinline__ void pdl_launch_dependents()
 {
 #ifndef MOKAB_SIM
@@ -401,7 +416,7 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
             const R cur = (STAGE == 4) ? R(0) : A.uCur[e];
             const R accIn = (STAGE == 1) ? R(0) : A.uAcc[e];
             if constexpr (FX) fxU = A.uOld[e];
-            const R h1 = __ldg(A.hOld + c.x), h2 = __ldg(A.hOld + c.y);
+            const R h1 = ld_state(A.hOld + c.x), h2 = ld_state(A.hOld + c.y);
             const R H1 = (kPert<R> && !FX) ? R(0) : __ldg(A.H + c.x), H2 = (kPert<R> && !FX) ? R(0) : __ldg(A.H + c.y);
             if constexpr (FX) {   // the flux of this edge through its length, as the cell phase forms it (commutative sum of the two thicknesses)
                 const R ha = kPert<R> ? add_rn(h1, H1) : h1, hb = kPert<R> ? add_rn(h2, H2) : h2;
@@ -440,7 +455,7 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
             }
             R uu[S2T ? S2T : 1];
 #pragma unroll
-            for (int i = 0; i < S2T; ++i) uu[i] = __ldg(A.uOld + idx[i]);
+            for (int i = 0; i < S2T; ++i) uu[i] = ld_state(A.uOld + idx[i]);
             if constexpr (TMA == 3) {   // this thread's own copies have landed: read them back (16-byte shared-memory loads, no bank conflicts)
                 cp_async_wait_all();
                 constexpr int NG = cpa_groups<R, S2T>(), V = cpa_vec<R>();
@@ -487,12 +502,12 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
         pdl_wait();
         const R cur = (STAGE == 4) ? R(0) : A.uCur[e];
         const R accIn = (STAGE == 1) ? R(0) : A.uAcc[e];
-        const R h1 = __ldg(A.hOld + c.x), h2 = __ldg(A.hOld + c.y);
+        const R h1 = ld_state(A.hOld + c.x), h2 = ld_state(A.hOld + c.y);
         const R H1 = kPert<R> ? R(0) : __ldg(A.H + c.x), H2 = kPert<R> ? R(0) : __ldg(A.H + c.y);
         k = kPert<R> ? -mul_rn(ld_stream(A.gdc + e), add_rn(h2, -h1))
                      : -mul_rn(ld_stream(A.gdc + e), add_rn(add_rn(h2, -H2), -add_rn(h1, -H1)));
         for (int i = 0; i < n; ++i) {
-            const R wu = mul_rn(ld_stream(A.wf + (size_t)i * nE + e), __ldg(A.uOld + ld_stream(A.eoe + (size_t)i * nE + e)));
+            const R wu = mul_rn(ld_stream(A.wf + (size_t)i * nE + e), ld_state(A.uOld + ld_stream(A.eoe + (size_t)i * nE + e)));
             k = add_rn(k, FOLD ? wu : mul_rn(wu, A.f0));
         }
         if (STAGE != 4) A.uOut[e] = add_rn(cur, mul_rn(A.a, k));       // Provis = Curr + a*tend (time_integration.jl:124)
@@ -517,7 +532,7 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
         int ee[ST ? ST : 1];
         if (live) {
             n = ld_stream(A.nEoC + cc);
-            hc = kPert<R> ? add_rn(__ldg(A.hOld + cc), __ldg(A.H + cc)) : __ldg(A.hOld + cc);
+            hc = kPert<R> ? add_rn(ld_state(A.hOld + cc), __ldg(A.H + cc)) : ld_state(A.hOld + cc);
             cur = (STAGE == 4) ? R(0) : A.hCur[cc];
             accIn = (STAGE == 1) ? R(0) : A.hAcc[cc];
 #pragma unroll
@@ -537,8 +552,8 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
                     } else {   // an edge of a neighbouring block: as the plain kernel does it
                         const int2 cs = __ldg(A.ce + e);
                         const int other = cs.x == cc ? cs.y : cs.x;
-                        const R ho = kPert<R> ? add_rn(__ldg(A.hOld + other), __ldg(A.H + other)) : __ldg(A.hOld + other);
-                        fl[i] = mul_rn(mul_rn(__ldg(A.uOld + e), mul_rn(R(0.5), add_rn(hc, ho))), __ldg(A.dv + e));
+                        const R ho = kPert<R> ? add_rn(ld_state(A.hOld + other), __ldg(A.H + other)) : ld_state(A.hOld + other);
+                        fl[i] = mul_rn(mul_rn(ld_state(A.uOld + e), mul_rn(R(0.5), add_rn(hc, ho))), __ldg(A.dv + e));
                     }
                 }
             }
@@ -558,7 +573,7 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
     if (cc < A.nCown) {
         const int n = ld_stream(A.nEoC + cc);
         // Float32: the arrays hold the perturbation h - H (see kPert); the flux needs the whole thickness
-        const R hc = kPert<R> ? add_rn(__ldg(A.hOld + cc), __ldg(A.H + cc)) : __ldg(A.hOld + cc);
+        const R hc = kPert<R> ? add_rn(ld_state(A.hOld + cc), __ldg(A.H + cc)) : ld_state(A.hOld + cc);
         const R cur = (STAGE == 4) ? R(0) : A.hCur[cc];
         const R accIn = (STAGE == 1) ? R(0) : A.hAcc[cc];
         R acc = R(0);
@@ -572,14 +587,14 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
             for (int i = 0; i < ST; ++i) {
                 const int e = ee[i] >= 0 ? (ee[i] >> 1) : 0;
                 cs[i] = __ldg(A.ce + e);
-                uu[i] = __ldg(A.uOld + e);
+                uu[i] = ld_state(A.uOld + e);
                 dd[i] = __ldg(A.dv + e);
             }
             const R invA = ld_stream(A.invArea + cc);
 #pragma unroll
             for (int i = 0; i < ST; ++i) {
                 const int other = cs[i].x == cc ? cs[i].y : cs[i].x;
-                const R ho = kPert<R> ? add_rn(__ldg(A.hOld + other), __ldg(A.H + other)) : __ldg(A.hOld + other);
+                const R ho = kPert<R> ? add_rn(ld_state(A.hOld + other), __ldg(A.H + other)) : ld_state(A.hOld + other);
                 // flux = u*hEdge (DiagnosticVars.jl:158-173), hEdge = 0.5*(h1+h2) (Operators.jl:201-222),
                 // tend += flux*dv*sign*invArea (horizontal_advection.jl:64-65)
                 const R f = mul_rn(mul_rn(mul_rn(uu[i], mul_rn(R(0.5), add_rn(hc, ho))), dd[i]), invA);
@@ -592,8 +607,8 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
                 const int e = ex >> 1;
                 const int2 cs = __ldg(A.ce + e);
                 const int other = cs.x == cc ? cs.y : cs.x;
-                const R ho = kPert<R> ? add_rn(__ldg(A.hOld + other), __ldg(A.H + other)) : __ldg(A.hOld + other);
-                const R f = mul_rn(mul_rn(mul_rn(__ldg(A.uOld + e), mul_rn(R(0.5), add_rn(hc, ho))), __ldg(A.dv + e)), invA);
+                const R ho = kPert<R> ? add_rn(ld_state(A.hOld + other), __ldg(A.H + other)) : ld_state(A.hOld + other);
+                const R f = mul_rn(mul_rn(mul_rn(ld_state(A.uOld + e), mul_rn(R(0.5), add_rn(hc, ho))), __ldg(A.dv + e)), invA);
                 acc = add_rn(acc, (ex & 1) ? f : -f);
             }
         }

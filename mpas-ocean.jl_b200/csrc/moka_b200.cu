@@ -727,6 +727,8 @@ struct Options {
                                   // `stage_prefetch_distance` blocks after it
     int stage_prefetch_distance = 0;   // MOKAB_STAGE_PREFETCH_DISTANCE: 0 = one wave of resident blocks (SMs x blocks per SM)
     int stage_wf_block_major = 0; // MOKAB_STAGE_WF_BLOCK_MAJOR: the plain stage kernel reads the Coriolis weights from the block-major copy
+    int stage_auto = 1;           // MOKAB_STAGE_AUTO: with stage_tma = 3, a launch takes the plain kernel (one resident block per SM fewer, no
+                                  // prefetch) when the wave-quantisation model says its last round of blocks costs less (prefer_plain_variant)
     int stage_flux_smem = 0;      // MOKAB_STAGE_FLUX_SMEM: the cp.async-weights stage kernel leaves the thickness flux of the block's own edges in
                                   // shared memory for its cell phase (kernels_fused.cuh: FX)
     int stage_pdl = 0;            // MOKAB_STAGE_PDL: stage launches carry the programmatic-stream-serialization attribute (kernels_fused.cuh: pdl_*)
@@ -748,6 +750,7 @@ struct Options {
         stage_prefetch = geti("MOKAB_STAGE_PREFETCH", 1) & 3;
         stage_prefetch_distance = std::max(0, geti("MOKAB_STAGE_PREFETCH_DISTANCE", 0));
         stage_wf_block_major = geti("MOKAB_STAGE_WF_BLOCK_MAJOR", 0) ? 1 : 0;
+        stage_auto = geti("MOKAB_STAGE_AUTO", 1) ? 1 : 0;
         stage_flux_smem = geti("MOKAB_STAGE_FLUX_SMEM", 0) ? 1 : 0;
         stage_pdl = geti("MOKAB_STAGE_PDL", 0) ? 1 : 0;
         decomp_serial_blocks = std::max(0, geti("MOKAB_DECOMP_SERIAL_BLOCKS", 0));
@@ -832,11 +835,27 @@ static void launch_pdl(void (*kernel)(P...), int grid, size_t smem, cudaStream_t
 }
 static bool stage_pdl_enabled()
 {
-#ifdef MOKAB_SIM
-    return false;
+#if defined(MOKAB_SIM) || !defined(MOKAB_STATE_LOADS_COHERENT)
+    return false;     // (the default build reads the state through the read-only path: kernels_fused.cuh ld_state)
 #else
     return options().stage_pdl != 0;
 #endif
+}
+
+// Which of the two tuned stage kernels a launch of `grid` blocks takes (option "stage_auto").  Blocks of one launch start
+// together and last about equally long, so a launch runs in ROUNDS of (SMs x resident blocks) and pays for a whole last round
+// however few blocks are left in it; a round lasts in proportion to the resident blocks r.  The cp.async-weights kernel
+// (r = 5 in Float64, 6 in Float32) moves ~2-3 % more bytes per second than the plain one (r = 4 / 5) once a launch has tens of
+// rounds, but on a small grid its longer rounds lose: measured r02h on 512 x 512 (1 024 blocks) 2.38 vs 2.97 G cell-steps/s
+// -- the model says 2 x 5 against 2 x 4 -- and on the 1 024 x 1 024 channel (4 096 blocks) 2.48 vs 2.65 G (6 x 5 against
+// 7 x 4); the parts of an 8-GPU run are grids of that size.
+static bool prefer_plain_variant(int grid, int num_sms, int r_cpa, int r_plain, double eff_cpa)
+{
+    auto cost = [&](int r, double eff) {
+        const int per_round = num_sms * r;
+        return (double)((grid + per_round - 1) / per_round) * r / eff;
+    };
+    return cost(r_plain, 1.0) < cost(r_cpa, eff_cpa);
 }
 
 // ---- fused RK4 ------------------------------------------------------------------------------------------------
@@ -868,7 +887,16 @@ static void launch_stage(mokab_ctx *ctx, const mokab_mesh *m, fused::StageArgs<R
         FusedMesh<R> &fm = fused_of<R>(const_cast<mokab_mesh *>(m));
         if (fm.wfB.n) { A.wfB = fm.wfB.p; A.wfBOff = fm.wfBOff.p; }
     }
-    if ((hex || hept) && stage_tma_mode() == 3) {   // the default: weights through per-thread cp.async into shared memory (kernels_fused.cuh)
+    bool use_cpa = (hex || hept) && stage_tma_mode() == 3;
+    if (use_cpa && options().stage_auto) {
+        const int rc = der ? fused::stage_blocks<R, true, 3>() : fused::stage_blocks<R, false, 3>();
+        const int rp = der ? fused::stage_blocks<R, true, 0>() : fused::stage_blocks<R, false, 0>();
+        if (prefer_plain_variant(grid, ctx->num_sms, rc, rp, sizeof(R) == 8 ? 1.02 : 1.03)) {
+            use_cpa = false;
+            A.pf = 0;
+        }
+    }
+    if (use_cpa) {   // the default: weights through per-thread cp.async into shared memory (kernels_fused.cuh)
         FusedMesh<R> &fm = fused_of<R>(const_cast<mokab_mesh *>(m));
         if (fm.wfI.n) {
             A.wfI = fm.wfI.p;
@@ -2499,6 +2527,7 @@ int mokab_set_option(const char *name, int64_t value)
         else if (n == "stage_prefetch") { MOKAB_REQUIRE(value >= 0 && value <= 3, "set_option: stage_prefetch must be 0..3"); o.stage_prefetch = (int)value; }
         else if (n == "stage_prefetch_distance") { MOKAB_REQUIRE(value >= 0 && value < (1 << 30), "set_option: bad stage_prefetch_distance"); o.stage_prefetch_distance = (int)value; }
         else if (n == "stage_wf_block_major") o.stage_wf_block_major = value ? 1 : 0;
+        else if (n == "stage_auto") o.stage_auto = value ? 1 : 0;
         else if (n == "stage_flux_smem") o.stage_flux_smem = value ? 1 : 0;
         else if (n == "stage_pdl") o.stage_pdl = value ? 1 : 0;
         else if (n == "decomp_serial_blocks") o.decomp_serial_blocks = (int)value;
@@ -2518,6 +2547,7 @@ int mokab_get_option(const char *name, int64_t *value)
         else if (n == "stage_prefetch") *value = o.stage_prefetch;
         else if (n == "stage_prefetch_distance") *value = o.stage_prefetch_distance;
         else if (n == "stage_wf_block_major") *value = o.stage_wf_block_major;
+        else if (n == "stage_auto") *value = o.stage_auto;
         else if (n == "stage_flux_smem") *value = o.stage_flux_smem;
         else if (n == "stage_pdl") *value = o.stage_pdl;
         else if (n == "decomp_serial_blocks") *value = o.decomp_serial_blocks;
