@@ -287,7 +287,7 @@ def run_b200(args):
                    "variant": {"lib": os.environ.get("MOKAB_LIB", "libmoka_b200.so"),
                                "stage_tma": L.get_option("stage_tma"), "stage_prefetch": L.get_option("stage_prefetch"),
                                "stage_prefetch_distance": L.get_option("stage_prefetch_distance"),
-                               "stage_flux_smem": L.get_option("stage_flux_smem"), "stage_pdl": L.get_option("stage_pdl")}},
+                               "stage_auto": L.get_option("stage_auto"), "stage_pdl": L.get_option("stage_pdl")}},
         "clocks": clocks,
         "e2e": {"value": nC / e2e_s, "unit": "cell-steps/s", "h2d_bytes_per_step": int((nE + nC) * item),
                 "d2h_bytes_per_step": int((nC + nE) * item), "ms_per_step": e2e_s * 1e3, "steps": Ke,

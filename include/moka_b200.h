@@ -247,6 +247,14 @@ int  mokab_adjoint_rk4(mokab_state *state);
  * dJ/d(initial normalVelocity, layerThickness, ssh): ssh is an input of its own here (only the first step's pressure
  * gradient reads the array), exactly as in Enzyme's d_Prog.ssh[end].  A tape holds steps of one stepper only. */
 int  mokab_adjoint_forward_euler(mokab_state *state);
+/* Domain-decomposed states (mokab_decomp_setup): the same calls.  mokab_timestep_rk4_decomposed /
+ * mokab_timestep_forward_euler_decomposed record every rank's part of the trajectory (halo copies included) while a tape is
+ * open; mokab_adjoint_seed seeds the owned cells; mokab_adjoint_rk4 / mokab_adjoint_forward_euler run the same gather-form
+ * kernels over the owned entities and, after every reversed stage / step, refresh the halo copies of what the next one
+ * gathers (recomputed stage states, kbar, lambda; ForwardEuler: lambda_u, lambda_hEdge, q) through the packed exchange of
+ * the communicator, over the SAME send / receive lists as the forward exchange -- in gather form no transposed,
+ * accumulating exchange is needed.  All ranks must make these calls together (they are collective).  The gradient comes
+ * back per rank on its owned entities; J is mokab_reduce_decomposed(MOKAB_SUM_SSH2) before the seed. */
 
 /* ---- staged RungeKutta4 for domain-decomposed runs (one process per GPU) --------------------------
  * The same fused stage kernel, launched per stage and per part so the host can overlap the halo
@@ -362,12 +370,13 @@ int  mokab_decomp_close(mokab_state *state);
  * setting.  "stage_prefetch": bit 0 = a block pulls the streams of its later iterations into L2 at entry, bit 1 = those of
  * the block launched "stage_prefetch_distance" blocks later (0 = one wave of resident blocks); "stage_tma": 1 / 2 = the
  * Coriolis weights through bulk asynchronous copies (slot-major rows / a block-major copy), 3 = through per-thread cp.async into
- * shared memory (one more resident block per SM); "stage_flux_smem": with stage_tma = 3, the edge phase leaves the thickness
- * flux of the block's own edges in shared memory and the cell phase reads it back after one barrier instead of gathering
- * cellsOnEdge, u, dvEdge and the neighbour's thickness again; "stage_pdl": stage launches carry the programmatic-stream-
- * serialization attribute, so the static half of stage s + 1 overlaps the tail of stage s.  Defaults: stage_tma = 3,
- * stage_prefetch = 1 (the fastest on B200, profiles/README.md r02d); the environment overrides them (MOKAB_STAGE_PREFETCH,
- * MOKAB_STAGE_PREFETCH_DISTANCE, MOKAB_STAGE_TMA, MOKAB_STAGE_FLUX_SMEM, MOKAB_STAGE_PDL). */
+ * shared memory (one more resident block per SM); "stage_auto": with stage_tma = 3, every Float64 launch takes whichever of
+ * the cp.async and the plain kernel a wave-quantisation model prefers for its number of blocks (small grids -- 512 x 512, the
+ * parts of an 8-GPU run -- are up to 25 % faster on the plain kernel, which keeps one block per SM fewer resident);
+ * "stage_pdl": stage launches carry the programmatic-stream-serialization attribute, so the static half of stage s + 1
+ * overlaps the tail of stage s.  Defaults: stage_tma = 3, stage_prefetch = 1, stage_auto = 1, stage_pdl = 0
+ * (profiles/README.md r02d, r02i); the environment overrides them (MOKAB_STAGE_PREFETCH, MOKAB_STAGE_PREFETCH_DISTANCE,
+ * MOKAB_STAGE_TMA, MOKAB_STAGE_AUTO, MOKAB_STAGE_PDL). */
 int  mokab_set_option(const char *name, int64_t value);
 int  mokab_get_option(const char *name, int64_t *value);
 /* number of interior / boundary blocks of the fused kernel (diagnostic) */

@@ -213,18 +213,59 @@ static void decomp_prepare(mokab_state *st)
     ensure_wf_interleaved<R>(m);
 }
 
+// what the reverse sweep needs of the input of the step about to run: RungeKutta4 (u, h) -- halo copies included, the stage
+// states are recomputed from them --, ForwardEuler (u, the lagged layerThicknessEdge)
+template <class R>
+static void decomp_tape_record(mokab_state *st, double dt, int kind)
+{
+    StateT<R> *t = typed<R>(st);
+    const mokab_mesh *m = st->mesh;
+    cudaStream_t s = st->ctx->stream;
+    if (kind == 1) {
+        if constexpr (sizeof(R) == 8) fe_tape_record(st, dt, t->u[st->cur].p, t->hE[st->cur].p);
+        return;
+    }
+    const size_t k = t->tapeDt.size();
+    MOKAB_CUDA(cudaMemcpyAsync(t->tapeU.p + k * m->nE, t->u[st->cur].p, m->nE * sizeof(R), cudaMemcpyDeviceToDevice, s));
+    MOKAB_CUDA(cudaMemcpyAsync(t->tapeH.p + k * m->nC, t->h[st->cur].p, m->nC * sizeof(R), cudaMemcpyDeviceToDevice, s));
+    t->tapeDt.push_back(dt);
+}
+
 template <class R>
 static void decomp_run(mokab_state *st, double dt, int64_t nsteps, int kind)
 {
     mokab_state::Decomp &D = st->dec;
     mokab_ctx *ctx = st->ctx;
+    if (typed<R>(st)->taping) {
+        StateT<R> *t = typed<R>(st);
+        MOKAB_REQUIRE((int64_t)t->tapeDt.size() + nsteps <= t->tapeCap, "timestep_*_decomposed: the tape is full (mokab_tape_begin max_steps)");
+        MOKAB_REQUIRE(t->tapeKind == 0 || t->tapeKind == kind + 1, "timestep_*_decomposed: the tape already holds steps of the other stepper");
+        t->tapeKind = kind + 1;             // (also a call with nsteps = 0: the seed then follows this stepper's state definition)
+        if (kind == 0 && nsteps > 0 && t->tapeH.n < (size_t)t->tapeCap * st->mesh->nC) t->tapeH.alloc((size_t)t->tapeCap * st->mesh->nC);
+    }
     if (nsteps <= 0) return;
     decomp_prepare<R>(st);
     if (!D.use_graph()) {
+        if (typed<R>(st)->taping) {
+            for (int64_t i = 0; i < nsteps; ++i) {
+                decomp_tape_record<R>(st, dt, kind);
+                if (kind == 0) decomp_enqueue_rk4<R>(st, dt, 1); else decomp_enqueue_fe(st, dt, 1);
+            }
+            return;
+        }
         if (kind == 0) decomp_enqueue_rk4<R>(st, dt, nsteps); else decomp_enqueue_fe(st, dt, nsteps);
         return;
     }
     if (!D.graphs_ready[kind] || D.graph_dt[kind] != dt || D.graph_epoch[kind] != options().epoch) decomp_build_graphs<R>(st, dt, kind);
+    if (typed<R>(st)->taping) {   // reverse mode: what the adjoint needs of the state before every step goes on the tape, one step per replay
+        for (int64_t i = 0; i < nsteps; ++i) {
+            decomp_tape_record<R>(st, dt, kind);
+            MOKAB_CUDA(cudaGraphLaunch(D.graph[kind][st->cur][0], ctx->stream));
+            ctx->launches += D.graph_launches[kind][0];
+            st->cur = 1 - st->cur;
+        }
+        return;
+    }
     int64_t left = nsteps;
     while (left >= 2) {                                            // (a two-step graph leaves the time-level parity where it was)
         MOKAB_CUDA(cudaGraphLaunch(D.graph[kind][st->cur][1], ctx->stream));

@@ -189,19 +189,19 @@ template <class R> __host__ __device__ constexpr int tma_align() { return 16 / (
 // (griddepcontrol.wait) only where it first touches the state -- its connectivity, metrics and weight copies (the L2
 // prefetches, the cp.async weights, cellsOnEdge, g/dc: ~60 % of the bytes of its first edge iteration) are issued before
 // that.  Both instructions are no-ops in a launch without the programmatic attribute.
-// Loads of the STATE (the output of the previous launch).  By default through the read-only path (__ldg), which is legal as
-// long as a launch starts after the previous one has completed; a programmatically dependent launch starts EARLIER, so lines
-// of a buffer that an older, still running launch reads can enter L1 after this launch's start-of-grid invalidation and be
-// stale by the time the buffer has been rewritten and this launch reads it (seen on hardware, r02h).  Builds with
-// MOKAB_STATE_LOADS_COHERENT (libmoka_b200_coh.so) use plain coherent loads, which griddepcontrol.wait orders; "stage_pdl" is
-// honoured by those builds only.
+// Loads of the STATE (the output of the previous launch) are plain coherent loads, not the read-only path (__ldg): a
+// programmatically dependent launch ("stage_pdl") starts before the previous one has finished, so lines of a buffer that an
+// older, still running launch reads can enter L1 AFTER this launch's start-of-grid invalidation and be stale once the buffer
+// has been rewritten and this launch reads it.  Seen on hardware (r02h: wrong results on a 3-block mesh with __ldg);
+// griddepcontrol.wait orders plain loads.  Measured cost of the change: none (r02i: 2.864 vs 2.851 G at 2048 x 2048, 4.281 vs
+// 4.270 G in Float32).  MOKAB_STATE_LOADS_LDG builds the read-only variant for A/B; it ignores "stage_pdl".
 template <class T>
 __device__ __forceinline__ T ld_state(const T *p)
 {
-#ifdef MOKAB_STATE_LOADS_COHERENT
-    return *p;
-#else
+#ifdef MOKAB_STATE_LOADS_LDG
     return __ldg(p);
+#else
+    return *p;
 #endif
 }
 __device__ __forceinline__ void pdl_launch_dependents()
@@ -217,16 +217,10 @@ __device__ __forceinline__ void pdl_wait()
 #endif
 }
 
-// FX = true (opt-in, "stage_flux_smem"; cp.async-weights variant only): the edge phase leaves u * hEdge * dv of every edge the
-// block owns in SHARED memory, and the cell phase -- after one block-wide barrier -- takes the flux of a slot from there when the
-// edge is one of the block's own (~90 % of the slots of a 16 x 16 patch) instead of gathering cellsOnEdge, u, dv and the other
-// cell's h again: four gathers per slot become one shared-memory read.  The product is formed with the cell phase's own
-// operation order ((u * (0.5 * (h1 + h2))) * dv; the sum of the two thicknesses commutes), so results stay bit-identical.
-template <class R, int STAGE, int S2T, int ST, bool FOLD, bool DER, bool PUSH = false, int TMA = 0, bool FX = false>
+template <class R, int STAGE, int S2T, int ST, bool FOLD, bool DER, bool PUSH = false, int TMA = 0>
 __global__ void __launch_bounds__(kThreads, (stage_blocks<R, DER, TMA>()))
 k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
 {
-    static_assert(!FX || (TMA == 3 && !PUSH && S2T != 0 && ST != 0), "FX rides on the cp.async-weights variant with compile-time row widths");
     pdl_launch_dependents();
     const int S2 = S2T ? S2T : S2rt;
     const int S = ST ? ST : Srt;
@@ -235,11 +229,9 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
     const int cBase = b * kTC;
     static_assert(TMA == 0 || (S2T != 0 && ST != 0), "the TMA variants stage compile-time many weight rows");
     [[maybe_unused]] unsigned char *cpa_slot = nullptr;             // TMA = 3: this thread's 16-byte slots, one per slot group, kThreads * 16 bytes apart
-    [[maybe_unused]] R *fxs = nullptr;                              // FX: u * hEdge * dv of the block's own edges
     if constexpr (TMA == 3) {
         MOKAB_DYN_SMEM(dyn3);
         cpa_slot = dyn3 + (size_t)threadIdx.x * 16;
-        if constexpr (FX) fxs = reinterpret_cast<R *>(dyn3 + (size_t)cpa_groups<R, S2T>() * kThreads * 16);
     }
     [[maybe_unused]] const R *sw = nullptr;
     [[maybe_unused]] bool weights_landed = false;
@@ -408,20 +400,13 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
                 }
             }
             const R g = ld_stream(A.gdc + e);
-            [[maybe_unused]] R fxD = R(0), fxU = R(0);
-            if constexpr (FX) fxD = ld_stream(A.dv + e);
             pdl_wait();                                                 // everything above is static; the state comes next
             // the RK operands are independent of the tendency: issue their loads now (they may alias the stores
             // below, so the compiler cannot hoist them itself)
             const R cur = (STAGE == 4) ? R(0) : A.uCur[e];
             const R accIn = (STAGE == 1) ? R(0) : A.uAcc[e];
-            if constexpr (FX) fxU = A.uOld[e];
             const R h1 = ld_state(A.hOld + c.x), h2 = ld_state(A.hOld + c.y);
-            const R H1 = (kPert<R> && !FX) ? R(0) : __ldg(A.H + c.x), H2 = (kPert<R> && !FX) ? R(0) : __ldg(A.H + c.y);
-            if constexpr (FX) {   // the flux of this edge through its length, as the cell phase forms it (commutative sum of the two thicknesses)
-                const R ha = kPert<R> ? add_rn(h1, H1) : h1, hb = kPert<R> ? add_rn(h2, H2) : h2;
-                fxs[e - e0] = mul_rn(mul_rn(fxU, mul_rn(R(0.5), add_rn(ha, hb))), fxD);
-            }
+            const R H1 = kPert<R> ? R(0) : __ldg(A.H + c.x), H2 = kPert<R> ? R(0) : __ldg(A.H + c.y);
             if (kDer && derived) {
                 // posE: bits 0-2 position of e in the row of cell 1, bits 3-5 in the row of cell 2, bit 7 = both rows
                 // have ST entries and the edge is not masked (the branch-free common case)
@@ -523,53 +508,6 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
     // ---- cells of this block ----------------------------------------------------------------------------
     const int cc = cBase + threadIdx.x;
     pdl_wait();                                                         // (a block that owns no edge has not waited yet)
-    if constexpr (FX) {
-        // Everything the cell needs that is not a flux is requested BEFORE the barrier, so those latencies run while the
-        // block's slower warps finish their edges; after it, a slot whose edge the block owns is one shared-memory read.
-        const bool live = cc < A.nCown;
-        int n = 0;
-        R hc = R(0), cur = R(0), accIn = R(0), invA = R(0);
-        int ee[ST ? ST : 1];
-        if (live) {
-            n = ld_stream(A.nEoC + cc);
-            hc = kPert<R> ? add_rn(ld_state(A.hOld + cc), __ldg(A.H + cc)) : ld_state(A.hOld + cc);
-            cur = (STAGE == 4) ? R(0) : A.hCur[cc];
-            accIn = (STAGE == 1) ? R(0) : A.hAcc[cc];
-#pragma unroll
-            for (int i = 0; i < ST; ++i) ee[i] = i < n ? __ldg(A.eoc + (size_t)i * nC + cc) : -1;
-            invA = ld_stream(A.invArea + cc);
-        }
-        __syncthreads();
-        if (live) {
-            R fl[ST ? ST : 1];
-#pragma unroll
-            for (int i = 0; i < ST; ++i) {
-                fl[i] = R(0);
-                if (ee[i] >= 0) {
-                    const int e = ee[i] >> 1;
-                    if ((unsigned)(e - e0) < (unsigned)(e1 - e0)) {
-                        fl[i] = fxs[e - e0];
-                    } else {   // an edge of a neighbouring block: as the plain kernel does it
-                        const int2 cs = __ldg(A.ce + e);
-                        const int other = cs.x == cc ? cs.y : cs.x;
-                        const R ho = kPert<R> ? add_rn(ld_state(A.hOld + other), __ldg(A.H + other)) : ld_state(A.hOld + other);
-                        fl[i] = mul_rn(mul_rn(ld_state(A.uOld + e), mul_rn(R(0.5), add_rn(hc, ho))), __ldg(A.dv + e));
-                    }
-                }
-            }
-            R acc = R(0);
-#pragma unroll
-            for (int i = 0; i < ST; ++i) {
-                const R f = mul_rn(fl[i], invA);
-                if (ee[i] >= 0) acc = add_rn(acc, (ee[i] & 1) ? f : -f);
-            }
-            const R k = acc;
-            if (STAGE != 4) A.hOut[cc] = add_rn(cur, mul_rn(A.a, k));
-            if (STAGE == 1) A.hAcc[cc] = add_rn(cur, mul_rn(A.b, k));
-            else            A.hAcc[cc] = add_rn(accIn, mul_rn(A.b, k));
-        }
-        return;
-    }
     if (cc < A.nCown) {
         const int n = ld_stream(A.nEoC + cc);
         // Float32: the arrays hold the perturbation h - H (see kPert); the flux needs the whole thickness

@@ -63,6 +63,12 @@ struct HostMesh {
     std::vector<int32_t> eoe;                  // slot-major (S2, nE)
     std::vector<double> woe;                   // slot-major (S2, nE); 0 beyond nEoE / on masked edges
     std::vector<uint8_t> nEoE;
+    // decomposed meshes: the edgesOnEdge / weightsOnEdge rows of the HALO edges, edge-major (nE - nEo, haloS2), new numbering, -1 =
+    // absent or not local.  No forward kernel reads them (a halo edge's tendency is its owner's business); the reverse mode does:
+    // the transposed Coriolis stencil of an owned edge lists every edge whose sum reads it, halo edges included.
+    std::vector<int32_t> haloEoe;
+    std::vector<double> haloWoe;
+    int haloS2 = 0;
     std::vector<double> dc, dv, fE;
     std::vector<int32_t> eoc, sgnC;            // slot-major (S, nC)
     std::vector<uint8_t> nEoC;
@@ -244,6 +250,8 @@ static void build_host_mesh(const mokab_mesh_desc &d, uint32_t flags, HostMesh &
     // ---- edges -----------------------------------------------------------------------------------
     m.ce.resize(2 * nE); m.eoe.assign((size_t)S2 * nE, -1); m.woe.assign((size_t)S2 * nE, 0.0);
     m.nEoE.resize(nE); m.dc.resize(nE); m.dv.resize(nE); m.fE.resize(nE);
+    m.haloS2 = S2f;
+    m.haloEoe.assign((size_t)(nE - nEo) * S2f, -1); m.haloWoe.assign((size_t)(nE - nEo) * S2f, 0.0);
 #pragma omp parallel for schedule(static)
     for (int64_t en = 0; en < nE; ++en) {
         const int64_t eo = m.permE[en];
@@ -262,6 +270,15 @@ static void build_host_mesh(const mokab_mesh_desc &d, uint32_t flags, HostMesh &
             // absent slots (0 entries) carry weight 0 like the padding: every kernel -- fused ForwardEuler reads the raw weights
             // with the padded index rows -- then agrees with the reference kernel, which skips them (coriolis kernel :67)
             m.woe[(size_t)i * nE + en] = (bnd || x == 0) ? 0.0 : d.weightsOnEdge[(int64_t)S2f * eo + i];
+        }
+        if (eo >= nEo && en >= nEo) {                                          // (halo edges keep their places behind the owned ones)
+            const int nh = std::min<int>(std::max<int>(d.nEdgesOnEdge[eo], 0), S2f);
+            for (int i = 0; i < nh; ++i) {
+                const int32_t x = d.edgesOnEdge[(int64_t)S2f * eo + i];
+                if (x < 1 || x > nE) continue;
+                m.haloEoe[(size_t)(en - nEo) * S2f + i] = invE[x - 1];
+                m.haloWoe[(size_t)(en - nEo) * S2f + i] = bnd ? 0.0 : d.weightsOnEdge[(int64_t)S2f * eo + i];
+            }
         }
     }
     m.f0 = m.fE[0];
@@ -395,6 +412,9 @@ struct mokab_mesh {
     mokab::DevBuf<int32_t> haloSend, haloRecv;  // combined [cells | edges] indices, device numbering
     std::vector<int32_t> hHaloSend;             // host copy (the push tables of the direct-store exchange are built from it)
     bool halo_ready = false;
+    std::vector<int32_t> hHaloEoe;              // decomposed meshes: the halo edges' rows (HostMesh::haloEoe), for the reverse mode
+    std::vector<double> hHaloWoe;
+    int haloS2 = 0;
     // adjoint: transpose of the Coriolis stencil (built on first use)
     mokab::DevBuf<int32_t> eoeT;
     mokab::DevBuf<double> woeT;

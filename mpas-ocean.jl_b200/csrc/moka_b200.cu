@@ -194,6 +194,7 @@ static void upload_mesh(mokab_ctx *ctx, HostMesh &hm, mokab_mesh *m)
     m->nBoundary = (int)hm.blkBoundary.size();
     m->hBlkEdgeStart.swap(hm.blkEdgeStart); m->hBlkInterior.swap(hm.blkInterior); m->hBlkBoundary.swap(hm.blkBoundary);
     m->permC.swap(hm.permC); m->permE.swap(hm.permE); m->permV.swap(hm.permV);
+    m->hHaloEoe.swap(hm.haloEoe); m->hHaloWoe.swap(hm.haloWoe); m->haloS2 = hm.haloS2;
     MOKAB_CUDA(cudaStreamSynchronize(s));
 }
 
@@ -649,7 +650,7 @@ static void run_fe_stage(mokab_state *st, double dt, int part, cudaStream_t stre
     mokab_ctx *ctx = st->ctx; mokab_mesh *m = const_cast<mokab_mesh *>(st->mesh); StateT<double> *t = st->d;
     const bool widths = (m->S2 == 10 && m->S == 6) || (m->S2 == 12 && m->S == 7);
     MOKAB_REQUIRE(widths, "forward_euler_stage: needs connectivity rows of at most (10, 6) or (12, 7) entries");
-    MOKAB_REQUIRE(!t->taping, "forward_euler_stage: recording a tape is not supported on decomposed meshes");
+    MOKAB_REQUIRE(!t->taping || st->dec.ready, "forward_euler_stage: a tape is recorded by mokab_timestep_forward_euler_decomposed, not by staged calls");
     MOKAB_REQUIRE(m->nV == 0, "forward_euler_stage: local meshes carry no vertices (relativeVorticity is not advanced)");
     ensure_fused<double>(m);
     FusedMesh<double> &fm = fused_of<double>(m);
@@ -729,15 +730,14 @@ struct Options {
     int stage_wf_block_major = 0; // MOKAB_STAGE_WF_BLOCK_MAJOR: the plain stage kernel reads the Coriolis weights from the block-major copy
     int stage_auto = 1;           // MOKAB_STAGE_AUTO: with stage_tma = 3, a launch takes the plain kernel (one resident block per SM fewer, no
                                   // prefetch) when the wave-quantisation model says its last round of blocks costs less (prefer_plain_variant)
-    int stage_flux_smem = 0;      // MOKAB_STAGE_FLUX_SMEM: the cp.async-weights stage kernel leaves the thickness flux of the block's own edges in
-                                  // shared memory for its cell phase (kernels_fused.cuh: FX)
     int stage_pdl = 0;            // MOKAB_STAGE_PDL: stage launches carry the programmatic-stream-serialization attribute (kernels_fused.cuh: pdl_*)
     int decomp_serial_blocks = 0;  // MOKAB_DECOMP_SERIAL_BLOCKS: with MOKAB_HALO_P2P_FUSED, a rank whose part has fewer blocks than this runs ONE
                                   // launch per stage (all blocks, exchange folded in) instead of the two-stream overlap schedule.
                                   // Off by default: measured SLOWER at N = 2 (profiles/README.md r02g) -- every block of stage s + 1
                                   // then waits for the neighbours' whole stage s, where the two-stream schedule lets the interior run
     int test_drop_dependency = 0; // TEST HOOK (tests/sim: does the checker have teeth?): 1 / 2 = leave out one of the two cross-stream
-                                  // waits of the decomposed RK4 schedule (interior after boundary / boundary after interior)
+                                  // waits of the decomposed RK4 schedule (interior after boundary / boundary after interior);
+                                  // 3 = leave out the halo copies of kbar in the decomposed reverse sweep
     int64_t epoch = 0;
     Options()
     {
@@ -751,7 +751,6 @@ struct Options {
         stage_prefetch_distance = std::max(0, geti("MOKAB_STAGE_PREFETCH_DISTANCE", 0));
         stage_wf_block_major = geti("MOKAB_STAGE_WF_BLOCK_MAJOR", 0) ? 1 : 0;
         stage_auto = geti("MOKAB_STAGE_AUTO", 1) ? 1 : 0;
-        stage_flux_smem = geti("MOKAB_STAGE_FLUX_SMEM", 0) ? 1 : 0;
         stage_pdl = geti("MOKAB_STAGE_PDL", 0) ? 1 : 0;
         decomp_serial_blocks = std::max(0, geti("MOKAB_DECOMP_SERIAL_BLOCKS", 0));
     }
@@ -835,8 +834,8 @@ static void launch_pdl(void (*kernel)(P...), int grid, size_t smem, cudaStream_t
 }
 static bool stage_pdl_enabled()
 {
-#if defined(MOKAB_SIM) || !defined(MOKAB_STATE_LOADS_COHERENT)
-    return false;     // (the default build reads the state through the read-only path: kernels_fused.cuh ld_state)
+#if defined(MOKAB_SIM) || defined(MOKAB_STATE_LOADS_LDG)
+    return false;     // (a build that reads the state through the read-only path must not start early: kernels_fused.cuh ld_state)
 #else
     return options().stage_pdl != 0;
 #endif
@@ -888,10 +887,12 @@ static void launch_stage(mokab_ctx *ctx, const mokab_mesh *m, fused::StageArgs<R
         if (fm.wfB.n) { A.wfB = fm.wfB.p; A.wfBOff = fm.wfBOff.p; }
     }
     bool use_cpa = (hex || hept) && stage_tma_mode() == 3;
-    if (use_cpa && options().stage_auto) {
+    // (Float64 only: in Float32 the model does not predict the measurements -- r02i: 1 024 blocks 4.14 (cp.async) vs 3.77 G
+    //  (plain), 4 096 blocks 3.65 vs 3.77, 16 384 blocks 4.27 vs 4.21 -- and the cp.async kernel wins or ties on balance)
+    if (use_cpa && options().stage_auto && sizeof(R) == 8) {
         const int rc = der ? fused::stage_blocks<R, true, 3>() : fused::stage_blocks<R, false, 3>();
         const int rp = der ? fused::stage_blocks<R, true, 0>() : fused::stage_blocks<R, false, 0>();
-        if (prefer_plain_variant(grid, ctx->num_sms, rc, rp, sizeof(R) == 8 ? 1.02 : 1.03)) {
+        if (prefer_plain_variant(grid, ctx->num_sms, rc, rp, 1.02)) {
             use_cpa = false;
             A.pf = 0;
         }
@@ -900,22 +901,13 @@ static void launch_stage(mokab_ctx *ctx, const mokab_mesh *m, fused::StageArgs<R
         FusedMesh<R> &fm = fused_of<R>(const_cast<mokab_mesh *>(m));
         if (fm.wfI.n) {
             A.wfI = fm.wfI.p;
-            size_t smem = (size_t)(hex ? fused::cpa_groups<R, 10>() : fused::cpa_groups<R, 12>()) * fused::kThreads * 16;
-            // "stage_flux_smem": + one value per edge of the largest block (under the 48 KB a launch gets without an opt-in)
-            const bool fx = options().stage_flux_smem && smem + (size_t)m->maxBlockEdges * sizeof(R) <= 48 * 1024;
-            if (fx) smem += (size_t)m->maxBlockEdges * sizeof(R);
+            const size_t smem = (size_t)(hex ? fused::cpa_groups<R, 10>() : fused::cpa_groups<R, 12>()) * fused::kThreads * 16;
             const bool pdl = stage_pdl_enabled();
 #define MOKAB_STAGE_CPA(S2T, ST, FOLD, DER)                                                                                          \
     do {                                                                                                                            \
-        if (fx) {                                                                                                                   \
-            auto k_rk_stage_fx = fused::k_rk_stage<R, STAGE, S2T, ST, FOLD, DER, false, 3, true>;                                   \
-            if (pdl) launch_pdl(k_rk_stage_fx, grid, smem, s, A, m->S2, m->S);                                                      \
-            else k_rk_stage_fx<<<grid, fused::kThreads, smem, s>>>(A, m->S2, m->S);                                                 \
-        } else {                                                                                                                    \
-            auto k_rk_stage_cpa = fused::k_rk_stage<R, STAGE, S2T, ST, FOLD, DER, false, 3>;                                        \
-            if (pdl) launch_pdl(k_rk_stage_cpa, grid, smem, s, A, m->S2, m->S);                                                     \
-            else k_rk_stage_cpa<<<grid, fused::kThreads, smem, s>>>(A, m->S2, m->S);                                                \
-        }                                                                                                                           \
+        auto k_rk_stage_cpa = fused::k_rk_stage<R, STAGE, S2T, ST, FOLD, DER, false, 3>;                                            \
+        if (pdl) launch_pdl(k_rk_stage_cpa, grid, smem, s, A, m->S2, m->S);                                                         \
+        else k_rk_stage_cpa<<<grid, fused::kThreads, smem, s>>>(A, m->S2, m->S);                                                    \
     } while (0)
             if (hex) {
                 if (der && m->uniformF)      MOKAB_STAGE_CPA(10, 6, false, true);
@@ -1080,6 +1072,28 @@ static void halo_pack(mokab_state *st, int stage, void *buf, cudaStream_t stream
     }
     MOKAB_CUDA(cudaGetLastError());
     ctx->launches++;
+}
+
+// Halo copies of an (edge array, cell array) pair that is not a stage output -- the stage states and the adjoint variables
+// of the reverse sweep on a decomposed mesh -- through the packed exchange of mokab_decomp_setup, on the context's stream.
+template <class R>
+static void halo_exchange_arrays(mokab_state *st, R *u, R *h)
+{
+    mokab_state::Decomp &D = st->dec;
+    mokab_ctx *ctx = st->ctx; const mokab_mesh *m = st->mesh;
+    cudaStream_t s = ctx->stream;
+    const int ns = (int)m->haloSend.n, nr = (int)m->haloRecv.n;
+    if (ns) {
+        k_halo_pack<R><<<nblk(ns), 256, 0, s>>>(ns, (int)m->nC, m->haloSend.p, (const R *)h, (const R *)u, (R *)D.sendBuf.p);
+        MOKAB_CUDA(cudaGetLastError());
+        ctx->launches++;
+    }
+    comm::all_to_all(D.comm, s, D.sendBuf.p, D.recvBuf.p, D.scnt.data(), D.rcnt.data(), sizeof(R));
+    if (nr) {
+        k_halo_unpack<R><<<nblk(nr), 256, 0, s>>>(nr, (int)m->nC, m->haloRecv.p, (const R *)D.recvBuf.p, h, u);
+        MOKAB_CUDA(cudaGetLastError());
+        ctx->launches++;
+    }
 }
 
 // one RK4 step reading time level `p`, writing level 1-p (four launches)
@@ -1305,9 +1319,8 @@ static void do_reduce(mokab_state *st, int which, double *out)
 static void ensure_adjoint_mesh(mokab_mesh *m)
 {
     if (m->adj_ready) return;
-    MOKAB_REQUIRE(m->nCo == m->nC && m->nEo == m->nE, "adjoint: domain-decomposed meshes are not supported");
     mokab_ctx *ctx = m->ctx;
-    const int64_t nE = m->nE, nC = m->nC;
+    const int64_t nE = m->nE, nC = m->nC, nEo = m->nEo, nCo = m->nCo;
     const int S2 = m->S2, S = m->S;
     std::vector<int32_t> eoe((size_t)S2 * nE), eoc((size_t)S * nC), sgn((size_t)S * nC);
     std::vector<double> woe((size_t)S2 * nE), fE(nE);
@@ -1323,9 +1336,10 @@ static void ensure_adjoint_mesh(mokab_mesh *m)
     MOKAB_CUDA(cudaMemcpy(nEoC.data(), m->nEoC.p, nEoC.size(), cudaMemcpyDeviceToHost));
     MOKAB_CUDA(cudaMemcpy(ce.data(), m->ce.p, ce.size() * sizeof(int2), cudaMemcpyDeviceToHost));
     // (1) edgeSignOnCell follows HorzMesh.jl:292-311 (-1 on the cellsOnEdge[1] side); (2) every edge is listed by
-    // both of its cells (once by its only cell when masked)
+    // both of its cells (once by its only cell when masked).  On a decomposed mesh the rows of the owned cells are
+    // checked (halo cells carry none), and (2) for the edges between two owned cells.
     std::vector<uint8_t> seen(nE, 0);
-    for (int64_t c = 0; c < nC; ++c)
+    for (int64_t c = 0; c < nCo; ++c)
         for (int i = 0; i < nEoC[c]; ++i) {
             const int32_t e = eoc[(size_t)i * nC + c];
             const bool first = ce[e].x == c;
@@ -1334,28 +1348,37 @@ static void ensure_adjoint_mesh(mokab_mesh *m)
                           "adjoint: edgeSignOnCell does not follow the reference's orientation rule (HorzMesh.jl:292-311)");
             seen[e]++;
         }
-    for (int64_t e = 0; e < nE; ++e)
-        MOKAB_REQUIRE(seen[e] == (ce[e].x == ce[e].y ? 1 : 2), "adjoint: an edge is not listed by both of its cells");
+    for (int64_t e = 0; e < nEo; ++e)
+        if (ce[e].x < nCo && ce[e].y < nCo)
+            MOKAB_REQUIRE(seen[e] == (ce[e].x == ce[e].y ? 1 : 2), "adjoint: an edge is not listed by both of its cells");
+    // transpose: row x (an OWNED edge) lists every local edge e -- owned, or a halo copy, whose rows the mesh keeps on the
+    // host for exactly this -- whose Coriolis sum reads u[x]
+    const int HS2 = m->haloS2;
+    auto for_each_entry = [&](auto &&fn) {
+        for (int64_t e = 0; e < nEo; ++e)
+            for (int i = 0; i < nEoE[e]; ++i) {
+                const int32_t x = eoe[(size_t)i * nE + e];
+                if (x >= 0 && x < nEo) fn(e, x, woe[(size_t)i * nE + e]);
+            }
+        for (int64_t e = nEo; e < nE; ++e)
+            for (int i = 0; i < HS2; ++i) {
+                const int32_t x = m->hHaloEoe[(size_t)(e - nEo) * HS2 + i];
+                if (x >= 0 && x < nEo) fn(e, x, m->hHaloWoe[(size_t)(e - nEo) * HS2 + i]);
+            }
+    };
     std::vector<int32_t> cnt(nE, 0);
-    for (int64_t e = 0; e < nE; ++e)
-        for (int i = 0; i < nEoE[e]; ++i) {
-            const int32_t x = eoe[(size_t)i * nE + e];
-            if (x >= 0) cnt[x]++;
-        }
+    for_each_entry([&](int64_t, int32_t x, double) { cnt[x]++; });
     int S2T = 1;
-    for (int64_t e = 0; e < nE; ++e) S2T = std::max(S2T, (int)cnt[e]);
+    for (int64_t e = 0; e < nEo; ++e) S2T = std::max(S2T, (int)cnt[e]);
     MOKAB_REQUIRE(S2T <= 255, "adjoint: transposed Coriolis stencil too wide");
     std::vector<int32_t> eoeT((size_t)S2T * nE, 0);
     std::vector<double> wT((size_t)S2T * nE, 0.0);
     std::vector<uint8_t> nT(nE, 0);
-    for (int64_t e = 0; e < nE; ++e)
-        for (int i = 0; i < nEoE[e]; ++i) {
-            const int32_t x = eoe[(size_t)i * nE + e];
-            if (x < 0) continue;
-            const int j = nT[x]++;
-            eoeT[(size_t)j * nE + x] = (int32_t)e;
-            wT[(size_t)j * nE + x] = woe[(size_t)i * nE + e] * fE[x];
-        }
+    for_each_entry([&](int64_t e, int32_t x, double w) {
+        const int j = nT[x]++;
+        eoeT[(size_t)j * nE + x] = (int32_t)e;
+        wT[(size_t)j * nE + x] = w * fE[x];
+    });
     m->S2T = S2T;
     m->eoeT.upload(eoeT, ctx->stream);
     m->woeT.upload(wT, ctx->stream);
@@ -1394,6 +1417,10 @@ static void adjoint_step(mokab_state *st, int64_t k)
     const double a[4] = {dt / 2.0, dt / 2.0, dt, 0.0};
     const double b[4] = {dt / 6.0, dt / 3.0, dt / 3.0, dt / 6.0};
     const R *u0 = t->tapeU.p + (size_t)k * m->nE, *h0 = t->tapeH.p + (size_t)k * m->nC;
+    // Decomposed mesh: in gather form an owned entity's adjoint reads the adjoint variables of the SAME neighbours its forward
+    // stencil read, so every array a stage consumes needs plain halo copies -- the lists of the forward exchange serve as they
+    // are (no transposed, accumulating exchange): 3 exchanges of the recomputed stage states + 4 of the adjoint variables.
+    const bool decomposed = st->dec.ready;
     // forward recompute; the accumulator output of the forward kernel goes to a kbar buffer that is still free
     for (int s = 1; s <= 3; ++s) {
         fused::StageArgs<R> A = stage_args<R>(st, dt, st->cur, s);
@@ -1401,6 +1428,7 @@ static void adjoint_step(mokab_state *st, int64_t k)
         A.uOld = s == 1 ? u0 : t->yU[s - 2].p; A.hOld = s == 1 ? h0 : t->yH[s - 2].p;
         A.uOut = t->yU[s - 1].p; A.hOut = t->yH[s - 1].p;
         if (s == 1) launch_stage<R, 1>(ctx, m, A); else launch_stage<R, 2>(ctx, m, A);
+        if (decomposed) halo_exchange_arrays<R>(st, t->yU[s - 1].p, t->yH[s - 1].p);   // the next stage, and the Jacobians, read y_s on halo entities
     }
     adjoint::AdjArgs<R> B;
     B.nE = (int)m->nE; B.nC = (int)m->nC; B.nCown = (int)m->nCo; B.S2T = m->S2T; B.S = m->S;
@@ -1432,6 +1460,10 @@ static void adjoint_step(mokab_state *st, int64_t k)
 #undef MOKAB_ADJ_LAUNCH
         MOKAB_CUDA(cudaGetLastError());
         ctx->launches++;
+        if (decomposed) {
+            if (s > 1) { if (options().test_drop_dependency != 3) halo_exchange_arrays<R>(st, B.kuOut, B.kqOut); }   // kbar of the previous stage (3: test hook)
+            else halo_exchange_arrays<R>(st, B.accU, B.accH);            // lam: what the next reversed step starts from
+        }
     }
     t->lamCur = 1 - p;
 }
@@ -1478,6 +1510,7 @@ static void adjoint_run(mokab_state *st)
     t->taping = false;
     t->tapeKind = 0;
     LAUNCH(ctx, adjoint::k_fold_dssh<R>, nblk(m->nC), 256, m->nC, t->dSsh.p, t->lamH[t->lamCur].p);
+    if (st->dec.ready) halo_exchange_arrays<R>(st, t->lamU[t->lamCur].p, t->lamH[t->lamCur].p);   // the owners' seeds on the halo copies
     for (int64_t k = (int64_t)t->tapeDt.size() - 1; k >= 0; --k) adjoint_step<R>(st, k);
     t->tapeDt.clear();
 }
@@ -1498,6 +1531,10 @@ static void adjoint_run_fe(mokab_state *st)
     const int64_t nmax = std::max(m->nC, m->nE);
     LAUNCH(ctx, adjoint::k_fe_adj_begin, nblk(nmax), 256, m->nC, m->nE, (const double *)fm.invArea.p, (const double *)t->dSsh.p,
            (const double *)t->lamH[p].p, t->lamS[p].p, t->lamE[p].p, t->lamQ[p].p);
+    // Decomposed mesh: a reversed step gathers lamU (transposed Coriolis stencil, pressure term), lamE and q on the neighbours its
+    // forward stencil read: plain halo copies of those three arrays per step, over the lists of the forward exchange.
+    const bool decomposed = st->dec.ready;
+    if (decomposed) halo_exchange_arrays<double>(st, t->lamU[p].p, t->lamQ[p].p);
     adjoint::FeAdjArgs A;
     A.nE = (int)m->nE; A.nC = (int)m->nC; A.nCown = (int)m->nCo; A.S2T = m->S2T; A.S = m->S;
     A.ce = m->ce.p; A.eoeT = m->eoeT.p; A.eoc = m->eocF.p; A.nEoET = m->nEoET.p; A.nEoC = m->nEoC.p;
@@ -1515,6 +1552,10 @@ static void adjoint_run_fe(mokab_state *st)
         else adjoint::k_fe_step_adj<0, 0><<<m->fusedBlocks, adjoint::kThreads, 0, ctx->stream>>>(A);
         MOKAB_CUDA(cudaGetLastError());
         ctx->launches++;
+        if (decomposed) {
+            halo_exchange_arrays<double>(st, A.outU, A.qOut);
+            halo_exchange_arrays<double>(st, A.outE, A.outH);
+        }
         p = 1 - p;
     }
     t->lamCur = p;
@@ -2528,7 +2569,6 @@ int mokab_set_option(const char *name, int64_t value)
         else if (n == "stage_prefetch_distance") { MOKAB_REQUIRE(value >= 0 && value < (1 << 30), "set_option: bad stage_prefetch_distance"); o.stage_prefetch_distance = (int)value; }
         else if (n == "stage_wf_block_major") o.stage_wf_block_major = value ? 1 : 0;
         else if (n == "stage_auto") o.stage_auto = value ? 1 : 0;
-        else if (n == "stage_flux_smem") o.stage_flux_smem = value ? 1 : 0;
         else if (n == "stage_pdl") o.stage_pdl = value ? 1 : 0;
         else if (n == "decomp_serial_blocks") o.decomp_serial_blocks = (int)value;
         else if (n == "test_drop_dependency") o.test_drop_dependency = (int)value;
@@ -2548,7 +2588,6 @@ int mokab_get_option(const char *name, int64_t *value)
         else if (n == "stage_prefetch_distance") *value = o.stage_prefetch_distance;
         else if (n == "stage_wf_block_major") *value = o.stage_wf_block_major;
         else if (n == "stage_auto") *value = o.stage_auto;
-        else if (n == "stage_flux_smem") *value = o.stage_flux_smem;
         else if (n == "stage_pdl") *value = o.stage_pdl;
         else if (n == "decomp_serial_blocks") *value = o.decomp_serial_blocks;
         else throw Error("get_option: unknown option '" + n + "'");

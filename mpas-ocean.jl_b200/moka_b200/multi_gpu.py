@@ -237,6 +237,44 @@ class DecomposedModel:
             self.validate_graph(dt)
         self._advance(dt, nsteps, fe)
 
+    def reverse_run_loop(self, dt: float, nsteps: int, seed: str | None = "ssh2", stepper=None) -> float:
+        """`autodiff(Reverse, ocn_run_loop, ...)` (test_Enzyme_end2end.jl:78-96) on the decomposed mesh: `nsteps` steps of
+        `stepper` (api.RungeKutta4, the default, or api.ForwardEuler, the stepper the reference differentiates) recording
+        every rank's part of the trajectory, then the reverse sweep -- the hand-written gather-form adjoints with plain halo
+        copies of everything a reversed stage / step consumes (recomputed stage states, adjoint variables), over the lists
+        of the forward exchange.  Returns J = sum ssh^2 over the whole mesh (`seed=None`: the caller has set the adjoint of
+        the final state with `prog.dev.set(L.D_*, ...)`); `gradient()` then holds dJ/d(initial state)."""
+        if stepper not in (None, api.RungeKutta4, api.ForwardEuler):
+            raise api.MokaError("DecomposedModel.reverse_run_loop: unknown stepper")
+        fe = stepper is api.ForwardEuler
+        if self._stepped and fe != self._fe:
+            raise api.MokaError("DecomposedModel.reverse_run_loop: one stepper per model -- build another DecomposedModel to change it")
+        if self.use_graph and not fe and nsteps > 0 and (not self._validated or self._graph_dt != dt):
+            self.validate_graph(dt)                               # (before the tape starts: validation steps the model)
+        lib = L.lib()
+        L.check(lib.mokab_tape_begin(self.handle, int(nsteps)))
+        self._stepped = self._stepped or nsteps > 0
+        self._fe = fe
+        self._advance(dt, nsteps, fe)
+        J = float("nan")
+        if seed is not None:
+            if seed != "ssh2":
+                raise api.MokaError("DecomposedModel.reverse_run_loop: unknown seed")
+            J = self.reduce("ssh2")
+            L.check(lib.mokab_adjoint_seed(self.handle, L.SUM_SSH2))
+        L.check((lib.mokab_adjoint_forward_euler if fe else lib.mokab_adjoint_rk4)(self.handle))
+        return J
+
+    def gradient(self):
+        """(d_normalVelocity on the owned edges, d_layerThickness on the owned cells) after `reverse_run_loop`."""
+        gu = np.asarray(self.prog.dev.get(L.D_NORMAL_VELOCITY), np.float64)[:self.loc["nEdgesOwned"]]
+        gh = np.asarray(self.prog.dev.get(L.D_LAYER_THICKNESS), np.float64)[:self.loc["nCellsOwned"]]
+        return gu, gh
+
+    def gradient_ssh(self):
+        """d_ssh on the owned cells: ForwardEuler reads the initial ssh array as an input of its own (first step's pressure gradient)."""
+        return np.asarray(self.prog.dev.get(L.D_SSH), np.float64)[:self.loc["nCellsOwned"]]
+
     def refresh_ssh(self) -> None:
         """ssh = layerThickness - restingThicknessSum (the decomposed RK4 entry point leaves it refreshed already)."""
 
@@ -528,7 +566,7 @@ def bench_main(args, rank, world, local):
                        "variant": {"lib": os.environ.get("MOKAB_LIB", "libmoka_b200.so"),
                                    "stage_tma": L.get_option("stage_tma"), "stage_prefetch": L.get_option("stage_prefetch"),
                                    "stage_prefetch_distance": L.get_option("stage_prefetch_distance"),
-                                   "stage_flux_smem": L.get_option("stage_flux_smem"), "stage_pdl": L.get_option("stage_pdl")}},
+                                   "stage_auto": L.get_option("stage_auto"), "stage_pdl": L.get_option("stage_pdl")}},
             "clocks": clocks,
             "e2e": {"value": nC_glob / e2e_s, "unit": "cell-steps/s", "h2d_bytes_per_step": int(cnt[0] * item),
                     "d2h_bytes_per_step": int(cnt[1] * item), "ms_per_step": e2e_s * 1e3, "steps": Ke,

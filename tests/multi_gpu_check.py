@@ -58,6 +58,29 @@ def main():
             e = (rel(gs, om.ssh[1]), rel(gu, om.normalVelocity[1]), rel(gh, om.layerThickness[1]))
             m0 = float(np.sum(m["areaCell"] * om.layerThickness[1]))
             errs.append(((overlap, graph, halo, stepper), e, abs(mass - m0) / m0, status))
+    # reverse mode on the decomposed mesh: J = sum ssh^2 after 6 steps and dJ/d(initial state) against the adjoint oracle
+    for halo, graph, stepper in (("nccl", True, "RungeKutta4"), ("p2p", False, "RungeKutta4"), ("nccl", True, "ForwardEuler")):
+        if os.environ.get("MOKAB_CHECK_HALO") and halo not in os.environ["MOKAB_CHECK_HALO"].split(","):
+            continue
+        model = multi_gpu.DecomposedModel(loc, multi_gpu.local_state(loc, *state), backend, local, graph=graph, halo=halo, runtime=rt, comm=comm)
+        J = model.reverse_run_loop(dt, 6, stepper=getattr(mb, stepper))
+        model.finish()
+        gu_o, gh_o = model.gradient()
+        no, ne = loc["nCellsOwned"], loc["nEdgesOwned"]
+        gu, gh = np.zeros(m["nEdges"]), np.zeros(m["nCells"])
+        gu[loc["edgesGlobal"][:ne]], gh[loc["cellsGlobal"][:no]] = gu_o, gh_o
+        gu, gh = comm.allreduce(gu), comm.allreduce(gh)        # (owned parts are disjoint: the sum assembles the global arrays)
+        model.close()
+        del model
+        if rank == 0:
+            import adjoint_oracle as AO
+            OC.sign_index_fields(m)
+            if stepper == "ForwardEuler":
+                Jo, ou, oh = AO.gradient_sum_ssh2_fe(m, state[0], state[1], state[2], dt, 6)[:3]
+            else:
+                Jo, ou, oh = AO.gradient_sum_ssh2(m, state[1], state[2], dt, 6)
+            rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))
+            errs.append((("reverse mode", graph, halo, stepper), (abs(J - Jo) / Jo, rel(gu, ou), rel(gh, oh)), 0.0, "n/a"))
     if rank == 0:
         print(errs)
         ok = all(max(e) <= 1e-12 and dm <= 1e-13 for _, e, dm, _ in errs)

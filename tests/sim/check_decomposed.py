@@ -97,6 +97,45 @@ def run(kind, nx, nparts, step_calls, overlap, graph, policy, seed, dtype=np.flo
     return ok, outs[0][1]
 
 
+def run_adjoint(kind, nx, nparts, nsteps, policy, seed, halo, graph, dtype=np.float64, stepper="RungeKutta4"):
+    """Reverse mode on the decomposed mesh (DecomposedModel.reverse_run_loop): J = sum ssh^2 after `nsteps` steps and
+    dJ/d(u0, h0) (ForwardEuler: and dJ/d ssh0), gathered from the ranks, against the scatter-form adjoint oracle on the
+    undecomposed mesh."""
+    import adjoint_oracle as AO
+    simcuda.set_policy(policy, seed)
+    m, mo, state, dt = case(kind, nx)
+    locs = partition.decompose(m, nparts)
+    fe = stepper == "ForwardEuler"
+
+    def body(r, comm):
+        model = multi_gpu.DecomposedModel(locs[r], multi_gpu.local_state(locs[r], *state), mb.B200(0), 0, dtype=dtype, overlap=True,
+                                          graph=graph, runtime=simcuda.SimRuntime(comm, r), halo=halo)
+        J = model.reverse_run_loop(dt, nsteps, stepper=mb.ForwardEuler if fe else mb.RungeKutta4)
+        model.finish()
+        gu, gh = model.gradient()
+        gs = model.gradient_ssh()
+        model.close()
+        return J, np.array(gu), np.array(gh), np.array(gs)
+
+    outs = simcuda.run_ranks(nparts, body)
+    gu, gh, gs = np.full(m["nEdges"], np.nan), np.full(m["nCells"], np.nan), np.full(m["nCells"], np.nan)
+    for loc, (_, u_, h_, s_) in zip(locs, outs):
+        gu[loc["edgesGlobal"][:loc["nEdgesOwned"]]] = u_
+        gh[loc["cellsGlobal"][:loc["nCellsOwned"]]] = h_
+        gs[loc["cellsGlobal"][:loc["nCellsOwned"]]] = s_
+    if fe:
+        Jo, ou, oh, os_, _ = AO.gradient_sum_ssh2_fe(mo, state[0], state[1], state[2], dt, nsteps)
+    else:
+        Jo, ou, oh = AO.gradient_sum_ssh2(mo, state[1], state[2], dt, nsteps)
+    tol = 1e-12 if dtype == np.float64 else 2e-4
+    eu = np.linalg.norm(gu - ou) / max(np.linalg.norm(ou), 1e-300)
+    eh = np.linalg.norm(gh - oh) / max(np.linalg.norm(oh), 1e-300)
+    ok = all(abs(o[0] - Jo) <= (1e-12 if dtype == np.float64 else 1e-5) * Jo for o in outs) and eu <= tol and eh <= tol
+    if fe:
+        ok = ok and np.linalg.norm(gs - os_) / max(np.linalg.norm(os_), 1e-300) <= tol
+    return ok, (eu, eh)
+
+
 def run_e2e(kind, nx, nparts, iters, policy, seed, halo):
     """bench.py's end-to-end leg at N > 1 (multi_gpu.bench_main.e2e_steps): every iteration uploads this rank's (u, h) from
     page-locked memory through the pipelined transfers, takes ONE step, refreshes ssh and downloads it -- copy streams, the
@@ -162,6 +201,10 @@ def run_mutations():
             ok = all(got.values()) if drop is None else not got["lazy"]
             bad += not ok
             print(f"schedule without {drop or 'nothing'}: {got} {'as expected' if ok else 'UNEXPECTED'}", flush=True)
+        L.set_option("test_drop_dependency", 3)                   # the reverse sweep without the halo copies of kbar
+        ok_adj, err = run_adjoint("igw", 48, 4, 3, "fifo", 1, "nccl", False)
+        bad += ok_adj
+        print(f"reverse sweep without the halo copies of kbar: rel-L2 {err[0]:.1e} / {err[1]:.1e} {'as expected' if not ok_adj else 'UNEXPECTED (passed)'}", flush=True)
     finally:
         L.set_option("test_drop_dependency", 0)
     print("SIM_MUTATIONS_DETECTED" if bad == 0 else "SIM_MUTATIONS_MISSED", flush=True)
@@ -290,6 +333,18 @@ def main():
             ok = run_e2e("igw", 48, 4, 5, policy, 3, halo)
             bad += not ok
             print(f"igw48 ranks=4 end-to-end leg (upload / step / download x5) {halo} {policy}: {'OK' if ok else 'MISMATCH'} {time.time() - t0:.1f}s", flush=True)
+    # reverse mode on decomposed meshes (both steppers; the exchange of the sweep is always the packed one)
+    for kind, nx, P, nsteps, halo, graph, stepper in [("igw", 48, 4, 5, "nccl", True, "RungeKutta4"), ("kelvin", 48, 4, 4, "p2p", False, "RungeKutta4"),
+                                                      ("igw", 96, 8, 3, "p2p_fused", True, "RungeKutta4"), ("igw", 48, 4, 6, "nccl", True, "ForwardEuler"),
+                                                      ("kelvin", 48, 3, 5, "nccl", False, "ForwardEuler")] + \
+            ([("voronoi", 24, 4, 4, "nccl", False, "RungeKutta4"), ("igw", 32, 2, 0, "nccl", True, "RungeKutta4"),
+              ("voronoi", 24, 4, 4, "nccl", True, "ForwardEuler")] if args.cases != "suite" else []):
+        for policy in args.policies.split(","):
+            t0 = time.time()
+            ok, (eu, eh) = run_adjoint(kind, nx, P, nsteps, policy, 4, halo, graph, stepper=stepper)
+            bad += not ok
+            print(f"{kind}{nx} ranks={P} reverse mode, {nsteps} {stepper} steps, {halo} {policy} {'graph' if graph else 'stream'}: "
+                  f"{'OK' if ok else 'MISMATCH'} (rel-L2 {eu:.1e} / {eh:.1e} against the adjoint oracle) {time.time() - t0:.1f}s", flush=True)
     for halo in (args.halo.split(",")[:1] if args.cases == "suite" else args.halo.split(",")):
         t0 = time.time()
         ok = run_driver(3, args.policies.split(",")[0], halo)

@@ -145,8 +145,7 @@ static inline bool is_coop_name(const char *kernel)
 {
     return __builtin_strstr(kernel, "reduce::k_") != nullptr || __builtin_strstr(kernel, "k_halo_push") != nullptr ||
            (__builtin_strstr(kernel, "k_rk_stage") != nullptr && __builtin_strstr(kernel, ", true>") != nullptr) ||   // the PUSH variant
-           __builtin_strstr(kernel, "k_rk_stage_tma") != nullptr ||                                                  // the TMA variant
-           __builtin_strstr(kernel, "k_rk_stage_fx") != nullptr;                                                     // the shared-memory flux variant
+           __builtin_strstr(kernel, "k_rk_stage_tma") != nullptr;                                                    // the TMA variant
 }
 // a device-side wait on memory that another stream (or rank) writes: retried by the scheduler until `ready` returns true
 void enqueue_try(cudaStream_t s, const char *name, std::function<bool()> ready);

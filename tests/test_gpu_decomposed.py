@@ -359,3 +359,32 @@ def test_in_library_decomposed_graphs_on_the_very_first_call(backend):
     om = OC.OracleModel(m, *state)
     om.run_loop(dt, 5, "RungeKutta4")
     assert np.array_equal(gu, om.normalVelocity[1]) and np.array_equal(gs, om.ssh[1])
+
+
+@pytest.mark.parametrize("stepper,graph", [("RungeKutta4", True), ("RungeKutta4", False), ("ForwardEuler", True)])
+def test_in_library_decomposed_reverse_mode_with_one_rank(backend, stepper, graph):
+    """DecomposedModel.reverse_run_loop -- the tape recorded by mokab_timestep_*_decomposed, then mokab_adjoint_* with the halo
+    copies of the reverse sweep (csrc/moka_b200.cu: halo_exchange_arrays) -- on a communicator of one rank: J and dJ/d(initial
+    state) against the scatter-form adjoint oracle.  With neighbours: tests/sim/check_decomposed.py (2 - 8 emulated ranks, every
+    halo path) and tests/multi_gpu_check.py under torchrun."""
+    import adjoint_oracle as AO
+    m = hex_mesh(32, with_dual=False)
+    ssh, u, h = mb.inertialGravityWave(m).initial_state()
+    dt = mb.cfl_dt(m["dc"])
+    loc = partition.decompose(m, 1)[0]
+    model = multi_gpu.DecomposedModel(loc, multi_gpu.local_state(loc, ssh, u, h), backend, 0, graph=graph, runtime=_SoloRuntime())
+    fe = stepper == "ForwardEuler"
+    J = model.reverse_run_loop(dt, 5, stepper=getattr(mb, stepper))
+    model.finish()
+    gu, gh = (np.array(a) for a in model.gradient())
+    gs = np.array(model.gradient_ssh())
+    model.close()
+    inv_e, inv_c = np.argsort(loc["edgesGlobal"]), np.argsort(loc["cellsGlobal"])
+    gu, gh, gs = gu[inv_e], gh[inv_c], gs[inv_c]
+    if fe:
+        Jo, ou, oh, os_, _ = AO.gradient_sum_ssh2_fe(m, ssh, u, h, dt, 5)
+        assert rel_l2(gs, os_) <= 1e-12
+    else:
+        Jo, ou, oh = AO.gradient_sum_ssh2(m, u, h, dt, 5)
+    assert abs(J - Jo) <= 1e-12 * Jo
+    assert rel_l2(gu, ou) <= 1e-12 and rel_l2(gh, oh) <= 1e-12

@@ -6,7 +6,7 @@ default variant's (all variants keep the operation order).  Prints one JSON line
 precision ({"best": ...}) -- tools/gpu_round2.sh feeds that to bench.py through the environment.
 
   python tools/stage_sweep.py [--workload igw2048] [--steps 40] [--warmup 5] [--dtypes f64,f32] [--explicit-eoe]
-                              [--variants prefetch:distance:tma[:flux_smem[:pdl[:auto]]],...]
+                              [--variants prefetch:distance:tma[:0[:pdl[:auto]]],...]
 Build variants (block size, resident blocks) are separate libraries: select with MOKAB_LIB and run this once per library.
 """
 from __future__ import annotations
@@ -44,7 +44,7 @@ def main():
     backend = mb.B200(0)
     peak, _ = bench.measured_peak_gbs()
     if args.variants:
-        variants = [tuple(int(x) for x in v.split(":")) for v in args.variants.split(",")]     # prefetch:distance:tma[:flux_smem[:pdl[:auto]]]
+        variants = [tuple(int(x) for x in v.split(":")) for v in args.variants.split(",")]     # prefetch:distance:tma[:0[:pdl[:auto]]]
     else:
         variants = [(0, 0, 0), (1, 0, 0), (2, 0, 0), (3, 0, 0), (2, 888, 0), (3, 888, 0), (2, 1184, 0), (3, 1184, 0),
                     (0, 0, 1), (1, 0, 1), (0, 0, 2), (1, 0, 2), (3, 0, 2)]
@@ -58,13 +58,12 @@ def main():
             ref = None
             for var in variants:
                 pf, dist, tma = var[:3]
-                fx, pdl = (var[3] if len(var) > 3 else 0), (var[4] if len(var) > 4 else 0)
+                pdl = var[4] if len(var) > 4 else 0              # (field 3 was the shared-memory flux experiment of r02h: removed, -9 %)
                 auto = var[5] if len(var) > 5 else 0            # (explicit variants are forced; ...:1 = let the library choose per launch)
                 L.set_option("stage_auto", auto)
                 L.set_option("stage_prefetch", pf)
                 L.set_option("stage_prefetch_distance", dist)
                 L.set_option("stage_tma", tma)
-                L.set_option("stage_flux_smem", fx)
                 L.set_option("stage_pdl", pdl)
                 prog = mb.PrognosticVars(ssh.astype(npdt), u.astype(npdt), h.astype(npdt), 2, mesh)
                 try:
@@ -78,14 +77,14 @@ def main():
                     ms = min(times)
                     out = (prog.ssh, prog.normalVelocity)
                 except mb.MokaError as ex:
-                    print(json.dumps({"dtype": dtype, "prefetch": pf, "distance": dist, "tma": tma, "flux_smem": fx, "pdl": pdl, "auto": auto, "error": str(ex)}), flush=True)
+                    print(json.dumps({"dtype": dtype, "prefetch": pf, "distance": dist, "tma": tma, "pdl": pdl, "auto": auto, "error": str(ex)}), flush=True)
                     continue
                 if ref is None:
                     ref = out
                 same = bool(np.array_equal(out[0], ref[0]) and np.array_equal(out[1], ref[1]))
                 value = nC * args.steps / (ms * 1e-3)
                 frac = per_cell_step * value / 1e9 / peak
-                rec = {"dtype": dtype, "prefetch": pf, "distance": dist, "tma": tma, "flux_smem": fx, "pdl": pdl, "auto": auto, "ms_per_step": ms / args.steps,
+                rec = {"dtype": dtype, "prefetch": pf, "distance": dist, "tma": tma, "pdl": pdl, "auto": auto, "ms_per_step": ms / args.steps,
                     "cell_steps_per_s": value, "roofline_frac": frac, "bit_identical_to_default": same,
                     "workload": args.workload, "lib": os.environ.get("MOKAB_LIB", "libmoka_b200.so"),
                     "explicit_eoe": args.explicit_eoe, "edge_order": order}
