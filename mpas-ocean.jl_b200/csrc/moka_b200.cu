@@ -728,8 +728,9 @@ struct Options {
                                   // `stage_prefetch_distance` blocks after it
     int stage_prefetch_distance = 0;   // MOKAB_STAGE_PREFETCH_DISTANCE: 0 = one wave of resident blocks (SMs x blocks per SM)
     int stage_wf_block_major = 0; // MOKAB_STAGE_WF_BLOCK_MAJOR: the plain stage kernel reads the Coriolis weights from the block-major copy
-    int stage_auto = 1;           // MOKAB_STAGE_AUTO: with stage_tma = 3, a launch takes the plain kernel (one resident block per SM fewer, no
-                                  // prefetch) when the wave-quantisation model says its last round of blocks costs less (prefer_plain_variant)
+    int stage_auto = 1;           // MOKAB_STAGE_AUTO: with stage_tma = 3, a Float64 launch of a few rounds of blocks takes the plain kernel (one
+                                  // resident block per SM fewer, no prefetch): prefer_plain_variant
+    int stage_auto_hi = 80;       // MOKAB_STAGE_AUTO_HI: ... up to this many blocks per SM (80 x 148 = 11 840 blocks)
     int stage_pdl = 0;            // MOKAB_STAGE_PDL: stage launches carry the programmatic-stream-serialization attribute (kernels_fused.cuh: pdl_*)
     int decomp_serial_blocks = 0;  // MOKAB_DECOMP_SERIAL_BLOCKS: with MOKAB_HALO_P2P_FUSED, a rank whose part has fewer blocks than this runs ONE
                                   // launch per stage (all blocks, exchange folded in) instead of the two-stream overlap schedule.
@@ -751,6 +752,7 @@ struct Options {
         stage_prefetch_distance = std::max(0, geti("MOKAB_STAGE_PREFETCH_DISTANCE", 0));
         stage_wf_block_major = geti("MOKAB_STAGE_WF_BLOCK_MAJOR", 0) ? 1 : 0;
         stage_auto = geti("MOKAB_STAGE_AUTO", 1) ? 1 : 0;
+        stage_auto_hi = std::max(0, geti("MOKAB_STAGE_AUTO_HI", 80));
         stage_pdl = geti("MOKAB_STAGE_PDL", 0) ? 1 : 0;
         decomp_serial_blocks = std::max(0, geti("MOKAB_DECOMP_SERIAL_BLOCKS", 0));
     }
@@ -841,20 +843,19 @@ static bool stage_pdl_enabled()
 #endif
 }
 
-// Which of the two tuned stage kernels a launch of `grid` blocks takes (option "stage_auto").  Blocks of one launch start
-// together and last about equally long, so a launch runs in ROUNDS of (SMs x resident blocks) and pays for a whole last round
-// however few blocks are left in it; a round lasts in proportion to the resident blocks r.  The cp.async-weights kernel
-// (r = 5 in Float64, 6 in Float32) moves ~2-3 % more bytes per second than the plain one (r = 4 / 5) once a launch has tens of
-// rounds, but on a small grid its longer rounds lose: measured r02h on 512 x 512 (1 024 blocks) 2.38 vs 2.97 G cell-steps/s
-// -- the model says 2 x 5 against 2 x 4 -- and on the 1 024 x 1 024 channel (4 096 blocks) 2.48 vs 2.65 G (6 x 5 against
-// 7 x 4); the parts of an 8-GPU run are grids of that size.
-static bool prefer_plain_variant(int grid, int num_sms, int r_cpa, int r_plain, double eff_cpa)
+// Which of the two tuned stage kernels a launch of `grid` blocks takes (option "stage_auto", Float64).  Blocks of one launch
+// start together and last about equally long, so a launch runs in ROUNDS of (SMs x resident blocks) and pays for a whole last
+// round; a round lasts longer the more blocks are resident.  The cp.async-weights kernel (5 resident blocks) moves 1-2 % more
+// bytes per second than the plain one (4) once a launch has tens of rounds, and its blocks are the quicker ones when a launch
+// is a single partial round; in between the plain kernel wins by a wide margin.  Measured (cp.async vs plain, G cell-steps/s):
+//   452 + 60 blocks per GPU (512 x 512 over 2 GPUs, r02j)   2.36 vs 2.19
+//   1 024 blocks (512 x 512, r02i)                           2.36 vs 2.96
+//   4 096 blocks (1024 x 1024 channel, r02i)                 2.48 vs 2.66
+//   16 384 blocks (2048 x 2048, r02i; sustained)             2.85 vs 2.87        65 536 blocks (4096 x 4096)   2.92 vs 2.91
+// Rule: the plain kernel for launches of more than one of its rounds and at most `stage_auto_hi` blocks per SM.
+static bool prefer_plain_variant(int grid, int num_sms, int r_plain)
 {
-    auto cost = [&](int r, double eff) {
-        const int per_round = num_sms * r;
-        return (double)((grid + per_round - 1) / per_round) * r / eff;
-    };
-    return cost(r_plain, 1.0) < cost(r_cpa, eff_cpa);
+    return grid > num_sms * r_plain && grid <= num_sms * options().stage_auto_hi;
 }
 
 // ---- fused RK4 ------------------------------------------------------------------------------------------------
@@ -887,12 +888,11 @@ static void launch_stage(mokab_ctx *ctx, const mokab_mesh *m, fused::StageArgs<R
         if (fm.wfB.n) { A.wfB = fm.wfB.p; A.wfBOff = fm.wfBOff.p; }
     }
     bool use_cpa = (hex || hept) && stage_tma_mode() == 3;
-    // (Float64 only: in Float32 the model does not predict the measurements -- r02i: 1 024 blocks 4.14 (cp.async) vs 3.77 G
-    //  (plain), 4 096 blocks 3.65 vs 3.77, 16 384 blocks 4.27 vs 4.21 -- and the cp.async kernel wins or ties on balance)
+    // (Float64 only: in Float32 the cp.async kernel wins or ties on balance -- r02i: 1 024 blocks 4.14 (cp.async) vs 3.77 G
+    //  (plain), 4 096 blocks 3.65 vs 3.77, 16 384 blocks 4.27 vs 4.21)
     if (use_cpa && options().stage_auto && sizeof(R) == 8) {
-        const int rc = der ? fused::stage_blocks<R, true, 3>() : fused::stage_blocks<R, false, 3>();
         const int rp = der ? fused::stage_blocks<R, true, 0>() : fused::stage_blocks<R, false, 0>();
-        if (prefer_plain_variant(grid, ctx->num_sms, rc, rp, 1.02)) {
+        if (prefer_plain_variant(grid, ctx->num_sms, rp)) {
             use_cpa = false;
             A.pf = 0;
         }
@@ -2569,6 +2569,7 @@ int mokab_set_option(const char *name, int64_t value)
         else if (n == "stage_prefetch_distance") { MOKAB_REQUIRE(value >= 0 && value < (1 << 30), "set_option: bad stage_prefetch_distance"); o.stage_prefetch_distance = (int)value; }
         else if (n == "stage_wf_block_major") o.stage_wf_block_major = value ? 1 : 0;
         else if (n == "stage_auto") o.stage_auto = value ? 1 : 0;
+        else if (n == "stage_auto_hi") { MOKAB_REQUIRE(value >= 0 && value < (1 << 20), "set_option: bad stage_auto_hi"); o.stage_auto_hi = (int)value; }
         else if (n == "stage_pdl") o.stage_pdl = value ? 1 : 0;
         else if (n == "decomp_serial_blocks") o.decomp_serial_blocks = (int)value;
         else if (n == "test_drop_dependency") o.test_drop_dependency = (int)value;
@@ -2588,6 +2589,7 @@ int mokab_get_option(const char *name, int64_t *value)
         else if (n == "stage_prefetch_distance") *value = o.stage_prefetch_distance;
         else if (n == "stage_wf_block_major") *value = o.stage_wf_block_major;
         else if (n == "stage_auto") *value = o.stage_auto;
+        else if (n == "stage_auto_hi") *value = o.stage_auto_hi;
         else if (n == "stage_pdl") *value = o.stage_pdl;
         else if (n == "decomp_serial_blocks") *value = o.decomp_serial_blocks;
         else throw Error("get_option: unknown option '" + n + "'");
