@@ -379,6 +379,13 @@ int  mokab_decomp_close(mokab_state *state);
  * MOKAB_STAGE_TMA, MOKAB_STAGE_AUTO, MOKAB_STAGE_PDL). */
 int  mokab_set_option(const char *name, int64_t value);
 int  mokab_get_option(const char *name, int64_t *value);
+/* Stage timeline (diagnostic; TRACE builds only -- `make -C mpas-ocean.jl_b200 libmoka_b200_trace.so`; the default build returns
+ * an error).  Between mokab_trace_begin(ctx, capacity) and mokab_trace_read every block of the stage and halo kernels appends a
+ * 48-byte record {u32 kind, block, grid, pad; u64 globaltimer at entry, at exit, after the wait for the peers} to a ring of
+ * `capacity` records; kind = RK stage | part << 4 for stage launches, 100 / 101 = halo push / wait kernels, 110 / 111 = pack /
+ * unpack.  `count` returns how many records were written in all.  tools/trace_stages.py prints the timeline of a step. */
+int  mokab_trace_begin(mokab_ctx *ctx, int64_t capacity);
+int  mokab_trace_read(mokab_ctx *ctx, void *records, int64_t max_records, int64_t *count);
 /* number of interior / boundary blocks of the fused kernel (diagnostic) */
 int  mokab_mesh_block_counts(const mokab_mesh *mesh, int64_t *interior, int64_t *boundary);
 /* number of fused-kernel blocks, and how many of them rebuild edgesOnEdge from edgesOnCell (diagnostic) */

@@ -112,6 +112,39 @@ struct mokab_ctx {
 
 namespace mokab {
 
+// ---- stage timeline (TRACE builds only: libmoka_b200_trace.so, -DMOKAB_TRACE) ---------------------------------------------
+// Where does the stage time of a decomposed run go?  nsys is not in the image and ncu serialises kernels, so the trace build
+// lets every block of the stage / halo kernels append one record -- which kernel, which block, %globaltimer at entry, after
+// the gate (kernels that wait for peers) and at exit -- to a ring in device memory; tools/trace_stages.py turns the records
+// of one step into a timeline per launch.  Nothing of this is compiled into libmoka_b200.so.
+#ifdef MOKAB_TRACE
+struct TraceRec { unsigned int kind, block, grid, pad; unsigned long long t0, t1, t2; };
+__device__ TraceRec *g_trace_buf;
+__device__ unsigned long long g_trace_count;
+__device__ unsigned int g_trace_cap;
+__device__ __forceinline__ unsigned long long trace_now()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void trace_emit(unsigned int kind, unsigned long long t0, unsigned long long t2)
+{
+    if (!g_trace_buf) return;
+    const unsigned long long i = atomicAdd(&g_trace_count, 1ull) % g_trace_cap;
+    TraceRec r;
+    r.kind = kind; r.block = blockIdx.x; r.grid = gridDim.x; r.pad = 0; r.t0 = t0; r.t1 = trace_now(); r.t2 = t2;
+    g_trace_buf[i] = r;
+}
+#define MOKAB_TRACE_BEGIN() unsigned long long tr0_ = 0, tr2_ = 0; if (threadIdx.x == 0) tr0_ = trace_now()
+#define MOKAB_TRACE_MARK() do { if (threadIdx.x == 0) tr2_ = trace_now(); } while (0)
+#define MOKAB_TRACE_END(kind) do { __syncthreads(); if (threadIdx.x == 0) trace_emit((kind), tr0_, tr2_); } while (0)
+#else
+#define MOKAB_TRACE_BEGIN() do { } while (0)
+#define MOKAB_TRACE_MARK() do { } while (0)
+#define MOKAB_TRACE_END(kind) do { } while (0)
+#endif
+
 // ---- device helpers -----------------------------------------------------------------------------
 // Streaming (read-once) loads: keep them out of L1 so the gathered state stays resident there.
 #ifdef MOKAB_SIM   // host build of the simulation tests (tests/sim): a plain load

@@ -107,6 +107,9 @@ struct StageArgs {
     const R *wfI;              // TMA = 3: the weights again, slot-INTERLEAVED -- 16 bytes per edge and slot group (k_build_wf_interleaved)
     const R *wfB;              // TMA = 2: the weights again, BLOCK-major -- block b's S2 rows back to back, each padded to 16 bytes,
     const long long *wfBOff;   //          starting at element wfBOff[b] (16-byte aligned): one contiguous run, one bulk copy per block
+#ifdef MOKAB_TRACE
+    int traceKind;             // TRACE builds: stage | part << 4 (common.cuh)
+#endif
 };
 
 // STAGE: 1 = first, 2 = middle (2 and 3), 4 = last.  S2/S: compile-time maxEdges2/maxEdges (0 = runtime).
@@ -222,6 +225,7 @@ __global__ void __launch_bounds__(kThreads, (stage_blocks<R, DER, TMA>()))
 k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
 {
     pdl_launch_dependents();
+    MOKAB_TRACE_BEGIN();
     const int S2 = S2T ? S2T : S2rt;
     const int S = ST ? ST : Srt;
     const int nE = A.nE, nC = A.nC;
@@ -305,6 +309,7 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
         }
 #endif
         __syncthreads();
+        MOKAB_TRACE_MARK();
     }
 
     constexpr bool kDer = DER && ST != 0 && S2T != 0;
@@ -575,6 +580,9 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
             }
         }
     }
+#ifdef MOKAB_TRACE
+    MOKAB_TRACE_END((unsigned)A.traceKind);
+#endif
 }
 
 // ---- fused RungeKutta4 stage for MULTI-LEVEL states (nVertLevels = K > 1) ------------------------------------------------
@@ -850,20 +858,26 @@ template <class R>
 __global__ void __launch_bounds__(256)
 k_halo_pack(int n, int nC, const int32_t *__restrict__ idx, const R *__restrict__ h, const R *__restrict__ u, R *__restrict__ buf)
 {
+    MOKAB_TRACE_BEGIN();
     const int k = blockIdx.x * 256 + threadIdx.x;
-    if (k >= n) return;
-    const int i = idx[k];
-    buf[k] = i < nC ? h[i] : u[i - nC];
+    if (k < n) {
+        const int i = idx[k];
+        buf[k] = i < nC ? h[i] : u[i - nC];
+    }
+    MOKAB_TRACE_END(110u);
 }
 template <class R>
 __global__ void __launch_bounds__(256)
 k_halo_unpack(int n, int nC, const int32_t *__restrict__ idx, const R *__restrict__ buf, R *__restrict__ h, R *__restrict__ u)
 {
+    MOKAB_TRACE_BEGIN();
     const int k = blockIdx.x * 256 + threadIdx.x;
-    if (k >= n) return;
-    const int i = idx[k];
-    if (i < nC) h[i] = buf[k];
-    else u[i - nC] = buf[k];
+    if (k < n) {
+        const int i = idx[k];
+        if (i < nC) h[i] = buf[k];
+        else u[i - nC] = buf[k];
+    }
+    MOKAB_TRACE_END(111u);
 }
 
 // ---- deterministic reductions (replace sumArray, reference run_loop.jl:47-51) --------------------------

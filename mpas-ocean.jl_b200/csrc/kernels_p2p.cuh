@@ -59,6 +59,7 @@ struct PushArgs {
 template <class R>
 __global__ void __launch_bounds__(256) k_halo_push(const PushArgs<R> A)
 {
+    MOKAB_TRACE_BEGIN();
     const int k = blockIdx.x * 256 + threadIdx.x;
     if (k < A.n) {
         const int s = A.src[k];
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(256) k_halo_push(const PushArgs<R> A)
             for (int p = 0; p < A.nrecv; ++p) add_system(A.arrival[p], 1ull);
         }
     }
+    MOKAB_TRACE_END(100u);
 }
 
 // a rank with receivers but nothing to send them this stage still has to tick their counters
@@ -97,20 +99,23 @@ __global__ void __launch_bounds__(kMaxPeers)
 k_halo_wait(int nsend, const int32_t *senders, const unsigned long long *arrival, unsigned long long *expect, int *error,
             long long timeout_cycles)
 {
+    MOKAB_TRACE_BEGIN();
     const int i = threadIdx.x;
-    if (i >= nsend) return;
-    const int q = senders[i];
+    if (i < nsend) {
+        const int q = senders[i];
 #ifndef MOKAB_SIM
-    const long long t0 = clock64();
-    while (!sender_ready(arrival, expect, q)) {
-        if (*(volatile int *)error || clock64() - t0 > timeout_cycles) {       // a peer died or the schedules diverged: never hang the GPU
-            atomicExch(error, 1);
-            break;
+        const long long t0 = clock64();
+        while (!sender_ready(arrival, expect, q)) {
+            if (*(volatile int *)error || clock64() - t0 > timeout_cycles) {       // a peer died or the schedules diverged: never hang the GPU
+                atomicExch(error, 1);
+                break;
+            }
+            __nanosleep(64);
         }
-        __nanosleep(64);
-    }
 #endif
-    expect[q] += 1ull;
+        expect[q] += 1ull;
+    }
+    MOKAB_TRACE_END(101u);
 }
 
 // The variant for launches that carry the exchange themselves (fused::k_rk_stage<..., PUSH>): those count their own

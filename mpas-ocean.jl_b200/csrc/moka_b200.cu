@@ -868,6 +868,9 @@ static void launch_stage(mokab_ctx *ctx, const mokab_mesh *m, fused::StageArgs<R
     if (part == MOKAB_PART_INTERIOR) { grid = m->nInterior; A.blockList = m->blkInterior.p; }
     if (part == MOKAB_PART_BOUNDARY || part == MOKAB_PART_BOUNDARY_PUSH) { grid = m->nBoundary; A.blockList = m->blkBoundary.p; }
     if (grid == 0) return;
+#ifdef MOKAB_TRACE
+    A.traceKind = STAGE | (part << 4);
+#endif
     cudaStream_t s = stream ? stream : ctx->stream;
     const bool hex = m->S2 == 10 && m->S == 6;
     const bool hept = m->S2 == 12 && m->S == 7;   // pentagons / hexagons / heptagons (quasi-uniform MPAS meshes): rows padded to 12 / 7
@@ -2555,6 +2558,56 @@ int mokab_p2p_error(mokab_state *state, int *out)
         state->ctx->bind();
         MOKAB_CUDA(cudaStreamSynchronize(state->ctx->stream));
         MOKAB_CUDA(cudaMemcpy(out, state->p2p.error.p, sizeof(int), cudaMemcpyDeviceToHost));
+    });
+}
+
+// ---- stage timeline of the TRACE build (common.cuh) --------------------------------------------------------------------------
+#ifdef MOKAB_TRACE
+static TraceRec *g_trace_host_buf = nullptr;
+static unsigned int g_trace_host_cap = 0;
+#endif
+int mokab_trace_begin(mokab_ctx *ctx, int64_t capacity)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(ctx && capacity >= 0, "trace_begin: bad argument");
+#ifdef MOKAB_TRACE
+        ctx->bind();
+        MOKAB_CUDA(cudaDeviceSynchronize());
+        TraceRec *none = nullptr;
+        MOKAB_CUDA(cudaMemcpyToSymbol(g_trace_buf, &none, sizeof(none)));
+        if (g_trace_host_buf) { cudaFree(g_trace_host_buf); g_trace_host_buf = nullptr; g_trace_host_cap = 0; }
+        if (capacity == 0) return;
+        MOKAB_CUDA(cudaMalloc(&g_trace_host_buf, (size_t)capacity * sizeof(TraceRec)));
+        MOKAB_CUDA(cudaMemset(g_trace_host_buf, 0, (size_t)capacity * sizeof(TraceRec)));
+        g_trace_host_cap = (unsigned int)capacity;
+        const unsigned long long zero = 0;
+        MOKAB_CUDA(cudaMemcpyToSymbol(g_trace_count, &zero, sizeof(zero)));
+        MOKAB_CUDA(cudaMemcpyToSymbol(g_trace_cap, &g_trace_host_cap, sizeof(g_trace_host_cap)));
+        MOKAB_CUDA(cudaMemcpyToSymbol(g_trace_buf, &g_trace_host_buf, sizeof(g_trace_host_buf)));
+#else
+        throw Error("trace_begin: this build carries no stage timeline (make libmoka_b200_trace.so, MOKAB_LIB=libmoka_b200_trace.so)");
+#endif
+    });
+}
+
+int mokab_trace_read(mokab_ctx *ctx, void *records, int64_t max_records, int64_t *count)
+{
+    return guarded([&] {
+        MOKAB_REQUIRE(ctx && count && (records || max_records == 0), "trace_read: bad argument");
+#ifdef MOKAB_TRACE
+        ctx->bind();
+        MOKAB_CUDA(cudaDeviceSynchronize());
+        unsigned long long n = 0;
+        MOKAB_CUDA(cudaMemcpyFromSymbol(&n, g_trace_count, sizeof(n)));
+        const int64_t have = (int64_t)std::min<unsigned long long>(n, g_trace_host_cap);
+        *count = (int64_t)n;
+        const int64_t take = std::min(have, max_records);
+        if (take > 0) MOKAB_CUDA(cudaMemcpy(records, g_trace_host_buf, (size_t)take * sizeof(TraceRec), cudaMemcpyDeviceToHost));
+#else
+        (void)records; (void)max_records;
+        *count = 0;
+        throw Error("trace_read: this build carries no stage timeline (make libmoka_b200_trace.so)");
+#endif
     });
 }
 

@@ -66,7 +66,7 @@ SYMBOLS = [
     "mokab_refresh_ssh", "mokab_mesh_block_counts", "mokab_mesh_derived_blocks",
     "mokab_halo_recv_device_indices", "mokab_p2p_blob_size", "mokab_p2p_export", "mokab_p2p_setup", "mokab_halo_push",
     "mokab_halo_wait", "mokab_halo_wait_arrivals", "mokab_p2p_error", "mokab_p2p_close",
-    "mokab_set_option", "mokab_get_option",
+    "mokab_set_option", "mokab_get_option", "mokab_trace_begin", "mokab_trace_read",
     "mokab_comm_get_unique_id", "mokab_comm_init", "mokab_comm_destroy", "mokab_comm_rank", "mokab_comm_barrier",
     "mokab_comm_allreduce_f64", "mokab_comm_allgather_bytes", "mokab_decomp_setup", "mokab_decomp_set_flags",
     "mokab_timestep_rk4_decomposed", "mokab_timestep_forward_euler_decomposed", "mokab_reduce_decomposed",
@@ -117,6 +117,7 @@ def bind(L):
         "mokab_timestep_rk4_decomposed": [vp, dbl, i64], "mokab_timestep_forward_euler_decomposed": [vp, dbl, i64],
         "mokab_reduce_decomposed": [vp, C.c_int, C.POINTER(dbl)], "mokab_decomp_synchronize": [vp], "mokab_decomp_close": [vp],
         "mokab_set_option": [C.c_char_p, i64], "mokab_get_option": [C.c_char_p, C.POINTER(i64)],
+        "mokab_trace_begin": [vp, i64], "mokab_trace_read": [vp, vp, i64, C.POINTER(i64)],
         "mokab_halo_push": [vp, C.c_int, vp], "mokab_halo_wait": [vp, vp], "mokab_halo_wait_arrivals": [vp, vp], "mokab_p2p_error": [vp, C.POINTER(C.c_int)], "mokab_p2p_close": [vp],
     }
     for name, args in sig.items():
