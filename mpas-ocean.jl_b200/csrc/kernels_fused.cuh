@@ -565,9 +565,8 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
             for (int j = P.startC[cc]; j < P.startC[cc + 1]; ++j) P.peerH[P.slotC[j]][P.dstC[j]] = v;
         }
     }
-    if constexpr (PUSH) {   // every storing thread fences, the last block to finish opens the next launch's gate and ticks the receivers
+    if constexpr (PUSH) {   // one fence per block after the barrier (kernels_p2p.cuh), the last block to finish opens the next launch's gate and ticks the receivers
         const PushStage<R> &P = *A.push;
-        p2p::fence_system();
         __syncthreads();
         if (threadIdx.x == 0) {
             p2p::fence_system();

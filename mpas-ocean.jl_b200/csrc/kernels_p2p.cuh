@@ -9,9 +9,9 @@
 // else: no message buffers, no unpack, no host involvement, and -- all protocol state living in device memory as
 // monotonically increasing counters -- the whole schedule is capture/replay invariant.
 //
-// Ordering.  Sender: data stores -> __threadfence_system() by every storing thread -> block barrier -> one thread
-// per block bumps a local done-counter; the block that sees the last ticket fences again and adds 1 (system scope)
-// to its slot in each receiver's arrival array.  Receiver: thread q spins with acquire loads until arrival[q] has
+// Ordering.  Sender: data stores -> block barrier -> one thread per block fences at system scope (cumulative over the
+// stores the barrier ordered before it) and bumps a local done-counter; the block that sees the last ticket fences again
+// and adds 1 (system scope) to its slot in each receiver's arrival array.  Receiver: thread q spins with acquire loads until arrival[q] has
 // reached the count it expects (its own counter of completed waits + 1), then the kernel ends and the stream order
 // makes the data visible to the stage kernel that follows.  Hazards: a rank can run at most one
 // RK stage ahead of a peer (its stage t needs the peer's stage t-1 counter), consecutive stage outputs alternate
@@ -68,8 +68,10 @@ __global__ void __launch_bounds__(256) k_halo_push(const PushArgs<R> A)
         const int p = A.slot[k];
         if (d >= 0) A.peerH[p][d] = v;
         else A.peerU[p][-d - 1] = v;
-        fence_system();
     }
+    // ONE system-scope fence per block, by the thread that takes the ticket after the block barrier (the barrier orders the
+    // other threads' stores before it, the fence is cumulative) -- not one per storing thread: r02l's timeline showed this
+    // kernel lasting 16 us whatever its size, i.e. the time of its ~160 per-warp MEMBAR.SYS.
     __syncthreads();
     if (threadIdx.x == 0) {
         fence_system();

@@ -731,6 +731,7 @@ struct Options {
     int stage_auto = 1;           // MOKAB_STAGE_AUTO: with stage_tma = 3, a Float64 launch of a few rounds of blocks takes the plain kernel (one
                                   // resident block per SM fewer, no prefetch): prefer_plain_variant
     int stage_auto_hi = 80;       // MOKAB_STAGE_AUTO_HI: ... up to this many blocks per SM (80 x 148 = 11 840 blocks)
+    int launch_priority = 1;      // MOKAB_LAUNCH_PRIORITY: launches into a prioritised stream carry that priority as a launch attribute (launch_ex)
     int stage_pdl = 0;            // MOKAB_STAGE_PDL: stage launches carry the programmatic-stream-serialization attribute (kernels_fused.cuh: pdl_*)
     int decomp_serial_blocks = 0;  // MOKAB_DECOMP_SERIAL_BLOCKS: with MOKAB_HALO_P2P_FUSED, a rank whose part has fewer blocks than this runs ONE
                                   // launch per stage (all blocks, exchange folded in) instead of the two-stream overlap schedule.
@@ -754,6 +755,7 @@ struct Options {
         stage_auto = geti("MOKAB_STAGE_AUTO", 1) ? 1 : 0;
         stage_auto_hi = std::max(0, geti("MOKAB_STAGE_AUTO_HI", 80));
         stage_pdl = geti("MOKAB_STAGE_PDL", 0) ? 1 : 0;
+        launch_priority = geti("MOKAB_LAUNCH_PRIORITY", 1) ? 1 : 0;
         decomp_serial_blocks = std::max(0, geti("MOKAB_DECOMP_SERIAL_BLOCKS", 0));
     }
 };
@@ -815,25 +817,52 @@ static void ensure_wf_interleaved(mokab_mesh *m)
     MOKAB_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
-// A stage launch with the programmatic-stream-serialization attribute ("stage_pdl"): the launch may become resident while the
-// previous kernel of the stream drains; the kernel itself waits (griddepcontrol.wait) before it touches the state.  Captured
-// into graphs as a programmatic dependency edge.
-template <class... P, class... A>
-static void launch_pdl(void (*kernel)(P...), int grid, size_t smem, cudaStream_t s, A &&...args)
+// Launches that carry attributes.  (1) "stage_pdl": the programmatic-stream-serialization attribute -- the launch may become
+// resident while the previous kernel of the stream drains; the kernel itself waits (griddepcontrol.wait) before it touches the
+// state.  (2) The PRIORITY of the stream the launch goes to, as an attribute of the launch itself: a kernel node captured from a
+// high-priority stream does not keep that priority by itself (r02l timeline: the wait kernel and the boundary blocks of the halo
+// stream were dispatched only after the LAST block of the concurrently running interior launch had been dispatched, i.e. the
+// boundary part ran after the interior part instead of next to it -- 13-17 us per stage exposed on 8 192-block parts); with the
+// attribute the block scheduler hands freed SM slots to the halo stream's kernels first, in graphs too.
+static int stream_priority_of(cudaStream_t s)
 {
 #ifdef MOKAB_SIM
-    (void)kernel; (void)grid; (void)smem; (void)s;
-    throw Error("stage_pdl: not available on the simulated runtime");
+    (void)s;
+    return 0;
+#else
+    int p = 0;
+    if (s && options().launch_priority) cudaStreamGetPriority(s, &p);
+    return p;
+#endif
+}
+template <class... P, class... A>
+static void launch_ex(void (*kernel)(P...), int grid, int block, size_t smem, cudaStream_t s, bool pdl, int priority, A &&...args)
+{
+#ifdef MOKAB_SIM
+    (void)kernel; (void)grid; (void)block; (void)smem; (void)s; (void)pdl; (void)priority;
+    throw Error("launch_ex: not available on the simulated runtime");
 #else
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)fused::kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    int n = 0;
+    if (pdl) { at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[n].val.programmaticStreamSerializationAllowed = 1; ++n; }
+    if (priority != 0) { at[n].id = cudaLaunchAttributePriority; at[n].val.priority = priority; ++n; }
+    cfg.attrs = at; cfg.numAttrs = (unsigned)n;
     MOKAB_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(std::forward<A>(args))...));
 #endif
 }
+// the small kernels of the halo exchange: a plain launch unless their stream has a priority to carry
+#ifdef MOKAB_SIM
+#define MOKAB_LAUNCH_ON(kernel, grid, block, s, ...) kernel<<<(grid), (block), 0, (s)>>>(__VA_ARGS__)
+#else
+#define MOKAB_LAUNCH_ON(kernel, grid, block, s, ...)                                                     \
+    do {                                                                                                 \
+        const int prio_ = stream_priority_of(s);                                                         \
+        if (prio_ != 0) launch_ex(kernel, (grid), (block), 0, (s), false, prio_, __VA_ARGS__);           \
+        else kernel<<<(grid), (block), 0, (s)>>>(__VA_ARGS__);                                           \
+    } while (0)
+#endif
 static bool stage_pdl_enabled()
 {
 #if defined(MOKAB_SIM) || defined(MOKAB_STATE_LOADS_LDG)
@@ -875,7 +904,12 @@ static void launch_stage(mokab_ctx *ctx, const mokab_mesh *m, fused::StageArgs<R
     const bool hex = m->S2 == 10 && m->S == 6;
     const bool hept = m->S2 == 12 && m->S == 7;   // pentagons / hexagons / heptagons (quasi-uniform MPAS meshes): rows padded to 12 / 7
     if (part == MOKAB_PART_BOUNDARY_PUSH || part == MOKAB_PART_ALL_PUSH) {   // explicit edgesOnEdge: a boundary block reads halo rows, which cannot be rebuilt
-#define MOKAB_STAGE_PUSH(S2T, ST, FOLD) fused::k_rk_stage<R, STAGE, S2T, ST, FOLD, false, true><<<grid, fused::kThreads, 0, s>>>(A, m->S2, m->S)
+        const int prioP = stream_priority_of(s);
+#define MOKAB_STAGE_PUSH(S2T, ST, FOLD)                                                                                             \
+    do {                                                                                                                            \
+        if (prioP != 0) launch_ex(fused::k_rk_stage<R, STAGE, S2T, ST, FOLD, false, true>, grid, fused::kThreads, 0, s, false, prioP, A, m->S2, m->S); \
+        else fused::k_rk_stage<R, STAGE, S2T, ST, FOLD, false, true><<<grid, fused::kThreads, 0, s>>>(A, m->S2, m->S);               \
+    } while (0)
         if (hex && m->uniformF)      MOKAB_STAGE_PUSH(10, 6, false);
         else if (hex)                MOKAB_STAGE_PUSH(10, 6, true);
         else if (m->uniformF)        MOKAB_STAGE_PUSH(0, 0, false);
@@ -906,10 +940,11 @@ static void launch_stage(mokab_ctx *ctx, const mokab_mesh *m, fused::StageArgs<R
             A.wfI = fm.wfI.p;
             const size_t smem = (size_t)(hex ? fused::cpa_groups<R, 10>() : fused::cpa_groups<R, 12>()) * fused::kThreads * 16;
             const bool pdl = stage_pdl_enabled();
+            const int prio = stream_priority_of(s);
 #define MOKAB_STAGE_CPA(S2T, ST, FOLD, DER)                                                                                          \
     do {                                                                                                                            \
         auto k_rk_stage_cpa = fused::k_rk_stage<R, STAGE, S2T, ST, FOLD, DER, false, 3>;                                            \
-        if (pdl) launch_pdl(k_rk_stage_cpa, grid, smem, s, A, m->S2, m->S);                                                         \
+        if (pdl || prio != 0) launch_ex(k_rk_stage_cpa, grid, fused::kThreads, smem, s, pdl, prio, A, m->S2, m->S);                 \
         else k_rk_stage_cpa<<<grid, fused::kThreads, smem, s>>>(A, m->S2, m->S);                                                    \
     } while (0)
             if (hex) {
@@ -960,10 +995,11 @@ static void launch_stage(mokab_ctx *ctx, const mokab_mesh *m, fused::StageArgs<R
         A.wStride = 0;
     }
     const bool pdl0 = stage_pdl_enabled();
+    const int prio0 = stream_priority_of(s);
 #define MOKAB_STAGE(S2T, ST, FOLD, DER)                                                                                              \
     do {                                                                                                                            \
         auto k_rk_stage_plain = fused::k_rk_stage<R, STAGE, S2T, ST, FOLD, DER>;                                                    \
-        if (pdl0) launch_pdl(k_rk_stage_plain, grid, 0, s, A, m->S2, m->S);                                                         \
+        if (pdl0 || prio0 != 0) launch_ex(k_rk_stage_plain, grid, fused::kThreads, 0, s, pdl0, prio0, A, m->S2, m->S);              \
         else k_rk_stage_plain<<<grid, fused::kThreads, 0, s>>>(A, m->S2, m->S);                                                     \
     } while (0)
     if (hex && der && m->uniformF)  MOKAB_STAGE(10, 6, false, true);
@@ -1068,10 +1104,10 @@ static void halo_pack(mokab_state *st, int stage, void *buf, cudaStream_t stream
     cudaStream_t s = stream ? stream : ctx->stream;
     if (!unpack) {
         const int n = (int)m->haloSend.n;
-        if (n) k_halo_pack<R><<<nblk(n), 256, 0, s>>>(n, (int)m->nC, m->haloSend.p, (const R *)h, (const R *)u, (R *)buf);
+        if (n) MOKAB_LAUNCH_ON(k_halo_pack<R>, nblk(n), 256, s, n, (int)m->nC, (const int32_t *)m->haloSend.p, (const R *)h, (const R *)u, (R *)buf);
     } else {
         const int n = (int)m->haloRecv.n;
-        if (n) k_halo_unpack<R><<<nblk(n), 256, 0, s>>>(n, (int)m->nC, m->haloRecv.p, (const R *)buf, h, u);
+        if (n) MOKAB_LAUNCH_ON(k_halo_unpack<R>, nblk(n), 256, s, n, (int)m->nC, (const int32_t *)m->haloRecv.p, (const R *)buf, h, u);
     }
     MOKAB_CUDA(cudaGetLastError());
     ctx->launches++;
@@ -1724,7 +1760,7 @@ static void p2p_push(mokab_state *st, int stage, cudaStream_t stream)
     if (nrecv == 0) return;
     cudaStream_t s = stream ? stream : ctx->stream;
     if (x.nPush == 0) {
-        p2p::k_halo_signal<<<1, 32, 0, s>>>(nrecv, (unsigned long long *const *)x.arrivalAt.p);
+        MOKAB_LAUNCH_ON(p2p::k_halo_signal, 1, 32, s, nrecv, (unsigned long long *const *)x.arrivalAt.p);
     } else {
         R *u, *h;
         stage_output<R>(st, stage, &u, &h);
@@ -1734,7 +1770,7 @@ static void p2p_push(mokab_state *st, int stage, cudaStream_t stream)
         A.h = h; A.u = u;
         A.peerH = (R *const *)x.peerH.p + (size_t)tgt * nrecv; A.peerU = (R *const *)x.peerU.p + (size_t)tgt * nrecv;
         A.done = x.done.p; A.arrival = (unsigned long long *const *)x.arrivalAt.p; A.nrecv = nrecv;
-        p2p::k_halo_push<R><<<nblk(A.n), 256, 0, s>>>(A);
+        MOKAB_LAUNCH_ON(p2p::k_halo_push<R>, nblk(A.n), 256, s, A);
     }
     MOKAB_CUDA(cudaGetLastError());
     ctx->launches++;
@@ -1767,8 +1803,8 @@ static void p2p_wait_arrivals(mokab_state *st, cudaStream_t stream)
 #ifdef MOKAB_SIM
     p2p_gate_sim(st, s);
 #else
-    p2p::k_halo_wait_arrivals<<<1, p2p::kMaxPeers, 0, s>>>(nsend, (const int32_t *)x.senders.p, (const unsigned long long *)x.arrival,
-                                                            (const unsigned long long *)x.expect.p, x.error.p, p2p_timeout_cycles());
+    MOKAB_LAUNCH_ON(p2p::k_halo_wait_arrivals, 1, p2p::kMaxPeers, s, nsend, (const int32_t *)x.senders.p, (const unsigned long long *)x.arrival,
+                    (const unsigned long long *)x.expect.p, (int *)x.error.p, p2p_timeout_cycles());
     MOKAB_CUDA(cudaGetLastError());
 #endif
     ctx->launches++;
@@ -1794,8 +1830,8 @@ static void p2p_wait(mokab_state *st, cudaStream_t stream)
         return true;
     });
 #else
-    p2p::k_halo_wait<<<1, p2p::kMaxPeers, 0, s>>>(nsend, (const int32_t *)x.senders.p, (const unsigned long long *)x.arrival,
-                                                   x.expect.p, x.error.p, p2p_timeout_cycles());
+    MOKAB_LAUNCH_ON(p2p::k_halo_wait, 1, p2p::kMaxPeers, s, nsend, (const int32_t *)x.senders.p, (const unsigned long long *)x.arrival,
+                    (unsigned long long *)x.expect.p, (int *)x.error.p, p2p_timeout_cycles());
     MOKAB_CUDA(cudaGetLastError());
 #endif
     ctx->launches++;
@@ -2624,6 +2660,7 @@ int mokab_set_option(const char *name, int64_t value)
         else if (n == "stage_auto") o.stage_auto = value ? 1 : 0;
         else if (n == "stage_auto_hi") { MOKAB_REQUIRE(value >= 0 && value < (1 << 20), "set_option: bad stage_auto_hi"); o.stage_auto_hi = (int)value; }
         else if (n == "stage_pdl") o.stage_pdl = value ? 1 : 0;
+        else if (n == "launch_priority") o.launch_priority = value ? 1 : 0;
         else if (n == "decomp_serial_blocks") o.decomp_serial_blocks = (int)value;
         else if (n == "test_drop_dependency") o.test_drop_dependency = (int)value;
         else throw Error("set_option: unknown option '" + n + "'");
@@ -2644,6 +2681,7 @@ int mokab_get_option(const char *name, int64_t *value)
         else if (n == "stage_auto") *value = o.stage_auto;
         else if (n == "stage_auto_hi") *value = o.stage_auto_hi;
         else if (n == "stage_pdl") *value = o.stage_pdl;
+        else if (n == "launch_priority") *value = o.launch_priority;
         else if (n == "decomp_serial_blocks") *value = o.decomp_serial_blocks;
         else throw Error("get_option: unknown option '" + n + "'");
     });
