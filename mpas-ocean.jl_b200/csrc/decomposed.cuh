@@ -190,7 +190,13 @@ static void decomp_build_graphs(mokab_state *st, double dt, int kind)
             st->cur = saved_cur;
             if (e != cudaSuccess) { ctx->launches = saved_launches; MOKAB_CUDA(e); }
             cudaGraphExec_t ge = nullptr;
+            // (per-node priorities -- the halo stream's launches carry theirs, moka_b200.cu: launch_ex -- count only in graphs
+            //  instantiated with this flag; without it every node runs at the priority of the stream the graph is launched into)
+#ifdef MOKAB_SIM
             e = cudaGraphInstantiate(&ge, g, 0);
+#else
+            e = cudaGraphInstantiate(&ge, g, options().launch_priority ? cudaGraphInstantiateFlagUseNodePriority : 0);
+#endif
             cudaGraphDestroy(g);
             if (e != cudaSuccess) { ctx->launches = saved_launches; MOKAB_CUDA(e); }
             D.graph[kind][p][n] = ge;
