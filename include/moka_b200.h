@@ -164,9 +164,12 @@ int  mokab_state_create(mokab_ctx *ctx, const mokab_mesh *mesh, int dtype, mokab
  * coriolis.jl:69-73, horizontal_advection.jl:60-66: one pressure gradient for the column, Coriolis and thickness flux per
  * level) but its drivers fill level 1 only (DiagnosticVars.jl:158-173, time_integration.jl:205-212); for nVertLevels > 1 the
  * semantics are project-defined: every level is stepped, ssh = sum over the levels of layerThickness -
- * restingThicknessSum.  Float64, undecomposed meshes; supported: state set/get, the src/ocn entry points, both steppers
- * (RungeKutta4 fused -- static data read once per column -- and unfused; ForwardEuler as the reference's kernel sequence),
- * mokab_reduce.  Not supported: the reverse mode, the staged / decomposed entry points. */
+ * restingThicknessSum.  Float64; supported: state set/get, the src/ocn entry points, both steppers (RungeKutta4 fused --
+ * static data read once per column -- and unfused; ForwardEuler as the reference's kernel sequence), mokab_reduce, and on
+ * decomposed meshes mokab_timestep_rk4_decomposed (whole-part stage launches, ONE halo message of nVertLevels + 1 planes per
+ * stage -- the levels of (layerThickness, normalVelocity) and the free surface --, packed exchange whatever the halo mode,
+ * captured graphs) and mokab_reduce_decomposed.  Not supported: the reverse mode, the staged entry points, ForwardEuler on
+ * decomposed meshes. */
 int  mokab_state_create_levels(mokab_ctx *ctx, const mokab_mesh *mesh, int dtype, int nVertLevels, mokab_state **out);
 int  mokab_state_levels(const mokab_state *state, int *nVertLevels);
 int  mokab_state_destroy(mokab_state *state);

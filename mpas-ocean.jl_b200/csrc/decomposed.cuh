@@ -52,6 +52,15 @@ static void decomp_enqueue_rk4(mokab_state *st, double dt, int64_t nsteps)
     const bool fused = D.mode == MOKAB_HALO_P2P_FUSED;             // the boundary launch carries the exchange itself
     const int boundary = fused ? MOKAB_PART_BOUNDARY_PUSH : MOKAB_PART_BOUNDARY;
     if (nsteps <= 0) return;
+    if constexpr (sizeof(R) == 8) {
+        if (st->K > 1) {   // multi-level states: whole-part launches of k_rk_stage_ml, one K + 1 plane message per stage (whatever the halo mode)
+            for (int64_t i = 0; i < nsteps; ++i) {
+                enqueue_rk4_step_ml(st, dt, st->cur);
+                st->cur = 1 - st->cur;
+            }
+            return;
+        }
+    }
     // Experiment (option "decomp_serial_blocks", off by default): parts of a few hundred blocks (Kelvin 1024x1024 over 8 GPUs: 512)
     // are a fraction of one wave of resident blocks, a stage kernel lasts ~12 us and the two-stream schedule's chain of launches
     // and cross-stream waits is the stage time; with the exchange folded into the launch such a part can run ONE kernel per
@@ -213,6 +222,15 @@ template <class R>
 static void decomp_prepare(mokab_state *st)
 {
     mokab_mesh *m = const_cast<mokab_mesh *>(st->mesh);
+    if (st->K > 1) {
+        mokab_state::Decomp &D = st->dec;
+        const size_t ns = std::max<size_t>(m->haloSend.n, 1) * (size_t)(st->K + 1) * 8, nr = std::max<size_t>(m->haloRecv.n, 1) * (size_t)(st->K + 1) * 8;
+        if (D.sendBufML.n < ns) { D.sendBufML.alloc(ns); D.sendBufML.zero(st->ctx->stream); }
+        if (D.recvBufML.n < nr) { D.recvBufML.alloc(nr); D.recvBufML.zero(st->ctx->stream); }
+        // the stage kernels gather ssh of the state they read: make ssh[cur] what the current layerThickness implies, halo copies
+        // included (every later step's ssh is written by the stage that produces its layerThickness, and exchanged with it)
+        update_ssh(st, st->d->h[st->cur].p, st->d->ssh[st->cur].p);
+    }
     ensure_fused<R>(m);
     stage_tma_prepare<R>();
     ensure_wf_block_major<R>(m);
@@ -358,6 +376,11 @@ static void decomp_setup(mokab_state *st, mokab_comm *c, const int64_t *scnt, co
     D.comm = c; D.mode = mode; D.flags = flags;
     D.scnt.assign(scnt, scnt + c->nranks); D.rcnt.assign(rcnt, rcnt + c->nranks);
     D.sendBuf.alloc((size_t)std::max<int64_t>(ns, 1) * sizeof(R)); D.recvBuf.alloc((size_t)std::max<int64_t>(nr, 1) * sizeof(R));
+    {
+        std::vector<int32_t> so((size_t)c->nranks + 1, 0), ro((size_t)c->nranks + 1, 0);
+        for (int q = 0; q < c->nranks; ++q) { so[q + 1] = so[q] + (int32_t)scnt[q]; ro[q + 1] = ro[q] + (int32_t)rcnt[q]; }
+        D.sendOff.upload(so, st->ctx->stream); D.recvOff.upload(ro, st->ctx->stream);
+    }
     D.sendBuf.zero(st->ctx->stream); D.recvBuf.zero(st->ctx->stream);
     int lo = 0, hi = 0;
 #ifndef MOKAB_SIM
@@ -371,7 +394,7 @@ static void decomp_setup(mokab_state *st, mokab_comm *c, const int64_t *scnt, co
     comm::all_to_all(c, D.halo, D.sendBuf.p, D.recvBuf.p, D.scnt.data(), D.rcnt.data(), sizeof(R));
     MOKAB_CUDA(cudaStreamSynchronize(D.halo));
     D.ready = true;
-    if (mode != MOKAB_HALO_NCCL) decomp_setup_p2p<R>(st);
+    if (mode != MOKAB_HALO_NCCL && st->K == 1) decomp_setup_p2p<R>(st);   // (multi-level states always use the packed exchange)
 }
 
 static void decomp_release(mokab_state *st)
@@ -382,6 +405,7 @@ static void decomp_release(mokab_state *st)
     D.events.clear();
     if (D.halo) { cudaStreamSynchronize(D.halo); cudaStreamDestroy(D.halo); D.halo = nullptr; }
     D.sendBuf.release(); D.recvBuf.release();
+    D.sendBufML.release(); D.recvBufML.release(); D.sendOff.release(); D.recvOff.release();
     D.ready = false;
     D.comm = nullptr;
 }
@@ -551,6 +575,8 @@ int mokab_timestep_rk4_decomposed(mokab_state *state, double dt, int64_t nsteps)
     return guarded([&] {
         MOKAB_REQUIRE(state && state->dec.ready, "timestep_rk4_decomposed: call mokab_decomp_setup first");
         MOKAB_REQUIRE(nsteps >= 0, "timestep_rk4_decomposed: nsteps must be >= 0");
+        MOKAB_REQUIRE(state->K == 1 || (state->dtype == MOKAB_F64 && !state->d->taping),
+                      "timestep_rk4_decomposed: multi-level states are Float64 and have no reverse mode");
         state->ctx->bind();
         leave_forward_euler(state);
         if (state->dtype == MOKAB_F64) { decomp_run<double>(state, dt, nsteps, 0); if (nsteps) refresh_ssh<double>(state); }
@@ -564,6 +590,7 @@ int mokab_timestep_forward_euler_decomposed(mokab_state *state, double dt, int64
         MOKAB_REQUIRE(state && state->dec.ready, "timestep_forward_euler_decomposed: call mokab_decomp_setup first");
         MOKAB_REQUIRE(nsteps >= 0, "timestep_forward_euler_decomposed: nsteps must be >= 0");
         require_f64(state, "timestep_forward_euler_decomposed");
+        MOKAB_REQUIRE(state->K == 1, "timestep_forward_euler_decomposed: single-level states only (nVertLevels == 1)");
         state->ctx->bind();
         if (nsteps > 0) run_fe_stage_prepare(state);               // (allocations and the hand-over copy, outside any capture)
         decomp_run<double>(state, dt, nsteps, 1);

@@ -596,6 +596,7 @@ k_rk_stage(const StageArgs<R> A, int S2rt, int Srt)
 // kernel's bit for bit (tested).  Float64, explicit edgesOnEdge, whole mesh (no halo parts).
 struct StageArgsML {
     int nE, nC, K;
+    int nCown;               // cells computed by this rank (the rest are halo copies: decomposed meshes)
     const int2 *ce;
     const int32_t *eoe;      // (S2, nE) absent -> self
     const int32_t *eoc;      // (S, nC)  (edge << 1) | (sign > 0)
@@ -649,7 +650,7 @@ k_rk_stage_ml(const StageArgsML A, int S2rt, int Srt)
         }
     }
     const int cc = b * kTC + threadIdx.x;
-    if (cc < nC) {
+    if (cc < A.nCown) {
         const int n = ld_stream(A.nEoC + cc);
         int ed[MAXS], other[MAXS];
         double dd[MAXS];
@@ -877,6 +878,52 @@ k_halo_unpack(int n, int nC, const int32_t *__restrict__ idx, const R *__restric
         else u[i - nC] = buf[k];
     }
     MOKAB_TRACE_END(111u);
+}
+
+// Multi-level states: one message per peer carries K + 1 planes -- the K levels of (h on halo cells, u on halo edges) and the
+// free surface of the halo cells (its edge part unused) -- so a stage needs ONE exchange whatever K.  Segment q of the message
+// (the entities rank q gets / sends, segOff[q] ... segOff[q + 1] of the single-level list) holds its planes back to back.
+template <class R>
+__device__ __forceinline__ size_t halo_ml_slot(int k, int plane, int K, const int32_t *__restrict__ segOff, int nseg)
+{
+    int lo = 0, hi = nseg;                 // the segment of item k: the last q with segOff[q] <= k
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (segOff[mid] <= k) lo = mid; else hi = mid;
+    }
+    const int cnt = segOff[lo + 1] - segOff[lo];
+    return (size_t)segOff[lo] * (size_t)(K + 1) + (size_t)plane * cnt + (size_t)(k - segOff[lo]);
+}
+template <class R>
+__global__ void __launch_bounds__(256)
+k_halo_pack_ml(int n, int nC, int nE, int K, const int32_t *__restrict__ idx, const int32_t *__restrict__ segOff, int nseg,
+               const R *__restrict__ h, const R *__restrict__ u, const R *__restrict__ ssh, R *__restrict__ buf)
+{
+    const int nb = (n + 255) / 256;                                   // grid = nb blocks per plane x (K + 1) planes
+    const int plane = blockIdx.x / nb, k = (blockIdx.x - plane * nb) * 256 + threadIdx.x;
+    if (k >= n) return;
+    const int i = idx[k];
+    R v;
+    if (plane < K) v = i < nC ? h[(size_t)plane * nC + i] : u[(size_t)plane * nE + (i - nC)];
+    else v = i < nC ? ssh[i] : R(0);
+    buf[halo_ml_slot<R>(k, plane, K, segOff, nseg)] = v;
+}
+template <class R>
+__global__ void __launch_bounds__(256)
+k_halo_unpack_ml(int n, int nC, int nE, int K, const int32_t *__restrict__ idx, const int32_t *__restrict__ segOff, int nseg,
+                 const R *__restrict__ buf, R *__restrict__ h, R *__restrict__ u, R *__restrict__ ssh)
+{
+    const int nb = (n + 255) / 256;
+    const int plane = blockIdx.x / nb, k = (blockIdx.x - plane * nb) * 256 + threadIdx.x;
+    if (k >= n) return;
+    const int i = idx[k];
+    const R v = buf[halo_ml_slot<R>(k, plane, K, segOff, nseg)];
+    if (plane < K) {
+        if (i < nC) h[(size_t)plane * nC + i] = v;
+        else u[(size_t)plane * nE + (i - nC)] = v;
+    } else if (i < nC) {
+        ssh[i] = v;
+    }
 }
 
 // ---- deterministic reductions (replace sumArray, reference run_loop.jl:47-51) --------------------------

@@ -131,6 +131,8 @@ struct mokab_state {
         uint32_t flags = 0;
         std::vector<int64_t> scnt, rcnt;                     // halo elements sent to / received from every rank
         mokab::DevBuf<unsigned char> sendBuf, recvBuf;       // packed messages (state dtype)
+        mokab::DevBuf<unsigned char> sendBufML, recvBufML;   // multi-level states: K + 1 planes per message (allocated on first use)
+        mokab::DevBuf<int32_t> sendOff, recvOff;             // first item of every rank's segment in the send / recv lists (nranks + 1)
         cudaStream_t halo = nullptr;                         // high-priority stream: boundary blocks + the exchange
         std::vector<cudaEvent_t> events;
         cudaGraphExec_t graph[2][2][2] = {};                 // [RungeKutta4 | ForwardEuler][time-level parity][one | two steps]
@@ -1199,6 +1201,32 @@ static void refresh_ssh(mokab_state *st, cudaStream_t stream = nullptr)
     }
 }
 
+// Multi-level states on a decomposed mesh: one packed exchange per stage of K + 1 planes (k_halo_pack_ml), on the context's
+// stream (the multi-level path has no interior / boundary split; the buffers are sized by decomp_prepare, outside any capture).
+static void halo_exchange_levels(mokab_state *st, double *u, double *h, double *ssh)
+{
+    mokab_state::Decomp &D = st->dec;
+    mokab_ctx *ctx = st->ctx; const mokab_mesh *m = st->mesh;
+    cudaStream_t s = ctx->stream;
+    const int K = st->K, nseg = D.comm->nranks;
+    const int ns = (int)m->haloSend.n, nr = (int)m->haloRecv.n;
+    MOKAB_REQUIRE(D.sendBufML.n >= (size_t)std::max(ns, 1) * (K + 1) * 8 && D.recvBufML.n >= (size_t)std::max(nr, 1) * (K + 1) * 8,
+                  "decomposed multi-level step: the level buffers are not allocated (internal)");
+    if (ns) {
+        k_halo_pack_ml<double><<<nblk(ns) * (K + 1), 256, 0, s>>>(ns, (int)m->nC, (int)m->nE, K, m->haloSend.p, D.sendOff.p, nseg,
+                                                                                            (const double *)h, (const double *)u, (const double *)ssh, (double *)D.sendBufML.p);
+        MOKAB_CUDA(cudaGetLastError());
+        ctx->launches++;
+    }
+    comm::all_to_all(D.comm, s, D.sendBufML.p, D.recvBufML.p, D.scnt.data(), D.rcnt.data(), sizeof(double) * (size_t)(K + 1));
+    if (nr) {
+        k_halo_unpack_ml<double><<<nblk(nr) * (K + 1), 256, 0, s>>>(nr, (int)m->nC, (int)m->nE, K, m->haloRecv.p, D.recvOff.p, nseg,
+                                                                                              (const double *)D.recvBufML.p, h, u, ssh);
+        MOKAB_CUDA(cudaGetLastError());
+        ctx->launches++;
+    }
+}
+
 // ---- fused RK4 on multi-level states (K > 1; fused::k_rk_stage_ml) ---------------------------------------------------------
 template <int STAGE>
 static void launch_stage_ml(mokab_ctx *ctx, const mokab_mesh *m, const fused::StageArgsML &A)
@@ -1225,7 +1253,7 @@ static void enqueue_rk4_step_ml(mokab_state *st, double dt, int p)
     StateT<double> *t = st->d;
     FusedMesh<double> &fm = fused_of<double>(m);
     fused::StageArgsML A;
-    A.nE = (int)m->nE; A.nC = (int)m->nC; A.K = st->K;
+    A.nE = (int)m->nE; A.nC = (int)m->nC; A.K = st->K; A.nCown = (int)m->nCo;
     A.ce = m->ce.p; A.eoe = m->eoeF.p; A.eoc = m->eocF.p; A.nEoE = m->nEoE.p; A.nEoC = m->nEoC.p; A.blkEdgeStart = m->blkEdgeStart.p;
     A.gdc = fm.gdc.p; A.wf = fm.wf.p; A.dv = fm.dv.p; A.invArea = fm.invArea.p; A.H = fm.H.p;
     A.uCur = t->u[p].p; A.hCur = t->h[p].p; A.uAcc = t->u[1 - p].p; A.hAcc = t->h[1 - p].p;
@@ -1243,6 +1271,8 @@ static void enqueue_rk4_step_ml(mokab_state *st, double dt, int p)
         if (stage == 1) launch_stage_ml<1>(ctx, m, A);
         else if (stage == 4) launch_stage_ml<4>(ctx, m, A);
         else launch_stage_ml<2>(ctx, m, A);
+        // decomposed mesh: the halo copies of what this stage wrote -- K levels of (u, h) and the free surface -- in one message
+        if (st->dec.ready) halo_exchange_levels(st, stage == 4 ? A.uAcc : A.uOut, stage == 4 ? A.hAcc : A.hOut, A.sshOut);
     }
 }
 
@@ -2023,8 +2053,6 @@ int mokab_state_create_levels(mokab_ctx *ctx, const mokab_mesh *mesh, int dtype,
         MOKAB_REQUIRE(ctx && mesh && out, "state_create: NULL argument");
         MOKAB_REQUIRE(nVertLevels >= 1 && nVertLevels <= 1024, "state_create: nVertLevels must be in 1..1024");
         MOKAB_REQUIRE(nVertLevels == 1 || dtype == MOKAB_F64, "state_create: multi-level states are Float64 (PrognosticVars.jl:91-93)");
-        MOKAB_REQUIRE(nVertLevels == 1 || (mesh->nCo == mesh->nC && mesh->nEo == mesh->nE),
-                      "state_create: multi-level states need an undecomposed mesh");
         MOKAB_REQUIRE(mesh->ctx == ctx, "state_create: mesh belongs to a different context (src/Architectures.jl:27-33)");
         MOKAB_REQUIRE(dtype == MOKAB_F64 || dtype == MOKAB_F32, "state_create: dtype must be MOKAB_F64 or MOKAB_F32");
         ctx->bind();

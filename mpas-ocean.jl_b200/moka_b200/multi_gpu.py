@@ -294,8 +294,12 @@ class DecomposedModel:
             self.comm.destroy()
 
     def owned(self, field: str) -> np.ndarray:
-        a = getattr(self.prog, field)
-        n = self.loc["nCellsOwned"] if field in ("ssh", "layerThickness") else self.loc["nEdgesOwned"]
+        """The rank's owned part of a field; multi-level fields come back as (owned entities, nVertLevels)."""
+        a = np.asarray(getattr(self.prog, field))
+        cells = field in ("ssh", "layerThickness")
+        n, nloc = (self.loc["nCellsOwned"], self.loc["nCells"]) if cells else (self.loc["nEdgesOwned"], self.loc["nEdges"])
+        if a.size != nloc:
+            a = a.reshape(nloc, -1)
         return a[:n]
 
     def reduce(self, which: str) -> float:

@@ -80,7 +80,7 @@ def build_local_mesh(m: dict, part: np.ndarray, rank: int) -> dict:
 
     loc = {"nCells": int(cells.size), "nEdges": int(edges.size), "nVertices": 0,
            "nCellsOwned": int(owned_c.size), "nEdgesOwned": int(owned_e.size),
-           "maxEdges": S, "maxEdges2": S2, "vertexDegree": m.get("vertexDegree", 3), "nVertLevels": 1,
+           "maxEdges": S, "maxEdges2": S2, "vertexDegree": m.get("vertexDegree", 3), "nVertLevels": int(m.get("nVertLevels", 1)),
            "dc": m.get("dc"), "x_period": m.get("x_period"), "y_period": m.get("y_period")}
     loc["cellsOnEdge"] = g2l_c[m["cellsOnEdge"][edges].astype(np.int64)]
     eoe_g = m["edgesOnEdge"][edges].astype(np.int64)

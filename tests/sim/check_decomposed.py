@@ -136,6 +136,50 @@ def run_adjoint(kind, nx, nparts, nsteps, policy, seed, halo, graph, dtype=np.fl
     return ok, (eu, eh)
 
 
+def run_levels(nx, nparts, K, step_calls, policy, seed, graph, halo="nccl"):
+    """Multi-level states (nVertLevels = K > 1) on the decomposed mesh: every level of (u, h) and the free surface of the halo
+    cells travel in one K + 1 plane message per stage (csrc/moka_b200.cu: halo_exchange_levels); the gathered result must equal
+    the numpy oracle with a level axis on the undecomposed mesh bit for bit."""
+    import moka_oracle as O
+    simcuda.set_policy(policy, seed)
+    m = dict(mb.periodic_hex(nx, nx, 1.0e7 / nx, with_dual=False))
+    OC.sign_index_fields(m)
+    ssh, u, h = mb.inertialGravityWave(m).initial_state()
+    rng = np.random.default_rng(K)
+    frac = rng.uniform(0.5, 1.5, K)
+    frac /= frac.sum()
+    rest = np.outer(np.full(m["nCells"], 1000.0), frac)
+    hk, uk = rest + np.outer(ssh, frac), np.outer(u, 1.0 + 0.1 * np.arange(K))
+    m["restingThickness"], m["nVertLevels"] = rest, K
+    dt = mb.cfl_dt(m["dc"])
+    locs = partition.decompose(m, nparts)
+
+    def body(r, comm):
+        model = multi_gpu.DecomposedModel(locs[r], multi_gpu.local_state(locs[r], ssh, uk, hk), mb.B200(0), 0, overlap=True, graph=graph,
+                                          runtime=simcuda.SimRuntime(comm, r), halo=halo)
+        for n in step_calls:
+            model.step(dt, n)
+        model.finish()
+        res = {f: np.array(model.owned(f)) for f in ("ssh", "normalVelocity", "layerThickness")}
+        mass, status = model.reduce("mass"), model.graph_status
+        model.close()
+        return res, status, mass
+
+    outs = simcuda.run_ranks(nparts, body)
+    gs, gu, gh = np.full(m["nCells"], np.nan), np.full((m["nEdges"], K), np.nan), np.full((m["nCells"], K), np.nan)
+    for loc, (res, _, _) in zip(locs, outs):
+        gu[loc["edgesGlobal"][:loc["nEdgesOwned"]]] = res["normalVelocity"]
+        gh[loc["cellsGlobal"][:loc["nCellsOwned"]]] = res["layerThickness"]
+        gs[loc["cellsGlobal"][:loc["nCellsOwned"]]] = res["ssh"]
+    prog = O.new_state(m, ssh, np.ascontiguousarray(uk.T), np.ascontiguousarray(hk.T))
+    for _ in range(sum(step_calls)):
+        O.timestep_rk4(m, prog, dt)
+    ok = np.array_equal(gu.T, prog["normalVelocity"][-1]) and np.array_equal(gh.T, prog["layerThickness"][-1]) and np.array_equal(gs, prog["ssh"][-1])
+    m0 = float(np.sum(m["areaCell"] * hk.sum(axis=1)))
+    ok = ok and abs(outs[0][2] - m0) <= 1e-13 * m0
+    return ok, outs[0][1]
+
+
 def run_e2e(kind, nx, nparts, iters, policy, seed, halo):
     """bench.py's end-to-end leg at N > 1 (multi_gpu.bench_main.e2e_steps): every iteration uploads this rank's (u, h) from
     page-locked memory through the pipelined transfers, takes ONE step, refreshes ssh and downloads it -- copy streams, the
@@ -345,6 +389,14 @@ def main():
             bad += not ok
             print(f"{kind}{nx} ranks={P} reverse mode, {nsteps} {stepper} steps, {halo} {policy} {'graph' if graph else 'stream'}: "
                   f"{'OK' if ok else 'MISMATCH'} (rel-L2 {eu:.1e} / {eh:.1e} against the adjoint oracle) {time.time() - t0:.1f}s", flush=True)
+    # multi-level states on decomposed meshes
+    for nx, P, K, calls, graph, halo in [(48, 4, 3, [3, 2], True, "nccl"), (32, 3, 10, [3], False, "p2p")] + ([(96, 8, 2, [2, 1], True, "p2p_fused")] if args.cases != "suite" else []):
+        for policy in args.policies.split(","):
+            t0 = time.time()
+            ok, status = run_levels(nx, P, K, calls, policy, 6, graph, halo)
+            bad += not ok
+            print(f"igw{nx} ranks={P} nVertLevels={K} steps={calls} {halo} {policy} {'graph [' + status + ']' if graph else 'stream'}: "
+                  f"{'OK' if ok else 'MISMATCH'} {time.time() - t0:.1f}s", flush=True)
     for halo in (args.halo.split(",")[:1] if args.cases == "suite" else args.halo.split(",")):
         t0 = time.time()
         ok = run_driver(3, args.policies.split(",")[0], halo)

@@ -388,3 +388,35 @@ def test_in_library_decomposed_reverse_mode_with_one_rank(backend, stepper, grap
         Jo, ou, oh = AO.gradient_sum_ssh2(m, u, h, dt, 5)
     assert abs(J - Jo) <= 1e-12 * Jo
     assert rel_l2(gu, ou) <= 1e-12 and rel_l2(gh, oh) <= 1e-12
+
+
+@pytest.mark.parametrize("K,graph", [(3, True), (10, False)])
+def test_in_library_decomposed_multilevel_with_one_rank(backend, K, graph):
+    """Multi-level states through mokab_timestep_rk4_decomposed (fused::k_rk_stage_ml over the owned blocks + one K + 1 plane halo
+    message per stage, csrc/moka_b200.cu: halo_exchange_levels) on a communicator of one rank: the numpy oracle with a level
+    axis, bit for bit.  With neighbours: tests/sim/check_decomposed.py (3 - 8 emulated ranks)."""
+    import moka_oracle as O
+    m = dict(hex_mesh(32, with_dual=False))
+    ssh, u, h = mb.inertialGravityWave(m).initial_state()
+    frac = np.random.default_rng(K).uniform(0.5, 1.5, K)
+    frac /= frac.sum()
+    rest = np.outer(np.full(m["nCells"], 1000.0), frac)
+    hk, uk = rest + np.outer(ssh, frac), np.outer(u, 1.0 + 0.1 * np.arange(K))
+    m["restingThickness"], m["nVertLevels"] = rest, K
+    dt = mb.cfl_dt(m["dc"])
+    loc = partition.decompose(m, 1)[0]
+    model = multi_gpu.DecomposedModel(loc, multi_gpu.local_state(loc, ssh, uk, hk), backend, 0, graph=graph, runtime=_SoloRuntime())
+    for n in (3, 2):
+        model.step(dt, n)
+    model.finish()
+    gu, gh, gs = (np.array(model.owned(f)) for f in ("normalVelocity", "layerThickness", "ssh"))
+    status = model.graph_status
+    model.close()
+    inv_e, inv_c = np.argsort(loc["edgesGlobal"]), np.argsort(loc["cellsGlobal"])
+    prog = O.new_state(m, ssh, np.ascontiguousarray(uk.T), np.ascontiguousarray(hk.T))
+    for _ in range(5):
+        O.timestep_rk4(m, prog, dt)
+    assert np.array_equal(gu[inv_e].T, prog["normalVelocity"][-1]) and np.array_equal(gh[inv_c].T, prog["layerThickness"][-1])
+    assert np.array_equal(gs[inv_c], prog["ssh"][-1])
+    if graph:
+        assert status.startswith("validated"), status
