@@ -396,7 +396,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-overlap", dest="no_overlap", action="store_true", help="multi-GPU: exchange after each full stage")
     ap.add_argument("--no-graph", dest="no_graph", action="store_true", help="multi-GPU: do not capture steps into a CUDA graph")
-    ap.add_argument("--halo", default="p2p", choices=["nccl", "p2p", "p2p_fused"],
+    ap.add_argument("--halo", default="p2p", choices=["nccl", "p2p", "p2p_fused", "p2p_ll"],
                     help="multi-GPU halo exchange: direct stores into the peers' memory with push / wait kernels (default: the "
                          "fastest at N = 2 and N = 8, profiles/README.md r02c / r02e), packed NCCL send/recv, or direct stores "
                          "from inside the boundary launch")

@@ -343,7 +343,10 @@ int  mokab_p2p_error(mokab_state *state, int *out);
 typedef struct mokab_comm mokab_comm;
 enum { MOKAB_HALO_NCCL = 0,       /* pack -> ncclSend/ncclRecv per neighbour (one group) -> unpack, on the halo stream             */
        MOKAB_HALO_P2P = 1,        /* direct stores into the neighbours' state arrays (CUDA IPC) + arrival counters: push / wait kernels */
-       MOKAB_HALO_P2P_FUSED = 2   /* the same stores issued by the boundary blocks themselves (MOKAB_PART_BOUNDARY_PUSH)            */ };
+       MOKAB_HALO_P2P_FUSED = 2,  /* the same stores issued by the boundary blocks themselves (MOKAB_PART_BOUNDARY_PUSH)            */
+       MOKAB_HALO_P2P_LL = 3      /* flag-in-data: every value travels as 8-byte {32 data bits, 32-bit exchange number} packets into a
+                                     receive area of the neighbour (CUDA IPC), whose wait kernel polls the packets and unpacks them --
+                                     no fence, no counter on the sending side (kernels_p2p.cuh)                                      */ };
 enum { MOKAB_DECOMP_NO_OVERLAP = 1u, /* exchange after each whole stage on one stream (diagnostic)                                   */
        MOKAB_DECOMP_NO_GRAPH = 2u    /* launch every step from the host instead of replaying captured 1- / 2-step graphs (diagnostic) */ };
 int  mokab_comm_get_unique_id(void *id_out);

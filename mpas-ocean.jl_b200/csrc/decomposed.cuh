@@ -38,6 +38,11 @@ static void decomp_exchange(mokab_state *st, int stage, cudaStream_t s)
         p2p_wait(st, s);
         return;
     }
+    if (D.mode == MOKAB_HALO_P2P_LL) {
+        p2p_push_ll<R>(st, stage, s);
+        p2p_wait_ll<R>(st, stage, s);
+        return;
+    }
     halo_pack<R>(st, stage, D.sendBuf.p, s, false);
     comm::all_to_all(D.comm, s, D.sendBuf.p, D.recvBuf.p, D.scnt.data(), D.rcnt.data(), sizeof(R));
     halo_pack<R>(st, stage, D.recvBuf.p, s, true);
@@ -353,6 +358,24 @@ static void decomp_setup_p2p(mokab_state *st)
     }
     dst.push_back(0);
     p2p_setup<R>(st, c->rank, n, blobs.data(), (int)peers.size(), peers.data(), counts.data(), dst.data(), (int)peers.size(), peers.data());
+    if (D.mode == MOKAB_HALO_P2P_LL) {
+        // flag-in-data exchange: every rank tells each peer where that peer's segment starts in its receive list and which slot it
+        // keeps for the peer's credit packet (behind the list, in peer order)
+        std::vector<int64_t> tell((size_t)2 * n, -1), told((size_t)2 * n, -1);
+        {
+            int64_t off = 0;
+            int at = 0;
+            for (int q = 0; q < n; ++q) {
+                if (D.scnt[q] > 0 || D.rcnt[q] > 0) { tell[2 * q] = off; tell[2 * q + 1] = (int64_t)m->haloRecv.n + at; ++at; }
+                off += D.rcnt[q];
+            }
+        }
+        comm::exchange_host(c, tell.data(), told.data(), 2 * sizeof(int64_t));
+        std::vector<int64_t> base, credit;
+        for (int32_t q : peers) { base.push_back(told[2 * (size_t)q]); credit.push_back(told[2 * (size_t)q + 1]); }
+        base.push_back(0); credit.push_back(0);
+        p2p_setup_ll<R>(st, counts.data(), base.data(), credit.data());
+    }
     double one = 1.0;
     comm::allreduce_f64(c, &one, 1, 0);                            // nobody pushes before everybody is mapped
 }
@@ -545,7 +568,7 @@ int mokab_decomp_setup(mokab_state *state, mokab_comm *c, const int64_t *send_co
 {
     return guarded([&] {
         MOKAB_REQUIRE(state && c && send_counts && recv_counts, "decomp_setup: NULL argument");
-        MOKAB_REQUIRE(halo_mode >= MOKAB_HALO_NCCL && halo_mode <= MOKAB_HALO_P2P_FUSED, "decomp_setup: unknown halo mode");
+        MOKAB_REQUIRE(halo_mode >= MOKAB_HALO_NCCL && halo_mode <= MOKAB_HALO_P2P_LL, "decomp_setup: unknown halo mode");
         state->ctx->bind();
         try {
             if (state->dtype == MOKAB_F64) decomp_setup<double>(state, c, send_counts, recv_counts, halo_mode, flags);

@@ -141,5 +141,149 @@ k_halo_wait_arrivals(int nsend, const int32_t *senders, const unsigned long long
 #endif
 }
 
+// ---- flag-in-data exchange (MOKAB_HALO_P2P_LL) --------------------------------------------------------------------------------
+// r02m's timeline of a 131 k-cell part: wait 1 -> boundary launch 7 -> k_halo_push 9 us -> ..., and what is left in the push kernel
+// is ordering, not data: one MEMBAR.SYS round trip per block, the ticket, a second fence and the tick of the peers' counters.
+// Here nothing is ordered at all.  A value crosses NVLink as 8-byte PACKETS {32 bits of the value, 32-bit exchange number}
+// (one packet per Float32, two per Float64): an aligned 8-byte store is single-copy atomic, so whoever reads a packet whose
+// upper half is the number it waits for has its lower half too -- NCCL's "LL" idea.  The sender's kernel just stores
+// (st.relaxed.sys) into a receive area in the neighbour's memory, slot = the entity's position in the neighbour's own receive
+// list; the neighbour's wait kernel polls one thread per slot and scatters the values into the halo slots of its state.
+// Exchange numbers live in device memory (one counter per side, bumped by the last block of every launch), so captured graphs
+// replay unchanged.  Slots are double-buffered by the parity of the exchange number: a rank starts exchange s + 2 only after
+// its wait of s + 1 has returned, which the neighbour feeds after ITS wait of s has consumed the packets of that parity.  That
+// needs every pair that exchanges anything to wait for each other, so besides the data every rank sends each peer one CREDIT
+// packet (number only) per exchange: a neighbour that receives without sending still holds its sender back.
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v)
+{
+#ifdef MOKAB_SIM
+    *p = v;
+#else
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#endif
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p)
+{
+#ifdef MOKAB_SIM
+    return *p;
+#else
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+#endif
+}
+template <class R>
+__host__ __device__ __forceinline__ unsigned long long ll_bits(R v)
+{
+    unsigned long long b = 0ull;
+    memcpy(&b, &v, sizeof(R));           // (little-endian: a Float32 fills the lower half)
+    return b;
+}
+template <class R>
+__host__ __device__ __forceinline__ R ll_value(unsigned long long b)
+{
+    R v;
+    memcpy(&v, &b, sizeof(R));
+    return v;
+}
+// slot `pos` of a receive area holds, for either parity of the exchange number, two packets (the second unused in Float32)
+__device__ __forceinline__ size_t ll_slot(int pos, unsigned int seq) { return ((size_t)pos * 2 + (seq & 1u)) * 2; }
+
+template <class R>
+struct LLPushArgs {
+    int n, nReal, nC;                    // items = the send list + one credit per peer; send list length; local cell count
+    const int32_t *src;                  // send list: local entity in the combined index space [cells | edges]
+    const int32_t *llDst;                // per item: its slot in the receiver's area
+    const uint8_t *slot;                 // per item: which receiver
+    const R *h, *u;                      // local stage output
+    unsigned long long *const *peerLL;   // per receiver: its receive area
+    unsigned int *seq, *done;            // exchanges issued so far; ticket counter (returns to 0 after every launch)
+};
+
+template <class R>
+__global__ void __launch_bounds__(256) k_halo_push_ll(const LLPushArgs<R> A)
+{
+    MOKAB_TRACE_BEGIN();
+    const unsigned int s = *(volatile unsigned int *)A.seq + 1u;
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if (k < A.n) {
+        unsigned long long bits = 0ull;
+        if (k < A.nReal) {
+            const int i = A.src[k];
+            bits = ll_bits<R>(i < A.nC ? A.h[i] : A.u[i - A.nC]);
+        }
+        unsigned long long *q = A.peerLL[A.slot[k]] + ll_slot(A.llDst[k], s);
+        const unsigned long long tag = (unsigned long long)s << 32;
+        st_relaxed_sys(q, (bits & 0xffffffffull) | tag);
+        if (sizeof(R) == 8) st_relaxed_sys(q + 1, (bits >> 32) | tag);
+    }
+    __syncthreads();                                       // every thread of the block has read the exchange number
+    if (threadIdx.x == 0) {
+        const unsigned int ticket = add_device(A.done, 1u);
+        if (ticket == gridDim.x - 1) { *A.done = 0u; *A.seq = s; }
+    }
+    MOKAB_TRACE_END(102u);
+}
+
+template <class R>
+struct LLWaitArgs {
+    int n, nReal, nC;                    // slots = the receive list + one credit per peer; receive list length; local cell count
+    const int32_t *idx;                  // receive list: where slot k goes in the combined index space [cells | edges]
+    const unsigned long long *ll;        // this rank's receive area
+    R *h, *u;                            // the stage output whose halo slots are filled
+    unsigned int *seq, *done;
+    int *error;
+    long long timeout_cycles;
+};
+
+// `ready` (simulated runtime: a host-side predicate retried by the stream scheduler; hardware: the spin below)
+template <class R>
+__host__ __device__ __forceinline__ bool ll_arrived(const unsigned long long *q, unsigned int s, unsigned long long *bits)
+{
+#if defined(__CUDA_ARCH__) && !defined(MOKAB_SIM)
+    const unsigned long long lo = ld_relaxed_sys(q), hi = sizeof(R) == 8 ? ld_relaxed_sys(q + 1) : ((unsigned long long)s << 32);
+#else
+    const unsigned long long lo = q[0], hi = sizeof(R) == 8 ? q[1] : ((unsigned long long)s << 32);
+#endif
+    if ((unsigned int)(lo >> 32) != s || (unsigned int)(hi >> 32) != s) return false;
+    *bits = (lo & 0xffffffffull) | (hi << 32);
+    return true;
+}
+
+template <class R>
+__global__ void __launch_bounds__(256) k_halo_wait_ll(const LLWaitArgs<R> A)
+{
+    MOKAB_TRACE_BEGIN();
+    const unsigned int s = *(volatile unsigned int *)A.seq + 1u;
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if (k < A.n) {
+        const unsigned long long *q = A.ll + ll_slot(k, s);
+        unsigned long long bits = 0ull;
+        bool ok = ll_arrived<R>(q, s, &bits);
+#ifndef MOKAB_SIM
+        const long long t0 = clock64();
+        while (!ok) {
+            if (*(volatile int *)A.error || clock64() - t0 > A.timeout_cycles) {   // a peer died or the schedules diverged: never hang the GPU
+                atomicExch(A.error, 1);
+                break;
+            }
+            __nanosleep(32);
+            ok = ll_arrived<R>(q, s, &bits);
+        }
+#endif
+        if (ok && k < A.nReal) {
+            const int i = A.idx[k];
+            if (i < A.nC) A.h[i] = ll_value<R>(bits);
+            else A.u[i - A.nC] = ll_value<R>(bits);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int ticket = add_device(A.done, 1u);
+        if (ticket == gridDim.x - 1) { *A.done = 0u; *A.seq = s; }
+    }
+    MOKAB_TRACE_END(103u);
+}
+
 }  // namespace p2p
 }  // namespace mokab

@@ -29,7 +29,8 @@ struct StateT {
     // arrival counters of the direct-store halo exchange -- lives in ONE allocation, so one CUDA IPC handle maps it
     // (several small cudaMalloc blocks can share a physical chunk, which IPC cannot map twice).
     DevBuf<unsigned char> slab;
-    size_t slabOff[9] = {};                // byte offsets: u0 u1 uP0 uP1 h0 h1 hP0 hP1 counters
+    size_t llSlots = 0;                    // slots of that receive area (0: the state was created before mokab_halo_setup)
+    size_t slabOff[10] = {};               // byte offsets: u0 u1 uP0 uP1 h0 h1 hP0 hP1 counters, receive area of the flag-in-data exchange
     DevBuf<R> u[2], h[2], ssh[2];          // two time levels; `cur` holds Prog.*[end]  (u, h: views into the slab)
     DevBuf<R> uP[2], hP[2];                // RK provisional ping-pong (views into the slab)
     DevBuf<R> hEdge, flux, divC, relVort, tendU, tendH, sshProv;
@@ -122,6 +123,16 @@ struct mokab_state {
         mokab::DevBuf<int32_t> startE, startC, dstE, dstC;
         mokab::DevBuf<uint8_t> slotE, slotC;
         mokab::DevBuf<unsigned char> stageDesc;              // 4 x fused::PushStage<R>
+        // flag-in-data exchange (MOKAB_HALO_P2P_LL; kernels_p2p.cuh)
+        std::vector<unsigned long long *> peerLLHost;        // [nrecv]: the receivers' receive areas (mapped)
+        std::vector<int64_t> peerLLSlots;                    //          and how many slots they have
+        mokab::DevBuf<unsigned long long *> peerLL;
+        mokab::DevBuf<int32_t> llDst;                        // per item of the send list (+ one credit per peer): its slot at the receiver
+        mokab::DevBuf<uint8_t> llSlot;                       //                                                   which receiver
+        mokab::DevBuf<unsigned int> llCtr;                   // [0] exchanges sent, [1] exchanges received, [2] / [3] the two ticket counters
+        unsigned long long *llArea = nullptr;                // this rank's receive area (in the slab)
+        int llSend = 0, llRecv = 0;                          // items sent / slots waited for per exchange (credits included)
+        bool llReady = false;
     } p2p;
     // domain-decomposed stepping inside the library (csrc/decomposed.cuh); set up by mokab_decomp_setup
     struct Decomp {
@@ -242,6 +253,10 @@ static void alloc_state(mokab_state *st)
         for (int i = 0; i < 4; ++i) { t->slabOff[i] = off; off += eb; }
         for (int i = 4; i < 8; ++i) { t->slabOff[i] = off; off += cb; }
         t->slabOff[8] = off; off += pad((size_t)kP2PCounters * sizeof(unsigned long long));
+        // MOKAB_HALO_P2P_LL: 32 bytes (two parities x two packets) per entry of the receive list + one credit slot per possible peer;
+        // sized from the halo lists the mesh has NOW (mokab_halo_setup before mokab_state_create, as every caller here does)
+        t->llSlots = m->halo_ready && K == 1 ? (size_t)m->haloRecv.n + (size_t)p2p::kMaxPeers : 0;
+        t->slabOff[9] = off; off += pad(t->llSlots * 32);
         t->slab.alloc(off); t->slab.zero(s);
         unsigned char *b = t->slab.p;
         t->u[0].view((R *)(b + t->slabOff[0]), K * m->nE); t->u[1].view((R *)(b + t->slabOff[1]), K * m->nE);
@@ -1641,7 +1656,8 @@ struct P2PBlob {
     int64_t pid;
     int32_t rank, dtype;
     void *base;                       // the state's slab
-    uint64_t off[9];                  // u0 u1 uP0 uP1 h0 h1 hP0 hP1 arrival counters
+    uint64_t off[10];                 // u0 u1 uP0 uP1 h0 h1 hP0 hP1 arrival counters, flag-in-data receive area
+    uint64_t llSlots;                 // slots of that area
     cudaIpcMemHandle_t handle;
 };
 
@@ -1675,7 +1691,8 @@ static void p2p_export(mokab_state *st, P2PBlob *b)
         x.exported = true;
     }
     b->base = t->slab.p;
-    for (int i = 0; i < 9; ++i) b->off[i] = t->slabOff[i];
+    for (int i = 0; i < 10; ++i) b->off[i] = t->slabOff[i];
+    b->llSlots = t->llSlots;
 #ifndef MOKAB_SIM
     MOKAB_CUDA(cudaIpcGetMemHandle(&b->handle, t->slab.p));
 #endif
@@ -1696,6 +1713,7 @@ static void p2p_setup(mokab_state *st, int rank, int nranks, const P2PBlob *blob
     x.rank = rank; x.nranks = nranks; x.nPush = total;
     x.recvRanks.assign(recv_ranks, recv_ranks + nrecv);
     x.sendRanks.assign(send_ranks, send_ranks + nsend);
+    x.peerLLHost.clear(); x.peerLLSlots.clear();
     // peer pointers: targets 0/1 = provisional buffers P0/P1, 2/3 = time levels 0/1
     std::vector<void *> pH((size_t)4 * std::max(nrecv, 1), nullptr), pU((size_t)4 * std::max(nrecv, 1), nullptr);
     std::vector<unsigned long long *> arr(std::max(nrecv, 1), nullptr);
@@ -1712,8 +1730,10 @@ static void p2p_setup(mokab_state *st, int rank, int nranks, const P2PBlob *blob
             x.opened.push_back(base);
 #endif
         }
-        void *ptr[9];
-        for (int k = 0; k < 9; ++k) ptr[k] = (unsigned char *)base + b.off[k];
+        void *ptr[10];
+        for (int k = 0; k < 10; ++k) ptr[k] = (unsigned char *)base + b.off[k];
+        x.peerLLHost.push_back((unsigned long long *)ptr[9]);
+        x.peerLLSlots.push_back((int64_t)b.llSlots);
         pU[0 * nrecv + i] = ptr[2]; pU[1 * nrecv + i] = ptr[3]; pU[2 * nrecv + i] = ptr[0]; pU[3 * nrecv + i] = ptr[1];
         pH[0 * nrecv + i] = ptr[6]; pH[1 * nrecv + i] = ptr[7]; pH[2 * nrecv + i] = ptr[4]; pH[3 * nrecv + i] = ptr[5];
         arr[i] = (unsigned long long *)ptr[8] + rank;
@@ -1864,6 +1884,93 @@ static void p2p_wait(mokab_state *st, cudaStream_t stream)
                     (unsigned long long *)x.expect.p, (int *)x.error.p, p2p_timeout_cycles());
     MOKAB_CUDA(cudaGetLastError());
 #endif
+    ctx->launches++;
+}
+
+// ---- flag-in-data exchange (MOKAB_HALO_P2P_LL) ---------------------------------------------------------------------------
+// after p2p_setup (peers mapped): where this rank's items land at every receiver.  recv_base[i] = the first slot of this
+// rank's segment in receiver i's receive list, credit_slot[i] = the slot receiver i keeps for this rank's credit packet.
+template <class R>
+static void p2p_setup_ll(mokab_state *st, const int64_t *counts, const int64_t *recv_base, const int64_t *credit_slot)
+{
+    mokab_ctx *ctx = st->ctx; const mokab_mesh *m = st->mesh;
+    mokab_state::P2P &x = st->p2p;
+    StateT<R> *t = typed<R>(st);
+    MOKAB_REQUIRE(x.ready, "p2p_setup_ll: call p2p_setup first");
+    const int npeer = (int)x.recvRanks.size();
+    MOKAB_REQUIRE(x.sendRanks == x.recvRanks, "p2p_setup_ll: the peer relation must be symmetric");
+    MOKAB_REQUIRE(t->llSlots >= (size_t)m->haloRecv.n + (size_t)npeer,
+                  "MOKAB_HALO_P2P_LL: the state has no receive area (create the state after mokab_halo_setup; single-level states)");
+    std::vector<int32_t> dst;
+    std::vector<uint8_t> slot;
+    for (int i = 0; i < npeer; ++i)
+        for (int64_t j = 0; j < counts[i]; ++j) { dst.push_back((int32_t)(recv_base[i] + j)); slot.push_back((uint8_t)i); }
+    MOKAB_REQUIRE((int64_t)dst.size() == (int64_t)m->haloSend.n, "p2p_setup_ll: counts do not add up to the send list");
+    for (int i = 0; i < npeer; ++i) {
+        MOKAB_REQUIRE(credit_slot[i] >= 0 && credit_slot[i] < x.peerLLSlots[i] && recv_base[i] + counts[i] <= x.peerLLSlots[i],
+                      "p2p_setup_ll: a slot lies outside the receiver's area");
+        dst.push_back((int32_t)credit_slot[i]); slot.push_back((uint8_t)i);
+    }
+    x.llSend = (int)dst.size(); x.llRecv = (int)m->haloRecv.n + npeer;
+    if (dst.empty()) { dst.push_back(0); slot.push_back(0); }
+    std::vector<unsigned long long *> pl(x.peerLLHost.begin(), x.peerLLHost.end());
+    if (pl.empty()) pl.push_back(nullptr);
+    x.llDst.upload(dst, ctx->stream); x.llSlot.upload(slot, ctx->stream); x.peerLL.upload(pl, ctx->stream);
+    x.llCtr.alloc(4); x.llCtr.zero(ctx->stream);
+    x.llArea = (unsigned long long *)(t->slab.p + t->slabOff[9]);        // zeroed with the slab: exchange number 0 = nothing yet
+    MOKAB_CUDA(cudaStreamSynchronize(ctx->stream));
+    x.llReady = true;
+}
+
+template <class R>
+static void p2p_push_ll(mokab_state *st, int stage, cudaStream_t stream)
+{
+    mokab_ctx *ctx = st->ctx; const mokab_mesh *m = st->mesh;
+    mokab_state::P2P &x = st->p2p;
+    MOKAB_REQUIRE(x.llReady, "halo exchange (MOKAB_HALO_P2P_LL): not set up");
+    if (x.llSend == 0) return;
+    cudaStream_t s = stream ? stream : ctx->stream;
+    R *u, *h;
+    stage_output<R>(st, stage, &u, &h);
+    p2p::LLPushArgs<R> A;
+    A.n = x.llSend; A.nReal = (int)m->haloSend.n; A.nC = (int)m->nC; A.src = m->haloSend.p; A.llDst = x.llDst.p; A.slot = x.llSlot.p;
+    A.h = h; A.u = u; A.peerLL = (unsigned long long *const *)x.peerLL.p; A.seq = x.llCtr.p; A.done = x.llCtr.p + 2;
+    MOKAB_LAUNCH_ON(p2p::k_halo_push_ll<R>, nblk(A.n), 256, s, A);
+    MOKAB_CUDA(cudaGetLastError());
+    ctx->launches++;
+}
+
+template <class R>
+static void p2p_wait_ll(mokab_state *st, int stage, cudaStream_t stream)
+{
+    mokab_ctx *ctx = st->ctx; const mokab_mesh *m = st->mesh;
+    mokab_state::P2P &x = st->p2p;
+    MOKAB_REQUIRE(x.llReady, "halo exchange (MOKAB_HALO_P2P_LL): not set up");
+    if (x.llRecv == 0) return;
+    cudaStream_t s = stream ? stream : ctx->stream;
+    R *u, *h;
+    stage_output<R>(st, stage, &u, &h);
+    p2p::LLWaitArgs<R> A;
+    A.n = x.llRecv; A.nReal = (int)m->haloRecv.n; A.nC = (int)m->nC; A.idx = m->haloRecv.p; A.ll = x.llArea; A.h = h; A.u = u;
+    A.seq = x.llCtr.p + 1; A.done = x.llCtr.p + 3; A.error = x.error.p; A.timeout_cycles = p2p_timeout_cycles();
+#ifdef MOKAB_SIM
+    // a spinning kernel cannot run on a simulator that executes kernels to completion: the same predicate becomes a stream
+    // operation that is retried until it holds, then the (non-spinning) kernel unpacks
+    {
+        const unsigned long long *ll = x.llArea;
+        const unsigned int *seq = x.llCtr.p + 1;
+        const int n = x.llRecv;
+        mokab_sim::enqueue_try(s, "p2p::k_halo_wait_ll", [=]() {
+            const unsigned int want = *seq + 1u;
+            unsigned long long bits;
+            for (int k = 0; k < n; ++k)
+                if (!p2p::ll_arrived<R>(ll + p2p::ll_slot(k, want), want, &bits)) return false;
+            return true;
+        });
+    }
+#endif
+    MOKAB_LAUNCH_ON(p2p::k_halo_wait_ll<R>, nblk(A.n), 256, s, A);
+    MOKAB_CUDA(cudaGetLastError());
     ctx->launches++;
 }
 

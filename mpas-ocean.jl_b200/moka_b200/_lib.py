@@ -20,7 +20,7 @@ CELLS, EDGES, VERTICES = range(3)
 RK4_FUSED, RK4_UNFUSED = 0, 1
 PART_ALL, PART_INTERIOR, PART_BOUNDARY, PART_BOUNDARY_PUSH, PART_ALL_PUSH = 0, 1, 2, 3, 4
 MESH_RENUMBER, MESH_EXPLICIT_EOE, MESH_KEEP_WIDTHS, MESH_EDGES_BY_CELL = 1, 2, 4, 8
-HALO_NCCL, HALO_P2P, HALO_P2P_FUSED = 0, 1, 2
+HALO_NCCL, HALO_P2P, HALO_P2P_FUSED, HALO_P2P_LL = 0, 1, 2, 3
 DECOMP_NO_OVERLAP, DECOMP_NO_GRAPH = 1, 2
 COMM_ID_BYTES = 128
 

@@ -140,7 +140,7 @@ class Communicator:
             self.handle = None
 
 
-HALO_MODES = {"nccl": L.HALO_NCCL, "p2p": L.HALO_P2P, "p2p_fused": L.HALO_P2P_FUSED}
+HALO_MODES = {"nccl": L.HALO_NCCL, "p2p": L.HALO_P2P, "p2p_fused": L.HALO_P2P_FUSED, "p2p_ll": L.HALO_P2P_LL}
 
 
 class DecomposedModel:
@@ -157,7 +157,8 @@ class DecomposedModel:
                  graph=False, runtime=None, halo="nccl", comm: Communicator | None = None):
         if halo not in HALO_MODES:
             raise api.MokaError("DecomposedModel: halo must be 'nccl' (packed NCCL send/recv), 'p2p' (direct peer stores, push and wait "
-                                "kernels) or 'p2p_fused' (direct peer stores from inside the boundary launch)")
+                                "kernels), 'p2p_fused' (direct peer stores from inside the boundary launch) or 'p2p_ll' (flag-in-data "
+                                "packets into the peers' receive areas)")
         self.halo_mode = halo
         self.rt = runtime if runtime is not None else TorchRuntime(device_index, group)
         self.loc, self.backend, self.overlap, self.use_graph = loc, backend, overlap, graph
@@ -553,7 +554,8 @@ def bench_main(args, rank, world, local):
         algo_per_launch = per_cell_step / 4.0 * loc["nCellsOwned"]
         achieved = algo_per_launch / ((ms * 1e-3) / (4 * steps_timed)) / 1e9
         halo_txt = {"nccl": "NCCL send/recv inside libmoka_b200.so", "p2p": "direct peer stores + arrival counters (push / wait kernels)",
-                    "p2p_fused": "direct peer stores from inside the boundary launch"}[model.halo_mode]
+                    "p2p_fused": "direct peer stores from inside the boundary launch",
+                    "p2p_ll": "flag-in-data packets into the peers' receive areas (no fence, no counter)"}[model.halo_mode]
         print(json.dumps({
             "metric": "RK4 cell-steps/sec", "value": value, "unit": "cell-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / steps_timed, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype,

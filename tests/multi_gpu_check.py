@@ -36,7 +36,8 @@ def main():
     cases = [(True, False, "nccl", "RungeKutta4"), (False, False, "nccl", "RungeKutta4"), (True, True, "nccl", "RungeKutta4"),
              (True, False, "p2p", "RungeKutta4"), (True, True, "p2p", "RungeKutta4"), (True, False, "p2p_fused", "RungeKutta4"),
              (True, True, "p2p_fused", "RungeKutta4"), (True, False, "nccl", "ForwardEuler"), (False, False, "nccl", "ForwardEuler"),
-             (True, True, "nccl", "ForwardEuler")]
+             (True, True, "nccl", "ForwardEuler"),
+             (True, False, "p2p_ll", "RungeKutta4"), (True, True, "p2p_ll", "RungeKutta4"), (False, False, "p2p_ll", "RungeKutta4")]   # flag-in-data packets
     if os.environ.get("MOKAB_CHECK_HALO"):
         cases = [c for c in cases if c[2] in os.environ["MOKAB_CHECK_HALO"].split(",")]
     for overlap, graph, halo, stepper in cases:
@@ -59,7 +60,7 @@ def main():
             m0 = float(np.sum(m["areaCell"] * om.layerThickness[1]))
             errs.append(((overlap, graph, halo, stepper), e, abs(mass - m0) / m0, status))
     # reverse mode on the decomposed mesh: J = sum ssh^2 after 6 steps and dJ/d(initial state) against the adjoint oracle
-    for halo, graph, stepper in (("nccl", True, "RungeKutta4"), ("p2p", False, "RungeKutta4"), ("nccl", True, "ForwardEuler")):
+    for halo, graph, stepper in (("nccl", True, "RungeKutta4"), ("p2p", False, "RungeKutta4"), ("nccl", True, "ForwardEuler"), ("p2p_ll", True, "RungeKutta4")):
         if os.environ.get("MOKAB_CHECK_HALO") and halo not in os.environ["MOKAB_CHECK_HALO"].split(","):
             continue
         model = multi_gpu.DecomposedModel(loc, multi_gpu.local_state(loc, *state), backend, local, graph=graph, halo=halo, runtime=rt, comm=comm)

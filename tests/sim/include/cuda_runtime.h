@@ -144,6 +144,7 @@ unsigned char *dynamic_smem();
 static inline bool is_coop_name(const char *kernel)
 {
     return __builtin_strstr(kernel, "reduce::k_") != nullptr || __builtin_strstr(kernel, "k_halo_push") != nullptr ||
+           __builtin_strstr(kernel, "k_halo_wait_ll") != nullptr ||
            (__builtin_strstr(kernel, "k_rk_stage") != nullptr && __builtin_strstr(kernel, ", true>") != nullptr) ||   // the PUSH variant
            __builtin_strstr(kernel, "k_rk_stage_tma") != nullptr;                                                    // the TMA variant
 }

@@ -30,6 +30,10 @@ def label(kind: int) -> str:
         return "halo push"
     if kind == 101:
         return "halo wait"
+    if kind == 102:
+        return "push (flag-in-data)"
+    if kind == 103:
+        return "wait + unpack (f-i-d)"
     if kind == 110:
         return "pack"
     if kind == 111:
@@ -65,7 +69,7 @@ def main():
     from moka_b200 import multi_gpu
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="igw512", choices=sorted(bench.WORKLOADS))
-    ap.add_argument("--halo", default="p2p", choices=["nccl", "p2p", "p2p_fused"])
+    ap.add_argument("--halo", default="p2p", choices=["nccl", "p2p", "p2p_fused", "p2p_ll"])
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--dtype", default="f64")
     ap.add_argument("--no-graph", dest="no_graph", action="store_true")
