@@ -326,7 +326,8 @@ def main():
     ap.add_argument("--seeds", type=int, default=2)
     ap.add_argument("--halo", default="nccl,p2p,p2p_fused",
                     help="halo exchange paths to check: the packed all-to-all, the direct peer stores (push / wait kernels), the "
-                         "direct peer stores from inside the boundary launch")
+                         "direct peer stores from inside the boundary launch; p2p_ll (flag-in-data packets) has its own short matrix "
+                         "unless it is listed here")
     ap.add_argument("--mutations", action="store_true", help="check that removing a cross-stream dependency of the schedule is detected")
     args = ap.parse_args()
     if args.mutations:
@@ -357,6 +358,19 @@ def main():
                         print(f"{kind}{nx} ranks={P} steps={calls} {halo_txt} {policy}{'/' + str(seed) if policy == 'random' else ''} "
                               f"{'overlap' if overlap else 'serial'} {'graph' if graph else 'stream'}: {'OK' if ok else 'MISMATCH'}"
                               f"{' [' + status + ']' if graph else ''} {time.time() - t0:.1f}s", flush=True)
+    # the flag-in-data exchange (MOKAB_HALO_P2P_LL): its own short matrix in the suite, the full one with --halo ...,p2p_ll
+    if "p2p_ll" not in args.halo.split(","):
+        for kind, nx, P, calls, overlap, graph in [("igw", 96, 8, [6], True, True), ("igw", 48, 4, [3, 6, 1, 4], True, False), ("kelvin", 48, 4, [5, 4], False, False)] + \
+                ([("voronoi", 24, 4, [5], True, True), ("igw", 128, 2, [3], True, True)] if args.cases != "suite" else []):
+            for policy in args.policies.split(","):
+                t0 = time.time()
+                ok, status = run(kind, nx, P, calls, overlap, graph, policy, 3, halo="p2p_ll")
+                bad += not ok
+                if graph and not status.startswith("validated"):
+                    bad += 1
+                    ok = False
+                print(f"{kind}{nx} ranks={P} steps={calls} p2p_ll {policy} {'overlap' if overlap else 'serial'} {'graph' if graph else 'stream'}: "
+                      f"{'OK' if ok else 'MISMATCH'}{' [' + status + ']' if graph else ''} {time.time() - t0:.1f}s", flush=True)
     # the reference's live stepper, ForwardEuler, on the decomposed mesh (packed exchange, two messages per step)
     if "nccl" in args.halo.split(","):
         for kind, nx, P, calls in [("igw", 96, 8, [5]), ("kelvin", 48, 4, [3, 4]), ("igw", 128, 2, [1, 2])] + ([("voronoi", 24, 4, [5])] if args.cases != "suite" else []):

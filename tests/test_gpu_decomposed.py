@@ -316,7 +316,7 @@ class _SoloRuntime:
 
 
 @pytest.mark.parametrize("halo,graph,stepper", [("nccl", True, "RungeKutta4"), ("nccl", False, "RungeKutta4"), ("p2p_fused", True, "RungeKutta4"),
-                                                ("nccl", True, "ForwardEuler")])
+                                                ("nccl", True, "ForwardEuler"), ("p2p_ll", True, "RungeKutta4")])
 def test_in_library_decomposed_entry_points_with_one_rank(backend, halo, graph, stepper):
     """mokab_comm_init / mokab_decomp_setup / mokab_timestep_*_decomposed (csrc/decomposed.cuh) on a communicator of ONE rank:
     the real NCCL initialisation, the halo stream fork / join, the captured 1- and 2-step graphs for both time-level parities
