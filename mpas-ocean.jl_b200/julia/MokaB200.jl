@@ -53,6 +53,9 @@ const LAYER_THICKNESS_EDGE, THICKNESS_FLUX, VELOCITY_DIV_CELL, RELATIVE_VORTICIT
 const TEND_NORMAL_VELOCITY, TEND_LAYER_THICKNESS = Cint(10), Cint(11)
 const D_SSH, D_NORMAL_VELOCITY, D_LAYER_THICKNESS = Cint(12), Cint(13), Cint(14)
 const SUM_SSH2 = Cint(0)
+# halo exchange of a domain-decomposed run (include/moka_b200.h): packed ncclSend/ncclRecv, direct peer stores (push / wait kernels),
+# direct peer stores from inside the boundary launch, flag-in-data packets into the peers' receive areas
+const HALO_NCCL, HALO_P2P, HALO_P2P_FUSED, HALO_P2P_LL = Cint(0), Cint(1), Cint(2), Cint(3)
 const RK4_FUSED = Cint(0)
 const MESH_RENUMBER = UInt32(1)
 
@@ -349,7 +352,11 @@ function autodiff_reverse_run_loop!(d_Prog::PrognosticVars, timestep, Prog::B200
     check(ccall((:mokab_tape_begin, libmoka), Cint, (Ptr{Cvoid}, Int64), bnd.state, nsteps))
     step!(bnd, Stepper, seconds(timestep), nsteps)
     r = Ref{Cdouble}(0.0)
-    check(ccall((:mokab_reduce, libmoka), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}), bnd.state, SUM_SSH2, r))
+    if bnd.comm == C_NULL
+        check(ccall((:mokab_reduce, libmoka), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}), bnd.state, SUM_SSH2, r))
+    else    # decomposed state (collective): the tape was recorded by mokab_timestep_*_decomposed, the sweep exchanges its own halo copies
+        check(ccall((:mokab_reduce_decomposed, libmoka), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}), bnd.state, SUM_SSH2, r))
+    end
     check(ccall((:mokab_adjoint_seed, libmoka), Cint, (Ptr{Cvoid}, Cint), bnd.state, SUM_SSH2))
     if Stepper === ForwardEuler
         check(ccall((:mokab_adjoint_forward_euler, libmoka), Cint, (Ptr{Cvoid},), bnd.state))
@@ -384,7 +391,8 @@ end
 # are the halo lists in the combined [cells | edges] index space, ordered by rank, send_counts / recv_counts how many entries
 # go to / come from every rank.
 function decompose!(Prog::B200Prog, mesh::Mesh, comm::Ptr{Cvoid}, nCellsOwned, nEdgesOwned,
-                    send_idx::Vector{Int32}, recv_idx::Vector{Int32}, send_counts::Vector{Int64}, recv_counts::Vector{Int64}; Diag = nothing, Tend = nothing)
+                    send_idx::Vector{Int32}, recv_idx::Vector{Int32}, send_counts::Vector{Int64}, recv_counts::Vector{Int64};
+                    Diag = nothing, Tend = nothing, halo_mode::Cint = HALO_P2P)
     haskey(BINDINGS, Prog) && error("decompose!: the state is already on the device")
     b = KA.get_backend(Prog.ssh[end])
     m = create_mesh(b, mesh; nCellsOwned = nCellsOwned, nEdgesOwned = nEdgesOwned)
@@ -399,7 +407,7 @@ function decompose!(Prog::B200Prog, mesh::Mesh, comm::Ptr{Cvoid}, nCellsOwned, n
         attach!(bnd, a, f; upload = true)
     end
     check(ccall((:mokab_decomp_setup, libmoka), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Cint, UInt32),
-                bnd.state, comm, send_counts, recv_counts, 0, 0))                                # MOKAB_HALO_NCCL, overlap + graphs
+                bnd.state, comm, send_counts, recv_counts, halo_mode, 0))                        # flags 0: overlap + captured graphs
     bind!(Prog, mesh; Diag = Diag, Tend = Tend)
 end
 
