@@ -346,7 +346,8 @@ enum { MOKAB_HALO_NCCL = 0,       /* pack -> ncclSend/ncclRecv per neighbour (on
        MOKAB_HALO_P2P_FUSED = 2,  /* the same stores issued by the boundary blocks themselves (MOKAB_PART_BOUNDARY_PUSH)            */
        MOKAB_HALO_P2P_LL = 3      /* flag-in-data: every value travels as 8-byte {32 data bits, 32-bit exchange number} packets into a
                                      receive area of the neighbour (CUDA IPC), whose wait kernel polls the packets and unpacks them --
-                                     no fence, no counter on the sending side (kernels_p2p.cuh)                                      */ };
+                                     no fence, no counter on the sending side (kernels_p2p.cuh); also carries ForwardEuler's two
+                                     messages per step and the halo copies of the reverse sweep                                     */ };
 enum { MOKAB_DECOMP_NO_OVERLAP = 1u, /* exchange after each whole stage on one stream (diagnostic)                                   */
        MOKAB_DECOMP_NO_GRAPH = 2u    /* launch every step from the host instead of replaying captured 1- / 2-step graphs (diagnostic) */ };
 int  mokab_comm_get_unique_id(void *id_out);

@@ -129,7 +129,8 @@ static void decomp_enqueue_fe(mokab_state *st, double dt, int64_t nsteps)
     mokab_state::Decomp &D = st->dec;
     cudaStream_t compute = st->ctx->stream;
     if (nsteps <= 0) return;
-    MOKAB_REQUIRE(D.mode == MOKAB_HALO_NCCL, "timestep_forward_euler_decomposed: ForwardEuler steps use the packed exchange (MOKAB_HALO_NCCL)");
+    MOKAB_REQUIRE(D.mode == MOKAB_HALO_NCCL || D.mode == MOKAB_HALO_P2P_LL,
+                  "timestep_forward_euler_decomposed: ForwardEuler steps use the packed exchange (MOKAB_HALO_NCCL) or the flag-in-data one (MOKAB_HALO_P2P_LL)");
     if (!D.overlap()) {
         for (int64_t i = 0; i < nsteps; ++i) {
             run_fe_stage(st, dt, MOKAB_PART_ALL, compute);

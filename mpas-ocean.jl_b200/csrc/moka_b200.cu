@@ -1132,12 +1132,19 @@ static void halo_pack(mokab_state *st, int stage, void *buf, cudaStream_t stream
 
 // Halo copies of an (edge array, cell array) pair that is not a stage output -- the stage states and the adjoint variables
 // of the reverse sweep on a decomposed mesh -- through the packed exchange of mokab_decomp_setup, on the context's stream.
+template <class R> static void p2p_push_ll_arrays(mokab_state *st, const R *u, const R *h, cudaStream_t stream);
+template <class R> static void p2p_wait_ll_arrays(mokab_state *st, R *u, R *h, cudaStream_t stream);
 template <class R>
 static void halo_exchange_arrays(mokab_state *st, R *u, R *h)
 {
     mokab_state::Decomp &D = st->dec;
     mokab_ctx *ctx = st->ctx; const mokab_mesh *m = st->mesh;
     cudaStream_t s = ctx->stream;
+    if (D.mode == MOKAB_HALO_P2P_LL) {   // flag-in-data packets carry values, not addresses: any array pair goes over them
+        p2p_push_ll_arrays<R>(st, u, h, s);
+        p2p_wait_ll_arrays<R>(st, u, h, s);
+        return;
+    }
     const int ns = (int)m->haloSend.n, nr = (int)m->haloRecv.n;
     if (ns) {
         k_halo_pack<R><<<nblk(ns), 256, 0, s>>>(ns, (int)m->nC, m->haloSend.p, (const R *)h, (const R *)u, (R *)D.sendBuf.p);
@@ -1922,16 +1929,15 @@ static void p2p_setup_ll(mokab_state *st, const int64_t *counts, const int64_t *
     x.llReady = true;
 }
 
+// (any (edge array, cell array) pair: the packets carry values, not addresses -- the receiver scatters into ITS arrays)
 template <class R>
-static void p2p_push_ll(mokab_state *st, int stage, cudaStream_t stream)
+static void p2p_push_ll_arrays(mokab_state *st, const R *u, const R *h, cudaStream_t stream)
 {
     mokab_ctx *ctx = st->ctx; const mokab_mesh *m = st->mesh;
     mokab_state::P2P &x = st->p2p;
     MOKAB_REQUIRE(x.llReady, "halo exchange (MOKAB_HALO_P2P_LL): not set up");
     if (x.llSend == 0) return;
     cudaStream_t s = stream ? stream : ctx->stream;
-    R *u, *h;
-    stage_output<R>(st, stage, &u, &h);
     p2p::LLPushArgs<R> A;
     A.n = x.llSend; A.nReal = (int)m->haloSend.n; A.nC = (int)m->nC; A.src = m->haloSend.p; A.llDst = x.llDst.p; A.slot = x.llSlot.p;
     A.h = h; A.u = u; A.peerLL = (unsigned long long *const *)x.peerLL.p; A.seq = x.llCtr.p; A.done = x.llCtr.p + 2;
@@ -1941,15 +1947,21 @@ static void p2p_push_ll(mokab_state *st, int stage, cudaStream_t stream)
 }
 
 template <class R>
-static void p2p_wait_ll(mokab_state *st, int stage, cudaStream_t stream)
+static void p2p_push_ll(mokab_state *st, int stage, cudaStream_t stream)
+{
+    R *u, *h;
+    stage_output<R>(st, stage, &u, &h);
+    p2p_push_ll_arrays<R>(st, u, h, stream);
+}
+
+template <class R>
+static void p2p_wait_ll_arrays(mokab_state *st, R *u, R *h, cudaStream_t stream)
 {
     mokab_ctx *ctx = st->ctx; const mokab_mesh *m = st->mesh;
     mokab_state::P2P &x = st->p2p;
     MOKAB_REQUIRE(x.llReady, "halo exchange (MOKAB_HALO_P2P_LL): not set up");
     if (x.llRecv == 0) return;
     cudaStream_t s = stream ? stream : ctx->stream;
-    R *u, *h;
-    stage_output<R>(st, stage, &u, &h);
     p2p::LLWaitArgs<R> A;
     A.n = x.llRecv; A.nReal = (int)m->haloRecv.n; A.nC = (int)m->nC; A.idx = m->haloRecv.p; A.ll = x.llArea; A.h = h; A.u = u;
     A.seq = x.llCtr.p + 1; A.done = x.llCtr.p + 3; A.error = x.error.p; A.timeout_cycles = p2p_timeout_cycles();
@@ -1972,6 +1984,14 @@ static void p2p_wait_ll(mokab_state *st, int stage, cudaStream_t stream)
     MOKAB_LAUNCH_ON(p2p::k_halo_wait_ll<R>, nblk(A.n), 256, s, A);
     MOKAB_CUDA(cudaGetLastError());
     ctx->launches++;
+}
+
+template <class R>
+static void p2p_wait_ll(mokab_state *st, int stage, cudaStream_t stream)
+{
+    R *u, *h;
+    stage_output<R>(st, stage, &u, &h);
+    p2p_wait_ll_arrays<R>(st, u, h, stream);
 }
 
 // stand-alone operators on host arrays -------------------------------------------------------------------

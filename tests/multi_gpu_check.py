@@ -37,7 +37,8 @@ def main():
              (True, False, "p2p", "RungeKutta4"), (True, True, "p2p", "RungeKutta4"), (True, False, "p2p_fused", "RungeKutta4"),
              (True, True, "p2p_fused", "RungeKutta4"), (True, False, "nccl", "ForwardEuler"), (False, False, "nccl", "ForwardEuler"),
              (True, True, "nccl", "ForwardEuler"),
-             (True, False, "p2p_ll", "RungeKutta4"), (True, True, "p2p_ll", "RungeKutta4"), (False, False, "p2p_ll", "RungeKutta4")]   # flag-in-data packets
+             (True, False, "p2p_ll", "RungeKutta4"), (True, True, "p2p_ll", "RungeKutta4"), (False, False, "p2p_ll", "RungeKutta4"),
+             (True, True, "p2p_ll", "ForwardEuler")]   # flag-in-data packets
     if os.environ.get("MOKAB_CHECK_HALO"):
         cases = [c for c in cases if c[2] in os.environ["MOKAB_CHECK_HALO"].split(",")]
     for overlap, graph, halo, stepper in cases:

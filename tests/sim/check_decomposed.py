@@ -371,6 +371,14 @@ def main():
                     ok = False
                 print(f"{kind}{nx} ranks={P} steps={calls} p2p_ll {policy} {'overlap' if overlap else 'serial'} {'graph' if graph else 'stream'}: "
                       f"{'OK' if ok else 'MISMATCH'}{' [' + status + ']' if graph else ''} {time.time() - t0:.1f}s", flush=True)
+        # ... and what else rides on it: ForwardEuler's two messages per step, the halo copies of the reverse sweep
+        for policy in args.policies.split(","):
+            t0 = time.time()
+            ok, _ = run("kelvin", 48, 4, [3, 4], True, False, policy, 5, stepper="ForwardEuler", halo="p2p_ll")
+            ok2, (eu, eh) = run_adjoint("igw", 48, 4, 4, policy, 4, "p2p_ll", True)
+            bad += (not ok) + (not ok2)
+            print(f"p2p_ll {policy}: ForwardEuler kelvin48 ranks=4 {'OK' if ok else 'MISMATCH'}; reverse mode igw48 ranks=4 {'OK' if ok2 else 'MISMATCH'} "
+                  f"({eu:.1e} / {eh:.1e}) {time.time() - t0:.1f}s", flush=True)
     # the reference's live stepper, ForwardEuler, on the decomposed mesh (packed exchange, two messages per step)
     if "nccl" in args.halo.split(","):
         for kind, nx, P, calls in [("igw", 96, 8, [5]), ("kelvin", 48, 4, [3, 4]), ("igw", 128, 2, [1, 2])] + ([("voronoi", 24, 4, [5])] if args.cases != "suite" else []):
