@@ -135,10 +135,12 @@ def one_case(rng, backend):
                 problems.append(f"decomposed ForwardEuler {nparts} ranks")
         # and, now and then, the product's DecomposedModel itself: one host thread per rank, two streams per rank, in-stream
         # exchange, a random sequence of step() calls (graph replays from both parities), against the same single-domain bits
-        if rng.integers(0, 3) == 0:
+        if rng.integers(0, 2) == 0:
             calls = [int(x) for x in rng.integers(1, 5, size=int(rng.integers(1, 4)))]
             overlap, graph = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
-            fe = halo == "nccl" and int(m["nEdgesOnCell"].max()) <= 7 and bool(rng.integers(0, 2))
+            if rng.integers(0, 3) == 0:
+                halo = "p2p_ll"                                   # the flag-in-data exchange exists in the library's own schedule only
+            fe = halo in ("nccl", "p2p_ll") and int(m["nEdgesOnCell"].max()) <= 7 and bool(rng.integers(0, 2))
             step_type = mb.ForwardEuler if fe else mb.RungeKutta4
             locs = partition.decompose(md, nparts)
 
@@ -161,7 +163,76 @@ def one_case(rng, backend):
             mb.ocn_timestep(dt, ref, None, None, None, step_type, nsteps=sum(calls))
             if not (np.array_equal(gu2, ref.normalVelocity) and np.array_equal(gh2, ref.layerThickness)):
                 problems.append(f"DecomposedModel {nparts} ranks {halo} overlap={overlap} graph={graph} calls={calls} {step_type.__name__}")
-            desc += f" + threads {calls} overlap={overlap} graph={graph}{' ForwardEuler' if fe else ''}"
+            desc += f" + threads {calls} {halo} overlap={overlap} graph={graph}{' ForwardEuler' if fe else ''}"
+            # the reverse mode on the same decomposition (either stepper; ForwardEuler where its exchange exists)
+            if rng.integers(0, 2) == 0:
+                na = min(nsteps, 3)
+
+                def body_adj(r, comm):
+                    model = multi_gpu.DecomposedModel(locs[r], multi_gpu.local_state(locs[r], ssh, u, h), mb.B200(0), 0, overlap=overlap,
+                                                      graph=graph, runtime=simcuda.SimRuntime(comm, r), halo=halo)
+                    J = model.reverse_run_loop(dt, na, stepper=step_type)
+                    model.finish()
+                    g = tuple(np.array(a) for a in model.gradient()) + (np.array(model.gradient_ssh()),)
+                    model.close()
+                    return J, g
+
+                outs = simcuda.run_ranks(nparts, body_adj)
+                au, ah, as_ = np.full(m["nEdges"], np.nan), np.full(m["nCells"], np.nan), np.full(m["nCells"], np.nan)
+                for loc, (_, (ru, rh, rs)) in zip(locs, outs):
+                    au[loc["edgesGlobal"][:loc["nEdgesOwned"]]] = ru
+                    ah[loc["cellsGlobal"][:loc["nCellsOwned"]]] = rh
+                    as_[loc["cellsGlobal"][:loc["nCellsOwned"]]] = rs
+                if fe:
+                    Jo, ou, oh, os_, _ = A.gradient_sum_ssh2_fe(mo, ssh, u, h, dt, na)
+                    okA = rel(as_, os_) <= 1e-11
+                else:
+                    Jo, ou, oh = A.gradient_sum_ssh2(mo, u, h, dt, na)
+                    okA = True
+                okA = okA and rel(au, ou) <= 1e-11 and rel(ah, oh) <= 1e-11 and all(abs(o[0] - Jo) <= 1e-11 * abs(Jo) for o in outs)
+                if not okA:
+                    problems.append(f"decomposed reverse mode {nparts} ranks {halo} {step_type.__name__}")
+                desc += " + reverse mode"
+        # multi-level columns on the same decomposition (uniform f or not; compile-time or run-time row widths)
+        if rng.integers(0, 3) == 0:
+            import moka_oracle as O
+            K = int(rng.integers(2, 6))
+            frac = rng.uniform(0.5, 1.5, K)
+            frac /= frac.sum()
+            mk = dict(md)
+            OC.sign_index_fields(mk)
+            H = h - ssh
+            rest = np.outer(H, frac)
+            hk, uk = rest + np.outer(ssh, frac), np.outer(u, 1.0 + 0.1 * np.arange(K))
+            mk["restingThickness"], mk["nVertLevels"] = rest, K
+            locs_k = partition.decompose(mk, nparts)
+            graph_k = bool(rng.integers(0, 2))
+            nk = int(rng.integers(1, 4))
+
+            def body_k(r, comm):
+                model = multi_gpu.DecomposedModel(locs_k[r], multi_gpu.local_state(locs_k[r], ssh, uk, hk), mb.B200(0), 0, graph=graph_k,
+                                                  runtime=simcuda.SimRuntime(comm, r), halo=str(rng_halo))
+                model.step(dt, nk)
+                model.finish()
+                res = tuple(np.array(model.owned(f)) for f in ("normalVelocity", "layerThickness", "ssh"))
+                model.close()
+                return res
+
+            rng_halo = rng.choice(["nccl", "p2p", "p2p_ll"])
+            outs = simcuda.run_ranks(nparts, body_k)
+            ku, kh, ks = np.full((m["nEdges"], K), np.nan), np.full((m["nCells"], K), np.nan), np.full(m["nCells"], np.nan)
+            for loc, (ru, rh, rs) in zip(locs_k, outs):
+                ku[loc["edgesGlobal"][:loc["nEdgesOwned"]]] = ru
+                kh[loc["cellsGlobal"][:loc["nCellsOwned"]]] = rh
+                ks[loc["cellsGlobal"][:loc["nCellsOwned"]]] = rs
+            # against the single-domain library run (itself bit-identical to the oracle with a level axis where weights are unfolded)
+            mesh_k = mb.Mesh({**m, "restingThickness": rest, "nVertLevels": K}, backend)
+            ref = mb.PrognosticVars(ssh, uk, hk, 2, mesh_k)
+            mb.ocn_timestep(dt, ref, None, None, None, mb.RungeKutta4, nsteps=nk)
+            if not (np.array_equal(ku, np.asarray(ref.normalVelocity).reshape(m["nEdges"], K)) and
+                    np.array_equal(kh, np.asarray(ref.layerThickness).reshape(m["nCells"], K)) and np.array_equal(ks, ref.ssh)):
+                problems.append(f"multi-level ({K}) decomposed {nparts} ranks {rng_halo} graph={graph_k}")
+            desc += f" + {K} levels decomposed ({rng_halo})"
     return f"{desc}; {nsteps} steps; renumber={renumber}; {policy}", problems
 
 
