@@ -129,7 +129,8 @@ static void all_to_all(mokab_comm *c, cudaStream_t s, const void *send, void *re
 static void exchange_host(mokab_comm *c, const void *send, void *recv, size_t bytes)
 {
     const size_t total = bytes * (size_t)c->nranks;
-    if (c->bufS.n < total) { c->bufS.alloc(total); c->bufR.alloc(total); }
+    if (c->bufS.n < total) c->bufS.alloc(total);     // (each on its own: exchange_host_v sizes the two differently)
+    if (c->bufR.n < total) c->bufR.alloc(total);
     std::vector<int64_t> cnt((size_t)c->nranks, (int64_t)bytes);
     MOKAB_CUDA(cudaMemcpyAsync(c->bufS.p, send, total, cudaMemcpyHostToDevice, c->stream));
     all_to_all(c, c->stream, c->bufS.p, c->bufR.p, cnt.data(), cnt.data(), 1);

@@ -72,6 +72,8 @@ def make_case(rng):
 
 def one_case(rng, backend):
     kind, m, mo, (ssh, u, h), dt, desc = make_case(rng)
+    trace = (lambda *a: print("   ..", *a, flush=True)) if os.environ.get("FUZZ_TRACE") else (lambda *a: None)
+    trace(desc)
     policy = str(rng.choice(["fifo", "lazy", "others_first", "random"]))
     simcuda.set_policy(policy, int(rng.integers(1, 1 << 30)))
     uniform_f = float(np.ptp(m["fEdge"])) == 0.0
@@ -102,6 +104,7 @@ def one_case(rng, backend):
             and np.array_equal(pfe.ssh, ofe.ssh[1])):
         problems.append("ForwardEuler")
     # both adjoints
+    trace("adjoints")
     na = min(nsteps, 4)
     pa = mb.PrognosticVars(ssh, u, h, 2, mesh)
     d = mb.ocn_init_shadows(pa)
@@ -118,6 +121,7 @@ def one_case(rng, backend):
     # decomposition with ranks emulated in this process: the same bits as the single-domain fused run
     nparts = int(rng.integers(2, 10))
     halo = str(rng.choice(["nccl", "p2p", "p2p_fused"]))
+    trace("decomposition", nparts, halo)
     if m["nCells"] >= 12 * nparts:
         md = {k: v for k, v in m.items() if k not in ("edgesOnVertex", "cellsOnVertex", "verticesOnEdge", "kiteAreasOnVertex",
                                                       "areaTriangle", "verticesOnCell", "edgeSignOnVertex")}
@@ -142,6 +146,7 @@ def one_case(rng, backend):
                 halo = "p2p_ll"                                   # the flag-in-data exchange exists in the library's own schedule only
             fe = halo in ("nccl", "p2p_ll") and int(m["nEdgesOnCell"].max()) <= 7 and bool(rng.integers(0, 2))
             step_type = mb.ForwardEuler if fe else mb.RungeKutta4
+            trace("DecomposedModel", calls, halo, overlap, graph, step_type.__name__)
             locs = partition.decompose(md, nparts)
 
             def body(r, comm):
@@ -167,6 +172,7 @@ def one_case(rng, backend):
             # the reverse mode on the same decomposition (either stepper; ForwardEuler where its exchange exists)
             if rng.integers(0, 2) == 0:
                 na = min(nsteps, 3)
+                trace("reverse mode on the decomposition", na)
 
                 def body_adj(r, comm):
                     model = multi_gpu.DecomposedModel(locs[r], multi_gpu.local_state(locs[r], ssh, u, h), mb.B200(0), 0, overlap=overlap,
@@ -197,6 +203,7 @@ def one_case(rng, backend):
         if rng.integers(0, 3) == 0:
             import moka_oracle as O
             K = int(rng.integers(2, 6))
+            trace("multi-level columns on the decomposition", K)
             frac = rng.uniform(0.5, 1.5, K)
             frac /= frac.sum()
             mk = dict(md)
