@@ -187,6 +187,79 @@ def test_two_rank_gloo_forward_euler_matches_single_domain(tmp_path):
     assert np.array_equal(gs, prog["ssh"][-1])
 
 
+def _worker_reverse(rank, world, port, nx, nsteps, out_dir):
+    """The reverse sweep of RungeKutta4 over gloo ranks with the scatter-form adjoint oracle as the per-rank compute: plain halo
+    copies -- over the SAME send / receive lists as the forward exchange -- of the stage states, of kbar after every reversed
+    stage and of lambda after every reversed step are all a rank needs for the gradient on its owned entities (DESIGN.md
+    section 7; what mokab_adjoint_rk4 does on a decomposed state, independent of the CUDA code)."""
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path[:0] = [here, os.path.join(os.path.dirname(here), "mpas-ocean.jl_b200"), os.path.join(os.path.dirname(here), "oracle")]
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import adjoint_oracle as A
+    import moka_b200.planar_hex as ph
+    import moka_oracle_c as OC
+    from moka_b200 import multi_gpu
+    m = ph.periodic_hex(nx, nx, 1.0e7 / nx, with_dual=False)
+    OC.sign_index_fields(m)
+    ssh, u, h = O.InertialGravityWave(m).initial_state()
+    loc = partition.decompose(m, world)[rank]
+    OC.sign_index_fields(loc)
+    sidx, scnt, ridx, rcnt = partition.flat_halo(loc, world)
+    ex = multi_gpu.HaloExchanger(scnt, rcnt, torch.float64, "cpu")
+    nCl, no, ne = loc["nCells"], loc["nCellsOwned"], loc["nEdgesOwned"]
+    dt = 0.5 * (1.0e7 / nx) / np.sqrt(O.GRAVITY * 1000.0)
+    a, b = [dt / 2, dt / 2, dt], [dt / 6, dt / 3, dt / 3, dt / 6]
+
+    def exchange(uu, hh):
+        comb = np.concatenate([hh, uu])
+        comb[nCl + ne:] = np.nan                                          # what a rank does not own is whatever the exchange brings
+        comb[no:nCl] = np.nan
+        ex.send[:len(sidx)] = torch.from_numpy(comb[sidx])
+        ex.exchange()
+        comb[ridx] = ex.recv[:len(ridx)].numpy()
+        return comb[nCl:], comb[:nCl]
+
+    # the forward trajectory (not under test here: tests above) from the single-domain oracle, restricted to the local mesh
+    traj = A.run_forward(m, u, h, dt, nsteps)
+    lam_u = np.zeros(loc["nEdges"])
+    lam_h = 2.0 * (traj[-1][1] - O.resting_thickness_sum(m))[loc["cellsGlobal"]]
+    for n in range(nsteps - 1, -1, -1):
+        ys = [(yu[loc["edgesGlobal"]], yh[loc["cellsGlobal"]]) for yu, yh in A.rk4_stage_states(m, traj[n][0], traj[n][1], dt)]
+        out_u, out_h = lam_u.copy(), lam_h.copy()
+        kbu, kbh = b[3] * lam_u, b[3] * lam_h
+        for s in (3, 2, 1, 0):
+            ybu, ybh = A.tendencies_vjp(loc, ys[s][0], ys[s][1], kbu, kbh)
+            out_u, out_h = out_u + ybu, out_h + ybh
+            if s > 0:
+                kbu, kbh = exchange(b[s - 1] * lam_u + a[s - 1] * ybu, b[s - 1] * lam_h + a[s - 1] * ybh)
+        lam_u, lam_h = exchange(out_u, out_h)
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), gu=lam_u[:ne], gh=lam_h[:no], ce=loc["cellsGlobal"][:no], ee=loc["edgesGlobal"][:ne])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_reverse_sweep_with_plain_halo_copies_matches_single_domain(tmp_path, world):
+    import adjoint_oracle as A
+    import torch.multiprocessing as mp
+    nx, nsteps = 16, 3
+    mp.spawn(_worker_reverse, args=(world, _free_port(), nx, nsteps, str(tmp_path)), nprocs=world, join=True)
+    m = hex_mesh(nx)
+    ssh, u, h = O.InertialGravityWave(m).initial_state()
+    dt = 0.5 * (1.0e7 / nx) / np.sqrt(O.GRAVITY * 1000.0)
+    _, gu, gh = A.gradient_sum_ssh2(m, u, h, dt, nsteps)
+    au, ah = np.full(m["nEdges"], np.nan), np.full(m["nCells"], np.nan)
+    for r in range(world):
+        z = np.load(tmp_path / f"r{r}.npz")
+        au[z["ee"]], ah[z["ce"]] = z["gu"], z["gh"]
+    assert np.linalg.norm(au - gu) <= 1e-12 * np.linalg.norm(gu)          # (sums reassociated: not bit for bit)
+    assert np.linalg.norm(ah - gh) <= 1e-12 * np.linalg.norm(gh)
+
+
 def test_as_many_parts_as_cells_and_one_more():
     """One cell per part is the limit: every rank must own a cell (an empty rank would launch empty grids); beyond it the
     partitioner refuses with a message instead of failing somewhere inside numpy."""
