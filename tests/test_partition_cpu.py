@@ -187,6 +187,79 @@ def test_two_rank_gloo_forward_euler_matches_single_domain(tmp_path):
     assert np.array_equal(gs, prog["ssh"][-1])
 
 
+def _levels_case(nx, K):
+    m = dict(hex_mesh(nx, with_dual=False))
+    ssh, u, h = O.InertialGravityWave(m).initial_state()
+    frac = np.random.default_rng(K).uniform(0.5, 1.5, K)
+    frac /= frac.sum()
+    rest = np.outer(np.full(m["nCells"], 1000.0), frac)
+    m["restingThickness"], m["nVertLevels"] = rest, K
+    return m, np.ascontiguousarray(np.outer(u, 1.0 + 0.1 * np.arange(K)).T), np.ascontiguousarray((rest + np.outer(ssh, frac)).T)
+
+
+def _worker_levels(rank, world, port, nx, K, nsteps, out_dir):
+    """RungeKutta4 of a K-level state over gloo ranks with the numpy oracle (level axis by broadcasting) as the per-rank compute:
+    the halo copies of every level of (h, u) after each stage are all a rank needs -- the free surface of a halo cell follows
+    from its column (the library sends it as one more plane because its kernels form ssh for owned cells only)."""
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path[:0] = [here, os.path.join(os.path.dirname(here), "mpas-ocean.jl_b200"), os.path.join(os.path.dirname(here), "oracle")]
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import moka_oracle_c as OC
+    from moka_b200 import multi_gpu
+    m, uk, hk = _levels_case(nx, K)
+    OC.sign_index_fields(m)
+    loc = partition.decompose(m, world)[rank]
+    OC.sign_index_fields(loc)
+    sidx, scnt, ridx, rcnt = partition.flat_halo(loc, world)
+    ex = multi_gpu.HaloExchanger(scnt, rcnt, torch.float64, "cpu")
+    nCl, no, ne = loc["nCells"], loc["nCellsOwned"], loc["nEdgesOwned"]
+    dt = 0.5 * (1.0e7 / nx) / np.sqrt(O.GRAVITY * 1000.0)
+    a, b = [dt / 2, dt / 2, dt], [dt / 6, dt / 3, dt / 3, dt / 6]
+
+    def exchange(uu, hh):
+        uo, ho = np.empty_like(uu), np.empty_like(hh)
+        for k in range(K):
+            comb = np.concatenate([hh[k], uu[k]])
+            ex.send[:len(sidx)] = torch.from_numpy(comb[sidx])
+            ex.exchange()
+            comb[ridx] = ex.recv[:len(ridx)].numpy()
+            uo[k], ho[k] = comb[nCl:], comb[:nCl]
+        return uo, ho
+
+    u_cur, h_cur = uk[:, loc["edgesGlobal"]].copy(), hk[:, loc["cellsGlobal"]].copy()
+    for _ in range(nsteps):
+        u_pro, h_pro, u_new, h_new = u_cur.copy(), h_cur.copy(), u_cur.copy(), h_cur.copy()
+        for s in range(4):
+            tu, th = O.tendencies_consistent(loc, u_pro, h_pro)
+            if s < 3:
+                u_pro, h_pro = exchange(u_cur + a[s] * tu, h_cur + a[s] * th)
+            u_new, h_new = u_new + b[s] * tu, h_new + b[s] * th
+        u_cur, h_cur = exchange(u_new, h_new)
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), u=u_cur[:, :ne], h=h_cur[:, :no], ce=loc["cellsGlobal"][:no], ee=loc["edgesGlobal"][:ne])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_multilevel_matches_single_domain(tmp_path):
+    import torch.multiprocessing as mp
+    nx, K, nsteps, world = 16, 3, 3, 2
+    mp.spawn(_worker_levels, args=(world, _free_port(), nx, K, nsteps, str(tmp_path)), nprocs=world, join=True)
+    m, uk, hk = _levels_case(nx, K)
+    prog = O.new_state(m, np.zeros(m["nCells"]), uk, hk)
+    dt = 0.5 * (1.0e7 / nx) / np.sqrt(O.GRAVITY * 1000.0)
+    for _ in range(nsteps):
+        O.timestep_rk4(m, prog, dt)
+    gu, gh = np.full((K, m["nEdges"]), np.nan), np.full((K, m["nCells"]), np.nan)
+    for r in range(world):
+        z = np.load(tmp_path / f"r{r}.npz")
+        gu[:, z["ee"]], gh[:, z["ce"]] = z["u"], z["h"]
+    assert np.array_equal(gu, prog["normalVelocity"][-1]) and np.array_equal(gh, prog["layerThickness"][-1])     # same arithmetic per entity
+
+
 def _worker_reverse(rank, world, port, nx, nsteps, out_dir):
     """The reverse sweep of RungeKutta4 over gloo ranks with the scatter-form adjoint oracle as the per-rank compute: plain halo
     copies -- over the SAME send / receive lists as the forward exchange -- of the stage states, of kbar after every reversed
