@@ -397,9 +397,10 @@ def main():
     ap.add_argument("--no-overlap", dest="no_overlap", action="store_true", help="multi-GPU: exchange after each full stage")
     ap.add_argument("--no-graph", dest="no_graph", action="store_true", help="multi-GPU: do not capture steps into a CUDA graph")
     ap.add_argument("--halo", default="p2p", choices=["nccl", "p2p", "p2p_fused", "p2p_ll"],
-                    help="multi-GPU halo exchange: direct stores into the peers' memory with push / wait kernels (default: the "
-                         "fastest at N = 2 and N = 8, profiles/README.md r02c / r02e), packed NCCL send/recv, or direct stores "
-                         "from inside the boundary launch")
+                    help="multi-GPU halo exchange: direct stores into the peers' memory with push / wait kernels (default: measured "
+                         "at N = 2 and N = 8, profiles/README.md r02c / r02e), packed NCCL send/recv, direct stores from inside the "
+                         "boundary launch, or flag-in-data packets (p2p_ll: no fence on the sending side, +22 %% on 131 k-cell parts "
+                         "at N = 2, equal on large ones, r02p; not yet run at N = 8)")
     ap.add_argument("--explicit-eoe", dest="explicit_eoe", action="store_true",
                     help="ablation: read edgesOnEdge from memory instead of rebuilding it from edgesOnCell")
     ap.add_argument("--quick", action="store_true", help="profiling runs: no clock-sampling load loop, one e2e step")

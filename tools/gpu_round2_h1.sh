@@ -1,4 +1,5 @@
 #!/bin/bash
+# (As run for r02h at commit ff81503: the shared-memory flux variant it measures was removed afterwards -- 9 % slower.)
 # Round 2, GPU pass H1 (one GPU): A/B of the two latency-side changes written after r02g -- the thickness flux of a block's own
 # edges through shared memory ("stage_flux_smem") and programmatic dependent launch of the stage kernels ("stage_pdl") -- as
 # 40-step bursts and as >= 0.5 s sustained batches (the live bench is power-capped), on 2048x2048 in both precisions and on the

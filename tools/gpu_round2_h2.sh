@@ -1,4 +1,5 @@
 #!/bin/bash
+# (As run for r02i at commit 342f12a: coherent state loads have been the default build since; libmoka_b200_ldg.so is the read-only variant now.)
 # Round 2, GPU pass H2 (one GPU): (1) the per-launch choice between the two tuned stage kernels by the wave-quantisation model
 # ("stage_auto") against either kernel forced, on every BASELINE mesh size; (2) the build that reads the state through plain
 # coherent loads (libmoka_b200_coh.so) against the default, and programmatic dependent launch on it ("stage_pdl"; r02h showed the
