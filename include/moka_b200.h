@@ -168,8 +168,11 @@ int  mokab_state_create(mokab_ctx *ctx, const mokab_mesh *mesh, int dtype, mokab
  * static data read once per column -- and unfused; ForwardEuler as the reference's kernel sequence), mokab_reduce, and on
  * decomposed meshes mokab_timestep_rk4_decomposed (whole-part stage launches, ONE halo message of nVertLevels + 1 planes per
  * stage -- the levels of (layerThickness, normalVelocity) and the free surface --, packed exchange whatever the halo mode,
- * captured graphs) and mokab_reduce_decomposed.  Not supported: the reverse mode, the staged entry points, ForwardEuler on
- * decomposed meshes. */
+ * captured graphs) and mokab_reduce_decomposed; the reverse mode of RungeKutta4 on undecomposed meshes (mokab_tape_begin ...
+ * mokab_adjoint_rk4: the forward recompute is the column kernel, every adjoint stage the single-level gather kernel per level
+ * with the pressure term -- one gradient per column -- taken from the level sum of kbar_u; MOKAB_D_* fields are (nVertLevels, n)
+ * like the state's).  Not supported: the ForwardEuler reverse mode, the reverse mode on decomposed meshes, the staged entry
+ * points, ForwardEuler on decomposed meshes. */
 int  mokab_state_create_levels(mokab_ctx *ctx, const mokab_mesh *mesh, int dtype, int nVertLevels, mokab_state **out);
 int  mokab_state_levels(const mokab_state *state, int *nVertLevels);
 int  mokab_state_destroy(mokab_state *state);

@@ -43,6 +43,7 @@ struct AdjArgs {
     R *accU, *accH;           // lam, accumulated over the four stages
     R *kuOut, *kqOut;         // kbar of the previous stage (not written by LAST)
     R aPrev, bPrev, bThis;    // a_{s-1}, b_{s-1};  b_4 (FIRST only)
+    const R *kuP;             // ML launches only: kbar_u summed over the levels of the column (k_sum_levels), for the pressure term
 };
 
 // MODE: 0 = FIRST (RK stage 4: kbar = b_4 lam', acc = lam' + ybar), 1 = MIDDLE (stages 3, 2), 2 = LAST (stage 1)
@@ -53,7 +54,11 @@ struct AdjArgs {
 #ifndef MOKAB_ADJ_MINBLOCKS
 #define MOKAB_ADJ_MINBLOCKS 4
 #endif
-template <class R, int MODE, int S2TT, int ST>
+// ML = true: one LEVEL of a multi-level state per launch (the arrays of the arguments point at that level).  Coriolis and
+// thickness flux act level by level, so everything is the single-level kernel -- except the pressure gradient, which is ONE
+// term -g/dc (ssh2 - ssh1), ssh = sum_k h_k - H, shared by the levels of a column: its adjoint is formed from kuP, the level
+// sum of kbar_u, and goes to every level of hbar alike.
+template <class R, int MODE, int S2TT, int ST, bool ML = false>
 __global__ void __launch_bounds__(kThreads, MOKAB_BLOCKS_SCALED(MOKAB_ADJ_MINBLOCKS))
 k_rk_stage_adj(const AdjArgs<R> A)
 {
@@ -119,7 +124,7 @@ k_rk_stage_adj(const AdjArgs<R> A)
                 for (int i = 0; i < CH; ++i) {
                     const int e = ee[i0 + i] >= 0 ? (ee[i0 + i] >> 1) : 0;
                     cs[i] = __ldg(A.ce + e);
-                    kue[i] = ku(e);
+                    kue[i] = ML ? __ldg(A.kuP + e) : ku(e);
                     dd[i] = __ldg(A.dv + e);
                     uu[i] = __ldg(A.uY + e);
                     gg[i] = __ldg(A.gdc + e);
@@ -144,7 +149,7 @@ k_rk_stage_adj(const AdjArgs<R> A)
                 const int2 cs = __ldg(A.ce + e);
                 const bool masked = cs.x == cs.y;
                 const int other = cs.x == cc ? cs.y : cs.x;
-                const R kue = ku(e);
+                const R kue = ML ? __ldg(A.kuP + e) : ku(e);
                 const R G = __ldg(A.dv + e) * sgn * (masked ? qc : qc - kq(other));
                 yb += (masked ? R(1) : R(0.5)) * __ldg(A.uY + e) * G;
                 if (!masked) yb -= sgn * __ldg(A.gdc + e) * kue;
@@ -280,6 +285,26 @@ __global__ void __launch_bounds__(256) k_fold_dssh(int64_t n, R *__restrict__ ds
     const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (c < n) {
         dh[c] += dssh[c];
+        dssh[c] = R(0);
+    }
+}
+
+// multi-level states: out[e] = factor * sum_k in[k * n + e] (level order), and the seed on ssh folded into every level of d_h
+template <class R>
+__global__ void __launch_bounds__(256) k_sum_levels(int64_t n, int K, R factor, const R *__restrict__ in, R *__restrict__ out)
+{
+    const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (e >= n) return;
+    R s = in[e];
+    for (int k = 1; k < K; ++k) s += in[(size_t)k * n + e];
+    out[e] = factor * s;
+}
+template <class R>
+__global__ void __launch_bounds__(256) k_fold_dssh_levels(int64_t n, int K, R *__restrict__ dssh, R *__restrict__ dh)
+{
+    const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (c < n) {
+        for (int k = 0; k < K; ++k) dh[(size_t)k * n + c] += dssh[c];
         dssh[c] = R(0);
     }
 }

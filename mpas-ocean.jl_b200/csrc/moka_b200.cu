@@ -61,6 +61,7 @@ struct StateT {
     int tapeKind = 0;                       // 0 = empty, 1 = RungeKutta4 steps, 2 = ForwardEuler steps (never mixed)
     DevBuf<R> lamS[2], lamE[2], lamQ[2];    // ForwardEuler adjoint: adjoints of ssh / hEdge, invArea * (lamH + lamS)
     DevBuf<R> yU[3], yH[3];                 // y_2, y_3, y_4 of the step being reversed
+    DevBuf<R> yS[4], kuP;                   // multi-level states: ssh of y_1 ... y_4 (the column kernel gathers it); level sum of kbar_u
     DevBuf<R> kbU[2], kbH[2];               // kbar ping-pong (kbH carries invArea * kbar_h)
     DevBuf<R> lamU[2], lamH[2], dSsh;       // lam' / lam, swapped every reversed step; seed on ssh
     int lamCur = 0;
@@ -291,11 +292,16 @@ static void ensure_adj_state(mokab_state *st)
     if (t->adj_ready) return;
     const mokab_mesh *m = st->mesh;
     cudaStream_t s = st->ctx->stream;
-    for (int i = 0; i < 3; ++i) { t->yU[i].alloc(m->nE); t->yH[i].alloc(m->nC); }
+    const size_t K = (size_t)st->K;
+    for (int i = 0; i < 3; ++i) { t->yU[i].alloc(K * m->nE); t->yH[i].alloc(K * m->nC); }
     for (int i = 0; i < 2; ++i) {
-        t->kbU[i].alloc(m->nE); t->kbH[i].alloc(m->nC);
-        t->lamU[i].alloc(m->nE); t->lamU[i].zero(s);
-        t->lamH[i].alloc(m->nC); t->lamH[i].zero(s);
+        t->kbU[i].alloc(K * m->nE); t->kbH[i].alloc(K * m->nC);
+        t->lamU[i].alloc(K * m->nE); t->lamU[i].zero(s);
+        t->lamH[i].alloc(K * m->nC); t->lamH[i].zero(s);
+    }
+    if (K > 1) {
+        for (int i = 0; i < 4; ++i) t->yS[i].alloc(m->nC);
+        t->kuP.alloc(m->nE);
     }
     t->dSsh.alloc(m->nC); t->dSsh.zero(s);
     t->adj_ready = true;
@@ -1303,8 +1309,29 @@ static void run_rk4_fused_ml(mokab_state *st, double dt, int64_t nsteps)
     mokab_ctx *ctx = st->ctx;
     StateT<double> *t = st->d;
     MOKAB_REQUIRE(st->dtype == MOKAB_F64, "timestep_rk4: multi-level states are Float64");
-    MOKAB_REQUIRE(!t->taping, "timestep_rk4: the reverse mode records single-level states only");
+    if (t->taping) {
+        MOKAB_REQUIRE((int64_t)t->tapeDt.size() + nsteps <= t->tapeCap, "timestep_rk4: the tape is full (mokab_tape_begin max_steps)");
+        MOKAB_REQUIRE(t->tapeKind != 2, "timestep_rk4: the tape already holds ForwardEuler steps");
+        t->tapeKind = 1;
+    }
     if (nsteps <= 0) return;
+    if (t->taping) {   // record the state before every step (plain launches: the tape slot changes per step)
+        const mokab_mesh *m = st->mesh;
+        const size_t K = (size_t)st->K;
+        ensure_fused<double>(const_cast<mokab_mesh *>(m));
+        if (t->tapeH.n < (size_t)t->tapeCap * K * m->nC) t->tapeH.alloc((size_t)t->tapeCap * K * m->nC);
+        update_ssh(st, t->h[st->cur].p, t->ssh[st->cur].p);
+        for (int64_t i = 0; i < nsteps; ++i) {
+            const size_t k = t->tapeDt.size();
+            MOKAB_CUDA(cudaMemcpyAsync(t->tapeU.p + k * K * m->nE, t->u[st->cur].p, K * m->nE * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+            MOKAB_CUDA(cudaMemcpyAsync(t->tapeH.p + k * K * m->nC, t->h[st->cur].p, K * m->nC * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+            t->tapeDt.push_back(dt);
+            enqueue_rk4_step_ml(st, dt, st->cur);
+            st->cur = 1 - st->cur;
+        }
+        update_ssh(st, t->h[1 - st->cur].p, t->ssh[1 - st->cur].p);
+        return;
+    }
     // the stage kernels gather ssh of the state they read: make ssh[cur] what the current layerThickness implies (every later
     // step's ssh is written by the stage that produces its layerThickness)
     update_ssh(st, t->h[st->cur].p, t->ssh[st->cur].p);
@@ -1529,6 +1556,7 @@ static void adjoint_step(mokab_state *st, int64_t k)
     const int p = t->lamCur;
     B.lamU = t->lamU[p].p; B.lamH = t->lamH[p].p; B.accU = t->lamU[1 - p].p; B.accH = t->lamH[1 - p].p;
     B.bThis = (R)b[3];
+    B.kuP = nullptr;
     const int grid = m->fusedBlocks;
     for (int s = 4; s >= 1; --s) {
         B.uY = s == 1 ? u0 : t->yU[s - 2].p; B.hY = s == 1 ? h0 : t->yH[s - 2].p;
@@ -1559,13 +1587,80 @@ static void adjoint_step(mokab_state *st, int64_t k)
     t->lamCur = 1 - p;
 }
 
+// The same for a multi-level state (Float64, undecomposed): the forward recompute is the column kernel (three launches, ssh of
+// every stage state kept because the next stage's single pressure gradient gathers it); every adjoint stage is one launch of the
+// single-level kernel PER LEVEL -- Coriolis and thickness flux act level by level -- with the pressure term taken from the level
+// sum of kbar_u (k_sum_levels), since ssh = sum_k h_k - H couples the levels of a column.
+static void adjoint_step_ml(mokab_state *st, int64_t k)
+{
+    mokab_ctx *ctx = st->ctx; mokab_mesh *m = const_cast<mokab_mesh *>(st->mesh);
+    StateT<double> *t = st->d;
+    FusedMesh<double> &fm = fused_of<double>(m);
+    const int K = st->K;
+    const size_t nE = (size_t)m->nE, nC = (size_t)m->nC;
+    const double dt = t->tapeDt[k];
+    const double a[4] = {dt / 2.0, dt / 2.0, dt, 0.0};
+    const double b[4] = {dt / 6.0, dt / 3.0, dt / 3.0, dt / 6.0};
+    const double *u0 = t->tapeU.p + (size_t)k * K * nE, *h0 = t->tapeH.p + (size_t)k * K * nC;
+    update_ssh(st, h0, t->yS[0].p);                                    // ssh of y_1 = the taped state
+    fused::StageArgsML A;
+    A.nE = (int)nE; A.nC = (int)nC; A.K = K; A.nCown = (int)m->nCo;
+    A.ce = m->ce.p; A.eoe = m->eoeF.p; A.eoc = m->eocF.p; A.nEoE = m->nEoE.p; A.nEoC = m->nEoC.p; A.blkEdgeStart = m->blkEdgeStart.p;
+    A.gdc = fm.gdc.p; A.wf = fm.wf.p; A.dv = fm.dv.p; A.invArea = fm.invArea.p; A.H = fm.H.p;
+    A.uCur = u0; A.hCur = h0; A.uAcc = t->kbU[1].p; A.hAcc = t->kbH[1].p;          // (the accumulator output lands in a kbar buffer that is still free)
+    A.f0 = m->f0;
+    for (int s = 1; s <= 3; ++s) {
+        A.a = a[s - 1]; A.b = b[s - 1];
+        A.uOld = s == 1 ? u0 : t->yU[s - 2].p; A.hOld = s == 1 ? h0 : t->yH[s - 2].p; A.sshOld = t->yS[s - 1].p;
+        A.uOut = t->yU[s - 1].p; A.hOut = t->yH[s - 1].p; A.sshOut = t->yS[s].p;
+        if (s == 1) launch_stage_ml<1>(ctx, m, A); else launch_stage_ml<2>(ctx, m, A);
+    }
+    const int p = t->lamCur;
+    const bool hex = m->S2T == 10 && m->S == 6, hept = m->S2T == 12 && m->S == 7;
+    const int grid = m->fusedBlocks;
+    for (int s = 4; s >= 1; --s) {
+        const int mode = s == 4 ? 0 : s > 1 ? 1 : 2;
+        const double *kuIn = mode == 0 ? t->lamU[p].p : t->kbU[s & 1].p;
+        // level sum of this stage's kbar_u (FIRST: kbar = b_4 lam')
+        LAUNCH(ctx, adjoint::k_sum_levels<double>, nblk(m->nE), 256, m->nE, K, mode == 0 ? b[3] : 1.0, kuIn, t->kuP.p);
+        for (int lev = 0; lev < K; ++lev) {
+            const size_t oe = (size_t)lev * nE, oc = (size_t)lev * nC;
+            adjoint::AdjArgs<double> B;
+            B.nE = (int)nE; B.nC = (int)nC; B.nCown = (int)m->nCo; B.S2T = m->S2T; B.S = m->S;
+            B.ce = m->ce.p; B.eoeT = m->eoeT.p; B.eoc = m->eocF.p; B.nEoET = m->nEoET.p; B.nEoC = m->nEoC.p;
+            B.blkEdgeStart = m->blkEdgeStart.p;
+            B.gdc = fm.gdc.p; B.wfT = fm.wfT.p; B.dv = fm.dv.p; B.invArea = fm.invArea.p; B.H = fm.H.p;
+            B.lamU = t->lamU[p].p + oe; B.lamH = t->lamH[p].p + oc; B.accU = t->lamU[1 - p].p + oe; B.accH = t->lamH[1 - p].p + oc;
+            B.bThis = b[3];
+            B.uY = (s == 1 ? u0 : t->yU[s - 2].p) + oe; B.hY = (s == 1 ? h0 : t->yH[s - 2].p) + oc;
+            B.kuIn = t->kbU[s & 1].p + oe; B.kqIn = t->kbH[s & 1].p + oc;
+            B.kuOut = t->kbU[(s - 1) & 1].p + oe; B.kqOut = t->kbH[(s - 1) & 1].p + oc;
+            B.aPrev = s > 1 ? a[s - 2] : 0.0; B.bPrev = s > 1 ? b[s - 2] : 0.0;
+            B.kuP = t->kuP.p;
+#define MOKAB_ADJ_ML_LAUNCH(MODE)                                                                                              \
+    do {                                                                                                                       \
+        if (hex) adjoint::k_rk_stage_adj<double, MODE, 10, 6, true><<<grid, adjoint::kThreads, 0, ctx->stream>>>(B);          \
+        else if (hept) adjoint::k_rk_stage_adj<double, MODE, 12, 7, true><<<grid, adjoint::kThreads, 0, ctx->stream>>>(B);    \
+        else adjoint::k_rk_stage_adj<double, MODE, 0, 0, true><<<grid, adjoint::kThreads, 0, ctx->stream>>>(B);               \
+    } while (0)
+            if (mode == 0) MOKAB_ADJ_ML_LAUNCH(0);
+            else if (mode == 1) MOKAB_ADJ_ML_LAUNCH(1);
+            else MOKAB_ADJ_ML_LAUNCH(2);
+#undef MOKAB_ADJ_ML_LAUNCH
+            MOKAB_CUDA(cudaGetLastError());
+            ctx->launches++;
+        }
+    }
+    t->lamCur = 1 - p;
+}
+
 template <class R>
 static void tape_begin(mokab_state *st, int64_t max_steps)
 {
     StateT<R> *t = typed<R>(st);
     const mokab_mesh *m = st->mesh;
     if (t->tapeCap < max_steps) {
-        t->tapeU.alloc((size_t)max_steps * m->nE);
+        t->tapeU.alloc((size_t)max_steps * (size_t)st->K * m->nE);
         t->tapeH.release();                 // RungeKutta4 tapes only: allocated by the first recorded RK4 step (run_rk4_fused)
         t->tapeE.release();                 // ForwardEuler tapes only: allocated by fe_tape_record
         t->tapeCap = max_steps;
@@ -1585,6 +1680,13 @@ static void adjoint_seed(mokab_state *st, int which)
     FusedMesh<R> &fm = fused_of<R>(m);
     t->lamU[t->lamCur].zero(ctx->stream);
     t->lamH[t->lamCur].zero(ctx->stream);
+    if constexpr (sizeof(R) == 8) {
+        if (st->K > 1) {   // multi-level: ssh = (sum of the column) - H, from the current layerThickness
+            update_ssh(st, t->h[st->cur].p, t->ssh[st->cur].p);
+            LAUNCH(ctx, adjoint::k_seed_ssh2_array<R>, nblk(m->nC), 256, m->nC, (const R *)t->ssh[st->cur].p, t->dSsh.p);
+            return;
+        }
+    }
     if (t->tapeKind == 2)
         LAUNCH(ctx, adjoint::k_seed_ssh2_array<R>, nblk(m->nC), 256, m->nC, (const R *)t->ssh[st->cur].p, t->dSsh.p);
     else
@@ -1600,6 +1702,15 @@ static void adjoint_run(mokab_state *st)
     ensure_adjoint<R>(st);
     t->taping = false;
     t->tapeKind = 0;
+    if constexpr (sizeof(R) == 8) {
+        if (st->K > 1) {
+            MOKAB_REQUIRE(!st->dec.ready, "adjoint_rk4: multi-level states have no reverse mode on decomposed meshes");
+            LAUNCH(ctx, adjoint::k_fold_dssh_levels<R>, nblk(m->nC), 256, m->nC, st->K, t->dSsh.p, t->lamH[t->lamCur].p);
+            for (int64_t k = (int64_t)t->tapeDt.size() - 1; k >= 0; --k) adjoint_step_ml(st, k);
+            t->tapeDt.clear();
+            return;
+        }
+    }
     LAUNCH(ctx, adjoint::k_fold_dssh<R>, nblk(m->nC), 256, m->nC, t->dSsh.p, t->lamH[t->lamCur].p);
     if (st->dec.ready) halo_exchange_arrays<R>(st, t->lamU[t->lamCur].p, t->lamH[t->lamCur].p);   // the owners' seeds on the halo copies
     for (int64_t k = (int64_t)t->tapeDt.size() - 1; k >= 0; --k) adjoint_step<R>(st, k);
@@ -1613,6 +1724,7 @@ static void adjoint_run_fe(mokab_state *st)
     MOKAB_REQUIRE(st->dtype == MOKAB_F64, "adjoint_forward_euler: ForwardEuler is Float64 only (PrognosticVars.jl:91-93)");
     StateT<double> *t = st->d;
     MOKAB_REQUIRE(t->tapeKind != 1, "adjoint_forward_euler: the tape holds RungeKutta4 steps (use mokab_adjoint_rk4)");
+    MOKAB_REQUIRE(st->K == 1, "adjoint_forward_euler: single-level states only (the multi-level reverse mode is RungeKutta4)");
     ensure_adjoint<double>(st);
     FusedMesh<double> &fm = fused_of<double>(m);
     for (int i = 0; i < 2; ++i)
@@ -2415,6 +2527,7 @@ int mokab_timestep_forward_euler(mokab_state *state, double dt, int64_t nsteps)
                       "timestep_forward_euler: this mesh has halo entities; domain-decomposed runs step with "
                       "mokab_timestep_forward_euler_decomposed (or mokab_forward_euler_stage + the halo exchange)");
         state->ctx->bind();
+        MOKAB_REQUIRE(!state->d->taping || state->K == 1, "timestep_forward_euler: the multi-level reverse mode is RungeKutta4");
         if (state->d->taping) {             // also a call with nsteps = 0: ssh is an input of its own for this stepper's seed
             MOKAB_REQUIRE(state->d->tapeKind != 1, "timestep_forward_euler: the tape already holds RungeKutta4 steps");
             // checked before the first step runs: a call either records all of its steps or leaves the state untouched
@@ -2481,7 +2594,7 @@ int mokab_tape_begin(mokab_state *state, int64_t max_steps)
     return guarded([&] {
         MOKAB_REQUIRE(state, "tape_begin: state is NULL");
         MOKAB_REQUIRE(max_steps >= 0, "tape_begin: max_steps must be >= 0");
-        MOKAB_REQUIRE(state->K == 1, "tape_begin: single-level states only (nVertLevels == 1)");
+        MOKAB_REQUIRE(state->K == 1 || !state->dec.ready, "tape_begin: multi-level states have no reverse mode on decomposed meshes");
         state->ctx->bind();
         if (state->dtype == MOKAB_F64) tape_begin<double>(state, max_steps); else tape_begin<float>(state, max_steps);
     });
@@ -2499,7 +2612,7 @@ int mokab_adjoint_seed(mokab_state *state, int which)
 {
     return guarded([&] {
         MOKAB_REQUIRE(state, "adjoint_seed: state is NULL");
-        MOKAB_REQUIRE(state->K == 1, "adjoint_seed: single-level states only (nVertLevels == 1)");
+        MOKAB_REQUIRE(state->K == 1 || !state->dec.ready, "adjoint_seed: multi-level states have no reverse mode on decomposed meshes");
         state->ctx->bind();
         if (state->dtype == MOKAB_F64) adjoint_seed<double>(state, which); else adjoint_seed<float>(state, which);
     });

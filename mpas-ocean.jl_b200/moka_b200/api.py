@@ -391,8 +391,8 @@ class ShadowPrognosticVars:
 
     def __init__(self, prog: PrognosticVars):
         self.dev = prog.dev
-        for f, n in ((L.D_SSH, prog.mesh.nCells), (L.D_NORMAL_VELOCITY, prog.mesh.nEdges), (L.D_LAYER_THICKNESS, prog.mesh.nCells)):
-            self.dev.set(f, np.zeros(n, self.dev.np_dtype))
+        for f in (L.D_SSH, L.D_NORMAL_VELOCITY, L.D_LAYER_THICKNESS):
+            self.dev.set(f, np.zeros(self.dev._len(f), self.dev.np_dtype))     # (multi-level states: (n, nVertLevels) like the state itself)
 
     ssh = property(lambda s: s.dev.get(L.D_SSH), lambda s, v: s.dev.set(L.D_SSH, v))
     normalVelocity = property(lambda s: s.dev.get(L.D_NORMAL_VELOCITY), lambda s, v: s.dev.set(L.D_NORMAL_VELOCITY, v))

@@ -140,6 +140,64 @@ def finite_difference(m, u0, h0, dt, nsteps, kind, k, eps=1e-8):
     return (jp - jm) / dist
 
 
+# ---- multi-level states (nVertLevels = K; arrays of shape (K, n), project-defined semantics: moka_oracle.ssh_from_thickness) ----
+def tendencies_vjp_levels(m, u, h, ku_bar, kh_bar):
+    """(ubar, hbar) = (dF/d(u, h))^T (ku_bar, kh_bar) for the K-level tendencies (moka_oracle.tendencies_consistent on (K, n)
+    arrays): Coriolis and thickness flux act level by level, the pressure gradient -g/dc (ssh2 - ssh1) with
+    ssh = sum_k h_k - restingThicknessSum is ONE term shared by every level of the column -- so its adjoint, formed from
+    the level sum of ku_bar, goes to every level of h alike."""
+    K = u.shape[0]
+    c1 = m["cellsOnEdge"][:, 0] - 1
+    c2 = m["cellsOnEdge"][:, 1] - 1
+    ubar, hbar = np.zeros_like(u), np.zeros_like(h)
+    g_dc = O.GRAVITY * (1.0 / m["dcEdge"])
+    for k in range(K):
+        ub, hb = tendencies_vjp(m, u[k], h[k], ku_bar[k], kh_bar[k])
+        gk = g_dc * ku_bar[k]                                            # take this level's own pressure adjoint out again ...
+        np.add.at(hb, c2, gk)
+        np.add.at(hb, c1, -gk)
+        ubar[k], hbar[k] = ub, hb
+    gsum = g_dc * ku_bar.sum(axis=0)                                     # ... and give every level the column's
+    p = np.zeros(m["nCells"])
+    np.add.at(p, c2, -gsum)
+    np.add.at(p, c1, gsum)
+    return ubar, hbar + p[None, :]
+
+
+def rk4_step_vjp_levels(m, u, h, dt, lam_u, lam_h):
+    a = [dt / 2.0, dt / 2.0, dt]
+    b = [dt / 6.0, dt / 3.0, dt / 3.0, dt / 6.0]
+    ys = rk4_stage_states(m, u, h, dt)                                   # (tendencies_consistent broadcasts over the level axis)
+    out_u, out_h = lam_u.copy(), lam_h.copy()
+    kbu, kbh = b[3] * lam_u, b[3] * lam_h
+    for s in (3, 2, 1, 0):
+        ybu, ybh = tendencies_vjp_levels(m, ys[s][0], ys[s][1], kbu, kbh)
+        out_u, out_h = out_u + ybu, out_h + ybh
+        if s > 0:
+            kbu, kbh = b[s - 1] * lam_u + a[s - 1] * ybu, b[s - 1] * lam_h + a[s - 1] * ybh
+    return out_u, out_h
+
+
+def run_forward_levels(m, u, h, dt, nsteps):
+    traj = [(u, h)]
+    for _ in range(nsteps):
+        prog = O.new_state(m, O.ssh_from_thickness(m, traj[-1][1]), traj[-1][0], traj[-1][1])
+        O.timestep_rk4(m, prog, dt)
+        traj.append((prog["normalVelocity"][-1], prog["layerThickness"][-1]))
+    return traj
+
+
+def gradient_sum_ssh2_levels(m, u0, h0, dt, nsteps):
+    """(J, dJ/du0, dJ/dh0) of J = sum ssh_N^2, ssh = sum_k h_k - restingThicknessSum, for (K, n) arrays."""
+    traj = run_forward_levels(m, u0, h0, dt, nsteps)
+    sshN = O.ssh_from_thickness(m, traj[-1][1])
+    lam_u = np.zeros_like(u0)
+    lam_h = np.repeat((2.0 * sshN)[None, :], u0.shape[0], axis=0)
+    for n in range(nsteps - 1, -1, -1):
+        lam_u, lam_h = rk4_step_vjp_levels(m, traj[n][0], traj[n][1], dt, lam_u, lam_h)
+    return float(np.sum(sshN * sshN)), lam_u, lam_h
+
+
 # ---- ForwardEuler: the stepper the reference actually differentiates (test_Enzyme_end2end.jl:78-96) ---------------
 # One step of moka_oracle.timestep_forward_euler maps (u, h, ssh, hE) -> (u', h', ssh', hE'), hE = Diag.layerThicknessEdge:
 #   flux = u * hE                       (the LAGGED hEdge: diagnostic_compute! forms the flux before it refreshes hEdge,

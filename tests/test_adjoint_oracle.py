@@ -198,3 +198,53 @@ def test_committed_forward_euler_adjoint_fixture_is_reproduced_by_the_oracle():
     assert np.array_equal(gs, g["d_ssh"]) and np.array_equal(ge, g["d_layerThicknessEdge"])
     k = meta["fd_index"]
     assert abs(gh[k] - float(g["fd_layerThickness"])) < 1e-4 and abs(gu[k] - float(g["fd_normalVelocity"])) < 1e-2
+
+
+def _levels_case(nx, K):
+    m = dict(hex_mesh(nx))
+    ssh, u, h = mb.inertialGravityWave(m).initial_state()
+    frac = np.random.default_rng(K).uniform(0.5, 1.5, K)
+    frac /= frac.sum()
+    rest = np.outer(np.full(m["nCells"], 1000.0), frac)
+    m["restingThickness"], m["nVertLevels"] = rest, K
+    uk = np.ascontiguousarray(np.outer(u, 1.0 + 0.1 * np.arange(K)).T)
+    hk = np.ascontiguousarray((rest + np.outer(ssh, frac)).T)
+    return m, uk, hk, mb.cfl_dt(m["dc"])
+
+
+def test_multilevel_vjp_is_the_transpose_of_the_multilevel_tendencies():
+    """Pins the level-axis adjoint oracle: <J v, w> = <v, J^T w> with J v from central differences of the (quadratic) K-level
+    tendencies, whose single pressure gradient per column couples the levels."""
+    m, u, h, dt = _levels_case(12, 3)
+    rng = np.random.default_rng(2)
+    du, dh = rng.standard_normal(u.shape), rng.standard_normal(h.shape)
+    wu, wh = rng.standard_normal(u.shape), rng.standard_normal(h.shape)
+    e = 1e-3
+    fp, fm = O.tendencies_consistent(m, u + e * du, h + e * dh), O.tendencies_consistent(m, u - e * du, h - e * dh)
+    tu, th = (fp[0] - fm[0]) / (2 * e), (fp[1] - fm[1]) / (2 * e)
+    ub, hb = A.tendencies_vjp_levels(m, u, h, wu, wh)
+    lhs, rhs = np.sum(tu * wu) + np.sum(th * wh), np.sum(du * ub) + np.sum(dh * hb)
+    assert abs(lhs - rhs) <= 1e-9 * max(abs(lhs), abs(rhs))
+
+
+def test_multilevel_gradient_matches_finite_differences():
+    m, u, h, dt = _levels_case(12, 3)
+    nsteps = 4
+    J, gu, gh = A.gradient_sum_ssh2_levels(m, u, h, dt, nsteps)
+
+    def objective(uu, hh):
+        return float(np.sum(O.ssh_from_thickness(m, A.run_forward_levels(m, uu, hh, dt, nsteps)[-1][1]) ** 2))
+
+    assert abs(J - objective(u, h)) <= 1e-12 * J
+    for k, i in ((0, 5), (2, 77), (1, 100)):
+        for kind, g, eps in (("h", gh, 1e-6), ("u", gu, 1e-4)):
+            up, hp, um, hm = u.copy(), h.copy(), u.copy(), h.copy()
+            (hp if kind == "h" else up)[k, i] += eps
+            (hm if kind == "h" else um)[k, i] -= eps
+            fd = (objective(up, hp) - objective(um, hm)) / (2 * eps)
+            assert abs(g[k, i] - fd) <= 1e-5 * abs(g[k, i]) + (1e-6 if kind == "h" else 1e-4), (kind, k, i, g[k, i], fd)
+    # with one level it is the single-level oracle
+    m1, u1, h1, _ = _levels_case(12, 1)
+    J1, gu1, gh1 = A.gradient_sum_ssh2_levels(m1, u1, h1, dt, 3)
+    Js, gus, ghs = A.gradient_sum_ssh2(m1, u1[0], h1[0], dt, 3)
+    assert abs(J1 - Js) <= 1e-13 * Js and np.allclose(gu1[0], gus, rtol=1e-12, atol=0) and np.allclose(gh1[0], ghs, rtol=1e-12, atol=1e-18)

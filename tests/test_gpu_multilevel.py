@@ -113,7 +113,35 @@ def test_multilevel_states_refuse_what_is_single_level_only(backend):
     m, ssh, uk, hk = _column_case(16, 2)
     p = mb.PrognosticVars(ssh, uk, hk, 2, mb.Mesh(m, backend))
     from moka_b200 import _lib as L
+    L.check(L.lib().mokab_tape_begin(p.dev.handle, 1))                 # the multi-level reverse mode is RungeKutta4:
+    with pytest.raises(mb.MokaError, match="multi-level reverse mode is RungeKutta4"):
+        mb.ocn_timestep(mb.cfl_dt(m["dc"]), p, None, None, None, mb.ForwardEuler)          # ... ForwardEuler steps cannot be recorded
     with pytest.raises(mb.MokaError, match="single-level"):
-        L.check(L.lib().mokab_tape_begin(p.dev.handle, 1))             # the reverse mode records single-level states
+        L.check(L.lib().mokab_adjoint_forward_euler(p.dev.handle))
     with pytest.raises(mb.MokaError, match="Float64"):
         mb.PrognosticVars(ssh.astype(np.float32), uk.astype(np.float32), hk.astype(np.float32), 2, mb.Mesh(m, backend))
+
+
+@pytest.mark.parametrize("K,nx", [(3, 24), (10, 16), (1, 16)])
+def test_multilevel_reverse_mode_matches_the_level_axis_adjoint_oracle(backend, K, nx):
+    """`autodiff(Reverse, ocn_run_loop, ...)` of J = sum ssh^2 on a K-level state (RungeKutta4): the forward recompute is the
+    column kernel, every adjoint stage the single-level gather kernel per level with the pressure term taken from the level
+    sum of kbar_u (csrc/moka_b200.cu: adjoint_step_ml) -- against oracle/adjoint_oracle.py: gradient_sum_ssh2_levels, which is
+    pinned by finite differences of the multi-level oracle (tests/test_adjoint_oracle.py)."""
+    import adjoint_oracle as AO
+    m, ssh, uk, hk = _column_case(nx, K, seed=5)
+    dt = mb.cfl_dt(m["dc"])
+    nsteps = 4
+    mesh = mb.Mesh(m, backend)
+    prog = mb.PrognosticVars(ssh, uk if K > 1 else uk[:, 0], hk if K > 1 else hk[:, 0], 2, mesh)
+    d_prog = mb.ocn_init_shadows(prog)
+    J = mb.autodiff_reverse_run_loop(dt, prog, d_prog, None, None, None, mb.RungeKutta4, nsteps)
+    Jo, gu, gh = AO.gradient_sum_ssh2_levels(m, np.ascontiguousarray(uk.T), np.ascontiguousarray(hk.T), dt, nsteps)
+    assert abs(J - Jo) <= 1e-12 * Jo
+    du = np.asarray(d_prog.normalVelocity).reshape(m["nEdges"], K)
+    dh = np.asarray(d_prog.layerThickness).reshape(m["nCells"], K)
+    assert rel_l2(du.T, gu) <= 1e-12 and rel_l2(dh.T, gh) <= 1e-12
+    # the forward run under the tape is the ordinary run, bit for bit
+    ref = mb.PrognosticVars(ssh, uk if K > 1 else uk[:, 0], hk if K > 1 else hk[:, 0], 2, mesh)
+    mb.ocn_timestep(dt, ref, None, None, None, mb.RungeKutta4, nsteps=nsteps)
+    assert np.array_equal(prog.normalVelocity, ref.normalVelocity) and np.array_equal(prog.ssh, ref.ssh)
