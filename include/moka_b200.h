@@ -171,8 +171,8 @@ int  mokab_state_create(mokab_ctx *ctx, const mokab_mesh *mesh, int dtype, mokab
  * captured graphs) and mokab_reduce_decomposed; the reverse mode of RungeKutta4 on undecomposed meshes (mokab_tape_begin ...
  * mokab_adjoint_rk4: the forward recompute is the column kernel, every adjoint stage the single-level gather kernel per level
  * with the pressure term -- one gradient per column -- taken from the level sum of kbar_u; MOKAB_D_* fields are (nVertLevels, n)
- * like the state's).  Not supported: the ForwardEuler reverse mode, the reverse mode on decomposed meshes, the staged entry
- * points, ForwardEuler on decomposed meshes. */
+ * like the state's), on decomposed meshes too (one K + 1 plane message per halo copy of the sweep; checked with emulated ranks
+ * only).  Not supported: the ForwardEuler reverse mode, the staged entry points, ForwardEuler on decomposed meshes. */
 int  mokab_state_create_levels(mokab_ctx *ctx, const mokab_mesh *mesh, int dtype, int nVertLevels, mokab_state **out);
 int  mokab_state_levels(const mokab_state *state, int *nVertLevels);
 int  mokab_state_destroy(mokab_state *state);

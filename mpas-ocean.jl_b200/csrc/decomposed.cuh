@@ -229,10 +229,7 @@ static void decomp_prepare(mokab_state *st)
 {
     mokab_mesh *m = const_cast<mokab_mesh *>(st->mesh);
     if (st->K > 1) {
-        mokab_state::Decomp &D = st->dec;
-        const size_t ns = std::max<size_t>(m->haloSend.n, 1) * (size_t)(st->K + 1) * 8, nr = std::max<size_t>(m->haloRecv.n, 1) * (size_t)(st->K + 1) * 8;
-        if (D.sendBufML.n < ns) { D.sendBufML.alloc(ns); D.sendBufML.zero(st->ctx->stream); }
-        if (D.recvBufML.n < nr) { D.recvBufML.alloc(nr); D.recvBufML.zero(st->ctx->stream); }
+        ensure_level_buffers(st);
         // the stage kernels gather ssh of the state they read: make ssh[cur] what the current layerThickness implies, halo copies
         // included (every later step's ssh is written by the stage that produces its layerThickness, and exchanged with it)
         update_ssh(st, st->d->h[st->cur].p, st->d->ssh[st->cur].p);
@@ -255,9 +252,9 @@ static void decomp_tape_record(mokab_state *st, double dt, int kind)
         if constexpr (sizeof(R) == 8) fe_tape_record(st, dt, t->u[st->cur].p, t->hE[st->cur].p);
         return;
     }
-    const size_t k = t->tapeDt.size();
-    MOKAB_CUDA(cudaMemcpyAsync(t->tapeU.p + k * m->nE, t->u[st->cur].p, m->nE * sizeof(R), cudaMemcpyDeviceToDevice, s));
-    MOKAB_CUDA(cudaMemcpyAsync(t->tapeH.p + k * m->nC, t->h[st->cur].p, m->nC * sizeof(R), cudaMemcpyDeviceToDevice, s));
+    const size_t k = t->tapeDt.size(), K = (size_t)st->K;
+    MOKAB_CUDA(cudaMemcpyAsync(t->tapeU.p + k * K * m->nE, t->u[st->cur].p, K * m->nE * sizeof(R), cudaMemcpyDeviceToDevice, s));
+    MOKAB_CUDA(cudaMemcpyAsync(t->tapeH.p + k * K * m->nC, t->h[st->cur].p, K * m->nC * sizeof(R), cudaMemcpyDeviceToDevice, s));
     t->tapeDt.push_back(dt);
 }
 
@@ -271,7 +268,7 @@ static void decomp_run(mokab_state *st, double dt, int64_t nsteps, int kind)
         MOKAB_REQUIRE((int64_t)t->tapeDt.size() + nsteps <= t->tapeCap, "timestep_*_decomposed: the tape is full (mokab_tape_begin max_steps)");
         MOKAB_REQUIRE(t->tapeKind == 0 || t->tapeKind == kind + 1, "timestep_*_decomposed: the tape already holds steps of the other stepper");
         t->tapeKind = kind + 1;             // (also a call with nsteps = 0: the seed then follows this stepper's state definition)
-        if (kind == 0 && nsteps > 0 && t->tapeH.n < (size_t)t->tapeCap * st->mesh->nC) t->tapeH.alloc((size_t)t->tapeCap * st->mesh->nC);
+        if (kind == 0 && nsteps > 0 && t->tapeH.n < (size_t)t->tapeCap * (size_t)st->K * st->mesh->nC) t->tapeH.alloc((size_t)t->tapeCap * (size_t)st->K * st->mesh->nC);
     }
     if (nsteps <= 0) return;
     decomp_prepare<R>(st);
@@ -599,8 +596,7 @@ int mokab_timestep_rk4_decomposed(mokab_state *state, double dt, int64_t nsteps)
     return guarded([&] {
         MOKAB_REQUIRE(state && state->dec.ready, "timestep_rk4_decomposed: call mokab_decomp_setup first");
         MOKAB_REQUIRE(nsteps >= 0, "timestep_rk4_decomposed: nsteps must be >= 0");
-        MOKAB_REQUIRE(state->K == 1 || (state->dtype == MOKAB_F64 && !state->d->taping),
-                      "timestep_rk4_decomposed: multi-level states are Float64 and have no reverse mode");
+        MOKAB_REQUIRE(state->K == 1 || state->dtype == MOKAB_F64, "timestep_rk4_decomposed: multi-level states are Float64");
         state->ctx->bind();
         leave_forward_euler(state);
         if (state->dtype == MOKAB_F64) { decomp_run<double>(state, dt, nsteps, 0); if (nsteps) refresh_ssh<double>(state); }

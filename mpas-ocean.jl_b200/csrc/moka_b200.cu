@@ -1231,6 +1231,15 @@ static void refresh_ssh(mokab_state *st, cudaStream_t stream = nullptr)
 
 // Multi-level states on a decomposed mesh: one packed exchange per stage of K + 1 planes (k_halo_pack_ml), on the context's
 // stream (the multi-level path has no interior / boundary split; the buffers are sized by decomp_prepare, outside any capture).
+static void ensure_level_buffers(mokab_state *st)          // (allocates: never inside a stream capture)
+{
+    mokab_state::Decomp &D = st->dec;
+    const mokab_mesh *m = st->mesh;
+    const size_t ns = std::max<size_t>(m->haloSend.n, 1) * (size_t)(st->K + 1) * 8, nr = std::max<size_t>(m->haloRecv.n, 1) * (size_t)(st->K + 1) * 8;
+    if (D.sendBufML.n < ns) { D.sendBufML.alloc(ns); D.sendBufML.zero(st->ctx->stream); }
+    if (D.recvBufML.n < nr) { D.recvBufML.alloc(nr); D.recvBufML.zero(st->ctx->stream); }
+}
+
 static void halo_exchange_levels(mokab_state *st, double *u, double *h, double *ssh)
 {
     mokab_state::Decomp &D = st->dec;
@@ -1603,6 +1612,10 @@ static void adjoint_step_ml(mokab_state *st, int64_t k)
     const double b[4] = {dt / 6.0, dt / 3.0, dt / 3.0, dt / 6.0};
     const double *u0 = t->tapeU.p + (size_t)k * K * nE, *h0 = t->tapeH.p + (size_t)k * K * nC;
     update_ssh(st, h0, t->yS[0].p);                                    // ssh of y_1 = the taped state
+    // Decomposed mesh: plain halo copies of every level of what a stage consumes, as in the single-level sweep -- one K + 1 plane
+    // message per exchange (the free-surface plane is only meaningful for the stage states; for the adjoint pairs it carries a
+    // scratch array).  kuP is formed locally from the exchanged kbar_u, halo edges included.
+    const bool decomposed = st->dec.ready;
     fused::StageArgsML A;
     A.nE = (int)nE; A.nC = (int)nC; A.K = K; A.nCown = (int)m->nCo;
     A.ce = m->ce.p; A.eoe = m->eoeF.p; A.eoc = m->eocF.p; A.nEoE = m->nEoE.p; A.nEoC = m->nEoC.p; A.blkEdgeStart = m->blkEdgeStart.p;
@@ -1614,6 +1627,7 @@ static void adjoint_step_ml(mokab_state *st, int64_t k)
         A.uOld = s == 1 ? u0 : t->yU[s - 2].p; A.hOld = s == 1 ? h0 : t->yH[s - 2].p; A.sshOld = t->yS[s - 1].p;
         A.uOut = t->yU[s - 1].p; A.hOut = t->yH[s - 1].p; A.sshOut = t->yS[s].p;
         if (s == 1) launch_stage_ml<1>(ctx, m, A); else launch_stage_ml<2>(ctx, m, A);
+        if (decomposed) halo_exchange_levels(st, t->yU[s - 1].p, t->yH[s - 1].p, t->yS[s].p);   // y_{s+1} and its free surface on the halo entities
     }
     const int p = t->lamCur;
     const bool hex = m->S2T == 10 && m->S == 6, hept = m->S2T == 12 && m->S == 7;
@@ -1649,6 +1663,10 @@ static void adjoint_step_ml(mokab_state *st, int64_t k)
 #undef MOKAB_ADJ_ML_LAUNCH
             MOKAB_CUDA(cudaGetLastError());
             ctx->launches++;
+        }
+        if (decomposed) {
+            if (s > 1) halo_exchange_levels(st, t->kbU[(s - 1) & 1].p, t->kbH[(s - 1) & 1].p, t->yS[0].p);
+            else halo_exchange_levels(st, t->lamU[1 - p].p, t->lamH[1 - p].p, t->yS[0].p);
         }
     }
     t->lamCur = 1 - p;
@@ -1704,8 +1722,9 @@ static void adjoint_run(mokab_state *st)
     t->tapeKind = 0;
     if constexpr (sizeof(R) == 8) {
         if (st->K > 1) {
-            MOKAB_REQUIRE(!st->dec.ready, "adjoint_rk4: multi-level states have no reverse mode on decomposed meshes");
             LAUNCH(ctx, adjoint::k_fold_dssh_levels<R>, nblk(m->nC), 256, m->nC, st->K, t->dSsh.p, t->lamH[t->lamCur].p);
+            if (st->dec.ready) ensure_level_buffers(st);
+            if (st->dec.ready) halo_exchange_levels(st, t->lamU[t->lamCur].p, t->lamH[t->lamCur].p, t->yS[0].p);   // the owners' seeds on the halo copies
             for (int64_t k = (int64_t)t->tapeDt.size() - 1; k >= 0; --k) adjoint_step_ml(st, k);
             t->tapeDt.clear();
             return;
@@ -2594,7 +2613,6 @@ int mokab_tape_begin(mokab_state *state, int64_t max_steps)
     return guarded([&] {
         MOKAB_REQUIRE(state, "tape_begin: state is NULL");
         MOKAB_REQUIRE(max_steps >= 0, "tape_begin: max_steps must be >= 0");
-        MOKAB_REQUIRE(state->K == 1 || !state->dec.ready, "tape_begin: multi-level states have no reverse mode on decomposed meshes");
         state->ctx->bind();
         if (state->dtype == MOKAB_F64) tape_begin<double>(state, max_steps); else tape_begin<float>(state, max_steps);
     });
@@ -2612,7 +2630,6 @@ int mokab_adjoint_seed(mokab_state *state, int which)
 {
     return guarded([&] {
         MOKAB_REQUIRE(state, "adjoint_seed: state is NULL");
-        MOKAB_REQUIRE(state->K == 1 || !state->dec.ready, "adjoint_seed: multi-level states have no reverse mode on decomposed meshes");
         state->ctx->bind();
         if (state->dtype == MOKAB_F64) adjoint_seed<double>(state, which); else adjoint_seed<float>(state, which);
     });

@@ -268,9 +268,11 @@ class DecomposedModel:
 
     def gradient(self):
         """(d_normalVelocity on the owned edges, d_layerThickness on the owned cells) after `reverse_run_loop`."""
-        gu = np.asarray(self.prog.dev.get(L.D_NORMAL_VELOCITY), np.float64)[:self.loc["nEdgesOwned"]]
-        gh = np.asarray(self.prog.dev.get(L.D_LAYER_THICKNESS), np.float64)[:self.loc["nCellsOwned"]]
-        return gu, gh
+        gu = np.asarray(self.prog.dev.get(L.D_NORMAL_VELOCITY), np.float64)
+        gh = np.asarray(self.prog.dev.get(L.D_LAYER_THICKNESS), np.float64)
+        if gu.size != self.loc["nEdges"]:                         # multi-level states: (local entities, nVertLevels)
+            gu, gh = gu.reshape(self.loc["nEdges"], -1), gh.reshape(self.loc["nCells"], -1)
+        return gu[:self.loc["nEdgesOwned"]], gh[:self.loc["nCellsOwned"]]
 
     def gradient_ssh(self):
         """d_ssh on the owned cells: ForwardEuler reads the initial ssh array as an input of its own (first step's pressure gradient)."""

@@ -83,6 +83,34 @@ def main():
                 Jo, ou, oh = AO.gradient_sum_ssh2(m, state[1], state[2], dt, 6)
             rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))
             errs.append((("reverse mode", graph, halo, stepper), (abs(J - Jo) / Jo, rel(gu, ou), rel(gh, oh)), 0.0, "n/a"))
+    # multi-level states: forward (bit for bit the numpy oracle with a level axis) and the reverse mode (level-axis adjoint oracle)
+    if not os.environ.get("MOKAB_CHECK_HALO"):
+        import moka_oracle as O
+        K = 3
+        mk = dict(m)
+        frac = np.random.default_rng(K).uniform(0.5, 1.5, K)
+        frac /= frac.sum()
+        rest = np.outer(state[2] - state[0], frac)
+        hk, uk = rest + np.outer(state[0], frac), np.outer(state[1], 1.0 + 0.1 * np.arange(K))
+        mk["restingThickness"], mk["nVertLevels"] = rest, K
+        lock = partition.decompose(mk, world)[rank]
+        model = multi_gpu.DecomposedModel(lock, multi_gpu.local_state(lock, state[0], uk, hk), backend, local, graph=True, runtime=rt, comm=comm)
+        J = model.reverse_run_loop(dt, 4)
+        model.finish()
+        no, ne = lock["nCellsOwned"], lock["nEdgesOwned"]
+        fu, gu_o, gh_o = np.array(model.owned("normalVelocity")), *model.gradient()
+        allu, gu, gh = (np.zeros((m["nEdges"], K)), np.zeros((m["nEdges"], K)), np.zeros((m["nCells"], K)))
+        allu[lock["edgesGlobal"][:ne]], gu[lock["edgesGlobal"][:ne]], gh[lock["cellsGlobal"][:no]] = fu, gu_o, gh_o
+        allu, gu, gh = (comm.allreduce(a.ravel()).reshape(a.shape) for a in (allu, gu, gh))
+        model.close()
+        del model
+        if rank == 0:
+            import adjoint_oracle as AO
+            OC.sign_index_fields(mk)
+            Jo, ou, oh = AO.gradient_sum_ssh2_levels(mk, np.ascontiguousarray(uk.T), np.ascontiguousarray(hk.T), dt, 4)
+            fwd = AO.run_forward_levels(mk, np.ascontiguousarray(uk.T), np.ascontiguousarray(hk.T), dt, 4)[-1][0]
+            rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))
+            errs.append((("multi-level reverse mode", True, "nccl", "RungeKutta4"), (abs(J - Jo) / Jo, rel(gu.T, ou), rel(gh.T, oh)), 0.0 if np.array_equal(allu.T, fwd) else 1.0, "n/a"))
     if rank == 0:
         print(errs)
         ok = all(max(e) <= 1e-12 and dm <= 1e-13 for _, e, dm, _ in errs)

@@ -180,6 +180,40 @@ def run_levels(nx, nparts, K, step_calls, policy, seed, graph, halo="nccl"):
     return ok, outs[0][1]
 
 
+def run_adjoint_levels(nx, nparts, K, nsteps, policy, seed, graph, halo="nccl"):
+    """The reverse mode of a K-level state on the decomposed mesh against the level-axis adjoint oracle on the undecomposed one."""
+    import adjoint_oracle as AO
+    simcuda.set_policy(policy, seed)
+    m = dict(mb.periodic_hex(nx, nx, 1.0e7 / nx, with_dual=False))
+    OC.sign_index_fields(m)
+    ssh, u, h = mb.inertialGravityWave(m).initial_state()
+    frac = np.random.default_rng(K).uniform(0.5, 1.5, K)
+    frac /= frac.sum()
+    rest = np.outer(np.full(m["nCells"], 1000.0), frac)
+    hk, uk = rest + np.outer(ssh, frac), np.outer(u, 1.0 + 0.1 * np.arange(K))
+    m["restingThickness"], m["nVertLevels"] = rest, K
+    dt = mb.cfl_dt(m["dc"])
+    locs = partition.decompose(m, nparts)
+
+    def body(r, comm):
+        model = multi_gpu.DecomposedModel(locs[r], multi_gpu.local_state(locs[r], ssh, uk, hk), mb.B200(0), 0, graph=graph,
+                                          runtime=simcuda.SimRuntime(comm, r), halo=halo)
+        J = model.reverse_run_loop(dt, nsteps)
+        model.finish()
+        gu, gh = model.gradient()
+        model.close()
+        return J, np.array(gu), np.array(gh)
+
+    outs = simcuda.run_ranks(nparts, body)
+    gu, gh = np.full((m["nEdges"], K), np.nan), np.full((m["nCells"], K), np.nan)
+    for loc, (_, u_, h_) in zip(locs, outs):
+        gu[loc["edgesGlobal"][:loc["nEdgesOwned"]]] = u_
+        gh[loc["cellsGlobal"][:loc["nCellsOwned"]]] = h_
+    Jo, ou, oh = AO.gradient_sum_ssh2_levels(m, np.ascontiguousarray(uk.T), np.ascontiguousarray(hk.T), dt, nsteps)
+    eu, eh = np.linalg.norm(gu.T - ou) / max(np.linalg.norm(ou), 1e-300), np.linalg.norm(gh.T - oh) / max(np.linalg.norm(oh), 1e-300)
+    return all(abs(o[0] - Jo) <= 1e-12 * Jo for o in outs) and eu <= 1e-12 and eh <= 1e-12, (eu, eh)
+
+
 def run_e2e(kind, nx, nparts, iters, policy, seed, halo):
     """bench.py's end-to-end leg at N > 1 (multi_gpu.bench_main.e2e_steps): every iteration uploads this rank's (u, h) from
     page-locked memory through the pipelined transfers, takes ONE step, refreshes ssh and downloads it -- copy streams, the
@@ -421,6 +455,13 @@ def main():
             bad += not ok
             print(f"igw{nx} ranks={P} nVertLevels={K} steps={calls} {halo} {policy} {'graph [' + status + ']' if graph else 'stream'}: "
                   f"{'OK' if ok else 'MISMATCH'} {time.time() - t0:.1f}s", flush=True)
+    for nx, P, K, nsteps, graph, halo in [(48, 4, 3, 3, True, "nccl")] + ([(32, 3, 5, 2, False, "p2p_ll"), (96, 8, 2, 2, True, "p2p")] if args.cases != "suite" else []):
+        for policy in extra_policies:
+            t0 = time.time()
+            ok, (eu, eh) = run_adjoint_levels(nx, P, K, nsteps, policy, 8, graph, halo)
+            bad += not ok
+            print(f"igw{nx} ranks={P} nVertLevels={K} reverse mode, {nsteps} steps, {halo} {policy} {'graph' if graph else 'stream'}: "
+                  f"{'OK' if ok else 'MISMATCH'} (rel-L2 {eu:.1e} / {eh:.1e} against the level-axis adjoint oracle) {time.time() - t0:.1f}s", flush=True)
     for halo in (args.halo.split(",")[:1] if args.cases == "suite" else args.halo.split(",")):
         t0 = time.time()
         ok = run_driver(3, args.policies.split(",")[0], halo)
