@@ -84,8 +84,8 @@ def main():
             rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))
             errs.append((("reverse mode", graph, halo, stepper), (abs(J - Jo) / Jo, rel(gu, ou), rel(gh, oh)), 0.0, "n/a"))
     # multi-level states: forward (bit for bit the numpy oracle with a level axis) and the reverse mode (level-axis adjoint oracle)
-    if not os.environ.get("MOKAB_CHECK_HALO"):
-        import moka_oracle as O
+    # (opt-in until its first hardware run: MOKAB_CHECK_LEVELS=1; with emulated ranks: tests/sim/check_decomposed.py run_levels / run_adjoint_levels)
+    if os.environ.get("MOKAB_CHECK_LEVELS") and not os.environ.get("MOKAB_CHECK_HALO"):
         K = 3
         mk = dict(m)
         frac = np.random.default_rng(K).uniform(0.5, 1.5, K)
